@@ -1,0 +1,228 @@
+/*
+ * lancet_gpu_realign.h — C ABI of the B200 read→haplotype realignment path.
+ *
+ * This is the drop-in boundary for the hot path of nygenome/Lancet2's
+ * `caller::Genotyper`.  The reference has no FFI layer; the seam is the C++
+ * member `Genotyper::Genotype(haps, reads, variant_set)`
+ * (reference: src/lancet/caller/genotyper.h:213-220, genotyper.cpp:224-235).
+ * One *group* below is the payload of exactly one `Genotype()` call (one graph
+ * component of one window): P haplotypes, R reads, V variants.  A *batch* is
+ * many groups, so that windows from many worker threads fill one GPU.
+ *
+ * What each entry point replaces in the reference:
+ *   lgr_create            Genotyper::Genotyper()            genotyper.cpp:89-191
+ *                         (mm_set_opt + the 10 option overrides, mm_tbuf_init)
+ *   lgr_genotype_batch    Genotyper::ResetData              genotyper.cpp:243-267
+ *                         + AlignToAllHaplotypes (mm_map)   genotyper.cpp:376-411
+ *                         + AssignReadToAlleles             genotyper.cpp:269-321
+ *                         + ScoreReadAtVariant              combined_scorer.cpp:60-108
+ *                         + ComputeLocalScore               local_scorer.cpp:166-279
+ *   lgr_hap_mid_occ       mm_mapopt_update (mid_occ latch)  genotyper.cpp:263-266
+ *   lgr_destroy           ~Genotyper (mm_idx_destroy, mm_tbuf_destroy)
+ *                                                           genotyper.h:226-250
+ * `Genotyper::AddToTable` (genotyper.cpp:423-456) stays on the host: it needs
+ * absl's per-process salted hash and string_view sample names; the adapter in
+ * lancet2_b200/host/ performs it from the lgr_assign records, in read order.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success and a negative LGR_E_* code on failure (no CPU fallback exists — a
+ * missing GPU is an error).  All buffers are caller-owned HOST memory unless a
+ * function name ends in `_dev`.  A context is bound to one GPU and may be used
+ * by one thread at a time; use one context per GPU/worker.
+ */
+#ifndef LANCET_GPU_REALIGN_H_
+#define LANCET_GPU_REALIGN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGR_ABI_VERSION 1
+
+/* error codes */
+#define LGR_OK 0
+#define LGR_E_ARG (-1)            /* bad argument / inconsistent batch      */
+#define LGR_E_CUDA (-2)           /* CUDA runtime failure (see lgr_last_error) */
+#define LGR_E_NO_DEVICE (-3)      /* no usable GPU                          */
+#define LGR_E_LIMIT (-4)          /* a sequence exceeds a compile-time cap  */
+#define LGR_E_CIGAR_OVERFLOW (-5) /* cigar overflow arena exhausted         */
+#define LGR_E_NOMEM (-6)
+
+/* compile-time caps of the device path (checked, never silently truncated) */
+#define LGR_MAX_READ_LEN 1024
+#define LGR_MAX_HAP_LEN 65535
+#define LGR_CIGAR_INLINE 8 /* u32 cigar ops stored inline per pair */
+
+/*
+ * Alignment / mapping parameters.  Defaults (lgr_default_params) are the
+ * reference's effective minimap2 option set: mm_set_opt(0) defaults plus the
+ * overrides in genotyper.cpp:109-190.
+ */
+typedef struct lgr_params {
+  int32_t k, w;                /* minimizer k-mer / window: 11, 5 (genotyper.cpp:189-190) */
+  int32_t a, b, q, e;          /* 1, 4, 12, 3 (scoring_constants.h:17-20)   */
+  int32_t sc_ambi;             /* 1 (minimap2 default)                      */
+  int32_t bw;                  /* 10000 (genotyper.cpp:140)                 */
+  int32_t zdrop;               /* 100000 (genotyper.cpp:131)                */
+  int32_t end_bonus;           /* 10000 (genotyper.cpp:181)                 */
+  int32_t max_gap;             /* 200 (genotyper.cpp:158)                   */
+  int32_t max_gap_ref;         /* 5000 (genotyper.cpp:159)                  */
+  int32_t max_chain_skip;      /* 25                                        */
+  int32_t max_chain_iter;      /* 5000                                      */
+  int32_t min_cnt;             /* 3                                         */
+  int32_t min_chain_score;     /* 40                                        */
+  int32_t min_dp_max;          /* 80 = 40 * a(default 2), never recomputed  */
+  int32_t mid_occ;             /* <=0: latch from first haplotype (mm_mapopt_update); else fixed */
+  int32_t min_mid_occ;         /* 10                                        */
+  int32_t max_mid_occ;         /* 1000000                                   */
+  int32_t max_max_occ;         /* 4095                                      */
+  int32_t occ_dist;            /* 500                                       */
+  int32_t best_n;              /* 1 (genotyper.cpp:110)                     */
+  int32_t seed;                /* 11                                        */
+  float mid_occ_frac;          /* 2e-4                                      */
+  float q_occ_frac;            /* 0.01                                      */
+  float chain_gap_scale;       /* 0.8                                       */
+  float chain_skip_scale;      /* 0.0                                       */
+  float mask_level;            /* 0.5                                       */
+  float pri_ratio;             /* 0.8                                       */
+  float max_clip_ratio;        /* 1.0                                       */
+  int32_t mask_len;            /* INT_MAX                                   */
+  int32_t cigar_arena_ops;     /* capacity (u32 ops) of the overflow cigar arena per batch */
+  int32_t reserved[7];
+} lgr_params;
+
+/*
+ * One batch of G groups.  Index spaces:
+ *   haplotypes 0..NH-1, group g owns [grp_hap_begin[g], grp_hap_begin[g+1]); its
+ *     first haplotype is the REF haplotype (genotyper.h REF_HAP_IDX = 0).
+ *   reads 0..NR-1, group g owns [grp_read_begin[g], grp_read_begin[g+1]), in
+ *     the reference's ReadCollector order (it is the evidence-append order).
+ *   variants 0..NV-1, group g owns [grp_var_begin[g], grp_var_begin[g+1]).
+ *   per-(variant,haplotype) bounds: variant v of group g with P_g haplotypes
+ *     owns var_start[var_hap_off[v] + h], h in [0,P_g)  (ExtractHapBounds,
+ *     genotyper.cpp:329-352): var_allele = -1 when haplotype h does not carry
+ *     the variant, 0 for the REF haplotype row, a+1 for ALT a.
+ * Sequences are the ASCII strings the reference passes (hap: std::string,
+ * genotyper.cpp:249; read: cbdg::Read::SeqPtr()); qualities are raw Phred
+ * bytes; read_name_hash is minimap2's __ac_X31_hash_string(qname), see
+ * lgr_x31_hash (mm_map mixes the read name into the hit-sort tie-break).
+ */
+typedef struct lgr_batch_in {
+  int32_t n_groups;
+  int32_t n_haps, n_reads, n_vars;
+  const int32_t* grp_hap_begin;  /* [G+1] */
+  const int32_t* grp_read_begin; /* [G+1] */
+  const int32_t* grp_var_begin;  /* [G+1] */
+  const int64_t* hap_off;        /* [NH+1] byte offsets into hap_bases  */
+  const uint8_t* hap_bases;      /* ASCII                               */
+  const int64_t* read_off;       /* [NR+1] byte offsets into read_bases/read_quals */
+  const uint8_t* read_bases;     /* ASCII                               */
+  const uint8_t* read_quals;     /* raw Phred                           */
+  const uint32_t* read_name_hash;/* [NR]                                */
+  const int64_t* var_hap_off;    /* [NV+1] offsets into var_* (P_g entries per variant) */
+  const int32_t* var_start;      /* mVarStart per (variant,hap)         */
+  const int32_t* var_len;        /* mVarLen   per (variant,hap)         */
+  const int8_t* var_allele;      /* allele index or -1                  */
+  const int32_t* grp_mid_occ;    /* [G] or NULL: per-group mid_occ (>0) overriding params.mid_occ */
+} lgr_batch_in;
+
+/* Result of mm_map(read, hap)[0] as consumed by AlignToAllHaplotypes
+ * (genotyper.cpp:396-404), one per (read, haplotype-of-its-group) pair.
+ * Pair index of read r (global) and local haplotype h: pair_off[r] + h, where
+ * pair_off[r] = sum over earlier reads of their group's P (lgr_pair_offsets). */
+typedef struct lgr_aln {
+  int32_t valid;     /* 0: mm_map returned no hit → haplotype skipped (genotyper.cpp:390-393) */
+  int32_t score;     /* mm_reg1_t::score   → Mm2AlnResult::mScore    */
+  int32_t rs, re;    /* mm_reg1_t::rs/re   → mRefStart/mRefEnd       */
+  int32_t qs, qe;    /* mm_reg1_t::qs/qe   → leading/trailing S in BuildCigar (genotyper.cpp:45-69) */
+  int32_t rev;       /* mm_reg1_t::rev (never inspected by the reference) */
+  int32_t dp_score;  /* mm_extra_t::dp_score */
+  int32_t dp_max;    /* mm_extra_t::dp_max   */
+  int32_t mlen, blen;/* mm_reg1_t::mlen/blen */
+  int32_t n_ambi;    /* mm_extra_t::n_ambi   */
+  int32_t nm;        /* hts::ComputeEditDistance(cigar, read, hap[rs,re)) (cigar_utils.h:48-94) */
+  int32_t n_cigar;   /* core ops (without the S bookends)            */
+  int32_t cigar_off; /* <0: ops are inline at cigar_inline[pair*LGR_CIGAR_INLINE]; else offset in cigar_arena */
+  int32_t n_regs;    /* number of hits mm_map would return            */
+} lgr_aln;
+
+/* ReadAlleleAssignment (genotyper.h:152-171), one per (read, variant-of-its-
+ * group): index asg_off[r] + v, asg_off[r] = sum over earlier reads of V_g. */
+typedef struct lgr_assign {
+  double local_score;     /* mLocalScore    */
+  double local_identity;  /* mLocalIdentity */
+  double folded_read_pos; /* mFoldedReadPos */
+  int32_t global_score;   /* mGlobalScore   */
+  uint32_t ref_nm;        /* mRefNm         */
+  uint32_t own_hap_nm;    /* mOwnHapNm      */
+  uint32_t hap_id;        /* mAssignedHaplotypeId */
+  int8_t allele;          /* mAllele        */
+  uint8_t base_qual;      /* mBaseQualAtVar */
+  uint8_t assigned;       /* 0: read has no assignment for this variant */
+  uint8_t pad[5];
+} lgr_assign;
+
+typedef struct lgr_batch_out {
+  int64_t n_pairs;         /* capacity of aln / cigar_inline (in pairs)  */
+  int64_t n_assign;        /* capacity of assign                         */
+  lgr_aln* aln;            /* [n_pairs]                                  */
+  uint32_t* cigar_inline;  /* [n_pairs * LGR_CIGAR_INLINE] BAM-encoded len<<4|op */
+  uint32_t* cigar_arena;   /* [cigar_arena_cap] overflow ops             */
+  int64_t cigar_arena_cap;
+  int64_t cigar_arena_used;/* out */
+  lgr_assign* assign;      /* [n_assign]                                 */
+} lgr_batch_out;
+
+/* per-batch device timing + work counters (filled by lgr_genotype_batch) */
+typedef struct lgr_stats {
+  float ms_h2d, ms_kernels, ms_d2h; /* CUDA-event times on the ctx stream */
+  float ms_k_index, ms_k_sketch, ms_k_map, ms_k_assign;
+  int64_t n_pairs, n_aligned;
+  int64_t dp_cells;        /* extension-DP cells actually computed       */
+  int64_t dp_cells_full;   /* cells of the un-pruned rectangles the reference computes */
+  int64_t chain_evals;     /* anchor-pair evaluations in the chain DP    */
+  int64_t n_anchors;
+  int64_t h2d_bytes, d2h_bytes;
+  int32_t kernel_launches;
+  int32_t reserved;
+} lgr_stats;
+
+typedef struct lgr_ctx lgr_ctx;
+
+int lgr_abi_version(void);
+void lgr_default_params(lgr_params* p);
+const char* lgr_strerror(int code);
+/* last CUDA / argument error message of this ctx (or of creation when ctx==NULL) */
+const char* lgr_last_error(const lgr_ctx* ctx);
+
+/* minimap2's __ac_X31_hash_string over a NUL-terminated read name (khash.h). */
+uint32_t lgr_x31_hash(const char* qname);
+
+/* helper: fills pair_off[NR+1] / asg_off[NR+1] for a batch (host side). */
+int lgr_pair_offsets(const lgr_batch_in* in, int64_t* pair_off, int64_t* asg_off);
+
+int lgr_create(int device_ordinal, const lgr_params* params, lgr_ctx** out);
+void lgr_destroy(lgr_ctx* ctx);
+
+/* mid_occ that mm_mapopt_update would latch from this haplotype
+ * (mm_idx_cal_max_occ with mid_occ_frac, clamped to [min_mid_occ, max_mid_occ]). */
+int lgr_hap_mid_occ(lgr_ctx* ctx, const uint8_t* hap, int32_t hap_len, int32_t* mid_occ);
+
+/* Synchronous: H2D of the batch, all kernels, D2H of the results. */
+int lgr_genotype_batch(lgr_ctx* ctx, const lgr_batch_in* in, lgr_batch_out* out, lgr_stats* stats);
+
+/* Device-resident variant for kernel-only timing: upload once, run many times,
+ * download when wanted.  `lgr_upload` keeps a device copy of `in` inside ctx. */
+int lgr_upload(lgr_ctx* ctx, const lgr_batch_in* in);
+int lgr_run_resident(lgr_ctx* ctx, lgr_stats* stats);
+int lgr_download(lgr_ctx* ctx, lgr_batch_out* out);
+
+/* raw CUDA stream (cudaStream_t) the ctx launches on, for external event timing */
+void* lgr_stream(lgr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANCET_GPU_REALIGN_H_ */

@@ -1,0 +1,90 @@
+// TEST INFRASTRUCTURE: C wrappers around the reference's OWN scoring functions,
+// compiled unmodified from /root/reference/src (see ../Makefile target `ref`).
+// Used only by tests/ to pin oracle/genotype_oracle.cpp and to generate the
+// golden vectors under tests/golden/ (tests/golden/gen_scoring_golden.py).
+#include <cstdint>
+#include <cstring>
+#include <string_view>
+#include <vector>
+
+#include "lancet/caller/allele_scoring_types.h"
+#include "lancet/caller/combined_scorer.h"
+#include "lancet/caller/genotyper.h"
+#include "lancet/caller/local_scorer.h"
+#include "lancet/caller/scoring_constants.h"
+#include "lancet/caller/variant_support.h"
+#include "lancet/hts/cigar_unit.h"
+#include "lancet/hts/cigar_utils.h"
+#include "lancet/hts/phred_quality.h"
+
+using lancet::hts::CigarUnit;
+
+static std::vector<CigarUnit> FromBam(const uint32_t* c, int n) {
+  std::vector<CigarUnit> v;
+  v.reserve(n);
+  for (int i = 0; i < n; ++i) v.emplace_back(c[i]);
+  return v;
+}
+
+extern "C" {
+
+double ref_phred_err(uint32_t q) { return lancet::hts::PhredToErrorProb(q); }
+
+void ref_encode(const char* s, int n, uint8_t* out) {
+  auto v = lancet::caller::EncodeSequence(std::string_view(s, (size_t)n));
+  std::memcpy(out, v.data(), v.size());
+}
+
+uint32_t ref_edit_distance(const uint32_t* cigar, int n, const uint8_t* q, int qn, const uint8_t* t, int tn) {
+  return lancet::hts::ComputeEditDistance(FromBam(cigar, n), absl::Span<uint8_t const>(q, qn),
+                                          absl::Span<uint8_t const>(t, tn));
+}
+
+uint64_t ref_refpos_to_qpos(const uint32_t* cigar, int n, uint64_t ref_pos) {
+  return lancet::hts::CigarRefPosToQueryPos(FromBam(cigar, n), (size_t)ref_pos);
+}
+
+double ref_softclip_penalty(const uint32_t* cigar, int n) {
+  return lancet::caller::ComputeSoftClipPenalty(FromBam(cigar, n));
+}
+
+void ref_local_score(const uint32_t* cigar, int n, const uint8_t* q, int qn, const uint8_t* t, int tn,
+                     const uint8_t* quals, int qualn, int32_t aln_start, int32_t var_start, int32_t var_len,
+                     double* out3, uint8_t* bq) {
+  auto const r = lancet::caller::ComputeLocalScore(
+      FromBam(cigar, n), absl::Span<uint8_t const>(q, qn), absl::Span<uint8_t const>(t, tn),
+      absl::Span<uint8_t const>(quals, qualn), aln_start, var_start, var_len, lancet::caller::SCORING_MATRIX);
+  out3[0] = r.mPbqScore, out3[1] = r.mRawScore, out3[2] = r.mIdentity;
+  *bq = r.mBaseQual;
+}
+
+// ScoreReadAtVariant (combined_scorer.cpp:60-108).  hap = full encoded haplotype.
+// out_f[0..3] = local_score, local_identity, folded_pos, CombinedScore();
+// out_i[0..5] = global_score, own_hap_nm, hap_id, allele, base_qual
+void ref_score_read_at_variant(const uint32_t* cigar, int n, int32_t score, int32_t rs, int32_t re, int hap_idx,
+                               const uint8_t* hap, int hap_n, const uint8_t* q, int qn, const uint8_t* quals,
+                               int32_t var_start, int32_t var_len, int allele, double* out_f, int64_t* out_i) {
+  lancet::caller::Mm2AlnResult aln;
+  aln.mCigar = FromBam(cigar, n);
+  aln.mScore = score, aln.mRefStart = rs, aln.mRefEnd = re, aln.mHapIdx = (size_t)hap_idx;
+  lancet::caller::ReadAlnContext ctx{absl::Span<uint8_t const>(q, qn), absl::Span<uint8_t const>(quals, qn),
+                                     (size_t)qn};
+  lancet::caller::HapVariantBounds b{var_start, var_len, (lancet::caller::AlleleIndex)allele};
+  auto const r = lancet::caller::ScoreReadAtVariant(aln, absl::Span<uint8_t const>(hap, hap_n), ctx, b);
+  out_f[0] = r.mLocalScore, out_f[1] = r.mLocalIdentity, out_f[2] = r.mFoldedReadPos, out_f[3] = r.CombinedScore();
+  out_i[0] = r.mGlobalScore, out_i[1] = r.mOwnHapNm, out_i[2] = r.mAssignedHaplotypeId, out_i[3] = r.mAllele;
+  out_i[4] = r.mBaseQualAtVar;
+}
+
+// ComputeHaplotypeEditDistance (combined_scorer.cpp:24-38) for a single alignment on hap_idx
+uint32_t ref_hap_edit_distance(const uint32_t* cigar, int n, int32_t rs, int32_t re, int aln_hap, int hap_idx,
+                               const uint8_t* hap, int hap_n, const uint8_t* q, int qn) {
+  std::vector<lancet::caller::Mm2AlnResult> alns(1);
+  alns[0].mCigar = FromBam(cigar, n);
+  alns[0].mRefStart = rs, alns[0].mRefEnd = re, alns[0].mHapIdx = (size_t)aln_hap;
+  return lancet::caller::ComputeHaplotypeEditDistance(alns, absl::Span<uint8_t const>(hap, hap_n),
+                                                      absl::Span<uint8_t const>(q, qn), (size_t)qn,
+                                                      (size_t)hap_idx);
+}
+
+}  // extern "C"
