@@ -42,6 +42,7 @@ struct DevParams {
 };
 
 constexpr int kSmallM = 12;                 // extension tails up to this many query bases run inline
+constexpr int kSmallCells = 512;            // ... and at most this many (pruned) DP cells
 constexpr int kInlineCig = 6;               // cigar ops kept inline in an ExtRec
 constexpr int kMaxWindow = 32;              // minimizer window cap (reference uses w = 5)
 constexpr int32_t kNegInf = -0x40000000;
@@ -505,12 +506,14 @@ LGR_HD void ext_dp_scalar(const DevParams& P, int m, int T, QF qf, TF tf, bool r
   *out_mqe_t = mqe_t;
 }
 
-// ksw2.h: ksw_backtrack from (i0, m-1); dir indexed [i*m + j].  `rev_cigar`: keep the
-// backtrack order (left extension), else reverse at the end.
-LGR_HD void ext_backtrack(const uint8_t* dir, int m, int i0, bool rev_cigar, CigBuf& cb) {
+// ksw2.h: ksw_backtrack from (i0, m-1); dirf(i, j) returns the direction byte of cell
+// (target i, query j).  `rev_cigar`: keep the backtrack order (left extension), else
+// reverse at the end.
+template <typename DirF>
+LGR_HD void ext_backtrack(DirF dirf, int m, int i0, bool rev_cigar, CigBuf& cb) {
   int i = i0, j = m - 1, state = 0;
   while (i >= 0 && j >= 0) {
-    const uint8_t tmp = dir[i * m + j];
+    const uint8_t tmp = dirf(i, j);
     if (state == 0) state = tmp & 7;
     else if (!(tmp >> (state + 2) & 1)) state = 0;
     if (state == 0) state = tmp & 7;
@@ -1019,6 +1022,12 @@ LGR_HD void export_reg(const Ws<S>& ws, int r, int qlen, RegRec* out) {
   if (out->c_qe < qlen && out->c_re < out->re0) R.m = qlen - out->c_qe, R.n = out->re0 - out->c_re;
 }
 
+// does this extension run inline in the pair's lane (true) or on a warp (k_ext_big)?
+LGR_HD bool ext_is_small(const DevParams& P, const ExtRec& E) {
+  if (E.m <= 0) return true;
+  return E.m <= kSmallM && E.m * prune_cols(P, E.m, E.n) <= kSmallCells;
+}
+
 // query / target accessors of an extension, as align.c presents them to ksw2
 struct ExtQuery {
   ReadView rv;
@@ -1048,7 +1057,7 @@ LGR_HD bool run_ext_scalar(const DevParams& P, const ReadView& rv, const uint8_t
   ext_dp_scalar(P, m, T, qf, tf, side == 0, dir, hcol, ecol, &E.max, &E.mqe_t);
   if (ctr) ctr->dp_cells += (int64_t)m * T, ctr->dp_cells_full += (int64_t)m * E.n;
   CigBuf cb{cig_tmp, 0, cig_tmp_cap};
-  ext_backtrack(dir, m, E.mqe_t, side == 0, cb);
+  ext_backtrack([&](int i, int j) { return dir[i * m + j]; }, m, E.mqe_t, side == 0, cb);
   E.n_cig = cb.n;
   if (cb.n > cig_tmp_cap) return false;
   if (cb.n <= kInlineCig) {

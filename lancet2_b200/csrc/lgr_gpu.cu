@@ -1,0 +1,1132 @@
+// lgr_gpu.cu — sm_100a kernels + the C-ABI of the B200 read→haplotype realignment path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+//
+// Pipeline per batch (all on one stream; see DESIGN.md for the data layout and rooflines):
+//   k_encode          ASCII → code bytes (nt4 | Lancet code) for haplotypes and reads
+//   k_hap_sketch      one lane per haplotype: minimizer sketch → unsorted table
+//   k_hap_sort        one CTA per haplotype: bitonic sort of the table (the "index")
+//   k_hap_mid         mid_occ a Genotyper would latch from each haplotype / group
+//   k_read_sketch     one lane per read: sketch + mm_seed_mz_flt
+//   k_map             one lane per (read, haplotype) pair: seeds → anchors → sort → chain DP →
+//                     backtrack → regs → small extensions inline → finish; pairs with a long
+//                     tail are parked (RegRec) and their tails queued
+//   k_ext_big         one warp per queued tail: anti-diagonal wavefront affine-gap DP with
+//                     shuffle neighbour exchange, direction bytes in HBM scratch, traceback
+//   k_finish          one lane per parked pair
+//   k_assign          one lane per (read, variant): local scoring + best-allele selection
+// There is no host fallback: every entry point fails with an error code when CUDA fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lancet_gpu_realign.h"
+#include "lgr_core.cuh"
+
+namespace {
+
+using namespace lgr;
+
+__constant__ double c_phred_err[256] = {
+#include "phred_lut.inc"
+};
+
+// counters (int64 slots in device memory)
+enum Ctr {
+  C_ITEM = 0, C_NDEF, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ALIGNED, C_TASKPOS, C_OVFPOS, C_COUNT
+};
+enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
+
+struct DefRec {   // a parked pair
+  int32_t read, hap, first_reg, n_regs;
+};
+struct TaskRec {  // one queued long tail
+  int32_t reg, side, read, hap;
+};
+
+struct Dev {      // everything the kernels need, passed by value
+  DevParams P;
+  int n_groups, n_haps, n_reads, n_vars;
+  int64_t n_pairs, n_assign;
+  // inputs
+  const int32_t *grp_hap_begin, *grp_read_begin, *grp_var_begin;
+  const int64_t *hap_off, *read_off, *var_hap_off;
+  const uint8_t *hap_bases, *read_bases, *read_quals;
+  const uint32_t* name_hash;
+  const int32_t *var_start, *var_len;
+  const int8_t* var_allele;
+  const int32_t* read_grp;      // [NR]
+  const int32_t* hap_grp;       // [NH]
+  const int64_t *pair_off, *asg_off;  // [NR+1]
+  const int32_t *item_hap, *item_r0, *item_n;  // phase-A work items: (hap, first read, #reads<=32)
+  int n_items;
+  // derived
+  uint8_t *hap_codes, *read_codes;
+  uint64_t* idx;                // [hap_off-indexed] sorted minimizer tables
+  int32_t *idx_n, *hap_mid;     // [NH]
+  int32_t* grp_mid;             // [G] in: >0 fixed, <=0 latch from first hap; out: effective
+  uint64_t* mz_x;               // [read_off-indexed]
+  uint32_t* mz_y;
+  int32_t* mz_n;                // [NR]
+  // phase A workspace
+  int32_t* ws;                  // [n_threads][A_COUNT][cap] interleaved per warp
+  int ws_cap;
+  uint32_t* fin_scratch;        // [n_threads][2][fin_cap]
+  int fin_cap;
+  // parked pairs / tails
+  RegRec* regs;  int64_t regs_cap;
+  DefRec* defs;  int64_t defs_cap;
+  TaskRec* tasks; int64_t tasks_cap;
+  uint32_t* ext_arena; int64_t ext_arena_cap;
+  int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
+  // k_ext_big scratch
+  uint8_t* dir_scratch; int64_t dir_per_warp;
+  int32_t* bnd_scratch; int64_t bnd_per_warp;   // Hb/Fb boundary rows
+  uint32_t* wcig_scratch; int wcig_cap;
+  // outputs
+  AlnOut* aln; uint32_t* cigar_inline; uint32_t* cigar_arena; int64_t cigar_arena_cap;
+  AssignOut* assign;
+  long long* ctr;
+};
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_encode(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = encode_base(src[i]);
+}
+
+// one lane per haplotype: sketch → table entries (hash<<17 | pos<<1|strand), unsorted
+__global__ void k_hap_sketch(Dev D) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= D.n_haps) return;
+  const int64_t off = D.hap_off[h];
+  const int len = (int)(D.hap_off[h + 1] - off);
+  uint64_t* tab = D.idx + off;
+  // simple two-array adaptor: x is staged in the table slot, y finalises it
+  struct XW {
+    uint64_t* t;
+    __device__ uint64_t& operator[](int i) const { return t[i]; }
+  };
+  struct YW {
+    uint64_t* t;
+    struct Ref {
+      uint64_t* p;
+      __device__ void operator=(uint32_t y) const { *p = (*p >> 8) << kIdxShift | (uint64_t)y; }
+    };
+    __device__ Ref operator[](int i) const { return Ref{t + i}; }
+  };
+  int n = 0;
+  if (len > 0) n = sketch(D.hap_codes + off, len, D.P.w, D.P.k, XW{tab}, YW{tab}, len);
+  if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
+  D.idx_n[h] = n;
+}
+
+// one CTA per haplotype: in-place bitonic sort of its table (keys are unique)
+__global__ void k_hap_sort(Dev D) {
+  const int h = blockIdx.x;
+  uint64_t* tab = D.idx + D.hap_off[h];
+  const int n = D.idx_n[h];
+  if (n <= 1) return;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  extern __shared__ uint64_t s_tab[];
+  const bool use_smem = np2 <= 2048;
+  uint64_t* a = use_smem ? s_tab : tab;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) s_tab[i] = i < n ? tab[i] : UINT64_MAX;
+    __syncthreads();
+  }
+  // all-ascending bitonic network (first step of every merge pairs i with its mirror
+  // i ^ (k-1)); with ascending comparators only, slots >= n act as +inf padding and are
+  // simply skipped.
+  const int lim = use_smem ? np2 : n;
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1, first = 1; j > 0; j >>= 1, first = 0) {
+      for (int i = threadIdx.x; i < lim; i += blockDim.x) {
+        const int l = first ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i && l < lim) {
+          const uint64_t vi = a[i], vl = a[l];
+          if (vi > vl) a[i] = vl, a[l] = vi;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (use_smem)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = s_tab[i];
+}
+
+__global__ void k_hap_mid(Dev D, float mid_occ_frac, int min_mid, int max_mid) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= D.n_haps) return;
+  D.hap_mid[h] = hap_mid_occ(D.idx + D.hap_off[h], D.idx_n[h], mid_occ_frac, min_mid, max_mid);
+}
+
+__global__ void k_group_mid(Dev D, int min_mid) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= D.n_groups) return;
+  if (D.grp_mid[g] > 0) return;
+  const int h0 = D.grp_hap_begin[g];
+  D.grp_mid[g] = D.grp_hap_begin[g + 1] > h0 ? D.hap_mid[h0] : min_mid;
+}
+
+// one lane per read: sketch + mm_seed_mz_flt (q_occ_max = the group's mid_occ)
+__global__ void k_read_sketch(Dev D) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= D.n_reads) return;
+  const int64_t off = D.read_off[r];
+  const int len = (int)(D.read_off[r + 1] - off);
+  int n = 0;
+  if (len > 0) {
+    n = sketch(D.read_codes + off, len, D.P.w, D.P.k, D.mz_x + off, D.mz_y + off, len);
+    if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
+    if (D.P.q_occ_frac > 0.0f) n = seed_mz_flt(D.mz_x + off, D.mz_y + off, n, D.grp_mid[D.read_grp[r]], D.P.q_occ_frac);
+  }
+  D.mz_n[r] = n;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_map: one lane per pair.  A warp takes one work item = (haplotype, up to 32 consecutive
+// reads of its group); all lanes therefore share the haplotype table and bases (L1 hits) and
+// their interleaved workspace accesses coalesce while they run in lock step.
+// FROM_LIST: second pass over pairs whose anchor count exceeded the fast workspace.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_invalid(AlnOut* o) {
+  o->valid = 0, o->score = 0, o->rs = 0, o->re = 0, o->qs = 0, o->qe = 0, o->rev = 0, o->dp_score = 0, o->dp_max = 0;
+  o->mlen = 0, o->blen = 0, o->n_ambi = 0, o->nm = 0, o->n_cigar = 0, o->cigar_off = -1, o->n_regs = 0;
+}
+
+__device__ __forceinline__ void store_final(const Dev& D, int64_t pair, const AlnOut& a, const uint32_t* cig, int nc) {
+  AlnOut o = a;
+  if (nc <= LGR_CIGAR_INLINE) {
+    o.cigar_off = -1;
+    uint32_t* dst = D.cigar_inline + pair * LGR_CIGAR_INLINE;
+    for (int i = 0; i < nc; ++i) dst[i] = cig[i];
+  } else {
+    const long long off = atomicAdd((unsigned long long*)&D.ctr[C_CIGARENA], (unsigned long long)nc);
+    if (off + nc > D.cigar_arena_cap) {
+      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_ARENA);
+      o.cigar_off = -2, o.n_cigar = 0;
+    } else {
+      o.cigar_off = (int32_t)off;
+      for (int i = 0; i < nc; ++i) D.cigar_arena[off + i] = cig[i];
+    }
+  }
+  D.aln[pair] = o;
+}
+
+template <bool FROM_LIST>
+__global__ void __launch_bounds__(128) k_map(Dev D) {
+  const int lane = threadIdx.x & 31;
+  const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gwarp = gthread >> 5;
+  Ws<32> ws;
+  ws.cap = D.ws_cap;
+  ws.base = D.ws + (size_t)gwarp * A_COUNT * D.ws_cap * 32 + lane;
+  uint32_t* fin0 = D.fin_scratch + (size_t)gthread * 2 * D.fin_cap;
+  RadixScratch rsx;
+  ChainCounters ctr{0, 0, 0, 0};
+  long long n_aligned = 0;
+  const long long n_work = FROM_LIST ? D.ctr[C_NOVF] : (long long)D.n_items;
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = atomicAdd((unsigned long long*)&D.ctr[FROM_LIST ? C_OVFPOS : C_ITEM], FROM_LIST ? 32ULL : 1ULL);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_work) break;
+    int r, h;
+    bool active;
+    if (FROM_LIST) {
+      active = item + lane < n_work;
+      r = active ? D.ovf_read[item + lane] : 0;
+      h = active ? D.ovf_hap[item + lane] : 0;
+    } else {
+      h = D.item_hap[item];
+      active = lane < D.item_n[item];
+      r = D.item_r0[item] + lane;
+    }
+    if (active) {
+      const int g = D.read_grp[r];
+      const int h_local = h - D.grp_hap_begin[g];
+      const int64_t pair = D.pair_off[r] + h_local;
+      const int64_t roff = D.read_off[r], hoff = D.hap_off[h];
+      const int qlen = (int)(D.read_off[r + 1] - roff);
+      const int hlen = (int)(D.hap_off[h + 1] - hoff);
+      ReadView rv{D.read_codes + roff, qlen};
+      const uint8_t* hapc = D.hap_codes + hoff;
+      PairIn pin{rv, hapc, hlen, D.idx + hoff, D.idx_n[h], D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], D.grp_mid[g]};
+      int n_regs = 0;
+      const int st = qlen > 0 ? map_chain_phase<32>(D.P, pin, ws, &rsx, &n_regs, &ctr) : kMapNoHit;
+      if (st == kMapOverflow) {
+        if (FROM_LIST) {
+          atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
+          write_invalid(&D.aln[pair]);
+        } else {
+          const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
+          if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h;
+          else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
+        }
+      } else if (st == kMapNoHit) {
+        write_invalid(&D.aln[pair]);
+      } else {
+        // decide: everything inline (all tails <= kSmallM, <= 2 regs) or park the pair
+        RegRec loc[2];
+        bool park = n_regs > 2;
+        if (!park) {
+          for (int i = 0; i < n_regs; ++i) {
+            export_reg<32>(ws, i, qlen, &loc[i]);
+            if (!ext_is_small(D.P, loc[i].ext[0]) || !ext_is_small(D.P, loc[i].ext[1])) park = true;
+          }
+        }
+        uint8_t dir[kSmallCells];
+        int32_t hcol[kSmallM], ecol[kSmallM];
+        uint32_t cig_tmp[2 * kSmallM + 4];
+        auto alloc_ext = [&](int n) -> int64_t {
+          const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)n);
+          if (o + n > D.ext_arena_cap) {
+            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
+            return -1;
+          }
+          return o;
+        };
+        if (!park) {
+          bool ok = true;
+          for (int i = 0; i < n_regs; ++i)
+            for (int side = 0; side < 2; ++side)
+              if (loc[i].ext[side].m > 0)
+                ok &= run_ext_scalar(D.P, rv, hapc, &loc[i], side, dir, hcol, ecol, cig_tmp, 2 * kSmallM + 4, D.ext_arena,
+                                     alloc_ext, &ctr);
+          FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
+          AlnOut ao;
+          const int nc = ok ? finish_pair(D.P, rv, hapc, loc, n_regs, D.ext_arena, fs, &ao) : -1;
+          if (nc < 0) {
+            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+            write_invalid(&D.aln[pair]);
+          } else {
+            store_final(D, pair, ao, fs.best, nc);
+            n_aligned += ao.valid;
+          }
+        } else {
+          const long long first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
+          const long long di = atomicAdd((unsigned long long*)&D.ctr[C_NDEF], 1ULL);
+          if (first + n_regs > D.regs_cap || di >= D.defs_cap) {
+            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+            write_invalid(&D.aln[pair]);
+          } else {
+            D.defs[di] = DefRec{r, h, (int32_t)first, n_regs};
+            for (int i = 0; i < n_regs; ++i) {
+              RegRec rr;
+              export_reg<32>(ws, i, qlen, &rr);
+              for (int side = 0; side < 2; ++side) {
+                const int m = rr.ext[side].m;
+                if (m <= 0) continue;
+                if (ext_is_small(D.P, rr.ext[side])) {
+                  run_ext_scalar(D.P, rv, hapc, &rr, side, dir, hcol, ecol, cig_tmp, 2 * kSmallM + 4, D.ext_arena, alloc_ext, &ctr);
+                } else {
+                  const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
+                  if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
+                  else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+                }
+              }
+              D.regs[first + i] = rr;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // stats
+  for (int o = 16; o > 0; o >>= 1) {
+    ctr.chain_evals += __shfl_down_sync(0xffffffffu, ctr.chain_evals, o);
+    ctr.n_anchors += __shfl_down_sync(0xffffffffu, ctr.n_anchors, o);
+    ctr.dp_cells += __shfl_down_sync(0xffffffffu, ctr.dp_cells, o);
+    ctr.dp_cells_full += __shfl_down_sync(0xffffffffu, ctr.dp_cells_full, o);
+    n_aligned += __shfl_down_sync(0xffffffffu, n_aligned, o);
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
+    atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)ctr.dp_cells);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
+    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_ext_big: one warp per long tail.  Lane l owns query row j = 32*blk + l and sweeps the
+// target columns; on step s it computes cell (i = s - l, j).  H and the F flowing down a
+// column travel to the lane below with two shuffles per step; E stays in the lane.  Rows
+// beyond 32 are processed in further passes with the boundary row (H, F) kept in scratch.
+// Direction bytes are stored diagonal-major ([blk][s][lane]) so that every step is one
+// coalesced 32-byte store.  Same recurrences, tie rules and column pruning as
+// ext_dp_scalar (which the lanes of k_map run for short tails).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ext_big(Dev D) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint8_t* dir = D.dir_scratch + (size_t)gwarp * D.dir_per_warp;
+  int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
+  int32_t* Fb = Hb + D.bnd_per_warp / 2;
+  uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
+  const long long n_tasks = D.ctr[C_NTASK] < D.tasks_cap ? D.ctr[C_NTASK] : D.tasks_cap;
+  const DevParams& P = D.P;
+  const int q = P.q, e = P.e;
+  long long cells = 0, cells_full = 0;
+  for (;;) {
+    long long ti = 0;
+    if (lane == 0) ti = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
+    ti = __shfl_sync(0xffffffffu, ti, 0);
+    if (ti >= n_tasks) break;
+    const TaskRec tk = D.tasks[ti];
+    RegRec* reg = D.regs + tk.reg;
+    const int side = tk.side;
+    const int64_t roff = D.read_off[tk.read], hoff = D.hap_off[tk.hap];
+    ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
+    const uint8_t* hapc = D.hap_codes + hoff;
+    const int m = reg->ext[side].m, n = reg->ext[side].n;
+    const int T = prune_cols(P, m, n);
+    const bool right = side == 0;
+    ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
+    ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
+    const int nblk = (m + 31) >> 5;
+    const int dstride = T + 32;  // steps per block (padded)
+    int32_t ezmax = 0, mqe = kNegInf, mqe_t = -1;
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int j = blk * 32 + lane;
+      const bool row_ok = j < m;
+      const int qc = row_ok ? qf(j) : 4;
+      int32_t e_cur = -(q + e * (j + 1)) - q - e;           // E(0, j)
+      int32_t diag = j == 0 ? 0 : -(q + e * j);             // H(-1, j-1)
+      int32_t h_last = 0, f_out = 0;
+      uint8_t* dblk = dir + (size_t)blk * dstride * 32;
+      const int nsteps = T + 31;
+      for (int s = 0; s < nsteps; ++s) {
+        int32_t up_h = __shfl_up_sync(0xffffffffu, h_last, 1);
+        int32_t up_f = __shfl_up_sync(0xffffffffu, f_out, 1);
+        const int i = s - lane;
+        const bool act = row_ok && i >= 0 && i < T;
+        if (lane == 0 && act) {
+          if (blk == 0) {
+            up_h = -(q + e * (i + 1));
+            up_f = up_h - q - e;
+          } else {
+            up_h = Hb[i];
+            up_f = Fb[i];
+          }
+        }
+        if (act) {
+          const int tc = tf(i);
+          const int32_t hd = diag + sub_score(P, tc, qc);
+          const int32_t ee = e_cur;
+          const int32_t f = up_f;
+          int32_t h;
+          uint32_t d;
+          if (!right) {
+            d = ee > hd ? 1u : 0u;
+            h = ee > hd ? ee : hd;
+            if (f > h) d = 2u, h = f;
+          } else {
+            d = hd > ee ? 0u : 1u;
+            h = hd > ee ? hd : ee;
+            if (!(h > f)) d = 2u, h = f;
+          }
+          const int32_t ho = h - q;
+          if (!right) {
+            if (ee > ho) d |= 0x08u;
+            if (f > ho) d |= 0x10u;
+          } else {
+            if (ee >= ho) d |= 0x08u;
+            if (f >= ho) d |= 0x10u;
+          }
+          dblk[(size_t)s * 32 + lane] = (uint8_t)d;
+          diag = up_h;
+          h_last = h;
+          e_cur = (ee > ho ? ee : ho) - e;
+          f_out = (f > ho ? f : ho) - e;
+          if (h > ezmax) ezmax = h;
+          if (j == m - 1 && h > mqe) mqe = h, mqe_t = i;
+          if (lane == 31 && blk + 1 < nblk) Hb[i] = h, Fb[i] = f_out;
+        }
+      }
+      __syncwarp();
+    }
+    // reduce: ez.max over lanes; (mqe, mqe_t) lives in the lane that owns row m-1
+    for (int o = 16; o > 0; o >>= 1) {
+      const int32_t v = __shfl_down_sync(0xffffffffu, ezmax, o);
+      ezmax = v > ezmax ? v : ezmax;
+    }
+    ezmax = __shfl_sync(0xffffffffu, ezmax, 0);
+    mqe_t = __shfl_sync(0xffffffffu, mqe_t, (m - 1) & 31);
+    __syncwarp();
+    if (lane == 0) {
+      ExtRec& E = reg->ext[side];
+      E.max = ezmax;
+      E.mqe_t = mqe_t;
+      CigBuf cb{wcig, 0, D.wcig_cap};
+      auto dirf = [&](int i, int j) -> uint8_t {
+        const int b = j >> 5, l = j & 31;
+        return dir[((size_t)b * dstride + (size_t)(i + l)) * 32 + l];
+      };
+      ext_backtrack(dirf, m, mqe_t, side == 0, cb);
+      E.n_cig = cb.n;
+      if (cb.n > D.wcig_cap) {
+        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+        E.n_cig = 0;
+      } else if (cb.n <= kInlineCig) {
+        E.cig_off = -1;
+        for (int c = 0; c < cb.n; ++c) E.inl[c] = wcig[c];
+      } else {
+        const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)cb.n);
+        if (o + cb.n > D.ext_arena_cap) {
+          atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
+          E.n_cig = 0;
+        } else {
+          E.cig_off = (int32_t)o;
+          for (int c = 0; c < cb.n; ++c) D.ext_arena[o + c] = wcig[c];
+        }
+      }
+      cells += (long long)m * T;
+      cells_full += (long long)m * n;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)cells);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)cells_full);
+  }
+}
+
+// one lane per parked pair
+__global__ void __launch_bounds__(128) k_finish(Dev D) {
+  const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_def = D.ctr[C_NDEF] < D.defs_cap ? D.ctr[C_NDEF] : D.defs_cap;
+  uint32_t* fin0 = D.fin_scratch + (size_t)gthread * 2 * D.fin_cap;
+  long long n_aligned = 0;
+  for (long long di = gthread; di < n_def; di += (long long)gridDim.x * blockDim.x) {
+    const DefRec d = D.defs[di];
+    const int g = D.read_grp[d.read];
+    const int64_t pair = D.pair_off[d.read] + (d.hap - D.grp_hap_begin[g]);
+    const int64_t roff = D.read_off[d.read], hoff = D.hap_off[d.hap];
+    ReadView rv{D.read_codes + roff, (int)(D.read_off[d.read + 1] - roff)};
+    FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
+    AlnOut ao;
+    const int nc = finish_pair(D.P, rv, D.hap_codes + hoff, D.regs + d.first_reg, d.n_regs, D.ext_arena, fs, &ao);
+    if (nc < 0) {
+      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+      write_invalid(&D.aln[pair]);
+    } else {
+      store_final(D, pair, ao, fs.best, nc);
+      n_aligned += ao.valid;
+    }
+  }
+  if (n_aligned) atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
+}
+
+// one lane per (read, variant): AssignReadToAlleles' inner loops (genotyper.cpp:294-318)
+__global__ void __launch_bounds__(128) k_assign(Dev D) {
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= D.n_assign) return;
+  // read r with asg_off[r] <= slot < asg_off[r+1]
+  int lo = 0, hi = D.n_reads;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (D.asg_off[mid] <= slot) lo = mid;
+    else hi = mid;
+  }
+  const int r = lo;  // asg_off[r] <= slot < asg_off[r+1]
+  const int v_local = (int)(slot - D.asg_off[r]);
+  const int g = D.read_grp[r];
+  const int h0 = D.grp_hap_begin[g], Pn = D.grp_hap_begin[g + 1] - h0;
+  const int v = D.grp_var_begin[g] + v_local;
+  const int64_t roff = D.read_off[r];
+  const int qlen = (int)(D.read_off[r + 1] - roff);
+  const int64_t pair0 = D.pair_off[r];
+  AssignOut best;
+  best.local_score = best.local_identity = best.folded_read_pos = 0.0;
+  best.global_score = 0, best.ref_nm = best.own_hap_nm = best.hap_id = 0, best.allele = 0, best.base_qual = 0, best.assigned = 0;
+  for (int i = 0; i < 5; ++i) best.pad[i] = 0;
+  double best_cs = 0.0;
+  uint32_t ref_nm = (uint32_t)qlen;
+  {
+    const AlnOut& a0 = D.aln[pair0];
+    if (Pn > 0 && a0.valid && a0.rs < a0.re) ref_nm = (uint32_t)a0.nm;
+  }
+  for (int h = 0; h < Pn; ++h) {
+    const AlnOut a = D.aln[pair0 + h];
+    if (!a.valid) continue;
+    const int64_t vh = D.var_hap_off[v] + h;
+    const int allele = D.var_allele[vh];
+    if (allele < 0) continue;
+    const int32_t vs = D.var_start[vh], vl = D.var_len[vh];
+    if (!(vs + vl > a.rs && vs < a.re)) continue;
+    const uint32_t* cig = a.cigar_off < 0 ? D.cigar_inline + (pair0 + h) * LGR_CIGAR_INLINE : D.cigar_arena + a.cigar_off;
+    AssignOut cand;
+    score_read_variant(a, cig, D.read_codes + roff, D.read_quals + roff, qlen, D.hap_codes + D.hap_off[h0 + h], vs, vl, allele, h,
+                       ref_nm, c_phred_err, &cand);
+    const double cs = (double)cand.global_score + cand.local_score * cand.local_identity;
+    if (best.assigned && cs <= best_cs) continue;
+    best = cand, best_cs = cs;
+  }
+  D.assign[slot] = best;
+}
+
+// =========================================================================================
+// host side
+// =========================================================================================
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct lgr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  lgr_params prm;
+  DevParams P;
+  std::string err;
+  int sm_count = 0;
+  // grow-only device buffers
+  std::vector<DevBuf*> all;
+  DevBuf b_grp_hap, b_grp_read, b_grp_var, b_hap_off, b_read_off, b_var_hap_off, b_hap_bases, b_read_bases, b_read_quals,
+      b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
+      b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_ws, b_fin, b_regs,
+      b_defs, b_tasks, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
+      b_ctr, b_ws_big;
+  Dev D;
+  bool resident = false;
+  int max_read_len = 0, max_hap_len = 0;
+  int64_t hap_bytes = 0, read_bytes = 0;
+  int map_blocks = 0, ext_blocks = 0;
+  cudaEvent_t ev[12];
+  // host staging of helper arrays
+  std::vector<int32_t> h_read_grp, h_hap_grp, h_item_hap, h_item_r0, h_item_n, h_grp_mid;
+  std::vector<int64_t> h_pair_off, h_asg_off;
+};
+
+static thread_local std::string g_create_err;
+
+#define LGR_CUDA(ctx, call)                                                                  \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+      return LGR_E_CUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+static int ensure(lgr_ctx* c, DevBuf& b, size_t bytes) {
+  if (bytes < 256) bytes = 256;
+  if (b.cap >= bytes) return LGR_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr, b.cap = 0;
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    c->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);
+    return LGR_E_NOMEM;
+  }
+  b.cap = want;
+  return LGR_OK;
+}
+
+extern "C" {
+
+int lgr_abi_version(void) { return LGR_ABI_VERSION; }
+
+void lgr_default_params(lgr_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->k = 11, p->w = 5;
+  p->a = 1, p->b = 4, p->q = 12, p->e = 3, p->sc_ambi = 1;
+  p->bw = 10000, p->zdrop = 100000, p->end_bonus = 10000;
+  p->max_gap = 200, p->max_gap_ref = 5000;
+  p->max_chain_skip = 25, p->max_chain_iter = 5000, p->min_cnt = 3, p->min_chain_score = 40;
+  p->min_dp_max = 80;
+  p->mid_occ = 0, p->min_mid_occ = 10, p->max_mid_occ = 1000000, p->max_max_occ = 4095;
+  p->occ_dist = 500, p->best_n = 1, p->seed = 11;
+  p->mid_occ_frac = 2e-4f, p->q_occ_frac = 0.01f, p->chain_gap_scale = 0.8f, p->chain_skip_scale = 0.0f;
+  p->mask_level = 0.5f, p->pri_ratio = 0.8f, p->max_clip_ratio = 1.0f;
+  p->mask_len = INT_MAX;
+  p->cigar_arena_ops = 1 << 20;
+}
+
+const char* lgr_strerror(int code) {
+  switch (code) {
+    case LGR_OK: return "ok";
+    case LGR_E_ARG: return "bad argument or inconsistent batch";
+    case LGR_E_CUDA: return "CUDA runtime failure";
+    case LGR_E_NO_DEVICE: return "no usable CUDA device (this path has no CPU fallback)";
+    case LGR_E_LIMIT: return "a sequence or intermediate exceeds a device-path cap";
+    case LGR_E_CIGAR_OVERFLOW: return "cigar overflow arena exhausted";
+    case LGR_E_NOMEM: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+
+const char* lgr_last_error(const lgr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+uint32_t lgr_x31_hash(const char* s) {
+  uint32_t h = (uint32_t)(int32_t)(signed char)*s;
+  if (h)
+    for (++s; *s; ++s) h = (h << 5) - h + (uint32_t)(int32_t)(signed char)*s;
+  return h;
+}
+
+int lgr_pair_offsets(const lgr_batch_in* in, int64_t* pair_off, int64_t* asg_off) {
+  if (!in || !pair_off || !asg_off) return LGR_E_ARG;
+  int64_t po = 0, ao = 0;
+  for (int g = 0; g < in->n_groups; ++g) {
+    const int P = in->grp_hap_begin[g + 1] - in->grp_hap_begin[g];
+    const int V = in->grp_var_begin[g + 1] - in->grp_var_begin[g];
+    for (int r = in->grp_read_begin[g]; r < in->grp_read_begin[g + 1]; ++r) {
+      pair_off[r] = po, asg_off[r] = ao;
+      po += P, ao += V;
+    }
+  }
+  pair_off[in->n_reads] = po, asg_off[in->n_reads] = ao;
+  return LGR_OK;
+}
+
+static int validate_params(const lgr_params* p, std::string& err) {
+  auto bad = [&](const char* m) { err = m; return LGR_E_ARG; };
+  if (p->k < 1 || 2 * p->k + kIdxShift > 64) return bad("k must satisfy 2k+17 <= 64 (k <= 23)");
+  if (p->w < 1 || p->w > kMaxWindow) return bad("w must be in [1,32]");
+  if (p->a < 0 || p->b < 0 || p->q < 0 || p->e < 1 || p->sc_ambi < 0) return bad("scores must be non-negative, e >= 1");
+  if (p->b > 2 * (p->q + p->e)) return bad("mismatch penalty exceeds 2(q+e): ksw2 returns early, unsupported");
+  // regime of the reference: the extension always reaches the query end and never z-drops
+  if (p->end_bonus < (p->a + std::max(p->b, p->sc_ambi)) * LGR_MAX_READ_LEN + p->q + p->e * LGR_MAX_READ_LEN)
+    return bad("end_bonus too small: device path requires reach_end for every extension (reference uses 10000)");
+  if (p->zdrop < 16 * LGR_MAX_READ_LEN) return bad("zdrop too small: device path requires that z-drop never fires (reference uses 100000)");
+  if (p->occ_dist != 0 && p->occ_dist < 256) return bad("occ_dist must be 0 or >= 256");
+  if (p->min_cnt < 1 || p->best_n < 0) return bad("min_cnt >= 1, best_n >= 0");
+  return LGR_OK;
+}
+
+int lgr_create(int device_ordinal, const lgr_params* params, lgr_ctx** out) {
+  if (!out) return LGR_E_ARG;
+  *out = nullptr;
+  lgr_params p;
+  if (params) p = *params;
+  else lgr_default_params(&p);
+  int rc = validate_params(&p, g_create_err);
+  if (rc != LGR_OK) return rc;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device_ordinal < 0 || device_ordinal >= n_dev) {
+    g_create_err = "no usable CUDA device";
+    (void)cudaGetLastError();
+    return LGR_E_NO_DEVICE;
+  }
+  lgr_ctx* c = new lgr_ctx();
+  c->device = device_ordinal;
+  c->prm = p;
+  if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = "cudaSetDevice/cudaStreamCreate failed";
+    delete c;
+    return LGR_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_ordinal);
+  c->sm_count = prop.multiProcessorCount;
+  for (auto& e : c->ev) cudaEventCreate(&e);
+  DevParams& d = c->P;
+  std::memset(&d, 0, sizeof(d));
+  d.k = p.k, d.w = p.w, d.a = p.a, d.b = p.b, d.q = p.q, d.e = p.e, d.sc_ambi = p.sc_ambi, d.bw = p.bw;
+  d.end_bonus = p.end_bonus, d.max_gap = p.max_gap, d.max_gap_ref = p.max_gap_ref, d.max_skip = p.max_chain_skip;
+  d.max_iter = p.max_chain_iter, d.min_cnt = p.min_cnt, d.min_sc = p.min_chain_score, d.min_dp_max = p.min_dp_max;
+  d.max_max_occ = p.max_max_occ, d.occ_dist = p.occ_dist, d.best_n = p.best_n, d.seed = p.seed, d.mask_len = p.mask_len;
+  d.pen_gap = (float)(p.chain_gap_scale * 0.01 * p.k);
+  d.pen_skip = (float)(p.chain_skip_scale * 0.01 * p.k);
+  d.mask_level = p.mask_level, d.pri_ratio = p.pri_ratio, d.max_clip_ratio = p.max_clip_ratio, d.q_occ_frac = p.q_occ_frac;
+  d.min_strand_sc = (int32_t)(p.max_gap * 0.8);
+  *out = c;
+  return LGR_OK;
+}
+
+void lgr_destroy(lgr_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  DevBuf* bufs[] = {&c->b_grp_hap, &c->b_grp_read, &c->b_grp_var, &c->b_hap_off, &c->b_read_off, &c->b_var_hap_off, &c->b_hap_bases,
+                    &c->b_read_bases, &c->b_read_quals, &c->b_name_hash, &c->b_var_start, &c->b_var_len, &c->b_var_allele,
+                    &c->b_read_grp, &c->b_hap_grp, &c->b_pair_off, &c->b_asg_off, &c->b_item_hap, &c->b_item_r0, &c->b_item_n,
+                    &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
+                    &c->b_mz_n, &c->b_ws, &c->b_fin, &c->b_regs, &c->b_defs, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
+                    &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
+                    &c->b_ctr, &c->b_ws_big};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (auto& e : c->ev) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void* lgr_stream(lgr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+static constexpr int kCapFast = 256;     // anchors per lane in the fast pass
+static constexpr int kCapBig = 16384;    // anchors per lane in the overflow pass
+static constexpr int kBigWarps = 4 * 37; // warps of the overflow pass (workspace = 28 arrays * cap * 4 B per lane)
+
+static int validate_batch(lgr_ctx* c, const lgr_batch_in* in) {
+  auto bad = [&](const std::string& m, int code = LGR_E_ARG) { c->err = m; return code; };
+  if (!in || in->n_groups < 0 || in->n_haps < 0 || in->n_reads < 0 || in->n_vars < 0) return bad("null or negative counts");
+  if (in->n_groups > 0 && (!in->grp_hap_begin || !in->grp_read_begin || !in->grp_var_begin)) return bad("null group arrays");
+  if (in->n_groups == 0) return LGR_OK;
+  if (in->grp_hap_begin[0] != 0 || in->grp_read_begin[0] != 0 || in->grp_var_begin[0] != 0) return bad("group prefix arrays must start at 0");
+  if (in->grp_hap_begin[in->n_groups] != in->n_haps || in->grp_read_begin[in->n_groups] != in->n_reads ||
+      in->grp_var_begin[in->n_groups] != in->n_vars)
+    return bad("group prefix arrays do not end at the totals");
+  c->max_read_len = 0, c->max_hap_len = 0;
+  for (int g = 0; g < in->n_groups; ++g) {
+    if (in->grp_hap_begin[g + 1] < in->grp_hap_begin[g] || in->grp_read_begin[g + 1] < in->grp_read_begin[g] ||
+        in->grp_var_begin[g + 1] < in->grp_var_begin[g])
+      return bad("group prefix arrays must be non-decreasing");
+    if (in->grp_read_begin[g + 1] > in->grp_read_begin[g] && in->grp_hap_begin[g + 1] == in->grp_hap_begin[g])
+      return bad("a group with reads needs at least the REF haplotype");
+  }
+  for (int h = 0; h < in->n_haps; ++h) {
+    const int64_t l = in->hap_off[h + 1] - in->hap_off[h];
+    if (l < 0) return bad("hap_off must be non-decreasing");
+    if (l > LGR_MAX_HAP_LEN) return bad("haplotype longer than LGR_MAX_HAP_LEN", LGR_E_LIMIT);
+    c->max_hap_len = std::max<int>(c->max_hap_len, (int)l);
+  }
+  for (int r = 0; r < in->n_reads; ++r) {
+    const int64_t l = in->read_off[r + 1] - in->read_off[r];
+    if (l < 0) return bad("read_off must be non-decreasing");
+    if (l > LGR_MAX_READ_LEN) return bad("read longer than LGR_MAX_READ_LEN", LGR_E_LIMIT);
+    c->max_read_len = std::max<int>(c->max_read_len, (int)l);
+  }
+  // ksw2 band (w = 1.5*bw + 1) must never bind
+  if ((int64_t)c->max_hap_len + c->max_read_len >= (int64_t)(c->prm.bw * 1.5))
+    return bad("haplotype+read length reaches the ksw2 band; unsupported by the device path", LGR_E_LIMIT);
+  for (int v = 0; v < in->n_vars; ++v)
+    if (in->var_hap_off[v + 1] < in->var_hap_off[v]) return bad("var_hap_off must be non-decreasing");
+  return LGR_OK;
+}
+
+#define UP(buf, src, bytes)                                                                              \
+  do {                                                                                                   \
+    if ((rc = ensure(c, c->buf, (bytes))) != LGR_OK) return rc;                                          \
+    if ((bytes) > 0) LGR_CUDA(c, cudaMemcpyAsync(c->buf.p, (src), (bytes), cudaMemcpyHostToDevice, c->stream)); \
+    h2d += (bytes);                                                                                      \
+  } while (0)
+
+static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
+  int rc = validate_batch(c, in);
+  if (rc != LGR_OK) return rc;
+  LGR_CUDA(c, cudaSetDevice(c->device));
+  int64_t h2d = 0;
+  const int G = in->n_groups, NH = in->n_haps, NR = in->n_reads, NV = in->n_vars;
+  // host helper arrays
+  c->h_read_grp.resize(NR + 1), c->h_hap_grp.resize(NH + 1), c->h_pair_off.resize(NR + 1), c->h_asg_off.resize(NR + 1);
+  c->h_grp_mid.resize(G + 1);
+  c->h_item_hap.clear(), c->h_item_r0.clear(), c->h_item_n.clear();
+  int64_t po = 0, ao = 0;
+  for (int g = 0; g < G; ++g) {
+    const int h0 = in->grp_hap_begin[g], h1 = in->grp_hap_begin[g + 1];
+    const int r0 = in->grp_read_begin[g], r1 = in->grp_read_begin[g + 1];
+    const int V = in->grp_var_begin[g + 1] - in->grp_var_begin[g];
+    for (int h = h0; h < h1; ++h) c->h_hap_grp[h] = g;
+    for (int r = r0; r < r1; ++r) {
+      c->h_read_grp[r] = g, c->h_pair_off[r] = po, c->h_asg_off[r] = ao;
+      po += h1 - h0, ao += V;
+    }
+    for (int h = h0; h < h1; ++h)
+      for (int r = r0; r < r1; r += 32) {
+        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(32, r1 - r));
+      }
+    int32_t mid = c->prm.mid_occ;
+    if (in->grp_mid_occ && in->grp_mid_occ[g] > 0) mid = in->grp_mid_occ[g];
+    c->h_grp_mid[g] = mid;
+  }
+  c->h_pair_off[NR] = po, c->h_asg_off[NR] = ao;
+  const int64_t hap_bytes = NH ? in->hap_off[NH] : 0, read_bytes = NR ? in->read_off[NR] : 0;
+  const int64_t nvh = NV ? in->var_hap_off[NV] : 0;
+  c->hap_bytes = hap_bytes, c->read_bytes = read_bytes;
+  UP(b_grp_hap, in->grp_hap_begin, sizeof(int32_t) * (G + 1));
+  UP(b_grp_read, in->grp_read_begin, sizeof(int32_t) * (G + 1));
+  UP(b_grp_var, in->grp_var_begin, sizeof(int32_t) * (G + 1));
+  UP(b_hap_off, in->hap_off, sizeof(int64_t) * (NH + 1));
+  UP(b_read_off, in->read_off, sizeof(int64_t) * (NR + 1));
+  UP(b_var_hap_off, in->var_hap_off, sizeof(int64_t) * (NV + 1));
+  UP(b_hap_bases, in->hap_bases, (size_t)hap_bytes);
+  UP(b_read_bases, in->read_bases, (size_t)read_bytes);
+  UP(b_read_quals, in->read_quals, (size_t)read_bytes);
+  UP(b_name_hash, in->read_name_hash, sizeof(uint32_t) * NR);
+  UP(b_var_start, in->var_start, sizeof(int32_t) * nvh);
+  UP(b_var_len, in->var_len, sizeof(int32_t) * nvh);
+  UP(b_var_allele, in->var_allele, (size_t)nvh);
+  UP(b_read_grp, c->h_read_grp.data(), sizeof(int32_t) * NR);
+  UP(b_hap_grp, c->h_hap_grp.data(), sizeof(int32_t) * NH);
+  UP(b_pair_off, c->h_pair_off.data(), sizeof(int64_t) * (NR + 1));
+  UP(b_asg_off, c->h_asg_off.data(), sizeof(int64_t) * (NR + 1));
+  UP(b_item_hap, c->h_item_hap.data(), sizeof(int32_t) * c->h_item_hap.size());
+  UP(b_item_r0, c->h_item_r0.data(), sizeof(int32_t) * c->h_item_r0.size());
+  UP(b_item_n, c->h_item_n.data(), sizeof(int32_t) * c->h_item_n.size());
+  UP(b_grp_mid, c->h_grp_mid.data(), sizeof(int32_t) * G);
+  // derived / scratch / outputs
+  const int64_t n_pairs = po, n_assign = ao;
+  if ((rc = ensure(c, c->b_hap_codes, hap_bytes)) || (rc = ensure(c, c->b_read_codes, read_bytes)) ||
+      (rc = ensure(c, c->b_idx, sizeof(uint64_t) * hap_bytes)) || (rc = ensure(c, c->b_idx_n, sizeof(int32_t) * NH)) ||
+      (rc = ensure(c, c->b_hap_mid, sizeof(int32_t) * NH)) || (rc = ensure(c, c->b_mz_x, sizeof(uint64_t) * read_bytes)) ||
+      (rc = ensure(c, c->b_mz_y, sizeof(uint32_t) * read_bytes)) || (rc = ensure(c, c->b_mz_n, sizeof(int32_t) * NR)))
+    return rc;
+  c->map_blocks = c->sm_count * 4;
+  const int64_t n_threads = (int64_t)c->map_blocks * 128;
+  const int fin_cap = 2 * c->max_read_len + 16;
+  const int Lm = std::max(c->max_read_len, 1);
+  const int Tmax = Lm + ((c->prm.a + std::max(c->prm.b, c->prm.sc_ambi)) * Lm) / c->prm.e + 2;
+  c->ext_blocks = c->sm_count * 4;
+  const int64_t ext_warps = (int64_t)c->ext_blocks * 4;
+  const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
+  const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
+  const int wcig_cap = 2 * Lm + 8;
+  const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024, defs_cap = n_pairs + 1024, tasks_cap = 2 * regs_cap;
+  const int64_t ext_arena_cap = 4 * n_pairs + (1 << 20);
+  const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
+  if ((rc = ensure(c, c->b_ws, sizeof(int32_t) * (size_t)n_threads * A_COUNT * kCapFast)) ||
+      (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)n_threads * 2 * fin_cap)) ||
+      (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_defs, sizeof(DefRec) * (size_t)defs_cap)) ||
+      (rc = ensure(c, c->b_tasks, sizeof(TaskRec) * (size_t)tasks_cap)) ||
+      (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
+      (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
+      (rc = ensure(c, c->b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
+      (rc = ensure(c, c->b_dir, (size_t)ext_warps * dir_per_warp)) ||
+      (rc = ensure(c, c->b_bnd, sizeof(int32_t) * (size_t)ext_warps * bnd_per_warp)) ||
+      (rc = ensure(c, c->b_wcig, sizeof(uint32_t) * (size_t)ext_warps * wcig_cap)) ||
+      (rc = ensure(c, c->b_aln, sizeof(AlnOut) * (size_t)n_pairs)) ||
+      (rc = ensure(c, c->b_cig_inline, sizeof(uint32_t) * (size_t)n_pairs * LGR_CIGAR_INLINE)) ||
+      (rc = ensure(c, c->b_cig_arena, sizeof(uint32_t) * (size_t)cig_arena_cap)) ||
+      (rc = ensure(c, c->b_assign, sizeof(AssignOut) * (size_t)n_assign)) || (rc = ensure(c, c->b_ctr, sizeof(long long) * C_COUNT)))
+    return rc;
+  Dev& D = c->D;
+  std::memset(&D, 0, sizeof(D));
+  D.P = c->P;
+  D.n_groups = G, D.n_haps = NH, D.n_reads = NR, D.n_vars = NV, D.n_pairs = n_pairs, D.n_assign = n_assign;
+  D.grp_hap_begin = (int32_t*)c->b_grp_hap.p, D.grp_read_begin = (int32_t*)c->b_grp_read.p, D.grp_var_begin = (int32_t*)c->b_grp_var.p;
+  D.hap_off = (int64_t*)c->b_hap_off.p, D.read_off = (int64_t*)c->b_read_off.p, D.var_hap_off = (int64_t*)c->b_var_hap_off.p;
+  D.hap_bases = (uint8_t*)c->b_hap_bases.p, D.read_bases = (uint8_t*)c->b_read_bases.p, D.read_quals = (uint8_t*)c->b_read_quals.p;
+  D.name_hash = (uint32_t*)c->b_name_hash.p;
+  D.var_start = (int32_t*)c->b_var_start.p, D.var_len = (int32_t*)c->b_var_len.p, D.var_allele = (int8_t*)c->b_var_allele.p;
+  D.read_grp = (int32_t*)c->b_read_grp.p, D.hap_grp = (int32_t*)c->b_hap_grp.p;
+  D.pair_off = (int64_t*)c->b_pair_off.p, D.asg_off = (int64_t*)c->b_asg_off.p;
+  D.item_hap = (int32_t*)c->b_item_hap.p, D.item_r0 = (int32_t*)c->b_item_r0.p, D.item_n = (int32_t*)c->b_item_n.p;
+  D.n_items = (int)c->h_item_hap.size();
+  D.hap_codes = (uint8_t*)c->b_hap_codes.p, D.read_codes = (uint8_t*)c->b_read_codes.p;
+  D.idx = (uint64_t*)c->b_idx.p, D.idx_n = (int32_t*)c->b_idx_n.p, D.hap_mid = (int32_t*)c->b_hap_mid.p;
+  D.grp_mid = (int32_t*)c->b_grp_mid.p;
+  D.mz_x = (uint64_t*)c->b_mz_x.p, D.mz_y = (uint32_t*)c->b_mz_y.p, D.mz_n = (int32_t*)c->b_mz_n.p;
+  D.ws = (int32_t*)c->b_ws.p, D.ws_cap = kCapFast;
+  D.fin_scratch = (uint32_t*)c->b_fin.p, D.fin_cap = fin_cap;
+  D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
+  D.defs = (DefRec*)c->b_defs.p, D.defs_cap = defs_cap;
+  D.tasks = (TaskRec*)c->b_tasks.p, D.tasks_cap = tasks_cap;
+  D.ext_arena = (uint32_t*)c->b_ext_arena.p, D.ext_arena_cap = ext_arena_cap;
+  D.ovf_read = (int32_t*)c->b_ovf_read.p, D.ovf_hap = (int32_t*)c->b_ovf_hap.p, D.ovf_cap = n_pairs;
+  D.dir_scratch = (uint8_t*)c->b_dir.p, D.dir_per_warp = dir_per_warp;
+  D.bnd_scratch = (int32_t*)c->b_bnd.p, D.bnd_per_warp = bnd_per_warp;
+  D.wcig_scratch = (uint32_t*)c->b_wcig.p, D.wcig_cap = wcig_cap;
+  D.aln = (AlnOut*)c->b_aln.p, D.cigar_inline = (uint32_t*)c->b_cig_inline.p, D.cigar_arena = (uint32_t*)c->b_cig_arena.p;
+  D.cigar_arena_cap = cig_arena_cap;
+  D.assign = (AssignOut*)c->b_assign.p;
+  D.ctr = (long long*)c->b_ctr.p;
+  c->resident = true;
+  if (h2d_bytes) *h2d_bytes = h2d;
+  return LGR_OK;
+}
+
+static int run_impl(lgr_ctx* c, lgr_stats* st) {
+  if (!c->resident) { c->err = "no batch uploaded"; return LGR_E_ARG; }
+  LGR_CUDA(c, cudaSetDevice(c->device));
+  Dev& D = c->D;
+  cudaStream_t s = c->stream;
+  int launches = 0;
+  // the group mid_occ array is an in/out: restore the requested values before every run
+  if (D.n_groups > 0)
+    LGR_CUDA(c, cudaMemcpyAsync(D.grp_mid, c->h_grp_mid.data(), sizeof(int32_t) * D.n_groups, cudaMemcpyHostToDevice, s));
+  LGR_CUDA(c, cudaMemsetAsync(D.ctr, 0, sizeof(long long) * C_COUNT, s));
+  cudaEventRecord(c->ev[0], s);
+  const int64_t hb = c->hap_bytes, rb = c->read_bytes;
+  if (D.n_pairs > 0) {
+    const int enc_blocks = c->sm_count * 8;
+    k_encode<<<enc_blocks, 256, 0, s>>>(D.hap_bases, D.hap_codes, hb);
+    k_encode<<<enc_blocks, 256, 0, s>>>(D.read_bases, D.read_codes, rb);
+    k_hap_sketch<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D);
+    k_hap_sort<<<D.n_haps, 128, 2048 * sizeof(uint64_t), s>>>(D);
+    k_hap_mid<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
+    k_group_mid<<<(D.n_groups + 127) / 128, 128, 0, s>>>(D, c->prm.min_mid_occ);
+    launches += 6;
+    cudaEventRecord(c->ev[1], s);
+    k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
+    launches += 1;
+    cudaEventRecord(c->ev[2], s);
+    k_map<false><<<c->map_blocks, 128, 0, s>>>(D);
+    launches += 1;
+    long long hctr[C_COUNT];
+    LGR_CUDA(c, cudaMemcpyAsync(hctr, D.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
+    LGR_CUDA(c, cudaStreamSynchronize(s));
+    if (hctr[C_NOVF] > 0) {
+      // overflow pass: same kernel, larger per-lane workspace, few warps
+      const int big_blocks = kBigWarps / 4;
+      int rc = ensure(c, c->b_ws_big, sizeof(int32_t) * (size_t)big_blocks * 128 * A_COUNT * kCapBig);
+      if (rc != LGR_OK) return rc;
+      Dev D2 = D;
+      D2.ws = (int32_t*)c->b_ws_big.p, D2.ws_cap = kCapBig;
+      k_map<true><<<big_blocks, 128, 0, s>>>(D2);
+      launches += 1;
+      LGR_CUDA(c, cudaMemcpyAsync(hctr, D.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
+      LGR_CUDA(c, cudaStreamSynchronize(s));
+    }
+    if (hctr[C_NTASK] > 0) {
+      k_ext_big<<<c->ext_blocks, 128, 0, s>>>(D);
+      launches += 1;
+    }
+    if (hctr[C_NDEF] > 0) {
+      const int fb = (int)std::min<long long>((hctr[C_NDEF] + 127) / 128, c->map_blocks);
+      k_finish<<<fb, 128, 0, s>>>(D);
+      launches += 1;
+    }
+    cudaEventRecord(c->ev[3], s);
+    if (D.n_assign > 0) {
+      k_assign<<<(unsigned)((D.n_assign + 127) / 128), 128, 0, s>>>(D);
+      launches += 1;
+    }
+  } else {
+    cudaEventRecord(c->ev[1], s), cudaEventRecord(c->ev[2], s), cudaEventRecord(c->ev[3], s);
+  }
+  cudaEventRecord(c->ev[4], s);
+  long long hctr[C_COUNT];
+  LGR_CUDA(c, cudaMemcpyAsync(hctr, D.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
+  LGR_CUDA(c, cudaStreamSynchronize(s));
+  LGR_CUDA(c, cudaGetLastError());
+  if (st) {
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); st->ms_kernels = ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); st->ms_k_index = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); st->ms_k_sketch = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); st->ms_k_map = ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); st->ms_k_assign = ms;
+    st->n_pairs = D.n_pairs, st->n_aligned = hctr[C_ALIGNED];
+    st->dp_cells = hctr[C_CELLS], st->dp_cells_full = hctr[C_CELLSFULL];
+    st->chain_evals = hctr[C_EVALS], st->n_anchors = hctr[C_ANCH];
+    st->kernel_launches = launches;
+  }
+  if (hctr[C_ERR]) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "device path limit hit (flags 0x%llx: 1 reg arena, 2 ext arena, 4 cigar arena, 8 anchor cap, 16 cigar scratch, 32 minimizer cap)",
+             hctr[C_ERR]);
+    c->err = buf;
+    return (hctr[C_ERR] == E_CIG_ARENA) ? LGR_E_CIGAR_OVERFLOW : LGR_E_LIMIT;
+  }
+  return LGR_OK;
+}
+
+static int download_impl(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
+  if (!c->resident || !out) { c->err = "nothing to download"; return LGR_E_ARG; }
+  LGR_CUDA(c, cudaSetDevice(c->device));
+  Dev& D = c->D;
+  int64_t d2h = 0;
+  if (out->aln) {
+    if (out->n_pairs < D.n_pairs) { c->err = "out->n_pairs too small"; return LGR_E_ARG; }
+    LGR_CUDA(c, cudaMemcpyAsync(out->aln, D.aln, sizeof(AlnOut) * D.n_pairs, cudaMemcpyDeviceToHost, c->stream));
+    d2h += sizeof(AlnOut) * D.n_pairs;
+    if (out->cigar_inline) {
+      LGR_CUDA(c, cudaMemcpyAsync(out->cigar_inline, D.cigar_inline, sizeof(uint32_t) * D.n_pairs * LGR_CIGAR_INLINE, cudaMemcpyDeviceToHost, c->stream));
+      d2h += sizeof(uint32_t) * D.n_pairs * LGR_CIGAR_INLINE;
+    }
+    long long used = 0;
+    LGR_CUDA(c, cudaMemcpyAsync(&used, D.ctr + C_CIGARENA, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    LGR_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->cigar_arena_used = used;
+    if (used > 0) {
+      if (!out->cigar_arena || out->cigar_arena_cap < used) { c->err = "host cigar arena too small"; return LGR_E_CIGAR_OVERFLOW; }
+      LGR_CUDA(c, cudaMemcpyAsync(out->cigar_arena, D.cigar_arena, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost, c->stream));
+      d2h += sizeof(uint32_t) * used;
+    }
+  }
+  if (out->assign && D.n_assign > 0) {
+    if (out->n_assign < D.n_assign) { c->err = "out->n_assign too small"; return LGR_E_ARG; }
+    LGR_CUDA(c, cudaMemcpyAsync(out->assign, D.assign, sizeof(AssignOut) * D.n_assign, cudaMemcpyDeviceToHost, c->stream));
+    d2h += sizeof(AssignOut) * D.n_assign;
+  }
+  LGR_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (d2h_bytes) *d2h_bytes = d2h;
+  return LGR_OK;
+}
+
+int lgr_upload(lgr_ctx* c, const lgr_batch_in* in) {
+  if (!c) return LGR_E_ARG;
+  int rc = upload_impl(c, in, nullptr);
+  if (rc == LGR_OK) LGR_CUDA(c, cudaStreamSynchronize(c->stream));
+  return rc;
+}
+
+int lgr_run_resident(lgr_ctx* c, lgr_stats* stats) {
+  if (!c) return LGR_E_ARG;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  return run_impl(c, stats);
+}
+
+int lgr_download(lgr_ctx* c, lgr_batch_out* out) {
+  if (!c) return LGR_E_ARG;
+  return download_impl(c, out, nullptr);
+}
+
+int lgr_genotype_batch(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_stats* stats) {
+  if (!c || !in || !out) return LGR_E_ARG;
+  lgr_stats st;
+  std::memset(&st, 0, sizeof(st));
+  int64_t h2d = 0, d2h = 0;
+  cudaEventRecord(c->ev[5], c->stream);
+  int rc = upload_impl(c, in, &h2d);
+  if (rc != LGR_OK) return rc;
+  cudaEventRecord(c->ev[6], c->stream);
+  rc = run_impl(c, &st);
+  if (rc != LGR_OK && rc != LGR_E_LIMIT && rc != LGR_E_CIGAR_OVERFLOW) return rc;
+  const int run_rc = rc;
+  cudaEventRecord(c->ev[7], c->stream);
+  rc = download_impl(c, out, &d2h);
+  cudaEventRecord(c->ev[8], c->stream);
+  cudaStreamSynchronize(c->stream);
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); st.ms_h2d = ms;
+  cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); st.ms_d2h = ms;
+  st.h2d_bytes = h2d, st.d2h_bytes = d2h;
+  if (stats) *stats = st;
+  return run_rc != LGR_OK ? run_rc : rc;
+}
+
+int lgr_hap_mid_occ(lgr_ctx* c, const uint8_t* hap, int32_t hap_len, int32_t* mid_occ) {
+  if (!c || !hap || hap_len < 0 || !mid_occ) return LGR_E_ARG;
+  if (hap_len > LGR_MAX_HAP_LEN) { c->err = "haplotype longer than LGR_MAX_HAP_LEN"; return LGR_E_LIMIT; }
+  // a one-haplotype, zero-read batch through the index kernels
+  const int32_t gb[2] = {0, 1}, zero2[2] = {0, 0};
+  const int64_t ho[2] = {0, hap_len}, ro[1] = {0}, vo[1] = {0};
+  lgr_batch_in in;
+  std::memset(&in, 0, sizeof(in));
+  in.n_groups = 1, in.n_haps = 1, in.n_reads = 0, in.n_vars = 0;
+  in.grp_hap_begin = gb, in.grp_read_begin = zero2, in.grp_var_begin = zero2;
+  in.hap_off = ho, in.hap_bases = hap, in.read_off = ro, in.var_hap_off = vo;
+  int rc = upload_impl(c, &in, nullptr);
+  if (rc != LGR_OK) return rc;
+  Dev& D = c->D;
+  cudaStream_t s = c->stream;
+  LGR_CUDA(c, cudaMemsetAsync(D.ctr, 0, sizeof(long long) * C_COUNT, s));
+  k_encode<<<8, 256, 0, s>>>(D.hap_bases, D.hap_codes, hap_len);
+  k_hap_sketch<<<1, 64, 0, s>>>(D);
+  k_hap_sort<<<1, 128, 2048 * sizeof(uint64_t), s>>>(D);
+  k_hap_mid<<<1, 64, 0, s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
+  LGR_CUDA(c, cudaMemcpyAsync(mid_occ, D.hap_mid, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  LGR_CUDA(c, cudaStreamSynchronize(s));
+  LGR_CUDA(c, cudaGetLastError());
+  c->resident = false;
+  return LGR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""Host-side handle on the CUDA realignment library (C-ABI in include/lancet_gpu_realign.h).
+
+`GpuRealigner` owns one `lgr_ctx` (one GPU, one stream).  It mirrors what one
+`lancet::caller::Genotyper` instance does for its worker thread (reference:
+src/lancet/caller/genotyper.h:213-220) but over batches of `Genotype()` payloads.
+No CPU path exists: construction raises when the library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+from . import abi
+
+
+class LgrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lgr error {code}: {msg}")
+        self.code = code
+
+
+class GpuRealigner:
+    def __init__(self, device: int = 0, params: Optional[abi.LgrParams] = None, lib_path: Optional[str] = None):
+        self.lib = abi.load_library(lib_path)
+        if self.lib.lgr_abi_version() != 1:
+            raise RuntimeError("ABI version mismatch")
+        if params is None:
+            params = abi.LgrParams()
+            self.lib.lgr_default_params(C.byref(params))
+        self.params = params
+        self._ctx = C.c_void_p()
+        rc = self.lib.lgr_create(device, C.byref(params), C.byref(self._ctx))
+        if rc != 0:
+            raise LgrError(rc, (self.lib.lgr_last_error(None) or b"").decode() or self.lib.lgr_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.lgr_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise LgrError(rc, (self.lib.lgr_last_error(self._ctx) or b"").decode() or self.lib.lgr_strerror(rc).decode())
+
+    def hap_mid_occ(self, hap: bytes) -> int:
+        out = C.c_int32(0)
+        self._check(self.lib.lgr_hap_mid_occ(self._ctx, hap, len(hap), C.byref(out)))
+        return out.value
+
+    def genotype_batch(self, batch: abi.Batch, result: Optional[abi.Result] = None, want_aln: bool = True,
+                       arena: int = 1 << 20) -> Tuple[abi.Result, abi.LgrStats]:
+        """H2D + kernels + D2H through `lgr_genotype_batch` (the call a Genotyper adapter makes)."""
+        res = result or abi.Result(batch, arena)
+        bi, bo = batch.c_struct(), res.c_struct()
+        if not want_aln:
+            bo.aln = None
+            bo.cigar_inline = None
+        st = abi.LgrStats()
+        self._check(self.lib.lgr_genotype_batch(self._ctx, C.byref(bi), C.byref(bo), C.byref(st)))
+        return res, st
+
+    def upload(self, batch: abi.Batch):
+        bi = batch.c_struct()
+        self._check(self.lib.lgr_upload(self._ctx, C.byref(bi)))
+
+    def run_resident(self) -> abi.LgrStats:
+        st = abi.LgrStats()
+        self._check(self.lib.lgr_run_resident(self._ctx, C.byref(st)))
+        return st
+
+    def download(self, batch: abi.Batch, result: Optional[abi.Result] = None, arena: int = 1 << 20) -> abi.Result:
+        res = result or abi.Result(batch, arena)
+        bo = res.c_struct()
+        self._check(self.lib.lgr_download(self._ctx, C.byref(bo)))
+        return res
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.lgr_stream(self._ctx) or 0)
