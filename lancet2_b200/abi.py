@@ -64,7 +64,7 @@ class LgrStats(C.Structure):
     _fields_ = [
         ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float),
         ("ms_k_index", C.c_float), ("ms_k_sketch", C.c_float), ("ms_k_map", C.c_float),
-        ("ms_k_assign", C.c_float),
+        ("ms_k_ext", C.c_float), ("ms_k_assign", C.c_float),
         ("n_pairs", C.c_int64), ("n_aligned", C.c_int64),
         ("dp_cells", C.c_int64), ("dp_cells_full", C.c_int64),
         ("chain_evals", C.c_int64), ("n_anchors", C.c_int64),

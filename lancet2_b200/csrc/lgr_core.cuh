@@ -41,8 +41,9 @@ struct DevParams {
   int32_t min_strand_sc;  // (int)(max_gap * 0.8)
 };
 
-constexpr int kSmallM = 12;                 // extension tails up to this many query bases run inline
-constexpr int kSmallCells = 512;            // ... and at most this many (pruned) DP cells
+constexpr int kSmallCells = 512;            // extension tails with at most this many (pruned) DP cells run inline
+constexpr int kSmallDim = 22;               // floor(sqrt(kSmallCells)): bound of min(m, T) for such a tail
+constexpr int kSmallCig = 96;               // cigar runs of such a tail (<= 4*min(m,T)+1; overflow is flagged)
 constexpr int kInlineCig = 6;               // cigar ops kept inline in an ExtRec
 constexpr int kMaxWindow = 32;              // minimizer window cap (reference uses w = 5)
 constexpr int32_t kNegInf = -0x40000000;
@@ -458,49 +459,87 @@ struct CigBuf {          // run-length cigar builder (ksw_push_cigar semantics)
   }
 };
 
+// One cell of the recurrence (shared by both sweep orders and by the warp kernel's lanes
+// in spirit): returns H, writes the direction byte and the E/F values flowing right/down.
+LGR_HD int32_t ext_cell(int32_t hd, int32_t ee, int32_t f, int q, int e, bool right, uint8_t* dout, int32_t* e_next,
+                        int32_t* f_next) {
+  int32_t h;
+  uint8_t d;
+  if (!right) {
+    d = ee > hd ? 1 : 0;
+    h = ee > hd ? ee : hd;
+    if (f > h) d = 2, h = f;
+  } else {
+    d = hd > ee ? 0 : 1;
+    h = hd > ee ? hd : ee;
+    if (!(h > f)) d = 2, h = f;
+  }
+  const int32_t ho = h - q;
+  if (!right) {
+    if (ee > ho) d |= 0x08;
+    if (f > ho) d |= 0x10;
+  } else {
+    if (ee >= ho) d |= 0x08;
+    if (f >= ho) d |= 0x10;
+  }
+  *dout = d;
+  *e_next = (ee > ho ? ee : ho) - e;
+  *f_next = (f > ho ? f : ho) - e;
+  return h;
+}
+
+// ha/fa: scratch of min(m, T) ints each.  The sweep keeps its line buffers over the
+// SHORTER dimension (reads overhanging a haplotype end give m ~ 100, T ~ 3), the values
+// are independent of the sweep order.
 template <typename QF, typename TF>
 LGR_HD void ext_dp_scalar(const DevParams& P, int m, int T, QF qf, TF tf, bool right, uint8_t* dir,
-                          int32_t* hcol, int32_t* ecol, int32_t* out_max, int32_t* out_mqe_t) {
+                          int32_t* ha, int32_t* fa, int32_t* out_max, int32_t* out_mqe_t) {
   const int q = P.q, e = P.e;
-  for (int j = 0; j < m; ++j) {
-    hcol[j] = -(q + e * (j + 1));
-    ecol[j] = hcol[j] - q - e;
-  }
   int32_t ezmax = 0, mqe = kNegInf, mqe_t = -1;
-  for (int i = 0; i < T; ++i) {
-    int32_t hdiag = i == 0 ? 0 : -(q + e * i);
-    int32_t f = -(q + e * (i + 1)) - q - e;
-    const int tc = tf(i);
+  if (m <= T) {
+    // target-major: ha[j] = H(i-1, j), fa[j] = E(i, j) (flows along the target)
     for (int j = 0; j < m; ++j) {
-      const int32_t hd = hdiag + sub_score(P, tc, qf(j));
-      const int32_t ee = ecol[j];
-      int32_t h;
-      uint8_t d;
-      if (!right) {
-        d = ee > hd ? 1 : 0;
-        h = ee > hd ? ee : hd;
-        if (f > h) d = 2, h = f;
-      } else {
-        d = hd > ee ? 0 : 1;
-        h = hd > ee ? hd : ee;
-        if (!(h > f)) d = 2, h = f;
-      }
-      const int32_t ho = h - q;
-      if (!right) {
-        if (ee > ho) d |= 0x08;
-        if (f > ho) d |= 0x10;
-      } else {
-        if (ee >= ho) d |= 0x08;
-        if (f >= ho) d |= 0x10;
-      }
-      dir[i * m + j] = d;
-      hdiag = hcol[j];
-      hcol[j] = h;
-      ecol[j] = (ee > ho ? ee : ho) - e;
-      f = (f > ho ? f : ho) - e;
-      if (h > ezmax) ezmax = h;
+      ha[j] = -(q + e * (j + 1));
+      fa[j] = ha[j] - q - e;
     }
-    if (hcol[m - 1] > mqe) mqe = hcol[m - 1], mqe_t = i;
+    for (int i = 0; i < T; ++i) {
+      int32_t hdiag = i == 0 ? 0 : -(q + e * i);
+      int32_t f = -(q + e * (i + 1)) - q - e;
+      const int tc = tf(i);
+      for (int j = 0; j < m; ++j) {
+        const int32_t hd = hdiag + sub_score(P, tc, qf(j));
+        int32_t en, fn;
+        const int32_t h = ext_cell(hd, fa[j], f, q, e, right, &dir[i * m + j], &en, &fn);
+        hdiag = ha[j];
+        ha[j] = h;
+        fa[j] = en;
+        f = fn;
+        if (h > ezmax) ezmax = h;
+      }
+      if (ha[m - 1] > mqe) mqe = ha[m - 1], mqe_t = i;
+    }
+  } else {
+    // query-major: ha[i] = H(i, j-1), fa[i] = F(i, j) (flows along the query)
+    for (int i = 0; i < T; ++i) {
+      ha[i] = -(q + e * (i + 1));
+      fa[i] = ha[i] - q - e;
+    }
+    for (int j = 0; j < m; ++j) {
+      int32_t hdiag = j == 0 ? 0 : -(q + e * j);
+      int32_t ee = -(q + e * (j + 1)) - q - e;
+      const int qc = qf(j);
+      for (int i = 0; i < T; ++i) {
+        const int32_t hd = hdiag + sub_score(P, tf(i), qc);
+        int32_t en, fn;
+        const int32_t h = ext_cell(hd, ee, fa[i], q, e, right, &dir[i * m + j], &en, &fn);
+        hdiag = ha[i];
+        ha[i] = h;
+        ee = en;
+        fa[i] = fn;
+        if (h > ezmax) ezmax = h;
+        if (j == m - 1 && h > mqe) mqe = h, mqe_t = i;
+      }
+    }
   }
   *out_max = ezmax;
   *out_mqe_t = mqe_t;
@@ -1025,7 +1064,7 @@ LGR_HD void export_reg(const Ws<S>& ws, int r, int qlen, RegRec* out) {
 // does this extension run inline in the pair's lane (true) or on a warp (k_ext_big)?
 LGR_HD bool ext_is_small(const DevParams& P, const ExtRec& E) {
   if (E.m <= 0) return true;
-  return E.m <= kSmallM && E.m * prune_cols(P, E.m, E.n) <= kSmallCells;
+  return (int64_t)E.m * prune_cols(P, E.m, E.n) <= kSmallCells;
 }
 
 // query / target accessors of an extension, as align.c presents them to ksw2

@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(128) k_map(Dev D) {
           }
         }
         uint8_t dir[kSmallCells];
-        int32_t hcol[kSmallM], ecol[kSmallM];
-        uint32_t cig_tmp[2 * kSmallM + 4];
+        int32_t hcol[kSmallDim + 2], ecol[kSmallDim + 2];
+        uint32_t cig_tmp[kSmallCig];
         auto alloc_ext = [&](int n) -> int64_t {
           const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)n);
           if (o + n > D.ext_arena_cap) {
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) k_map(Dev D) {
           for (int i = 0; i < n_regs; ++i)
             for (int side = 0; side < 2; ++side)
               if (loc[i].ext[side].m > 0)
-                ok &= run_ext_scalar(D.P, rv, hapc, &loc[i], side, dir, hcol, ecol, cig_tmp, 2 * kSmallM + 4, D.ext_arena,
+                ok &= run_ext_scalar(D.P, rv, hapc, &loc[i], side, dir, hcol, ecol, cig_tmp, kSmallCig, D.ext_arena,
                                      alloc_ext, &ctr);
           FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
           AlnOut ao;
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(128) k_map(Dev D) {
                 const int m = rr.ext[side].m;
                 if (m <= 0) continue;
                 if (ext_is_small(D.P, rr.ext[side])) {
-                  run_ext_scalar(D.P, rv, hapc, &rr, side, dir, hcol, ecol, cig_tmp, 2 * kSmallM + 4, D.ext_arena, alloc_ext, &ctr);
+                  run_ext_scalar(D.P, rv, hapc, &rr, side, dir, hcol, ecol, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, &ctr);
                 } else {
                   const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
                   if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
@@ -968,6 +968,7 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     cudaEventRecord(c->ev[2], s);
     k_map<false><<<c->map_blocks, 128, 0, s>>>(D);
     launches += 1;
+    cudaEventRecord(c->ev[9], s);
     long long hctr[C_COUNT];
     LGR_CUDA(c, cudaMemcpyAsync(hctr, D.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
     LGR_CUDA(c, cudaStreamSynchronize(s));
@@ -998,7 +999,7 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
       launches += 1;
     }
   } else {
-    cudaEventRecord(c->ev[1], s), cudaEventRecord(c->ev[2], s), cudaEventRecord(c->ev[3], s);
+    cudaEventRecord(c->ev[1], s), cudaEventRecord(c->ev[2], s), cudaEventRecord(c->ev[9], s), cudaEventRecord(c->ev[3], s);
   }
   cudaEventRecord(c->ev[4], s);
   long long hctr[C_COUNT];
@@ -1010,7 +1011,8 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); st->ms_kernels = ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); st->ms_k_index = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); st->ms_k_sketch = ms;
-    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); st->ms_k_map = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[9]); st->ms_k_map = ms;
+    cudaEventElapsedTime(&ms, c->ev[9], c->ev[3]); st->ms_k_ext = ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); st->ms_k_assign = ms;
     st->n_pairs = D.n_pairs, st->n_aligned = hctr[C_ALIGNED];
     st->dp_cells = hctr[C_CELLS], st->dp_cells_full = hctr[C_CELLSFULL];

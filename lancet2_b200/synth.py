@@ -101,3 +101,137 @@ def make_group(rng: np.random.Generator, read_len: int = 150, hap_len: int = 100
 def make_groups(seed: int, n_groups: int, **kw) -> List[Group]:
     rng = np.random.default_rng(seed)
     return [make_group(rng, name_prefix=f"g{g}r", **kw) for g in range(n_groups)]
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE.json config 2: "synthetic 30x/30x tumor-normal 2x150bp reads over a 1 Mb
+# synthetic reference with spiked SNVs/InDels".  Graph assembly / SPOA stay host code in the
+# reference and are out of scope here, so this generator emits what they would hand to
+# Genotyper::Genotype for every 1000 bp window (step 800, core/window_builder.h:19-38) that
+# contains a variant: the window's REF haplotype, one ALT haplotype per spiked variant (plus
+# the all-variants haplotype when a window holds several), every tumor/normal read that
+# overlaps the window in ReadCollector order (normal before tumor, then qname), and the
+# per-haplotype variant bounds.
+# --------------------------------------------------------------------------------------
+def make_region_groups(seed: int = 42, ref_len: int = 1_000_000, cov_normal: float = 30.0, cov_tumor: float = 30.0,
+                       read_len: int = 150, window: int = 1000, step: int = 800, var_every: int = 2000,
+                       sub_err: float = 0.002, max_groups: int = 0) -> List[Group]:
+    rng = np.random.default_rng(seed)
+    ref = _rand_bases(rng, ref_len)
+    # ---- spiked variants (sorted, spaced so that they never overlap) ----
+    n_var = max(1, ref_len // var_every)
+    pos = np.sort(rng.choice(np.arange(400, ref_len - 800, 400), size=min(n_var, (ref_len - 1200) // 400), replace=False))
+    pos = pos + rng.integers(0, 50, size=pos.size)
+    variants = []  # (pos, ref_allele bytes, alt_allele bytes, vaf_normal, vaf_tumor)
+    for p in pos.tolist():
+        u = rng.random()
+        if u < 0.70:
+            alt_b = _ACGT[(int(np.where(_ACGT == ref[p])[0][0]) + int(rng.integers(1, 4))) % 4]
+            ra, aa = ref[p:p + 1].tobytes(), bytes([alt_b])
+        else:
+            ln = int(rng.integers(1, 21)) if u < 0.90 else int(rng.integers(21, 301))
+            if rng.random() < 0.5:
+                ra, aa = ref[p:p + 1].tobytes(), ref[p:p + 1].tobytes() + _rand_bases(rng, ln).tobytes()
+            else:
+                ra, aa = ref[p:p + 1 + ln].tobytes(), ref[p:p + 1].tobytes()
+        c = rng.random()
+        if c < 0.5:
+            vn, vt = 0.0, float(rng.choice([0.05, 0.1, 0.25, 0.5]))
+        elif c < 0.8:
+            vn = vt = 0.5
+        else:
+            vn = vt = 1.0
+        variants.append((p, ra, aa, vn, vt))
+    vpos = np.asarray([v[0] for v in variants], dtype=np.int64)
+
+    # ---- reads ----
+    def sample_reads(cov, is_tumor, tag):
+        n_frag = int(cov * ref_len / (2 * read_len))
+        ins = np.clip(rng.normal(400, 50, n_frag).astype(np.int64), 2 * read_len // 2 + 20, 800)
+        fs = rng.integers(0, ref_len - 900, size=n_frag)
+        starts = np.concatenate([fs, fs + ins - read_len])
+        frag_id = np.concatenate([np.arange(n_frag), np.arange(n_frag)])
+        idx = starts[:, None] + np.arange(read_len)[None, :]
+        seqs = ref[idx]
+        # reads spanning a variant: rebuild from the mutated sequence with probability VAF
+        lo = np.searchsorted(vpos, starts - 301, side="left")
+        hi = np.searchsorted(vpos, starts + read_len, side="left")
+        for i in np.nonzero(hi > lo)[0].tolist():
+            s = int(starts[i])
+            out, cur = [], s
+            need = read_len
+            for k in range(int(lo[i]), int(hi[i])):
+                p, ra, aa, vn, vt = variants[k]
+                vaf = vt if is_tumor else vn
+                if p + len(ra) <= cur or rng.random() >= vaf:
+                    continue
+                if p < cur:  # read starts inside the ref allele: skip the variant
+                    continue
+                out.append(ref[cur:p].tobytes())
+                out.append(aa)
+                cur = p + len(ra)
+                if sum(map(len, out)) >= need:
+                    break
+            got = b"".join(out)
+            if len(got) < need:
+                got += ref[cur:cur + need - len(got)].tobytes()
+            seqs[i] = np.frombuffer(got[:need], dtype=np.uint8)
+        err = rng.random(seqs.shape) < sub_err
+        seqs[err] = _ACGT[rng.integers(0, 4, size=int(err.sum()))]
+        quals = _QV[rng.choice(3, size=seqs.shape, p=_QP)]
+        names = np.asarray([f"{tag}{f:07d}" for f in frag_id.tolist()])
+        return starts, seqs, quals, names
+
+    samples = [sample_reads(cov_normal, False, "n"), sample_reads(cov_tumor, True, "t")]
+    order = [np.argsort(s[0], kind="stable") for s in samples]
+
+    groups: List[Group] = []
+    for w0 in range(0, ref_len - window + 1, step):
+        k0, k1 = np.searchsorted(vpos, w0 + 50), np.searchsorted(vpos, w0 + window - 50 - 301)
+        if k1 <= k0:
+            continue
+        wv = [variants[k] for k in range(k0, k1)]
+        wv = [v for v in wv if v[0] + len(v[1]) < w0 + window - 20]
+        if not wv:
+            continue
+        ref_hap = ref[w0:w0 + window].tobytes()
+        hap_sets = [[i] for i in range(len(wv))]
+        if len(wv) > 1:
+            hap_sets.append(list(range(len(wv))))
+        haps = [ref_hap]
+        shifts = []  # per alt hap: dict variant index -> start on that hap
+        for hs in hap_sets:
+            out, cur, sh, starts_on_hap = [], 0, 0, {}
+            for vi in hs:
+                p, ra, aa, _, _ = wv[vi]
+                lp = p - w0
+                out.append(ref_hap[cur:lp])
+                starts_on_hap[vi] = lp + sh
+                out.append(aa)
+                cur = lp + len(ra)
+                sh += len(aa) - len(ra)
+            out.append(ref_hap[cur:])
+            haps.append(b"".join(out))
+            shifts.append(starts_on_hap)
+        rows = []
+        for vi, (p, ra, aa, _, _) in enumerate(wv):
+            row = [(-1, 0, -1)] * len(haps)
+            row[0] = (p - w0, len(ra), 0)
+            for hi_, soh in enumerate(shifts):
+                if vi in soh:
+                    row[hi_ + 1] = (soh[vi], len(aa), 1)
+            rows.append(row)
+        reads, quals, names = [], [], []
+        for (starts, seqs, qv, nm), od in zip(samples, order):
+            ss = starts[od]
+            a, b = np.searchsorted(ss, w0 - read_len + 1), np.searchsorted(ss, w0 + window)
+            sel = od[a:b]
+            sel = sel[np.argsort(nm[sel], kind="stable")]
+            for i in sel.tolist():
+                reads.append(seqs[i].tobytes())
+                quals.append(qv[i].tobytes())
+                names.append(str(nm[i]))
+        groups.append(Group(haps=haps, reads=reads, quals=quals, names=names, variants=rows))
+        if max_groups and len(groups) >= max_groups:
+            break
+    return groups

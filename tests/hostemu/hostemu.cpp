@@ -93,7 +93,7 @@ extern "C" int emu_genotype_batch(const lgr_params* prm, const lgr_batch_in* in,
               if (E.m <= 0) continue;
               const int T = prune_cols(P, E.m, E.n);
               std::vector<uint8_t> dir((size_t)E.m * T);
-              std::vector<int32_t> hcol(E.m), ecol(E.m);
+              std::vector<int32_t> hcol(std::max(E.m, T) + 1), ecol(std::max(E.m, T) + 1);
               std::vector<uint32_t> tmp(2 * E.m + 4);
               if (!run_ext_scalar(P, rv, hc, &regs[i], side, dir.data(), hcol.data(), ecol.data(), tmp.data(),
                                   (int)tmp.size(), ext_arena.data(), alloc, &ctr))
