@@ -615,49 +615,14 @@ LGR_HD int idx_lower_bound(const uint64_t* idx, int n, uint64_t key) {
 
 constexpr int kIdxShift = 17;  // bits of (pos<<1|strand) below the hash in the table
 
-// status codes of map_chain_phase
-enum { kMapNoHit = 0, kMapOk = 1, kMapOverflow = -1 };
-
 // ------------------------------------------------------------------------------------
-// Phase A: seeds → anchors → sort → chain DP → backtrack → regs → parent/sub selection
-// → per-reg SR stretch + extension windows.  On return (kMapOk) the surviving regs are
-// in the R_* arrays [0, *n_regs) and the per-reg stretch in R_AUX*/A_* as documented
-// at the end.  Restates minimap2 map.c:mm_map_frag up to (not including) the ksw2 calls.
+// seed.c: mm_seed_select — called only when some seed occurs more than mid_occ times.
+// seedq packs q_pos (pos<<1|strand, 20 bits) | span<<20 | tandem<<28 | flt<<29.
 // ------------------------------------------------------------------------------------
-template <int S>
-LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& ws, RadixScratch* rsx,
-                            int* n_regs_out, ChainCounters* ctr) {
-  const int cap = ws.cap;
-  auto ax = ws.arr(A_AX), ay = ws.arr(A_AY), sx = ws.arr(A_SX), sy = ws.arr(A_SY);
-  auto f = ws.arr(A_F), p = ws.arr(A_P), t = ws.arr(A_T), v = ws.arr(A_V), z = ws.arr(A_Z);
-  auto perm = ws.arr(A_PERM);
-  auto seedq = ws.arr(A_SEEDQ), seedn = ws.arr(A_SEEDN), seeds = ws.arr(A_SEEDS);
-  const int qlen = in.read.qlen;
-  *n_regs_out = 0;
-
-  // ---- seed.c: mm_seed_collect_all -------------------------------------------------
-  // seedq: q_pos (pos<<1|strand) | span<<20 | tandem<<28 | flt<<29 ; seedn: occurrences ;
-  // seeds: first index in the table
-  int n_m = 0, n_high = 0;
-  for (int i = 0; i < in.mz_n; ++i) {
-    const uint64_t hx = in.mz_x[i] >> 8;
-    const int s0 = idx_lower_bound(in.idx, in.idx_n, hx << kIdxShift);
-    const int s1 = idx_lower_bound(in.idx, in.idx_n, (hx + 1) << kIdxShift);
-    const int occ = s1 - s0;
-    if (occ == 0) continue;
-    if (n_m >= cap) return kMapOverflow;
-    uint32_t tandem = 0;
-    if (i > 0 && hx == in.mz_x[i - 1] >> 8) tandem = 1;
-    if (i < in.mz_n - 1 && hx == in.mz_x[i + 1] >> 8) tandem = 1;
-    seedq[n_m] = (int32_t)(in.mz_y[i] | (uint32_t)(in.mz_x[i] & 0xff) << 20 | tandem << 28);
-    seedn[n_m] = occ;
-    seeds[n_m] = s0;
-    if (occ > in.mid_occ) ++n_high;
-    ++n_m;
-  }
-  // ---- seed.c: mm_seed_select (occ_dist > 0 && max_max_occ > max_occ) or plain cut --
-  if (n_high > 0) {
-    const int max_occ = in.mid_occ;
+template <typename SQ, typename SN>
+LGR_HD void seed_select(const DevParams& P, SQ seedq, SN seedn, int n_m, int qlen, int mid_occ) {
+  {
+    const int max_occ = mid_occ;
     if (P.occ_dist > 0 && P.max_max_occ > max_occ) {
       if (n_m > 1) {
         int last0 = -1;
@@ -697,109 +662,23 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
         if (seedn[i] > max_occ) seedq[i] = (int32_t)((uint32_t)seedq[i] | 1u << 29);
     }
   }
-  // ---- map.c: collect_seed_hits -----------------------------------------------------
-  int n_a = 0;
-  for (int i = 0; i < n_m; ++i) {
-    const uint32_t sq = (uint32_t)seedq[i];
-    if (sq >> 29 & 1) continue;
-    const uint32_t q_pos = sq & 0xfffff, q_span = sq >> 20 & 0xff, tandem = sq >> 28 & 1;
-    const int occ = seedn[i], s0 = seeds[i];
-    if (n_a + occ > cap) return kMapOverflow;
-    for (int k = 0; k < occ; ++k) {
-      const uint32_t rk = (uint32_t)(in.idx[s0 + k] & ((1u << kIdxShift) - 1));
-      const uint32_t rpos = rk >> 1;
-      uint32_t x32, qp;
-      if ((rk & 1) == (q_pos & 1)) {
-        x32 = rpos;
-        qp = q_pos >> 1;
-      } else {
-        x32 = 1u << 31 | rpos;
-        qp = (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
-      }
-      ax[n_a] = (int32_t)x32;
-      ay[n_a] = (int32_t)(tandem << 24 | q_span << 16 | (qp & 0xffff));
-      ++n_a;
-    }
-  }
-  if (ctr) ctr->n_anchors += n_a;
-  if (n_a == 0) return kMapNoHit;
-  // ---- radix_sort_128x(a) by x --------------------------------------------------------
-  {
-    bool sorted = true;
-    for (int i = 1; i < n_a; ++i)
-      if ((uint32_t)ax[i] < (uint32_t)ax[i - 1]) { sorted = false; break; }
-    if (sorted && n_a <= 64) {
-      for (int i = 0; i < n_a; ++i) sx[i] = ax[i], sy[i] = ay[i];
-    } else {
-      // NB: for n_a > 64 even an already sorted input is permuted by the in-place radix
-      // passes when keys tie, so the emulation always runs.
-      for (int i = 0; i < n_a; ++i) perm[i] = i;
-      radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
-      for (int i = 0; i < n_a; ++i) sx[i] = ax[perm[i]], sy[i] = ay[perm[i]];
-    }
-  }
-  // ---- lchain.c: mg_lchain_dp ---------------------------------------------------------
-  int32_t max_dist_x = P.max_gap_ref > 0 ? P.max_gap_ref : P.max_gap;
-  int32_t max_dist_y = qlen > P.max_gap ? qlen : P.max_gap;  // MM_F_SR
-  if (max_dist_x < P.bw) max_dist_x = P.bw;
-  if (max_dist_y < P.bw) max_dist_y = P.bw;
-  {
-    int st = 0, max_ii = -1;
-    int64_t n_iter = 0;
-    for (int i = 0; i < n_a; ++i) t[i] = 0;
-    for (int i = 0; i < n_a; ++i) {
-      const uint32_t xi = (uint32_t)sx[i], yi = (uint32_t)sy[i];
-      int max_j = -1, end_j;
-      int32_t max_f = anchor_span(yi), n_skip = 0;
-      while (st < i && ((xi >> 31) != ((uint32_t)sx[st] >> 31) ||
-                        anchor_rpos(xi) > anchor_rpos((uint32_t)sx[st]) + max_dist_x))
-        ++st;
-      if (i - st > P.max_iter) st = i - P.max_iter;
-      int j;
-      for (j = i - 1; j >= st; --j) {
-        int32_t sc = comput_sc(xi, yi, (uint32_t)sx[j], (uint32_t)sy[j], max_dist_x, max_dist_y, P.bw,
-                               P.pen_gap, P.pen_skip);
-        ++n_iter;
-        if (sc == INT32_MIN) continue;
-        sc += f[j];
-        if (sc > max_f) {
-          max_f = sc, max_j = j;
-          if (n_skip > 0) --n_skip;
-        } else if (t[j] == i) {
-          if (++n_skip > P.max_skip) break;
-        }
-        if (p[j] >= 0) t[p[j]] = i;
-      }
-      end_j = j;
-      bool far;
-      if (max_ii >= 0) {
-        const uint32_t xm = (uint32_t)sx[max_ii];
-        far = (xi >> 31) != (xm >> 31) || anchor_rpos(xi) - anchor_rpos(xm) > max_dist_x;
-      } else {
-        far = true;
-      }
-      if (max_ii < 0 || far) {
-        int32_t mx = INT32_MIN;
-        max_ii = -1;
-        for (j = i - 1; j >= st; --j)
-          if (mx < f[j]) mx = f[j], max_ii = j;
-      }
-      if (max_ii >= 0 && max_ii < end_j) {
-        const int32_t tmp = comput_sc(xi, yi, (uint32_t)sx[max_ii], (uint32_t)sy[max_ii], max_dist_x,
-                                      max_dist_y, P.bw, P.pen_gap, P.pen_skip);
-        if (tmp != INT32_MIN && max_f < tmp + f[max_ii]) max_f = tmp + f[max_ii], max_j = max_ii;
-      }
-      f[i] = max_f, p[i] = max_j;
-      if (max_ii < 0) {
-        max_ii = i;
-      } else {
-        const uint32_t xm = (uint32_t)sx[max_ii];
-        const bool near = (xi >> 31) == (xm >> 31) && anchor_rpos(xi) - anchor_rpos(xm) <= max_dist_x;
-        if (near && f[max_ii] < f[i]) max_ii = i;
-      }
-    }
-    if (ctr) ctr->chain_evals += n_iter;
-  }
+}
+
+// status codes of map_chain_phase
+enum { kMapNoHit = 0, kMapOk = 1, kMapOverflow = -1 };
+
+// ------------------------------------------------------------------------------------
+// Phase A, second half: from the chain DP result (sx/sy sorted anchors, f/p per anchor,
+// n_a of them) to the surviving regs with their SR stretch and extension windows.  Scalar;
+// run by every lane in the thread-per-pair kernel and by lane 0 in the warp-per-pair one.
+// ------------------------------------------------------------------------------------
+template <int S>
+LGR_HDN int map_chain_tail(const DevParams& P, int qlen, int hap_len, uint32_t name_hash, const Ws<S>& ws,
+                           RadixScratch* rsx, int n_a, int* n_regs_out) {
+  auto ax = ws.arr(A_AX), ay = ws.arr(A_AY), sx = ws.arr(A_SX), sy = ws.arr(A_SY);
+  auto f = ws.arr(A_F), p = ws.arr(A_P), t = ws.arr(A_T), v = ws.arr(A_V), z = ws.arr(A_Z);
+  auto perm = ws.arr(A_PERM);
+  *n_regs_out = 0;
   // ---- lchain.c: mg_chain_backtrack ------------------------------------------------------
   // z[k] = anchor ids with f >= min_sc sorted by f (radix_sort_128x on x = f); chains are
   // collected from the highest score down.  Output: chain c has score u_sc[c], count
@@ -873,7 +752,7 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
     }
   }
   // ---- hit.c: mm_gen_regs --------------------------------------------------------------------
-  uint32_t hash = in.name_hash;
+  uint32_t hash = name_hash;
   hash ^= wang_hash((uint32_t)qlen) + wang_hash((uint32_t)P.seed);
   hash = wang_hash(hash);
   {
@@ -1034,12 +913,157 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
     const int32_t rs0 = rs - l > 0 ? rs - l : 0;
     l = qlen - qe;
     l += l * P.a + P.end_bonus > P.q ? (l * P.a + P.end_bonus - P.q) / P.e : 0;
-    const int32_t re0 = re + l < in.hap_len ? re + l : in.hap_len;
+    const int32_t re0 = re + l < hap_len ? re + l : hap_len;
     r_qs[r] = qs, r_qe[r] = qe, r_rs[r] = rs, r_re[r] = re;
     f[r] = rs0, p[r] = re0;
   }
   *n_regs_out = n_regs;
   return kMapOk;
+}
+
+// ------------------------------------------------------------------------------------
+// Phase A: seeds → anchors → sort → chain DP → backtrack → regs → parent/sub selection
+// → per-reg SR stretch + extension windows.  On return (kMapOk) the surviving regs are
+// in the R_* arrays [0, *n_regs) and the per-reg stretch in R_AUX*/A_* as documented
+// at the end.  Restates minimap2 map.c:mm_map_frag up to (not including) the ksw2 calls.
+// ------------------------------------------------------------------------------------
+template <int S>
+LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& ws, RadixScratch* rsx,
+                            int* n_regs_out, ChainCounters* ctr) {
+  const int cap = ws.cap;
+  auto ax = ws.arr(A_AX), ay = ws.arr(A_AY), sx = ws.arr(A_SX), sy = ws.arr(A_SY);
+  auto f = ws.arr(A_F), p = ws.arr(A_P), t = ws.arr(A_T), v = ws.arr(A_V), z = ws.arr(A_Z);
+  auto perm = ws.arr(A_PERM);
+  auto seedq = ws.arr(A_SEEDQ), seedn = ws.arr(A_SEEDN), seeds = ws.arr(A_SEEDS);
+  const int qlen = in.read.qlen;
+  *n_regs_out = 0;
+
+  // ---- seed.c: mm_seed_collect_all -------------------------------------------------
+  // seedq: q_pos (pos<<1|strand) | span<<20 | tandem<<28 | flt<<29 ; seedn: occurrences ;
+  // seeds: first index in the table
+  int n_m = 0, n_high = 0;
+  for (int i = 0; i < in.mz_n; ++i) {
+    const uint64_t hx = in.mz_x[i] >> 8;
+    const int s0 = idx_lower_bound(in.idx, in.idx_n, hx << kIdxShift);
+    const int s1 = idx_lower_bound(in.idx, in.idx_n, (hx + 1) << kIdxShift);
+    const int occ = s1 - s0;
+    if (occ == 0) continue;
+    if (n_m >= cap) return kMapOverflow;
+    uint32_t tandem = 0;
+    if (i > 0 && hx == in.mz_x[i - 1] >> 8) tandem = 1;
+    if (i < in.mz_n - 1 && hx == in.mz_x[i + 1] >> 8) tandem = 1;
+    seedq[n_m] = (int32_t)(in.mz_y[i] | (uint32_t)(in.mz_x[i] & 0xff) << 20 | tandem << 28);
+    seedn[n_m] = occ;
+    seeds[n_m] = s0;
+    if (occ > in.mid_occ) ++n_high;
+    ++n_m;
+  }
+  // ---- seed.c: mm_seed_select (occ_dist > 0 && max_max_occ > max_occ) or plain cut --
+  if (n_high > 0) seed_select(P, seedq, seedn, n_m, qlen, in.mid_occ);
+  // ---- map.c: collect_seed_hits -----------------------------------------------------
+  int n_a = 0;
+  for (int i = 0; i < n_m; ++i) {
+    const uint32_t sq = (uint32_t)seedq[i];
+    if (sq >> 29 & 1) continue;
+    const uint32_t q_pos = sq & 0xfffff, q_span = sq >> 20 & 0xff, tandem = sq >> 28 & 1;
+    const int occ = seedn[i], s0 = seeds[i];
+    if (n_a + occ > cap) return kMapOverflow;
+    for (int k = 0; k < occ; ++k) {
+      const uint32_t rk = (uint32_t)(in.idx[s0 + k] & ((1u << kIdxShift) - 1));
+      const uint32_t rpos = rk >> 1;
+      uint32_t x32, qp;
+      if ((rk & 1) == (q_pos & 1)) {
+        x32 = rpos;
+        qp = q_pos >> 1;
+      } else {
+        x32 = 1u << 31 | rpos;
+        qp = (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
+      }
+      ax[n_a] = (int32_t)x32;
+      ay[n_a] = (int32_t)(tandem << 24 | q_span << 16 | (qp & 0xffff));
+      ++n_a;
+    }
+  }
+  if (ctr) ctr->n_anchors += n_a;
+  if (n_a == 0) return kMapNoHit;
+  // ---- radix_sort_128x(a) by x --------------------------------------------------------
+  {
+    bool sorted = true;
+    for (int i = 1; i < n_a; ++i)
+      if ((uint32_t)ax[i] < (uint32_t)ax[i - 1]) { sorted = false; break; }
+    if (sorted && n_a <= 64) {
+      for (int i = 0; i < n_a; ++i) sx[i] = ax[i], sy[i] = ay[i];
+    } else {
+      // NB: for n_a > 64 even an already sorted input is permuted by the in-place radix
+      // passes when keys tie, so the emulation always runs.
+      for (int i = 0; i < n_a; ++i) perm[i] = i;
+      radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
+      for (int i = 0; i < n_a; ++i) sx[i] = ax[perm[i]], sy[i] = ay[perm[i]];
+    }
+  }
+  // ---- lchain.c: mg_lchain_dp ---------------------------------------------------------
+  int32_t max_dist_x = P.max_gap_ref > 0 ? P.max_gap_ref : P.max_gap;
+  int32_t max_dist_y = qlen > P.max_gap ? qlen : P.max_gap;  // MM_F_SR
+  if (max_dist_x < P.bw) max_dist_x = P.bw;
+  if (max_dist_y < P.bw) max_dist_y = P.bw;
+  {
+    int st = 0, max_ii = -1;
+    int64_t n_iter = 0;
+    for (int i = 0; i < n_a; ++i) t[i] = 0;
+    for (int i = 0; i < n_a; ++i) {
+      const uint32_t xi = (uint32_t)sx[i], yi = (uint32_t)sy[i];
+      int max_j = -1, end_j;
+      int32_t max_f = anchor_span(yi), n_skip = 0;
+      while (st < i && ((xi >> 31) != ((uint32_t)sx[st] >> 31) ||
+                        anchor_rpos(xi) > anchor_rpos((uint32_t)sx[st]) + max_dist_x))
+        ++st;
+      if (i - st > P.max_iter) st = i - P.max_iter;
+      int j;
+      for (j = i - 1; j >= st; --j) {
+        int32_t sc = comput_sc(xi, yi, (uint32_t)sx[j], (uint32_t)sy[j], max_dist_x, max_dist_y, P.bw,
+                               P.pen_gap, P.pen_skip);
+        ++n_iter;
+        if (sc == INT32_MIN) continue;
+        sc += f[j];
+        if (sc > max_f) {
+          max_f = sc, max_j = j;
+          if (n_skip > 0) --n_skip;
+        } else if (t[j] == i) {
+          if (++n_skip > P.max_skip) break;
+        }
+        if (p[j] >= 0) t[p[j]] = i;
+      }
+      end_j = j;
+      bool far;
+      if (max_ii >= 0) {
+        const uint32_t xm = (uint32_t)sx[max_ii];
+        far = (xi >> 31) != (xm >> 31) || anchor_rpos(xi) - anchor_rpos(xm) > max_dist_x;
+      } else {
+        far = true;
+      }
+      if (max_ii < 0 || far) {
+        int32_t mx = INT32_MIN;
+        max_ii = -1;
+        for (j = i - 1; j >= st; --j)
+          if (mx < f[j]) mx = f[j], max_ii = j;
+      }
+      if (max_ii >= 0 && max_ii < end_j) {
+        const int32_t tmp = comput_sc(xi, yi, (uint32_t)sx[max_ii], (uint32_t)sy[max_ii], max_dist_x,
+                                      max_dist_y, P.bw, P.pen_gap, P.pen_skip);
+        if (tmp != INT32_MIN && max_f < tmp + f[max_ii]) max_f = tmp + f[max_ii], max_j = max_ii;
+      }
+      f[i] = max_f, p[i] = max_j;
+      if (max_ii < 0) {
+        max_ii = i;
+      } else {
+        const uint32_t xm = (uint32_t)sx[max_ii];
+        const bool near = (xi >> 31) == (xm >> 31) && anchor_rpos(xi) - anchor_rpos(xm) <= max_dist_x;
+        if (near && f[max_ii] < f[i]) max_ii = i;
+      }
+    }
+    if (ctr) ctr->chain_evals += n_iter;
+  }
+  return map_chain_tail<S>(P, qlen, in.hap_len, in.name_hash, ws, rsx, n_a, n_regs_out);
 }
 
 // fill a RegRec (without the extension results) from the workspace after map_chain_phase

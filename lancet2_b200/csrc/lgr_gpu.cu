@@ -89,6 +89,8 @@ struct Dev {      // everything the kernels need, passed by value
   uint8_t* dir_scratch; int64_t dir_per_warp;
   int32_t* bnd_scratch; int64_t bnd_per_warp;   // Hb/Fb boundary rows
   uint32_t* wcig_scratch; int wcig_cap;
+  RegRec* wreg_scratch;          // [warps][CAP] regs of the pair a warp is working on
+  RadixScratch* rsx_scratch;     // [warps]
   // outputs
   AlnOut* aln; uint32_t* cigar_inline; uint32_t* cigar_arena; int64_t cigar_arena_cap;
   AssignOut* assign;
@@ -360,14 +362,109 @@ __global__ void __launch_bounds__(128) k_map(Dev D) {
 }
 
 // ---------------------------------------------------------------------------------------
-// k_ext_big: one warp per long tail.  Lane l owns query row j = 32*blk + l and sweeps the
-// target columns; on step s it computes cell (i = s - l, j).  H and the F flowing down a
-// column travel to the lane below with two shuffles per step; E stays in the lane.  Rows
-// beyond 32 are processed in further passes with the boundary row (H, F) kept in scratch.
+// ext_dp_warp: one warp computes one extension tail.  Lane l owns query row j = 32*blk + l and
+// sweeps the target columns; on step s it computes cell (i = s - l, j).  H and the F flowing
+// down a column travel to the lane below with two shuffles per step; E stays in the lane.
+// Rows beyond 32 are processed in further passes with the boundary row (H, F) kept in scratch.
 // Direction bytes are stored diagonal-major ([blk][s][lane]) so that every step is one
-// coalesced 32-byte store.  Same recurrences, tie rules and column pruning as
-// ext_dp_scalar (which the lanes of k_map run for short tails).
+// coalesced 32-byte store.  Same recurrences, tie rules and column pruning as ext_dp_scalar.
+// All 32 lanes must call it; results are written by lane 0 into reg->ext[side].
 // ---------------------------------------------------------------------------------------
+__device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, const ReadView& rv, const uint8_t* hapc,
+                                         uint8_t* dir, int32_t* Hb, int32_t* Fb, uint32_t* wcig, long long* cells,
+                                         long long* cells_full) {
+  const int lane = threadIdx.x & 31;
+  const DevParams& P = D.P;
+  const int q = P.q, e = P.e;
+  const int m = reg->ext[side].m, n = reg->ext[side].n;
+  const int T = prune_cols(P, m, n);
+  const bool right = side == 0;
+  ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
+  ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
+  const int nblk = (m + 31) >> 5;
+  const int dstride = T + 32;  // steps per block (padded)
+  int32_t ezmax = 0, mqe = kNegInf, mqe_t = -1;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int j = blk * 32 + lane;
+    const bool row_ok = j < m;
+    const int qc = row_ok ? qf(j) : 4;
+    int32_t e_cur = -(q + e * (j + 1)) - q - e;  // E(0, j)
+    int32_t diag = j == 0 ? 0 : -(q + e * j);    // H(-1, j-1)
+    int32_t h_last = 0, f_out = 0;
+    uint8_t* dblk = dir + (size_t)blk * dstride * 32;
+    const int nsteps = T + 31;
+    for (int s = 0; s < nsteps; ++s) {
+      int32_t up_h = __shfl_up_sync(0xffffffffu, h_last, 1);
+      int32_t up_f = __shfl_up_sync(0xffffffffu, f_out, 1);
+      const int i = s - lane;
+      const bool act = row_ok && i >= 0 && i < T;
+      if (lane == 0 && act) {
+        if (blk == 0) {
+          up_h = -(q + e * (i + 1));
+          up_f = up_h - q - e;
+        } else {
+          up_h = Hb[i];
+          up_f = Fb[i];
+        }
+      }
+      if (act) {
+        const int32_t hd = diag + sub_score(P, tf(i), qc);
+        uint8_t d;
+        int32_t en, fn;
+        const int32_t h = ext_cell(hd, e_cur, up_f, q, e, right, &d, &en, &fn);
+        dblk[(size_t)s * 32 + lane] = d;
+        diag = up_h;
+        h_last = h;
+        e_cur = en;
+        f_out = fn;
+        if (h > ezmax) ezmax = h;
+        if (j == m - 1 && h > mqe) mqe = h, mqe_t = i;
+        if (lane == 31 && blk + 1 < nblk) Hb[i] = h, Fb[i] = fn;
+      }
+    }
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int32_t v = __shfl_down_sync(0xffffffffu, ezmax, o);
+    ezmax = v > ezmax ? v : ezmax;
+  }
+  ezmax = __shfl_sync(0xffffffffu, ezmax, 0);
+  mqe_t = __shfl_sync(0xffffffffu, mqe_t, (m - 1) & 31);
+  __syncwarp();
+  if (lane == 0) {
+    ExtRec& E = reg->ext[side];
+    E.max = ezmax;
+    E.mqe_t = mqe_t;
+    CigBuf cb{wcig, 0, D.wcig_cap};
+    auto dirf = [&](int i, int j) -> uint8_t {
+      const int b = j >> 5, l = j & 31;
+      return dir[((size_t)b * dstride + (size_t)(i + l)) * 32 + l];
+    };
+    ext_backtrack(dirf, m, mqe_t, side == 0, cb);
+    E.n_cig = cb.n;
+    if (cb.n > D.wcig_cap) {
+      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+      E.n_cig = 0;
+    } else if (cb.n <= kInlineCig) {
+      E.cig_off = -1;
+      for (int c = 0; c < cb.n; ++c) E.inl[c] = wcig[c];
+    } else {
+      const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)cb.n);
+      if (o + cb.n > D.ext_arena_cap) {
+        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
+        E.n_cig = 0;
+      } else {
+        E.cig_off = (int32_t)o;
+        for (int c = 0; c < cb.n; ++c) D.ext_arena[o + c] = wcig[c];
+      }
+    }
+    *cells += (long long)m * T;
+    *cells_full += (long long)m * n;
+  }
+  __syncwarp();
+}
+
+// k_ext_big: one warp per queued long tail (tails parked by the overflow pass k_map<true>)
 __global__ void __launch_bounds__(128) k_ext_big(Dev D) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -376,8 +473,6 @@ __global__ void __launch_bounds__(128) k_ext_big(Dev D) {
   int32_t* Fb = Hb + D.bnd_per_warp / 2;
   uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
   const long long n_tasks = D.ctr[C_NTASK] < D.tasks_cap ? D.ctr[C_NTASK] : D.tasks_cap;
-  const DevParams& P = D.P;
-  const int q = P.q, e = P.e;
   long long cells = 0, cells_full = 0;
   for (;;) {
     long long ti = 0;
@@ -385,121 +480,364 @@ __global__ void __launch_bounds__(128) k_ext_big(Dev D) {
     ti = __shfl_sync(0xffffffffu, ti, 0);
     if (ti >= n_tasks) break;
     const TaskRec tk = D.tasks[ti];
-    RegRec* reg = D.regs + tk.reg;
-    const int side = tk.side;
     const int64_t roff = D.read_off[tk.read], hoff = D.hap_off[tk.hap];
     ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
-    const uint8_t* hapc = D.hap_codes + hoff;
-    const int m = reg->ext[side].m, n = reg->ext[side].n;
-    const int T = prune_cols(P, m, n);
-    const bool right = side == 0;
-    ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
-    ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
-    const int nblk = (m + 31) >> 5;
-    const int dstride = T + 32;  // steps per block (padded)
-    int32_t ezmax = 0, mqe = kNegInf, mqe_t = -1;
-    for (int blk = 0; blk < nblk; ++blk) {
-      const int j = blk * 32 + lane;
-      const bool row_ok = j < m;
-      const int qc = row_ok ? qf(j) : 4;
-      int32_t e_cur = -(q + e * (j + 1)) - q - e;           // E(0, j)
-      int32_t diag = j == 0 ? 0 : -(q + e * j);             // H(-1, j-1)
-      int32_t h_last = 0, f_out = 0;
-      uint8_t* dblk = dir + (size_t)blk * dstride * 32;
-      const int nsteps = T + 31;
-      for (int s = 0; s < nsteps; ++s) {
-        int32_t up_h = __shfl_up_sync(0xffffffffu, h_last, 1);
-        int32_t up_f = __shfl_up_sync(0xffffffffu, f_out, 1);
-        const int i = s - lane;
-        const bool act = row_ok && i >= 0 && i < T;
-        if (lane == 0 && act) {
-          if (blk == 0) {
-            up_h = -(q + e * (i + 1));
-            up_f = up_h - q - e;
-          } else {
-            up_h = Hb[i];
-            up_f = Fb[i];
-          }
-        }
-        if (act) {
-          const int tc = tf(i);
-          const int32_t hd = diag + sub_score(P, tc, qc);
-          const int32_t ee = e_cur;
-          const int32_t f = up_f;
-          int32_t h;
-          uint32_t d;
-          if (!right) {
-            d = ee > hd ? 1u : 0u;
-            h = ee > hd ? ee : hd;
-            if (f > h) d = 2u, h = f;
-          } else {
-            d = hd > ee ? 0u : 1u;
-            h = hd > ee ? hd : ee;
-            if (!(h > f)) d = 2u, h = f;
-          }
-          const int32_t ho = h - q;
-          if (!right) {
-            if (ee > ho) d |= 0x08u;
-            if (f > ho) d |= 0x10u;
-          } else {
-            if (ee >= ho) d |= 0x08u;
-            if (f >= ho) d |= 0x10u;
-          }
-          dblk[(size_t)s * 32 + lane] = (uint8_t)d;
-          diag = up_h;
-          h_last = h;
-          e_cur = (ee > ho ? ee : ho) - e;
-          f_out = (f > ho ? f : ho) - e;
-          if (h > ezmax) ezmax = h;
-          if (j == m - 1 && h > mqe) mqe = h, mqe_t = i;
-          if (lane == 31 && blk + 1 < nblk) Hb[i] = h, Fb[i] = f_out;
-        }
-      }
-      __syncwarp();
-    }
-    // reduce: ez.max over lanes; (mqe, mqe_t) lives in the lane that owns row m-1
-    for (int o = 16; o > 0; o >>= 1) {
-      const int32_t v = __shfl_down_sync(0xffffffffu, ezmax, o);
-      ezmax = v > ezmax ? v : ezmax;
-    }
-    ezmax = __shfl_sync(0xffffffffu, ezmax, 0);
-    mqe_t = __shfl_sync(0xffffffffu, mqe_t, (m - 1) & 31);
-    __syncwarp();
-    if (lane == 0) {
-      ExtRec& E = reg->ext[side];
-      E.max = ezmax;
-      E.mqe_t = mqe_t;
-      CigBuf cb{wcig, 0, D.wcig_cap};
-      auto dirf = [&](int i, int j) -> uint8_t {
-        const int b = j >> 5, l = j & 31;
-        return dir[((size_t)b * dstride + (size_t)(i + l)) * 32 + l];
-      };
-      ext_backtrack(dirf, m, mqe_t, side == 0, cb);
-      E.n_cig = cb.n;
-      if (cb.n > D.wcig_cap) {
-        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
-        E.n_cig = 0;
-      } else if (cb.n <= kInlineCig) {
-        E.cig_off = -1;
-        for (int c = 0; c < cb.n; ++c) E.inl[c] = wcig[c];
-      } else {
-        const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)cb.n);
-        if (o + cb.n > D.ext_arena_cap) {
-          atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
-          E.n_cig = 0;
-        } else {
-          E.cig_off = (int32_t)o;
-          for (int c = 0; c < cb.n; ++c) D.ext_arena[o + c] = wcig[c];
-        }
-      }
-      cells += (long long)m * T;
-      cells_full += (long long)m * n;
-    }
-    __syncwarp();
+    ext_dp_warp(D, D.regs + tk.reg, tk.side, rv, D.hap_codes + hoff, dir, Hb, Fb, wcig, &cells, &cells_full);
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)cells);
     atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)cells_full);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_map_warp: ONE WARP PER (read, haplotype) PAIR.  A CTA (8 warps) takes a work item =
+// (haplotype, up to 64 consecutive reads of its group), stages the haplotype's code bytes and
+// minimizer table in shared memory, and its warps walk the reads.  Per pair, all chain state
+// (seeds, anchors, f/p/t, chains, regs: A_COUNT arrays of CAP int32) lives in the warp's slice
+// of shared memory:
+//   seeds     32 minimizers at a time: binary search in the staged table, ballot-compacted
+//   anchors   warp prefix sum over occurrence counts
+//   chain DP  for anchor i, 32 predecessors j at a time: comput_sc in parallel, then minimap2's
+//             sequential max / max_skip / break automaton reproduced exactly with a prefix-max
+//             scan, a (max,+) scan for the saturating skip counter and ballots
+//   tail      backtrack → regs → stretch: the scalar core (map_chain_tail) on lane 0
+//   extension short tails scalar on lane 0, long tails on the whole warp (ext_dp_warp)
+//   finish    scalar core on lane 0 (cigar assembly, mm_fix_cigar, mm_update_extra, NM)
+// Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_map<true>).
+// ---------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 8;
+constexpr int kHapSmem = 2048;   // haplotype code bytes staged per CTA
+constexpr int kIdxSmem = 768;    // minimizer table entries staged per CTA
+
+template <int CAP>
+__device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const Ws<1>& ws, RadixScratch* rsx,
+                                               ChainCounters* ctr, int* n_a_out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const DevParams& P = D.P;
+  auto ax = ws.arr(A_AX), ay = ws.arr(A_AY), sx = ws.arr(A_SX), sy = ws.arr(A_SY);
+  auto f = ws.arr(A_F), p = ws.arr(A_P), t = ws.arr(A_T), perm = ws.arr(A_PERM);
+  auto seedq = ws.arr(A_SEEDQ), seedn = ws.arr(A_SEEDN), seeds = ws.arr(A_SEEDS);
+  const int qlen = in.read.qlen;
+  // ---- seeds (mm_seed_collect_all) ----
+  int n_m = 0, n_high = 0;
+  for (int base = 0; base < in.mz_n; base += 32) {
+    const int i = base + lane;
+    int occ = 0, s0 = 0;
+    uint32_t sq = 0;
+    if (i < in.mz_n) {
+      const uint64_t mx = in.mz_x[i];
+      const uint64_t hx = mx >> 8;
+      s0 = idx_lower_bound(in.idx, in.idx_n, hx << kIdxShift);
+      const int s1 = idx_lower_bound(in.idx, in.idx_n, (hx + 1) << kIdxShift);
+      occ = s1 - s0;
+      if (occ > 0) {
+        uint32_t tandem = 0;
+        if (i > 0 && hx == in.mz_x[i - 1] >> 8) tandem = 1;
+        if (i < in.mz_n - 1 && hx == in.mz_x[i + 1] >> 8) tandem = 1;
+        sq = in.mz_y[i] | (uint32_t)(mx & 0xff) << 20 | tandem << 28;
+      }
+    }
+    const unsigned hit = __ballot_sync(full, occ > 0);
+    const int pos = n_m + __popc(hit & ((1u << lane) - 1));
+    if (occ > 0 && pos < CAP) seedq[pos] = (int32_t)sq, seedn[pos] = occ, seeds[pos] = s0;
+    n_high += __popc(__ballot_sync(full, occ > in.mid_occ));
+    n_m += __popc(hit);
+  }
+  if (n_m > CAP) return kMapOverflow;
+  __syncwarp();
+  if (n_high > 0) {
+    if (lane == 0) seed_select(P, seedq, seedn, n_m, qlen, in.mid_occ);
+    __syncwarp();
+  }
+  // ---- anchors (collect_seed_hits) ----
+  int n_a = 0;
+  for (int base = 0; base < n_m; base += 32) {
+    const int i = base + lane;
+    int occ = 0;
+    uint32_t sq = 0;
+    if (i < n_m) {
+      sq = (uint32_t)seedq[i];
+      if (!(sq >> 29 & 1)) occ = seedn[i];
+    }
+    int inc = occ;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(full, inc, o);
+      if (lane >= o) inc += v;
+    }
+    const int total = __shfl_sync(full, inc, 31);
+    if (n_a + total > CAP) return kMapOverflow;
+    if (occ > 0) {
+      const uint32_t q_pos = sq & 0xfffff, q_span = sq >> 20 & 0xff, tandem = sq >> 28 & 1;
+      const int s0 = seeds[i];
+      int off = n_a + inc - occ;
+      for (int k = 0; k < occ; ++k, ++off) {
+        const uint32_t rk = (uint32_t)(in.idx[s0 + k] & ((1u << kIdxShift) - 1));
+        const uint32_t rpos = rk >> 1;
+        uint32_t x32, qp;
+        if ((rk & 1) == (q_pos & 1)) {
+          x32 = rpos;
+          qp = q_pos >> 1;
+        } else {
+          x32 = 1u << 31 | rpos;
+          qp = (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
+        }
+        ax[off] = (int32_t)x32;
+        ay[off] = (int32_t)(tandem << 24 | q_span << 16 | (qp & 0xffff));
+      }
+    }
+    n_a += total;
+  }
+  if (lane == 0 && ctr) ctr->n_anchors += n_a;
+  *n_a_out = n_a;
+  if (n_a == 0) return kMapNoHit;
+  __syncwarp();
+  // ---- radix_sort_128x(a): already-sorted fast path, else the exact emulation on lane 0 ----
+  {
+    bool ok = true;
+    for (int i = lane + 1; i < n_a; i += 32) ok &= (uint32_t)ax[i] >= (uint32_t)ax[i - 1];
+    const bool sorted = __all_sync(full, ok);
+    if (sorted && n_a <= 64) {
+      for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
+    } else {
+      if (lane == 0) {
+        for (int i = 0; i < n_a; ++i) perm[i] = i;
+        radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
+        for (int i = 0; i < n_a; ++i) sx[i] = ax[perm[i]], sy[i] = ay[perm[i]];
+      }
+    }
+  }
+  for (int i = lane; i < n_a; i += 32) t[i] = 0;
+  __syncwarp();
+  // ---- mg_lchain_dp ----
+  int32_t max_dist_x = P.max_gap_ref > 0 ? P.max_gap_ref : P.max_gap;
+  int32_t max_dist_y = qlen > P.max_gap ? qlen : P.max_gap;
+  if (max_dist_x < P.bw) max_dist_x = P.bw;
+  if (max_dist_y < P.bw) max_dist_y = P.bw;
+  int st = 0, max_ii = -1;
+  long long n_iter = 0;
+  for (int i = 0; i < n_a; ++i) {
+    const uint32_t xi = (uint32_t)sx[i], yi = (uint32_t)sy[i];
+    while (st < i && ((xi >> 31) != ((uint32_t)sx[st] >> 31) || anchor_rpos(xi) > anchor_rpos((uint32_t)sx[st]) + max_dist_x)) ++st;
+    if (i - st > P.max_iter) st = i - P.max_iter;
+    int32_t max_f = anchor_span(yi);
+    int max_j = -1, n_skip = 0, end_j = st - 1;
+    for (int jb = i - 1; jb >= st; jb -= 32) {
+      const int j = jb - lane;
+      int32_t sc = INT32_MIN;
+      int pj = -1;
+      if (j >= st) {
+        sc = comput_sc(xi, yi, (uint32_t)sx[j], (uint32_t)sy[j], max_dist_x, max_dist_y, P.bw, P.pen_gap, P.pen_skip);
+        if (sc != INT32_MIN) sc += f[j], pj = p[j];
+      }
+      const bool valid = sc != INT32_MIN;
+      // stamps t[p[j]] = i of this chunk: predecessors processed earlier (higher j, lower lane) are
+      // visible to later lanes after the barrier; stamps written by lanes at/after a break only
+      // touch entries that are never read again for this i.
+      if (valid && pj >= 0) t[pj] = i;
+      __syncwarp();
+      const bool stamped = valid && t[j] == i;
+      // exclusive prefix max of the candidate scores (sequential "sc > max_f" test)
+      int32_t pm = sc;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t v = __shfl_up_sync(full, pm, o);
+        if (lane >= o && v > pm) pm = v;
+      }
+      int32_t excl = __shfl_up_sync(full, pm, 1);
+      if (lane == 0) excl = INT32_MIN;
+      if (max_f > excl) excl = max_f;
+      const bool newmax = valid && sc > excl;
+      // saturating skip counter: n -> max(n + a, b) per lane, composed left to right
+      const int ev = newmax ? -1 : (stamped ? 1 : 0);
+      int a = ev, b = ev == 1 ? 1 : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int au = __shfl_up_sync(full, a, o), bu = __shfl_up_sync(full, b, o);
+        if (lane >= o) {
+          const int nb = bu + a;
+          b = nb > b ? nb : b;
+          a = au + a;
+        }
+      }
+      int n_after = n_skip + a;
+      if (b > n_after) n_after = b;
+      const unsigned brk = __ballot_sync(full, ev == 1 && n_after > P.max_skip);
+      const int last = brk ? __ffs(brk) - 1 : 31;
+      const unsigned nmask = __ballot_sync(full, newmax) & (last == 31 ? 0xffffffffu : ((2u << last) - 1));
+      if (nmask) {
+        const int src = 31 - __clz(nmask);
+        max_f = __shfl_sync(full, sc, src);
+        max_j = jb - src;
+      }
+      n_skip = __shfl_sync(full, n_after, last);
+      const int n_in = jb - st + 1 < 32 ? jb - st + 1 : 32;
+      if (brk) {
+        n_iter += last + 1;
+        end_j = jb - last;
+        break;
+      }
+      n_iter += n_in;
+      __syncwarp();
+    }
+    bool far = true;
+    if (max_ii >= 0) {
+      const uint32_t xm = (uint32_t)sx[max_ii];
+      far = (xi >> 31) != (xm >> 31) || anchor_rpos(xi) - anchor_rpos(xm) > max_dist_x;
+    }
+    if (max_ii < 0 || far) {
+      int32_t bf = INT32_MIN;
+      int bj = -1;
+      for (int j = i - 1 - lane; j >= st; j -= 32)
+        if (f[j] > bf) bf = f[j], bj = j;
+      for (int o = 16; o > 0; o >>= 1) {
+        const int32_t of = __shfl_xor_sync(full, bf, o);
+        const int oj = __shfl_xor_sync(full, bj, o);
+        if (of > bf || (of == bf && oj > bj)) bf = of, bj = oj;
+      }
+      max_ii = bj;
+    }
+    if (max_ii >= 0 && max_ii < end_j) {
+      const int32_t tmp = comput_sc(xi, yi, (uint32_t)sx[max_ii], (uint32_t)sy[max_ii], max_dist_x, max_dist_y, P.bw, P.pen_gap, P.pen_skip);
+      if (tmp != INT32_MIN && max_f < tmp + f[max_ii]) max_f = tmp + f[max_ii], max_j = max_ii;
+    }
+    __syncwarp();
+    if (lane == 0) f[i] = max_f, p[i] = max_j;
+    if (max_ii < 0) {
+      max_ii = i;
+    } else {
+      const uint32_t xm = (uint32_t)sx[max_ii];
+      const bool near = (xi >> 31) == (xm >> 31) && anchor_rpos(xi) - anchor_rpos(xm) <= max_dist_x;
+      if (near && f[max_ii] < max_f) max_ii = i;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && ctr) ctr->chain_evals += n_iter;
+  return kMapOk;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* s_idx = reinterpret_cast<uint64_t*>(smem_raw);
+  uint8_t* s_hap = smem_raw + sizeof(uint64_t) * kIdxSmem;
+  int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw + sizeof(uint64_t) * kIdxSmem + kHapSmem);
+  __shared__ long long s_item;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * kWarpsPerCta + warp;
+  Ws<1> ws{s_ws + (size_t)warp * A_COUNT * CAP, CAP};
+  uint8_t* dir = D.dir_scratch + (size_t)gwarp * D.dir_per_warp;
+  int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
+  int32_t* Fb = Hb + D.bnd_per_warp / 2;
+  uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
+  uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
+  RegRec* wregs = D.wreg_scratch + (size_t)gwarp * CAP;
+  RadixScratch* rsx = D.rsx_scratch + gwarp;
+  ChainCounters ctr{0, 0, 0, 0};
+  long long n_aligned = 0;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd((unsigned long long*)&D.ctr[C_ITEM], 1ULL);
+    __syncthreads();
+    const long long item = s_item;
+    if (item >= D.n_items) break;
+    const int h = D.item_hap[item], r0 = D.item_r0[item], nr = D.item_n[item];
+    const int64_t hoff = D.hap_off[h];
+    const int hlen = (int)(D.hap_off[h + 1] - hoff);
+    const int idx_n = D.idx_n[h];
+    const uint8_t* hapc = D.hap_codes + hoff;
+    const uint64_t* idx = D.idx + hoff;
+    if (hlen <= kHapSmem) {
+      for (int i = threadIdx.x; i < hlen; i += blockDim.x) s_hap[i] = hapc[i];
+      hapc = s_hap;
+    }
+    if (idx_n <= kIdxSmem) {
+      for (int i = threadIdx.x; i < idx_n; i += blockDim.x) s_idx[i] = idx[i];
+      idx = s_idx;
+    }
+    __syncthreads();
+    const int g = D.hap_grp[h];
+    const int h_local = h - D.grp_hap_begin[g];
+    const int mid_occ = D.grp_mid[g];
+    for (int rr = warp; rr < nr; rr += kWarpsPerCta) {
+      const int r = r0 + rr;
+      const int64_t pair = D.pair_off[r] + h_local;
+      const int64_t roff = D.read_off[r];
+      const int qlen = (int)(D.read_off[r + 1] - roff);
+      ReadView rv{D.read_codes + roff, qlen};
+      PairIn pin{rv, hapc, hlen, idx, idx_n, D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], mid_occ};
+      int n_a = 0, n_regs = 0;
+      int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, ws, rsx, &ctr, &n_a) : kMapNoHit;
+      if (st == kMapOk) {
+        if (lane == 0) st = map_chain_tail<1>(D.P, qlen, hlen, pin.name_hash, ws, rsx, n_a, &n_regs);
+        st = __shfl_sync(full, st, 0);
+        n_regs = __shfl_sync(full, n_regs, 0);
+      }
+      if (st == kMapOverflow) {
+        if (lane == 0) {
+          const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
+          if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h;
+          else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
+        }
+      } else if (st == kMapNoHit) {
+        if (lane == 0) write_invalid(&D.aln[pair]);
+      } else {
+        // extensions of every surviving reg, then finish on lane 0
+        bool ok = true;
+        for (int i = 0; i < n_regs; ++i) {
+          if (lane == 0) export_reg<1>(ws, i, qlen, &wregs[i]);
+          __syncwarp();
+          for (int side = 0; side < 2; ++side) {
+            int m = 0, small = 1;
+            if (lane == 0) m = wregs[i].ext[side].m, small = ext_is_small(D.P, wregs[i].ext[side]) ? 1 : 0;
+            m = __shfl_sync(full, m, 0);
+            small = __shfl_sync(full, small, 0);
+            if (m <= 0) continue;
+            if (small) {
+              if (lane == 0) {
+                uint8_t sdir[kSmallCells];
+                int32_t ha[kSmallDim + 2], fa[kSmallDim + 2];
+                uint32_t cig_tmp[kSmallCig];
+                auto alloc_ext = [&](int n) -> int64_t {
+                  const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)n);
+                  if (o + n > D.ext_arena_cap) {
+                    atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
+                    return -1;
+                  }
+                  return o;
+                };
+                ok &= run_ext_scalar(D.P, rv, hapc, &wregs[i], side, sdir, ha, fa, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, &ctr);
+              }
+            } else {
+              long long c1 = 0, c2 = 0;
+              ext_dp_warp(D, &wregs[i], side, rv, hapc, dir, Hb, Fb, wcig, &c1, &c2);
+              ctr.dp_cells += c1, ctr.dp_cells_full += c2;
+            }
+            __syncwarp();
+          }
+        }
+        if (lane == 0) {
+          FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
+          AlnOut ao;
+          const int nc = ok ? finish_pair(D.P, rv, hapc, wregs, n_regs, D.ext_arena, fs, &ao) : -1;
+          if (nc < 0) {
+            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+            write_invalid(&D.aln[pair]);
+          } else {
+            store_final(D, pair, ao, fs.best, nc);
+            n_aligned += ao.valid;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
+    atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)ctr.dp_cells);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
+    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
   }
 }
 
@@ -600,12 +938,13 @@ struct lgr_ctx {
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_ws, b_fin, b_regs,
       b_defs, b_tasks, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
-      b_ctr, b_ws_big;
+      b_ctr, b_ws_big, b_wreg, b_rsx;
   Dev D;
   bool resident = false;
   int max_read_len = 0, max_hap_len = 0;
   int64_t hap_bytes = 0, read_bytes = 0;
-  int map_blocks = 0, ext_blocks = 0;
+  int map_blocks = 0, ext_blocks = 0, warp_blocks = 0, warp_cap = 64;
+  size_t warp_smem = 0;
   cudaEvent_t ev[12];
   // host staging of helper arrays
   std::vector<int32_t> h_read_grp, h_hap_grp, h_item_hap, h_item_r0, h_item_n, h_grp_mid;
@@ -759,7 +1098,7 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
                     &c->b_mz_n, &c->b_ws, &c->b_fin, &c->b_regs, &c->b_defs, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
-                    &c->b_ctr, &c->b_ws_big};
+                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& e : c->ev) cudaEventDestroy(e);
@@ -769,7 +1108,6 @@ void lgr_destroy(lgr_ctx* c) {
 
 void* lgr_stream(lgr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
-static constexpr int kCapFast = 256;     // anchors per lane in the fast pass
 static constexpr int kCapBig = 16384;    // anchors per lane in the overflow pass
 static constexpr int kBigWarps = 4 * 37; // warps of the overflow pass (workspace = 28 arrays * cap * 4 B per lane)
 
@@ -838,8 +1176,8 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       po += h1 - h0, ao += V;
     }
     for (int h = h0; h < h1; ++h)
-      for (int r = r0; r < r1; r += 32) {
-        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(32, r1 - r));
+      for (int r = r0; r < r1; r += 64) {
+        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(64, r1 - r));
       }
     int32_t mid = c->prm.mid_occ;
     if (in->grp_mid_occ && in->grp_mid_occ[g] > 0) mid = in->grp_mid_occ[g];
@@ -882,15 +1220,35 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int fin_cap = 2 * c->max_read_len + 16;
   const int Lm = std::max(c->max_read_len, 1);
   const int Tmax = Lm + ((c->prm.a + std::max(c->prm.b, c->prm.sc_ambi)) * Lm) / c->prm.e + 2;
+  // warp-per-pair kernel: CAP anchors per pair in shared memory
+  c->warp_cap = c->max_read_len <= 160 ? 64 : 128;
+  c->warp_smem = sizeof(uint64_t) * kIdxSmem + kHapSmem + (size_t)kWarpsPerCta * A_COUNT * c->warp_cap * sizeof(int32_t);
+  {
+    int per_sm = 0;
+    cudaError_t e1, e2;
+    if (c->warp_cap == 64) {
+      e1 = cudaFuncSetAttribute(k_map_warp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_warp<64>, kWarpsPerCta * 32, c->warp_smem);
+    } else {
+      e1 = cudaFuncSetAttribute(k_map_warp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_warp<128>, kWarpsPerCta * 32, c->warp_smem);
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || per_sm < 1) {
+      c->err = "k_map_warp does not fit on this device (shared memory / registers)";
+      return LGR_E_CUDA;
+    }
+    c->warp_blocks = c->sm_count * per_sm;
+  }
   c->ext_blocks = c->sm_count * 4;
-  const int64_t ext_warps = (int64_t)c->ext_blocks * 4;
+  const int64_t ext_warps = std::max<int64_t>((int64_t)c->ext_blocks * 4, (int64_t)c->warp_blocks * kWarpsPerCta);
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
   const int wcig_cap = 2 * Lm + 8;
   const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024, defs_cap = n_pairs + 1024, tasks_cap = 2 * regs_cap;
   const int64_t ext_arena_cap = 4 * n_pairs + (1 << 20);
   const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
-  if ((rc = ensure(c, c->b_ws, sizeof(int32_t) * (size_t)n_threads * A_COUNT * kCapFast)) ||
+  if ((rc = ensure(c, c->b_wreg, sizeof(RegRec) * (size_t)ext_warps * c->warp_cap)) ||
+      (rc = ensure(c, c->b_rsx, sizeof(RadixScratch) * (size_t)ext_warps)) ||
       (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)n_threads * 2 * fin_cap)) ||
       (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_defs, sizeof(DefRec) * (size_t)defs_cap)) ||
       (rc = ensure(c, c->b_tasks, sizeof(TaskRec) * (size_t)tasks_cap)) ||
@@ -922,7 +1280,8 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.idx = (uint64_t*)c->b_idx.p, D.idx_n = (int32_t*)c->b_idx_n.p, D.hap_mid = (int32_t*)c->b_hap_mid.p;
   D.grp_mid = (int32_t*)c->b_grp_mid.p;
   D.mz_x = (uint64_t*)c->b_mz_x.p, D.mz_y = (uint32_t*)c->b_mz_y.p, D.mz_n = (int32_t*)c->b_mz_n.p;
-  D.ws = (int32_t*)c->b_ws.p, D.ws_cap = kCapFast;
+  D.ws = nullptr, D.ws_cap = 0;
+  D.wreg_scratch = (RegRec*)c->b_wreg.p, D.rsx_scratch = (RadixScratch*)c->b_rsx.p;
   D.fin_scratch = (uint32_t*)c->b_fin.p, D.fin_cap = fin_cap;
   D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
   D.defs = (DefRec*)c->b_defs.p, D.defs_cap = defs_cap;
@@ -966,7 +1325,8 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
     launches += 1;
     cudaEventRecord(c->ev[2], s);
-    k_map<false><<<c->map_blocks, 128, 0, s>>>(D);
+    if (c->warp_cap == 64) k_map_warp<64><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
+    else k_map_warp<128><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
     launches += 1;
     cudaEventRecord(c->ev[9], s);
     long long hctr[C_COUNT];
