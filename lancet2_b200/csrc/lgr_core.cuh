@@ -1166,9 +1166,17 @@ struct RegFinal {
   int32_t rs, re, qs, qe, dp_score, dp_max, mlen, blen, n_ambi, n_cig;
 };
 
-// align one reg's pieces into its final cigar + stats.  Returns false on scratch overflow.
-LGR_HD bool finish_reg(const DevParams& P, const ReadView& rv, const uint8_t* hap, const RegRec& reg,
-                       const uint32_t* ext_arena, uint32_t* c, int cap, RegFinal* out) {
+// Assembled-but-unscored reg: cigar in c[0..n), coordinates after mm_fix_cigar, and where the
+// (strand) query / haplotype walk of mm_update_extra starts.
+struct RegAsm {
+  int32_t n, rs, re, qs, qe;  // final mm_reg1_t coordinates (qs/qe on the forward read)
+  int32_t qb, tb;             // strand-query / haplotype offsets of the first cigar column
+  int32_t dp_ext;             // sum of ez.max of the extensions (dp_score without the core)
+};
+
+// align.c: mm_append_cigar x3 + coordinates + mm_fix_cigar.  Scalar.  false on scratch overflow.
+LGR_HD bool assemble_fix_reg(const ReadView& rv, const uint8_t* hap, const RegRec& reg, const uint32_t* ext_arena,
+                             uint32_t* c, int cap, RegAsm* out) {
   const int qlen = rv.qlen;
   const int rev = reg.rev;
   int n = 0;
@@ -1186,17 +1194,9 @@ LGR_HD bool finish_reg(const DevParams& P, const ReadView& rv, const uint8_t* ha
   } else {
     rs1 = reg.c_rs, qs1 = reg.c_qs;
   }
-  {  // ungapped core
-    int32_t score = 0;
-    const int len = reg.c_qe - reg.c_qs;
-    for (int j = 0; j < len; ++j) {
-      const int qc = rv.at(rev, reg.c_qs + j), tc = hap[reg.c_rs + j] & 0xf;
-      if (qc >= 4 || tc >= 4) score += P.e;
-      else score += qc == tc ? P.a : -P.b;
-    }
-    const uint32_t op = (uint32_t)len << 4;
+  {
+    const uint32_t op = (uint32_t)(reg.c_qe - reg.c_qs) << 4;
     cig_append(c, n, cap, &op, 1, ovf);
-    dp_score += score;
   }
   re1 = reg.c_re, qe1 = reg.c_qe;
   if (R.m > 0) {
@@ -1286,11 +1286,29 @@ LGR_HD bool finish_reg(const DevParams& P, const ReadView& rv, const uint8_t* ha
       --n;
     }
   }
-  // ---- mm_update_extra ----
+  out->n = n, out->rs = r_rs, out->re = r_re, out->qs = r_qs, out->qe = r_qe;
+  out->qb = qs1 + qshift, out->tb = rs1 + tshift, out->dp_ext = dp_score;
+  return true;
+}
+
+// align.c: the SR "gap filling" block — ungapped score of the co-linear core (N scores +e2 = +e)
+LGR_HD int32_t core_score_scalar(const DevParams& P, const ReadView& rv, const uint8_t* hap, const RegRec& reg) {
+  int32_t score = 0;
+  const int len = reg.c_qe - reg.c_qs;
+  for (int j = 0; j < len; ++j) {
+    const int qc = rv.at(reg.rev, reg.c_qs + j), tc = hap[reg.c_rs + j] & 0xf;
+    if (qc >= 4 || tc >= 4) score += P.e;
+    else score += qc == tc ? P.a : -P.b;
+  }
+  return score;
+}
+
+// align.c: mm_update_extra (is_eqx = 0, log_gap = 0 under MM_F_SR): mlen / blen / n_ambi / dp_max
+LGR_HD void update_extra_scalar(const DevParams& P, const ReadView& rv, int rev, const uint8_t* hap, int qb, int tb,
+                                const uint32_t* c, int n, RegFinal* out) {
   {
     int32_t toff = 0, qoff = 0, blen = 0, mlen = 0, n_ambi_tot = 0;
     double s = 0.0, mx = 0.0;
-    const int qb = qs1 + qshift, tb = rs1 + tshift;
     for (int k = 0; k < n; ++k) {
       const uint32_t op = c[k] & 0xf;
       const int len = (int)(c[k] >> 4);
@@ -1329,11 +1347,20 @@ LGR_HD bool finish_reg(const DevParams& P, const ReadView& rv, const uint8_t* ha
     out->blen = blen, out->mlen = mlen, out->n_ambi = n_ambi_tot;
     out->dp_max = (int32_t)(mx + .499);
   }
-  out->rs = r_rs, out->re = r_re, out->qs = r_qs, out->qe = r_qe;
-  out->dp_score = dp_score;
-  out->n_cig = n;
+}
+
+// align one reg's pieces into its final cigar + stats.  Returns false on scratch overflow.
+LGR_HD bool finish_reg(const DevParams& P, const ReadView& rv, const uint8_t* hap, const RegRec& reg,
+                       const uint32_t* ext_arena, uint32_t* c, int cap, RegFinal* out) {
+  RegAsm ra;
+  if (!assemble_fix_reg(rv, hap, reg, ext_arena, c, cap, &ra)) return false;
+  update_extra_scalar(P, rv, reg.rev, hap, ra.qb, ra.tb, c, ra.n, out);
+  out->rs = ra.rs, out->re = ra.re, out->qs = ra.qs, out->qe = ra.qe;
+  out->dp_score = ra.dp_ext + core_score_scalar(P, rv, hap, reg);
+  out->n_cig = ra.n;
   return true;
 }
+
 
 // hts::ComputeEditDistance over minimap2's cigar (M/I/D only) with Lancet codes; the S
 // bookends of BuildCigar only advance the query (cigar_utils.h:48-94, genotyper.cpp:45-69).
@@ -1359,51 +1386,11 @@ LGR_HD int32_t edit_distance(const uint8_t* read_codes, int qlen, const uint8_t*
   return nm;
 }
 
-// Finish one pair from its reg records.  regs[0..n_regs) in mm_gen_regs order (after
-// chain_post).  Writes the winning alignment to *out and its cigar to out_cig (cap ops;
-// returns the op count, or -1 on scratch overflow).
-LGR_HD int finish_pair(const DevParams& P, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
-                       const uint32_t* ext_arena, FinishScratch& fs, AlnOut* out) {
-  const int qlen = rv.qlen;
-  // survivors of mm_filter_regs, with the key of mm_hit_sort: (dp_max<<32 | hash).  Ties on
-  // the full key keep the LATER reg first (stable ascending sort, then reversed).
-  int best = -1, n_surv = 0;
-  uint64_t best_key = 0;
-  RegFinal bf;
-  bf.n_cig = 0;
-  // for the final mm_set_parent/mm_select_sub (n_regs only) remember survivors' (qs,qe,rs,re,
-  // score,dp_max,rev,cnt) — at most 8 tracked exactly; n_regs output saturates there.
-  constexpr int kTrack = 8;
-  int32_t s_qs[kTrack], s_qe[kTrack], s_rs[kTrack], s_re[kTrack], s_score[kTrack];
-  uint64_t s_key[kTrack];
-  for (int r = 0; r < n_regs; ++r) {
-    RegFinal rf;
-    if (!finish_reg(P, rv, hap, regs[r], ext_arena, fs.cig, fs.cap, &rf)) return -1;
-    // mm_filter_regs
-    bool flt = false;
-    if (regs[r].cnt < P.min_cnt) flt = true;
-    if (rf.mlen < P.min_sc) flt = true;
-    else if (rf.dp_max < P.min_dp_max) flt = true;
-    else if ((float)rf.qs > (float)qlen * P.max_clip_ratio && (float)(qlen - rf.qe) > (float)qlen * P.max_clip_ratio) flt = true;
-    if (flt) continue;
-    const uint64_t key = (uint64_t)(uint32_t)rf.dp_max << 32 | regs[r].hash;
-    if (n_surv < kTrack) {
-      s_qs[n_surv] = rf.qs, s_qe[n_surv] = rf.qe, s_rs[n_surv] = rf.rs, s_re[n_surv] = rf.re;
-      s_score[n_surv] = regs[r].score, s_key[n_surv] = key;
-    }
-    ++n_surv;
-    if (best < 0 || key >= best_key) {
-      best = r, best_key = key, bf = rf;
-      uint32_t* tmp = fs.best;
-      fs.best = fs.cig;
-      fs.cig = tmp;
-    }
-  }
-  out->valid = 0, out->score = 0, out->rs = out->re = out->qs = out->qe = 0, out->rev = 0, out->dp_score = 0;
-  out->dp_max = 0, out->mlen = out->blen = out->n_ambi = 0, out->nm = 0, out->n_cigar = 0, out->cigar_off = -1;
-  out->n_regs = 0;
-  if (best < 0) return 0;
-  // number of hits mm_map returns: mm_hit_sort order, mm_set_parent, mm_select_sub(check_strand=0)
+// number of hits mm_map returns for the survivors of mm_filter_regs: mm_hit_sort order,
+// mm_set_parent, mm_select_sub(check_strand = 0).  Tracked exactly for up to kTrack survivors.
+constexpr int kTrack = 8;
+LGR_HD int select_returned(const DevParams& P, int n_surv, const int32_t* s_qs, const int32_t* s_qe, const int32_t* s_rs,
+                           const int32_t* s_re, const int32_t* s_score, const uint64_t* s_key) {
   int n_ret = n_surv;
   if (n_surv > 1 && n_surv <= kTrack && P.pri_ratio > 0.0f) {
     int ord[kTrack];
@@ -1477,6 +1464,53 @@ LGR_HD int finish_pair(const DevParams& P, const ReadView& rv, const uint8_t* ha
     }
     n_ret = kept;
   }
+  return n_ret;
+}
+
+// Finish one pair from its reg records.  regs[0..n_regs) in mm_gen_regs order (after
+// chain_post).  Writes the winning alignment to *out and its cigar to out_cig (cap ops;
+// returns the op count, or -1 on scratch overflow).
+LGR_HD int finish_pair(const DevParams& P, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
+                       const uint32_t* ext_arena, FinishScratch& fs, AlnOut* out) {
+  const int qlen = rv.qlen;
+  // survivors of mm_filter_regs, with the key of mm_hit_sort: (dp_max<<32 | hash).  Ties on
+  // the full key keep the LATER reg first (stable ascending sort, then reversed).
+  int best = -1, n_surv = 0;
+  uint64_t best_key = 0;
+  RegFinal bf;
+  bf.n_cig = 0;
+  // for the final mm_set_parent/mm_select_sub (n_regs only) remember survivors' (qs,qe,rs,re,
+  // score,dp_max,rev,cnt) — at most 8 tracked exactly; n_regs output saturates there.
+  int32_t s_qs[kTrack], s_qe[kTrack], s_rs[kTrack], s_re[kTrack], s_score[kTrack];
+  uint64_t s_key[kTrack];
+  for (int r = 0; r < n_regs; ++r) {
+    RegFinal rf;
+    if (!finish_reg(P, rv, hap, regs[r], ext_arena, fs.cig, fs.cap, &rf)) return -1;
+    // mm_filter_regs
+    bool flt = false;
+    if (regs[r].cnt < P.min_cnt) flt = true;
+    if (rf.mlen < P.min_sc) flt = true;
+    else if (rf.dp_max < P.min_dp_max) flt = true;
+    else if ((float)rf.qs > (float)qlen * P.max_clip_ratio && (float)(qlen - rf.qe) > (float)qlen * P.max_clip_ratio) flt = true;
+    if (flt) continue;
+    const uint64_t key = (uint64_t)(uint32_t)rf.dp_max << 32 | regs[r].hash;
+    if (n_surv < kTrack) {
+      s_qs[n_surv] = rf.qs, s_qe[n_surv] = rf.qe, s_rs[n_surv] = rf.rs, s_re[n_surv] = rf.re;
+      s_score[n_surv] = regs[r].score, s_key[n_surv] = key;
+    }
+    ++n_surv;
+    if (best < 0 || key >= best_key) {
+      best = r, best_key = key, bf = rf;
+      uint32_t* tmp = fs.best;
+      fs.best = fs.cig;
+      fs.cig = tmp;
+    }
+  }
+  out->valid = 0, out->score = 0, out->rs = out->re = out->qs = out->qe = 0, out->rev = 0, out->dp_score = 0;
+  out->dp_max = 0, out->mlen = out->blen = out->n_ambi = 0, out->nm = 0, out->n_cigar = 0, out->cigar_off = -1;
+  out->n_regs = 0;
+  if (best < 0) return 0;
+  const int n_ret = select_returned(P, n_surv, s_qs, s_qe, s_rs, s_re, s_score, s_key);
   out->valid = 1;
   out->score = regs[best].score;
   out->rs = bf.rs, out->re = bf.re, out->qs = bf.qs, out->qe = bf.qe;

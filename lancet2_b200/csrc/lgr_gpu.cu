@@ -506,9 +506,7 @@ __global__ void __launch_bounds__(128) k_ext_big(Dev D) {
 //   finish    scalar core on lane 0 (cigar assembly, mm_fix_cigar, mm_update_extra, NM)
 // Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_map<true>).
 // ---------------------------------------------------------------------------------------
-constexpr int kWarpsPerCta = 8;
-constexpr int kHapSmem = 2048;   // haplotype code bytes staged per CTA
-constexpr int kIdxSmem = 768;    // minimizer table entries staged per CTA
+constexpr int kWarpsPerCta = 4;
 
 template <int CAP>
 __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const Ws<1>& ws, RadixScratch* rsx,
@@ -715,13 +713,199 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
   return kMapOk;
 }
 
+// ---- warp-parallel pieces of the finish phase (all 32 lanes call; results are uniform) ----
+__device__ __forceinline__ int32_t warp_core_score(const DevParams& P, const ReadView& rv, int rev, const uint8_t* hap,
+                                                   int c_qs, int c_rs, int len) {
+  const int lane = threadIdx.x & 31;
+  int32_t sc = 0;
+  for (int j = lane; j < len; j += 32) {
+    const int qc = rv.at(rev, c_qs + j), tc = hap[c_rs + j] & 0xf;
+    sc += (qc >= 4 || tc >= 4) ? P.e : (qc == tc ? P.a : -P.b);
+  }
+  return __reduce_add_sync(0xffffffffu, sc);
+}
+
+// mm_update_extra: the running score s = max(s + m, 0) with its maximum is a (max,+) recurrence;
+// a chunk of 32 columns is folded with an ordered tree reduction of (A,B,C,D):
+//   s_out = max(s + A, B), best = max(s + C, D).  All quantities are integers (upstream keeps them
+// in doubles that only ever hold integers, dp_max = (int)(max + .499)).
+__device__ __noinline__ void warp_update_extra(const DevParams& P, const ReadView& rv, int rev, const uint8_t* hap, int qb,
+                                               int tb, const uint32_t* c, int n, RegFinal* out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  constexpr int NEG = -(1 << 28);
+  int32_t toff = 0, qoff = 0, blen = 0, mlen = 0, n_ambi_tot = 0, s = 0, mx = 0;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t op = c[k] & 0xf;
+    const int len = (int)(c[k] >> 4);
+    if (op == 0) {
+      for (int base = 0; base < len; base += 32) {
+        const int l = base + lane;
+        const bool valid = l < len;
+        int m = 0;
+        bool ambi = false, diff = false;
+        if (valid) {
+          const int cq = rv.at(rev, qb + qoff + l), ct = hap[tb + toff + l] & 0xf;
+          ambi = ct > 3 || cq > 3;
+          diff = !ambi && ct != cq;
+          m = sub_score(P, ct, cq);
+        }
+        const int na = __popc(__ballot_sync(full, ambi)), nd = __popc(__ballot_sync(full, diff));
+        const int cnt = len - base < 32 ? len - base : 32;
+        blen += cnt - na, mlen += cnt - (na + nd), n_ambi_tot += na;
+        if (__ballot_sync(full, valid && m < 0) == 0) {
+          s += __reduce_add_sync(full, m);
+          if (s > mx) mx = s;
+        } else {
+          int A = valid ? m : 0, B = valid ? 0 : NEG, C = valid ? m : NEG, Dd = valid ? 0 : NEG;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int Ay = __shfl_down_sync(full, A, o), By = __shfl_down_sync(full, B, o);
+            const int Cy = __shfl_down_sync(full, C, o), Dy = __shfl_down_sync(full, Dd, o);
+            if (lane + o < 32) {
+              int d2 = B + Cy;
+              if (Dd > d2) d2 = Dd;
+              if (Dy > d2) d2 = Dy;
+              const int c2 = A + Cy > C ? A + Cy : C;
+              const int b2 = B + Ay > By ? B + Ay : By;
+              A = A + Ay, B = b2, C = c2, Dd = d2;
+              if (B < NEG) B = NEG;
+              if (C < NEG) C = NEG;
+              if (Dd < NEG) Dd = NEG;
+            }
+          }
+          A = __shfl_sync(full, A, 0), B = __shfl_sync(full, B, 0), C = __shfl_sync(full, C, 0), Dd = __shfl_sync(full, Dd, 0);
+          int best = s + C > Dd ? s + C : Dd;
+          if (best > mx) mx = best;
+          s = s + A > B ? s + A : B;
+        }
+      }
+      toff += len, qoff += len;
+    } else if (op == 1 || op == 2) {
+      int na = 0;
+      for (int base = 0; base < len; base += 32) {
+        const int l = base + lane;
+        bool ambi = false;
+        if (l < len) ambi = op == 1 ? rv.at(rev, qb + qoff + l) > 3 : (hap[tb + toff + l] & 0xf) > 3;
+        na += __popc(__ballot_sync(full, ambi));
+      }
+      blen += len - na, n_ambi_tot += na;
+      s -= P.q + P.e;
+      if (s < 0) s = 0;
+      if (op == 1) qoff += len;
+      else toff += len;
+    } else if (op == 3) {
+      toff += len;
+    }
+  }
+  out->blen = blen, out->mlen = mlen, out->n_ambi = n_ambi_tot, out->dp_max = mx;
+}
+
+__device__ __forceinline__ int32_t warp_edit_distance(const uint8_t* read_codes, int qlen, const uint8_t* hap, int rs, int re,
+                                                      int qs, const uint32_t* c, int n) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int32_t nm = 0;
+  int qpos = qs, tpos = 0;
+  const int tn = re - rs;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t op = c[k] & 0xf;
+    const int len = (int)(c[k] >> 4);
+    if (op == 0) {
+      for (int base = 0; base < len; base += 32) {
+        const int l = base + lane;
+        bool mis = false;
+        if (l < len) {
+          const int qp = qpos + l, tp = tpos + l;
+          mis = qp < qlen && tp < tn && (read_codes[qp] >> 4) != (hap[rs + tp] >> 4);
+        }
+        nm += __popc(__ballot_sync(full, mis));
+      }
+      qpos += len, tpos += len;
+    } else if (op == 1) {
+      nm += len, qpos += len;
+    } else if (op == 2) {
+      nm += len, tpos += len;
+    } else if (op == 3) {
+      tpos += len;
+    }
+  }
+  return nm;
+}
+
+// finish_pair (lgr_core.cuh) with the per-base loops spread over the warp.  Uniform control flow;
+// cigar assembly / mm_fix_cigar stay scalar on lane 0.  Returns the op count of the winning cigar
+// (in fs.best), or -1 on scratch overflow; *out is valid on every lane.
+__device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
+                                             FinishScratch& fs, AlnOut* out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const DevParams& P = D.P;
+  const int qlen = rv.qlen;
+  int best = -1, n_surv = 0;
+  uint64_t best_key = 0;
+  RegFinal bf;
+  bf.n_cig = 0;
+  int32_t s_qs[kTrack], s_qe[kTrack], s_rs[kTrack], s_re[kTrack], s_score[kTrack];
+  uint64_t s_key[kTrack];
+  for (int r = 0; r < n_regs; ++r) {
+    RegAsm ra;
+    int okf = 1;
+    if (lane == 0) okf = assemble_fix_reg(rv, hap, regs[r], D.ext_arena, fs.cig, fs.cap, &ra) ? 1 : 0;
+    okf = __shfl_sync(full, okf, 0);
+    if (!okf) return -1;
+    ra.n = __shfl_sync(full, ra.n, 0), ra.rs = __shfl_sync(full, ra.rs, 0), ra.re = __shfl_sync(full, ra.re, 0);
+    ra.qs = __shfl_sync(full, ra.qs, 0), ra.qe = __shfl_sync(full, ra.qe, 0), ra.qb = __shfl_sync(full, ra.qb, 0);
+    ra.tb = __shfl_sync(full, ra.tb, 0), ra.dp_ext = __shfl_sync(full, ra.dp_ext, 0);
+    __syncwarp();
+    const int rev = regs[r].rev, c_qs = regs[r].c_qs, c_qe = regs[r].c_qe, c_rs = regs[r].c_rs;
+    const int32_t score = regs[r].score, cnt = regs[r].cnt;
+    const uint32_t hash = regs[r].hash;
+    RegFinal rf;
+    warp_update_extra(P, rv, rev, hap, ra.qb, ra.tb, fs.cig, ra.n, &rf);
+    rf.rs = ra.rs, rf.re = ra.re, rf.qs = ra.qs, rf.qe = ra.qe, rf.n_cig = ra.n;
+    rf.dp_score = ra.dp_ext + warp_core_score(P, rv, rev, hap, c_qs, c_rs, c_qe - c_qs);
+    bool flt = false;
+    if (cnt < P.min_cnt) flt = true;
+    if (rf.mlen < P.min_sc) flt = true;
+    else if (rf.dp_max < P.min_dp_max) flt = true;
+    else if ((float)rf.qs > (float)qlen * P.max_clip_ratio && (float)(qlen - rf.qe) > (float)qlen * P.max_clip_ratio) flt = true;
+    if (flt) continue;
+    const uint64_t key = (uint64_t)(uint32_t)rf.dp_max << 32 | hash;
+    if (n_surv < kTrack) {
+      s_qs[n_surv] = rf.qs, s_qe[n_surv] = rf.qe, s_rs[n_surv] = rf.rs, s_re[n_surv] = rf.re;
+      s_score[n_surv] = score, s_key[n_surv] = key;
+    }
+    ++n_surv;
+    if (best < 0 || key >= best_key) {
+      best = r, best_key = key, bf = rf;
+      uint32_t* tmp = fs.best;
+      fs.best = fs.cig;
+      fs.cig = tmp;
+    }
+  }
+  out->valid = 0, out->score = 0, out->rs = out->re = out->qs = out->qe = 0, out->rev = 0, out->dp_score = 0;
+  out->dp_max = 0, out->mlen = out->blen = out->n_ambi = 0, out->nm = 0, out->n_cigar = 0, out->cigar_off = -1;
+  out->n_regs = 0;
+  if (best < 0) return 0;
+  const int n_ret = n_surv > 1 ? select_returned(P, n_surv, s_qs, s_qe, s_rs, s_re, s_score, s_key) : n_surv;
+  out->valid = 1;
+  out->score = regs[best].score;
+  out->rs = bf.rs, out->re = bf.re, out->qs = bf.qs, out->qe = bf.qe;
+  out->rev = regs[best].rev;
+  out->dp_score = bf.dp_score, out->dp_max = bf.dp_max, out->mlen = bf.mlen, out->blen = bf.blen;
+  out->n_ambi = bf.n_ambi;
+  out->n_cigar = bf.n_cig;
+  out->n_regs = n_ret;
+  out->nm = warp_edit_distance(rv.codes, qlen, hap, bf.rs, bf.re, bf.qs, fs.best, bf.n_cig);
+  return bf.n_cig;
+}
+
+constexpr int kWarpItemReads = 16;  // reads per warp work item (all against one haplotype)
+
 template <int CAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 5) k_map_warp(Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* s_idx = reinterpret_cast<uint64_t*>(smem_raw);
-  uint8_t* s_hap = smem_raw + sizeof(uint64_t) * kIdxSmem;
-  int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw + sizeof(uint64_t) * kIdxSmem + kHapSmem);
-  __shared__ long long s_item;
+  int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kWarpsPerCta + warp;
@@ -736,9 +920,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
   ChainCounters ctr{0, 0, 0, 0};
   long long n_aligned = 0;
   for (;;) {
-    if (threadIdx.x == 0) s_item = atomicAdd((unsigned long long*)&D.ctr[C_ITEM], 1ULL);
-    __syncthreads();
-    const long long item = s_item;
+    long long item = 0;
+    if (lane == 0) item = atomicAdd((unsigned long long*)&D.ctr[C_ITEM], 1ULL);
+    item = __shfl_sync(full, item, 0);
     if (item >= D.n_items) break;
     const int h = D.item_hap[item], r0 = D.item_r0[item], nr = D.item_n[item];
     const int64_t hoff = D.hap_off[h];
@@ -746,19 +930,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
     const int idx_n = D.idx_n[h];
     const uint8_t* hapc = D.hap_codes + hoff;
     const uint64_t* idx = D.idx + hoff;
-    if (hlen <= kHapSmem) {
-      for (int i = threadIdx.x; i < hlen; i += blockDim.x) s_hap[i] = hapc[i];
-      hapc = s_hap;
-    }
-    if (idx_n <= kIdxSmem) {
-      for (int i = threadIdx.x; i < idx_n; i += blockDim.x) s_idx[i] = idx[i];
-      idx = s_idx;
-    }
-    __syncthreads();
     const int g = D.hap_grp[h];
     const int h_local = h - D.grp_hap_begin[g];
     const int mid_occ = D.grp_mid[g];
-    for (int rr = warp; rr < nr; rr += kWarpsPerCta) {
+    for (int rr = 0; rr < nr; ++rr) {
       const int r = r0 + rr;
       const int64_t pair = D.pair_off[r] + h_local;
       const int64_t roff = D.read_off[r];
@@ -781,8 +956,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
       } else if (st == kMapNoHit) {
         if (lane == 0) write_invalid(&D.aln[pair]);
       } else {
-        // extensions of every surviving reg, then finish on lane 0
-        bool ok = true;
+        // extensions of every surviving reg, then finish
+        int okw = 1;
         for (int i = 0; i < n_regs; ++i) {
           if (lane == 0) export_reg<1>(ws, i, qlen, &wregs[i]);
           __syncwarp();
@@ -805,7 +980,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
                   }
                   return o;
                 };
-                ok &= run_ext_scalar(D.P, rv, hapc, &wregs[i], side, sdir, ha, fa, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, &ctr);
+                if (!run_ext_scalar(D.P, rv, hapc, &wregs[i], side, sdir, ha, fa, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, &ctr)) okw = 0;
               }
             } else {
               long long c1 = 0, c2 = 0;
@@ -815,10 +990,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
             __syncwarp();
           }
         }
+        okw = __shfl_sync(full, okw, 0);
+        FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
+        AlnOut ao;
+        const int nc = okw ? finish_pair_warp(D, rv, hapc, wregs, n_regs, fs, &ao) : -1;
         if (lane == 0) {
-          FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
-          AlnOut ao;
-          const int nc = ok ? finish_pair(D.P, rv, hapc, wregs, n_regs, D.ext_arena, fs, &ao) : -1;
           if (nc < 0) {
             atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
             write_invalid(&D.aln[pair]);
@@ -830,7 +1006,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_map_warp(Dev D) {
       }
       __syncwarp();
     }
-    __syncthreads();
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
@@ -1176,8 +1351,8 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       po += h1 - h0, ao += V;
     }
     for (int h = h0; h < h1; ++h)
-      for (int r = r0; r < r1; r += 64) {
-        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(64, r1 - r));
+      for (int r = r0; r < r1; r += kWarpItemReads) {
+        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(kWarpItemReads, r1 - r));
       }
     int32_t mid = c->prm.mid_occ;
     if (in->grp_mid_occ && in->grp_mid_occ[g] > 0) mid = in->grp_mid_occ[g];
@@ -1222,7 +1397,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int Tmax = Lm + ((c->prm.a + std::max(c->prm.b, c->prm.sc_ambi)) * Lm) / c->prm.e + 2;
   // warp-per-pair kernel: CAP anchors per pair in shared memory
   c->warp_cap = c->max_read_len <= 160 ? 64 : 128;
-  c->warp_smem = sizeof(uint64_t) * kIdxSmem + kHapSmem + (size_t)kWarpsPerCta * A_COUNT * c->warp_cap * sizeof(int32_t);
+  c->warp_smem = (size_t)kWarpsPerCta * A_COUNT * c->warp_cap * sizeof(int32_t);
   {
     int per_sm = 0;
     cudaError_t e1, e2;
