@@ -392,7 +392,8 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
     int32_t diag = j == 0 ? 0 : -(q + e * j);    // H(-1, j-1)
     int32_t h_last = 0, f_out = 0;
     uint8_t* dblk = dir + (size_t)blk * dstride * 32;
-    const int nsteps = T + 31;
+    const int rows = m - blk * 32 < 32 ? m - blk * 32 : 32;
+    const int nsteps = T + rows - 1;
     for (int s = 0; s < nsteps; ++s) {
       int32_t up_h = __shfl_up_sync(0xffffffffu, h_last, 1);
       int32_t up_f = __shfl_up_sync(0xffffffffu, f_out, 1);
@@ -636,38 +637,62 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
       if (valid && pj >= 0) t[pj] = i;
       __syncwarp();
       const bool stamped = valid && t[j] == i;
-      // exclusive prefix max of the candidate scores (sequential "sc > max_f" test)
-      int32_t pm = sc;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int32_t v = __shfl_up_sync(full, pm, o);
-        if (lane >= o && v > pm) pm = v;
-      }
-      int32_t excl = __shfl_up_sync(full, pm, 1);
-      if (lane == 0) excl = INT32_MIN;
-      if (max_f > excl) excl = max_f;
-      const bool newmax = valid && sc > excl;
-      // saturating skip counter: n -> max(n + a, b) per lane, composed left to right
-      const int ev = newmax ? -1 : (stamped ? 1 : 0);
-      int a = ev, b = ev == 1 ? 1 : 0;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int au = __shfl_up_sync(full, a, o), bu = __shfl_up_sync(full, b, o);
-        if (lane >= o) {
-          const int nb = bu + a;
-          b = nb > b ? nb : b;
-          a = au + a;
+      // record setters of the sequential "sc > max_f" test: lanes whose score exceeds max_f and
+      // every earlier lane of the chunk.  Usually there is at most one, so they are peeled off
+      // with ballots instead of a prefix-max scan.
+      unsigned nmask_all = 0;
+      {
+        int32_t cur = max_f;
+        unsigned cand = __ballot_sync(full, valid && sc > cur);
+        while (cand) {
+          const int l = __ffs(cand) - 1;
+          nmask_all |= 1u << l;
+          cur = __shfl_sync(full, sc, l);
+          cand = __ballot_sync(full, valid && sc > cur) & ~((2u << l) - 1);
         }
       }
-      int n_after = n_skip + a;
-      if (b > n_after) n_after = b;
-      const unsigned brk = __ballot_sync(full, ev == 1 && n_after > P.max_skip);
-      const int last = brk ? __ffs(brk) - 1 : 31;
-      const unsigned nmask = __ballot_sync(full, newmax) & (last == 31 ? 0xffffffffu : ((2u << last) - 1));
+      const bool newmax = (nmask_all >> lane) & 1;
+      const int ev = newmax ? -1 : (stamped ? 1 : 0);
+      const unsigned smask = __ballot_sync(full, ev == 1);
+      int last = 31;
+      unsigned brk = 0;
+      // the skip counter only ever decrements on a record setter; when every record setter comes
+      // before the first stamped lane and the counter enters at 0 (or there is none), the
+      // decrements are no-ops and the counter is a running popcount of the stamped lanes
+      const bool simple = nmask_all == 0 || (n_skip == 0 && (smask == 0 || (31 - __clz(nmask_all)) < (__ffs(smask) - 1)));
+      if (simple) {
+        const int need = P.max_skip + 1 - n_skip;  // stamped lanes until the break
+        const int tot = __popc(smask);
+        if (need <= tot) {
+          last = (int)__fns(smask, 0, need);
+          brk = 1u << last;
+          n_skip = P.max_skip + 1;
+        } else {
+          n_skip += tot;
+        }
+      } else {
+        // general case: n -> max(n + a, b) per lane, composed left to right ((max,+) scan)
+        int a = ev, b = ev == 1 ? 1 : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int au = __shfl_up_sync(full, a, o), bu = __shfl_up_sync(full, b, o);
+          if (lane >= o) {
+            const int nb = bu + a;
+            b = nb > b ? nb : b;
+            a = au + a;
+          }
+        }
+        int n_after = n_skip + a;
+        if (b > n_after) n_after = b;
+        brk = __ballot_sync(full, ev == 1 && n_after > P.max_skip);
+        last = brk ? __ffs(brk) - 1 : 31;
+        n_skip = __shfl_sync(full, n_after, last);
+      }
+      const unsigned nmask = nmask_all & (last == 31 ? 0xffffffffu : ((2u << last) - 1));
       if (nmask) {
         const int src = 31 - __clz(nmask);
         max_f = __shfl_sync(full, sc, src);
         max_j = jb - src;
       }
-      n_skip = __shfl_sync(full, n_after, last);
       const int n_in = jb - st + 1 < 32 ? jb - st + 1 : 32;
       if (brk) {
         n_iter += last + 1;
@@ -900,6 +925,153 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
   return bf.n_cig;
 }
 
+// ---------------------------------------------------------------------------------------
+// warp_chain_tail_fast: map_chain_tail for the overwhelmingly common shape — every anchor with
+// f >= min_sc lies on ONE chain that is accepted.  All lanes execute it uniformly on the shared
+// arrays.  Returns kMapOk (one reg, R_* / stretch filled exactly as map_chain_tail would),
+// kMapNoHit, or -2 when the shape is different (then lane 0 runs the exact scalar map_chain_tail
+// from scratch).
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ int warp_chain_tail_fast(const DevParams& P, int qlen, int hap_len, uint32_t name_hash, const Ws<1>& ws, int n_a) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  auto sx = ws.arr(A_SX), sy = ws.arr(A_SY), f = ws.arr(A_F), p = ws.arr(A_P), t = ws.arr(A_T), v = ws.arr(A_V);
+  auto cx = ws.arr(A_CX), cy = ws.arr(A_CY);
+  // z = anchors with f >= min_sc; its top (processed first upstream) is the max (f, index)
+  int n_z = 0;
+  int32_t bf = INT32_MIN;
+  int bi = -1;
+  for (int base = 0; base < n_a; base += 32) {
+    const int i = base + lane;
+    const bool in = i < n_a && f[i] >= P.min_sc;
+    n_z += __popc(__ballot_sync(full, in));
+    if (in && (f[i] > bf || (f[i] == bf && i > bi))) bf = f[i], bi = i;
+    if (i < n_a) t[i] = 0;
+  }
+  if (n_z == 0) return kMapNoHit;
+  if (n_z > 64) return -2;  // upstream's unstable radix pass decides the order: exact scalar path
+  for (int o = 16; o > 0; o >>= 1) {
+    const int32_t of = __shfl_xor_sync(full, bf, o);
+    const int oi = __shfl_xor_sync(full, bi, o);
+    if (of > bf || (of == bf && oi > bi)) bf = of, bi = oi;
+  }
+  __syncwarp();
+  // mg_chain_bk_end + collection for the top anchor (t[] is all zero: first chain)
+  const int zi = bi;
+  const int32_t zx = bf;
+  int end_i;
+  {
+    int i = zi, max_i = zi;
+    int32_t max_s = 0;
+    do {
+      i = p[i];
+      const int32_t s = i < 0 ? zx : zx - f[i];
+      if (s > max_s) max_s = s, max_i = i;
+      else if (max_s - s > P.bw) break;
+    } while (i >= 0);
+    end_i = max_i;
+  }
+  int cnt = 0;
+  int i;
+  for (i = zi; i != end_i; i = p[i]) {
+    if (lane == 0) v[cnt] = i, t[i] = 1;
+    ++cnt;
+  }
+  const int32_t sc = i < 0 ? zx : zx - f[i];
+  __syncwarp();
+  if (!(sc >= P.min_sc && cnt >= P.min_cnt)) return -2;  // rejected top chain: general path
+  // any other candidate left?  (they would start further chains upstream)
+  {
+    bool other = false;
+    for (int j = lane; j < n_a; j += 32) other |= f[j] >= P.min_sc && t[j] == 0;
+    if (__any_sync(full, other)) return -2;
+  }
+  // compact_a: ascending anchors of the chain
+  for (int j = lane; j < cnt; j += 32) {
+    const int id = v[cnt - 1 - j];
+    cx[j] = sx[id], cy[j] = sy[id];
+  }
+  __syncwarp();
+  // mm_gen_regs for the single chain
+  uint32_t hash = name_hash;
+  hash ^= wang_hash((uint32_t)qlen) + wang_hash((uint32_t)P.seed);
+  hash = wang_hash(hash);
+  const uint32_t x0 = (uint32_t)cx[0], y0 = (uint32_t)cy[0];
+  const uint32_t h = (uint32_t)hash64_full((hash64_full(anchor_x64(x0)) + hash64_full(anchor_y64(y0))) ^ hash);
+  const int rev = (int)(x0 >> 31);
+  // mm_max_stretch (uniform sequential scan over the chain)
+  int as1 = 0, cnt1 = cnt;
+  if (cnt >= 2) {
+    int32_t max_score = -1, max_i = -1, max_len = 0;
+    int32_t score = anchor_span(y0), len = 1;
+    int k;
+    uint32_t px = x0, py = y0;
+    for (k = 0; k < cnt - 1; ++k) {
+      const uint32_t nx = (uint32_t)cx[k + 1], ny = (uint32_t)cy[k + 1];
+      const int32_t q_span = anchor_span(ny);
+      const int32_t lr = anchor_rpos(nx) - anchor_rpos(px);
+      const int32_t lq = anchor_qpos(ny) - anchor_qpos(py);
+      if (lq == lr) {
+        score += lq < q_span ? lq : q_span;
+        ++len;
+      } else {
+        if (score > max_score) max_score = score, max_len = len, max_i = k - len + 1;
+        score = q_span;
+        len = 1;
+      }
+      px = nx, py = ny;
+    }
+    if (score > max_score) max_score = score, max_len = len, max_i = k - len + 1;
+    as1 = max_i, cnt1 = max_len;
+  }
+  const uint32_t ys = (uint32_t)cy[as1];
+  const int32_t rs = anchor_rpos((uint32_t)cx[as1]) + 1 - anchor_span(ys);
+  const int32_t qs = anchor_qpos(ys) + 1 - anchor_span(ys);
+  const int32_t re = anchor_rpos((uint32_t)cx[as1 + cnt1 - 1]) + 1;
+  const int32_t qe = anchor_qpos((uint32_t)cy[as1 + cnt1 - 1]) + 1;
+  int32_t l = qs;
+  l += l * P.a + P.end_bonus > P.q ? (l * P.a + P.end_bonus - P.q) / P.e : 0;
+  const int32_t rs0 = rs - l > 0 ? rs - l : 0;
+  l = qlen - qe;
+  l += l * P.a + P.end_bonus > P.q ? (l * P.a + P.end_bonus - P.q) / P.e : 0;
+  const int32_t re0 = re + l < hap_len ? re + l : hap_len;
+  __syncwarp();
+  if (lane == 0) {
+    ws.arr(R_SCORE)[0] = sc, ws.arr(R_CNT)[0] = cnt, ws.arr(R_AS)[0] = 0, ws.arr(R_HASH)[0] = (int32_t)((uint32_t)cnt ^ h);
+    ws.arr(R_REV)[0] = rev, ws.arr(R_PARENT)[0] = 0, ws.arr(R_ID)[0] = 0;
+    ws.arr(R_QS)[0] = qs, ws.arr(R_QE)[0] = qe, ws.arr(R_RS)[0] = rs, ws.arr(R_RE)[0] = re;
+    f[0] = rs0, p[0] = re0;
+  }
+  __syncwarp();
+  return kMapOk;
+}
+
+// exact-match shortcut of an extension tail: if the m query bases equal the first m target
+// bases (no ambiguity codes), the only path reaching the score m*a is the gap-free diagonal, so
+// ksw2 would return max = mqe = m*a at target offset m-1 with the cigar mM — no DP needed.
+__device__ __forceinline__ bool warp_ext_exact(const DevParams& P, const ReadView& rv, const uint8_t* hapc, RegRec* reg, int side,
+                                               int64_t* cells_full) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int m = reg->ext[side].m, n = reg->ext[side].n;
+  if (n < m || P.a <= 0) return false;
+  ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
+  ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
+  bool same = true;
+  for (int j = lane; j < m; j += 32) {
+    const int qc = qf(j), tc = tf(j);
+    same &= qc == tc && qc < 4;
+  }
+  if (!__all_sync(full, same)) return false;
+  if (lane == 0) {
+    ExtRec& E = reg->ext[side];
+    E.max = m * P.a, E.mqe_t = m - 1, E.n_cig = 1, E.cig_off = -1, E.inl[0] = (uint32_t)m << 4;
+    *cells_full += (int64_t)m * n;
+  }
+  __syncwarp();
+  return true;
+}
+
 constexpr int kWarpItemReads = 16;  // reads per warp work item (all against one haplotype)
 
 template <int CAP>
@@ -943,9 +1115,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) k_map_warp(Dev D) {
       int n_a = 0, n_regs = 0;
       int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, ws, rsx, &ctr, &n_a) : kMapNoHit;
       if (st == kMapOk) {
-        if (lane == 0) st = map_chain_tail<1>(D.P, qlen, hlen, pin.name_hash, ws, rsx, n_a, &n_regs);
-        st = __shfl_sync(full, st, 0);
-        n_regs = __shfl_sync(full, n_regs, 0);
+        st = warp_chain_tail_fast(D.P, qlen, hlen, pin.name_hash, ws, n_a);
+        n_regs = 1;
+        if (st == -2) {
+          if (lane == 0) st = map_chain_tail<1>(D.P, qlen, hlen, pin.name_hash, ws, rsx, n_a, &n_regs);
+          st = __shfl_sync(full, st, 0);
+          n_regs = __shfl_sync(full, n_regs, 0);
+        }
       }
       if (st == kMapOverflow) {
         if (lane == 0) {
@@ -967,6 +1143,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) k_map_warp(Dev D) {
             m = __shfl_sync(full, m, 0);
             small = __shfl_sync(full, small, 0);
             if (m <= 0) continue;
+            if (warp_ext_exact(D.P, rv, hapc, &wregs[i], side, &ctr.dp_cells_full)) continue;
             if (small) {
               if (lane == 0) {
                 uint8_t sdir[kSmallCells];
