@@ -46,9 +46,6 @@ enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP =
 struct DefRec {   // a parked pair
   int32_t read, hap, first_reg, n_regs;
 };
-struct TaskRec {  // one queued long tail
-  int32_t reg, side, read, hap;
-};
 
 struct Dev {      // everything the kernels need, passed by value
   DevParams P;
@@ -82,7 +79,6 @@ struct Dev {      // everything the kernels need, passed by value
   // parked pairs / tails
   RegRec* regs;  int64_t regs_cap;
   DefRec* defs;  int64_t defs_cap;
-  TaskRec* tasks; int64_t tasks_cap;
   uint32_t* ext_arena; int64_t ext_arena_cap;
   int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
   // k_ext_big scratch
@@ -322,22 +318,7 @@ __global__ void __launch_bounds__(128) k_map(Dev D) {
             write_invalid(&D.aln[pair]);
           } else {
             D.defs[di] = DefRec{r, h, (int32_t)first, n_regs};
-            for (int i = 0; i < n_regs; ++i) {
-              RegRec rr;
-              export_reg<32>(ws, i, qlen, &rr);
-              for (int side = 0; side < 2; ++side) {
-                const int m = rr.ext[side].m;
-                if (m <= 0) continue;
-                if (ext_is_small(D.P, rr.ext[side])) {
-                  run_ext_scalar(D.P, rv, hapc, &rr, side, dir, hcol, ecol, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, &ctr);
-                } else {
-                  const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
-                  if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
-                  else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
-                }
-              }
-              D.regs[first + i] = rr;
-            }
+            for (int i = 0; i < n_regs; ++i) export_reg<32>(ws, i, qlen, &D.regs[first + i]);  // extensions: k_finish_warp
           }
         }
       }
@@ -463,32 +444,6 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
     *cells_full += (long long)m * n;
   }
   __syncwarp();
-}
-
-// k_ext_big: one warp per queued long tail (tails parked by the overflow pass k_map<true>)
-__global__ void __launch_bounds__(128) k_ext_big(Dev D) {
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  uint8_t* dir = D.dir_scratch + (size_t)gwarp * D.dir_per_warp;
-  int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
-  int32_t* Fb = Hb + D.bnd_per_warp / 2;
-  uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
-  const long long n_tasks = D.ctr[C_NTASK] < D.tasks_cap ? D.ctr[C_NTASK] : D.tasks_cap;
-  long long cells = 0, cells_full = 0;
-  for (;;) {
-    long long ti = 0;
-    if (lane == 0) ti = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
-    ti = __shfl_sync(0xffffffffu, ti, 0);
-    if (ti >= n_tasks) break;
-    const TaskRec tk = D.tasks[ti];
-    const int64_t roff = D.read_off[tk.read], hoff = D.hap_off[tk.hap];
-    ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
-    ext_dp_warp(D, D.regs + tk.reg, tk.side, rv, D.hap_codes + hoff, dir, Hb, Fb, wcig, &cells, &cells_full);
-  }
-  if (lane == 0) {
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)cells);
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)cells_full);
-  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1074,23 +1029,18 @@ __device__ __forceinline__ bool warp_ext_exact(const DevParams& P, const ReadVie
 
 constexpr int kWarpItemReads = 16;  // reads per warp work item (all against one haplotype)
 
+// Phase A kernel: seeds → anchors → chain DP → regs, one warp per pair.  Every pair with at least
+// one reg is parked: its RegRecs go to the arena and a DefRec to the list k_finish_warp consumes.
 template <int CAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 5) k_map_warp(Dev D) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) k_chain_warp(Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kWarpsPerCta + warp;
   Ws<1> ws{s_ws + (size_t)warp * A_COUNT * CAP, CAP};
-  uint8_t* dir = D.dir_scratch + (size_t)gwarp * D.dir_per_warp;
-  int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
-  int32_t* Fb = Hb + D.bnd_per_warp / 2;
-  uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
-  uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
-  RegRec* wregs = D.wreg_scratch + (size_t)gwarp * CAP;
   RadixScratch* rsx = D.rsx_scratch + gwarp;
   ChainCounters ctr{0, 0, 0, 0};
-  long long n_aligned = 0;
   for (;;) {
     long long item = 0;
     if (lane == 0) item = atomicAdd((unsigned long long*)&D.ctr[C_ITEM], 1ULL);
@@ -1123,61 +1073,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) k_map_warp(Dev D) {
           n_regs = __shfl_sync(full, n_regs, 0);
         }
       }
-      if (st == kMapOverflow) {
-        if (lane == 0) {
+      if (lane == 0) {
+        if (st == kMapOverflow) {
           const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
           if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h;
           else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
-        }
-      } else if (st == kMapNoHit) {
-        if (lane == 0) write_invalid(&D.aln[pair]);
-      } else {
-        // extensions of every surviving reg, then finish
-        int okw = 1;
-        for (int i = 0; i < n_regs; ++i) {
-          if (lane == 0) export_reg<1>(ws, i, qlen, &wregs[i]);
-          __syncwarp();
-          for (int side = 0; side < 2; ++side) {
-            int m = 0, small = 1;
-            if (lane == 0) m = wregs[i].ext[side].m, small = ext_is_small(D.P, wregs[i].ext[side]) ? 1 : 0;
-            m = __shfl_sync(full, m, 0);
-            small = __shfl_sync(full, small, 0);
-            if (m <= 0) continue;
-            if (warp_ext_exact(D.P, rv, hapc, &wregs[i], side, &ctr.dp_cells_full)) continue;
-            if (small) {
-              if (lane == 0) {
-                uint8_t sdir[kSmallCells];
-                int32_t ha[kSmallDim + 2], fa[kSmallDim + 2];
-                uint32_t cig_tmp[kSmallCig];
-                auto alloc_ext = [&](int n) -> int64_t {
-                  const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)n);
-                  if (o + n > D.ext_arena_cap) {
-                    atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
-                    return -1;
-                  }
-                  return o;
-                };
-                if (!run_ext_scalar(D.P, rv, hapc, &wregs[i], side, sdir, ha, fa, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, &ctr)) okw = 0;
-              }
-            } else {
-              long long c1 = 0, c2 = 0;
-              ext_dp_warp(D, &wregs[i], side, rv, hapc, dir, Hb, Fb, wcig, &c1, &c2);
-              ctr.dp_cells += c1, ctr.dp_cells_full += c2;
-            }
-            __syncwarp();
-          }
-        }
-        okw = __shfl_sync(full, okw, 0);
-        FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
-        AlnOut ao;
-        const int nc = okw ? finish_pair_warp(D, rv, hapc, wregs, n_regs, fs, &ao) : -1;
-        if (lane == 0) {
-          if (nc < 0) {
-            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+        } else if (st == kMapNoHit) {
+          write_invalid(&D.aln[pair]);
+        } else {
+          const long long first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
+          const long long di = atomicAdd((unsigned long long*)&D.ctr[C_NDEF], 1ULL);
+          if (first + n_regs > D.regs_cap || di >= D.defs_cap) {
+            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
             write_invalid(&D.aln[pair]);
           } else {
-            store_final(D, pair, ao, fs.best, nc);
-            n_aligned += ao.valid;
+            D.defs[di] = DefRec{r, h, (int32_t)first, n_regs};
+            for (int i = 0; i < n_regs; ++i) export_reg<1>(ws, i, qlen, &D.regs[first + i]);
           }
         }
       }
@@ -1187,36 +1098,88 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) k_map_warp(Dev D) {
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
     atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)ctr.dp_cells);
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
-    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
   }
 }
 
-// one lane per parked pair
-__global__ void __launch_bounds__(128) k_finish(Dev D) {
-  const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+// scalar short extension on lane 0 (kept out of line: it is the cold side of k_finish_warp)
+__device__ __noinline__ bool ext_small_lane0(const Dev& D, const ReadView& rv, const uint8_t* hapc, RegRec* reg, int side,
+                                            ChainCounters* ctr) {
+  uint8_t sdir[kSmallCells];
+  int32_t ha[kSmallDim + 2], fa[kSmallDim + 2];
+  uint32_t cig_tmp[kSmallCig];
+  auto alloc_ext = [&](int n) -> int64_t {
+    const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)n);
+    if (o + n > D.ext_arena_cap) {
+      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
+      return -1;
+    }
+    return o;
+  };
+  return run_ext_scalar(D.P, rv, hapc, reg, side, sdir, ha, fa, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, ctr);
+}
+
+// Phase B kernel: one warp per parked pair: pending extensions (exact-match shortcut, scalar short
+// tails, warp wavefront for the rest), then the warp-parallel finish, then the final record.
+__global__ void __launch_bounds__(128, 6) k_finish_warp(Dev D) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint8_t* dir = D.dir_scratch + (size_t)gwarp * D.dir_per_warp;
+  int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
+  int32_t* Fb = Hb + D.bnd_per_warp / 2;
+  uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
+  uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
   const long long n_def = D.ctr[C_NDEF] < D.defs_cap ? D.ctr[C_NDEF] : D.defs_cap;
-  uint32_t* fin0 = D.fin_scratch + (size_t)gthread * 2 * D.fin_cap;
+  ChainCounters ctr{0, 0, 0, 0};
   long long n_aligned = 0;
-  for (long long di = gthread; di < n_def; di += (long long)gridDim.x * blockDim.x) {
+  for (;;) {
+    long long di = 0;
+    if (lane == 0) di = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
+    di = __shfl_sync(full, di, 0);
+    if (di >= n_def) break;
     const DefRec d = D.defs[di];
     const int g = D.read_grp[d.read];
     const int64_t pair = D.pair_off[d.read] + (d.hap - D.grp_hap_begin[g]);
     const int64_t roff = D.read_off[d.read], hoff = D.hap_off[d.hap];
     ReadView rv{D.read_codes + roff, (int)(D.read_off[d.read + 1] - roff)};
+    const uint8_t* hapc = D.hap_codes + hoff;
+    RegRec* regs = D.regs + d.first_reg;
+    int okw = 1;
+    for (int i = 0; i < d.n_regs; ++i) {
+      for (int side = 0; side < 2; ++side) {
+        const int m = regs[i].ext[side].m;
+        if (m <= 0 || regs[i].ext[side].mqe_t >= 0) continue;  // none, or already computed
+        if (warp_ext_exact(D.P, rv, hapc, &regs[i], side, &ctr.dp_cells_full)) continue;
+        if (ext_is_small(D.P, regs[i].ext[side])) {
+          if (lane == 0 && !ext_small_lane0(D, rv, hapc, &regs[i], side, &ctr)) okw = 0;
+        } else {
+          long long c1 = 0, c2 = 0;
+          ext_dp_warp(D, &regs[i], side, rv, hapc, dir, Hb, Fb, wcig, &c1, &c2);
+          ctr.dp_cells += c1, ctr.dp_cells_full += c2;
+        }
+        __syncwarp();
+      }
+    }
+    okw = __shfl_sync(full, okw, 0);
     FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
     AlnOut ao;
-    const int nc = finish_pair(D.P, rv, D.hap_codes + hoff, D.regs + d.first_reg, d.n_regs, D.ext_arena, fs, &ao);
-    if (nc < 0) {
-      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
-      write_invalid(&D.aln[pair]);
-    } else {
-      store_final(D, pair, ao, fs.best, nc);
-      n_aligned += ao.valid;
+    const int nc = okw ? finish_pair_warp(D, rv, hapc, regs, d.n_regs, fs, &ao) : -1;
+    if (lane == 0) {
+      if (nc < 0) {
+        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+        write_invalid(&D.aln[pair]);
+      } else {
+        store_final(D, pair, ao, fs.best, nc);
+        n_aligned += ao.valid;
+      }
     }
+    __syncwarp();
   }
-  if (n_aligned) atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)ctr.dp_cells);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
+    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
+  }
 }
 
 // one lane per (read, variant): AssignReadToAlleles' inner loops (genotyper.cpp:294-318)
@@ -1461,7 +1424,7 @@ void lgr_destroy(lgr_ctx* c) {
 void* lgr_stream(lgr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 static constexpr int kCapBig = 16384;    // anchors per lane in the overflow pass
-static constexpr int kBigWarps = 4 * 37; // warps of the overflow pass (workspace = 28 arrays * cap * 4 B per lane)
+static constexpr int kBigWarps = 4 * 19; // warps of the overflow pass (workspace = 28 arrays * cap * 4 B per lane, pre-allocated)
 
 static int validate_batch(lgr_ctx* c, const lgr_batch_in* in) {
   auto bad = [&](const std::string& m, int code = LGR_E_ARG) { c->err = m; return code; };
@@ -1579,14 +1542,14 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
     int per_sm = 0;
     cudaError_t e1, e2;
     if (c->warp_cap == 64) {
-      e1 = cudaFuncSetAttribute(k_map_warp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
-      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_warp<64>, kWarpsPerCta * 32, c->warp_smem);
+      e1 = cudaFuncSetAttribute(k_chain_warp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_warp<64>, kWarpsPerCta * 32, c->warp_smem);
     } else {
-      e1 = cudaFuncSetAttribute(k_map_warp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
-      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_warp<128>, kWarpsPerCta * 32, c->warp_smem);
+      e1 = cudaFuncSetAttribute(k_chain_warp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
+      e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_warp<128>, kWarpsPerCta * 32, c->warp_smem);
     }
     if (e1 != cudaSuccess || e2 != cudaSuccess || per_sm < 1) {
-      c->err = "k_map_warp does not fit on this device (shared memory / registers)";
+      c->err = "k_chain_warp does not fit on this device (shared memory / registers)";
       return LGR_E_CUDA;
     }
     c->warp_blocks = c->sm_count * per_sm;
@@ -1596,14 +1559,13 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
   const int wcig_cap = 2 * Lm + 8;
-  const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024, defs_cap = n_pairs + 1024, tasks_cap = 2 * regs_cap;
+  const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024, defs_cap = n_pairs + 1024;
   const int64_t ext_arena_cap = 4 * n_pairs + (1 << 20);
   const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
   if ((rc = ensure(c, c->b_wreg, sizeof(RegRec) * (size_t)ext_warps * c->warp_cap)) ||
       (rc = ensure(c, c->b_rsx, sizeof(RadixScratch) * (size_t)ext_warps)) ||
       (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)n_threads * 2 * fin_cap)) ||
       (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_defs, sizeof(DefRec) * (size_t)defs_cap)) ||
-      (rc = ensure(c, c->b_tasks, sizeof(TaskRec) * (size_t)tasks_cap)) ||
       (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
       (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
       (rc = ensure(c, c->b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
@@ -1613,7 +1575,8 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       (rc = ensure(c, c->b_aln, sizeof(AlnOut) * (size_t)n_pairs)) ||
       (rc = ensure(c, c->b_cig_inline, sizeof(uint32_t) * (size_t)n_pairs * LGR_CIGAR_INLINE)) ||
       (rc = ensure(c, c->b_cig_arena, sizeof(uint32_t) * (size_t)cig_arena_cap)) ||
-      (rc = ensure(c, c->b_assign, sizeof(AssignOut) * (size_t)n_assign)) || (rc = ensure(c, c->b_ctr, sizeof(long long) * C_COUNT)))
+      (rc = ensure(c, c->b_assign, sizeof(AssignOut) * (size_t)n_assign)) || (rc = ensure(c, c->b_ctr, sizeof(long long) * C_COUNT)) ||
+      (rc = ensure(c, c->b_ws_big, sizeof(int32_t) * (size_t)(kBigWarps * 32) * A_COUNT * kCapBig)))
     return rc;
   Dev& D = c->D;
   std::memset(&D, 0, sizeof(D));
@@ -1637,7 +1600,6 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.fin_scratch = (uint32_t*)c->b_fin.p, D.fin_cap = fin_cap;
   D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
   D.defs = (DefRec*)c->b_defs.p, D.defs_cap = defs_cap;
-  D.tasks = (TaskRec*)c->b_tasks.p, D.tasks_cap = tasks_cap;
   D.ext_arena = (uint32_t*)c->b_ext_arena.p, D.ext_arena_cap = ext_arena_cap;
   D.ovf_read = (int32_t*)c->b_ovf_read.p, D.ovf_hap = (int32_t*)c->b_ovf_hap.p, D.ovf_cap = n_pairs;
   D.dir_scratch = (uint8_t*)c->b_dir.p, D.dir_per_warp = dir_per_warp;
@@ -1677,34 +1639,20 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
     launches += 1;
     cudaEventRecord(c->ev[2], s);
-    if (c->warp_cap == 64) k_map_warp<64><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
-    else k_map_warp<128><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
+    if (c->warp_cap == 64) k_chain_warp<64><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
+    else k_chain_warp<128><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
     launches += 1;
     cudaEventRecord(c->ev[9], s);
-    long long hctr[C_COUNT];
-    LGR_CUDA(c, cudaMemcpyAsync(hctr, D.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
-    LGR_CUDA(c, cudaStreamSynchronize(s));
-    if (hctr[C_NOVF] > 0) {
-      // overflow pass: same kernel, larger per-lane workspace, few warps
-      const int big_blocks = kBigWarps / 4;
-      int rc = ensure(c, c->b_ws_big, sizeof(int32_t) * (size_t)big_blocks * 128 * A_COUNT * kCapBig);
-      if (rc != LGR_OK) return rc;
+    {
+      // overflow pass (pairs whose seeds/anchors exceed the shared-memory cap): lane-per-pair over
+      // a large HBM workspace; exits immediately when the list is empty (no host round trip)
       Dev D2 = D;
       D2.ws = (int32_t*)c->b_ws_big.p, D2.ws_cap = kCapBig;
-      k_map<true><<<big_blocks, 128, 0, s>>>(D2);
-      launches += 1;
-      LGR_CUDA(c, cudaMemcpyAsync(hctr, D.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
-      LGR_CUDA(c, cudaStreamSynchronize(s));
-    }
-    if (hctr[C_NTASK] > 0) {
-      k_ext_big<<<c->ext_blocks, 128, 0, s>>>(D);
+      k_map<true><<<kBigWarps / 4, 128, 0, s>>>(D2);
       launches += 1;
     }
-    if (hctr[C_NDEF] > 0) {
-      const int fb = (int)std::min<long long>((hctr[C_NDEF] + 127) / 128, c->map_blocks);
-      k_finish<<<fb, 128, 0, s>>>(D);
-      launches += 1;
-    }
+    k_finish_warp<<<c->ext_blocks, 128, 0, s>>>(D);
+    launches += 1;
     cudaEventRecord(c->ev[3], s);
     if (D.n_assign > 0) {
       k_assign<<<(unsigned)((D.n_assign + 127) / 128), 128, 0, s>>>(D);
