@@ -571,6 +571,49 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
   if (max_dist_y < P.bw) max_dist_y = P.bw;
   int st = 0, max_ii = -1;
   long long n_iter = 0;
+  // ---- co-linear fast path ----------------------------------------------------------------
+  // All anchors on one strand and one diagonal, strictly increasing, equal spans, no skip
+  // penalty: then for every i the best predecessor is i-1 (sc_{i-1} = f[i-1] + min(span, dq) >=
+  // f[j] + min(span, dq_ij) for all j < i-1 because sum(min(span, g)) >= min(span, sum g); ties
+  // go to the first j scanned, i-1), there is no gap penalty (dd = 0), so f is a prefix sum and
+  // p[i] = i-1.  The predecessor scan upstream visits min(i, max_skip + 2) anchors for anchor i
+  // (j = i-1 raises the maximum, every further j is stamped by its successor's predecessor link
+  // and bumps the skip counter until it exceeds max_skip), which gives its iteration count.
+  {
+    const uint32_t x0 = (uint32_t)sx[0], y0 = (uint32_t)sy[0];
+    const int diag0 = anchor_rpos(x0) - anchor_qpos(y0), span0 = anchor_span(y0);
+    bool ok = true;
+    for (int i = lane; i < n_a; i += 32) {
+      const uint32_t x = (uint32_t)sx[i], y = (uint32_t)sy[i];
+      ok &= (x >> 31) == (x0 >> 31) && anchor_rpos(x) - anchor_qpos(y) == diag0 && anchor_span(y) == span0;
+      if (i > 0) ok &= anchor_rpos(x) > anchor_rpos((uint32_t)sx[i - 1]);
+    }
+    const int tot_span = anchor_rpos((uint32_t)sx[n_a - 1]) - anchor_rpos(x0);
+    const bool colinear = __all_sync(full, ok) && P.pen_skip == 0.0f && P.max_skip >= 0 && n_a <= P.max_iter &&
+                          tot_span <= max_dist_x && tot_span <= max_dist_y && span0 > 0;
+    if (colinear) {
+      int32_t carry = span0;  // f[0]
+      for (int base = 0; base < n_a; base += 32) {
+        const int i = base + lane;
+        int32_t c = 0;
+        if (i > 0 && i < n_a) {
+          const int32_t dq = anchor_rpos((uint32_t)sx[i]) - anchor_rpos((uint32_t)sx[i - 1]);
+          c = dq < span0 ? dq : span0;
+        }
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t v = __shfl_up_sync(full, c, o);
+          if (lane >= o) c += v;
+        }
+        if (i < n_a) f[i] = carry + c, p[i] = i - 1;
+        carry += __shfl_sync(full, c, 31);
+      }
+      const int cap_it = P.max_skip + 2;
+      for (int i = 1; i < n_a; ++i) n_iter += i < cap_it ? i : cap_it;
+      if (lane == 0 && ctr) ctr->chain_evals += n_iter;
+      __syncwarp();
+      return kMapOk;
+    }
+  }
   for (int i = 0; i < n_a; ++i) {
     const uint32_t xi = (uint32_t)sx[i], yi = (uint32_t)sy[i];
     while (st < i && ((xi >> 31) != ((uint32_t)sx[st] >> 31) || anchor_rpos(xi) > anchor_rpos((uint32_t)sx[st]) + max_dist_x)) ++st;
@@ -1554,7 +1597,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
     }
     c->warp_blocks = c->sm_count * per_sm;
   }
-  c->ext_blocks = c->sm_count * 4;
+  c->ext_blocks = c->sm_count * 6;
   const int64_t ext_warps = std::max<int64_t>((int64_t)c->ext_blocks * 4, (int64_t)c->warp_blocks * kWarpsPerCta);
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);

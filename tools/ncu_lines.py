@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Attribute an ncu source-page (SASS) profile to CUDA source lines using nvdisasm -g line info.
-usage: tools/ncu_lines.py report.ncu-rep lib.so kernel_substring [top_n]
+usage: tools/ncu_lines.py report.ncu-rep lib.so mangled_kernel_substring [top_n] [human_kernel_substring]
 The library must be the same build the report was taken from."""
 import collections
 import csv
@@ -36,7 +36,13 @@ def main():
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
             line_of.append(cur)
-    sass = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    parts = out.split('"Kernel Name",')[1:]
+    human = sys.argv[5] if len(sys.argv) > 5 else None
+    part = parts[0]
+    if human:
+        part = [p for p in parts if human in p.split("\n", 1)[0]][0]
+    sass = list(csv.reader(('"Kernel Name",' + part).splitlines()))
     h2 = sass[1]
     ci = {h: i for i, h in enumerate(h2)}
     agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
