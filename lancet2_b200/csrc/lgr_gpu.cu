@@ -352,8 +352,9 @@ __global__ void __launch_bounds__(128) k_map(Dev D) {
 // All 32 lanes must call it; results are written by lane 0 into reg->ext[side].
 // ---------------------------------------------------------------------------------------
 __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, const ReadView& rv, const uint8_t* hapc,
-                                         uint8_t* dir, int32_t* Hb, int32_t* Fb, uint32_t* wcig, long long* cells,
-                                         long long* cells_full) {
+                                         uint8_t* dir_g, uint8_t* dir_s, int dir_s_cap, int32_t* Hb, int32_t* Fb, uint32_t* wcig,
+                                         long long* cells, long long* cells_full) {
+  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
   const int q = P.q, e = P.e;
@@ -363,55 +364,68 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
   ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
   ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
   const int nblk = (m + 31) >> 5;
-  const int dstride = T + 32;  // steps per block (padded)
+  // direction bytes: block b holds rows [32b, 32b+rows_b) as [step][row]; shared memory when the
+  // whole matrix fits the warp's slice, else the HBM scratch
+  const int rows_last = m - (nblk - 1) * 32;
+  const int dir_bytes = (nblk - 1) * 32 * (T + 31) + rows_last * (T + rows_last - 1);
+  uint8_t* dir = dir_bytes <= dir_s_cap ? dir_s : dir_g;
   int32_t ezmax = 0, mqe = kNegInf, mqe_t = -1;
   for (int blk = 0; blk < nblk; ++blk) {
     const int j = blk * 32 + lane;
-    const bool row_ok = j < m;
+    const int rows = m - blk * 32 < 32 ? m - blk * 32 : 32;
+    const bool row_ok = lane < rows;
     const int qc = row_ok ? qf(j) : 4;
     int32_t e_cur = -(q + e * (j + 1)) - q - e;  // E(0, j)
     int32_t diag = j == 0 ? 0 : -(q + e * j);    // H(-1, j-1)
-    int32_t h_last = 0, f_out = 0;
-    uint8_t* dblk = dir + (size_t)blk * dstride * 32;
-    const int rows = m - blk * 32 < 32 ? m - blk * 32 : 32;
+    int32_t hf = 0;                               // packed (H low16, F-out high16) of my last cell
+    uint8_t* dblk = dir + (size_t)blk * 32 * (T + 31);
     const int nsteps = T + rows - 1;
-    for (int s = 0; s < nsteps; ++s) {
-      int32_t up_h = __shfl_up_sync(0xffffffffu, h_last, 1);
-      int32_t up_f = __shfl_up_sync(0xffffffffu, f_out, 1);
-      const int i = s - lane;
-      const bool act = row_ok && i >= 0 && i < T;
-      if (lane == 0 && act) {
+    const bool save_bnd = blk + 1 < nblk;
+    // Per 32 steps every lane fetches one target base (and one packed boundary cell for row
+    // blocks > 0): coalesced, off the per-step dependency chain, and the step body stays
+    // branch-free — lane l takes its base t[s-l] with one indexed shuffle out of the current or
+    // previous 32-base register window, lane 0 takes its boundary input with a broadcast.
+    int tprev = 4, tcur = 4, bcur = 0;
+    for (int s0 = 0; s0 < nsteps; s0 += 32) {
+      const int ti = s0 + lane;
+      tprev = tcur;
+      tcur = ti < T ? tf(ti) : 4;
+      if (blk > 0) bcur = ti < T ? Hb[ti] : 0;
+      const int kmax = nsteps - s0 < 32 ? nsteps - s0 : 32;
+      for (int k = 0; k < kmax; ++k) {
+        const int s = s0 + k;
+        const int i = s - lane;
+        const int tc = __shfl_sync(full, k >= lane ? tcur : tprev, (k - lane) & 31);
+        int up_hf = __shfl_up_sync(full, hf, 1);
+        int feed;
         if (blk == 0) {
-          up_h = -(q + e * (i + 1));
-          up_f = up_h - q - e;
+          const int32_t h0 = -(q + e * (s + 1));
+          feed = (int)(((uint32_t)h0 & 0xffffu) | ((uint32_t)(h0 - q - e) << 16));
         } else {
-          up_h = Hb[i];
-          up_f = Fb[i];
+          feed = __shfl_sync(full, bcur, k);
         }
-      }
-      if (act) {
-        const int32_t hd = diag + sub_score(P, tf(i), qc);
-        uint8_t d;
-        int32_t en, fn;
-        const int32_t h = ext_cell(hd, e_cur, up_f, q, e, right, &d, &en, &fn);
-        dblk[(size_t)s * 32 + lane] = d;
-        diag = up_h;
-        h_last = h;
-        e_cur = en;
-        f_out = fn;
-        if (h > ezmax) ezmax = h;
-        if (j == m - 1 && h > mqe) mqe = h, mqe_t = i;
-        if (lane == 31 && blk + 1 < nblk) Hb[i] = h, Fb[i] = fn;
+        if (lane == 0) up_hf = feed;
+        const int32_t up_h = (int32_t)(int16_t)(up_hf & 0xffff);
+        const int32_t up_f = up_hf >> 16;
+        if (row_ok && i >= 0 && i < T) {
+          const int32_t sc = (tc > 3 || qc > 3) ? -P.sc_ambi : (tc == qc ? P.a : -P.b);
+          uint8_t d;
+          int32_t en, fn;
+          const int32_t h = ext_cell(diag + sc, e_cur, up_f, q, e, right, &d, &en, &fn);
+          dblk[s * rows + lane] = d;
+          diag = up_h;
+          e_cur = en;
+          hf = (int)(((uint32_t)h & 0xffffu) | ((uint32_t)fn << 16));
+          if (h > ezmax) ezmax = h;
+          if (j == m - 1 && h > mqe) mqe = h, mqe_t = i;
+          if (save_bnd && lane == 31) Hb[i] = hf;
+        }
       }
     }
     __syncwarp();
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const int32_t v = __shfl_down_sync(0xffffffffu, ezmax, o);
-    ezmax = v > ezmax ? v : ezmax;
-  }
-  ezmax = __shfl_sync(0xffffffffu, ezmax, 0);
-  mqe_t = __shfl_sync(0xffffffffu, mqe_t, (m - 1) & 31);
+  ezmax = __reduce_max_sync(full, ezmax);
+  mqe_t = __shfl_sync(full, mqe_t, (m - 1) & 31);
   __syncwarp();
   if (lane == 0) {
     ExtRec& E = reg->ext[side];
@@ -420,7 +434,8 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
     CigBuf cb{wcig, 0, D.wcig_cap};
     auto dirf = [&](int i, int j) -> uint8_t {
       const int b = j >> 5, l = j & 31;
-      return dir[((size_t)b * dstride + (size_t)(i + l)) * 32 + l];
+      const int rows = m - b * 32 < 32 ? m - b * 32 : 32;
+      return dir[(size_t)b * 32 * (T + 31) + (size_t)(i + l) * rows + l];
     };
     ext_backtrack(dirf, m, mqe_t, side == 0, cb);
     E.n_cig = cb.n;
@@ -1163,7 +1178,11 @@ __device__ __noinline__ bool ext_small_lane0(const Dev& D, const ReadView& rv, c
 
 // Phase B kernel: one warp per parked pair: pending extensions (exact-match shortcut, scalar short
 // tails, warp wavefront for the rest), then the warp-parallel finish, then the final record.
+constexpr int kTinyCells = 24;         // extensions up to this many cells run scalar on lane 0
+constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
+
 __global__ void __launch_bounds__(128, 6) k_finish_warp(Dev D) {
+  __shared__ uint8_t s_dir[4 * kDirSmemPerWarp];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1193,11 +1212,11 @@ __global__ void __launch_bounds__(128, 6) k_finish_warp(Dev D) {
         const int m = regs[i].ext[side].m;
         if (m <= 0 || regs[i].ext[side].mqe_t >= 0) continue;  // none, or already computed
         if (warp_ext_exact(D.P, rv, hapc, &regs[i], side, &ctr.dp_cells_full)) continue;
-        if (ext_is_small(D.P, regs[i].ext[side])) {
+        if ((int64_t)m * prune_cols(D.P, m, regs[i].ext[side].n) <= kTinyCells) {  // a handful of cells: not worth a wavefront
           if (lane == 0 && !ext_small_lane0(D, rv, hapc, &regs[i], side, &ctr)) okw = 0;
         } else {
           long long c1 = 0, c2 = 0;
-          ext_dp_warp(D, &regs[i], side, rv, hapc, dir, Hb, Fb, wcig, &c1, &c2);
+          ext_dp_warp(D, &regs[i], side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig, &c1, &c2);
           ctr.dp_cells += c1, ctr.dp_cells_full += c2;
         }
         __syncwarp();
@@ -1497,6 +1516,12 @@ static int validate_batch(lgr_ctx* c, const lgr_batch_in* in) {
     if (l < 0) return bad("read_off must be non-decreasing");
     if (l > LGR_MAX_READ_LEN) return bad("read longer than LGR_MAX_READ_LEN", LGR_E_LIMIT);
     c->max_read_len = std::max<int>(c->max_read_len, (int)l);
+  }
+  {  // the warp wavefront exchanges H/F as packed int16: bound |H| for the longest read
+    const int Lm = c->max_read_len, mm = std::max(c->prm.b, c->prm.sc_ambi);
+    const int64_t Tm = Lm + ((int64_t)(c->prm.a + mm) * Lm) / c->prm.e + 2;
+    if (c->prm.q + (int64_t)c->prm.e * (Tm + Lm) + (int64_t)(mm + c->prm.a) * Lm > 32000)
+      return bad("scores could leave the int16 range of the extension kernel for this read length / scoring", LGR_E_LIMIT);
   }
   // ksw2 band (w = 1.5*bw + 1) must never bind
   if ((int64_t)c->max_hap_len + c->max_read_len >= (int64_t)(c->prm.bw * 1.5))
