@@ -174,6 +174,88 @@ LGR_HD int sketch(const uint8_t* codes, int len, int w, int k, OutX out_x, OutY 
 }
 
 // ------------------------------------------------------------------------------------
+// sketch_sr<W>: the same mm_sketch state machine with the w-slot ring buffer unrolled into
+// a shift register of compile-time width, so that every slot lives in a register (the ring
+// buffer version indexes its slots dynamically, which puts them in local memory and the
+// per-base latency of the one-lane-per-sequence sketch kernels is exactly that).
+// Ring → shift register: after the write, slots read oldest → newest are win[0..W-1]; the
+// minimum's slot index drops by one per write and "buf_pos == min_pos" is "index fell below 0".
+// emit(x, y) receives the minimizers in upstream order; returns their count.
+// ------------------------------------------------------------------------------------
+template <int W, typename Emit>
+LGR_HD int sketch_sr(const uint8_t* codes, int len, int k, Emit emit) {
+  const uint64_t shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
+  uint64_t kmer0 = 0, kmer1 = 0;
+  uint64_t wx[W];
+  uint32_t wy[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) wx[j] = UINT64_MAX, wy[j] = UINT32_MAX;
+  uint64_t min_x = UINT64_MAX;
+  uint32_t min_y = UINT32_MAX;
+  int l = 0, min_idx = W - 1, kmer_span = 0, n = 0;
+  for (int i = 0; i < len; ++i) {
+    const int c = codes[i] & 0xf;
+    uint64_t ix = UINT64_MAX;
+    uint32_t iy = UINT32_MAX;
+    if (c < 4) {
+      kmer_span = l + 1 < k ? l + 1 : k;
+      kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
+      kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+      if (kmer0 == kmer1) continue;
+      const int z = kmer0 < kmer1 ? 0 : 1;
+      ++l;
+      if (l >= k && kmer_span < 256) {
+        ix = hash64_mask(z ? kmer1 : kmer0, mask) << 8 | (uint64_t)kmer_span;
+        iy = (uint32_t)i << 1 | (uint32_t)z;
+      }
+    } else {
+      l = 0;
+      kmer_span = 0;
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < W; ++j) wx[j] = wx[j + 1], wy[j] = wy[j + 1];
+    wx[W - 1] = ix, wy[W - 1] = iy;
+    --min_idx;
+    if (l == W + k - 1 && min_x != UINT64_MAX) {
+#pragma unroll
+      for (int j = 0; j + 1 < W; ++j)
+        if (min_x == wx[j] && wy[j] != min_y) emit(wx[j], wy[j]), ++n;
+    }
+    if (ix <= min_x) {
+      if (l >= W + k && min_x != UINT64_MAX) emit(min_x, min_y), ++n;
+      min_x = ix, min_y = iy, min_idx = W - 1;
+    } else if (min_idx < 0) {
+      if (l >= W + k - 1 && min_x != UINT64_MAX) emit(min_x, min_y), ++n;
+      min_x = UINT64_MAX;
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (min_x >= wx[j]) min_x = wx[j], min_y = wy[j], min_idx = j;
+      if (l >= W + k - 1 && min_x != UINT64_MAX) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          if (min_x == wx[j] && min_y != wy[j]) emit(wx[j], wy[j]), ++n;
+      }
+    }
+  }
+  if (min_x != UINT64_MAX) emit(min_x, min_y), ++n;
+  return n;
+}
+
+// dispatcher: register-resident window for the reference's w = 5, ring buffer otherwise.
+// Stores at most `cap` minimizers through out_x / out_y; returns the full count.
+template <typename OutX, typename OutY>
+LGR_HD int sketch_any(const uint8_t* codes, int len, int w, int k, OutX out_x, OutY out_y, int cap) {
+  if (w == 5) {
+    int m = 0;
+    return sketch_sr<5>(codes, len, k, [&](uint64_t x, uint32_t y) {
+      if (m < cap) out_x[m] = x, out_y[m] = y;
+      ++m;
+    });
+  }
+  return sketch(codes, len, w, k, out_x, out_y, cap);
+}
+
+// ------------------------------------------------------------------------------------
 // seed.c: mm_seed_mz_flt — drop query minimizers that occur more than q_occ_max times in
 // the query and more than q_occ_frac of all its minimizers.  Count based, so the unstable
 // sort upstream uses to group them does not matter.  In place; returns the new count.

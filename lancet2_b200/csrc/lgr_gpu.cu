@@ -107,8 +107,7 @@ __global__ void k_hap_sketch(Dev D) {
   const int64_t off = D.hap_off[h];
   const int len = (int)(D.hap_off[h + 1] - off);
   uint64_t* tab = D.idx + off;
-  // simple two-array adaptor: x is staged in the table slot, y finalises it
-  struct XW {
+  struct XW {  // x arrives first and is staged in the slot, y finalises the packed entry
     uint64_t* t;
     __device__ uint64_t& operator[](int i) const { return t[i]; }
   };
@@ -121,17 +120,26 @@ __global__ void k_hap_sketch(Dev D) {
     __device__ Ref operator[](int i) const { return Ref{t + i}; }
   };
   int n = 0;
-  if (len > 0) n = sketch(D.hap_codes + off, len, D.P.w, D.P.k, XW{tab}, YW{tab}, len);
+  if (len > 0) {
+    if (D.P.w == 5) {
+      int m = 0;
+      n = sketch_sr<5>(D.hap_codes + off, len, D.P.k, [&](uint64_t x, uint32_t y) {
+        if (m < len) tab[m] = (x >> 8) << kIdxShift | (uint64_t)y;
+        ++m;
+      });
+    } else {
+      n = sketch(D.hap_codes + off, len, D.P.w, D.P.k, XW{tab}, YW{tab}, len);
+    }
+  }
   if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
   D.idx_n[h] = n;
 }
 
 // one CTA per haplotype: in-place bitonic sort of its table (keys are unique)
-__global__ void k_hap_sort(Dev D) {
+__global__ void k_hap_sort(Dev D, float mid_occ_frac, int min_mid, int max_mid) {
   const int h = blockIdx.x;
   uint64_t* tab = D.idx + D.hap_off[h];
   const int n = D.idx_n[h];
-  if (n <= 1) return;
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   extern __shared__ uint64_t s_tab[];
@@ -159,12 +167,46 @@ __global__ void k_hap_sort(Dev D) {
   }
   if (use_smem)
     for (int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = s_tab[i];
-}
-
-__global__ void k_hap_mid(Dev D, float mid_occ_frac, int min_mid, int max_mid) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= D.n_haps) return;
-  D.hap_mid[h] = hap_mid_occ(D.idx + D.hap_off[h], D.idx_n[h], mid_occ_frac, min_mid, max_mid);
+  // mid_occ this haplotype would latch (mm_idx_cal_max_occ + clamp): histogram of the run
+  // lengths of equal hashes; the kk-th smallest run length is read off the cumulative counts.
+  __shared__ int s_hist[64];
+  __shared__ int s_keys;
+  if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_keys = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t key = a[i] >> kIdxShift;
+    if (i == 0 || (a[i - 1] >> kIdxShift) != key) {
+      int len = 1;
+      while (i + len < n && (a[i + len] >> kIdxShift) == key) ++len;
+      atomicAdd(&s_hist[len < 63 ? len : 63], 1);
+      atomicAdd(&s_keys, 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t mid = INT32_MAX;
+    if (mid_occ_frac > 0.f && s_keys > 0) {
+      const uint32_t kk = (uint32_t)((1. - (double)mid_occ_frac) * (double)s_keys);
+      uint32_t cum = 0;
+      int v = 1;
+      for (; v < 63; ++v) {
+        cum += (uint32_t)s_hist[v];
+        if (cum > kk) break;
+      }
+      if (v < 63) {
+        mid = v + 1;
+        if (mid < min_mid) mid = min_mid;
+        if (max_mid > min_mid && mid > max_mid) mid = max_mid;
+      } else {
+        mid = hap_mid_occ(a, n, mid_occ_frac, min_mid, max_mid);  // very long runs: exact slow path
+      }
+    } else {
+      if (mid < min_mid) mid = min_mid;
+      if (max_mid > min_mid && mid > max_mid) mid = max_mid;
+    }
+    D.hap_mid[h] = mid;
+  }
 }
 
 __global__ void k_group_mid(Dev D, int min_mid) {
@@ -183,7 +225,7 @@ __global__ void k_read_sketch(Dev D) {
   const int len = (int)(D.read_off[r + 1] - off);
   int n = 0;
   if (len > 0) {
-    n = sketch(D.read_codes + off, len, D.P.w, D.P.k, D.mz_x + off, D.mz_y + off, len);
+    n = sketch_any(D.read_codes + off, len, D.P.w, D.P.k, D.mz_x + off, D.mz_y + off, len);
     if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
     if (D.P.q_occ_frac > 0.0f) n = seed_mz_flt(D.mz_x + off, D.mz_y + off, n, D.grp_mid[D.read_grp[r]], D.P.q_occ_frac);
   }
@@ -1699,10 +1741,9 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     k_encode<<<enc_blocks, 256, 0, s>>>(D.hap_bases, D.hap_codes, hb);
     k_encode<<<enc_blocks, 256, 0, s>>>(D.read_bases, D.read_codes, rb);
     k_hap_sketch<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D);
-    k_hap_sort<<<D.n_haps, 128, 2048 * sizeof(uint64_t), s>>>(D);
-    k_hap_mid<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
+    k_hap_sort<<<D.n_haps, 128, 2048 * sizeof(uint64_t), s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
     k_group_mid<<<(D.n_groups + 127) / 128, 128, 0, s>>>(D, c->prm.min_mid_occ);
-    launches += 6;
+    launches += 5;
     cudaEventRecord(c->ev[1], s);
     k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
     launches += 1;
@@ -1850,8 +1891,7 @@ int lgr_hap_mid_occ(lgr_ctx* c, const uint8_t* hap, int32_t hap_len, int32_t* mi
   LGR_CUDA(c, cudaMemsetAsync(D.ctr, 0, sizeof(long long) * C_COUNT, s));
   k_encode<<<8, 256, 0, s>>>(D.hap_bases, D.hap_codes, hap_len);
   k_hap_sketch<<<1, 64, 0, s>>>(D);
-  k_hap_sort<<<1, 128, 2048 * sizeof(uint64_t), s>>>(D);
-  k_hap_mid<<<1, 64, 0, s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
+  k_hap_sort<<<1, 128, 2048 * sizeof(uint64_t), s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
   LGR_CUDA(c, cudaMemcpyAsync(mid_occ, D.hap_mid, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   LGR_CUDA(c, cudaStreamSynchronize(s));
   LGR_CUDA(c, cudaGetLastError());

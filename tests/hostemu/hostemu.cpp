@@ -46,7 +46,7 @@ extern "C" int emu_genotype_batch(const lgr_params* prm, const lgr_batch_in* in,
     const int len = (int)(in->hap_off[h + 1] - in->hap_off[h]);
     std::vector<uint64_t> x(len + 1);
     std::vector<uint32_t> y(len + 1);
-    const int n = len > 0 ? sketch(hapc.data() + in->hap_off[h], len, P.w, P.k, x.data(), y.data(), len + 1) : 0;
+    const int n = len > 0 ? sketch_any(hapc.data() + in->hap_off[h], len, P.w, P.k, x.data(), y.data(), len + 1) : 0;
     idx[h].resize(n);
     for (int i = 0; i < n; ++i) idx[h][i] = (x[i] >> 8) << kIdxShift | y[i];
     std::sort(idx[h].begin(), idx[h].end());
@@ -69,7 +69,7 @@ extern "C" int emu_genotype_batch(const lgr_params* prm, const lgr_batch_in* in,
       const uint8_t* rq = in->read_quals + in->read_off[r];
       std::vector<uint64_t> mx(qlen + 1);
       std::vector<uint32_t> my(qlen + 1);
-      int mz_n = qlen > 0 ? sketch(rc_, qlen, P.w, P.k, mx.data(), my.data(), qlen + 1) : 0;
+      int mz_n = qlen > 0 ? sketch_any(rc_, qlen, P.w, P.k, mx.data(), my.data(), qlen + 1) : 0;
       if (P.q_occ_frac > 0.0f) mz_n = seed_mz_flt(mx.data(), my.data(), mz_n, mid_occ, P.q_occ_frac);
       ReadView rv{rc_, qlen};
       std::vector<AlnOut> alns(Pn);

@@ -90,3 +90,14 @@ def test_fixed_mid_occ_and_group_override():
     want, _ = O.oracle_genotype(batch, prm)
     rc, got, _ = H.emu_genotype(batch, prm)
     assert rc == 0 and not compare_results(batch, want, got)
+
+
+@pytest.mark.parametrize("k,w", [(15, 10), (11, 3), (13, 5)])
+def test_other_minimizer_parameters(k, w):
+    """generic ring-buffer sketch (w != 5) and the register-window sketch (w == 5) vs the oracle"""
+    batch = abi.Batch(synth.make_groups(21, 2, n_reads=48, n_haps=3, hap_len=700, n_frac=0.01))
+    prm = O.default_params()
+    prm.k, prm.w = k, w
+    want, _ = O.oracle_genotype(batch, prm)
+    rc, got, _ = H.emu_genotype(batch, prm)
+    assert rc == 0 and not compare_results(batch, want, got)
