@@ -1,0 +1,155 @@
+// adapter_capi.cpp — C hooks around lancet_gpu::GpuGenotyper so that the pytest suite can
+// drive the C++ adapter (ctypes) without a C++ test runner.  Test support only; the product
+// boundary is include/lancet_gpu_realign.h + host/gpu_genotyper.h.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gpu_genotyper.h"
+
+namespace {
+
+void AppI(std::string& s, long long v) { char b[32]; std::snprintf(b, sizeof(b), "%lld,", v); s += b; }
+void AppD(std::string& s, double v) { char b[48]; std::snprintf(b, sizeof(b), "%a,", v); s += b; }
+
+// plain snprintf/std::string on purpose (no iostreams)
+void DumpAllele(std::string& s, const lancet_gpu::PerAlleleData& d) {
+  s += "fwdbq:";
+  for (auto v : d.mFwdBaseQuals) AppI(s, v);
+  s += "|revbq:";
+  for (auto v : d.mRevBaseQuals) AppI(s, v);
+  s += "|mapq:";
+  for (auto v : d.mMapQuals) AppI(s, v);
+  s += "|aln:";
+  for (auto v : d.mAlnScores) AppD(s, v);
+  s += "|isz:";
+  for (auto v : d.mProperPairIsizes) AppD(s, v);
+  s += "|fold:";
+  for (auto v : d.mFoldedReadPositions) AppD(s, v);
+  s += "|refnm:";
+  for (auto v : d.mRefNmValues) AppD(s, v);
+  s += "|ownnm:";
+  for (auto v : d.mOwnHapNmValues) AppD(s, v);
+  s += "|starts:";
+  for (auto v : d.mAlignmentStarts) AppI(s, v);
+  s += "|hapids:";
+  for (auto v : d.mHaplotypeIds) AppI(s, v);
+  s += "|sc:" + std::to_string(d.mSoftClipCount) + "|hashes:";
+  std::vector<std::pair<std::uint32_t, int>> hs;
+  for (auto& kv : d.mNameHashes) hs.emplace_back(kv.first, (int)(kv.second == lancet_gpu::Strand::REV));
+  std::sort(hs.begin(), hs.end());
+  for (auto& kv : hs) s += std::to_string(kv.first) + ":" + std::to_string(kv.second) + ",";
+}
+
+int WriteOut(const std::string& s, char* out, long long cap) {
+  if ((long long)s.size() + 1 > cap) return -1;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
+}  // namespace
+
+extern "C" {
+
+// Feed one evidence stream through lancet_gpu::VariantSupport::AddEvidence and dump the
+// per-allele vectors (same text format as oracle/ref_shim/ref_capi.cpp:ref_add_evidence_dump).
+int lgr_adapter_add_evidence_dump(int n, const long long* isize, const long long* start, const double* aln,
+                                  const double* fold, const unsigned* hash, const unsigned* ref_nm, const unsigned* own_nm,
+                                  const unsigned* hap_id, const unsigned char* allele, const unsigned char* rev,
+                                  const unsigned char* bq, const unsigned char* mapq, const unsigned char* softclip,
+                                  const unsigned char* proper, char* out, long long cap) {
+  lancet_gpu::VariantSupport vs;
+  for (int i = 0; i < n; ++i) {
+    lancet_gpu::ReadEvidence ev;
+    ev.mInsertSize = isize[i], ev.mAlignmentStart = start[i], ev.mAlnScore = aln[i], ev.mFoldedReadPos = fold[i];
+    ev.mRnameHash = hash[i], ev.mRefNm = ref_nm[i], ev.mOwnHapNm = own_nm[i], ev.mAssignedHaplotypeId = hap_id[i];
+    ev.mAllele = allele[i], ev.mStrand = rev[i] ? lancet_gpu::Strand::REV : lancet_gpu::Strand::FWD;
+    ev.mBaseQual = bq[i], ev.mMapQual = mapq[i], ev.mIsSoftClipped = softclip[i] != 0, ev.mIsProperPair = proper[i] != 0;
+    vs.AddEvidence(ev);
+  }
+  std::string os;
+  for (std::size_t a = 0; a < vs.AlleleData().size(); ++a) {
+    os += "A" + std::to_string(a) + "|";
+    DumpAllele(os, vs.AlleleData()[a]);
+    os += "\n";
+  }
+  return WriteOut(os, out, cap);
+}
+
+// Run GpuGenotyper::GenotypeMany on a batch given in the C-ABI's SoA form plus the per-read
+// metadata AddToTable needs; dump every (group, variant, sample, allele) evidence block.
+// names: NUL-separated read names; samples: NUL-separated sample names, sample_id per read.
+// The name hash is X31 of the name (deterministic stand-in for absl::HashOf in tests).
+int lgr_adapter_genotype_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
+                              const int* sample_id, const long long* start0, const long long* isize,
+                              const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
+                              char* out, long long cap) {
+  try {
+    std::vector<std::string_view> qn, sn;
+    for (const char* p = names; (int)qn.size() < in->n_reads; p += std::strlen(p) + 1) qn.emplace_back(p);
+    int n_samples = 0;
+    for (int r = 0; r < in->n_reads; ++r) n_samples = std::max(n_samples, sample_id[r] + 1);
+    for (const char* p = samples; (int)sn.size() < n_samples; p += std::strlen(p) + 1) sn.emplace_back(p);
+    std::vector<std::string> haps(in->n_haps);
+    for (int h = 0; h < in->n_haps; ++h)
+      haps[h].assign(reinterpret_cast<const char*>(in->hap_bases) + in->hap_off[h], (size_t)(in->hap_off[h + 1] - in->hap_off[h]));
+    std::vector<lancet_gpu::ReadIn> reads(in->n_reads);
+    for (int r = 0; r < in->n_reads; ++r) {
+      const size_t len = (size_t)(in->read_off[r + 1] - in->read_off[r]);
+      reads[r] = lancet_gpu::ReadIn{qn[r], std::string_view(reinterpret_cast<const char*>(in->read_bases) + in->read_off[r], len),
+                                    in->read_quals + in->read_off[r], sn[sample_id[r]], start0[r], isize[r], sam_flag[r], mapq[r],
+                                    softclip[r] != 0};
+    }
+    std::vector<lancet_gpu::VariantIn> vars(in->n_vars);
+    std::vector<lancet_gpu::GenotypeJob> jobs;
+    for (int g = 0; g < in->n_groups; ++g) {
+      const int h0 = in->grp_hap_begin[g], P = in->grp_hap_begin[g + 1] - h0;
+      for (int v = in->grp_var_begin[g]; v < in->grp_var_begin[g + 1]; ++v) {
+        lancet_gpu::VariantIn& vi = vars[v];
+        vi.key = &vars[v];
+        const long long o = in->var_hap_off[v];
+        vi.local_ref_start0 = (size_t)in->var_start[o], vi.ref_allele_len = (size_t)in->var_len[o];
+        int max_al = 0;
+        for (int h = 1; h < P; ++h) max_al = std::max(max_al, (int)in->var_allele[o + h]);
+        vi.alts.resize(max_al);
+        for (int h = 1; h < P; ++h) {
+          const int al = in->var_allele[o + h];
+          if (al <= 0) continue;
+          vi.alts[al - 1].seq_len = (size_t)in->var_len[o + h];
+          vi.alts[al - 1].hap_start0.emplace_back((size_t)h, (size_t)in->var_start[o + h]);
+        }
+      }
+      jobs.push_back(lancet_gpu::GenotypeJob{haps.data() + h0, (size_t)P, reads.data() + in->grp_read_begin[g],
+                                             (size_t)(in->grp_read_begin[g + 1] - in->grp_read_begin[g]),
+                                             vars.data() + in->grp_var_begin[g],
+                                             (size_t)(in->grp_var_begin[g + 1] - in->grp_var_begin[g])});
+    }
+    lancet_gpu::GpuGenotyper gt(device);
+    auto hashfn = [](std::string_view q) { return lgr_x31_hash(std::string(q).c_str()); };
+    std::vector<lancet_gpu::Result> res = gt.GenotypeMany(jobs, hashfn);
+    std::string os;
+    for (int g = 0; g < in->n_groups; ++g) {
+      for (int v = in->grp_var_begin[g]; v < in->grp_var_begin[g + 1]; ++v) {
+        auto it = res[g].find(&vars[v]);
+        if (it == res[g].end()) continue;
+        for (const auto& ns : it->second) {
+          const auto& ad = ns.mData->AlleleData();
+          for (std::size_t a = 0; a < ad.size(); ++a) {
+            os += "G" + std::to_string(g) + " V" + std::to_string(v - in->grp_var_begin[g]) + " S" + std::string(ns.mSampleName) +
+                  " A" + std::to_string(a) + "|";
+            DumpAllele(os, ad[a]);
+            os += "\n";
+          }
+        }
+      }
+    }
+    return WriteOut(os, out, cap);
+  } catch (const std::exception& e) {
+    std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
+    return -2;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// gpu_genotyper.h — host-side mirror of lancet::caller::Genotyper over the lgr_* C-ABI.
+//
+// Same call shape as the reference class (src/lancet/caller/genotyper.h:213-220):
+//   Genotyper();   Result Genotype(Haplotypes, Reads, VariantSet const&);
+// with plain std types instead of abseil / cbdg types so that it builds without the
+// reference's dependencies; INTEGRATION.md shows the three-line glue that maps
+// cbdg::Read / RawVariant onto ReadIn / VariantIn inside Lancet2.
+//
+// What runs where:
+//   GPU  (lgr_genotype_batch): ResetData + AlignToAllHaplotypes + AssignReadToAlleles
+//        (genotyper.cpp:243-321, 376-411) for every read of every queued Genotype() call
+//   host (this file): AddToTable → VariantSupport::AddEvidence (genotyper.cpp:423-456,
+//        variant_support.cpp:23-67), in the reference's read order, because it needs the
+//        per-process salted absl::HashOf(qname) and string_view sample names
+// Errors: any non-zero lgr code becomes std::runtime_error — the reference's
+// terminate-on-exception behaviour (core/async_worker.cpp:73-97) is preserved, there is no
+// CPU fallback.
+#ifndef LANCET2_B200_HOST_GPU_GENOTYPER_H_
+#define LANCET2_B200_HOST_GPU_GENOTYPER_H_
+
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../include/lancet_gpu_realign.h"
+
+namespace lancet_gpu {
+
+using AlleleIndex = std::uint8_t;  // variant_support.h:32
+enum class Strand : bool { FWD, REV };  // per_allele_data.h:12
+
+// what Genotype() reads from a cbdg::Read (cbdg/read.h:100-117)
+struct ReadIn {
+  std::string_view qname;        // QnameView()
+  std::string_view seq;          // SeqView()
+  const std::uint8_t* qual;      // QualView().data(), seq.size() entries
+  std::string_view sample_name;  // SampleName()
+  std::int64_t start0;           // StartPos0()
+  std::int64_t insert_size;      // InsertSize()
+  std::uint16_t sam_flag;        // Flag(): 0x10 reverse strand, 0x2 proper pair
+  std::uint8_t map_qual;         // MapQual()
+  bool is_soft_clipped;          // IsSoftClipped()
+};
+
+// what ExtractHapBounds reads from a RawVariant (genotyper.cpp:329-352; raw_variant.h:64-80,
+// alt_allele.h:29-52)
+struct AltAlleleIn {
+  std::size_t seq_len;                                             // mSequence.size()
+  std::vector<std::pair<std::size_t, std::size_t>> hap_start0;     // mLocalHapStart0Idxs (hap → start)
+};
+struct VariantIn {
+  const void* key;                 // RawVariant const* (the Result key)
+  std::size_t local_ref_start0;    // mLocalRefStart0Idx
+  std::size_t ref_allele_len;      // mRefAllele.size()
+  std::vector<AltAlleleIn> alts;   // mAlts, in order
+};
+
+struct ReadEvidence {  // variant_support.h:64-84
+  std::int64_t mInsertSize, mAlignmentStart;
+  double mAlnScore, mFoldedReadPos;
+  std::uint32_t mRnameHash, mRefNm, mOwnHapNm, mAssignedHaplotypeId;
+  AlleleIndex mAllele;
+  Strand mStrand;
+  std::uint8_t mBaseQual, mMapQual;
+  bool mIsSoftClipped, mIsProperPair;
+};
+
+struct PerAlleleData {  // per_allele_data.h:25-73
+  std::unordered_map<std::uint32_t, Strand> mNameHashes;
+  std::vector<std::uint8_t> mFwdBaseQuals, mRevBaseQuals, mMapQuals;
+  std::vector<double> mAlnScores, mProperPairIsizes, mFoldedReadPositions, mRefNmValues, mOwnHapNmValues;
+  std::vector<std::int64_t> mAlignmentStarts;
+  std::vector<std::uint32_t> mHaplotypeIds;
+  std::size_t mSoftClipCount = 0;
+};
+
+class VariantSupport {  // the AddEvidence half of variant_support.h
+ public:
+  void AddEvidence(ReadEvidence const& evidence);  // variant_support.cpp:23-67
+  [[nodiscard]] const std::vector<PerAlleleData>& AlleleData() const noexcept { return mAlleleData; }
+
+ private:
+  std::vector<PerAlleleData> mAlleleData;
+};
+
+class SupportArray {  // support_array.h:25-43
+ public:
+  struct NamedSupport {
+    std::string_view mSampleName;
+    std::unique_ptr<VariantSupport> mData;
+  };
+  VariantSupport& FindOrCreate(std::string_view sample_name);  // support_array.cpp:19-28
+  [[nodiscard]] auto begin() const { return mItems.begin(); }
+  [[nodiscard]] auto end() const { return mItems.end(); }
+
+ private:
+  std::vector<NamedSupport> mItems;
+};
+
+using Result = std::unordered_map<const void*, SupportArray>;  // genotyper.h:217
+
+// hash of the read name used for the dedup key; inside Lancet2 pass
+//   [](std::string_view q) { return static_cast<std::uint32_t>(absl::HashOf(q)); }
+using NameHashFn = std::function<std::uint32_t(std::string_view)>;
+
+// One payload of Genotyper::Genotype (borrowed for the duration of the call that consumes it)
+struct GenotypeJob {
+  const std::string* haps;
+  std::size_t n_haps;
+  const ReadIn* reads;
+  std::size_t n_reads;
+  const VariantIn* variants;
+  std::size_t n_variants;
+};
+
+class GpuGenotyper {
+ public:
+  explicit GpuGenotyper(int device_ordinal = 0, const lgr_params* params = nullptr);
+  ~GpuGenotyper();
+  GpuGenotyper(const GpuGenotyper&) = delete;
+  GpuGenotyper& operator=(const GpuGenotyper&) = delete;
+
+  // drop-in for Genotyper::Genotype (genotyper.cpp:224-235): one group, synchronous
+  [[nodiscard]] Result Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
+                                const VariantIn* variants, std::size_t n_variants, const NameHashFn& name_hash);
+
+  // many Genotype() payloads in ONE device batch (what fills a B200); results in job order
+  [[nodiscard]] std::vector<Result> GenotypeMany(const std::vector<GenotypeJob>& jobs, const NameHashFn& name_hash);
+
+  [[nodiscard]] const lgr_stats& LastStats() const noexcept { return mStats; }
+
+ private:
+  lgr_ctx* mCtx = nullptr;
+  lgr_params mParams;
+  std::int32_t mLatchedMidOcc = 0;  // mm_mapopt_update latches mid_occ from the first index it sees
+  lgr_stats mStats{};
+};
+
+}  // namespace lancet_gpu
+
+#endif  // LANCET2_B200_HOST_GPU_GENOTYPER_H_

@@ -88,3 +88,65 @@ uint32_t ref_hap_edit_distance(const uint32_t* cigar, int n, int32_t rs, int32_t
 }
 
 }  // extern "C"
+
+// The reference's own VariantSupport::AddEvidence (variant_support.cpp:23-67, compiled
+// unmodified) over one evidence stream; dumps the per-allele vectors as text.  Pins the
+// adapter's AddEvidence restatement (lancet2_b200/host/gpu_genotyper.cpp).
+// (plain snprintf/std::string: no iostreams, the host python may carry another libstdc++)
+#include <algorithm>
+#include <cstdio>
+#include <string>
+namespace {
+void AppI(std::string& s, long long v) { char b[32]; std::snprintf(b, sizeof(b), "%lld,", v); s += b; }
+void AppD(std::string& s, double v) { char b[48]; std::snprintf(b, sizeof(b), "%a,", v); s += b; }
+}  // namespace
+extern "C" int ref_add_evidence_dump(int n, const long long* isize, const long long* start, const double* aln,
+                                     const double* fold, const unsigned* hash, const unsigned* ref_nm,
+                                     const unsigned* own_nm, const unsigned* hap_id, const unsigned char* allele,
+                                     const unsigned char* rev, const unsigned char* bq, const unsigned char* mapq,
+                                     const unsigned char* softclip, const unsigned char* proper, char* out, long long cap) {
+  using namespace lancet::caller;
+  VariantSupport vs;
+  for (int i = 0; i < n; ++i) {
+    VariantSupport::ReadEvidence ev{};
+    ev.mInsertSize = isize[i], ev.mAlignmentStart = start[i], ev.mAlnScore = aln[i], ev.mFoldedReadPos = fold[i];
+    ev.mRnameHash = hash[i], ev.mRefNm = ref_nm[i], ev.mOwnHapNm = own_nm[i], ev.mAssignedHaplotypeId = hap_id[i];
+    ev.mAllele = allele[i], ev.mStrand = rev[i] ? Strand::REV : Strand::FWD;
+    ev.mBaseQual = bq[i], ev.mMapQual = mapq[i], ev.mIsSoftClipped = softclip[i] != 0, ev.mIsProperPair = proper[i] != 0;
+    vs.AddEvidence(ev);
+  }
+  std::string s;
+  auto const ad = vs.AlleleData();
+  for (std::size_t a = 0; a < ad.size(); ++a) {
+    auto const& d = ad[a];
+    s += "A" + std::to_string(a) + "|fwdbq:";
+    for (auto v : d.mFwdBaseQuals) AppI(s, v);
+    s += "|revbq:";
+    for (auto v : d.mRevBaseQuals) AppI(s, v);
+    s += "|mapq:";
+    for (auto v : d.mMapQuals) AppI(s, v);
+    s += "|aln:";
+    for (auto v : d.mAlnScores) AppD(s, v);
+    s += "|isz:";
+    for (auto v : d.mProperPairIsizes) AppD(s, v);
+    s += "|fold:";
+    for (auto v : d.mFoldedReadPositions) AppD(s, v);
+    s += "|refnm:";
+    for (auto v : d.mRefNmValues) AppD(s, v);
+    s += "|ownnm:";
+    for (auto v : d.mOwnHapNmValues) AppD(s, v);
+    s += "|starts:";
+    for (auto v : d.mAlignmentStarts) AppI(s, v);
+    s += "|hapids:";
+    for (auto v : d.mHaplotypeIds) AppI(s, v);
+    s += "|sc:" + std::to_string(d.mSoftClipCount) + "|hashes:";
+    std::vector<std::pair<unsigned, int>> hs;
+    for (auto const& kv : d.mNameHashes) hs.emplace_back(kv.first, (int)(kv.second == Strand::REV));
+    std::sort(hs.begin(), hs.end());
+    for (auto& kv : hs) s += std::to_string(kv.first) + ":" + std::to_string(kv.second) + ",";
+    s += "\n";
+  }
+  if ((long long)s.size() + 1 > cap) return -1;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}

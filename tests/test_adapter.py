@@ -1,0 +1,109 @@
+"""C++ Genotyper adapter (lancet2_b200/host/gpu_genotyper.{h,cpp}):
+ * CPU: its AddEvidence restatement against golden dumps made by the reference's own
+   VariantSupport::AddEvidence (tests/golden/evidence_golden.json);
+ * GPU: Genotype()/GenotypeMany() end to end — evidence per (variant, sample, allele), in the
+   reference's read order, must equal what the oracle's assignments give through AddToTable."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from lancet2_b200 import abi, synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "evidence_golden.json")
+FIELDS = [("isize", np.int64), ("start", np.int64), ("aln", np.float64), ("fold", np.float64), ("hash", np.uint32),
+          ("ref_nm", np.uint32), ("own_nm", np.uint32), ("hap_id", np.uint32), ("allele", np.uint8), ("rev", np.uint8),
+          ("bq", np.uint8), ("mapq", np.uint8), ("softclip", np.uint8), ("proper", np.uint8)]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(abi.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    lb = abi.load_library()
+    lb.lgr_adapter_add_evidence_dump.argtypes = [C.c_int] + [C.c_void_p] * 14 + [C.c_char_p, C.c_longlong]
+    lb.lgr_adapter_add_evidence_dump.restype = C.c_int
+    lb.lgr_adapter_genotype_dump.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + \
+        [C.c_void_p] * 6 + [C.c_char_p, C.c_longlong]
+    lb.lgr_adapter_genotype_dump.restype = C.c_int
+    return lb
+
+
+def add_evidence_dump(lib, st):
+    arrs = [np.ascontiguousarray(st[k], dtype=dt) for k, dt in FIELDS]
+    buf = C.create_string_buffer(1 << 22)
+    n = lib.lgr_adapter_add_evidence_dump(len(arrs[0]), *[a.ctypes.data for a in arrs], buf, len(buf))
+    assert n >= 0
+    return buf.value.decode()
+
+
+def test_add_evidence_matches_reference_golden(lib):
+    cases = json.load(open(GOLD))["cases"]
+    assert len(cases) >= 50
+    for c in cases:
+        assert add_evidence_dump(lib, c["stream"]) == c["dump"]
+
+
+@pytest.mark.gpu
+def test_adapter_genotype_matches_oracle_evidence(lib):
+    rng = np.random.default_rng(5)
+    groups = synth.make_region_groups(9, ref_len=40_000)[:6] + synth.make_groups(3, 2, n_reads=64, n_haps=5, hap_len=700)
+    batch = abi.Batch(groups)
+    nr = batch.n_reads
+    names = [nm for g in groups for nm in g.names]
+    sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
+    start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
+    isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
+    flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
+    mapq = rng.integers(0, 61, nr).astype(np.uint8)
+    softclip = rng.integers(0, 2, nr).astype(np.uint8)
+    bi = batch.c_struct()
+    buf = C.create_string_buffer(64 << 20)
+    n = lib.lgr_adapter_genotype_dump(0, C.byref(bi), b"\0".join(x.encode() for x in names) + b"\0", b"normal\0tumor\0",
+                                      sample_id.ctypes.data, start0.ctypes.data, isize.ctypes.data, flag.ctypes.data,
+                                      mapq.ctypes.data, softclip.ctypes.data, buf, len(buf))
+    assert n >= 0, buf.value.decode()
+    got = buf.value.decode().splitlines()
+
+    # expected: oracle assignments → AddToTable (genotyper.cpp:423-456) → AddEvidence
+    prm = O.default_params()
+    want, _ = O.oracle_genotype(batch, prm)
+    expect = []
+    snames = ["normal", "tumor"]
+    for g_i, g in enumerate(groups):
+        r0, r1 = batch.grp_read_begin[g_i], batch.grp_read_begin[g_i + 1]
+        for v in range(len(g.variants)):
+            order, streams = [], {}
+            for r in range(r0, r1):
+                a = want.assign[batch.asg_off[r] + v]
+                if not a["assigned"]:
+                    continue
+                s = int(sample_id[r])
+                if s not in streams:
+                    order.append(s)
+                    streams[s] = {k: [] for k, _ in FIELDS}
+                st = streams[s]
+                st["isize"].append(int(isize[r]))
+                st["start"].append(int(start0[r]))
+                st["aln"].append(float(a["global_score"]) + float(a["local_score"]) * float(a["local_identity"]))
+                st["fold"].append(float(a["folded_read_pos"]))
+                st["hash"].append(abi.x31_hash(names[r]))
+                st["ref_nm"].append(int(a["ref_nm"]))
+                st["own_nm"].append(int(a["own_hap_nm"]))
+                st["hap_id"].append(int(a["hap_id"]))
+                st["allele"].append(int(a["allele"]))
+                st["rev"].append(1 if flag[r] & 0x10 else 0)
+                st["bq"].append(int(a["base_qual"]))
+                st["mapq"].append(int(mapq[r]))
+                st["softclip"].append(int(softclip[r]))
+                st["proper"].append(1 if flag[r] & 0x2 else 0)
+            for s in order:
+                for line in add_evidence_dump(lib, streams[s]).splitlines():
+                    al, rest = line.split("|", 1)
+                    expect.append(f"G{g_i} V{v} S{snames[s]} {al}|{rest}")
+    assert len(got) == len(expect) and len(got) > 10
+    assert got == expect

@@ -1,0 +1,89 @@
+"""world_size-2 (gloo, CPU) test of the multi-GPU host logic: groups are partitioned over
+ranks, every rank processes only its shard (the oracle stands in for the GPU here — tests may
+use it), results are gathered and put back in submission order; the merged result must equal
+the single-process one bit for bit.  No collective touches the data path itself."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _digest(batch, res):
+    return (res.aln[:batch.n_pairs].tobytes(), res.assign[:batch.n_assign].tobytes(),
+            tuple(tuple(res.cigar(i)) for i in range(batch.n_pairs)))
+
+
+def _worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle_lib as O
+    from lancet2_b200 import abi, synth
+    from lancet2_b200.dispatch import merge_in_submission_order, partition_groups
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    groups = synth.make_groups(5, 7, n_reads=24, n_haps=3, hap_len=500) + synth.make_region_groups(3, ref_len=20_000)[:3]
+    shards = partition_groups(groups, world)
+    mine = []
+    for gi in shards[rank]:
+        b = abi.Batch([groups[gi]])
+        r, _ = O.oracle_genotype(b)
+        mine.append(_digest(b, r))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        merged = merge_in_submission_order(shards, gathered)
+        single = []
+        for g in groups:
+            b = abi.Batch([g])
+            r, _ = O.oracle_genotype(b)
+            single.append(_digest(b, r))
+        q.put((merged == single, [len(s) for s in shards], sorted(i for s in shards for i in s) == list(range(len(groups)))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_is_lossless_and_ordered():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, sizes, complete = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and complete and min(sizes) >= 1
+
+
+def test_partition_balances_cost():
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from lancet2_b200 import synth
+    from lancet2_b200.dispatch import group_cost, partition_groups
+    rng = np.random.default_rng(1)
+    groups = [synth.make_group(rng, n_reads=int(rng.integers(8, 64)), n_haps=int(rng.integers(2, 6)), hap_len=400) for _ in range(40)]
+    for world in (1, 2, 4, 8):
+        shards = partition_groups(groups, world)
+        loads = [sum(group_cost(groups[i]) for i in s) for s in shards]
+        assert sorted(i for s in shards for i in s) == list(range(len(groups)))
+        assert max(loads) <= 1.25 * (sum(loads) / world) + max(group_cost(g) for g in groups)
+    with pytest.raises(ValueError):
+        partition_groups(groups, 0)
