@@ -520,6 +520,7 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
 // Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_map<true>).
 // ---------------------------------------------------------------------------------------
 constexpr int kWarpsPerCta = 4;
+constexpr int kMapOkColinear = 2;  // warp_seed_chain: chain DP done by the co-linear closed form
 
 template <int CAP>
 __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const Ws<1>& ws, RadixScratch* rsx,
@@ -541,7 +542,9 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
       const uint64_t mx = in.mz_x[i];
       const uint64_t hx = mx >> 8;
       s0 = idx_lower_bound(in.idx, in.idx_n, hx << kIdxShift);
-      const int s1 = idx_lower_bound(in.idx, in.idx_n, (hx + 1) << kIdxShift);
+      int s1 = s0;
+      while (s1 < in.idx_n && (in.idx[s1] >> kIdxShift) == hx && s1 - s0 < 8) ++s1;
+      if (s1 - s0 == 8) s1 = idx_lower_bound(in.idx, in.idx_n, (hx + 1) << kIdxShift);  // long run: finish by bisection
       occ = s1 - s0;
       if (occ > 0) {
         uint32_t tandem = 0;
@@ -664,11 +667,11 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
         if (i < n_a) f[i] = carry + c, p[i] = i - 1;
         carry += __shfl_sync(full, c, 31);
       }
-      const int cap_it = P.max_skip + 2;
-      for (int i = 1; i < n_a; ++i) n_iter += i < cap_it ? i : cap_it;
+      const long long cap_it = P.max_skip + 2, nm1 = n_a - 1;  // sum_{i=1}^{n_a-1} min(i, cap_it)
+      n_iter = nm1 <= cap_it ? nm1 * (nm1 + 1) / 2 : cap_it * (cap_it + 1) / 2 + (nm1 - cap_it) * cap_it;
       if (lane == 0 && ctr) ctr->chain_evals += n_iter;
       __syncwarp();
-      return kMapOk;
+      return kMapOkColinear;
     }
   }
   for (int i = 0; i < n_a; ++i) {
@@ -1101,6 +1104,42 @@ __device__ __noinline__ int warp_chain_tail_fast(const DevParams& P, int qlen, i
   return kMapOk;
 }
 
+// Tail of a co-linear pair in closed form: f is strictly increasing and p[i] = i-1, so the top
+// of z is the last anchor, mg_chain_bk_end walks to the start (s = zx - f[i] grows all the way,
+// f > 0), the chain is ALL anchors with score f[n_a-1]; if it fails min_sc / min_cnt every other
+// candidate is already marked used, so there is no hit.  All anchors share the diagonal, hence
+// mm_max_stretch returns the whole chain.  Fills the same R_* slots as map_chain_tail.
+__device__ __forceinline__ int warp_chain_tail_colinear(const DevParams& P, int qlen, int hap_len, uint32_t name_hash,
+                                                        const Ws<1>& ws, int n_a) {
+  const int lane = threadIdx.x & 31;
+  auto sx = ws.arr(A_SX), sy = ws.arr(A_SY), f = ws.arr(A_F), p = ws.arr(A_P);
+  const int32_t sc = f[n_a - 1];
+  if (!(sc >= P.min_sc && n_a >= P.min_cnt)) return kMapNoHit;
+  const uint32_t x0 = (uint32_t)sx[0], y0 = (uint32_t)sy[0], x1 = (uint32_t)sx[n_a - 1], y1 = (uint32_t)sy[n_a - 1];
+  uint32_t hash = name_hash;
+  hash ^= wang_hash((uint32_t)qlen) + wang_hash((uint32_t)P.seed);
+  hash = wang_hash(hash);
+  const uint32_t h = (uint32_t)hash64_full((hash64_full(anchor_x64(x0)) + hash64_full(anchor_y64(y0))) ^ hash);
+  const int32_t span = anchor_span(y0);
+  const int32_t rs = anchor_rpos(x0) + 1 - span, qs = anchor_qpos(y0) + 1 - span;
+  const int32_t re = anchor_rpos(x1) + 1, qe = anchor_qpos(y1) + 1;
+  int32_t l = qs;
+  l += l * P.a + P.end_bonus > P.q ? (l * P.a + P.end_bonus - P.q) / P.e : 0;
+  const int32_t rs0 = rs - l > 0 ? rs - l : 0;
+  l = qlen - qe;
+  l += l * P.a + P.end_bonus > P.q ? (l * P.a + P.end_bonus - P.q) / P.e : 0;
+  const int32_t re0 = re + l < hap_len ? re + l : hap_len;
+  __syncwarp();
+  if (lane == 0) {
+    ws.arr(R_SCORE)[0] = sc, ws.arr(R_CNT)[0] = n_a, ws.arr(R_AS)[0] = 0, ws.arr(R_HASH)[0] = (int32_t)((uint32_t)n_a ^ h);
+    ws.arr(R_REV)[0] = (int32_t)(x0 >> 31), ws.arr(R_PARENT)[0] = 0, ws.arr(R_ID)[0] = 0;
+    ws.arr(R_QS)[0] = qs, ws.arr(R_QE)[0] = qe, ws.arr(R_RS)[0] = rs, ws.arr(R_RE)[0] = re;
+    f[0] = rs0, p[0] = re0;
+  }
+  __syncwarp();
+  return kMapOk;
+}
+
 // exact-match shortcut of an extension tail: if the m query bases equal the first m target
 // bases (no ambiguity codes), the only path reaching the score m*a is the gap-free diagonal, so
 // ksw2 would return max = mqe = m*a at target offset m-1 with the cigar mM — no DP needed.
@@ -1164,7 +1203,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) k_chain_warp(Dev D) {
       PairIn pin{rv, hapc, hlen, idx, idx_n, D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], mid_occ};
       int n_a = 0, n_regs = 0;
       int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, ws, rsx, &ctr, &n_a) : kMapNoHit;
-      if (st == kMapOk) {
+      if (st == kMapOkColinear) {
+        st = warp_chain_tail_colinear(D.P, qlen, hlen, pin.name_hash, ws, n_a);
+        n_regs = 1;
+      } else if (st == kMapOk) {
         st = warp_chain_tail_fast(D.P, qlen, hlen, pin.name_hash, ws, n_a);
         n_regs = 1;
         if (st == -2) {
