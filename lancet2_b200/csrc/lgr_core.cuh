@@ -182,17 +182,63 @@ LGR_HD int sketch(const uint8_t* codes, int len, int w, int k, OutX out_x, OutY 
 // minimum's slot index drops by one per write and "buf_pos == min_pos" is "index fell below 0".
 // emit(x, y) receives the minimizers in upstream order; returns their count.
 // ------------------------------------------------------------------------------------
+// The window state machine of mm_sketch on its own: step(ix, iy, l) consumes the k-mer record of
+// one base (ix = UINT64_MAX when the base has no valid k-mer; l = number of consecutive
+// unambiguous bases ending here, 0 for an ambiguous base) — shared by the sequential sketch
+// below and by the warp kernel that computes the records 32 at a time.
+template <int W>
+struct MinimizerWindow {
+  uint64_t wx[W];
+  uint32_t wy[W];
+  uint64_t min_x;
+  uint32_t min_y;
+  int min_idx, k;
+  LGR_HD void init(int k_) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) wx[j] = UINT64_MAX, wy[j] = UINT32_MAX;
+    min_x = UINT64_MAX, min_y = UINT32_MAX, min_idx = W - 1, k = k_;
+  }
+  template <typename Emit>
+  LGR_HD void step(uint64_t ix, uint32_t iy, int l, Emit& emit) {
+#pragma unroll
+    for (int j = 0; j + 1 < W; ++j) wx[j] = wx[j + 1], wy[j] = wy[j + 1];
+    wx[W - 1] = ix, wy[W - 1] = iy;
+    --min_idx;
+    if (l == W + k - 1 && min_x != UINT64_MAX) {
+#pragma unroll
+      for (int j = 0; j + 1 < W; ++j)
+        if (min_x == wx[j] && wy[j] != min_y) emit(wx[j], wy[j]);
+    }
+    if (ix <= min_x) {
+      if (l >= W + k && min_x != UINT64_MAX) emit(min_x, min_y);
+      min_x = ix, min_y = iy, min_idx = W - 1;
+    } else if (min_idx < 0) {
+      if (l >= W + k - 1 && min_x != UINT64_MAX) emit(min_x, min_y);
+      min_x = UINT64_MAX;
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (min_x >= wx[j]) min_x = wx[j], min_y = wy[j], min_idx = j;
+      if (l >= W + k - 1 && min_x != UINT64_MAX) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          if (min_x == wx[j] && min_y != wy[j]) emit(wx[j], wy[j]);
+      }
+    }
+  }
+  template <typename Emit>
+  LGR_HD void finish(Emit& emit) {
+    if (min_x != UINT64_MAX) emit(min_x, min_y);
+  }
+};
+
 template <int W, typename Emit>
 LGR_HD int sketch_sr(const uint8_t* codes, int len, int k, Emit emit) {
   const uint64_t shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
   uint64_t kmer0 = 0, kmer1 = 0;
-  uint64_t wx[W];
-  uint32_t wy[W];
-#pragma unroll
-  for (int j = 0; j < W; ++j) wx[j] = UINT64_MAX, wy[j] = UINT32_MAX;
-  uint64_t min_x = UINT64_MAX;
-  uint32_t min_y = UINT32_MAX;
-  int l = 0, min_idx = W - 1, kmer_span = 0, n = 0;
+  MinimizerWindow<W> win;
+  win.init(k);
+  int l = 0, kmer_span = 0, n = 0;
+  auto count_emit = [&](uint64_t x, uint32_t y) { emit(x, y), ++n; };
   for (int i = 0; i < len; ++i) {
     const int c = codes[i] & 0xf;
     uint64_t ix = UINT64_MAX;
@@ -212,32 +258,9 @@ LGR_HD int sketch_sr(const uint8_t* codes, int len, int k, Emit emit) {
       l = 0;
       kmer_span = 0;
     }
-#pragma unroll
-    for (int j = 0; j + 1 < W; ++j) wx[j] = wx[j + 1], wy[j] = wy[j + 1];
-    wx[W - 1] = ix, wy[W - 1] = iy;
-    --min_idx;
-    if (l == W + k - 1 && min_x != UINT64_MAX) {
-#pragma unroll
-      for (int j = 0; j + 1 < W; ++j)
-        if (min_x == wx[j] && wy[j] != min_y) emit(wx[j], wy[j]), ++n;
-    }
-    if (ix <= min_x) {
-      if (l >= W + k && min_x != UINT64_MAX) emit(min_x, min_y), ++n;
-      min_x = ix, min_y = iy, min_idx = W - 1;
-    } else if (min_idx < 0) {
-      if (l >= W + k - 1 && min_x != UINT64_MAX) emit(min_x, min_y), ++n;
-      min_x = UINT64_MAX;
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (min_x >= wx[j]) min_x = wx[j], min_y = wy[j], min_idx = j;
-      if (l >= W + k - 1 && min_x != UINT64_MAX) {
-#pragma unroll
-        for (int j = 0; j < W; ++j)
-          if (min_x == wx[j] && min_y != wy[j]) emit(wx[j], wy[j]), ++n;
-      }
-    }
+    win.step(ix, iy, l, count_emit);
   }
-  if (min_x != UINT64_MAX) emit(min_x, min_y), ++n;
+  win.finish(count_emit);
   return n;
 }
 

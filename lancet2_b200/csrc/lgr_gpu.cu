@@ -135,6 +135,71 @@ __global__ void k_hap_sketch(Dev D) {
   D.idx_n[h] = n;
 }
 
+// one WARP per haplotype (odd k, w == 5): the 32 lanes compute the k-mer records (hash, strand,
+// run length of unambiguous bases) of 32 consecutive positions in parallel, then lane 0 feeds
+// them through the window state machine (MinimizerWindow<5>, same code as the sequential
+// sketch) and writes the table entries in order.
+__global__ void __launch_bounds__(128) k_hap_sketch_warp(Dev D) {
+  __shared__ uint64_t s_x[4][32];
+  __shared__ uint32_t s_y[4][32];
+  __shared__ int s_l[4][32];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (h >= D.n_haps) return;
+  const int64_t off = D.hap_off[h];
+  const int len = (int)(D.hap_off[h + 1] - off);
+  const uint8_t* codes = D.hap_codes + off;
+  uint64_t* tab = D.idx + off;
+  const int k = D.P.k;
+  const uint64_t mask = (1ULL << 2 * k) - 1;
+  MinimizerWindow<5> win;
+  win.init(k);
+  int n = 0;
+  auto emit = [&](uint64_t x, uint32_t y) {
+    if (n < len) tab[n] = (x >> 8) << kIdxShift | (uint64_t)y;
+    ++n;
+  };
+  int run_in = 0;  // unambiguous run length ending just before this chunk
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    const int c = i < len ? (codes[i] & 0xf) : 4;
+    // run length: distance to the last ambiguous base at or before i (inclusive scan of "last N")
+    int lastn = c > 3 ? i : -1;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(full, lastn, o);
+      if (lane >= o && v > lastn) lastn = v;
+    }
+    const int l = lastn >= 0 ? i - lastn : run_in + lane + 1;
+    uint64_t ix = UINT64_MAX;
+    uint32_t iy = UINT32_MAX;
+    if (i < len && l >= k) {
+      uint64_t k0 = 0, k1 = 0;
+      for (int t = 0; t < k; ++t) {
+        const uint64_t b = codes[i - k + 1 + t] & 0xf;
+        k0 = k0 << 2 | b;
+        k1 = k1 >> 2 | (3ULL ^ b) << 2 * (k - 1);
+      }
+      const int z = k0 < k1 ? 0 : 1;
+      ix = hash64_mask(z ? k1 : k0, mask) << 8 | (uint64_t)k;
+      iy = (uint32_t)i << 1 | (uint32_t)z;
+    }
+    s_x[warp][lane] = ix, s_y[warp][lane] = iy, s_l[warp][lane] = i < len ? l : 0;
+    run_in = __shfl_sync(full, l, 31);
+    __syncwarp();
+    if (lane == 0) {
+      const int cnt = len - base < 32 ? len - base : 32;
+      for (int t = 0; t < cnt; ++t) win.step(s_x[warp][t], s_y[warp][t], s_l[warp][t], emit);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    win.finish(emit);
+    if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
+    D.idx_n[h] = n;
+  }
+}
+
 // one CTA per haplotype: in-place bitonic sort of its table (keys are unique)
 __global__ void k_hap_sort(Dev D, float mid_occ_frac, int min_mid, int max_mid) {
   const int h = blockIdx.x;
@@ -225,9 +290,32 @@ __global__ void k_read_sketch(Dev D) {
   const int len = (int)(D.read_off[r + 1] - off);
   int n = 0;
   if (len > 0) {
-    n = sketch_any(D.read_codes + off, len, D.P.w, D.P.k, D.mz_x + off, D.mz_y + off, len);
+    // 32 saturating 4-bit counters of the minimizer hashes (bucket = low hash bits): a minimizer
+    // can only repeat more than q_occ_max times if its bucket does, so the O(n^2) filter is
+    // skipped for the (vast majority of) reads where no bucket gets that full
+    uint64_t cnt_lo = 0, cnt_hi = 0;
+    uint64_t* mzx = D.mz_x + off;
+    uint32_t* mzy = D.mz_y + off;
+    auto emit = [&](uint64_t x, uint32_t y) {
+      if (n < len) mzx[n] = x, mzy[n] = y;
+      ++n;
+      const int b = (int)(x >> 8) & 31, sh = (b & 15) * 4;
+      uint64_t& w = b < 16 ? cnt_lo : cnt_hi;
+      if (((w >> sh) & 15) < 15) w += 1ULL << sh;
+    };
+    if (D.P.w == 5) sketch_sr<5>(D.read_codes + off, len, D.P.k, emit);
+    else n = sketch(D.read_codes + off, len, D.P.w, D.P.k, mzx, mzy, len), cnt_lo = cnt_hi = ~0ULL;
     if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
-    if (D.P.q_occ_frac > 0.0f) n = seed_mz_flt(D.mz_x + off, D.mz_y + off, n, D.grp_mid[D.read_grp[r]], D.P.q_occ_frac);
+    const int q_occ_max = D.grp_mid[D.read_grp[r]];
+    bool may_repeat = q_occ_max < 15;
+    if (may_repeat) {
+      may_repeat = false;
+      for (int b = 0; b < 16; ++b)
+        may_repeat |= (int)((cnt_lo >> (4 * b)) & 15) > q_occ_max || (int)((cnt_hi >> (4 * b)) & 15) > q_occ_max;
+    } else {
+      may_repeat = true;  // counters saturate at 15: cannot rule anything out
+    }
+    if (D.P.q_occ_frac > 0.0f && may_repeat) n = seed_mz_flt(mzx, mzy, n, q_occ_max, D.P.q_occ_frac);
   }
   D.mz_n[r] = n;
 }
@@ -1782,7 +1870,8 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     const int enc_blocks = c->sm_count * 8;
     k_encode<<<enc_blocks, 256, 0, s>>>(D.hap_bases, D.hap_codes, hb);
     k_encode<<<enc_blocks, 256, 0, s>>>(D.read_bases, D.read_codes, rb);
-    k_hap_sketch<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D);
+    if (D.P.w == 5 && (D.P.k & 1)) k_hap_sketch_warp<<<(D.n_haps + 3) / 4, 128, 0, s>>>(D);
+    else k_hap_sketch<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D);
     k_hap_sort<<<D.n_haps, 128, 2048 * sizeof(uint64_t), s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
     k_group_mid<<<(D.n_groups + 127) / 128, 128, 0, s>>>(D, c->prm.min_mid_occ);
     launches += 5;
