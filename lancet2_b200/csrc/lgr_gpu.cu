@@ -43,6 +43,9 @@ enum Ctr {
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
+constexpr int kBucketBits = 9;
+constexpr int kBuckets = 1 << kBucketBits;
+
 struct DefRec {   // a parked pair
   int32_t read, hap, first_reg, n_regs;
 };
@@ -67,6 +70,8 @@ struct Dev {      // everything the kernels need, passed by value
   uint8_t *hap_codes, *read_codes;
   uint64_t* idx;                // [hap_off-indexed] sorted minimizer tables
   int32_t *idx_n, *hap_mid;     // [NH]
+  uint16_t* bkt;                // [NH][kBuckets+1] start of every hash bucket (top hash bits) in the sorted table
+  int bkt_shift;                // hash >> bkt_shift = bucket
   int32_t* grp_mid;             // [G] in: >0 fixed, <=0 latch from first hap; out: effective
   uint64_t* mz_x;               // [read_off-indexed]
   uint32_t* mz_y;
@@ -232,6 +237,13 @@ __global__ void k_hap_sort(Dev D, float mid_occ_frac, int min_mid, int max_mid) 
   }
   if (use_smem)
     for (int i = threadIdx.x; i < n; i += blockDim.x) tab[i] = s_tab[i];
+  // bucket directory: entries are sorted by hash, so the entries whose top hash bits equal b are
+  // the contiguous range [bkt[b], bkt[b+1]); k_chain_warp starts its lookups there
+  {
+    uint16_t* bk = D.bkt + (size_t)h * (kBuckets + 1);
+    for (int b = threadIdx.x; b <= kBuckets; b += blockDim.x)
+      bk[b] = (uint16_t)idx_lower_bound(a, n, ((uint64_t)b << D.bkt_shift) << kIdxShift);
+  }
   // mid_occ this haplotype would latch (mm_idx_cal_max_occ + clamp): histogram of the run
   // lengths of equal hashes; the kk-th smallest run length is read off the cumulative counts.
   __shared__ int s_hist[64];
@@ -611,8 +623,8 @@ constexpr int kWarpsPerCta = 4;
 constexpr int kMapOkColinear = 2;  // warp_seed_chain: chain DP done by the co-linear closed form
 
 template <int CAP>
-__device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const Ws<1>& ws, RadixScratch* rsx,
-                                               ChainCounters* ctr, int* n_a_out) {
+__device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const uint16_t* bkt, const Ws<1>& ws,
+                                               RadixScratch* rsx, ChainCounters* ctr, int* n_a_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
@@ -629,7 +641,18 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     if (i < in.mz_n) {
       const uint64_t mx = in.mz_x[i];
       const uint64_t hx = mx >> 8;
-      s0 = idx_lower_bound(in.idx, in.idx_n, hx << kIdxShift);
+      {  // bisection restricted to the minimizer's hash bucket (usually 0-2 entries)
+        const int b = (int)(hx >> D.bkt_shift);
+        int lo = bkt[b];
+        int hi = bkt[b + 1];
+        const uint64_t key = hx << kIdxShift;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (in.idx[mid] < key) lo = mid + 1;
+          else hi = mid;
+        }
+        s0 = lo;
+      }
       int s1 = s0;
       while (s1 < in.idx_n && (in.idx[s1] >> kIdxShift) == hx && s1 - s0 < 8) ++s1;
       if (s1 - s0 == 8) s1 = idx_lower_bound(in.idx, in.idx_n, (hx + 1) << kIdxShift);  // long run: finish by bisection
@@ -1003,6 +1026,64 @@ __device__ __forceinline__ int32_t warp_edit_distance(const uint8_t* read_codes,
   return nm;
 }
 
+// One pass over a gap-free forward-strand alignment (cigar = one M op, the normal case):
+// mm_update_extra's mlen / blen / n_ambi / dp_max, the ungapped core score and NM together,
+// from the same two code bytes per column.
+__device__ __noinline__ void warp_finish_pure_m(const DevParams& P, const uint8_t* read_codes, const uint8_t* hap, int qb, int tb,
+                                                int len, int c_qs, int c_qe, RegFinal* out, int32_t* core_out, int32_t* nm_out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  constexpr int NEG = -(1 << 28);
+  int32_t blen = 0, mlen = 0, n_ambi_tot = 0, s = 0, mx = 0, core = 0, nm = 0;
+  for (int base = 0; base < len; base += 32) {
+    const int l = base + lane;
+    const bool valid = l < len;
+    int m = 0, cm = 0;
+    bool ambi = false, diff = false, mis = false;
+    if (valid) {
+      const int qb_ = read_codes[qb + l], tb_ = hap[tb + l];
+      const int cq = qb_ & 0xf, ct = tb_ & 0xf;
+      ambi = ct > 3 || cq > 3;
+      diff = !ambi && ct != cq;
+      m = ambi ? -P.sc_ambi : (diff ? -P.b : P.a);
+      mis = (qb_ >> 4) != (tb_ >> 4);
+      if (qb + l >= c_qs && qb + l < c_qe) cm = ambi ? P.e : (diff ? -P.b : P.a);
+    }
+    const int na = __popc(__ballot_sync(full, ambi)), nd = __popc(__ballot_sync(full, diff));
+    nm += __popc(__ballot_sync(full, mis));
+    core += __reduce_add_sync(full, cm);
+    const int cnt = len - base < 32 ? len - base : 32;
+    blen += cnt - na, mlen += cnt - (na + nd), n_ambi_tot += na;
+    if (__ballot_sync(full, valid && m < 0) == 0) {
+      s += __reduce_add_sync(full, m);
+      if (s > mx) mx = s;
+    } else {
+      int A = valid ? m : 0, B = valid ? 0 : NEG, C = valid ? m : NEG, Dd = valid ? 0 : NEG;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int Ay = __shfl_down_sync(full, A, o), By = __shfl_down_sync(full, B, o);
+        const int Cy = __shfl_down_sync(full, C, o), Dy = __shfl_down_sync(full, Dd, o);
+        if (lane + o < 32) {
+          int d2 = B + Cy;
+          if (Dd > d2) d2 = Dd;
+          if (Dy > d2) d2 = Dy;
+          const int c2 = A + Cy > C ? A + Cy : C;
+          const int b2 = B + Ay > By ? B + Ay : By;
+          A = A + Ay, B = b2, C = c2, Dd = d2;
+          if (B < NEG) B = NEG;
+          if (C < NEG) C = NEG;
+          if (Dd < NEG) Dd = NEG;
+        }
+      }
+      A = __shfl_sync(full, A, 0), B = __shfl_sync(full, B, 0), C = __shfl_sync(full, C, 0), Dd = __shfl_sync(full, Dd, 0);
+      const int best = s + C > Dd ? s + C : Dd;
+      if (best > mx) mx = best;
+      s = s + A > B ? s + A : B;
+    }
+  }
+  out->blen = blen, out->mlen = mlen, out->n_ambi = n_ambi_tot, out->dp_max = mx;
+  *core_out = core, *nm_out = nm;
+}
+
 // finish_pair (lgr_core.cuh) with the per-base loops spread over the warp.  Uniform control flow;
 // cigar assembly / mm_fix_cigar stay scalar on lane 0.  Returns the op count of the winning cigar
 // (in fs.best), or -1 on scratch overflow; *out is valid on every lane.
@@ -1013,6 +1094,7 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
   const DevParams& P = D.P;
   const int qlen = rv.qlen;
   int best = -1, n_surv = 0;
+  int32_t best_nm = -1;
   uint64_t best_key = 0;
   RegFinal bf;
   bf.n_cig = 0;
@@ -1032,9 +1114,16 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
     const int32_t score = regs[r].score, cnt = regs[r].cnt;
     const uint32_t hash = regs[r].hash;
     RegFinal rf;
-    warp_update_extra(P, rv, rev, hap, ra.qb, ra.tb, fs.cig, ra.n, &rf);
+    int32_t nm_reg = -1;
+    if (ra.n == 1 && rev == 0 && (fs.cig[0] & 0xf) == 0) {
+      int32_t core = 0;
+      warp_finish_pure_m(P, rv.codes, hap, ra.qb, ra.tb, (int)(fs.cig[0] >> 4), c_qs, c_qe, &rf, &core, &nm_reg);
+      rf.dp_score = ra.dp_ext + core;
+    } else {
+      warp_update_extra(P, rv, rev, hap, ra.qb, ra.tb, fs.cig, ra.n, &rf);
+      rf.dp_score = ra.dp_ext + warp_core_score(P, rv, rev, hap, c_qs, c_rs, c_qe - c_qs);
+    }
     rf.rs = ra.rs, rf.re = ra.re, rf.qs = ra.qs, rf.qe = ra.qe, rf.n_cig = ra.n;
-    rf.dp_score = ra.dp_ext + warp_core_score(P, rv, rev, hap, c_qs, c_rs, c_qe - c_qs);
     bool flt = false;
     if (cnt < P.min_cnt) flt = true;
     if (rf.mlen < P.min_sc) flt = true;
@@ -1048,7 +1137,7 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
     }
     ++n_surv;
     if (best < 0 || key >= best_key) {
-      best = r, best_key = key, bf = rf;
+      best = r, best_key = key, bf = rf, best_nm = nm_reg;
       uint32_t* tmp = fs.best;
       fs.best = fs.cig;
       fs.cig = tmp;
@@ -1067,7 +1156,7 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
   out->n_ambi = bf.n_ambi;
   out->n_cigar = bf.n_cig;
   out->n_regs = n_ret;
-  out->nm = warp_edit_distance(rv.codes, qlen, hap, bf.rs, bf.re, bf.qs, fs.best, bf.n_cig);
+  out->nm = best_nm >= 0 ? best_nm : warp_edit_distance(rv.codes, qlen, hap, bf.rs, bf.re, bf.qs, fs.best, bf.n_cig);
   return bf.n_cig;
 }
 
@@ -1228,26 +1317,45 @@ __device__ __forceinline__ int warp_chain_tail_colinear(const DevParams& P, int 
   return kMapOk;
 }
 
-// exact-match shortcut of an extension tail: if the m query bases equal the first m target
-// bases (no ambiguity codes), the only path reaching the score m*a is the gap-free diagonal, so
-// ksw2 would return max = mqe = m*a at target offset m-1 with the cigar mM — no DP needed.
+// Closed forms of an extension tail (both proven in DESIGN.md §4, both checked against the DP by
+// the parity tests):
+//  * exact match, n >= m: the m query bases equal the first m target bases (no ambiguity codes).
+//    The only path reaching m*a is the gap-free diagonal ⇒ max = mqe = m*a at target offset m-1,
+//    cigar mM.
+//  * overhang, n < m: the first n query bases equal the n target bases and the LAST query base
+//    differs from the last target base.  Every path ends in column <= n-1, has at most n matches
+//    and at least m-n inserted bases; n*a - (q + e(m-n)) is reached only by "n matches, then one
+//    insertion of m-n" (an insertion anywhere earlier would have to match t[n-1] with q[m-1]).
+//    ⇒ max = n*a, mqe_t = n-1, cigar nM (m-n)I in alignment order (the left extension reports it
+//    outward-in as (m-n)I nM).  Needs a, q, e > 0.
 __device__ __forceinline__ bool warp_ext_exact(const DevParams& P, const ReadView& rv, const uint8_t* hapc, RegRec* reg, int side,
                                                int64_t* cells_full) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int m = reg->ext[side].m, n = reg->ext[side].n;
-  if (n < m || P.a <= 0) return false;
+  if (P.a <= 0) return false;
+  const int nn = n < m ? n : m;  // bases that must match
+  if (n < m && (P.q <= 0 || P.e <= 0)) return false;
   ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
   ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
   bool same = true;
-  for (int j = lane; j < m; j += 32) {
+  for (int j = lane; j < nn; j += 32) {
     const int qc = qf(j), tc = tf(j);
     same &= qc == tc && qc < 4;
   }
+  if (n < m && lane == 0) same &= qf(m - 1) != tf(n - 1);
   if (!__all_sync(full, same)) return false;
   if (lane == 0) {
     ExtRec& E = reg->ext[side];
-    E.max = m * P.a, E.mqe_t = m - 1, E.n_cig = 1, E.cig_off = -1, E.inl[0] = (uint32_t)m << 4;
+    E.max = nn * P.a, E.mqe_t = nn - 1, E.cig_off = -1;
+    if (n >= m) {
+      E.n_cig = 1, E.inl[0] = (uint32_t)m << 4;
+    } else {
+      E.n_cig = 2;
+      const uint32_t mop = (uint32_t)n << 4, iop = (uint32_t)(m - n) << 4 | 1u;
+      if (side == 0) E.inl[0] = iop, E.inl[1] = mop;
+      else E.inl[0] = mop, E.inl[1] = iop;
+    }
     *cells_full += (int64_t)m * n;
   }
   __syncwarp();
@@ -1290,7 +1398,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) k_chain_warp(Dev D) {
       ReadView rv{D.read_codes + roff, qlen};
       PairIn pin{rv, hapc, hlen, idx, idx_n, D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], mid_occ};
       int n_a = 0, n_regs = 0;
-      int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, ws, rsx, &ctr, &n_a) : kMapNoHit;
+      int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, D.bkt + (size_t)h * (kBuckets + 1), ws, rsx, &ctr, &n_a) : kMapNoHit;
       if (st == kMapOkColinear) {
         st = warp_chain_tail_colinear(D.P, qlen, hlen, pin.name_hash, ws, n_a);
         n_regs = 1;
@@ -1487,7 +1595,7 @@ struct lgr_ctx {
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_ws, b_fin, b_regs,
       b_defs, b_tasks, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
-      b_ctr, b_ws_big, b_wreg, b_rsx;
+      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt;
   Dev D;
   bool resident = false;
   int max_read_len = 0, max_hap_len = 0;
@@ -1647,7 +1755,7 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
                     &c->b_mz_n, &c->b_ws, &c->b_fin, &c->b_regs, &c->b_defs, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
-                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx};
+                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& e : c->ev) cudaEventDestroy(e);
@@ -1767,7 +1875,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int64_t n_pairs = po, n_assign = ao;
   if ((rc = ensure(c, c->b_hap_codes, hap_bytes)) || (rc = ensure(c, c->b_read_codes, read_bytes)) ||
       (rc = ensure(c, c->b_idx, sizeof(uint64_t) * hap_bytes)) || (rc = ensure(c, c->b_idx_n, sizeof(int32_t) * NH)) ||
-      (rc = ensure(c, c->b_hap_mid, sizeof(int32_t) * NH)) || (rc = ensure(c, c->b_mz_x, sizeof(uint64_t) * read_bytes)) ||
+      (rc = ensure(c, c->b_hap_mid, sizeof(int32_t) * NH)) || (rc = ensure(c, c->b_bkt, sizeof(uint16_t) * (size_t)NH * (kBuckets + 1))) || (rc = ensure(c, c->b_mz_x, sizeof(uint64_t) * read_bytes)) ||
       (rc = ensure(c, c->b_mz_y, sizeof(uint32_t) * read_bytes)) || (rc = ensure(c, c->b_mz_n, sizeof(int32_t) * NR)))
     return rc;
   c->map_blocks = c->sm_count * 4;
@@ -1834,6 +1942,8 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.hap_codes = (uint8_t*)c->b_hap_codes.p, D.read_codes = (uint8_t*)c->b_read_codes.p;
   D.idx = (uint64_t*)c->b_idx.p, D.idx_n = (int32_t*)c->b_idx_n.p, D.hap_mid = (int32_t*)c->b_hap_mid.p;
   D.grp_mid = (int32_t*)c->b_grp_mid.p;
+  D.bkt = (uint16_t*)c->b_bkt.p;
+  D.bkt_shift = 2 * c->prm.k > kBucketBits ? 2 * c->prm.k - kBucketBits : 0;
   D.mz_x = (uint64_t*)c->b_mz_x.p, D.mz_y = (uint32_t*)c->b_mz_y.p, D.mz_n = (int32_t*)c->b_mz_n.p;
   D.ws = nullptr, D.ws_cap = 0;
   D.wreg_scratch = (RegRec*)c->b_wreg.p, D.rsx_scratch = (RadixScratch*)c->b_rsx.p;
