@@ -1,19 +1,20 @@
 // lgr_gpu.cu — sm_100a kernels + the C-ABI of the B200 read→haplotype realignment path.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 //
-// Pipeline per batch (all on one stream; see DESIGN.md for the data layout and rooflines):
-//   k_encode          ASCII → code bytes (nt4 | Lancet code) for haplotypes and reads
-//   k_hap_sketch      one lane per haplotype: minimizer sketch → unsorted table
-//   k_hap_sort        one CTA per haplotype: bitonic sort of the table (the "index")
-//   k_hap_mid         mid_occ a Genotyper would latch from each haplotype / group
-//   k_read_sketch     one lane per read: sketch + mm_seed_mz_flt
-//   k_map             one lane per (read, haplotype) pair: seeds → anchors → sort → chain DP →
-//                     backtrack → regs → small extensions inline → finish; pairs with a long
-//                     tail are parked (RegRec) and their tails queued
-//   k_ext_big         one warp per queued tail: anti-diagonal wavefront affine-gap DP with
-//                     shuffle neighbour exchange, direction bytes in HBM scratch, traceback
-//   k_finish          one lane per parked pair
-//   k_assign          one lane per (read, variant): local scoring + best-allele selection
+// Pipeline per batch (all on one stream, no host sync inside; DESIGN.md has layout and rooflines):
+//   k_encode            ASCII → code bytes (nt4 | Lancet code) for haplotypes and reads
+//   k_hap_sketch_warp   one warp per haplotype: minimizer sketch → unsorted table
+//   k_hap_sort          one CTA per haplotype: bitonic sort of the table (the "index"), hash-bucket
+//                       directory, mid_occ the haplotype would latch
+//   k_group_mid         effective mid_occ per group
+//   k_read_sketch       one lane per read: sketch + mm_seed_mz_flt
+//   k_chain_warp        ONE WARP PER (read, haplotype) PAIR: seeds → anchors → sort → chain DP →
+//                       backtrack → regs → SR stretch; regs parked in HBM (RegRec)
+//   k_chain_overflow    the same for pairs whose anchors exceed the shared-memory cap (lane per pair)
+//   k_finish_warp       one warp per parked pair: extensions (closed forms / anti-diagonal
+//                       wavefront DP with shuffle neighbour exchange + traceback), cigar assembly,
+//                       mm_fix_cigar, mm_update_extra, filter/sort, NM → lgr_aln
+//   k_assign            one lane per (read, variant): local scoring + best-allele selection
 // There is no host fallback: every entry point fails with an error code when CUDA fails.
 #include <cuda_runtime.h>
 
@@ -38,7 +39,7 @@ __constant__ double c_phred_err[256] = {
 
 // counters (int64 slots in device memory)
 enum Ctr {
-  C_ITEM = 0, C_NDEF, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ITEM = 0, C_UNUSED0, C_UNUSED1, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
   C_ALIGNED, C_TASKPOS, C_OVFPOS, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
@@ -46,8 +47,8 @@ enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP =
 constexpr int kBucketBits = 9;
 constexpr int kBuckets = 1 << kBucketBits;
 
-struct DefRec {   // a parked pair
-  int32_t read, hap, first_reg, n_regs;
+struct PairReg {  // per pair: its parked RegRecs in the arena (n == 0: nothing to finish)
+  int32_t first, n, read, hap;
 };
 
 struct Dev {      // everything the kernels need, passed by value
@@ -83,7 +84,7 @@ struct Dev {      // everything the kernels need, passed by value
   int fin_cap;
   // parked pairs / tails
   RegRec* regs;  int64_t regs_cap;
-  DefRec* defs;  int64_t defs_cap;
+  PairReg* pair_reg;             // [n_pairs]
   uint32_t* ext_arena; int64_t ext_arena_cap;
   int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
   // k_ext_big scratch
@@ -332,12 +333,6 @@ __global__ void k_read_sketch(Dev D) {
   D.mz_n[r] = n;
 }
 
-// ---------------------------------------------------------------------------------------
-// k_map: one lane per pair.  A warp takes one work item = (haplotype, up to 32 consecutive
-// reads of its group); all lanes therefore share the haplotype table and bases (L1 hits) and
-// their interleaved workspace accesses coalesce while they run in lock step.
-// FROM_LIST: second pass over pairs whose anchor count exceeded the fast workspace.
-// ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void write_invalid(AlnOut* o) {
   o->valid = 0, o->score = 0, o->rs = 0, o->re = 0, o->qs = 0, o->qe = 0, o->rev = 0, o->dp_score = 0, o->dp_max = 0;
   o->mlen = 0, o->blen = 0, o->n_ambi = 0, o->nm = 0, o->n_cigar = 0, o->cigar_off = -1, o->n_regs = 0;
@@ -362,125 +357,66 @@ __device__ __forceinline__ void store_final(const Dev& D, int64_t pair, const Al
   D.aln[pair] = o;
 }
 
-template <bool FROM_LIST>
-__global__ void __launch_bounds__(128) k_map(Dev D) {
+// ---------------------------------------------------------------------------------------
+// k_chain_overflow: phase A for the pairs whose seeds/anchors exceeded the shared-memory cap of
+// k_chain_warp (tandem repeats: hundreds to thousands of anchors).  One LANE per pair running the
+// scalar core (map_chain_phase) over a 16384-anchor HBM workspace interleaved per warp; regs are
+// parked exactly like k_chain_warp does.  Exits immediately when the overflow list is empty.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_chain_overflow(Dev D) {
   const int lane = threadIdx.x & 31;
   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
   const int gwarp = gthread >> 5;
+  const long long n_work = D.ctr[C_NOVF] < D.ovf_cap ? D.ctr[C_NOVF] : D.ovf_cap;
+  if (n_work == 0) return;
   Ws<32> ws;
   ws.cap = D.ws_cap;
   ws.base = D.ws + (size_t)gwarp * A_COUNT * D.ws_cap * 32 + lane;
-  uint32_t* fin0 = D.fin_scratch + (size_t)gthread * 2 * D.fin_cap;
   RadixScratch rsx;
   ChainCounters ctr{0, 0, 0, 0};
-  long long n_aligned = 0;
-  const long long n_work = FROM_LIST ? D.ctr[C_NOVF] : (long long)D.n_items;
   for (;;) {
     long long item = 0;
-    if (lane == 0) item = atomicAdd((unsigned long long*)&D.ctr[FROM_LIST ? C_OVFPOS : C_ITEM], FROM_LIST ? 32ULL : 1ULL);
+    if (lane == 0) item = atomicAdd((unsigned long long*)&D.ctr[C_OVFPOS], 32ULL);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_work) break;
-    int r, h;
-    bool active;
-    if (FROM_LIST) {
-      active = item + lane < n_work;
-      r = active ? D.ovf_read[item + lane] : 0;
-      h = active ? D.ovf_hap[item + lane] : 0;
-    } else {
-      h = D.item_hap[item];
-      active = lane < D.item_n[item];
-      r = D.item_r0[item] + lane;
-    }
-    if (active) {
+    if (item + lane < n_work) {
+      const int r = D.ovf_read[item + lane], h = D.ovf_hap[item + lane];
       const int g = D.read_grp[r];
-      const int h_local = h - D.grp_hap_begin[g];
-      const int64_t pair = D.pair_off[r] + h_local;
+      const int64_t pair = D.pair_off[r] + (h - D.grp_hap_begin[g]);
       const int64_t roff = D.read_off[r], hoff = D.hap_off[h];
       const int qlen = (int)(D.read_off[r + 1] - roff);
       const int hlen = (int)(D.hap_off[h + 1] - hoff);
       ReadView rv{D.read_codes + roff, qlen};
-      const uint8_t* hapc = D.hap_codes + hoff;
-      PairIn pin{rv, hapc, hlen, D.idx + hoff, D.idx_n[h], D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], D.grp_mid[g]};
+      PairIn pin{rv, D.hap_codes + hoff, hlen, D.idx + hoff, D.idx_n[h], D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], D.grp_mid[g]};
       int n_regs = 0;
       const int st = qlen > 0 ? map_chain_phase<32>(D.P, pin, ws, &rsx, &n_regs, &ctr) : kMapNoHit;
+      PairReg pr{0, 0, r, h};
       if (st == kMapOverflow) {
-        if (FROM_LIST) {
-          atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
-          write_invalid(&D.aln[pair]);
-        } else {
-          const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
-          if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h;
-          else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
-        }
+        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
+        write_invalid(&D.aln[pair]);
       } else if (st == kMapNoHit) {
         write_invalid(&D.aln[pair]);
       } else {
-        // decide: everything inline (all tails <= kSmallM, <= 2 regs) or park the pair
-        RegRec loc[2];
-        bool park = n_regs > 2;
-        if (!park) {
-          for (int i = 0; i < n_regs; ++i) {
-            export_reg<32>(ws, i, qlen, &loc[i]);
-            if (!ext_is_small(D.P, loc[i].ext[0]) || !ext_is_small(D.P, loc[i].ext[1])) park = true;
-          }
-        }
-        uint8_t dir[kSmallCells];
-        int32_t hcol[kSmallDim + 2], ecol[kSmallDim + 2];
-        uint32_t cig_tmp[kSmallCig];
-        auto alloc_ext = [&](int n) -> int64_t {
-          const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)n);
-          if (o + n > D.ext_arena_cap) {
-            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
-            return -1;
-          }
-          return o;
-        };
-        if (!park) {
-          bool ok = true;
-          for (int i = 0; i < n_regs; ++i)
-            for (int side = 0; side < 2; ++side)
-              if (loc[i].ext[side].m > 0)
-                ok &= run_ext_scalar(D.P, rv, hapc, &loc[i], side, dir, hcol, ecol, cig_tmp, kSmallCig, D.ext_arena,
-                                     alloc_ext, &ctr);
-          FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
-          AlnOut ao;
-          const int nc = ok ? finish_pair(D.P, rv, hapc, loc, n_regs, D.ext_arena, fs, &ao) : -1;
-          if (nc < 0) {
-            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
-            write_invalid(&D.aln[pair]);
-          } else {
-            store_final(D, pair, ao, fs.best, nc);
-            n_aligned += ao.valid;
-          }
+        const long long first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
+        if (first + n_regs > D.regs_cap) {
+          atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+          write_invalid(&D.aln[pair]);
         } else {
-          const long long first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
-          const long long di = atomicAdd((unsigned long long*)&D.ctr[C_NDEF], 1ULL);
-          if (first + n_regs > D.regs_cap || di >= D.defs_cap) {
-            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
-            write_invalid(&D.aln[pair]);
-          } else {
-            D.defs[di] = DefRec{r, h, (int32_t)first, n_regs};
-            for (int i = 0; i < n_regs; ++i) export_reg<32>(ws, i, qlen, &D.regs[first + i]);  // extensions: k_finish_warp
-          }
+          pr = PairReg{(int32_t)first, n_regs, r, h};
+          for (int i = 0; i < n_regs; ++i) export_reg<32>(ws, i, qlen, &D.regs[first + i]);
         }
       }
+      D.pair_reg[pair] = pr;
     }
     __syncwarp();
   }
-  // stats
   for (int o = 16; o > 0; o >>= 1) {
     ctr.chain_evals += __shfl_down_sync(0xffffffffu, ctr.chain_evals, o);
     ctr.n_anchors += __shfl_down_sync(0xffffffffu, ctr.n_anchors, o);
-    ctr.dp_cells += __shfl_down_sync(0xffffffffu, ctr.dp_cells, o);
-    ctr.dp_cells_full += __shfl_down_sync(0xffffffffu, ctr.dp_cells_full, o);
-    n_aligned += __shfl_down_sync(0xffffffffu, n_aligned, o);
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
     atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)ctr.dp_cells);
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
-    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
   }
 }
 
@@ -617,7 +553,7 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
 //   tail      backtrack → regs → stretch: the scalar core (map_chain_tail) on lane 0
 //   extension short tails scalar on lane 0, long tails on the whole warp (ext_dp_warp)
 //   finish    scalar core on lane 0 (cigar assembly, mm_fix_cigar, mm_update_extra, NM)
-// Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_map<true>).
+// Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_chain_overflow).
 // ---------------------------------------------------------------------------------------
 constexpr int kWarpsPerCta = 4;
 constexpr int kMapOkColinear = 2;  // warp_seed_chain: chain DP done by the co-linear closed form
@@ -1365,7 +1301,7 @@ __device__ __forceinline__ bool warp_ext_exact(const DevParams& P, const ReadVie
 constexpr int kWarpItemReads = 16;  // reads per warp work item (all against one haplotype)
 
 // Phase A kernel: seeds → anchors → chain DP → regs, one warp per pair.  Every pair with at least
-// one reg is parked: its RegRecs go to the arena and a DefRec to the list k_finish_warp consumes.
+// one reg is parked: its RegRecs go to the arena and its PairReg slot tells k_finish_warp where.
 template <int CAP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) k_chain_warp(Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1418,14 +1354,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 6) k_chain_warp(Dev D) {
           else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
         } else if (st == kMapNoHit) {
           write_invalid(&D.aln[pair]);
+          D.pair_reg[pair] = PairReg{0, 0, r, h};
         } else {
           const long long first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
-          const long long di = atomicAdd((unsigned long long*)&D.ctr[C_NDEF], 1ULL);
-          if (first + n_regs > D.regs_cap || di >= D.defs_cap) {
+          if (first + n_regs > D.regs_cap) {
             atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
             write_invalid(&D.aln[pair]);
+            D.pair_reg[pair] = PairReg{0, 0, r, h};
           } else {
-            D.defs[di] = DefRec{r, h, (int32_t)first, n_regs};
+            D.pair_reg[pair] = PairReg{(int32_t)first, n_regs, r, h};
             for (int i = 0; i < n_regs; ++i) export_reg<1>(ws, i, qlen, &D.regs[first + i]);
           }
         }
@@ -1471,23 +1408,25 @@ __global__ void __launch_bounds__(128, 6) k_finish_warp(Dev D) {
   int32_t* Fb = Hb + D.bnd_per_warp / 2;
   uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
   uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
-  const long long n_def = D.ctr[C_NDEF] < D.defs_cap ? D.ctr[C_NDEF] : D.defs_cap;
   ChainCounters ctr{0, 0, 0, 0};
   long long n_aligned = 0;
+  // parked pairs are taken one at a time (pair order): extension work per pair varies by orders
+  // of magnitude, so the finest granularity balances best
   for (;;) {
-    long long di = 0;
-    if (lane == 0) di = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
-    di = __shfl_sync(full, di, 0);
-    if (di >= n_def) break;
-    const DefRec d = D.defs[di];
-    const int g = D.read_grp[d.read];
-    const int64_t pair = D.pair_off[d.read] + (d.hap - D.grp_hap_begin[g]);
-    const int64_t roff = D.read_off[d.read], hoff = D.hap_off[d.hap];
-    ReadView rv{D.read_codes + roff, (int)(D.read_off[d.read + 1] - roff)};
-    const uint8_t* hapc = D.hap_codes + hoff;
-    RegRec* regs = D.regs + d.first_reg;
+    long long pair = 0;
+    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
+    pair = __shfl_sync(full, pair, 0);
+    if (pair >= D.n_pairs) break;
+   {
+    const PairReg d = D.pair_reg[pair];
+    if (d.n <= 0) continue;
+    const int read = d.read;
+    const uint8_t* hapc = D.hap_codes + D.hap_off[d.hap];
+    const int64_t roff = D.read_off[read];
+    ReadView rv{D.read_codes + roff, (int)(D.read_off[read + 1] - roff)};
+    RegRec* regs = D.regs + d.first;
     int okw = 1;
-    for (int i = 0; i < d.n_regs; ++i) {
+    for (int i = 0; i < d.n; ++i) {
       for (int side = 0; side < 2; ++side) {
         const int m = regs[i].ext[side].m;
         if (m <= 0 || regs[i].ext[side].mqe_t >= 0) continue;  // none, or already computed
@@ -1505,7 +1444,7 @@ __global__ void __launch_bounds__(128, 6) k_finish_warp(Dev D) {
     okw = __shfl_sync(full, okw, 0);
     FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
     AlnOut ao;
-    const int nc = okw ? finish_pair_warp(D, rv, hapc, regs, d.n_regs, fs, &ao) : -1;
+    const int nc = okw ? finish_pair_warp(D, rv, hapc, regs, d.n, fs, &ao) : -1;
     if (lane == 0) {
       if (nc < 0) {
         atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
@@ -1516,6 +1455,7 @@ __global__ void __launch_bounds__(128, 6) k_finish_warp(Dev D) {
       }
     }
     __syncwarp();
+   }
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)ctr.dp_cells);
@@ -1594,7 +1534,7 @@ struct lgr_ctx {
   DevBuf b_grp_hap, b_grp_read, b_grp_var, b_hap_off, b_read_off, b_var_hap_off, b_hap_bases, b_read_bases, b_read_quals,
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_ws, b_fin, b_regs,
-      b_defs, b_tasks, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
+      b_pair_reg, b_tasks, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
       b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt;
   Dev D;
   bool resident = false;
@@ -1753,7 +1693,7 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_read_bases, &c->b_read_quals, &c->b_name_hash, &c->b_var_start, &c->b_var_len, &c->b_var_allele,
                     &c->b_read_grp, &c->b_hap_grp, &c->b_pair_off, &c->b_asg_off, &c->b_item_hap, &c->b_item_r0, &c->b_item_n,
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
-                    &c->b_mz_n, &c->b_ws, &c->b_fin, &c->b_regs, &c->b_defs, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
+                    &c->b_mz_n, &c->b_ws, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
                     &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt};
   for (DevBuf* b : bufs)
@@ -1907,13 +1847,13 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
   const int wcig_cap = 2 * Lm + 8;
-  const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024, defs_cap = n_pairs + 1024;
+  const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024;
   const int64_t ext_arena_cap = 4 * n_pairs + (1 << 20);
   const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
   if ((rc = ensure(c, c->b_wreg, sizeof(RegRec) * (size_t)ext_warps * c->warp_cap)) ||
       (rc = ensure(c, c->b_rsx, sizeof(RadixScratch) * (size_t)ext_warps)) ||
       (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)n_threads * 2 * fin_cap)) ||
-      (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_defs, sizeof(DefRec) * (size_t)defs_cap)) ||
+      (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_pair_reg, sizeof(PairReg) * (size_t)n_pairs)) ||
       (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
       (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
       (rc = ensure(c, c->b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
@@ -1949,7 +1889,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.wreg_scratch = (RegRec*)c->b_wreg.p, D.rsx_scratch = (RadixScratch*)c->b_rsx.p;
   D.fin_scratch = (uint32_t*)c->b_fin.p, D.fin_cap = fin_cap;
   D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
-  D.defs = (DefRec*)c->b_defs.p, D.defs_cap = defs_cap;
+  D.pair_reg = (PairReg*)c->b_pair_reg.p;
   D.ext_arena = (uint32_t*)c->b_ext_arena.p, D.ext_arena_cap = ext_arena_cap;
   D.ovf_read = (int32_t*)c->b_ovf_read.p, D.ovf_hap = (int32_t*)c->b_ovf_hap.p, D.ovf_cap = n_pairs;
   D.dir_scratch = (uint8_t*)c->b_dir.p, D.dir_per_warp = dir_per_warp;
@@ -1998,7 +1938,7 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
       // a large HBM workspace; exits immediately when the list is empty (no host round trip)
       Dev D2 = D;
       D2.ws = (int32_t*)c->b_ws_big.p, D2.ws_cap = kCapBig;
-      k_map<true><<<kBigWarps / 4, 128, 0, s>>>(D2);
+      k_chain_overflow<<<kBigWarps / 4, 128, 0, s>>>(D2);
       launches += 1;
     }
     k_finish_warp<<<c->ext_blocks, 128, 0, s>>>(D);
