@@ -1302,8 +1302,14 @@ constexpr int kWarpItemReads = 16;  // reads per warp work item (all against one
 
 // Phase A kernel: seeds → anchors → chain DP → regs, one warp per pair.  Every pair with at least
 // one reg is parked: its RegRecs go to the arena and its PairReg slot tells k_finish_warp where.
+#ifndef LGR_CHAIN_MINB
+#define LGR_CHAIN_MINB 7
+#endif
+#ifndef LGR_FIN_MINB
+#define LGR_FIN_MINB 8
+#endif
 template <int CAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 6) k_chain_warp(Dev D) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_warp(Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
   const unsigned full = 0xffffffffu;
@@ -1398,7 +1404,7 @@ __device__ __noinline__ bool ext_small_lane0(const Dev& D, const ReadView& rv, c
 constexpr int kTinyCells = 24;         // extensions up to this many cells run scalar on lane 0
 constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
 
-__global__ void __launch_bounds__(128, 6) k_finish_warp(Dev D) {
+__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D) {
   __shared__ uint8_t s_dir[4 * kDirSmemPerWarp];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -1842,7 +1848,11 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
     }
     c->warp_blocks = c->sm_count * per_sm;
   }
-  c->ext_blocks = c->sm_count * 6;
+  {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    c->ext_blocks = c->sm_count * per_sm;
+  }
   const int64_t ext_warps = std::max<int64_t>((int64_t)c->ext_blocks * 4, (int64_t)c->warp_blocks * kWarpsPerCta);
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
