@@ -77,6 +77,7 @@ struct Dev {      // everything the kernels need, passed by value
   uint64_t* mz_x;               // [read_off-indexed]
   uint32_t* mz_y;
   int32_t* mz_n;                // [NR]
+  uint64_t* mz_cnt;             // [NR][2] bucket counters of the read's minimizer hashes
   // phase A workspace
   int32_t* ws;                  // [n_threads][A_COUNT][cap] interleaved per warp
   int ws_cap;
@@ -295,18 +296,17 @@ __global__ void k_group_mid(Dev D, int min_mid) {
   D.grp_mid[g] = D.grp_hap_begin[g + 1] > h0 ? D.hap_mid[h0] : min_mid;
 }
 
-// one lane per read: sketch + mm_seed_mz_flt (q_occ_max = the group's mid_occ)
+// one lane per read: sketch.  Independent of the haplotype index, so it runs on a second stream
+// next to the haplotype kernels.  Alongside the minimizers it leaves 32 saturating 4-bit
+// counters of their hashes (bucket = low hash bits) for k_read_filter.
 __global__ void k_read_sketch(Dev D) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= D.n_reads) return;
   const int64_t off = D.read_off[r];
   const int len = (int)(D.read_off[r + 1] - off);
   int n = 0;
+  uint64_t cnt_lo = 0, cnt_hi = 0;
   if (len > 0) {
-    // 32 saturating 4-bit counters of the minimizer hashes (bucket = low hash bits): a minimizer
-    // can only repeat more than q_occ_max times if its bucket does, so the O(n^2) filter is
-    // skipped for the (vast majority of) reads where no bucket gets that full
-    uint64_t cnt_lo = 0, cnt_hi = 0;
     uint64_t* mzx = D.mz_x + off;
     uint32_t* mzy = D.mz_y + off;
     auto emit = [&](uint64_t x, uint32_t y) {
@@ -319,18 +319,30 @@ __global__ void k_read_sketch(Dev D) {
     if (D.P.w == 5) sketch_sr<5>(D.read_codes + off, len, D.P.k, emit);
     else n = sketch(D.read_codes + off, len, D.P.w, D.P.k, mzx, mzy, len), cnt_lo = cnt_hi = ~0ULL;
     if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
-    const int q_occ_max = D.grp_mid[D.read_grp[r]];
-    bool may_repeat = q_occ_max < 15;
-    if (may_repeat) {
-      may_repeat = false;
-      for (int b = 0; b < 16; ++b)
-        may_repeat |= (int)((cnt_lo >> (4 * b)) & 15) > q_occ_max || (int)((cnt_hi >> (4 * b)) & 15) > q_occ_max;
-    } else {
-      may_repeat = true;  // counters saturate at 15: cannot rule anything out
-    }
-    if (D.P.q_occ_frac > 0.0f && may_repeat) n = seed_mz_flt(mzx, mzy, n, q_occ_max, D.P.q_occ_frac);
   }
   D.mz_n[r] = n;
+  D.mz_cnt[2 * (size_t)r] = cnt_lo, D.mz_cnt[2 * (size_t)r + 1] = cnt_hi;
+}
+
+// one lane per read: mm_seed_mz_flt (q_occ_max = the group's mid_occ, known once the haplotype
+// tables exist).  A minimizer can only repeat more than q_occ_max times if its bucket counter
+// does, so the O(n^2) filter only runs for the few reads where some bucket got that full.
+__global__ void k_read_filter(Dev D) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= D.n_reads || D.P.q_occ_frac <= 0.0f) return;
+  const int n = D.mz_n[r];
+  const int q_occ_max = D.grp_mid[D.read_grp[r]];
+  if (n <= q_occ_max) return;
+  const uint64_t cnt_lo = D.mz_cnt[2 * (size_t)r], cnt_hi = D.mz_cnt[2 * (size_t)r + 1];
+  bool may_repeat = true;  // counters saturate at 15: above that nothing can be ruled out
+  if (q_occ_max < 15) {
+    may_repeat = false;
+    for (int b = 0; b < 16; ++b)
+      may_repeat |= (int)((cnt_lo >> (4 * b)) & 15) > q_occ_max || (int)((cnt_hi >> (4 * b)) & 15) > q_occ_max;
+  }
+  if (!may_repeat) return;
+  const int64_t off = D.read_off[r];
+  D.mz_n[r] = seed_mz_flt(D.mz_x + off, D.mz_y + off, n, q_occ_max, D.P.q_occ_frac);
 }
 
 __device__ __forceinline__ void write_invalid(AlnOut* o) {
@@ -1298,7 +1310,7 @@ __device__ __forceinline__ bool warp_ext_exact(const DevParams& P, const ReadVie
   return true;
 }
 
-constexpr int kWarpItemReads = 16;  // reads per warp work item (all against one haplotype)
+constexpr int kWarpItemReads = 4;  // reads per warp work item (all against one haplotype)
 
 // Phase A kernel: seeds → anchors → chain DP → regs, one warp per pair.  Every pair with at least
 // one reg is parked: its RegRecs go to the arena and its PairReg slot tells k_finish_warp where.
@@ -1530,7 +1542,8 @@ struct DevBuf {
 
 struct lgr_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   lgr_params prm;
   DevParams P;
   std::string err;
@@ -1541,7 +1554,7 @@ struct lgr_ctx {
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_ws, b_fin, b_regs,
       b_pair_reg, b_tasks, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
-      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt;
+      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt;
   Dev D;
   bool resident = false;
   int max_read_len = 0, max_hap_len = 0;
@@ -1678,6 +1691,9 @@ int lgr_create(int device_ordinal, const lgr_params* params, lgr_ctx** out) {
   cudaGetDeviceProperties(&prop, device_ordinal);
   c->sm_count = prop.multiProcessorCount;
   for (auto& e : c->ev) cudaEventCreate(&e);
+  cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   DevParams& d = c->P;
   std::memset(&d, 0, sizeof(d));
   d.k = p.k, d.w = p.w, d.a = p.a, d.b = p.b, d.q = p.q, d.e = p.e, d.sc_ambi = p.sc_ambi, d.bw = p.bw;
@@ -1701,10 +1717,13 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
                     &c->b_mz_n, &c->b_ws, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
-                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt};
+                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& e : c->ev) cudaEventDestroy(e);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1822,7 +1841,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   if ((rc = ensure(c, c->b_hap_codes, hap_bytes)) || (rc = ensure(c, c->b_read_codes, read_bytes)) ||
       (rc = ensure(c, c->b_idx, sizeof(uint64_t) * hap_bytes)) || (rc = ensure(c, c->b_idx_n, sizeof(int32_t) * NH)) ||
       (rc = ensure(c, c->b_hap_mid, sizeof(int32_t) * NH)) || (rc = ensure(c, c->b_bkt, sizeof(uint16_t) * (size_t)NH * (kBuckets + 1))) || (rc = ensure(c, c->b_mz_x, sizeof(uint64_t) * read_bytes)) ||
-      (rc = ensure(c, c->b_mz_y, sizeof(uint32_t) * read_bytes)) || (rc = ensure(c, c->b_mz_n, sizeof(int32_t) * NR)))
+      (rc = ensure(c, c->b_mz_y, sizeof(uint32_t) * read_bytes)) || (rc = ensure(c, c->b_mz_n, sizeof(int32_t) * NR)) || (rc = ensure(c, c->b_mz_cnt, sizeof(uint64_t) * 2 * (size_t)NR)))
     return rc;
   c->map_blocks = c->sm_count * 4;
   const int64_t n_threads = (int64_t)c->map_blocks * 128;
@@ -1895,6 +1914,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.bkt = (uint16_t*)c->b_bkt.p;
   D.bkt_shift = 2 * c->prm.k > kBucketBits ? 2 * c->prm.k - kBucketBits : 0;
   D.mz_x = (uint64_t*)c->b_mz_x.p, D.mz_y = (uint32_t*)c->b_mz_y.p, D.mz_n = (int32_t*)c->b_mz_n.p;
+  D.mz_cnt = (uint64_t*)c->b_mz_cnt.p;
   D.ws = nullptr, D.ws_cap = 0;
   D.wreg_scratch = (RegRec*)c->b_wreg.p, D.rsx_scratch = (RadixScratch*)c->b_rsx.p;
   D.fin_scratch = (uint32_t*)c->b_fin.p, D.fin_cap = fin_cap;
@@ -1928,15 +1948,23 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
   const int64_t hb = c->hap_bytes, rb = c->read_bytes;
   if (D.n_pairs > 0) {
     const int enc_blocks = c->sm_count * 8;
+    // read side (encode + sketch) on the second stream, haplotype side (encode, sketch, sort,
+    // mid_occ) on the main one; they join before the minimizer filter
+    cudaStream_t s2 = c->stream2;
+    cudaEventRecord(c->ev_fork, s);
+    cudaStreamWaitEvent(s2, c->ev_fork, 0);
+    k_encode<<<enc_blocks, 256, 0, s2>>>(D.read_bases, D.read_codes, rb);
+    k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s2>>>(D);
+    cudaEventRecord(c->ev_join, s2);
     k_encode<<<enc_blocks, 256, 0, s>>>(D.hap_bases, D.hap_codes, hb);
-    k_encode<<<enc_blocks, 256, 0, s>>>(D.read_bases, D.read_codes, rb);
     if (D.P.w == 5 && (D.P.k & 1)) k_hap_sketch_warp<<<(D.n_haps + 3) / 4, 128, 0, s>>>(D);
     else k_hap_sketch<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D);
     k_hap_sort<<<D.n_haps, 128, 2048 * sizeof(uint64_t), s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
     k_group_mid<<<(D.n_groups + 127) / 128, 128, 0, s>>>(D, c->prm.min_mid_occ);
-    launches += 5;
+    cudaStreamWaitEvent(s, c->ev_join, 0);
+    launches += 6;
     cudaEventRecord(c->ev[1], s);
-    k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
+    k_read_filter<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
     launches += 1;
     cudaEventRecord(c->ev[2], s);
     if (c->warp_cap == 64) k_chain_warp<64><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
