@@ -39,7 +39,7 @@ __constant__ double c_phred_err[256] = {
 
 // counters (int64 slots in device memory)
 enum Ctr {
-  C_ITEM = 0, C_UNUSED0, C_UNUSED1, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ITEM = 0, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
   C_ALIGNED, C_TASKPOS, C_OVFPOS, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
@@ -79,9 +79,9 @@ struct Dev {      // everything the kernels need, passed by value
   int32_t* mz_n;                // [NR]
   uint64_t* mz_cnt;             // [NR][2] bucket counters of the read's minimizer hashes
   // phase A workspace
-  int32_t* ws;                  // [n_threads][A_COUNT][cap] interleaved per warp
+  int32_t* ws;                  // k_chain_overflow: [warps][A_COUNT][cap][32 lanes] workspace
   int ws_cap;
-  uint32_t* fin_scratch;        // [n_threads][2][fin_cap]
+  uint32_t* fin_scratch;        // [warps][2][fin_cap] cigar staging of k_finish_warp
   int fin_cap;
   // parked pairs / tails
   RegRec* regs;  int64_t regs_cap;
@@ -1552,14 +1552,14 @@ struct lgr_ctx {
   std::vector<DevBuf*> all;
   DevBuf b_grp_hap, b_grp_read, b_grp_var, b_hap_off, b_read_off, b_var_hap_off, b_hap_bases, b_read_bases, b_read_quals,
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
-      b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_ws, b_fin, b_regs,
-      b_pair_reg, b_tasks, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
+      b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
+      b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
       b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt;
   Dev D;
   bool resident = false;
   int max_read_len = 0, max_hap_len = 0;
   int64_t hap_bytes = 0, read_bytes = 0;
-  int map_blocks = 0, ext_blocks = 0, warp_blocks = 0, warp_cap = 64;
+  int ext_blocks = 0, warp_blocks = 0, warp_cap = 64;
   size_t warp_smem = 0;
   cudaEvent_t ev[12];
   // host staging of helper arrays
@@ -1715,7 +1715,7 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_read_bases, &c->b_read_quals, &c->b_name_hash, &c->b_var_start, &c->b_var_len, &c->b_var_allele,
                     &c->b_read_grp, &c->b_hap_grp, &c->b_pair_off, &c->b_asg_off, &c->b_item_hap, &c->b_item_r0, &c->b_item_n,
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
-                    &c->b_mz_n, &c->b_ws, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
+                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
                     &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt};
   for (DevBuf* b : bufs)
@@ -1843,8 +1843,6 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       (rc = ensure(c, c->b_hap_mid, sizeof(int32_t) * NH)) || (rc = ensure(c, c->b_bkt, sizeof(uint16_t) * (size_t)NH * (kBuckets + 1))) || (rc = ensure(c, c->b_mz_x, sizeof(uint64_t) * read_bytes)) ||
       (rc = ensure(c, c->b_mz_y, sizeof(uint32_t) * read_bytes)) || (rc = ensure(c, c->b_mz_n, sizeof(int32_t) * NR)) || (rc = ensure(c, c->b_mz_cnt, sizeof(uint64_t) * 2 * (size_t)NR)))
     return rc;
-  c->map_blocks = c->sm_count * 4;
-  const int64_t n_threads = (int64_t)c->map_blocks * 128;
   const int fin_cap = 2 * c->max_read_len + 16;
   const int Lm = std::max(c->max_read_len, 1);
   const int Tmax = Lm + ((c->prm.a + std::max(c->prm.b, c->prm.sc_ambi)) * Lm) / c->prm.e + 2;
@@ -1881,7 +1879,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
   if ((rc = ensure(c, c->b_wreg, sizeof(RegRec) * (size_t)ext_warps * c->warp_cap)) ||
       (rc = ensure(c, c->b_rsx, sizeof(RadixScratch) * (size_t)ext_warps)) ||
-      (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)n_threads * 2 * fin_cap)) ||
+      (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap)) ||
       (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_pair_reg, sizeof(PairReg) * (size_t)n_pairs)) ||
       (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
       (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
