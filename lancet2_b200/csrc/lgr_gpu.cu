@@ -39,13 +39,17 @@ __constant__ double c_phred_err[256] = {
 
 // counters (int64 slots in device memory)
 enum Ctr {
-  C_ITEM = 0, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
-  C_ALIGNED, C_TASKPOS, C_OVFPOS, C_COUNT
+  C_ITEM = 0, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
 constexpr int kBucketBits = 9;
 constexpr int kBuckets = 1 << kBucketBits;
+
+struct TaskRec {  // one extension that needs the wavefront DP
+  int32_t reg, side, read, hap;
+};
 
 struct PairReg {  // per pair: its parked RegRecs in the arena (n == 0: nothing to finish)
   int32_t first, n, read, hap;
@@ -86,6 +90,7 @@ struct Dev {      // everything the kernels need, passed by value
   // parked pairs / tails
   RegRec* regs;  int64_t regs_cap;
   PairReg* pair_reg;             // [n_pairs]
+  TaskRec* tasks; int64_t tasks_cap;
   uint32_t* ext_arena; int64_t ext_arena_cap;
   int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
   // k_ext_big scratch
@@ -415,7 +420,16 @@ __global__ void __launch_bounds__(128) k_chain_overflow(Dev D) {
           write_invalid(&D.aln[pair]);
         } else {
           pr = PairReg{(int32_t)first, n_regs, r, h};
-          for (int i = 0; i < n_regs; ++i) export_reg<32>(ws, i, qlen, &D.regs[first + i]);
+          for (int i = 0; i < n_regs; ++i) {
+            RegRec* rg = &D.regs[first + i];
+            export_reg<32>(ws, i, qlen, rg);
+            for (int side = 0; side < 2; ++side) {
+              if (rg->ext[side].m <= 0) continue;
+              const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
+              if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
+              else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+            }
+          }
         }
       }
       D.pair_reg[pair] = pr;
@@ -1365,6 +1379,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
           n_regs = __shfl_sync(full, n_regs, 0);
         }
       }
+      long long first = -1;
       if (lane == 0) {
         if (st == kMapOverflow) {
           const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
@@ -1374,14 +1389,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
           write_invalid(&D.aln[pair]);
           D.pair_reg[pair] = PairReg{0, 0, r, h};
         } else {
-          const long long first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
+          first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
           if (first + n_regs > D.regs_cap) {
             atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
             write_invalid(&D.aln[pair]);
             D.pair_reg[pair] = PairReg{0, 0, r, h};
+            first = -1;
           } else {
             D.pair_reg[pair] = PairReg{(int32_t)first, n_regs, r, h};
             for (int i = 0; i < n_regs; ++i) export_reg<1>(ws, i, qlen, &D.regs[first + i]);
+          }
+        }
+      }
+      first = __shfl_sync(full, first, 0);
+      __syncwarp();
+      if (first >= 0) {
+        // extensions: closed forms here (warp-parallel compare), everything else → wavefront queue
+        for (int i = 0; i < n_regs; ++i) {
+          RegRec* rg = &D.regs[first + i];
+          for (int side = 0; side < 2; ++side) {
+            if (rg->ext[side].m <= 0) continue;
+            if (warp_ext_exact(D.P, rv, hapc, rg, side, &ctr.dp_cells_full)) continue;
+            if (lane == 0) {
+              const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
+              if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
+              else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+            }
           }
         }
       }
@@ -1391,32 +1424,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
     atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
   }
 }
 
-// scalar short extension on lane 0 (kept out of line: it is the cold side of k_finish_warp)
-__device__ __noinline__ bool ext_small_lane0(const Dev& D, const ReadView& rv, const uint8_t* hapc, RegRec* reg, int side,
-                                            ChainCounters* ctr) {
-  uint8_t sdir[kSmallCells];
-  int32_t ha[kSmallDim + 2], fa[kSmallDim + 2];
-  uint32_t cig_tmp[kSmallCig];
-  auto alloc_ext = [&](int n) -> int64_t {
-    const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)n);
-    if (o + n > D.ext_arena_cap) {
-      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
-      return -1;
-    }
-    return o;
-  };
-  return run_ext_scalar(D.P, rv, hapc, reg, side, sdir, ha, fa, cig_tmp, kSmallCig, D.ext_arena, alloc_ext, ctr);
-}
-
-// Phase B kernel: one warp per parked pair: pending extensions (exact-match shortcut, scalar short
-// tails, warp wavefront for the rest), then the warp-parallel finish, then the final record.
-constexpr int kTinyCells = 24;         // extensions up to this many cells run scalar on lane 0
+// Phase B1 kernel: the extensions no closed form covered, one warp per queued extension, through
+// the anti-diagonal wavefront.  Nothing but DP code lives here, so resident warps share one hot loop.
 constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
 
-__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D) {
+__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_ext_warp(Dev D) {
   __shared__ uint8_t s_dir[4 * kDirSmemPerWarp];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -1425,17 +1441,43 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D) {
   int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
   int32_t* Fb = Hb + D.bnd_per_warp / 2;
   uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
+  long long cells = 0, cells_full = 0;
+  long long n_task = D.ctr[C_NTASK];
+  if (n_task > D.tasks_cap) n_task = D.tasks_cap;
+  for (;;) {
+    long long t = 0;
+    if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
+    t = __shfl_sync(full, t, 0);
+    if (t >= n_task) break;
+    const TaskRec tk = D.tasks[t];
+    const uint8_t* hapc = D.hap_codes + D.hap_off[tk.hap];
+    const int64_t roff = D.read_off[tk.read];
+    ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
+    long long c1 = 0, c2 = 0;
+    ext_dp_warp(D, &D.regs[tk.reg], tk.side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig,
+                &c1, &c2);
+    cells += c1, cells_full += c2;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)cells);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)cells_full);
+  }
+}
+
+// Phase B2 kernel: one warp per parked pair, every extension already done: the warp-parallel
+// finish (assemble, fix, extra, filter, sort) and the final record.
+__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
-  ChainCounters ctr{0, 0, 0, 0};
   long long n_aligned = 0;
-  // parked pairs are taken one at a time (pair order): extension work per pair varies by orders
-  // of magnitude, so the finest granularity balances best
   for (;;) {
     long long pair = 0;
-    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
+    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[C_FINPOS], 1ULL);
     pair = __shfl_sync(full, pair, 0);
     if (pair >= D.n_pairs) break;
-   {
     const PairReg d = D.pair_reg[pair];
     if (d.n <= 0) continue;
     const int read = d.read;
@@ -1443,26 +1485,9 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D) {
     const int64_t roff = D.read_off[read];
     ReadView rv{D.read_codes + roff, (int)(D.read_off[read + 1] - roff)};
     RegRec* regs = D.regs + d.first;
-    int okw = 1;
-    for (int i = 0; i < d.n; ++i) {
-      for (int side = 0; side < 2; ++side) {
-        const int m = regs[i].ext[side].m;
-        if (m <= 0 || regs[i].ext[side].mqe_t >= 0) continue;  // none, or already computed
-        if (warp_ext_exact(D.P, rv, hapc, &regs[i], side, &ctr.dp_cells_full)) continue;
-        if ((int64_t)m * prune_cols(D.P, m, regs[i].ext[side].n) <= kTinyCells) {  // a handful of cells: not worth a wavefront
-          if (lane == 0 && !ext_small_lane0(D, rv, hapc, &regs[i], side, &ctr)) okw = 0;
-        } else {
-          long long c1 = 0, c2 = 0;
-          ext_dp_warp(D, &regs[i], side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig, &c1, &c2);
-          ctr.dp_cells += c1, ctr.dp_cells_full += c2;
-        }
-        __syncwarp();
-      }
-    }
-    okw = __shfl_sync(full, okw, 0);
     FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
     AlnOut ao;
-    const int nc = okw ? finish_pair_warp(D, rv, hapc, regs, d.n, fs, &ao) : -1;
+    const int nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, &ao);
     if (lane == 0) {
       if (nc < 0) {
         atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
@@ -1473,13 +1498,8 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D) {
       }
     }
     __syncwarp();
-   }
   }
-  if (lane == 0) {
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)ctr.dp_cells);
-    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
-    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
-  }
+  if (lane == 0) atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED], (unsigned long long)n_aligned);
 }
 
 // one lane per (read, variant): AssignReadToAlleles' inner loops (genotyper.cpp:294-318)
@@ -1554,12 +1574,12 @@ struct lgr_ctx {
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
       b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
-      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt;
+      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks;
   Dev D;
   bool resident = false;
   int max_read_len = 0, max_hap_len = 0;
   int64_t hap_bytes = 0, read_bytes = 0;
-  int ext_blocks = 0, warp_blocks = 0, warp_cap = 64;
+  int ext_blocks = 0, fin_blocks = 0, warp_blocks = 0, warp_cap = 64;
   size_t warp_smem = 0;
   cudaEvent_t ev[12];
   // host staging of helper arrays
@@ -1715,7 +1735,7 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_read_bases, &c->b_read_quals, &c->b_name_hash, &c->b_var_start, &c->b_var_len, &c->b_var_allele,
                     &c->b_read_grp, &c->b_hap_grp, &c->b_pair_off, &c->b_asg_off, &c->b_item_hap, &c->b_item_r0, &c->b_item_n,
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
-                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_ext_arena, &c->b_ovf_read,
+                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
                     &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt};
   for (DevBuf* b : bufs)
@@ -1867,10 +1887,12 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   }
   {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     c->ext_blocks = c->sm_count * per_sm;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    c->fin_blocks = c->sm_count * per_sm;
   }
-  const int64_t ext_warps = std::max<int64_t>((int64_t)c->ext_blocks * 4, (int64_t)c->warp_blocks * kWarpsPerCta);
+  const int64_t ext_warps = std::max<int64_t>((int64_t)std::max(c->ext_blocks, c->fin_blocks) * 4, (int64_t)c->warp_blocks * kWarpsPerCta);
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
   const int wcig_cap = 2 * Lm + 8;
@@ -1881,6 +1903,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       (rc = ensure(c, c->b_rsx, sizeof(RadixScratch) * (size_t)ext_warps)) ||
       (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap)) ||
       (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_pair_reg, sizeof(PairReg) * (size_t)n_pairs)) ||
+      (rc = ensure(c, c->b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2)) ||
       (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
       (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
       (rc = ensure(c, c->b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
@@ -1918,6 +1941,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.fin_scratch = (uint32_t*)c->b_fin.p, D.fin_cap = fin_cap;
   D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
   D.pair_reg = (PairReg*)c->b_pair_reg.p;
+  D.tasks = (TaskRec*)c->b_tasks.p, D.tasks_cap = regs_cap * 2;
   D.ext_arena = (uint32_t*)c->b_ext_arena.p, D.ext_arena_cap = ext_arena_cap;
   D.ovf_read = (int32_t*)c->b_ovf_read.p, D.ovf_hap = (int32_t*)c->b_ovf_hap.p, D.ovf_cap = n_pairs;
   D.dir_scratch = (uint8_t*)c->b_dir.p, D.dir_per_warp = dir_per_warp;
@@ -1977,8 +2001,9 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
       k_chain_overflow<<<kBigWarps / 4, 128, 0, s>>>(D2);
       launches += 1;
     }
-    k_finish_warp<<<c->ext_blocks, 128, 0, s>>>(D);
-    launches += 1;
+    k_ext_warp<<<c->ext_blocks, 128, 0, s>>>(D);
+    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D);
+    launches += 2;
     cudaEventRecord(c->ev[3], s);
     if (D.n_assign > 0) {
       k_assign<<<(unsigned)((D.n_assign + 127) / 128), 128, 0, s>>>(D);
