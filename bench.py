@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-contexts", type=int, default=2)
+    ap.add_argument("--e2e-inflight", type=int, default=3)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,37 +242,36 @@ def main():
         _, e2e_st = gpu.genotype_batch(batch, result=res, want_aln=False)
     barrier()
     e2e_single_s = time.perf_counter() - t0
-    # E2E_CTX contexts in flight (what a multi-threaded caller does: the reference runs one
-    # Genotyper per worker thread): every step is still a full lgr_genotype_batch with its own
-    # H2D and D2H; the copies of one context overlap the kernels of the other
-    n_ctx = max(1, args.e2e_contexts)
+    # pipelined: the same per-step call through lgr_submit/lgr_wait with a few batches in flight on
+    # ONE context and ONE host thread: every step still carries its own H2D and D2H, but the
+    # copies of one step overlap the kernels of the previous one
+    depth = max(1, min(args.e2e_inflight, abi.LGR_MAX_INFLIGHT))
     e2e_s = e2e_single_s
-    if n_ctx > 1:
-        ctxs = [gpu] + [GpuRealigner(local_rank) for _ in range(n_ctx - 1)]
+    if depth > 1:
         ress = [res]
-        for _ in range(n_ctx - 1):
+        for _ in range(depth - 1):
             r2 = abi.Result(batch, 1 << 20)
             pin_result(r2, torch)
             ress.append(r2)
-        for c, r in zip(ctxs, ress):
-            c.genotype_batch(batch, result=r, want_aln=False)
-        per = [args.steps // n_ctx + (1 if i < args.steps % n_ctx else 0) for i in range(n_ctx)]
 
-        def work(i):
-            for _ in range(per[i]):
-                ctxs[i].genotype_batch(batch, result=ress[i], want_aln=False)
+        def pipeline(n_steps):
+            open_t = []
+            stl = None
+            for i in range(n_steps):
+                if len(open_t) == depth:
+                    stl = gpu.wait(open_t.pop(0))
+                t, _ = gpu.submit(batch, result=ress[i % depth], want_aln=False)
+                open_t.append(t)
+            for t in open_t:
+                stl = gpu.wait(t)
+            return stl
 
+        pipeline(2 * depth)
         barrier()
         t0 = time.perf_counter()
-        ths = [threading.Thread(target=work, args=(i,)) for i in range(n_ctx)]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
+        e2e_st = pipeline(args.steps)
         barrier()
         e2e_s = time.perf_counter() - t0
-        for c in ctxs[1:]:
-            c.close()
     clocks = sampler.stop()
 
     # max over ranks
@@ -307,13 +306,13 @@ def main():
                        "reads": batch.n_reads, "haplotypes": batch.n_haps, "variants": batch.n_vars,
                        "l2": "flushed between timed steps (512 MiB write, untimed)", "timing": "CUDA events on the library stream"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(e2e_st.h2d_bytes), "d2h_bytes_per_step": int(e2e_st.d2h_bytes),
-                    "contexts_in_flight": max(1, args.e2e_contexts),
-                    "single_context_value": total_pairs * args.steps / e2e_single_s,
+                    "batches_in_flight": depth,
+                    "synchronous_value": total_pairs * args.steps / e2e_single_s,
                     "ms_h2d": e2e_st.ms_h2d, "ms_kernels": e2e_st.ms_kernels, "ms_d2h": e2e_st.ms_d2h,
-                    "note": "every step is one lgr_genotype_batch call from pinned host buffers (H2D + kernels + D2H); with 2 contexts the copies of one call overlap the kernels of the other"},
+                    "note": "every step is one lgr_submit+lgr_wait of the whole batch from pinned host buffers (H2D + kernels + D2H per step, one host thread); batches_in_flight steps are outstanding so copies overlap kernels; synchronous_value is the same through lgr_genotype_batch, one call at a time"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_map", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "k_chain_warp", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": map_ms,
                          "note": "path is integer-issue bound, not HBM bound; see DESIGN.md §roofline"},

@@ -49,10 +49,12 @@ extern "C" {
 #define LGR_E_LIMIT (-4)          /* a sequence exceeds a compile-time cap  */
 #define LGR_E_CIGAR_OVERFLOW (-5) /* cigar overflow arena exhausted         */
 #define LGR_E_NOMEM (-6)
+#define LGR_E_BUSY (-7)           /* all LGR_MAX_INFLIGHT submission slots in use */
 
 /* compile-time caps of the device path (checked, never silently truncated) */
 #define LGR_MAX_READ_LEN 1024
 #define LGR_MAX_HAP_LEN 65535
+#define LGR_MAX_INFLIGHT 4         /* lgr_submit tickets outstanding per ctx */
 #define LGR_CIGAR_INLINE 8 /* u32 cigar ops stored inline per pair */
 
 /*
@@ -215,6 +217,19 @@ int lgr_hap_mid_occ(lgr_ctx* ctx, const uint8_t* hap, int32_t hap_len, int32_t* 
 
 /* Synchronous: H2D of the batch, all kernels, D2H of the results. */
 int lgr_genotype_batch(lgr_ctx* ctx, const lgr_batch_in* in, lgr_batch_out* out, lgr_stats* stats);
+
+/* Asynchronous form of lgr_genotype_batch ("one lgr_ctx + >=2 streams +
+ * double-buffered staging per GPU; results return via ticket").  lgr_submit enqueues H2D,
+ * kernels and D2H of one batch on a private slot (own streams and device buffers) and returns
+ * at once; up to LGR_MAX_INFLIGHT batches may be outstanding, so the copies of one batch
+ * overlap the kernels of another.  `in`/`out` buffers must stay valid (and should be pinned
+ * for real overlap) until lgr_wait(ticket) returns; lgr_wait reports the batch's status and
+ * statistics exactly as lgr_genotype_batch would.  Tickets may be waited in any order.
+ * Replaces the synchronous per-window call at core/variant_builder.cpp:258-259 for a host that
+ * pipelines windows. */
+typedef int32_t lgr_ticket;
+int lgr_submit(lgr_ctx* ctx, const lgr_batch_in* in, lgr_batch_out* out, lgr_ticket* ticket);
+int lgr_wait(lgr_ctx* ctx, lgr_ticket ticket, lgr_stats* stats);
 
 /* Device-resident variant for kernel-only timing: upload once, run many times,
  * download when wanted.  `lgr_upload` keeps a device copy of `in` inside ctx. */

@@ -16,6 +16,7 @@ import numpy as np
 LGR_CIGAR_INLINE = 8
 LGR_MAX_READ_LEN = 1024
 LGR_MAX_HAP_LEN = 65535
+LGR_MAX_INFLIGHT = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblancet_gpu_realign.so")
@@ -239,7 +240,7 @@ class Result:
 _SYMBOLS = [
     "lgr_abi_version", "lgr_default_params", "lgr_strerror", "lgr_last_error", "lgr_x31_hash",
     "lgr_pair_offsets", "lgr_create", "lgr_destroy", "lgr_hap_mid_occ", "lgr_genotype_batch",
-    "lgr_upload", "lgr_run_resident", "lgr_download", "lgr_stream",
+    "lgr_upload", "lgr_run_resident", "lgr_download", "lgr_stream", "lgr_submit", "lgr_wait",
 ]
 
 
@@ -280,6 +281,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.lgr_run_resident.restype = C.c_int
     lib.lgr_download.argtypes = [C.c_void_p, C.POINTER(LgrBatchOut)]
     lib.lgr_download.restype = C.c_int
+    lib.lgr_submit.argtypes = [C.c_void_p, C.POINTER(LgrBatchIn), C.POINTER(LgrBatchOut), C.POINTER(C.c_int32)]
+    lib.lgr_submit.restype = C.c_int
+    lib.lgr_wait.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LgrStats)]
+    lib.lgr_wait.restype = C.c_int
     lib.lgr_stream.argtypes = [C.c_void_p]
     lib.lgr_stream.restype = C.c_void_p
     return lib

@@ -83,6 +83,19 @@ LGR_HD uint64_t hash64_mask(uint64_t key, uint64_t mask) {
   key = (key + (key << 31)) & mask;
   return key;
 }
+// the same function in 32-bit arithmetic, exact whenever the mask has at most 32 bits (k <= 16):
+// adds and left shifts commute with reduction mod 2^32 and every right shift acts on a value
+// already reduced by the mask
+LGR_HD uint32_t hash64_mask_narrow(uint32_t key, uint32_t mask) {
+  key = (~key + (key << 21)) & mask;
+  key = key ^ key >> 24;
+  key = ((key + (key << 3)) + (key << 8)) & mask;
+  key = key ^ key >> 14;
+  key = ((key + (key << 2)) + (key << 4)) & mask;
+  key = key ^ key >> 28;
+  key = (key + (key << 31)) & mask;
+  return key;
+}
 LGR_HD uint64_t hash64_full(uint64_t key) {
   key = ~key + (key << 21);
   key = key ^ key >> 24;
@@ -186,39 +199,40 @@ LGR_HD int sketch(const uint8_t* codes, int len, int w, int k, OutX out_x, OutY 
 // one base (ix = UINT64_MAX when the base has no valid k-mer; l = number of consecutive
 // unambiguous bases ending here, 0 for an ambiguous base) — shared by the sequential sketch
 // below and by the warp kernel that computes the records 32 at a time.
-template <int W>
+template <int W, typename XT = uint64_t>
 struct MinimizerWindow {
-  uint64_t wx[W];
+  static constexpr XT kMax = (XT)~(XT)0;
+  XT wx[W];
   uint32_t wy[W];
-  uint64_t min_x;
+  XT min_x;
   uint32_t min_y;
   int min_idx, k;
   LGR_HD void init(int k_) {
 #pragma unroll
-    for (int j = 0; j < W; ++j) wx[j] = UINT64_MAX, wy[j] = UINT32_MAX;
-    min_x = UINT64_MAX, min_y = UINT32_MAX, min_idx = W - 1, k = k_;
+    for (int j = 0; j < W; ++j) wx[j] = kMax, wy[j] = UINT32_MAX;
+    min_x = kMax, min_y = UINT32_MAX, min_idx = W - 1, k = k_;
   }
   template <typename Emit>
-  LGR_HD void step(uint64_t ix, uint32_t iy, int l, Emit& emit) {
+  LGR_HD void step(XT ix, uint32_t iy, int l, Emit& emit) {
 #pragma unroll
     for (int j = 0; j + 1 < W; ++j) wx[j] = wx[j + 1], wy[j] = wy[j + 1];
     wx[W - 1] = ix, wy[W - 1] = iy;
     --min_idx;
-    if (l == W + k - 1 && min_x != UINT64_MAX) {
+    if (l == W + k - 1 && min_x != kMax) {
 #pragma unroll
       for (int j = 0; j + 1 < W; ++j)
         if (min_x == wx[j] && wy[j] != min_y) emit(wx[j], wy[j]);
     }
     if (ix <= min_x) {
-      if (l >= W + k && min_x != UINT64_MAX) emit(min_x, min_y);
+      if (l >= W + k && min_x != kMax) emit(min_x, min_y);
       min_x = ix, min_y = iy, min_idx = W - 1;
     } else if (min_idx < 0) {
-      if (l >= W + k - 1 && min_x != UINT64_MAX) emit(min_x, min_y);
-      min_x = UINT64_MAX;
+      if (l >= W + k - 1 && min_x != kMax) emit(min_x, min_y);
+      min_x = kMax;
 #pragma unroll
       for (int j = 0; j < W; ++j)
         if (min_x >= wx[j]) min_x = wx[j], min_y = wy[j], min_idx = j;
-      if (l >= W + k - 1 && min_x != UINT64_MAX) {
+      if (l >= W + k - 1 && min_x != kMax) {
 #pragma unroll
         for (int j = 0; j < W; ++j)
           if (min_x == wx[j] && min_y != wy[j]) emit(wx[j], wy[j]);
@@ -227,31 +241,36 @@ struct MinimizerWindow {
   }
   template <typename Emit>
   LGR_HD void finish(Emit& emit) {
-    if (min_x != UINT64_MAX) emit(min_x, min_y);
+    if (min_x != kMax) emit(min_x, min_y);
   }
 };
 
-template <int W, typename Emit>
-LGR_HD int sketch_sr(const uint8_t* codes, int len, int k, Emit emit) {
-  const uint64_t shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
-  uint64_t kmer0 = 0, kmer1 = 0;
-  MinimizerWindow<W> win;
+// XT = uint32_t is exact for 2k + 8 <= 32 (hash << 8 | span fits, and never equals the all-ones
+// "no k-mer" marker); Emit always receives the 64-bit record value.
+template <int W, typename XT, typename Emit>
+LGR_HD int sketch_sr_impl(const uint8_t* codes, int len, int k, Emit emit) {
+  const int shift1 = 2 * (k - 1);
+  const XT mask = (XT)(((uint64_t)1 << 2 * k) - 1);
+  XT kmer0 = 0, kmer1 = 0;
+  MinimizerWindow<W, XT> win;
   win.init(k);
   int l = 0, kmer_span = 0, n = 0;
-  auto count_emit = [&](uint64_t x, uint32_t y) { emit(x, y), ++n; };
+  auto count_emit = [&](XT x, uint32_t y) { emit((uint64_t)x, y), ++n; };
   for (int i = 0; i < len; ++i) {
     const int c = codes[i] & 0xf;
-    uint64_t ix = UINT64_MAX;
+    XT ix = MinimizerWindow<W, XT>::kMax;
     uint32_t iy = UINT32_MAX;
     if (c < 4) {
       kmer_span = l + 1 < k ? l + 1 : k;
-      kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
-      kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+      kmer0 = (kmer0 << 2 | (XT)c) & mask;
+      kmer1 = (kmer1 >> 2) | ((XT)3 ^ (XT)c) << shift1;
       if (kmer0 == kmer1) continue;
       const int z = kmer0 < kmer1 ? 0 : 1;
       ++l;
       if (l >= k && kmer_span < 256) {
-        ix = hash64_mask(z ? kmer1 : kmer0, mask) << 8 | (uint64_t)kmer_span;
+        const XT key = z ? kmer1 : kmer0;
+        const XT hv = sizeof(XT) == 4 ? (XT)hash64_mask_narrow((uint32_t)key, (uint32_t)mask) : (XT)hash64_mask((uint64_t)key, (uint64_t)mask);
+        ix = hv << 8 | (XT)kmer_span;
         iy = (uint32_t)i << 1 | (uint32_t)z;
       }
     } else {
@@ -262,6 +281,12 @@ LGR_HD int sketch_sr(const uint8_t* codes, int len, int k, Emit emit) {
   }
   win.finish(count_emit);
   return n;
+}
+
+template <int W, typename Emit>
+LGR_HD int sketch_sr(const uint8_t* codes, int len, int k, Emit emit) {
+  if (2 * k + 8 <= 32) return sketch_sr_impl<W, uint32_t>(codes, len, k, emit);
+  return sketch_sr_impl<W, uint64_t>(codes, len, k, emit);
 }
 
 // dispatcher: register-resident window for the reference's w = 5, ring buffer otherwise.

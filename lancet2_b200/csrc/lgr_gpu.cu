@@ -39,8 +39,8 @@ __constant__ double c_phred_err[256] = {
 
 // counters (int64 slots in device memory)
 enum Ctr {
-  C_ITEM = 0, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
-  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_COUNT
+  C_ITEM = 0, C_NTASK, C_NDP, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ALIGNED, C_TASKPOS, C_FINPOS, C_FINPOS2, C_OVFPOS, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
@@ -50,6 +50,8 @@ constexpr int kBuckets = 1 << kBucketBits;
 struct TaskRec {  // one extension that needs the wavefront DP
   int32_t reg, side, read, hap;
 };
+
+constexpr int32_t kPairHasTask = 1 << 30;  // PairReg::n flag: some extension waits for the wavefront kernel
 
 struct PairReg {  // per pair: its parked RegRecs in the arena (n == 0: nothing to finish)
   int32_t first, n, read, hap;
@@ -91,6 +93,7 @@ struct Dev {      // everything the kernels need, passed by value
   RegRec* regs;  int64_t regs_cap;
   PairReg* pair_reg;             // [n_pairs]
   TaskRec* tasks; int64_t tasks_cap;
+  int32_t* dp_pairs;             // [n_pairs] pairs with a queued extension (finished in the second pass)
   uint32_t* ext_arena; int64_t ext_arena_cap;
   int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
   // k_ext_big scratch
@@ -106,10 +109,23 @@ struct Dev {      // everything the kernels need, passed by value
 };
 
 // ---------------------------------------------------------------------------------------
+// both buffers come from cudaMalloc (256-byte aligned): 16 bases per lane and iteration
 __global__ void k_encode(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] = encode_base(src[i]);
+  const int64_t n16 = n >> 4;
+  for (int64_t v = tid; v < n16; v += stride) {
+    uint4 w = reinterpret_cast<const uint4*>(src)[v];
+    uint32_t* p = &w.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t x = p[j];
+      p[j] = (uint32_t)encode_base((uint8_t)x) | (uint32_t)encode_base((uint8_t)(x >> 8)) << 8 |
+             (uint32_t)encode_base((uint8_t)(x >> 16)) << 16 | (uint32_t)encode_base((uint8_t)(x >> 24)) << 24;
+    }
+    reinterpret_cast<uint4*>(dst)[v] = w;
+  }
+  for (int64_t i = (n16 << 4) + tid; i < n; i += stride) dst[i] = encode_base(src[i]);
 }
 
 // one lane per haplotype: sketch → table entries (hash<<17 | pos<<1|strand), unsorted
@@ -147,14 +163,19 @@ __global__ void k_hap_sketch(Dev D) {
   D.idx_n[h] = n;
 }
 
-// one WARP per haplotype (odd k, w == 5): the 32 lanes compute the k-mer records (hash, strand,
-// run length of unambiguous bases) of 32 consecutive positions in parallel, then lane 0 feeds
-// them through the window state machine (MinimizerWindow<5>, same code as the sequential
-// sketch) and writes the table entries in order.
+// one WARP per haplotype (odd k, w == 5), one LANE per position.  With odd k no k-mer is its own
+// reverse complement, so mm_sketch never skips an iteration and its window state before
+// position i is a pure function of the W records before i: the ring holds exactly those, and
+// `min` is their right-most minimum (a new record takes over on <=, the rescan keeps the last
+// of equals, otherwise nothing to the right of `min` can be <= it).  Every lane rebuilds that
+// state from its W predecessors, runs the one `MinimizerWindow::step` of its own position
+// (same code as the sequential sketch) and the warp concatenates the emissions in order.
+template <typename XT>
 __global__ void __launch_bounds__(128) k_hap_sketch_warp(Dev D) {
-  __shared__ uint64_t s_x[4][32];
-  __shared__ uint32_t s_y[4][32];
-  __shared__ int s_l[4][32];
+  constexpr XT kNone = MinimizerWindow<5, XT>::kMax;
+  constexpr int W = 5;
+  __shared__ XT s_x[4][32 + W];
+  __shared__ uint32_t s_y[4][32 + W];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -164,14 +185,11 @@ __global__ void __launch_bounds__(128) k_hap_sketch_warp(Dev D) {
   const uint8_t* codes = D.hap_codes + off;
   uint64_t* tab = D.idx + off;
   const int k = D.P.k;
-  const uint64_t mask = (1ULL << 2 * k) - 1;
-  MinimizerWindow<5> win;
-  win.init(k);
+  const XT mask = (XT)((1ULL << 2 * k) - 1);
+  XT* sx = s_x[warp];
+  uint32_t* sy = s_y[warp];
+  if (lane < W) sx[lane] = kNone, sy[lane] = UINT32_MAX;  // records "before" position 0
   int n = 0;
-  auto emit = [&](uint64_t x, uint32_t y) {
-    if (n < len) tab[n] = (x >> 8) << kIdxShift | (uint64_t)y;
-    ++n;
-  };
   int run_in = 0;  // unambiguous run length ending just before this chunk
   for (int base = 0; base < len; base += 32) {
     const int i = base + lane;
@@ -183,30 +201,62 @@ __global__ void __launch_bounds__(128) k_hap_sketch_warp(Dev D) {
       if (lane >= o && v > lastn) lastn = v;
     }
     const int l = lastn >= 0 ? i - lastn : run_in + lane + 1;
-    uint64_t ix = UINT64_MAX;
+    XT ix = kNone;
     uint32_t iy = UINT32_MAX;
     if (i < len && l >= k) {
-      uint64_t k0 = 0, k1 = 0;
+      XT k0 = 0, k1 = 0;
       for (int t = 0; t < k; ++t) {
-        const uint64_t b = codes[i - k + 1 + t] & 0xf;
+        const XT b = (XT)(codes[i - k + 1 + t] & 0xf);
         k0 = k0 << 2 | b;
-        k1 = k1 >> 2 | (3ULL ^ b) << 2 * (k - 1);
+        k1 = k1 >> 2 | ((XT)3 ^ b) << 2 * (k - 1);
       }
       const int z = k0 < k1 ? 0 : 1;
-      ix = hash64_mask(z ? k1 : k0, mask) << 8 | (uint64_t)k;
+      const XT key = z ? k1 : k0;
+      const XT hv = sizeof(XT) == 4 ? (XT)hash64_mask_narrow((uint32_t)key, (uint32_t)mask) : (XT)hash64_mask((uint64_t)key, (uint64_t)mask);
+      ix = hv << 8 | (XT)k;
       iy = (uint32_t)i << 1 | (uint32_t)z;
     }
-    s_x[warp][lane] = ix, s_y[warp][lane] = iy, s_l[warp][lane] = i < len ? l : 0;
+    __syncwarp();
+    sx[W + lane] = ix, sy[W + lane] = iy;
     run_in = __shfl_sync(full, l, 31);
     __syncwarp();
-    if (lane == 0) {
-      const int cnt = len - base < 32 ? len - base : 32;
-      for (int t = 0; t < cnt; ++t) win.step(s_x[warp][t], s_y[warp][t], s_l[warp][t], emit);
+    // the state before position i, from records i-W .. i-1
+    MinimizerWindow<W, XT> win;
+    win.k = k;
+    win.min_x = kNone, win.min_y = UINT32_MAX, win.min_idx = W - 1;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      win.wx[j] = sx[lane + j], win.wy[j] = sy[lane + j];
+      if (win.min_x >= win.wx[j]) win.min_x = win.wx[j], win.min_y = win.wy[j], win.min_idx = j;
     }
+    const MinimizerWindow<W, XT> before = win;
+    int cnt = 0;
+    if (i < len) {
+      auto count = [&](XT, uint32_t) { ++cnt; };
+      win.step(ix, iy, l, count);
+      if (i == len - 1) win.finish(count);
+    }
+    int pos = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(full, pos, o);
+      if (lane >= o) pos += v;
+    }
+    const int total = __shfl_sync(full, pos, 31);
+    if (cnt > 0) {
+      int m = n + pos - cnt;
+      auto put = [&](XT x, uint32_t y) {
+        if (m < len) tab[m] = (uint64_t)(x >> 8) << kIdxShift | (uint64_t)y;
+        ++m;
+      };
+      win = before;
+      win.step(ix, iy, l, put);
+      if (i == len - 1) win.finish(put);
+    }
+    n += total;
     __syncwarp();
+    if (lane < W) sx[lane] = sx[32 + lane], sy[lane] = sy[32 + lane];  // carry the last W records over
   }
   if (lane == 0) {
-    win.finish(emit);
     if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
     D.idx_n[h] = n;
   }
@@ -428,8 +478,10 @@ __global__ void __launch_bounds__(128) k_chain_overflow(Dev D) {
               const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
               if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
               else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+              pr.n |= kPairHasTask;
             }
           }
+          if (pr.n & kPairHasTask) D.dp_pairs[atomicAdd((unsigned long long*)&D.ctr[C_NDP], 1ULL)] = (int32_t)pair;
         }
       }
       D.pair_reg[pair] = pr;
@@ -1405,17 +1457,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
       __syncwarp();
       if (first >= 0) {
         // extensions: closed forms here (warp-parallel compare), everything else → wavefront queue
+        bool queued = false;
         for (int i = 0; i < n_regs; ++i) {
           RegRec* rg = &D.regs[first + i];
           for (int side = 0; side < 2; ++side) {
             if (rg->ext[side].m <= 0) continue;
             if (warp_ext_exact(D.P, rv, hapc, rg, side, &ctr.dp_cells_full)) continue;
+            queued = true;
             if (lane == 0) {
               const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
               if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
               else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
             }
           }
+        }
+        if (queued && lane == 0) {
+          D.pair_reg[pair].n = n_regs | kPairHasTask;
+          D.dp_pairs[atomicAdd((unsigned long long*)&D.ctr[C_NDP], 1ULL)] = (int32_t)pair;
         }
       }
       __syncwarp();
@@ -1467,18 +1525,24 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_ext_warp(Dev D) {
 
 // Phase B2 kernel: one warp per parked pair, every extension already done: the warp-parallel
 // finish (assemble, fix, extra, filter, sort) and the final record.
-__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D) {
+// pass 0 (concurrent with k_ext_warp on the other stream): every pair without a queued
+// extension; pass 1 (after k_ext_warp): the queued ones, from the dp_pairs list.
+__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D, int pass, uint32_t* fin_scratch) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
+  uint32_t* fin0 = fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
   long long n_aligned = 0;
+  const long long n_work = pass == 0 ? D.n_pairs : D.ctr[C_NDP];
   for (;;) {
     long long pair = 0;
-    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[C_FINPOS], 1ULL);
+    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[pass == 0 ? C_FINPOS : C_FINPOS2], 1ULL);
     pair = __shfl_sync(full, pair, 0);
-    if (pair >= D.n_pairs) break;
-    const PairReg d = D.pair_reg[pair];
+    if (pair >= n_work) break;
+    if (pass) pair = D.dp_pairs[pair];
+    PairReg d = D.pair_reg[pair];
+    if (pass == 0 && (d.n & kPairHasTask)) continue;
+    d.n &= ~kPairHasTask;
     if (d.n <= 0) continue;
     const int read = d.read;
     const uint8_t* hapc = D.hap_codes + D.hap_off[d.hap];
@@ -1574,7 +1638,7 @@ struct lgr_ctx {
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
       b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
-      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks;
+      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks, b_dp_pairs;
   Dev D;
   bool resident = false;
   int max_read_len = 0, max_hap_len = 0;
@@ -1582,6 +1646,13 @@ struct lgr_ctx {
   int ext_blocks = 0, fin_blocks = 0, warp_blocks = 0, warp_cap = 64;
   size_t warp_smem = 0;
   cudaEvent_t ev[12];
+  long long* h_ctr = nullptr;  // pinned copy of the device counters
+  int launches = 0;
+  // asynchronous submissions (lgr_submit/lgr_wait): child contexts, one per slot in flight
+  lgr_ctx* slot[LGR_MAX_INFLIGHT] = {};
+  bool slot_busy[LGR_MAX_INFLIGHT] = {};
+  lgr_batch_out* slot_out[LGR_MAX_INFLIGHT] = {};
+  int64_t slot_h2d[LGR_MAX_INFLIGHT] = {}, slot_d2h[LGR_MAX_INFLIGHT] = {};
   // host staging of helper arrays
   std::vector<int32_t> h_read_grp, h_hap_grp, h_item_hap, h_item_r0, h_item_n, h_grp_mid;
   std::vector<int64_t> h_pair_off, h_asg_off;
@@ -1634,6 +1705,7 @@ void lgr_default_params(lgr_params* p) {
 }
 
 const char* lgr_strerror(int code) {
+  if (code == LGR_E_BUSY) return "all submission slots in flight";
   switch (code) {
     case LGR_OK: return "ok";
     case LGR_E_ARG: return "bad argument or inconsistent batch";
@@ -1711,6 +1783,11 @@ int lgr_create(int device_ordinal, const lgr_params* params, lgr_ctx** out) {
   cudaGetDeviceProperties(&prop, device_ordinal);
   c->sm_count = prop.multiProcessorCount;
   for (auto& e : c->ev) cudaEventCreate(&e);
+  if (cudaMallocHost((void**)&c->h_ctr, sizeof(long long) * (C_COUNT + 1)) != cudaSuccess) {
+    g_create_err = "cudaMallocHost failed";
+    delete c;
+    return LGR_E_CUDA;
+  }
   cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
@@ -1730,12 +1807,17 @@ int lgr_create(int device_ordinal, const lgr_params* params, lgr_ctx** out) {
 
 void lgr_destroy(lgr_ctx* c) {
   if (!c) return;
+  for (lgr_ctx*& ch : c->slot) {
+    lgr_destroy(ch);
+    ch = nullptr;
+  }
   cudaSetDevice(c->device);
+  if (c->h_ctr) cudaFreeHost(c->h_ctr);
   DevBuf* bufs[] = {&c->b_grp_hap, &c->b_grp_read, &c->b_grp_var, &c->b_hap_off, &c->b_read_off, &c->b_var_hap_off, &c->b_hap_bases,
                     &c->b_read_bases, &c->b_read_quals, &c->b_name_hash, &c->b_var_start, &c->b_var_len, &c->b_var_allele,
                     &c->b_read_grp, &c->b_hap_grp, &c->b_pair_off, &c->b_asg_off, &c->b_item_hap, &c->b_item_r0, &c->b_item_n,
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
-                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
+                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_dp_pairs, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
                     &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt};
   for (DevBuf* b : bufs)
@@ -1832,6 +1914,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
     c->h_grp_mid[g] = mid;
   }
   c->h_pair_off[NR] = po, c->h_asg_off[NR] = ao;
+  if (po > (int64_t)1 << 30) { c->err = "more than 2^30 (read, haplotype) pairs in one batch"; return LGR_E_LIMIT; }
   const int64_t hap_bytes = NH ? in->hap_off[NH] : 0, read_bytes = NR ? in->read_off[NR] : 0;
   const int64_t nvh = NV ? in->var_hap_off[NV] : 0;
   c->hap_bytes = hap_bytes, c->read_bytes = read_bytes;
@@ -1904,6 +1987,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap)) ||
       (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_pair_reg, sizeof(PairReg) * (size_t)n_pairs)) ||
       (rc = ensure(c, c->b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2)) ||
+      (rc = ensure(c, c->b_dp_pairs, sizeof(int32_t) * (size_t)(n_pairs + 1))) ||
       (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
       (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
       (rc = ensure(c, c->b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
@@ -1942,6 +2026,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
   D.pair_reg = (PairReg*)c->b_pair_reg.p;
   D.tasks = (TaskRec*)c->b_tasks.p, D.tasks_cap = regs_cap * 2;
+  D.dp_pairs = (int32_t*)c->b_dp_pairs.p;
   D.ext_arena = (uint32_t*)c->b_ext_arena.p, D.ext_arena_cap = ext_arena_cap;
   D.ovf_read = (int32_t*)c->b_ovf_read.p, D.ovf_hap = (int32_t*)c->b_ovf_hap.p, D.ovf_cap = n_pairs;
   D.dir_scratch = (uint8_t*)c->b_dir.p, D.dir_per_warp = dir_per_warp;
@@ -1956,7 +2041,8 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   return LGR_OK;
 }
 
-static int run_impl(lgr_ctx* c, lgr_stats* st) {
+// enqueue one pass of the whole path on the context's streams; no host synchronisation
+static int run_launch(lgr_ctx* c) {
   if (!c->resident) { c->err = "no batch uploaded"; return LGR_E_ARG; }
   LGR_CUDA(c, cudaSetDevice(c->device));
   Dev& D = c->D;
@@ -1979,7 +2065,8 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s2>>>(D);
     cudaEventRecord(c->ev_join, s2);
     k_encode<<<enc_blocks, 256, 0, s>>>(D.hap_bases, D.hap_codes, hb);
-    if (D.P.w == 5 && (D.P.k & 1)) k_hap_sketch_warp<<<(D.n_haps + 3) / 4, 128, 0, s>>>(D);
+    if (D.P.w == 5 && (D.P.k & 1) && 2 * D.P.k + 8 <= 32) k_hap_sketch_warp<uint32_t><<<(D.n_haps + 3) / 4, 128, 0, s>>>(D);
+    else if (D.P.w == 5 && (D.P.k & 1)) k_hap_sketch_warp<uint64_t><<<(D.n_haps + 3) / 4, 128, 0, s>>>(D);
     else k_hap_sketch<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D);
     k_hap_sort<<<D.n_haps, 128, 2048 * sizeof(uint64_t), s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
     k_group_mid<<<(D.n_groups + 127) / 128, 128, 0, s>>>(D, c->prm.min_mid_occ);
@@ -2001,9 +2088,15 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
       k_chain_overflow<<<kBigWarps / 4, 128, 0, s>>>(D2);
       launches += 1;
     }
-    k_ext_warp<<<c->ext_blocks, 128, 0, s>>>(D);
-    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D);
-    launches += 2;
+    // the few long wavefront extensions run beside the many pairs that need none
+    cudaEventRecord(c->ev_fork, s);
+    cudaStreamWaitEvent(s2, c->ev_fork, 0);
+    k_ext_warp<<<c->ext_blocks, 128, 0, s2>>>(D);
+    cudaEventRecord(c->ev_join, s2);
+    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D, 0, D.fin_scratch);
+    cudaStreamWaitEvent(s, c->ev_join, 0);
+    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D, 1, D.fin_scratch);
+    launches += 3;
     cudaEventRecord(c->ev[3], s);
     if (D.n_assign > 0) {
       k_assign<<<(unsigned)((D.n_assign + 127) / 128), 128, 0, s>>>(D);
@@ -2013,10 +2106,17 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
     cudaEventRecord(c->ev[1], s), cudaEventRecord(c->ev[2], s), cudaEventRecord(c->ev[9], s), cudaEventRecord(c->ev[3], s);
   }
   cudaEventRecord(c->ev[4], s);
-  long long hctr[C_COUNT];
-  LGR_CUDA(c, cudaMemcpyAsync(hctr, D.ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
-  LGR_CUDA(c, cudaStreamSynchronize(s));
+  LGR_CUDA(c, cudaMemcpyAsync(c->h_ctr, D.ctr, sizeof(long long) * C_COUNT, cudaMemcpyDeviceToHost, s));
+  c->launches = launches;
+  return LGR_OK;
+}
+
+// after the stream has drained: statistics and the device-side limit flags
+static int run_finish(lgr_ctx* c, lgr_stats* st) {
   LGR_CUDA(c, cudaGetLastError());
+  Dev& D = c->D;
+  const long long* hctr = c->h_ctr;
+  const int launches = c->launches;
   if (st) {
     float ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]); st->ms_kernels = ms;
@@ -2040,7 +2140,16 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
   return LGR_OK;
 }
 
-static int download_impl(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
+static int run_impl(lgr_ctx* c, lgr_stats* st) {
+  int rc = run_launch(c);
+  if (rc != LGR_OK) return rc;
+  LGR_CUDA(c, cudaStreamSynchronize(c->stream));
+  return run_finish(c, st);
+}
+
+// enqueue the device→host copies whose sizes are known up front (records, inline cigars,
+// assignments); the overflow cigar arena follows in download_finish once its fill is known
+static int download_launch(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
   if (!c->resident || !out) { c->err = "nothing to download"; return LGR_E_ARG; }
   LGR_CUDA(c, cudaSetDevice(c->device));
   Dev& D = c->D;
@@ -2053,24 +2162,38 @@ static int download_impl(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
       LGR_CUDA(c, cudaMemcpyAsync(out->cigar_inline, D.cigar_inline, sizeof(uint32_t) * D.n_pairs * LGR_CIGAR_INLINE, cudaMemcpyDeviceToHost, c->stream));
       d2h += sizeof(uint32_t) * D.n_pairs * LGR_CIGAR_INLINE;
     }
-    long long used = 0;
-    LGR_CUDA(c, cudaMemcpyAsync(&used, D.ctr + C_CIGARENA, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-    LGR_CUDA(c, cudaStreamSynchronize(c->stream));
-    out->cigar_arena_used = used;
-    if (used > 0) {
-      if (!out->cigar_arena || out->cigar_arena_cap < used) { c->err = "host cigar arena too small"; return LGR_E_CIGAR_OVERFLOW; }
-      LGR_CUDA(c, cudaMemcpyAsync(out->cigar_arena, D.cigar_arena, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost, c->stream));
-      d2h += sizeof(uint32_t) * used;
-    }
+    LGR_CUDA(c, cudaMemcpyAsync(c->h_ctr + C_COUNT, D.ctr + C_CIGARENA, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   }
   if (out->assign && D.n_assign > 0) {
     if (out->n_assign < D.n_assign) { c->err = "out->n_assign too small"; return LGR_E_ARG; }
     LGR_CUDA(c, cudaMemcpyAsync(out->assign, D.assign, sizeof(AssignOut) * D.n_assign, cudaMemcpyDeviceToHost, c->stream));
     d2h += sizeof(AssignOut) * D.n_assign;
   }
-  LGR_CUDA(c, cudaStreamSynchronize(c->stream));
   if (d2h_bytes) *d2h_bytes = d2h;
   return LGR_OK;
+}
+
+// stream already drained by the caller
+static int download_finish(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
+  Dev& D = c->D;
+  if (out->aln) {
+    const long long used = c->h_ctr[C_COUNT];
+    out->cigar_arena_used = used;
+    if (used > 0) {
+      if (!out->cigar_arena || out->cigar_arena_cap < used) { c->err = "host cigar arena too small"; return LGR_E_CIGAR_OVERFLOW; }
+      LGR_CUDA(c, cudaMemcpyAsync(out->cigar_arena, D.cigar_arena, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost, c->stream));
+      LGR_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (d2h_bytes) *d2h_bytes += sizeof(uint32_t) * used;
+    }
+  }
+  return LGR_OK;
+}
+
+static int download_impl(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
+  int rc = download_launch(c, out, d2h_bytes);
+  if (rc != LGR_OK) return rc;
+  LGR_CUDA(c, cudaStreamSynchronize(c->stream));
+  return download_finish(c, out, d2h_bytes);
 }
 
 int lgr_upload(lgr_ctx* c, const lgr_batch_in* in) {
@@ -2112,6 +2235,65 @@ int lgr_genotype_batch(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, l
   cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]); st.ms_d2h = ms;
   st.h2d_bytes = h2d, st.d2h_bytes = d2h;
   if (stats) *stats = st;
+  return run_rc != LGR_OK ? run_rc : rc;
+}
+
+int lgr_submit(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_ticket* ticket) {
+  if (!c || !in || !out || !ticket) return LGR_E_ARG;
+  int t = -1;
+  for (int i = 0; i < LGR_MAX_INFLIGHT && t < 0; ++i)
+    if (!c->slot_busy[i]) t = i;
+  if (t < 0) { c->err = "all submission slots are in flight; lgr_wait one first"; return LGR_E_BUSY; }
+  if (!c->slot[t]) {
+    int rc = lgr_create(c->device, &c->prm, &c->slot[t]);
+    if (rc != LGR_OK) { c->err = g_create_err; return rc; }
+  }
+  lgr_ctx* ch = c->slot[t];
+  int64_t h2d = 0, d2h = 0;
+  cudaEventRecord(ch->ev[5], ch->stream);
+  int rc = upload_impl(ch, in, &h2d);
+  if (rc == LGR_OK) {
+    cudaEventRecord(ch->ev[6], ch->stream);
+    rc = run_launch(ch);
+  }
+  if (rc == LGR_OK) {
+    cudaEventRecord(ch->ev[7], ch->stream);
+    rc = download_launch(ch, out, &d2h);
+    cudaEventRecord(ch->ev[8], ch->stream);
+  }
+  if (rc != LGR_OK) {
+    cudaStreamSynchronize(ch->stream);  // leave the slot idle
+    c->err = ch->err;
+    return rc;
+  }
+  c->slot_busy[t] = true, c->slot_out[t] = out, c->slot_h2d[t] = h2d, c->slot_d2h[t] = d2h;
+  *ticket = t;
+  return LGR_OK;
+}
+
+int lgr_wait(lgr_ctx* c, lgr_ticket t, lgr_stats* stats) {
+  if (!c || t < 0 || t >= LGR_MAX_INFLIGHT || !c->slot_busy[t]) {
+    if (c) c->err = "lgr_wait: unknown ticket";
+    return LGR_E_ARG;
+  }
+  lgr_ctx* ch = c->slot[t];
+  c->slot_busy[t] = false;
+  if (cudaStreamSynchronize(ch->stream) != cudaSuccess) {
+    c->err = std::string("lgr_wait: ") + cudaGetErrorString(cudaGetLastError());
+    return LGR_E_CUDA;
+  }
+  lgr_stats st;
+  std::memset(&st, 0, sizeof(st));
+  const int run_rc = run_finish(ch, &st);
+  int rc = LGR_OK;
+  int64_t d2h = c->slot_d2h[t];
+  if (run_rc == LGR_OK || run_rc == LGR_E_LIMIT || run_rc == LGR_E_CIGAR_OVERFLOW) rc = download_finish(ch, c->slot_out[t], &d2h);
+  float ms;
+  cudaEventElapsedTime(&ms, ch->ev[5], ch->ev[6]); st.ms_h2d = ms;
+  cudaEventElapsedTime(&ms, ch->ev[7], ch->ev[8]); st.ms_d2h = ms;
+  st.h2d_bytes = c->slot_h2d[t], st.d2h_bytes = d2h;
+  if (stats) *stats = st;
+  if (run_rc != LGR_OK || rc != LGR_OK) c->err = ch->err;
   return run_rc != LGR_OK ? run_rc : rc;
 }
 

@@ -29,6 +29,7 @@ class GpuRealigner:
             self.lib.lgr_default_params(C.byref(params))
         self.params = params
         self._ctx = C.c_void_p()
+        self._inflight = {}
         rc = self.lib.lgr_create(device, C.byref(params), C.byref(self._ctx))
         if rc != 0:
             raise LgrError(rc, (self.lib.lgr_last_error(None) or b"").decode() or self.lib.lgr_strerror(rc).decode())
@@ -64,6 +65,28 @@ class GpuRealigner:
         st = abi.LgrStats()
         self._check(self.lib.lgr_genotype_batch(self._ctx, C.byref(bi), C.byref(bo), C.byref(st)))
         return res, st
+
+    def submit(self, batch: abi.Batch, result: Optional[abi.Result] = None, want_aln: bool = True,
+               arena: int = 1 << 20) -> Tuple[int, abi.Result]:
+        """`lgr_submit`: enqueue H2D + kernels + D2H of one batch and return (ticket, result buffers).
+        The buffers are filled once `wait(ticket)` returns; up to LGR_MAX_INFLIGHT tickets may be open."""
+        res = result or abi.Result(batch, arena)
+        bi, bo = batch.c_struct(), res.c_struct()
+        if not want_aln:
+            bo.aln = None
+            bo.cigar_inline = None
+        t = C.c_int32(-1)
+        self._check(self.lib.lgr_submit(self._ctx, C.byref(bi), C.byref(bo), C.byref(t)))
+        self._inflight[t.value] = (batch, res, bi, bo)  # keep every host buffer alive until wait()
+        return t.value, res
+
+    def wait(self, ticket: int) -> abi.LgrStats:
+        st = abi.LgrStats()
+        try:
+            self._check(self.lib.lgr_wait(self._ctx, ticket, C.byref(st)))
+        finally:
+            self._inflight.pop(ticket, None)
+        return st
 
     def upload(self, batch: abi.Batch):
         bi = batch.c_struct()

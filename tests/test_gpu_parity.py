@@ -82,3 +82,30 @@ def test_limits_fail_loudly(gpu):
     g = abi.Group(haps=[hap], reads=[b"C" * 2000], quals=[b"\x25" * 2000], names=["x"], variants=[])
     with pytest.raises(LgrError):
         gpu.genotype_batch(abi.Batch([g]))
+
+
+def test_submit_wait_tickets_overlap_and_match_oracle(gpu):
+    """lgr_submit/lgr_wait: several batches in flight on one ctx, waited out of order, each
+    bit-identical to the oracle; the slot limit and bad tickets fail loudly."""
+    from lancet2_b200.realign import LgrError
+    batches = [abi.Batch(synth.make_groups(900 + i, 3 + i, n_reads=64 + 16 * i, n_haps=2 + i, hap_len=500 + 100 * i))
+               for i in range(abi.LGR_MAX_INFLIGHT)]
+    for rnd in range(2):  # second round reuses the slots' device buffers
+        tickets = [gpu.submit(b) for b in batches]
+        assert sorted(t for t, _ in tickets) == list(range(abi.LGR_MAX_INFLIGHT))
+        with pytest.raises(LgrError) as ei:
+            gpu.submit(batches[0])
+        assert ei.value.code == -7
+        for (t, res), b in reversed(list(zip(tickets, batches))):
+            st = gpu.wait(t)
+            want, wst = O.oracle_genotype(b, gpu.params, n_threads=8)
+            errs = compare_results(b, want, res)
+            assert not errs, "\n".join(errs[:20])
+            assert st.n_pairs == b.n_pairs and st.n_aligned == wst.n_aligned and st.h2d_bytes > 0 and st.d2h_bytes > 0
+    with pytest.raises(LgrError):
+        gpu.wait(0)  # nothing outstanding
+    # assignments-only submission (what the Genotyper adapter asks for)
+    t, res = gpu.submit(batches[1], want_aln=False)
+    gpu.wait(t)
+    want, _ = O.oracle_genotype(batches[1], gpu.params, n_threads=8)
+    assert not compare_results(batches[1], want, res, check_aln=False)
