@@ -250,7 +250,7 @@ def declared_symbols() -> List[str]:
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
     """dlopen the CUDA library.  Raises (never falls back) when it is missing."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("LGR_LIBRARY") or LIB_PATH  # LGR_LIBRARY: A/B builds of the same ABI
     if not os.path.exists(path):
         raise RuntimeError(
             f"CUDA extension not built: {path} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'` "

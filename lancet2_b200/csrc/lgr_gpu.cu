@@ -129,7 +129,7 @@ __global__ void k_encode(const uint8_t* __restrict__ src, uint8_t* __restrict__ 
 }
 
 // one lane per haplotype: sketch → table entries (hash<<17 | pos<<1|strand), unsorted
-__global__ void k_hap_sketch(Dev D) {
+__global__ void k_hap_sketch(const __grid_constant__ Dev D) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= D.n_haps) return;
   const int64_t off = D.hap_off[h];
@@ -171,7 +171,7 @@ __global__ void k_hap_sketch(Dev D) {
 // state from its W predecessors, runs the one `MinimizerWindow::step` of its own position
 // (same code as the sequential sketch) and the warp concatenates the emissions in order.
 template <typename XT>
-__global__ void __launch_bounds__(128) k_hap_sketch_warp(Dev D) {
+__global__ void __launch_bounds__(128) k_hap_sketch_warp(const __grid_constant__ Dev D) {
   constexpr XT kNone = MinimizerWindow<5, XT>::kMax;
   constexpr int W = 5;
   __shared__ XT s_x[4][32 + W];
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(128) k_hap_sketch_warp(Dev D) {
 }
 
 // one CTA per haplotype: in-place bitonic sort of its table (keys are unique)
-__global__ void k_hap_sort(Dev D, float mid_occ_frac, int min_mid, int max_mid) {
+__global__ void k_hap_sort(const __grid_constant__ Dev D, float mid_occ_frac, int min_mid, int max_mid) {
   const int h = blockIdx.x;
   uint64_t* tab = D.idx + D.hap_off[h];
   const int n = D.idx_n[h];
@@ -343,7 +343,7 @@ __global__ void k_hap_sort(Dev D, float mid_occ_frac, int min_mid, int max_mid) 
   }
 }
 
-__global__ void k_group_mid(Dev D, int min_mid) {
+__global__ void k_group_mid(const __grid_constant__ Dev D, int min_mid) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= D.n_groups) return;
   if (D.grp_mid[g] > 0) return;
@@ -354,7 +354,7 @@ __global__ void k_group_mid(Dev D, int min_mid) {
 // one lane per read: sketch.  Independent of the haplotype index, so it runs on a second stream
 // next to the haplotype kernels.  Alongside the minimizers it leaves 32 saturating 4-bit
 // counters of their hashes (bucket = low hash bits) for k_read_filter.
-__global__ void k_read_sketch(Dev D) {
+__global__ void k_read_sketch(const __grid_constant__ Dev D) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= D.n_reads) return;
   const int64_t off = D.read_off[r];
@@ -382,7 +382,7 @@ __global__ void k_read_sketch(Dev D) {
 // one lane per read: mm_seed_mz_flt (q_occ_max = the group's mid_occ, known once the haplotype
 // tables exist).  A minimizer can only repeat more than q_occ_max times if its bucket counter
 // does, so the O(n^2) filter only runs for the few reads where some bucket got that full.
-__global__ void k_read_filter(Dev D) {
+__global__ void k_read_filter(const __grid_constant__ Dev D) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= D.n_reads || D.P.q_occ_frac <= 0.0f) return;
   const int n = D.mz_n[r];
@@ -430,7 +430,7 @@ __device__ __forceinline__ void store_final(const Dev& D, int64_t pair, const Al
 // scalar core (map_chain_phase) over a 16384-anchor HBM workspace interleaved per warp; regs are
 // parked exactly like k_chain_warp does.  Exits immediately when the overflow list is empty.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_chain_overflow(Dev D) {
+__global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ Dev D) {
   const int lane = threadIdx.x & 31;
   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
   const int gwarp = gthread >> 5;
@@ -1101,8 +1101,14 @@ __device__ __noinline__ void warp_finish_pure_m(const DevParams& P, const uint8_
 // finish_pair (lgr_core.cuh) with the per-base loops spread over the warp.  Uniform control flow;
 // cigar assembly / mm_fix_cigar stay scalar on lane 0.  Returns the op count of the winning cigar
 // (in fs.best), or -1 on scratch overflow; *out is valid on every lane.
+struct TrackBlock {  // surviving regs of one pair (mm_set_parent / mm_select_sub inputs), one per warp in shared memory
+  uint64_t key[kTrack];
+  int32_t qs[kTrack], qe[kTrack], rs[kTrack], re[kTrack], score[kTrack];
+};
+constexpr int kFinSmemCig = 64;  // cigar ops of a reg kept in shared memory; longer ones use the HBM scratch
+
 __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
-                                             FinishScratch& fs, AlnOut* out) {
+                                             FinishScratch& fs, TrackBlock* trk, AlnOut* out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
@@ -1112,8 +1118,8 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
   uint64_t best_key = 0;
   RegFinal bf;
   bf.n_cig = 0;
-  int32_t s_qs[kTrack], s_qe[kTrack], s_rs[kTrack], s_re[kTrack], s_score[kTrack];
-  uint64_t s_key[kTrack];
+  int32_t *s_qs = trk->qs, *s_qe = trk->qe, *s_rs = trk->rs, *s_re = trk->re, *s_score = trk->score;
+  uint64_t* s_key = trk->key;
   for (int r = 0; r < n_regs; ++r) {
     RegAsm ra;
     int okf = 1;
@@ -1145,7 +1151,7 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
     else if ((float)rf.qs > (float)qlen * P.max_clip_ratio && (float)(qlen - rf.qe) > (float)qlen * P.max_clip_ratio) flt = true;
     if (flt) continue;
     const uint64_t key = (uint64_t)(uint32_t)rf.dp_max << 32 | hash;
-    if (n_surv < kTrack) {
+    if (n_surv < kTrack && lane == 0) {
       s_qs[n_surv] = rf.qs, s_qe[n_surv] = rf.qe, s_rs[n_surv] = rf.rs, s_re[n_surv] = rf.re;
       s_score[n_surv] = score, s_key[n_surv] = key;
     }
@@ -1161,6 +1167,7 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
   out->dp_max = 0, out->mlen = out->blen = out->n_ambi = 0, out->nm = 0, out->n_cigar = 0, out->cigar_off = -1;
   out->n_regs = 0;
   if (best < 0) return 0;
+  __syncwarp();
   const int n_ret = n_surv > 1 ? select_returned(P, n_surv, s_qs, s_qe, s_rs, s_re, s_score, s_key) : n_surv;
   out->valid = 1;
   out->score = regs[best].score;
@@ -1383,11 +1390,14 @@ constexpr int kWarpItemReads = 4;  // reads per warp work item (all against one 
 #ifndef LGR_CHAIN_MINB
 #define LGR_CHAIN_MINB 7
 #endif
+#ifndef LGR_EXT_CTAS
+#define LGR_EXT_CTAS 8  // CTAs per SM of k_ext_warp (the rest of the SM is left to the concurrent k_finish_warp pass)
+#endif
 #ifndef LGR_FIN_MINB
 #define LGR_FIN_MINB 8
 #endif
 template <int CAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_warp(Dev D) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_warp(const __grid_constant__ Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
   const unsigned full = 0xffffffffu;
@@ -1490,7 +1500,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
 // the anti-diagonal wavefront.  Nothing but DP code lives here, so resident warps share one hot loop.
 constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
 
-__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_ext_warp(Dev D) {
+__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_ext_warp(const __grid_constant__ Dev D) {
   __shared__ uint8_t s_dir[4 * kDirSmemPerWarp];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -1527,11 +1537,15 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_ext_warp(Dev D) {
 // finish (assemble, fix, extra, filter, sort) and the final record.
 // pass 0 (concurrent with k_ext_warp on the other stream): every pair without a queued
 // extension; pass 1 (after k_ext_warp): the queued ones, from the dp_pairs list.
-__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D, int pass, uint32_t* fin_scratch) {
+__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_constant__ Dev D, int pass, uint32_t* fin_scratch) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ TrackBlock s_trk[4];
+  __shared__ uint32_t s_cig[4][2 * kFinSmemCig];
   uint32_t* fin0 = fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
+  TrackBlock* trk = &s_trk[threadIdx.x >> 5];
+  uint32_t* scig = s_cig[threadIdx.x >> 5];
   long long n_aligned = 0;
   const long long n_work = pass == 0 ? D.n_pairs : D.ctr[C_NDP];
   for (;;) {
@@ -1549,9 +1563,15 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D, int pa
     const int64_t roff = D.read_off[read];
     ReadView rv{D.read_codes + roff, (int)(D.read_off[read + 1] - roff)};
     RegRec* regs = D.regs + d.first;
-    FinishScratch fs{fin0, fin0 + D.fin_cap, D.fin_cap};
+    // cigars live in shared memory; the rare reg with more ops than fit reruns on the HBM scratch
+    FinishScratch fs{scig, scig + kFinSmemCig, kFinSmemCig};
     AlnOut ao;
-    const int nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, &ao);
+    int nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &ao);
+    if (nc < 0) {
+      __syncwarp();
+      fs = FinishScratch{fin0, fin0 + D.fin_cap, D.fin_cap};
+      nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &ao);
+    }
     if (lane == 0) {
       if (nc < 0) {
         atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
@@ -1567,7 +1587,7 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(Dev D, int pa
 }
 
 // one lane per (read, variant): AssignReadToAlleles' inner loops (genotyper.cpp:294-318)
-__global__ void __launch_bounds__(128) k_assign(Dev D) {
+__global__ void __launch_bounds__(128) k_assign(const __grid_constant__ Dev D) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= D.n_assign) return;
   // read r with asg_off[r] <= slot < asg_off[r+1]
@@ -1971,7 +1991,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    c->ext_blocks = c->sm_count * per_sm;
+    c->ext_blocks = c->sm_count * std::min(per_sm, LGR_EXT_CTAS);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     c->fin_blocks = c->sm_count * per_sm;
   }
