@@ -518,8 +518,20 @@ enum WsArray {
 template <int S>
 struct Ws {
   int32_t* base;  // already offset to this lane
-  int cap;
-  LGR_HD Strided<int32_t, S> arr(int k) const { return Strided<int32_t, S>{base + (size_t)k * cap * S}; }
+  // capacities, packed (keeps the struct at two words: a third member made nvcc lose track of
+  // the shared address space of `base` in k_chain_warp and fall back to generic LD/ST):
+  // low 16 bits = elements of the anchor-sized arrays (A_*), high bits = elements of the
+  // chain/reg-sized arrays (R_*; 0 = same as the anchor arrays).  A pair with more chains
+  // than that overflows.
+  int caps;
+  LGR_HD int cap() const { return caps & 0xffff; }
+  LGR_HD int rcap() const { return caps >> 16 ? caps >> 16 : caps; }
+  static LGR_HD int pack(int cap_, int rcap_) { return cap_ | rcap_ << 16; }
+  LGR_HD Strided<int32_t, S> arr(int k) const {
+    const int off = k < R_SCORE ? k * cap() : R_SCORE * cap() + (k - R_SCORE) * rcap();
+    return Strided<int32_t, S>{base + (size_t)off * S};
+  }
+  static LGR_HD size_t elems(int cap_, int rcap_) { return (size_t)R_SCORE * cap_ + (size_t)(A_COUNT - R_SCORE) * rcap_; }
 };
 
 // ------------------------------------------------------------------------------------
@@ -847,6 +859,7 @@ LGR_HDN int map_chain_tail(const DevParams& P, int qlen, int hap_len, uint32_t n
       for (i = zi; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
       const int32_t sc = i < 0 ? zx : zx - f[i];
       if (sc >= P.min_sc && n_v > n_v0 && n_v - n_v0 >= P.min_cnt) {
+        if (n_u >= ws.rcap()) return kMapOverflow;
         u_sc[n_u] = sc, u_cnt[n_u] = n_v - n_v0;
         ++n_u;
       } else {
@@ -1060,7 +1073,7 @@ LGR_HDN int map_chain_tail(const DevParams& P, int qlen, int hap_len, uint32_t n
 template <int S>
 LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& ws, RadixScratch* rsx,
                             int* n_regs_out, ChainCounters* ctr) {
-  const int cap = ws.cap;
+  const int cap = ws.cap();
   auto ax = ws.arr(A_AX), ay = ws.arr(A_AY), sx = ws.arr(A_SX), sy = ws.arr(A_SY);
   auto f = ws.arr(A_F), p = ws.arr(A_P), t = ws.arr(A_T), v = ws.arr(A_V), z = ws.arr(A_Z);
   auto perm = ws.arr(A_PERM);

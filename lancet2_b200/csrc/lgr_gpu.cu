@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
   const long long n_work = D.ctr[C_NOVF] < D.ovf_cap ? D.ctr[C_NOVF] : D.ovf_cap;
   if (n_work == 0) return;
   Ws<32> ws;
-  ws.cap = D.ws_cap;
+  ws.caps = D.ws_cap;  // 16384: fits the low half, chain arrays the same size
   ws.base = D.ws + (size_t)gwarp * A_COUNT * D.ws_cap * 32 + lane;
   RadixScratch rsx;
   ChainCounters ctr{0, 0, 0, 0};
@@ -1387,15 +1387,23 @@ constexpr int kWarpItemReads = 4;  // reads per warp work item (all against one 
 
 // Phase A kernel: seeds → anchors → chain DP → regs, one warp per pair.  Every pair with at least
 // one reg is parked: its RegRecs go to the arena and its PairReg slot tells k_finish_warp where.
+#ifndef LGR_CHAIN_CARVEOUT
+#define LGR_CHAIN_CARVEOUT -1  // cudaSharedmemCarveoutDefault: the chain kernel gains from every KB left to L1 (measured)
+#endif
 #ifndef LGR_CHAIN_MINB
-#define LGR_CHAIN_MINB 7
+#define LGR_CHAIN_MINB 9
 #endif
 #ifndef LGR_EXT_CTAS
 #define LGR_EXT_CTAS 8  // CTAs per SM of k_ext_warp (the rest of the SM is left to the concurrent k_finish_warp pass)
 #endif
+#ifndef LGR_EXT_MINB
+#define LGR_EXT_MINB 8
+#endif
 #ifndef LGR_FIN_MINB
 #define LGR_FIN_MINB 8
 #endif
+constexpr int kRegCap = 16;  // chains per pair held in shared memory (more → overflow pass)
+
 template <int CAP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_warp(const __grid_constant__ Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1403,7 +1411,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kWarpsPerCta + warp;
-  Ws<1> ws{s_ws + (size_t)warp * A_COUNT * CAP, CAP};
+  Ws<1> ws{s_ws + (size_t)warp * Ws<1>::elems(CAP, kRegCap), Ws<1>::pack(CAP, kRegCap)};
   RadixScratch* rsx = D.rsx_scratch + gwarp;
   ChainCounters ctr{0, 0, 0, 0};
   for (;;) {
@@ -1500,7 +1508,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
 // the anti-diagonal wavefront.  Nothing but DP code lives here, so resident warps share one hot loop.
 constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
 
-__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_ext_warp(const __grid_constant__ Dev D) {
+__global__ void __launch_bounds__(128, LGR_EXT_MINB) k_ext_warp(const __grid_constant__ Dev D) {
   __shared__ uint8_t s_dir[4 * kDirSmemPerWarp];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -1971,15 +1979,17 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int Tmax = Lm + ((c->prm.a + std::max(c->prm.b, c->prm.sc_ambi)) * Lm) / c->prm.e + 2;
   // warp-per-pair kernel: CAP anchors per pair in shared memory
   c->warp_cap = c->max_read_len <= 160 ? 64 : 128;
-  c->warp_smem = (size_t)kWarpsPerCta * A_COUNT * c->warp_cap * sizeof(int32_t);
+  c->warp_smem = (size_t)kWarpsPerCta * Ws<1>::elems(c->warp_cap, kRegCap) * sizeof(int32_t);
   {
     int per_sm = 0;
     cudaError_t e1, e2;
     if (c->warp_cap == 64) {
       e1 = cudaFuncSetAttribute(k_chain_warp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
+      cudaFuncSetAttribute(k_chain_warp<64>, cudaFuncAttributePreferredSharedMemoryCarveout, LGR_CHAIN_CARVEOUT);
       e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_warp<64>, kWarpsPerCta * 32, c->warp_smem);
     } else {
       e1 = cudaFuncSetAttribute(k_chain_warp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
+      cudaFuncSetAttribute(k_chain_warp<128>, cudaFuncAttributePreferredSharedMemoryCarveout, LGR_CHAIN_CARVEOUT);
       e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_warp<128>, kWarpsPerCta * 32, c->warp_smem);
     }
     if (e1 != cudaSuccess || e2 != cudaSuccess || per_sm < 1) {
