@@ -193,6 +193,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the realignment path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from lancet2_b200.realign import GpuRealigner
@@ -325,7 +327,7 @@ def main():
                      "ms_index": last.ms_k_index, "ms_sketch": last.ms_k_sketch, "ms_map": last.ms_k_map, "ms_ext": last.ms_k_ext,
                      "ms_assign": last.ms_k_assign, "wall_resident_s": wall_resident},
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:
             import oracle_lib as O
             cores = os.cpu_count() or 1
             prm = O.default_params()
