@@ -300,6 +300,22 @@ def main():
         abytes = algorithmic_bytes(batch)
         map_ms = statistics.mean(ms_map)
         achieved = abytes / (map_ms * 1e-3) / 1e9
+        # per-launch DRAM traffic and warp-instruction count of the dominant kernel: static for a
+        # given build and workload, taken from the committed ncu capture (never measured under ncu here)
+        static = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_ncu_static.json")) as fh:
+                static = json.load(fh)
+        except OSError:
+            pass
+        wl = static.get(args.workload, {}) if world == 1 or args.workload in static else {}
+        traffic = wl.get("dram_bytes_per_launch")
+        issue = None
+        if wl.get("warp_inst_per_launch") and static.get("int_issue_peak_warp_inst_per_s"):
+            ach = wl["warp_inst_per_launch"] / (map_ms * 1e-3)
+            issue = {"kernel": "k_chain_warp", "achieved": ach, "peak": static["int_issue_peak_warp_inst_per_s"], "unit": "warp-instr/s",
+                     "frac": ach / static["int_issue_peak_warp_inst_per_s"],
+                     "source": "instruction count: " + wl.get("source", "ncu") + "; peak: " + static.get("int_issue_peak_source", "")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -315,9 +331,10 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_chain_warp", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": map_ms,
-                         "note": "path is integer-issue bound, not HBM bound; see DESIGN.md §roofline"},
+                         "note": "path is integer-issue / latency bound, not HBM bound (DESIGN.md §roofline); `issue` is the same kernel against the measured INT issue peak"},
+            "issue": issue,
             "work": {"aligned_frac": last.n_aligned / max(1, last.n_pairs), "chain_evals_per_pair": last.chain_evals / max(1, last.n_pairs),
                      "anchors_per_pair": last.n_anchors / max(1, last.n_pairs), "dp_cells_per_pair": last.dp_cells / max(1, last.n_pairs),
                      "dp_cells_full_per_pair": last.dp_cells_full / max(1, last.n_pairs),
