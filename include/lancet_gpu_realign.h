@@ -33,6 +33,7 @@
 #ifndef LANCET_GPU_REALIGN_H_
 #define LANCET_GPU_REALIGN_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -236,6 +237,12 @@ int lgr_wait(lgr_ctx* ctx, lgr_ticket ticket, lgr_stats* stats);
 int lgr_upload(lgr_ctx* ctx, const lgr_batch_in* in);
 int lgr_run_resident(lgr_ctx* ctx, lgr_stats* stats);
 int lgr_download(lgr_ctx* ctx, lgr_batch_out* out);
+
+/* Page-locked host memory for batch buffers (cudaMallocHost / cudaFreeHost): with pinned `in`/`out`
+ * buffers the copies of lgr_submit are truly asynchronous.  NULL when it cannot be had (the
+ * caller may fall back to ordinary memory; only the overlap is lost). */
+void* lgr_alloc_pinned(size_t bytes);
+void lgr_free_pinned(void* p);
 
 /* raw CUDA stream (cudaStream_t) the ctx launches on, for external event timing */
 void* lgr_stream(lgr_ctx* ctx);

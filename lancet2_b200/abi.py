@@ -241,6 +241,7 @@ _SYMBOLS = [
     "lgr_abi_version", "lgr_default_params", "lgr_strerror", "lgr_last_error", "lgr_x31_hash",
     "lgr_pair_offsets", "lgr_create", "lgr_destroy", "lgr_hap_mid_occ", "lgr_genotype_batch",
     "lgr_upload", "lgr_run_resident", "lgr_download", "lgr_stream", "lgr_submit", "lgr_wait",
+    "lgr_alloc_pinned", "lgr_free_pinned",
 ]
 
 
@@ -285,6 +286,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.lgr_submit.restype = C.c_int
     lib.lgr_wait.argtypes = [C.c_void_p, C.c_int32, C.POINTER(LgrStats)]
     lib.lgr_wait.restype = C.c_int
+    lib.lgr_alloc_pinned.argtypes = [C.c_size_t]
+    lib.lgr_alloc_pinned.restype = C.c_void_p
+    lib.lgr_free_pinned.argtypes = [C.c_void_p]
+    lib.lgr_free_pinned.restype = None
     lib.lgr_stream.argtypes = [C.c_void_p]
     lib.lgr_stream.restype = C.c_void_p
     return lib

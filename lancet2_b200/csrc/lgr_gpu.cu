@@ -39,8 +39,8 @@ __constant__ double c_phred_err[256] = {
 
 // counters (int64 slots in device memory)
 enum Ctr {
-  C_ITEM = 0, C_NTASK, C_NDP, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
-  C_ALIGNED, C_TASKPOS, C_FINPOS, C_FINPOS2, C_OVFPOS, C_COUNT
+  C_ITEM = 0, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
@@ -50,8 +50,6 @@ constexpr int kBuckets = 1 << kBucketBits;
 struct TaskRec {  // one extension that needs the wavefront DP
   int32_t reg, side, read, hap;
 };
-
-constexpr int32_t kPairHasTask = 1 << 30;  // PairReg::n flag: some extension waits for the wavefront kernel
 
 struct PairReg {  // per pair: its parked RegRecs in the arena (n == 0: nothing to finish)
   int32_t first, n, read, hap;
@@ -93,7 +91,6 @@ struct Dev {      // everything the kernels need, passed by value
   RegRec* regs;  int64_t regs_cap;
   PairReg* pair_reg;             // [n_pairs]
   TaskRec* tasks; int64_t tasks_cap;
-  int32_t* dp_pairs;             // [n_pairs] pairs with a queued extension (finished in the second pass)
   uint32_t* ext_arena; int64_t ext_arena_cap;
   int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
   // k_ext_big scratch
@@ -478,10 +475,8 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
               const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
               if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
               else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
-              pr.n |= kPairHasTask;
             }
           }
-          if (pr.n & kPairHasTask) D.dp_pairs[atomicAdd((unsigned long long*)&D.ctr[C_NDP], 1ULL)] = (int32_t)pair;
         }
       }
       D.pair_reg[pair] = pr;
@@ -1383,7 +1378,7 @@ __device__ __forceinline__ bool warp_ext_exact(const DevParams& P, const ReadVie
   return true;
 }
 
-constexpr int kWarpItemReads = 4;  // reads per warp work item (all against one haplotype)
+constexpr int kWarpItemReads = 4;  // reads per warp work item (all against one haplotype) in machine-filling batches
 
 // Phase A kernel: seeds → anchors → chain DP → regs, one warp per pair.  Every pair with at least
 // one reg is parked: its RegRecs go to the arena and its PairReg slot tells k_finish_warp where.
@@ -1392,9 +1387,6 @@ constexpr int kWarpItemReads = 4;  // reads per warp work item (all against one 
 #endif
 #ifndef LGR_CHAIN_MINB
 #define LGR_CHAIN_MINB 9
-#endif
-#ifndef LGR_EXT_CTAS
-#define LGR_EXT_CTAS 8  // CTAs per SM of k_ext_warp (the rest of the SM is left to the concurrent k_finish_warp pass)
 #endif
 #ifndef LGR_EXT_MINB
 #define LGR_EXT_MINB 8
@@ -1475,23 +1467,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
       __syncwarp();
       if (first >= 0) {
         // extensions: closed forms here (warp-parallel compare), everything else → wavefront queue
-        bool queued = false;
         for (int i = 0; i < n_regs; ++i) {
           RegRec* rg = &D.regs[first + i];
           for (int side = 0; side < 2; ++side) {
             if (rg->ext[side].m <= 0) continue;
             if (warp_ext_exact(D.P, rv, hapc, rg, side, &ctr.dp_cells_full)) continue;
-            queued = true;
             if (lane == 0) {
               const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
               if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
               else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
             }
           }
-        }
-        if (queued && lane == 0) {
-          D.pair_reg[pair].n = n_regs | kPairHasTask;
-          D.dp_pairs[atomicAdd((unsigned long long*)&D.ctr[C_NDP], 1ULL)] = (int32_t)pair;
         }
       }
       __syncwarp();
@@ -1543,28 +1529,22 @@ __global__ void __launch_bounds__(128, LGR_EXT_MINB) k_ext_warp(const __grid_con
 
 // Phase B2 kernel: one warp per parked pair, every extension already done: the warp-parallel
 // finish (assemble, fix, extra, filter, sort) and the final record.
-// pass 0 (concurrent with k_ext_warp on the other stream): every pair without a queued
-// extension; pass 1 (after k_ext_warp): the queued ones, from the dp_pairs list.
-__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_constant__ Dev D, int pass, uint32_t* fin_scratch) {
+__global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_constant__ Dev D) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   __shared__ TrackBlock s_trk[4];
   __shared__ uint32_t s_cig[4][2 * kFinSmemCig];
-  uint32_t* fin0 = fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
+  uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
   TrackBlock* trk = &s_trk[threadIdx.x >> 5];
   uint32_t* scig = s_cig[threadIdx.x >> 5];
   long long n_aligned = 0;
-  const long long n_work = pass == 0 ? D.n_pairs : D.ctr[C_NDP];
   for (;;) {
     long long pair = 0;
-    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[pass == 0 ? C_FINPOS : C_FINPOS2], 1ULL);
+    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[C_FINPOS], 1ULL);
     pair = __shfl_sync(full, pair, 0);
-    if (pair >= n_work) break;
-    if (pass) pair = D.dp_pairs[pair];
-    PairReg d = D.pair_reg[pair];
-    if (pass == 0 && (d.n & kPairHasTask)) continue;
-    d.n &= ~kPairHasTask;
+    if (pair >= D.n_pairs) break;
+    const PairReg d = D.pair_reg[pair];
     if (d.n <= 0) continue;
     const int read = d.read;
     const uint8_t* hapc = D.hap_codes + D.hap_off[d.hap];
@@ -1666,7 +1646,7 @@ struct lgr_ctx {
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
       b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
-      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks, b_dp_pairs;
+      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks;
   Dev D;
   bool resident = false;
   int max_read_len = 0, max_hap_len = 0;
@@ -1845,7 +1825,7 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_read_bases, &c->b_read_quals, &c->b_name_hash, &c->b_var_start, &c->b_var_len, &c->b_var_allele,
                     &c->b_read_grp, &c->b_hap_grp, &c->b_pair_off, &c->b_asg_off, &c->b_item_hap, &c->b_item_r0, &c->b_item_n,
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
-                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_dp_pairs, &c->b_ext_arena, &c->b_ovf_read,
+                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
                     &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt};
   for (DevBuf* b : bufs)
@@ -1856,6 +1836,19 @@ void lgr_destroy(lgr_ctx* c) {
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+void* lgr_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void lgr_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 void* lgr_stream(lgr_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -1924,6 +1917,14 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   c->h_grp_mid.resize(G + 1);
   c->h_item_hap.clear(), c->h_item_r0.clear(), c->h_item_n.clear();
   int64_t po = 0, ao = 0;
+  // reads per warp work item: several reads of one haplotype amortise the item's fixed cost when
+  // the batch fills the machine many times over; a small batch (one Genotype() call) is latency
+  // bound instead and wants every pair on its own warp
+  int64_t pairs_total = 0;
+  for (int g = 0; g < G; ++g)
+    pairs_total += (int64_t)(in->grp_read_begin[g + 1] - in->grp_read_begin[g]) * (in->grp_hap_begin[g + 1] - in->grp_hap_begin[g]);
+  const int64_t warps_resident = (int64_t)c->sm_count * 36;
+  const int item_reads = pairs_total >= 8 * warps_resident ? kWarpItemReads : (pairs_total >= 3 * warps_resident ? 2 : 1);
   for (int g = 0; g < G; ++g) {
     const int h0 = in->grp_hap_begin[g], h1 = in->grp_hap_begin[g + 1];
     const int r0 = in->grp_read_begin[g], r1 = in->grp_read_begin[g + 1];
@@ -1934,8 +1935,8 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       po += h1 - h0, ao += V;
     }
     for (int h = h0; h < h1; ++h)
-      for (int r = r0; r < r1; r += kWarpItemReads) {
-        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(kWarpItemReads, r1 - r));
+      for (int r = r0; r < r1; r += item_reads) {
+        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(item_reads, r1 - r));
       }
     int32_t mid = c->prm.mid_occ;
     if (in->grp_mid_occ && in->grp_mid_occ[g] > 0) mid = in->grp_mid_occ[g];
@@ -2001,7 +2002,7 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    c->ext_blocks = c->sm_count * std::min(per_sm, LGR_EXT_CTAS);
+    c->ext_blocks = c->sm_count * per_sm;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     c->fin_blocks = c->sm_count * per_sm;
   }
@@ -2017,7 +2018,6 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap)) ||
       (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_pair_reg, sizeof(PairReg) * (size_t)n_pairs)) ||
       (rc = ensure(c, c->b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2)) ||
-      (rc = ensure(c, c->b_dp_pairs, sizeof(int32_t) * (size_t)(n_pairs + 1))) ||
       (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
       (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
       (rc = ensure(c, c->b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
@@ -2056,7 +2056,6 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
   D.pair_reg = (PairReg*)c->b_pair_reg.p;
   D.tasks = (TaskRec*)c->b_tasks.p, D.tasks_cap = regs_cap * 2;
-  D.dp_pairs = (int32_t*)c->b_dp_pairs.p;
   D.ext_arena = (uint32_t*)c->b_ext_arena.p, D.ext_arena_cap = ext_arena_cap;
   D.ovf_read = (int32_t*)c->b_ovf_read.p, D.ovf_hap = (int32_t*)c->b_ovf_hap.p, D.ovf_cap = n_pairs;
   D.dir_scratch = (uint8_t*)c->b_dir.p, D.dir_per_warp = dir_per_warp;
@@ -2118,15 +2117,9 @@ static int run_launch(lgr_ctx* c) {
       k_chain_overflow<<<kBigWarps / 4, 128, 0, s>>>(D2);
       launches += 1;
     }
-    // the few long wavefront extensions run beside the many pairs that need none
-    cudaEventRecord(c->ev_fork, s);
-    cudaStreamWaitEvent(s2, c->ev_fork, 0);
-    k_ext_warp<<<c->ext_blocks, 128, 0, s2>>>(D);
-    cudaEventRecord(c->ev_join, s2);
-    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D, 0, D.fin_scratch);
-    cudaStreamWaitEvent(s, c->ev_join, 0);
-    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D, 1, D.fin_scratch);
-    launches += 3;
+    k_ext_warp<<<c->ext_blocks, 128, 0, s>>>(D);
+    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D);
+    launches += 2;
     cudaEventRecord(c->ev[3], s);
     if (D.n_assign > 0) {
       k_assign<<<(unsigned)((D.n_assign + 127) / 128), 128, 0, s>>>(D);

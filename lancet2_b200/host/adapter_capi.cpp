@@ -2,9 +2,12 @@
 // drive the C++ adapter (ctypes) without a C++ test runner.  Test support only; the product
 // boundary is include/lancet_gpu_realign.h + host/gpu_genotyper.h.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gpu_genotyper.h"
@@ -78,74 +81,152 @@ int lgr_adapter_add_evidence_dump(int n, const long long* isize, const long long
   return WriteOut(os, out, cap);
 }
 
-// Run GpuGenotyper::GenotypeMany on a batch given in the C-ABI's SoA form plus the per-read
-// metadata AddToTable needs; dump every (group, variant, sample, allele) evidence block.
-// names: NUL-separated read names; samples: NUL-separated sample names, sample_id per read.
-// The name hash is X31 of the name (deterministic stand-in for absl::HashOf in tests).
+}  // extern "C"
+
+namespace {
+
+// Rebuilds the C++-side view (strings, ReadIn, VariantIn, one GenotypeJob per group) of a batch
+// given in the C-ABI's SoA form plus the per-read metadata AddToTable needs.
+struct JobSet {
+  std::vector<std::string_view> qn, sn;
+  std::vector<std::string> haps;
+  std::vector<lancet_gpu::ReadIn> reads;
+  std::vector<lancet_gpu::VariantIn> vars;
+  std::vector<lancet_gpu::GenotypeJob> jobs;
+};
+
+void BuildJobs(const lgr_batch_in* in, const char* names, const char* samples, const int* sample_id, const long long* start0,
+               const long long* isize, const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
+               JobSet& js) {
+  for (const char* p = names; (int)js.qn.size() < in->n_reads; p += std::strlen(p) + 1) js.qn.emplace_back(p);
+  int n_samples = 0;
+  for (int r = 0; r < in->n_reads; ++r) n_samples = std::max(n_samples, sample_id[r] + 1);
+  for (const char* p = samples; (int)js.sn.size() < n_samples; p += std::strlen(p) + 1) js.sn.emplace_back(p);
+  js.haps.resize(in->n_haps);
+  for (int h = 0; h < in->n_haps; ++h)
+    js.haps[h].assign(reinterpret_cast<const char*>(in->hap_bases) + in->hap_off[h], (size_t)(in->hap_off[h + 1] - in->hap_off[h]));
+  js.reads.resize(in->n_reads);
+  for (int r = 0; r < in->n_reads; ++r) {
+    const size_t len = (size_t)(in->read_off[r + 1] - in->read_off[r]);
+    js.reads[r] = lancet_gpu::ReadIn{js.qn[r], std::string_view(reinterpret_cast<const char*>(in->read_bases) + in->read_off[r], len),
+                                     in->read_quals + in->read_off[r], js.sn[sample_id[r]], start0[r], isize[r], sam_flag[r],
+                                     mapq[r], softclip[r] != 0};
+  }
+  js.vars.resize(in->n_vars);
+  for (int g = 0; g < in->n_groups; ++g) {
+    const int h0 = in->grp_hap_begin[g], P = in->grp_hap_begin[g + 1] - h0;
+    for (int v = in->grp_var_begin[g]; v < in->grp_var_begin[g + 1]; ++v) {
+      lancet_gpu::VariantIn& vi = js.vars[v];
+      vi.key = &js.vars[v];
+      const long long o = in->var_hap_off[v];
+      vi.local_ref_start0 = (size_t)in->var_start[o], vi.ref_allele_len = (size_t)in->var_len[o];
+      int max_al = 0;
+      for (int h = 1; h < P; ++h) max_al = std::max(max_al, (int)in->var_allele[o + h]);
+      vi.alts.resize(max_al);
+      for (int h = 1; h < P; ++h) {
+        const int al = in->var_allele[o + h];
+        if (al <= 0) continue;
+        vi.alts[al - 1].seq_len = (size_t)in->var_len[o + h];
+        vi.alts[al - 1].hap_start0.emplace_back((size_t)h, (size_t)in->var_start[o + h]);
+      }
+    }
+    js.jobs.push_back(lancet_gpu::GenotypeJob{js.haps.data() + h0, (size_t)P, js.reads.data() + in->grp_read_begin[g],
+                                              (size_t)(in->grp_read_begin[g + 1] - in->grp_read_begin[g]),
+                                              js.vars.data() + in->grp_var_begin[g],
+                                              (size_t)(in->grp_var_begin[g + 1] - in->grp_var_begin[g])});
+  }
+}
+
+std::string DumpResults(const lgr_batch_in* in, const JobSet& js, const std::vector<lancet_gpu::Result>& res) {
+  std::string os;
+  for (int g = 0; g < in->n_groups; ++g) {
+    for (int v = in->grp_var_begin[g]; v < in->grp_var_begin[g + 1]; ++v) {
+      auto it = res[g].find(&js.vars[v]);
+      if (it == res[g].end()) continue;
+      for (const auto& ns : it->second) {
+        const auto& ad = ns.mData->AlleleData();
+        for (std::size_t a = 0; a < ad.size(); ++a) {
+          os += "G" + std::to_string(g) + " V" + std::to_string(v - in->grp_var_begin[g]) + " S" + std::string(ns.mSampleName) +
+                " A" + std::to_string(a) + "|";
+          DumpAllele(os, ad[a]);
+          os += "\n";
+        }
+      }
+    }
+  }
+  return os;
+}
+
+std::uint32_t X31OfView(std::string_view q) { return lgr_x31_hash(std::string(q).c_str()); }
+
+}  // namespace
+
+extern "C" {
+
+// Run GpuGenotyper::GenotypeMany on the batch; dump every (group, variant, sample, allele)
+// evidence block.  names: NUL-separated read names; samples: NUL-separated sample names,
+// sample_id per read.  The name hash is X31 of the name (deterministic stand-in for
+// absl::HashOf in tests).
 int lgr_adapter_genotype_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
                               const int* sample_id, const long long* start0, const long long* isize,
                               const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
                               char* out, long long cap) {
   try {
-    std::vector<std::string_view> qn, sn;
-    for (const char* p = names; (int)qn.size() < in->n_reads; p += std::strlen(p) + 1) qn.emplace_back(p);
-    int n_samples = 0;
-    for (int r = 0; r < in->n_reads; ++r) n_samples = std::max(n_samples, sample_id[r] + 1);
-    for (const char* p = samples; (int)sn.size() < n_samples; p += std::strlen(p) + 1) sn.emplace_back(p);
-    std::vector<std::string> haps(in->n_haps);
-    for (int h = 0; h < in->n_haps; ++h)
-      haps[h].assign(reinterpret_cast<const char*>(in->hap_bases) + in->hap_off[h], (size_t)(in->hap_off[h + 1] - in->hap_off[h]));
-    std::vector<lancet_gpu::ReadIn> reads(in->n_reads);
-    for (int r = 0; r < in->n_reads; ++r) {
-      const size_t len = (size_t)(in->read_off[r + 1] - in->read_off[r]);
-      reads[r] = lancet_gpu::ReadIn{qn[r], std::string_view(reinterpret_cast<const char*>(in->read_bases) + in->read_off[r], len),
-                                    in->read_quals + in->read_off[r], sn[sample_id[r]], start0[r], isize[r], sam_flag[r], mapq[r],
-                                    softclip[r] != 0};
-    }
-    std::vector<lancet_gpu::VariantIn> vars(in->n_vars);
-    std::vector<lancet_gpu::GenotypeJob> jobs;
-    for (int g = 0; g < in->n_groups; ++g) {
-      const int h0 = in->grp_hap_begin[g], P = in->grp_hap_begin[g + 1] - h0;
-      for (int v = in->grp_var_begin[g]; v < in->grp_var_begin[g + 1]; ++v) {
-        lancet_gpu::VariantIn& vi = vars[v];
-        vi.key = &vars[v];
-        const long long o = in->var_hap_off[v];
-        vi.local_ref_start0 = (size_t)in->var_start[o], vi.ref_allele_len = (size_t)in->var_len[o];
-        int max_al = 0;
-        for (int h = 1; h < P; ++h) max_al = std::max(max_al, (int)in->var_allele[o + h]);
-        vi.alts.resize(max_al);
-        for (int h = 1; h < P; ++h) {
-          const int al = in->var_allele[o + h];
-          if (al <= 0) continue;
-          vi.alts[al - 1].seq_len = (size_t)in->var_len[o + h];
-          vi.alts[al - 1].hap_start0.emplace_back((size_t)h, (size_t)in->var_start[o + h]);
-        }
-      }
-      jobs.push_back(lancet_gpu::GenotypeJob{haps.data() + h0, (size_t)P, reads.data() + in->grp_read_begin[g],
-                                             (size_t)(in->grp_read_begin[g + 1] - in->grp_read_begin[g]),
-                                             vars.data() + in->grp_var_begin[g],
-                                             (size_t)(in->grp_var_begin[g + 1] - in->grp_var_begin[g])});
-    }
+    JobSet js;
+    BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
     lancet_gpu::GpuGenotyper gt(device);
-    auto hashfn = [](std::string_view q) { return lgr_x31_hash(std::string(q).c_str()); };
-    std::vector<lancet_gpu::Result> res = gt.GenotypeMany(jobs, hashfn);
-    std::string os;
-    for (int g = 0; g < in->n_groups; ++g) {
-      for (int v = in->grp_var_begin[g]; v < in->grp_var_begin[g + 1]; ++v) {
-        auto it = res[g].find(&vars[v]);
-        if (it == res[g].end()) continue;
-        for (const auto& ns : it->second) {
-          const auto& ad = ns.mData->AlleleData();
-          for (std::size_t a = 0; a < ad.size(); ++a) {
-            os += "G" + std::to_string(g) + " V" + std::to_string(v - in->grp_var_begin[g]) + " S" + std::string(ns.mSampleName) +
-                  " A" + std::to_string(a) + "|";
-            DumpAllele(os, ad[a]);
-            os += "\n";
+    std::vector<lancet_gpu::Result> res = gt.GenotypeMany(js.jobs, X31OfView);
+    return WriteOut(DumpResults(in, js, res), out, cap);
+  } catch (const std::exception& e) {
+    std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
+    return -2;
+  }
+}
+
+// Same batch, but every group is a separate blocking GenotypeBatcher::Genotype() call issued
+// from `n_threads` worker threads (round-robin over the groups, `rounds` times), the way
+// Lancet2's workers would call it.  counters[5] = batches, jobs, pairs, max jobs in one batch,
+// wall nanoseconds of the worker phase.  cap <= 0 skips the dump (timing runs).
+int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
+                             const int* sample_id, const long long* start0, const long long* isize,
+                             const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
+                             int n_threads, int rounds, unsigned long long* counters, char* out, long long cap) {
+  try {
+    JobSet js;
+    BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
+    std::vector<lancet_gpu::Result> res(js.jobs.size());
+    std::vector<std::string> errors((size_t)n_threads);
+    {
+      lancet_gpu::GenotypeBatcher::Options opt;
+      opt.device = device;
+      lancet_gpu::GenotypeBatcher batcher(opt, X31OfView);
+      std::vector<std::thread> workers;
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int t = 0; t < n_threads; ++t) {
+        workers.emplace_back([&, t] {
+          try {
+            for (int round = 0; round < rounds; ++round)
+              for (std::size_t g = (size_t)t; g < js.jobs.size(); g += (size_t)n_threads) {
+                const lancet_gpu::GenotypeJob& j = js.jobs[g];
+                res[g] = batcher.Genotype(j.haps, j.n_haps, j.reads, j.n_reads, j.variants, j.n_variants);
+              }
+          } catch (const std::exception& e) {
+            errors[(size_t)t] = e.what();
           }
-        }
+        });
+      }
+      for (auto& w : workers) w.join();
+      const auto c = batcher.Stats();
+      const auto t1 = std::chrono::steady_clock::now();
+      if (counters) {
+        counters[0] = c.batches, counters[1] = c.jobs, counters[2] = c.pairs, counters[3] = c.max_jobs_in_batch;
+        counters[4] = (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
       }
     }
-    return WriteOut(os, out, cap);
+    for (const auto& e : errors)
+      if (!e.empty()) throw std::runtime_error(e);
+    if (cap <= 0) return 0;
+    return WriteOut(DumpResults(in, js, res), out, cap);
   } catch (const std::exception& e) {
     std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
     return -2;

@@ -2,6 +2,8 @@
 // and AddToTable/AddEvidence in the reference's read order.
 #include "gpu_genotyper.h"
 
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -42,54 +44,80 @@ static void Check(lgr_ctx* ctx, int rc) {
   }
 }
 
-GpuGenotyper::GpuGenotyper(int device_ordinal, const lgr_params* params) {
-  if (params) mParams = *params;
-  else lgr_default_params(&mParams);
-  Check(nullptr, lgr_create(device_ordinal, &mParams, &mCtx));
-}
-
-GpuGenotyper::~GpuGenotyper() { lgr_destroy(mCtx); }
-
-Result GpuGenotyper::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
-                              const VariantIn* variants, std::size_t n_variants, const NameHashFn& name_hash) {
-  std::vector<GenotypeJob> jobs{GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants}};
-  return std::move(GenotypeMany(jobs, name_hash)[0]);
-}
-
-std::vector<Result> GpuGenotyper::GenotypeMany(const std::vector<GenotypeJob>& jobs, const NameHashFn& name_hash) {
-  const int G = static_cast<int>(jobs.size());
-  std::vector<Result> results(jobs.size());
-  if (G == 0) return results;
-  // mm_mapopt_update latches mid_occ from the first index this Genotyper ever builds
-  // (genotyper.cpp:263-266); later haplotypes never refresh it.
-  if (mParams.mid_occ <= 0 && mLatchedMidOcc <= 0) {
-    for (const GenotypeJob& j : jobs) {
-      if (j.n_haps == 0) continue;
-      Check(mCtx, lgr_hap_mid_occ(mCtx, reinterpret_cast<const std::uint8_t*>(j.haps[0].data()),
-                                  static_cast<std::int32_t>(j.haps[0].size()), &mLatchedMidOcc));
-      break;
-    }
+// ---------------------------------------------------------------------------------------------
+// PackedBatch
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+void PackedBatch::Free(Buf<T>& b) {
+  if (b.p) {
+    if (b.pinned) lgr_free_pinned(b.p);
+    else std::free(b.p);
   }
-  // ---- SoA batch ----
-  std::vector<std::int32_t> ghb(G + 1, 0), grb(G + 1, 0), gvb(G + 1, 0), gmid(G, mLatchedMidOcc);
-  std::vector<std::int64_t> hap_off{0}, read_off{0}, var_hap_off{0};
-  std::vector<std::uint8_t> hap_bases, read_bases, read_quals;
-  std::vector<std::uint32_t> x31;
-  std::vector<std::int32_t> var_start, var_len;
-  std::vector<std::int8_t> var_allele;
-  for (int g = 0; g < G; ++g) {
+  b.p = nullptr, b.n = b.cap = 0;
+}
+
+template <typename T>
+void PackedBatch::Reserve(Buf<T>& b, std::size_t n) {
+  if (n <= b.cap) return;
+  std::size_t cap = b.cap ? b.cap : 256;
+  while (cap < n) cap += cap / 2 + 64;
+  bool pinned = true;
+  T* p = static_cast<T*>(lgr_alloc_pinned(cap * sizeof(T)));
+  if (!p) {
+    pinned = false;
+    p = static_cast<T*>(std::malloc(cap * sizeof(T)));
+    if (!p) throw std::bad_alloc();
+  }
+  if (b.n) std::memcpy(p, b.p, b.n * sizeof(T));
+  const std::size_t keep = b.n;
+  Free(b);
+  b.p = p, b.n = keep, b.cap = cap, b.pinned = pinned;
+}
+
+template <typename T>
+void PackedBatch::Push(Buf<T>& b, T v) {
+  if (b.n == b.cap) Reserve(b, b.n + 1);
+  b.p[b.n++] = v;
+}
+
+template <typename T>
+void PackedBatch::Append(Buf<T>& b, const T* src, std::size_t n) {
+  Reserve(b, b.n + n + 1);
+  if (n) std::memcpy(b.p + b.n, src, n * sizeof(T));
+  b.n += n;
+}
+
+PackedBatch::~PackedBatch() {
+  Free(mGhb), Free(mGrb), Free(mGvb), Free(mGmid), Free(mVarStart), Free(mVarLen);
+  Free(mHapOff), Free(mReadOff), Free(mVarHapOff);
+  Free(mHapBases), Free(mReadBases), Free(mReadQuals);
+  Free(mX31), Free(mVarAllele), Free(mAssign);
+}
+
+void PackedBatch::Pack(const GenotypeJob* jobs, std::size_t n_jobs, std::int32_t latched_mid_occ) {
+  for (auto* b : {&mGhb, &mGrb, &mGvb, &mGmid, &mVarStart, &mVarLen}) b->n = 0;
+  for (auto* b : {&mHapOff, &mReadOff, &mVarHapOff}) b->n = 0;
+  for (auto* b : {&mHapBases, &mReadBases, &mReadQuals}) b->n = 0;
+  mX31.n = 0, mVarAllele.n = 0;
+  mJobAsg.clear();
+  Push<std::int32_t>(mGhb, 0), Push<std::int32_t>(mGrb, 0), Push<std::int32_t>(mGvb, 0);
+  Push<std::int64_t>(mHapOff, 0), Push<std::int64_t>(mReadOff, 0), Push<std::int64_t>(mVarHapOff, 0);
+  std::int64_t n_assign = 0;
+  mPairs = 0;
+  std::string qn;
+  for (std::size_t g = 0; g < n_jobs; ++g) {
     const GenotypeJob& j = jobs[g];
     for (std::size_t h = 0; h < j.n_haps; ++h) {
-      hap_bases.insert(hap_bases.end(), j.haps[h].begin(), j.haps[h].end());
-      hap_off.push_back(static_cast<std::int64_t>(hap_bases.size()));
+      Append(mHapBases, reinterpret_cast<const std::uint8_t*>(j.haps[h].data()), j.haps[h].size());
+      Push(mHapOff, static_cast<std::int64_t>(mHapBases.n));
     }
     for (std::size_t r = 0; r < j.n_reads; ++r) {
       const ReadIn& rd = j.reads[r];
-      read_bases.insert(read_bases.end(), rd.seq.begin(), rd.seq.end());
-      read_quals.insert(read_quals.end(), rd.qual, rd.qual + rd.seq.size());
-      read_off.push_back(static_cast<std::int64_t>(read_bases.size()));
-      const std::string qn(rd.qname);  // mm_map receives the NUL-terminated QnamePtr()
-      x31.push_back(lgr_x31_hash(qn.c_str()));
+      Append(mReadBases, reinterpret_cast<const std::uint8_t*>(rd.seq.data()), rd.seq.size());
+      Append(mReadQuals, rd.qual, rd.seq.size());
+      Push(mReadOff, static_cast<std::int64_t>(mReadBases.n));
+      qn.assign(rd.qname);  // mm_map receives the NUL-terminated QnamePtr()
+      Push(mX31, lgr_x31_hash(qn.c_str()));
     }
     for (std::size_t v = 0; v < j.n_variants; ++v) {
       const VariantIn& var = j.variants[v];
@@ -107,66 +135,227 @@ std::vector<Result> GpuGenotyper::GenotypeMany(const std::vector<GenotypeJob>& j
                 break;
               }
         }
-        var_start.push_back(st), var_len.push_back(ln), var_allele.push_back(al);
+        Push(mVarStart, st), Push(mVarLen, ln), Push(mVarAllele, al);
       }
-      var_hap_off.push_back(static_cast<std::int64_t>(var_start.size()));
+      Push(mVarHapOff, static_cast<std::int64_t>(mVarStart.n));
     }
-    ghb[g + 1] = ghb[g] + static_cast<std::int32_t>(j.n_haps);
-    grb[g + 1] = grb[g] + static_cast<std::int32_t>(j.n_reads);
-    gvb[g + 1] = gvb[g] + static_cast<std::int32_t>(j.n_variants);
+    Push(mGhb, mGhb.p[g] + static_cast<std::int32_t>(j.n_haps));
+    Push(mGrb, mGrb.p[g] + static_cast<std::int32_t>(j.n_reads));
+    Push(mGvb, mGvb.p[g] + static_cast<std::int32_t>(j.n_variants));
+    Push(mGmid, latched_mid_occ);
+    mJobAsg.push_back(n_assign);
+    n_assign += static_cast<std::int64_t>(j.n_reads) * static_cast<std::int64_t>(j.n_variants);
+    mPairs += static_cast<std::int64_t>(j.n_reads) * static_cast<std::int64_t>(j.n_haps);
   }
-  // keep pointers valid for empty vectors
-  hap_bases.push_back(0), read_bases.push_back(0), read_quals.push_back(0), x31.push_back(0);
-  var_start.push_back(0), var_len.push_back(0), var_allele.push_back(0);
-  lgr_batch_in in;
-  std::memset(&in, 0, sizeof(in));
-  in.n_groups = G, in.n_haps = ghb[G], in.n_reads = grb[G], in.n_vars = gvb[G];
-  in.grp_hap_begin = ghb.data(), in.grp_read_begin = grb.data(), in.grp_var_begin = gvb.data();
-  in.hap_off = hap_off.data(), in.hap_bases = hap_bases.data();
-  in.read_off = read_off.data(), in.read_bases = read_bases.data(), in.read_quals = read_quals.data();
-  in.read_name_hash = x31.data();
-  in.var_hap_off = var_hap_off.data(), in.var_start = var_start.data(), in.var_len = var_len.data();
-  in.var_allele = var_allele.data();
-  in.grp_mid_occ = mLatchedMidOcc > 0 ? gmid.data() : nullptr;
-  std::vector<std::int64_t> pair_off(in.n_reads + 1), asg_off(in.n_reads + 1);
-  Check(mCtx, lgr_pair_offsets(&in, pair_off.data(), asg_off.data()));
-  std::vector<lgr_assign> assign(static_cast<std::size_t>(asg_off[in.n_reads]) + 1);
-  lgr_batch_out out;
-  std::memset(&out, 0, sizeof(out));
-  out.n_assign = asg_off[in.n_reads];
-  out.assign = assign.data();  // out.aln stays NULL: the adapter only needs the assignments
-  Check(mCtx, lgr_genotype_batch(mCtx, &in, &out, &mStats));
-  // ---- AddToTable (genotyper.cpp:423-456), reads in the caller's order ----
-  for (int g = 0; g < G; ++g) {
-    const GenotypeJob& j = jobs[g];
-    Result& table = results[g];
-    for (std::size_t r = 0; r < j.n_reads; ++r) {
-      const ReadIn& rd = j.reads[r];
-      const std::int64_t base = asg_off[grb[g] + static_cast<std::int64_t>(r)];
-      std::uint32_t rname_hash = 0;
-      bool hashed = false;
-      for (std::size_t v = 0; v < j.n_variants; ++v) {
-        const lgr_assign& a = assign[static_cast<std::size_t>(base) + v];
-        if (!a.assigned) continue;
-        if (!hashed) rname_hash = name_hash(rd.qname), hashed = true;
-        VariantSupport& support = table[j.variants[v].key].FindOrCreate(rd.sample_name);
-        ReadEvidence ev;
-        ev.mInsertSize = rd.insert_size;
-        ev.mAlignmentStart = rd.start0;
-        ev.mAlnScore = static_cast<double>(a.global_score) + (a.local_score * a.local_identity);  // CombinedScore()
-        ev.mFoldedReadPos = a.folded_read_pos;
-        ev.mRnameHash = rname_hash;
-        ev.mRefNm = a.ref_nm, ev.mOwnHapNm = a.own_hap_nm, ev.mAssignedHaplotypeId = a.hap_id;
-        ev.mAllele = static_cast<AlleleIndex>(a.allele);
-        ev.mStrand = (rd.sam_flag & 0x10) ? Strand::REV : Strand::FWD;
-        ev.mBaseQual = a.base_qual, ev.mMapQual = rd.map_qual;
-        ev.mIsSoftClipped = rd.is_soft_clipped;
-        ev.mIsProperPair = (rd.sam_flag & 0x2) != 0;
-        support.AddEvidence(ev);
-      }
+  // keep every pointer valid for empty arrays
+  Reserve(mHapBases, mHapBases.n + 1), Reserve(mReadBases, mReadBases.n + 1), Reserve(mReadQuals, mReadQuals.n + 1);
+  Reserve(mX31, mX31.n + 1), Reserve(mVarStart, mVarStart.n + 1), Reserve(mVarLen, mVarLen.n + 1);
+  Reserve(mVarAllele, mVarAllele.n + 1), Reserve(mGmid, mGmid.n + 1);
+  Reserve(mAssign, static_cast<std::size_t>(n_assign) + 1);
+  mAssign.n = static_cast<std::size_t>(n_assign);
+  const int G = static_cast<int>(n_jobs);
+  std::memset(&mIn, 0, sizeof(mIn));
+  mIn.n_groups = G, mIn.n_haps = mGhb.p[G], mIn.n_reads = mGrb.p[G], mIn.n_vars = mGvb.p[G];
+  mIn.grp_hap_begin = mGhb.p, mIn.grp_read_begin = mGrb.p, mIn.grp_var_begin = mGvb.p;
+  mIn.hap_off = mHapOff.p, mIn.hap_bases = mHapBases.p;
+  mIn.read_off = mReadOff.p, mIn.read_bases = mReadBases.p, mIn.read_quals = mReadQuals.p;
+  mIn.read_name_hash = mX31.p;
+  mIn.var_hap_off = mVarHapOff.p, mIn.var_start = mVarStart.p, mIn.var_len = mVarLen.p, mIn.var_allele = mVarAllele.p;
+  mIn.grp_mid_occ = latched_mid_occ > 0 ? mGmid.p : nullptr;
+  std::memset(&mOut, 0, sizeof(mOut));
+  mOut.n_assign = n_assign;
+  mOut.assign = mAssign.p;  // out.aln stays NULL: the adapter only needs the assignments
+}
+
+Result PackedBatch::BuildResult(const GenotypeJob& j, const lgr_assign* assign, const NameHashFn& name_hash) {
+  Result table;
+  for (std::size_t r = 0; r < j.n_reads; ++r) {
+    const ReadIn& rd = j.reads[r];
+    std::uint32_t rname_hash = 0;
+    bool hashed = false;
+    for (std::size_t v = 0; v < j.n_variants; ++v) {
+      const lgr_assign& a = assign[r * j.n_variants + v];
+      if (!a.assigned) continue;
+      if (!hashed) rname_hash = name_hash(rd.qname), hashed = true;
+      VariantSupport& support = table[j.variants[v].key].FindOrCreate(rd.sample_name);
+      ReadEvidence ev;
+      ev.mInsertSize = rd.insert_size;
+      ev.mAlignmentStart = rd.start0;
+      ev.mAlnScore = static_cast<double>(a.global_score) + (a.local_score * a.local_identity);  // CombinedScore()
+      ev.mFoldedReadPos = a.folded_read_pos;
+      ev.mRnameHash = rname_hash;
+      ev.mRefNm = a.ref_nm, ev.mOwnHapNm = a.own_hap_nm, ev.mAssignedHaplotypeId = a.hap_id;
+      ev.mAllele = static_cast<AlleleIndex>(a.allele);
+      ev.mStrand = (rd.sam_flag & 0x10) ? Strand::REV : Strand::FWD;
+      ev.mBaseQual = a.base_qual, ev.mMapQual = rd.map_qual;
+      ev.mIsSoftClipped = rd.is_soft_clipped;
+      ev.mIsProperPair = (rd.sam_flag & 0x2) != 0;
+      support.AddEvidence(ev);
     }
   }
+  return table;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GpuGenotyper
+// ---------------------------------------------------------------------------------------------
+GpuGenotyper::GpuGenotyper(int device_ordinal, const lgr_params* params) {
+  if (params) mParams = *params;
+  else lgr_default_params(&mParams);
+  Check(nullptr, lgr_create(device_ordinal, &mParams, &mCtx));
+  mBatch = std::make_unique<PackedBatch>();
+}
+
+GpuGenotyper::~GpuGenotyper() {
+  mBatch.reset();
+  lgr_destroy(mCtx);
+}
+
+Result GpuGenotyper::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
+                              const VariantIn* variants, std::size_t n_variants, const NameHashFn& name_hash) {
+  std::vector<GenotypeJob> jobs{GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants}};
+  return std::move(GenotypeMany(jobs, name_hash)[0]);
+}
+
+// mm_mapopt_update latches mid_occ from the first index a Genotyper ever builds
+// (genotyper.cpp:263-266); later haplotypes never refresh it.
+static void LatchMidOcc(lgr_ctx* ctx, const lgr_params& prm, const GenotypeJob* jobs, std::size_t n, std::int32_t* latched) {
+  if (prm.mid_occ > 0 || *latched > 0) return;
+  for (std::size_t i = 0; i < n; ++i) {
+    if (jobs[i].n_haps == 0) continue;
+    Check(ctx, lgr_hap_mid_occ(ctx, reinterpret_cast<const std::uint8_t*>(jobs[i].haps[0].data()),
+                               static_cast<std::int32_t>(jobs[i].haps[0].size()), latched));
+    return;
+  }
+}
+
+std::vector<Result> GpuGenotyper::GenotypeMany(const std::vector<GenotypeJob>& jobs, const NameHashFn& name_hash) {
+  std::vector<Result> results(jobs.size());
+  if (jobs.empty()) return results;
+  LatchMidOcc(mCtx, mParams, jobs.data(), jobs.size(), &mLatchedMidOcc);
+  mBatch->Pack(jobs.data(), jobs.size(), mLatchedMidOcc);
+  Check(mCtx, lgr_genotype_batch(mCtx, &mBatch->In(), &mBatch->Out(), &mStats));
+  for (std::size_t g = 0; g < jobs.size(); ++g) results[g] = PackedBatch::BuildResult(jobs[g], mBatch->JobAssign(g), name_hash);
   return results;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GenotypeBatcher
+// ---------------------------------------------------------------------------------------------
+GenotypeBatcher::GenotypeBatcher(const Options& opt, NameHashFn name_hash) : mOpt(opt), mNameHash(std::move(name_hash)) {
+  if (mOpt.depth < 1) mOpt.depth = 1;
+  if (mOpt.depth > LGR_MAX_INFLIGHT) mOpt.depth = LGR_MAX_INFLIGHT;
+  if (opt.params) mParams = *opt.params;
+  else lgr_default_params(&mParams);
+  mOpt.params = nullptr;
+  Check(nullptr, lgr_create(mOpt.device, &mParams, &mCtx));
+  for (int i = 0; i < mOpt.depth; ++i) mSlots.push_back(std::make_unique<Slot>());
+  mThread = std::thread([this] { Run(); });
+}
+
+GenotypeBatcher::~GenotypeBatcher() {
+  {
+    std::lock_guard<std::mutex> lk(mMu);
+    mStop = true;
+  }
+  mCv.notify_all();
+  if (mThread.joinable()) mThread.join();
+  mSlots.clear();
+  lgr_destroy(mCtx);
+}
+
+Result GenotypeBatcher::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
+                                 const VariantIn* variants, std::size_t n_variants) {
+  Pending p;
+  p.job = GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants};
+  std::future<std::vector<lgr_assign>> fut = p.done.get_future();
+  {
+    std::lock_guard<std::mutex> lk(mMu);
+    if (mStop) throw std::runtime_error("lancet_gpu::GenotypeBatcher: shut down");
+    mQueue.push_back(std::move(p));
+  }
+  mCv.notify_all();
+  const std::vector<lgr_assign> assign = fut.get();  // rethrows a device error on this worker
+  // AddToTable on the calling worker: the serial batcher thread only moves bytes
+  return PackedBatch::BuildResult(GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants}, assign.data(), mNameHash);
+}
+
+GenotypeBatcher::Counters GenotypeBatcher::Stats() {
+  std::lock_guard<std::mutex> lk(mMu);
+  return mCounters;
+}
+
+void GenotypeBatcher::Complete(Slot& s) {
+  std::exception_ptr err;
+  try {
+    Check(mCtx, lgr_wait(mCtx, s.ticket, nullptr));
+  } catch (...) {
+    err = std::current_exception();
+  }
+  s.ticket = -1;
+  for (std::size_t j = 0; j < s.jobs.size(); ++j) {
+    Pending& p = s.jobs[j];
+    if (err) {
+      p.done.set_exception(err);
+      continue;
+    }
+    const lgr_assign* a = s.pb.JobAssign(j);
+    p.done.set_value(std::vector<lgr_assign>(a, a + p.job.n_reads * p.job.n_variants));
+  }
+  s.jobs.clear();
+}
+
+void GenotypeBatcher::Run() {
+  std::size_t head = 0, tail = 0, inflight = 0;  // slots [tail, head) hold submitted batches
+  for (;;) {
+    std::vector<Pending> take;
+    {
+      std::unique_lock<std::mutex> lk(mMu);
+      if (inflight == 0) {
+        mCv.wait(lk, [&] { return mStop || !mQueue.empty(); });
+        if (mQueue.empty()) break;  // stop requested and nothing left
+        // the GPU is idle: give the other workers a moment to arrive so they share the launch
+        if (mOpt.linger_us > 0 && !mStop)
+          mCv.wait_for(lk, std::chrono::microseconds(mOpt.linger_us), [&] { return mStop || mQueue.size() >= mOpt.max_jobs; });
+      }
+      std::int64_t pairs = 0;
+      while (!mQueue.empty() && take.size() < mOpt.max_jobs) {
+        const GenotypeJob& j = mQueue.front().job;
+        const std::int64_t p = static_cast<std::int64_t>(j.n_reads) * static_cast<std::int64_t>(j.n_haps);
+        if (!take.empty() && pairs + p > mOpt.max_pairs) break;
+        pairs += p;
+        take.push_back(std::move(mQueue.front()));
+        mQueue.pop_front();
+      }
+      if (!take.empty()) {
+        mCounters.batches += 1, mCounters.jobs += take.size(), mCounters.pairs += static_cast<std::uint64_t>(pairs);
+        if (take.size() > mCounters.max_jobs_in_batch) mCounters.max_jobs_in_batch = take.size();
+      }
+    }
+    if (take.empty()) {  // nothing new to pack: hand the oldest batch back as soon as it is done
+      Complete(*mSlots[tail % mSlots.size()]);
+      ++tail, --inflight;
+      continue;
+    }
+    if (inflight == mSlots.size()) {
+      Complete(*mSlots[tail % mSlots.size()]);
+      ++tail, --inflight;
+    }
+    Slot& s = *mSlots[head % mSlots.size()];
+    s.jobs = std::move(take);
+    try {
+      std::vector<GenotypeJob> jobs;
+      jobs.reserve(s.jobs.size());
+      for (const Pending& p : s.jobs) jobs.push_back(p.job);
+      LatchMidOcc(mCtx, mParams, jobs.data(), jobs.size(), &mLatchedMidOcc);
+      s.pb.Pack(jobs.data(), jobs.size(), mLatchedMidOcc);
+      Check(mCtx, lgr_submit(mCtx, &s.pb.In(), &s.pb.Out(), &s.ticket));
+      ++head, ++inflight;
+    } catch (...) {
+      for (Pending& p : s.jobs) p.done.set_exception(std::current_exception());
+      s.jobs.clear();
+    }
+  }
 }
 
 }  // namespace lancet_gpu

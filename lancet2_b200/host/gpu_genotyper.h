@@ -18,11 +18,16 @@
 #ifndef LANCET2_B200_HOST_GPU_GENOTYPER_H_
 #define LANCET2_B200_HOST_GPU_GENOTYPER_H_
 
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
 #include <functional>
+#include <future>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -118,6 +123,47 @@ struct GenotypeJob {
   std::size_t n_variants;
 };
 
+// SoA staging of many GenotypeJobs in the C-ABI's layout (pinned host memory when available) and
+// the host half of the path: AddToTable from the returned lgr_assign records.
+class PackedBatch {
+ public:
+  PackedBatch() = default;
+  ~PackedBatch();
+  PackedBatch(const PackedBatch&) = delete;
+  PackedBatch& operator=(const PackedBatch&) = delete;
+  // ResetData's inputs + ExtractHapBounds' dense table for every job (genotyper.cpp:243-267, 329-352)
+  void Pack(const GenotypeJob* jobs, std::size_t n_jobs, std::int32_t latched_mid_occ);
+  [[nodiscard]] const lgr_batch_in& In() const noexcept { return mIn; }
+  [[nodiscard]] lgr_batch_out& Out() noexcept { return mOut; }
+  [[nodiscard]] std::int64_t Pairs() const noexcept { return mPairs; }
+  // the lgr_assign records of job j ([read][variant], n_reads * n_variants of them)
+  [[nodiscard]] const lgr_assign* JobAssign(std::size_t j) const noexcept { return mAssign.p + mJobAsg[j]; }
+  // AddToTable (genotyper.cpp:423-456) for one job, reads in the caller's order
+  static Result BuildResult(const GenotypeJob& job, const lgr_assign* assign, const NameHashFn& name_hash);
+
+ private:
+  template <typename T>
+  struct Buf {  // grow-only; lgr_alloc_pinned with a malloc fallback
+    T* p = nullptr;
+    std::size_t n = 0, cap = 0;
+    bool pinned = false;
+  };
+  template <typename T> static void Reserve(Buf<T>& b, std::size_t n);
+  template <typename T> static void Push(Buf<T>& b, T v);
+  template <typename T> static void Append(Buf<T>& b, const T* src, std::size_t n);
+  template <typename T> static void Free(Buf<T>& b);
+  Buf<std::int32_t> mGhb, mGrb, mGvb, mGmid, mVarStart, mVarLen;
+  Buf<std::int64_t> mHapOff, mReadOff, mVarHapOff;
+  Buf<std::uint8_t> mHapBases, mReadBases, mReadQuals;
+  Buf<std::uint32_t> mX31;
+  Buf<std::int8_t> mVarAllele;
+  Buf<lgr_assign> mAssign;
+  std::vector<std::int64_t> mJobAsg;
+  lgr_batch_in mIn{};
+  lgr_batch_out mOut{};
+  std::int64_t mPairs = 0;
+};
+
 class GpuGenotyper {
  public:
   explicit GpuGenotyper(int device_ordinal = 0, const lgr_params* params = nullptr);
@@ -139,6 +185,63 @@ class GpuGenotyper {
   lgr_params mParams;
   std::int32_t mLatchedMidOcc = 0;  // mm_mapopt_update latches mid_occ from the first index it sees
   lgr_stats mStats{};
+  std::unique_ptr<PackedBatch> mBatch;
+};
+
+// Cross-thread batcher: the reference runs one Genotyper per worker thread
+// (core/variant_builder.h:94, core/pipeline_executor.cpp:174-197) and each Genotype() call
+// carries only ~10^3-10^4 pairs.  One GenotypeBatcher per GPU lets all workers share the device:
+// Genotype() has the reference's blocking call shape, but the payloads of every thread that is
+// waiting at that moment travel in ONE device batch (lgr_submit), up to `depth` batches in
+// flight so that packing/H2D of one overlaps the kernels of another; AddToTable runs on the
+// calling worker when its slice of the assignments is back.
+class GenotypeBatcher {
+ public:
+  struct Options {
+    int device = 0;
+    int depth = 3;                       // batches in flight (<= LGR_MAX_INFLIGHT)
+    std::int64_t max_pairs = 1 << 21;    // (read, haplotype) pairs per device batch
+    std::size_t max_jobs = 8192;         // Genotype() payloads per device batch
+    int linger_us = 100;                 // idle GPU: wait this long for more workers to arrive before launching
+    const lgr_params* params = nullptr;
+  };
+  struct Counters {
+    std::uint64_t batches = 0, jobs = 0, pairs = 0, max_jobs_in_batch = 0;
+  };
+  GenotypeBatcher(const Options& opt, NameHashFn name_hash);
+  ~GenotypeBatcher();  // drains what is queued, then joins
+  GenotypeBatcher(const GenotypeBatcher&) = delete;
+  GenotypeBatcher& operator=(const GenotypeBatcher&) = delete;
+
+  // thread-safe drop-in for Genotyper::Genotype (genotyper.cpp:224-235); blocks the calling worker
+  [[nodiscard]] Result Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
+                                const VariantIn* variants, std::size_t n_variants);
+  [[nodiscard]] Counters Stats();
+
+ private:
+  struct Pending {
+    GenotypeJob job;
+    std::promise<std::vector<lgr_assign>> done;
+  };
+  struct Slot {
+    PackedBatch pb;
+    std::vector<Pending> jobs;
+    lgr_ticket ticket = -1;
+  };
+  void Run();
+  void Complete(Slot& s);
+  Options mOpt;
+  NameHashFn mNameHash;
+  lgr_ctx* mCtx = nullptr;
+  lgr_params mParams;
+  std::int32_t mLatchedMidOcc = 0;
+  std::mutex mMu;
+  std::condition_variable mCv;
+  std::deque<Pending> mQueue;
+  bool mStop = false;
+  Counters mCounters;
+  std::vector<std::unique_ptr<Slot>> mSlots;
+  std::thread mThread;
 };
 
 }  // namespace lancet_gpu

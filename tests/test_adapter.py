@@ -30,6 +30,9 @@ def lib():
     lb.lgr_adapter_genotype_dump.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + \
         [C.c_void_p] * 6 + [C.c_char_p, C.c_longlong]
     lb.lgr_adapter_genotype_dump.restype = C.c_int
+    lb.lgr_adapter_batcher_dump.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + \
+        [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
+    lb.lgr_adapter_batcher_dump.restype = C.c_int
     return lb
 
 
@@ -107,3 +110,37 @@ def test_adapter_genotype_matches_oracle_evidence(lib):
                     expect.append(f"G{g_i} V{v} S{snames[s]} {al}|{rest}")
     assert len(got) == len(expect) and len(got) > 10
     assert got == expect
+
+
+@pytest.mark.gpu
+def test_cross_thread_batcher_equals_synchronous_adapter(lib):
+    """GenotypeBatcher: every group issued as its own blocking Genotype() call from
+    8 worker threads must give exactly the evidence the one-shot GenotypeMany gives, and the
+    calls must actually have shared device batches."""
+    rng = np.random.default_rng(11)
+    groups = synth.make_region_groups(5, ref_len=60_000)[:24] + synth.make_groups(8, 8, n_reads=96, n_haps=4, hap_len=800)
+    batch = abi.Batch(groups)
+    nr = batch.n_reads
+    names = [nm for g in groups for nm in g.names]
+    sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
+    start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
+    isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
+    flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
+    mapq = rng.integers(0, 61, nr).astype(np.uint8)
+    softclip = rng.integers(0, 2, nr).astype(np.uint8)
+    bi = batch.c_struct()
+    nm_blob = b"\0".join(x.encode() for x in names) + b"\0"
+    args = (sample_id.ctypes.data, start0.ctypes.data, isize.ctypes.data, flag.ctypes.data, mapq.ctypes.data, softclip.ctypes.data)
+    buf1 = C.create_string_buffer(64 << 20)
+    n1 = lib.lgr_adapter_genotype_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, buf1, len(buf1))
+    assert n1 > 0, buf1.value.decode()
+    buf2 = C.create_string_buffer(64 << 20)
+    counters = np.zeros(5, dtype=np.uint64)
+    rounds = 3
+    n2 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 8, rounds, counters.ctypes.data,
+                                      buf2, len(buf2))
+    assert n2 > 0, buf2.value.decode()
+    assert buf2.value == buf1.value
+    batches, jobs, pairs, max_jobs = (int(x) for x in counters[:4])
+    assert jobs == rounds * len(groups) and pairs == rounds * batch.n_pairs
+    assert batches < jobs and max_jobs > 1, (batches, jobs, max_jobs)  # calls were coalesced
