@@ -509,6 +509,7 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
   const int q = P.q, e = P.e;
+  const int32_t sc_match = P.a, sc_mis = -P.b, sc_amb = -P.sc_ambi;  // in registers: the loop's generic stores could alias P
   const int m = reg->ext[side].m, n = reg->ext[side].n;
   const int T = prune_cols(P, m, n);
   const bool right = side == 0;
@@ -559,7 +560,7 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
         const int32_t up_h = (int32_t)(int16_t)(up_hf & 0xffff);
         const int32_t up_f = up_hf >> 16;
         if (row_ok && i >= 0 && i < T) {
-          const int32_t sc = (tc > 3 || qc > 3) ? -P.sc_ambi : (tc == qc ? P.a : -P.b);
+          const int32_t sc = (tc > 3 || qc > 3) ? sc_amb : (tc == qc ? sc_match : sc_mis);
           uint8_t d;
           int32_t en, fn;
           const int32_t h = ext_cell(diag + sc, e_cur, up_f, q, e, right, &d, &en, &fn);
@@ -578,17 +579,64 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
   ezmax = __reduce_max_sync(full, ezmax);
   mqe_t = __shfl_sync(full, mqe_t, (m - 1) & 31);
   __syncwarp();
-  if (lane == 0) {
-    ExtRec& E = reg->ext[side];
-    E.max = ezmax;
-    E.mqe_t = mqe_t;
-    CigBuf cb{wcig, 0, D.wcig_cap};
-    auto dirf = [&](int i, int j) -> uint8_t {
+  // ksw_backtrack, warp-cooperative: the path mostly runs down the diagonal, so the 32 lanes
+  // fetch the direction bytes of the next 32 diagonal cells in one go and the (warp-uniform)
+  // state machine walks them by shuffle; a gap step leaves the diagonal and refetches.  One
+  // memory round trip per <= 32 steps instead of one per step (the bytes of a long tail sit in L2).
+  // Runs of equal ops are counted in registers and pushed once (same result as ksw_push_cigar).
+  CigBuf cb{wcig, 0, D.wcig_cap};
+  {
+    auto dirf = [&](int i, int j) -> uint32_t {
       const int b = j >> 5, l = j & 31;
       const int rows = m - b * 32 < 32 ? m - b * 32 : 32;
       return dir[(size_t)b * 32 * (T + 31) + (size_t)(i + l) * rows + l];
     };
-    ext_backtrack(dirf, m, mqe_t, side == 0, cb);
+    int i = mqe_t, j = m - 1, state = 0;
+    uint32_t run_op = 0;
+    int run_len = 0;
+    auto emit = [&](uint32_t op) {
+      if (run_len > 0 && op == run_op) {
+        ++run_len;
+      } else {
+        if (run_len > 0 && lane == 0) cb.push(run_op, run_len);
+        run_op = op, run_len = 1;
+      }
+    };
+    while (i >= 0 && j >= 0) {
+      const int wi = i - lane, wj = j - lane;
+      const uint32_t dv = (wi >= 0 && wj >= 0) ? dirf(wi, wj) : 0u;
+      for (int k = 0; k < 32; ++k) {
+        const uint32_t tmp = __shfl_sync(full, dv, k);
+        if (state == 0) state = tmp & 7;
+        else if (!(tmp >> (state + 2) & 1)) state = 0;
+        if (state == 0) state = tmp & 7;
+        if (state == 0) {
+          emit(0), --i, --j;
+          if (i < 0 || j < 0) break;
+        } else {
+          if (state == 1) emit(2), --i;
+          else emit(1), --j;
+          break;  // off this diagonal
+        }
+      }
+    }
+    if (lane == 0) {
+      if (run_len > 0) cb.push(run_op, run_len);
+      if (i >= 0) cb.push(2, i + 1);
+      if (j >= 0) cb.push(1, j + 1);
+      if (side != 0 && cb.n <= cb.cap) {  // right extension: ksw2 reverses the backtrack order
+        for (int a = 0; a < cb.n >> 1; ++a) {
+          const uint32_t t = cb.ops[a];
+          cb.ops[a] = cb.ops[cb.n - 1 - a];
+          cb.ops[cb.n - 1 - a] = t;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    ExtRec& E = reg->ext[side];
+    E.max = ezmax;
+    E.mqe_t = mqe_t;
     E.n_cig = cb.n;
     if (cb.n > D.wcig_cap) {
       atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
@@ -1490,6 +1538,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
   }
 }
 
+#ifdef LGR_EXT_HIST
+__device__ unsigned long long g_ext_hist[256];  // [m] task count, [128 + m] warp cycles (debug builds only)
+#endif
+
 // Phase B1 kernel: the extensions no closed form covered, one warp per queued extension, through
 // the anti-diagonal wavefront.  Nothing but DP code lives here, so resident warps share one hot loop.
 constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
@@ -1516,8 +1568,19 @@ __global__ void __launch_bounds__(128, LGR_EXT_MINB) k_ext_warp(const __grid_con
     const int64_t roff = D.read_off[tk.read];
     ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
     long long c1 = 0, c2 = 0;
+#ifdef LGR_EXT_HIST
+    const long long t_begin = clock64();
+#endif
     ext_dp_warp(D, &D.regs[tk.reg], tk.side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig,
                 &c1, &c2);
+#ifdef LGR_EXT_HIST
+    if (lane == 0) {
+      int mb = D.regs[tk.reg].ext[tk.side].m;
+      mb = mb > 127 ? 127 : mb;
+      atomicAdd(&g_ext_hist[mb], 1ULL);
+      atomicAdd(&g_ext_hist[128 + mb], (unsigned long long)(clock64() - t_begin));
+    }
+#endif
     cells += c1, cells_full += c2;
     __syncwarp();
   }
@@ -1837,6 +1900,17 @@ void lgr_destroy(lgr_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
+
+#ifdef LGR_EXT_HIST
+int lgr_debug_ext_hist(unsigned long long* out256, int reset) {
+  if (cudaMemcpyFromSymbol(out256, g_ext_hist, sizeof(unsigned long long) * 256) != cudaSuccess) return LGR_E_CUDA;
+  if (reset) {
+    static const unsigned long long zero[256] = {};
+    cudaMemcpyToSymbol(g_ext_hist, zero, sizeof(zero));
+  }
+  return LGR_OK;
+}
+#endif
 
 void* lgr_alloc_pinned(size_t bytes) {
   void* p = nullptr;
