@@ -502,6 +502,8 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
 // coalesced 32-byte store.  Same recurrences, tie rules and column pruning as ext_dp_scalar.
 // All 32 lanes must call it; results are written by lane 0 into reg->ext[side].
 // ---------------------------------------------------------------------------------------
+constexpr int kDynPruneMinRows = 12;  // shorter tails: the static bound is already small, skip the extra pass
+
 __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, const ReadView& rv, const uint8_t* hapc,
                                          uint8_t* dir_g, uint8_t* dir_s, int dir_s_cap, int32_t* Hb, int32_t* Fb, uint32_t* wcig,
                                          long long* cells, long long* cells_full) {
@@ -511,10 +513,52 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
   const int q = P.q, e = P.e;
   const int32_t sc_match = P.a, sc_mis = -P.b, sc_amb = -P.sc_ambi;  // in registers: the loop's generic stores could alias P
   const int m = reg->ext[side].m, n = reg->ext[side].n;
-  const int T = prune_cols(P, m, n);
+  int T = prune_cols(P, m, n);
   const bool right = side == 0;
   ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
   ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
+  // Data-dependent column bound (exact).  Any path ending in the last query row at target column
+  // i = m-1+d (d > 0) deletes at least d target bases: its score is <= a*m - q - e*d, and every
+  // cell at or beyond that column is bounded the same way.  If LB is the score of SOME path that
+  // ends in the last row at an earlier column, columns with a*m - q - e*d <= LB can hold neither
+  // the first maximum of the last row nor the global maximum, and the traceback never enters
+  // them (cells only depend on smaller columns).  prune_cols uses the worst case LB = -b*m;
+  // here every lane scores one concrete family of paths — the main diagonal for p bases, one
+  // gap of delta = lane-15 (deletion > 0, insertion < 0), then the shifted diagonal — and the
+  // warp keeps the best, which for a tail that crosses an indel is close to the optimum.
+  if (n >= m && P.e > 0 && m >= kDynPruneMinRows && 2 * m + 32 <= dir_s_cap) {
+    // stage the m query codes and the first m+16 target codes in the warp's shared-memory slice
+    // (free until the direction bytes are written) so that the 32 lanes read bytes, not functors
+    uint8_t* sq = dir_s;
+    uint8_t* st = dir_s + m;
+    const int nt = m + 16 < n ? m + 16 : n;
+    for (int x = lane; x < m; x += 32) sq[x] = (uint8_t)qf(x);
+    for (int x = lane; x < nt; x += 32) st[x] = (uint8_t)tf(x);
+    __syncwarp();
+    const int delta = lane - 15;
+    int32_t lb = kNegInf;
+    if (delta >= 0 ? m + delta <= n : -delta < m) {
+      const int k = delta < 0 ? -delta : 0;  // inserted query bases
+      const uint8_t* t0 = st;
+      const uint8_t* t1 = st + (delta > 0 ? delta : 0);
+      const uint8_t* q1 = sq + k;
+      int32_t p0 = 0, ps = 0, best = 0;      // P0[p], shifted prefix, max(P0 - shifted)
+      const int steps = m - k;
+      for (int p = 0; p < steps; ++p) {
+        const int tcp = t0[p], tcs = t1[p], qcp = sq[p], qcs = q1[p];
+        p0 += (tcp > 3 || qcp > 3) ? sc_amb : (tcp == qcp ? sc_match : sc_mis);
+        ps += (tcs > 3 || qcs > 3) ? sc_amb : (tcs == qcs ? sc_match : sc_mis);
+        const int32_t dlt = p0 - ps;
+        if (dlt > best) best = dlt;
+      }
+      lb = best + ps - (delta != 0 ? q + e * (delta < 0 ? -delta : delta) : 0);
+    }
+    lb = __reduce_max_sync(full, lb);
+    const int X = P.a * m - q - lb;
+    const int Dd = X <= 0 ? 0 : X / e;
+    if (m + Dd < T) T = m + Dd;
+    __syncwarp();  // the staging bytes are dead from here on; the slice becomes direction storage
+  }
   const int nblk = (m + 31) >> 5;
   // direction bytes: block b holds rows [32b, 32b+rows_b) as [step][row]; shared memory when the
   // whole matrix fits the warp's slice, else the HBM scratch
