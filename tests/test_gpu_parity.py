@@ -208,3 +208,62 @@ def test_alphabet_quality_and_size_edges(gpu):
     assert not errs, "\n".join(errs[:20])
     assert got.aln[0]["valid"] == 1 and got.aln[0]["nm"] == 0      # lower case read == upper case haplotype
     assert got.aln[int(batch.pair_off[4])]["valid"] == 0            # 5 bp read: no minimizer
+
+
+def _params(**kw):
+    p = O.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+OPTION_SETS = {
+    # other minimizer geometry: even k takes the lane-per-haplotype sketch (symmetric k-mers are
+    # skipped), w != 5 the ring-buffer sketch, k = 15 the 64-bit window
+    "k12w5": dict(k=12, w=5),
+    "k15w10": dict(k=15, w=10),
+    "k9w3": dict(k=9, w=3),
+    # other scoring: minimap2's own sr preset values and a cheap-gap set
+    "sr_preset_scores": dict(a=2, b=8, q=12, e=2, end_bonus=20000),
+    "cheap_gaps": dict(a=1, b=2, q=3, e=1),
+    # chaining knobs
+    "chain_knobs": dict(max_chain_skip=5, max_chain_iter=50, min_cnt=2, min_chain_score=25, max_gap=100),
+    "fixed_mid_occ": dict(mid_occ=3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(OPTION_SETS))
+def test_other_option_sets_match_oracle(name):
+    """the kernels are not specialised to the reference's option values: every set must stay
+    bit-identical to the oracle run with the same lgr_params (or be refused by validate_params)"""
+    from lancet2_b200.realign import GpuRealigner, LgrError
+    prm = _params(**OPTION_SETS[name])
+    rng = np.random.default_rng(31)
+    groups = synth.make_groups(41, 4, n_reads=96, n_haps=4, hap_len=700) + \
+        synth.make_groups(42, 2, read_len=250, hap_len=1200, n_haps=3, n_reads=48, sub_err=0.02, indel_err=0.002) + \
+        [str_group(rng, 150, 700, 3, 48)]
+    batch = abi.Batch(groups)
+    try:
+        g = GpuRealigner(0, params=prm)
+    except LgrError as e:
+        pytest.skip(f"option set refused by the device path: {e}")
+    try:
+        want, wst = O.oracle_genotype(batch, prm, n_threads=8)
+        got, st = g.genotype_batch(batch)
+        errs = compare_results(batch, want, got)
+        assert not errs, "\n".join(errs[:20])
+        assert (st.n_aligned, st.chain_evals, st.n_anchors) == (wst.n_aligned, wst.chain_evals, wst.n_anchors)
+        assert st.n_aligned > 0
+    finally:
+        g.close()
+
+
+def test_full_microbench_point_matches_oracle(gpu):
+    """the cfg5 bench point at full size (2.1 M pairs) against the oracle, every field"""
+    batch = abi.Batch(synth.make_groups(42, 1024, read_len=150, hap_len=1000, n_haps=8, n_reads=256))
+    assert batch.n_pairs == 2_097_152
+    want, wst = O.oracle_genotype(batch, gpu.params, n_threads=24)
+    got, st = gpu.genotype_batch(batch, arena=1 << 22)
+    errs = compare_results(batch, want, got)
+    assert not errs, "\n".join(errs[:20])
+    assert (st.n_aligned, st.chain_evals, st.dp_cells_full) == (wst.n_aligned, wst.chain_evals, wst.dp_cells_full)
