@@ -212,30 +212,48 @@ struct MinimizerWindow {
     for (int j = 0; j < W; ++j) wx[j] = kMax, wy[j] = UINT32_MAX;
     min_x = kMax, min_y = UINT32_MAX, min_idx = W - 1, k = k_;
   }
+  // One position of mm_sketch's window loop.  Written so that the common emission (the old
+  // minimum, when a new record takes over or the minimum leaves the window) has ONE call site
+  // and the rescan is a select chain: lanes of a warp that sketch different sequences then
+  // diverge only on that one short predicated block, not on four copies of it.  The two
+  // "identical k-mer" emission loops stay as (rare) branches.
   template <typename Emit>
   LGR_HD void step(XT ix, uint32_t iy, int l, Emit& emit) {
 #pragma unroll
     for (int j = 0; j + 1 < W; ++j) wx[j] = wx[j + 1], wy[j] = wy[j + 1];
     wx[W - 1] = ix, wy[W - 1] = iy;
     --min_idx;
-    if (l == W + k - 1 && min_x != kMax) {
+    const bool have_min = min_x != kMax;
+    if (l == W + k - 1 && have_min) {  // first full window of a run: identical k-mers not stored yet
 #pragma unroll
       for (int j = 0; j + 1 < W; ++j)
-        if (min_x == wx[j] && wy[j] != min_y) emit(wx[j], wy[j]);
+        if (min_x == wx[j] && wy[j] != min_y) emit(min_x, wy[j]);
     }
-    if (ix <= min_x) {
-      if (l >= W + k && min_x != kMax) emit(min_x, min_y);
+    const bool takes_over = ix <= min_x;
+    const bool fell_out = !takes_over && min_idx < 0;
+    if (have_min && ((takes_over && l >= W + k) || (fell_out && l >= W + k - 1))) emit(min_x, min_y);
+    // right-most minimum of the window (what the rescan finds); only used when the old one fell out
+    XT rx = kMax;
+    uint32_t ry = UINT32_MAX;
+    int ri = W - 1;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const bool le = rx >= wx[j];
+      rx = le ? wx[j] : rx, ry = le ? wy[j] : ry, ri = le ? j : ri;
+    }
+    if (takes_over) {
       min_x = ix, min_y = iy, min_idx = W - 1;
-    } else if (min_idx < 0) {
-      if (l >= W + k - 1 && min_x != kMax) emit(min_x, min_y);
-      min_x = kMax;
+    } else if (fell_out) {
+      min_x = rx, min_y = ry, min_idx = ri;
+      if (l >= W + k - 1 && rx != kMax) {
+        bool any = false;
 #pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (min_x >= wx[j]) min_x = wx[j], min_y = wy[j], min_idx = j;
-      if (l >= W + k - 1 && min_x != kMax) {
+        for (int j = 0; j < W; ++j) any |= rx == wx[j] && ry != wy[j];
+        if (any) {
 #pragma unroll
-        for (int j = 0; j < W; ++j)
-          if (min_x == wx[j] && min_y != wy[j]) emit(wx[j], wy[j]);
+          for (int j = 0; j < W; ++j)
+            if (rx == wx[j] && ry != wy[j]) emit(rx, wy[j]);
+        }
       }
     }
   }
