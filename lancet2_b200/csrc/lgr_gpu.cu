@@ -1789,7 +1789,7 @@ static int ensure(lgr_ctx* c, DevBuf& b, size_t bytes) {
   if (b.cap >= bytes) return LGR_OK;
   if (b.p) cudaFree(b.p);
   b.p = nullptr, b.cap = 0;
-  size_t want = bytes + bytes / 8;
+  size_t want = bytes + bytes / 2;  // cudaFree/cudaMalloc synchronise the device: regrow rarely
   cudaError_t e = cudaMalloc(&b.p, want);
   if (e != cudaSuccess) {
     c->err = std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e);

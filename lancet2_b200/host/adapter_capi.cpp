@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -185,12 +186,13 @@ int lgr_adapter_genotype_dump(int device, const lgr_batch_in* in, const char* na
 
 // Same batch, but every group is a separate blocking GenotypeBatcher::Genotype() call issued
 // from `n_threads` worker threads (round-robin over the groups, `rounds` times), the way
-// Lancet2's workers would call it.  counters[5] = batches, jobs, pairs, max jobs in one batch,
-// wall nanoseconds of the worker phase.  cap <= 0 skips the dump (timing runs).
+// Lancet2's workers would call it.  counters[9] = batches, jobs, pairs, max jobs in one batch,
+// wall nanoseconds of the worker phase, batcher-thread nanoseconds in pack / submit / wait / deliver.  cap <= 0 skips the dump (timing runs).  window > 1:
+// every worker keeps that many groups enqueued (Enqueue/Collect) instead of blocking per group.
 int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
                              const int* sample_id, const long long* start0, const long long* isize,
                              const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
-                             int n_threads, int rounds, unsigned long long* counters, char* out, long long cap) {
+                             int n_threads, int rounds, int window, unsigned long long* counters, char* out, long long cap) {
   try {
     JobSet js;
     BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
@@ -205,11 +207,24 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
       for (int t = 0; t < n_threads; ++t) {
         workers.emplace_back([&, t] {
           try {
-            for (int round = 0; round < rounds; ++round)
-              for (std::size_t g = (size_t)t; g < js.jobs.size(); g += (size_t)n_threads) {
-                const lancet_gpu::GenotypeJob& j = js.jobs[g];
-                res[g] = batcher.Genotype(j.haps, j.n_haps, j.reads, j.n_reads, j.variants, j.n_variants);
+            for (int round = 0; round < rounds; ++round) {
+              if (window <= 1) {  // the reference's call shape: one blocking call per group
+                for (std::size_t g = (size_t)t; g < js.jobs.size(); g += (size_t)n_threads) {
+                  const lancet_gpu::GenotypeJob& j = js.jobs[g];
+                  res[g] = batcher.Genotype(j.haps, j.n_haps, j.reads, j.n_reads, j.variants, j.n_variants);
+                }
+              } else {  // split ProcessWindow: up to `window` groups enqueued per worker before collecting
+                std::deque<std::pair<std::size_t, lancet_gpu::GenotypeBatcher::Ticket>> open_t;
+                for (std::size_t g = (size_t)t; g < js.jobs.size(); g += (size_t)n_threads) {
+                  if ((int)open_t.size() == window) {
+                    res[open_t.front().first] = batcher.Collect(open_t.front().second);
+                    open_t.pop_front();
+                  }
+                  open_t.emplace_back(g, batcher.Enqueue(js.jobs[g]));
+                }
+                for (auto& ot : open_t) res[ot.first] = batcher.Collect(ot.second);
               }
+            }
           } catch (const std::exception& e) {
             errors[(size_t)t] = e.what();
           }
@@ -221,6 +236,7 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
       if (counters) {
         counters[0] = c.batches, counters[1] = c.jobs, counters[2] = c.pairs, counters[3] = c.max_jobs_in_batch;
         counters[4] = (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+        counters[5] = c.ns_pack, counters[6] = c.ns_submit, counters[7] = c.ns_wait, counters[8] = c.ns_deliver;
       }
     }
     for (const auto& e : errors)

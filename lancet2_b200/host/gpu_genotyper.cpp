@@ -60,7 +60,7 @@ template <typename T>
 void PackedBatch::Reserve(Buf<T>& b, std::size_t n) {
   if (n <= b.cap) return;
   std::size_t cap = b.cap ? b.cap : 256;
-  while (cap < n) cap += cap / 2 + 64;
+  while (cap < n) cap = cap * 2 + 64;  // pinned allocations are slow: grow rarely
   bool pinned = true;
   T* p = static_cast<T*>(lgr_alloc_pinned(cap * sizeof(T)));
   if (!p) {
@@ -94,51 +94,94 @@ PackedBatch::~PackedBatch() {
   Free(mX31), Free(mVarAllele), Free(mAssign);
 }
 
+void PackedJob::Build(const GenotypeJob& j) {
+  n_haps = j.n_haps, n_reads = j.n_reads, n_variants = j.n_variants;
+  hap_bases.clear(), read_bases.clear(), read_quals.clear(), x31.clear();
+  var_start.clear(), var_len.clear(), var_allele.clear();
+  hap_off.assign(1, 0), read_off.assign(1, 0), var_hap_off.assign(1, 0);
+  std::size_t hap_total = 0, read_total = 0;
+  for (std::size_t h = 0; h < j.n_haps; ++h) hap_total += j.haps[h].size();
+  for (std::size_t r = 0; r < j.n_reads; ++r) read_total += j.reads[r].seq.size();
+  hap_bases.reserve(hap_total), read_bases.reserve(read_total), read_quals.reserve(read_total);
+  x31.reserve(j.n_reads), read_off.reserve(j.n_reads + 1), hap_off.reserve(j.n_haps + 1);
+  for (std::size_t h = 0; h < j.n_haps; ++h) {
+    hap_bases.insert(hap_bases.end(), j.haps[h].begin(), j.haps[h].end());
+    hap_off.push_back(static_cast<std::int64_t>(hap_bases.size()));
+  }
+  std::string qn;
+  for (std::size_t r = 0; r < j.n_reads; ++r) {
+    const ReadIn& rd = j.reads[r];
+    read_bases.insert(read_bases.end(), rd.seq.begin(), rd.seq.end());
+    read_quals.insert(read_quals.end(), rd.qual, rd.qual + rd.seq.size());
+    read_off.push_back(static_cast<std::int64_t>(read_bases.size()));
+    qn.assign(rd.qname);  // mm_map receives the NUL-terminated QnamePtr()
+    x31.push_back(lgr_x31_hash(qn.c_str()));
+  }
+  for (std::size_t v = 0; v < j.n_variants; ++v) {
+    const VariantIn& var = j.variants[v];
+    for (std::size_t h = 0; h < j.n_haps; ++h) {  // ExtractHapBounds (genotyper.cpp:329-352)
+      std::int32_t st = -1, ln = 0;
+      std::int8_t al = -1;
+      if (h == 0) {
+        st = static_cast<std::int32_t>(var.local_ref_start0), ln = static_cast<std::int32_t>(var.ref_allele_len), al = 0;
+      } else {
+        for (std::size_t a = 0; a < var.alts.size() && al < 0; ++a)
+          for (const auto& kv : var.alts[a].hap_start0)
+            if (kv.first == h) {
+              st = static_cast<std::int32_t>(kv.second), ln = static_cast<std::int32_t>(var.alts[a].seq_len);
+              al = static_cast<std::int8_t>(a + 1);
+              break;
+            }
+      }
+      var_start.push_back(st), var_len.push_back(ln), var_allele.push_back(al);
+    }
+    var_hap_off.push_back(static_cast<std::int64_t>(var_start.size()));
+  }
+}
+
 void PackedBatch::Pack(const GenotypeJob* jobs, std::size_t n_jobs, std::int32_t latched_mid_occ) {
+  std::vector<PackedJob> packed(n_jobs);
+  std::vector<const PackedJob*> ptrs(n_jobs);
+  for (std::size_t g = 0; g < n_jobs; ++g) packed[g].Build(jobs[g]), ptrs[g] = &packed[g];
+  PackPrepared(ptrs.data(), n_jobs, latched_mid_occ);
+}
+
+void PackedBatch::PackPrepared(const PackedJob* const* jobs, std::size_t n_jobs, std::int32_t latched_mid_occ) {
   for (auto* b : {&mGhb, &mGrb, &mGvb, &mGmid, &mVarStart, &mVarLen}) b->n = 0;
   for (auto* b : {&mHapOff, &mReadOff, &mVarHapOff}) b->n = 0;
   for (auto* b : {&mHapBases, &mReadBases, &mReadQuals}) b->n = 0;
   mX31.n = 0, mVarAllele.n = 0;
   mJobAsg.clear();
+  // sizes first: one reservation per array, then straight block copies
+  std::size_t nh = 0, nr = 0, nv = 0, hb = 0, rb = 0, vh = 0;
+  for (std::size_t g = 0; g < n_jobs; ++g) {
+    const PackedJob& j = *jobs[g];
+    nh += j.n_haps, nr += j.n_reads, nv += j.n_variants;
+    hb += j.hap_bases.size(), rb += j.read_bases.size(), vh += j.var_start.size();
+  }
+  Reserve(mGhb, n_jobs + 2), Reserve(mGrb, n_jobs + 2), Reserve(mGvb, n_jobs + 2), Reserve(mGmid, n_jobs + 1);
+  Reserve(mHapOff, nh + 2), Reserve(mReadOff, nr + 2), Reserve(mVarHapOff, nv + 2);
+  Reserve(mHapBases, hb + 1), Reserve(mReadBases, rb + 1), Reserve(mReadQuals, rb + 1);
+  Reserve(mX31, nr + 1), Reserve(mVarStart, vh + 1), Reserve(mVarLen, vh + 1), Reserve(mVarAllele, vh + 1);
   Push<std::int32_t>(mGhb, 0), Push<std::int32_t>(mGrb, 0), Push<std::int32_t>(mGvb, 0);
   Push<std::int64_t>(mHapOff, 0), Push<std::int64_t>(mReadOff, 0), Push<std::int64_t>(mVarHapOff, 0);
   std::int64_t n_assign = 0;
   mPairs = 0;
-  std::string qn;
+  auto rebase = [](Buf<std::int64_t>& dst, const std::vector<std::int64_t>& rel, std::int64_t base) {
+    for (std::size_t i = 1; i < rel.size(); ++i) dst.p[dst.n++] = rel[i] + base;
+  };
   for (std::size_t g = 0; g < n_jobs; ++g) {
-    const GenotypeJob& j = jobs[g];
-    for (std::size_t h = 0; h < j.n_haps; ++h) {
-      Append(mHapBases, reinterpret_cast<const std::uint8_t*>(j.haps[h].data()), j.haps[h].size());
-      Push(mHapOff, static_cast<std::int64_t>(mHapBases.n));
-    }
-    for (std::size_t r = 0; r < j.n_reads; ++r) {
-      const ReadIn& rd = j.reads[r];
-      Append(mReadBases, reinterpret_cast<const std::uint8_t*>(rd.seq.data()), rd.seq.size());
-      Append(mReadQuals, rd.qual, rd.seq.size());
-      Push(mReadOff, static_cast<std::int64_t>(mReadBases.n));
-      qn.assign(rd.qname);  // mm_map receives the NUL-terminated QnamePtr()
-      Push(mX31, lgr_x31_hash(qn.c_str()));
-    }
-    for (std::size_t v = 0; v < j.n_variants; ++v) {
-      const VariantIn& var = j.variants[v];
-      for (std::size_t h = 0; h < j.n_haps; ++h) {  // ExtractHapBounds (genotyper.cpp:329-352)
-        std::int32_t st = -1, ln = 0;
-        std::int8_t al = -1;
-        if (h == 0) {
-          st = static_cast<std::int32_t>(var.local_ref_start0), ln = static_cast<std::int32_t>(var.ref_allele_len), al = 0;
-        } else {
-          for (std::size_t a = 0; a < var.alts.size() && al < 0; ++a)
-            for (const auto& kv : var.alts[a].hap_start0)
-              if (kv.first == h) {
-                st = static_cast<std::int32_t>(kv.second), ln = static_cast<std::int32_t>(var.alts[a].seq_len);
-                al = static_cast<std::int8_t>(a + 1);
-                break;
-              }
-        }
-        Push(mVarStart, st), Push(mVarLen, ln), Push(mVarAllele, al);
-      }
-      Push(mVarHapOff, static_cast<std::int64_t>(mVarStart.n));
-    }
+    const PackedJob& j = *jobs[g];
+    rebase(mHapOff, j.hap_off, static_cast<std::int64_t>(mHapBases.n));
+    rebase(mReadOff, j.read_off, static_cast<std::int64_t>(mReadBases.n));
+    rebase(mVarHapOff, j.var_hap_off, static_cast<std::int64_t>(mVarStart.n));
+    Append(mHapBases, j.hap_bases.data(), j.hap_bases.size());
+    Append(mReadBases, j.read_bases.data(), j.read_bases.size());
+    Append(mReadQuals, j.read_quals.data(), j.read_quals.size());
+    Append(mX31, j.x31.data(), j.x31.size());
+    Append(mVarStart, j.var_start.data(), j.var_start.size());
+    Append(mVarLen, j.var_len.data(), j.var_len.size());
+    Append(mVarAllele, j.var_allele.data(), j.var_allele.size());
     Push(mGhb, mGhb.p[g] + static_cast<std::int32_t>(j.n_haps));
     Push(mGrb, mGrb.p[g] + static_cast<std::int32_t>(j.n_reads));
     Push(mGvb, mGvb.p[g] + static_cast<std::int32_t>(j.n_variants));
@@ -147,10 +190,6 @@ void PackedBatch::Pack(const GenotypeJob* jobs, std::size_t n_jobs, std::int32_t
     n_assign += static_cast<std::int64_t>(j.n_reads) * static_cast<std::int64_t>(j.n_variants);
     mPairs += static_cast<std::int64_t>(j.n_reads) * static_cast<std::int64_t>(j.n_haps);
   }
-  // keep every pointer valid for empty arrays
-  Reserve(mHapBases, mHapBases.n + 1), Reserve(mReadBases, mReadBases.n + 1), Reserve(mReadQuals, mReadQuals.n + 1);
-  Reserve(mX31, mX31.n + 1), Reserve(mVarStart, mVarStart.n + 1), Reserve(mVarLen, mVarLen.n + 1);
-  Reserve(mVarAllele, mVarAllele.n + 1), Reserve(mGmid, mGmid.n + 1);
   Reserve(mAssign, static_cast<std::size_t>(n_assign) + 1);
   mAssign.n = static_cast<std::size_t>(n_assign);
   const int G = static_cast<int>(n_jobs);
@@ -264,20 +303,33 @@ GenotypeBatcher::~GenotypeBatcher() {
   lgr_destroy(mCtx);
 }
 
-Result GenotypeBatcher::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
-                                 const VariantIn* variants, std::size_t n_variants) {
+GenotypeBatcher::Ticket GenotypeBatcher::Enqueue(const GenotypeJob& job) {
   Pending p;
-  p.job = GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants};
-  std::future<std::vector<lgr_assign>> fut = p.done.get_future();
+  p.job = job;
+  p.packed = std::make_unique<PackedJob>();
+  p.packed->Build(job);  // on the enqueuing worker: the batcher thread only concatenates
+  Ticket t;
+  t.job = job;
+  t.done = p.done.get_future();
   {
     std::lock_guard<std::mutex> lk(mMu);
     if (mStop) throw std::runtime_error("lancet_gpu::GenotypeBatcher: shut down");
     mQueue.push_back(std::move(p));
   }
   mCv.notify_all();
-  const std::vector<lgr_assign> assign = fut.get();  // rethrows a device error on this worker
-  // AddToTable on the calling worker: the serial batcher thread only moves bytes
-  return PackedBatch::BuildResult(GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants}, assign.data(), mNameHash);
+  return t;
+}
+
+Result GenotypeBatcher::Collect(Ticket& ticket) {
+  const std::vector<lgr_assign> assign = ticket.done.get();  // rethrows a device error on this thread
+  // AddToTable on the collecting thread: the serial batcher thread only moves bytes
+  return PackedBatch::BuildResult(ticket.job, assign.data(), mNameHash);
+}
+
+Result GenotypeBatcher::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
+                                 const VariantIn* variants, std::size_t n_variants) {
+  Ticket t = Enqueue(GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants});
+  return Collect(t);
 }
 
 GenotypeBatcher::Counters GenotypeBatcher::Stats() {
@@ -285,13 +337,20 @@ GenotypeBatcher::Counters GenotypeBatcher::Stats() {
   return mCounters;
 }
 
+static std::uint64_t NowNs() {
+  return static_cast<std::uint64_t>(
+      std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+
 void GenotypeBatcher::Complete(Slot& s) {
   std::exception_ptr err;
+  const std::uint64_t t0 = NowNs();
   try {
     Check(mCtx, lgr_wait(mCtx, s.ticket, nullptr));
   } catch (...) {
     err = std::current_exception();
   }
+  const std::uint64_t t1 = NowNs();
   s.ticket = -1;
   for (std::size_t j = 0; j < s.jobs.size(); ++j) {
     Pending& p = s.jobs[j];
@@ -303,6 +362,9 @@ void GenotypeBatcher::Complete(Slot& s) {
     p.done.set_value(std::vector<lgr_assign>(a, a + p.job.n_reads * p.job.n_variants));
   }
   s.jobs.clear();
+  const std::uint64_t t2 = NowNs();
+  std::lock_guard<std::mutex> lk(mMu);
+  mCounters.ns_wait += t1 - t0, mCounters.ns_deliver += t2 - t1;
 }
 
 void GenotypeBatcher::Run() {
@@ -348,9 +410,18 @@ void GenotypeBatcher::Run() {
       jobs.reserve(s.jobs.size());
       for (const Pending& p : s.jobs) jobs.push_back(p.job);
       LatchMidOcc(mCtx, mParams, jobs.data(), jobs.size(), &mLatchedMidOcc);
-      s.pb.Pack(jobs.data(), jobs.size(), mLatchedMidOcc);
+      const std::uint64_t t0 = NowNs();
+      std::vector<const PackedJob*> packed;
+      packed.reserve(s.jobs.size());
+      for (const Pending& p : s.jobs) packed.push_back(p.packed.get());
+      s.pb.PackPrepared(packed.data(), packed.size(), mLatchedMidOcc);
+      for (Pending& p : s.jobs) p.packed.reset();
+      const std::uint64_t t1 = NowNs();
       Check(mCtx, lgr_submit(mCtx, &s.pb.In(), &s.pb.Out(), &s.ticket));
+      const std::uint64_t t2 = NowNs();
       ++head, ++inflight;
+      std::lock_guard<std::mutex> lk(mMu);
+      mCounters.ns_pack += t1 - t0, mCounters.ns_submit += t2 - t1;
     } catch (...) {
       for (Pending& p : s.jobs) p.done.set_exception(std::current_exception());
       s.jobs.clear();

@@ -123,6 +123,19 @@ struct GenotypeJob {
   std::size_t n_variants;
 };
 
+// One Genotype() payload already in the C-ABI's SoA layout, offsets relative to the job.  Built by
+// the thread that owns the payload (the per-read work — copies, X31 name hash, ExtractHapBounds'
+// dense table — parallelises over the workers); PackedBatch then only concatenates blocks.
+struct PackedJob {
+  std::vector<std::uint8_t> hap_bases, read_bases, read_quals;
+  std::vector<std::int64_t> hap_off, read_off, var_hap_off;  // each starts at 0
+  std::vector<std::uint32_t> x31;
+  std::vector<std::int32_t> var_start, var_len;
+  std::vector<std::int8_t> var_allele;
+  std::size_t n_haps = 0, n_reads = 0, n_variants = 0;
+  void Build(const GenotypeJob& job);  // ResetData's inputs + ExtractHapBounds (genotyper.cpp:243-267, 329-352)
+};
+
 // SoA staging of many GenotypeJobs in the C-ABI's layout (pinned host memory when available) and
 // the host half of the path: AddToTable from the returned lgr_assign records.
 class PackedBatch {
@@ -133,6 +146,8 @@ class PackedBatch {
   PackedBatch& operator=(const PackedBatch&) = delete;
   // ResetData's inputs + ExtractHapBounds' dense table for every job (genotyper.cpp:243-267, 329-352)
   void Pack(const GenotypeJob* jobs, std::size_t n_jobs, std::int32_t latched_mid_occ);
+  // the same from payloads their owners have packed already (block copies + offset rebasing only)
+  void PackPrepared(const PackedJob* const* jobs, std::size_t n_jobs, std::int32_t latched_mid_occ);
   [[nodiscard]] const lgr_batch_in& In() const noexcept { return mIn; }
   [[nodiscard]] lgr_batch_out& Out() noexcept { return mOut; }
   [[nodiscard]] std::int64_t Pairs() const noexcept { return mPairs; }
@@ -207,6 +222,7 @@ class GenotypeBatcher {
   };
   struct Counters {
     std::uint64_t batches = 0, jobs = 0, pairs = 0, max_jobs_in_batch = 0;
+    std::uint64_t ns_pack = 0, ns_submit = 0, ns_wait = 0, ns_deliver = 0;  // batcher-thread time per stage
   };
   GenotypeBatcher(const Options& opt, NameHashFn name_hash);
   ~GenotypeBatcher();  // drains what is queued, then joins
@@ -216,11 +232,23 @@ class GenotypeBatcher {
   // thread-safe drop-in for Genotyper::Genotype (genotyper.cpp:224-235); blocks the calling worker
   [[nodiscard]] Result Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
                                 const VariantIn* variants, std::size_t n_variants);
+
+  // The two halves of Genotype() for a caller that has split ProcessWindow:
+  // Enqueue returns at once, the worker goes on to assemble its next window, and Collect (on any
+  // thread) waits for the device and runs AddToTable.  The job's buffers are borrowed until
+  // Collect returns.  With many windows enqueued per worker the batches fill the GPU.
+  struct Ticket {
+    GenotypeJob job{};
+    std::future<std::vector<lgr_assign>> done;
+  };
+  [[nodiscard]] Ticket Enqueue(const GenotypeJob& job);
+  [[nodiscard]] Result Collect(Ticket& ticket);
   [[nodiscard]] Counters Stats();
 
  private:
   struct Pending {
     GenotypeJob job;
+    std::unique_ptr<PackedJob> packed;  // built by the enqueuing thread
     std::promise<std::vector<lgr_assign>> done;
   };
   struct Slot {

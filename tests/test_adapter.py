@@ -31,7 +31,7 @@ def lib():
         [C.c_void_p] * 6 + [C.c_char_p, C.c_longlong]
     lb.lgr_adapter_genotype_dump.restype = C.c_int
     lb.lgr_adapter_batcher_dump.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + \
-        [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
+        [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
     lb.lgr_adapter_batcher_dump.restype = C.c_int
     return lb
 
@@ -135,12 +135,19 @@ def test_cross_thread_batcher_equals_synchronous_adapter(lib):
     n1 = lib.lgr_adapter_genotype_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, buf1, len(buf1))
     assert n1 > 0, buf1.value.decode()
     buf2 = C.create_string_buffer(64 << 20)
-    counters = np.zeros(5, dtype=np.uint64)
+    counters = np.zeros(9, dtype=np.uint64)
     rounds = 3
-    n2 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 8, rounds, counters.ctypes.data,
+    n2 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 8, rounds, 1, counters.ctypes.data,
                                       buf2, len(buf2))
     assert n2 > 0, buf2.value.decode()
     assert buf2.value == buf1.value
     batches, jobs, pairs, max_jobs = (int(x) for x in counters[:4])
     assert jobs == rounds * len(groups) and pairs == rounds * batch.n_pairs
     assert batches < jobs and max_jobs > 1, (batches, jobs, max_jobs)  # calls were coalesced
+    # Enqueue/Collect: two workers with 16 groups in flight each — same evidence, fewer device batches
+    buf3 = C.create_string_buffer(64 << 20)
+    n3 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 2, rounds, 16, counters.ctypes.data,
+                                      buf3, len(buf3))
+    assert n3 > 0, buf3.value.decode()
+    assert buf3.value == buf1.value
+    assert int(counters[0]) < batches and int(counters[3]) >= 8, counters
