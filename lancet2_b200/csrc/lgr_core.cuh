@@ -416,15 +416,35 @@ LGR_HDN void radix_sort_perm(Perm perm, int n, KeyFn key, RadixScratch* rs) {
   while (sp > 0) {
     --sp;
     const int beg = rs->st_beg[sp], end = rs->st_end[sp];
-    const int s = rs->st_s[sp];
-    for (int k = 0; k < 256; ++k) rs->bb[k] = rs->be[k] = (uint16_t)beg;  // be[] = counts first
+    int s = rs->st_s[sp];
+    {
+      // A level at which all keys of the range share the byte puts them in one bucket: the
+      // permutation loop moves nothing and (the range being > 64) the next level gets the same
+      // range.  Jump straight to the highest byte that differs; none left = nothing to do.
+      const uint64_t k0 = key(perm[beg]);
+      uint64_t diff = 0;
+      for (int i = beg + 1; i < end; ++i) diff |= key(perm[i]) ^ k0;
+      if (s < 56) diff &= (1ULL << (s + 8)) - 1;
+      if (diff == 0) continue;
+      int top = 0;
+      for (uint64_t d = diff >> 8; d; d >>= 8) ++top;
+      s = 8 * top;
+    }
+    // only the buckets between the smallest and the largest byte present can be non-empty;
+    // everything the full 256-bucket loops would do outside that span is a no-op
+    int kmin = 255, kmax = 0;
+    for (int i = beg; i < end; ++i) {
+      const int b = (int)(key(perm[i]) >> s & 255);
+      kmin = b < kmin ? b : kmin, kmax = b > kmax ? b : kmax;
+    }
+    for (int k = kmin; k <= kmax; ++k) rs->bb[k] = rs->be[k] = (uint16_t)beg;  // be[] = counts first
     for (int i = beg; i < end; ++i) ++rs->be[(int)(key(perm[i]) >> s & 255)];
     // k->e += (k-1)->e - beg ; k->b = (k-1)->e
-    for (int k = 1; k < 256; ++k) {
+    for (int k = kmin + 1; k <= kmax; ++k) {
       rs->be[k] = (uint16_t)(rs->be[k] + rs->be[k - 1] - beg);
       rs->bb[k] = rs->be[k - 1];
     }
-    for (int k = 0; k < 256;) {
+    for (int k = kmin; k <= kmax;) {
       if (rs->bb[k] != rs->be[k]) {
         int l = (int)(key(perm[rs->bb[k]]) >> s & 255);
         if (l != k) {
@@ -446,7 +466,7 @@ LGR_HDN void radix_sort_perm(Perm perm, int n, KeyFn key, RadixScratch* rs) {
     if (s) {
       const int s2 = s > 8 ? s - 8 : 0;
       int b0 = beg;
-      for (int k = 0; k < 256; ++k) {
+      for (int k = kmin; k <= kmax; ++k) {
         const int e0 = rs->be[k];
         if (e0 - b0 > 64) {
           rs->st_beg[sp] = (uint16_t)b0, rs->st_end[sp] = (uint16_t)e0, rs->st_s[sp] = (uint8_t)s2;
@@ -1149,14 +1169,16 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
   if (n_a == 0) return kMapNoHit;
   // ---- radix_sort_128x(a) by x --------------------------------------------------------
   {
-    bool sorted = true;
-    for (int i = 1; i < n_a; ++i)
+    bool sorted = true, strict = true;
+    for (int i = 1; i < n_a; ++i) {
       if ((uint32_t)ax[i] < (uint32_t)ax[i - 1]) { sorted = false; break; }
-    if (sorted && n_a <= 64) {
+      if ((uint32_t)ax[i] == (uint32_t)ax[i - 1]) strict = false;
+    }
+    if (sorted && (n_a <= 64 || strict)) {
       for (int i = 0; i < n_a; ++i) sx[i] = ax[i], sy[i] = ay[i];
     } else {
-      // NB: for n_a > 64 even an already sorted input is permuted by the in-place radix
-      // passes when keys tie, so the emulation always runs.
+      // NB: for n_a > 64 an already sorted input is still permuted by the in-place radix
+      // passes when keys tie, so only a strictly increasing sequence may skip the emulation.
       for (int i = 0; i < n_a; ++i) perm[i] = i;
       radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
       for (int i = 0; i < n_a; ++i) sx[i] = ax[perm[i]], sy[i] = ay[perm[i]];

@@ -821,10 +821,17 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
   __syncwarp();
   // ---- radix_sort_128x(a): already-sorted fast path, else the exact emulation on lane 0 ----
   {
-    bool ok = true;
-    for (int i = lane + 1; i < n_a; i += 32) ok &= (uint32_t)ax[i] >= (uint32_t)ax[i - 1];
+    // sorted input is left alone by upstream's insertion sort (n <= 64, stable); its in-place
+    // radix passes (n > 64) may permute elements whose keys tie, so beyond 64 anchors only a
+    // STRICTLY increasing key sequence — which has exactly one sorted order — can skip the emulation
+    bool ok = true, strict = true;
+    for (int i = lane + 1; i < n_a; i += 32) {
+      const uint32_t cur = (uint32_t)ax[i], prev = (uint32_t)ax[i - 1];
+      ok &= cur >= prev, strict &= cur > prev;
+    }
     const bool sorted = __all_sync(full, ok);
-    if (sorted && n_a <= 64) {
+    const bool strictly = __all_sync(full, strict);
+    if (sorted && (n_a <= 64 || strictly)) {
       for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
     } else {
       if (lane == 0) {
@@ -1292,11 +1299,21 @@ __device__ __noinline__ int warp_chain_tail_fast(const DevParams& P, int qlen, i
     if (i < n_a) t[i] = 0;
   }
   if (n_z == 0) return kMapNoHit;
-  if (n_z > 64) return -2;  // upstream's unstable radix pass decides the order: exact scalar path
   for (int o = 16; o > 0; o >>= 1) {
     const int32_t of = __shfl_xor_sync(full, bf, o);
     const int oi = __shfl_xor_sync(full, bi, o);
     if (of > bf || (of == bf && oi > bi)) bf = of, bi = oi;
+  }
+  if (n_z > 64) {
+    // beyond 64 candidates upstream's in-place radix pass orders ties arbitrarily: the chain it
+    // starts with is only certain when the maximum is unique (every other candidate is then
+    // swallowed by that chain or sends us to the general path below)
+    int ties = 0;
+    for (int base = 0; base < n_a; base += 32) {
+      const int i = base + lane;
+      ties += __popc(__ballot_sync(full, i < n_a && f[i] == bf));
+    }
+    if (ties > 1) return -2;  // exact scalar path
   }
   __syncwarp();
   // mg_chain_bk_end + collection for the top anchor (t[] is all zero: first chain)
