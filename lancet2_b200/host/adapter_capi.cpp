@@ -189,19 +189,22 @@ int lgr_adapter_genotype_dump(int device, const lgr_batch_in* in, const char* na
 // Lancet2's workers would call it.  counters[9] = batches, jobs, pairs, max jobs in one batch,
 // wall nanoseconds of the worker phase, batcher-thread nanoseconds in pack / submit / wait / deliver.  cap <= 0 skips the dump (timing runs).  window > 1:
 // every worker keeps that many groups enqueued (Enqueue/Collect) instead of blocking per group.
+// n_devices > 1: a GenotypeDispatcher over devices device .. device+n_devices-1; counters[9 + d] =
+// payloads that went to device d (counters must hold 17 entries).
 int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
                              const int* sample_id, const long long* start0, const long long* isize,
                              const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
-                             int n_threads, int rounds, int window, unsigned long long* counters, char* out, long long cap) {
+                             int n_threads, int rounds, int window, int n_devices, unsigned long long* counters, char* out,
+                             long long cap) {
   try {
     JobSet js;
     BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
     std::vector<lancet_gpu::Result> res(js.jobs.size());
     std::vector<std::string> errors((size_t)n_threads);
     {
-      lancet_gpu::GenotypeBatcher::Options opt;
-      opt.device = device;
-      lancet_gpu::GenotypeBatcher batcher(opt, X31OfView);
+      std::vector<int> devices;
+      for (int d = 0; d < (n_devices > 1 ? n_devices : 1); ++d) devices.push_back(device + d);
+      lancet_gpu::GenotypeDispatcher batcher(devices, X31OfView);
       std::vector<std::thread> workers;
       const auto t0 = std::chrono::steady_clock::now();
       for (int t = 0; t < n_threads; ++t) {
@@ -214,7 +217,7 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
                   res[g] = batcher.Genotype(j.haps, j.n_haps, j.reads, j.n_reads, j.variants, j.n_variants);
                 }
               } else {  // split ProcessWindow: up to `window` groups enqueued per worker before collecting
-                std::deque<std::pair<std::size_t, lancet_gpu::GenotypeBatcher::Ticket>> open_t;
+                std::deque<std::pair<std::size_t, lancet_gpu::GenotypeDispatcher::Ticket>> open_t;
                 for (std::size_t g = (size_t)t; g < js.jobs.size(); g += (size_t)n_threads) {
                   if ((int)open_t.size() == window) {
                     res[open_t.front().first] = batcher.Collect(open_t.front().second);
@@ -231,8 +234,15 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
         });
       }
       for (auto& w : workers) w.join();
-      const auto c = batcher.Stats();
       const auto t1 = std::chrono::steady_clock::now();
+      lancet_gpu::GenotypeBatcher::Counters c;  // summed over the devices; counters[9 + d] = jobs of device d
+      for (std::size_t d = 0; d < batcher.Devices(); ++d) {
+        const auto cd = batcher.Stats(d);
+        c.batches += cd.batches, c.jobs += cd.jobs, c.pairs += cd.pairs;
+        c.max_jobs_in_batch = std::max(c.max_jobs_in_batch, cd.max_jobs_in_batch);
+        c.ns_pack += cd.ns_pack, c.ns_submit += cd.ns_submit, c.ns_wait += cd.ns_wait, c.ns_deliver += cd.ns_deliver;
+        if (counters && d < 8) counters[9 + d] = cd.jobs;
+      }
       if (counters) {
         counters[0] = c.batches, counters[1] = c.jobs, counters[2] = c.pairs, counters[3] = c.max_jobs_in_batch;
         counters[4] = (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();

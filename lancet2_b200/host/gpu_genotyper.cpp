@@ -429,4 +429,58 @@ void GenotypeBatcher::Run() {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GenotypeDispatcher
+// ---------------------------------------------------------------------------------------------
+GenotypeDispatcher::GenotypeDispatcher(const std::vector<int>& devices, NameHashFn name_hash, GenotypeBatcher::Options base) {
+  if (devices.empty()) throw std::runtime_error("lancet_gpu::GenotypeDispatcher: no devices given (there is no CPU fallback)");
+  mOutstanding = std::make_unique<std::atomic<std::int64_t>[]>(devices.size());
+  for (std::size_t i = 0; i < devices.size(); ++i) {
+    base.device = devices[i];
+    mOutstanding[i].store(0);
+    mBatchers.push_back(std::make_unique<GenotypeBatcher>(base, name_hash));
+  }
+}
+
+std::int64_t GenotypeDispatcher::Cost(const GenotypeJob& job) {
+  std::int64_t hap_total = 0;
+  for (std::size_t h = 0; h < job.n_haps; ++h) hap_total += static_cast<std::int64_t>(job.haps[h].size());
+  return static_cast<std::int64_t>(job.n_reads) * hap_total + 1;
+}
+
+GenotypeDispatcher::Ticket GenotypeDispatcher::Enqueue(const GenotypeJob& job) {
+  std::size_t best = 0;
+  std::int64_t best_load = mOutstanding[0].load(std::memory_order_relaxed);
+  for (std::size_t i = 1; i < mBatchers.size(); ++i) {
+    const std::int64_t load = mOutstanding[i].load(std::memory_order_relaxed);
+    if (load < best_load) best = i, best_load = load;
+  }
+  Ticket t;
+  t.device_slot = best;
+  t.cost = Cost(job);
+  mOutstanding[best].fetch_add(t.cost, std::memory_order_relaxed);
+  try {
+    t.inner = mBatchers[best]->Enqueue(job);
+  } catch (...) {
+    mOutstanding[best].fetch_sub(t.cost, std::memory_order_relaxed);
+    throw;
+  }
+  return t;
+}
+
+Result GenotypeDispatcher::Collect(Ticket& ticket) {
+  struct Release {
+    std::atomic<std::int64_t>& load;
+    std::int64_t cost;
+    ~Release() { load.fetch_sub(cost, std::memory_order_relaxed); }
+  } release{mOutstanding[ticket.device_slot], ticket.cost};
+  return mBatchers[ticket.device_slot]->Collect(ticket.inner);
+}
+
+Result GenotypeDispatcher::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
+                                    const VariantIn* variants, std::size_t n_variants) {
+  Ticket t = Enqueue(GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants});
+  return Collect(t);
+}
+
 }  // namespace lancet_gpu

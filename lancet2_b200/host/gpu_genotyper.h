@@ -18,6 +18,7 @@
 #ifndef LANCET2_B200_HOST_GPU_GENOTYPER_H_
 #define LANCET2_B200_HOST_GPU_GENOTYPER_H_
 
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -270,6 +271,33 @@ class GenotypeBatcher {
   Counters mCounters;
   std::vector<std::unique_ptr<Slot>> mSlots;
   std::thread mThread;
+};
+
+// Several GPUs of one box: one GenotypeBatcher per device behind one entry point.
+// Whole Genotype() payloads are routed — never split, the per-variant arg-max needs all haplotype
+// pairs of a read together — to the device with the least outstanding work (cost = reads x
+// total haplotype length, the same estimate lancet2_b200/dispatch.py uses).  No collective: the
+// results come back to the caller that enqueued them, and output order is the caller's order.
+class GenotypeDispatcher {
+ public:
+  GenotypeDispatcher(const std::vector<int>& devices, NameHashFn name_hash, GenotypeBatcher::Options base = {});
+  struct Ticket {
+    std::size_t device_slot = 0;
+    std::int64_t cost = 0;
+    GenotypeBatcher::Ticket inner;
+  };
+  [[nodiscard]] Ticket Enqueue(const GenotypeJob& job);
+  [[nodiscard]] Result Collect(Ticket& ticket);
+  // thread-safe drop-in for Genotyper::Genotype (genotyper.cpp:224-235)
+  [[nodiscard]] Result Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
+                                const VariantIn* variants, std::size_t n_variants);
+  [[nodiscard]] std::size_t Devices() const noexcept { return mBatchers.size(); }
+  [[nodiscard]] GenotypeBatcher::Counters Stats(std::size_t device_slot) { return mBatchers[device_slot]->Stats(); }
+  static std::int64_t Cost(const GenotypeJob& job);
+
+ private:
+  std::vector<std::unique_ptr<GenotypeBatcher>> mBatchers;
+  std::unique_ptr<std::atomic<std::int64_t>[]> mOutstanding;
 };
 
 }  // namespace lancet_gpu

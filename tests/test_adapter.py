@@ -31,7 +31,7 @@ def lib():
         [C.c_void_p] * 6 + [C.c_char_p, C.c_longlong]
     lb.lgr_adapter_genotype_dump.restype = C.c_int
     lb.lgr_adapter_batcher_dump.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + \
-        [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
+        [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
     lb.lgr_adapter_batcher_dump.restype = C.c_int
     return lb
 
@@ -135,9 +135,9 @@ def test_cross_thread_batcher_equals_synchronous_adapter(lib):
     n1 = lib.lgr_adapter_genotype_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, buf1, len(buf1))
     assert n1 > 0, buf1.value.decode()
     buf2 = C.create_string_buffer(64 << 20)
-    counters = np.zeros(9, dtype=np.uint64)
+    counters = np.zeros(17, dtype=np.uint64)
     rounds = 3
-    n2 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 8, rounds, 1, counters.ctypes.data,
+    n2 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 8, rounds, 1, 1, counters.ctypes.data,
                                       buf2, len(buf2))
     assert n2 > 0, buf2.value.decode()
     assert buf2.value == buf1.value
@@ -146,8 +146,19 @@ def test_cross_thread_batcher_equals_synchronous_adapter(lib):
     assert batches < jobs and max_jobs > 1, (batches, jobs, max_jobs)  # calls were coalesced
     # Enqueue/Collect: two workers with 16 groups in flight each — same evidence, fewer device batches
     buf3 = C.create_string_buffer(64 << 20)
-    n3 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 2, rounds, 16, counters.ctypes.data,
+    n3 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 2, rounds, 16, 1, counters.ctypes.data,
                                       buf3, len(buf3))
     assert n3 > 0, buf3.value.decode()
     assert buf3.value == buf1.value
     assert int(counters[0]) < batches and int(counters[3]) >= 8, counters
+    # GenotypeDispatcher over every GPU of the box (one on the default test box): same evidence, and with
+    # more than one device every device gets a share of the payloads
+    import torch
+    n_dev = min(torch.cuda.device_count(), 8)
+    buf4 = C.create_string_buffer(64 << 20)
+    n4 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 4, rounds, 8, n_dev, counters.ctypes.data,
+                                      buf4, len(buf4))
+    assert n4 > 0, buf4.value.decode()
+    assert buf4.value == buf1.value
+    per_dev = [int(x) for x in counters[9:9 + n_dev]]
+    assert sum(per_dev) == rounds * len(groups) and all(x > 0 for x in per_dev), per_dev
