@@ -1,0 +1,120 @@
+// lgr_dev.cuh — device descriptor, counters, parked-pair records, launch-shape knobs, result writers
+// Part of the single translation unit lgr_gpu.cu (included there, in order); see that file's header.
+#ifndef LANCET2_B200_LGR_DEV_CUH_
+#define LANCET2_B200_LGR_DEV_CUH_
+
+namespace {
+
+using namespace lgr;
+
+__constant__ double c_phred_err[256] = {
+#include "phred_lut.inc"
+};
+
+// counters (int64 slots in device memory)
+enum Ctr {
+  C_ITEM = 0, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_COUNT
+};
+enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
+
+constexpr int kBucketBits = 9;
+constexpr int kBuckets = 1 << kBucketBits;
+
+struct TaskRec {  // one extension that needs the wavefront DP
+  int32_t reg, side, read, hap;
+};
+
+struct PairReg {  // per pair: its parked RegRecs in the arena (n == 0: nothing to finish)
+  int32_t first, n, read, hap;
+};
+
+struct Dev {      // everything the kernels need, passed by value
+  DevParams P;
+  int n_groups, n_haps, n_reads, n_vars;
+  int64_t n_pairs, n_assign;
+  // inputs
+  const int32_t *grp_hap_begin, *grp_read_begin, *grp_var_begin;
+  const int64_t *hap_off, *read_off, *var_hap_off;
+  const uint8_t *hap_bases, *read_bases, *read_quals;
+  const uint32_t* name_hash;
+  const int32_t *var_start, *var_len;
+  const int8_t* var_allele;
+  const int32_t* read_grp;      // [NR]
+  const int32_t* hap_grp;       // [NH]
+  const int64_t *pair_off, *asg_off;  // [NR+1]
+  const int32_t *item_hap, *item_r0, *item_n;  // phase-A work items: (hap, first read, #reads<=32)
+  int n_items;
+  // derived
+  uint8_t *hap_codes, *read_codes;
+  uint64_t* idx;                // [hap_off-indexed] sorted minimizer tables
+  int32_t *idx_n, *hap_mid;     // [NH]
+  uint16_t* bkt;                // [NH][kBuckets+1] start of every hash bucket (top hash bits) in the sorted table
+  int bkt_shift;                // hash >> bkt_shift = bucket
+  int32_t* grp_mid;             // [G] in: >0 fixed, <=0 latch from first hap; out: effective
+  uint64_t* mz_x;               // [read_off-indexed]
+  uint32_t* mz_y;
+  int32_t* mz_n;                // [NR]
+  uint64_t* mz_cnt;             // [NR][2] bucket counters of the read's minimizer hashes
+  // phase A workspace
+  int32_t* ws;                  // k_chain_overflow: [warps][A_COUNT][cap][32 lanes] workspace
+  int ws_cap;
+  uint32_t* fin_scratch;        // [warps][2][fin_cap] cigar staging of k_finish_warp
+  int fin_cap;
+  // parked pairs / tails
+  RegRec* regs;  int64_t regs_cap;
+  PairReg* pair_reg;             // [n_pairs]
+  TaskRec* tasks; int64_t tasks_cap;
+  uint32_t* ext_arena; int64_t ext_arena_cap;
+  int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
+  // k_ext_big scratch
+  uint8_t* dir_scratch; int64_t dir_per_warp;
+  int32_t* bnd_scratch; int64_t bnd_per_warp;   // Hb/Fb boundary rows
+  uint32_t* wcig_scratch; int wcig_cap;
+  RegRec* wreg_scratch;          // [warps][CAP] regs of the pair a warp is working on
+  RadixScratch* rsx_scratch;     // [warps]
+  // outputs
+  AlnOut* aln; uint32_t* cigar_inline; uint32_t* cigar_arena; int64_t cigar_arena_cap;
+  AssignOut* assign;
+  long long* ctr;
+};
+
+#ifndef LGR_CHAIN_CARVEOUT
+#define LGR_CHAIN_CARVEOUT -1  // cudaSharedmemCarveoutDefault: the chain kernel gains from every KB left to L1 (measured)
+#endif
+#ifndef LGR_CHAIN_MINB
+#define LGR_CHAIN_MINB 9
+#endif
+#ifndef LGR_EXT_MINB
+#define LGR_EXT_MINB 8
+#endif
+#ifndef LGR_FIN_MINB
+#define LGR_FIN_MINB 8
+#endif
+__device__ __forceinline__ void write_invalid(AlnOut* o) {
+  o->valid = 0, o->score = 0, o->rs = 0, o->re = 0, o->qs = 0, o->qe = 0, o->rev = 0, o->dp_score = 0, o->dp_max = 0;
+  o->mlen = 0, o->blen = 0, o->n_ambi = 0, o->nm = 0, o->n_cigar = 0, o->cigar_off = -1, o->n_regs = 0;
+}
+
+__device__ __forceinline__ void store_final(const Dev& D, int64_t pair, const AlnOut& a, const uint32_t* cig, int nc) {
+  AlnOut o = a;
+  if (nc <= LGR_CIGAR_INLINE) {
+    o.cigar_off = -1;
+    uint32_t* dst = D.cigar_inline + pair * LGR_CIGAR_INLINE;
+    for (int i = 0; i < nc; ++i) dst[i] = cig[i];
+  } else {
+    const long long off = atomicAdd((unsigned long long*)&D.ctr[C_CIGARENA], (unsigned long long)nc);
+    if (off + nc > D.cigar_arena_cap) {
+      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_ARENA);
+      o.cigar_off = -2, o.n_cigar = 0;
+    } else {
+      o.cigar_off = (int32_t)off;
+      for (int i = 0; i < nc; ++i) D.cigar_arena[off + i] = cig[i];
+    }
+  }
+  D.aln[pair] = o;
+}
+
+}  // namespace
+
+#endif  // LANCET2_B200_LGR_DEV_CUH_

@@ -1,0 +1,273 @@
+// lgr_kernels_ext.cuh — ksw2-style extension: anti-diagonal wavefront DP, warp traceback, k_ext_warp
+// Part of the single translation unit lgr_gpu.cu (included there, in order); see that file's header.
+#ifndef LANCET2_B200_LGR_KERNELS_EXT_CUH_
+#define LANCET2_B200_LGR_KERNELS_EXT_CUH_
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// ext_dp_warp: one warp computes one extension tail.  Lane l owns query row j = 32*blk + l and
+// sweeps the target columns; on step s it computes cell (i = s - l, j).  H and the F flowing
+// down a column travel to the lane below with two shuffles per step; E stays in the lane.
+// Rows beyond 32 are processed in further passes with the boundary row (H, F) kept in scratch.
+// Direction bytes are stored diagonal-major ([blk][s][lane]) so that every step is one
+// coalesced 32-byte store.  Same recurrences, tie rules and column pruning as ext_dp_scalar.
+// All 32 lanes must call it; results are written by lane 0 into reg->ext[side].
+// ---------------------------------------------------------------------------------------
+constexpr int kDynPruneMinRows = 12;  // shorter tails: the static bound is already small, skip the extra pass
+
+__device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, const ReadView& rv, const uint8_t* hapc,
+                                         uint8_t* dir_g, uint8_t* dir_s, int dir_s_cap, int32_t* Hb, int32_t* Fb, uint32_t* wcig,
+                                         long long* cells, long long* cells_full) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const DevParams& P = D.P;
+  const int q = P.q, e = P.e;
+  const int32_t sc_match = P.a, sc_mis = -P.b, sc_amb = -P.sc_ambi;  // in registers: the loop's generic stores could alias P
+  const int m = reg->ext[side].m, n = reg->ext[side].n;
+  int T = prune_cols(P, m, n);
+  const bool right = side == 0;
+  ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
+  ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
+  // Data-dependent column bound (exact).  Any path ending in the last query row at target column
+  // i = m-1+d (d > 0) deletes at least d target bases: its score is <= a*m - q - e*d, and every
+  // cell at or beyond that column is bounded the same way.  If LB is the score of SOME path that
+  // ends in the last row at an earlier column, columns with a*m - q - e*d <= LB can hold neither
+  // the first maximum of the last row nor the global maximum, and the traceback never enters
+  // them (cells only depend on smaller columns).  prune_cols uses the worst case LB = -b*m;
+  // here every lane scores one concrete family of paths — the main diagonal for p bases, one
+  // gap of delta = lane-15 (deletion > 0, insertion < 0), then the shifted diagonal — and the
+  // warp keeps the best, which for a tail that crosses an indel is close to the optimum.
+  if (n >= m && P.e > 0 && m >= kDynPruneMinRows && 2 * m + 32 <= dir_s_cap) {
+    // stage the m query codes and the first m+16 target codes in the warp's shared-memory slice
+    // (free until the direction bytes are written) so that the 32 lanes read bytes, not functors
+    uint8_t* sq = dir_s;
+    uint8_t* st = dir_s + m;
+    const int nt = m + 16 < n ? m + 16 : n;
+    for (int x = lane; x < m; x += 32) sq[x] = (uint8_t)qf(x);
+    for (int x = lane; x < nt; x += 32) st[x] = (uint8_t)tf(x);
+    __syncwarp();
+    const int delta = lane - 15;
+    int32_t lb = kNegInf;
+    if (delta >= 0 ? m + delta <= n : -delta < m) {
+      const int k = delta < 0 ? -delta : 0;  // inserted query bases
+      const uint8_t* t0 = st;
+      const uint8_t* t1 = st + (delta > 0 ? delta : 0);
+      const uint8_t* q1 = sq + k;
+      int32_t p0 = 0, ps = 0, best = 0;      // P0[p], shifted prefix, max(P0 - shifted)
+      const int steps = m - k;
+      for (int p = 0; p < steps; ++p) {
+        const int tcp = t0[p], tcs = t1[p], qcp = sq[p], qcs = q1[p];
+        p0 += (tcp > 3 || qcp > 3) ? sc_amb : (tcp == qcp ? sc_match : sc_mis);
+        ps += (tcs > 3 || qcs > 3) ? sc_amb : (tcs == qcs ? sc_match : sc_mis);
+        const int32_t dlt = p0 - ps;
+        if (dlt > best) best = dlt;
+      }
+      lb = best + ps - (delta != 0 ? q + e * (delta < 0 ? -delta : delta) : 0);
+    }
+    lb = __reduce_max_sync(full, lb);
+    const int X = P.a * m - q - lb;
+    const int Dd = X <= 0 ? 0 : X / e;
+    if (m + Dd < T) T = m + Dd;
+    __syncwarp();  // the staging bytes are dead from here on; the slice becomes direction storage
+  }
+  const int nblk = (m + 31) >> 5;
+  // direction bytes: block b holds rows [32b, 32b+rows_b) as [step][row]; shared memory when the
+  // whole matrix fits the warp's slice, else the HBM scratch
+  const int rows_last = m - (nblk - 1) * 32;
+  const int dir_bytes = (nblk - 1) * 32 * (T + 31) + rows_last * (T + rows_last - 1);
+  uint8_t* dir = dir_bytes <= dir_s_cap ? dir_s : dir_g;
+  int32_t ezmax = 0, mqe = kNegInf, mqe_t = -1;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int j = blk * 32 + lane;
+    const int rows = m - blk * 32 < 32 ? m - blk * 32 : 32;
+    const bool row_ok = lane < rows;
+    const int qc = row_ok ? qf(j) : 4;
+    int32_t e_cur = -(q + e * (j + 1)) - q - e;  // E(0, j)
+    int32_t diag = j == 0 ? 0 : -(q + e * j);    // H(-1, j-1)
+    int32_t hf = 0;                               // packed (H low16, F-out high16) of my last cell
+    uint8_t* dblk = dir + (size_t)blk * 32 * (T + 31);
+    const int nsteps = T + rows - 1;
+    const bool save_bnd = blk + 1 < nblk;
+    // Per 32 steps every lane fetches one target base (and one packed boundary cell for row
+    // blocks > 0): coalesced, off the per-step dependency chain, and the step body stays
+    // branch-free — lane l takes its base t[s-l] with one indexed shuffle out of the current or
+    // previous 32-base register window, lane 0 takes its boundary input with a broadcast.
+    int tprev = 4, tcur = 4, bcur = 0;
+    for (int s0 = 0; s0 < nsteps; s0 += 32) {
+      const int ti = s0 + lane;
+      tprev = tcur;
+      tcur = ti < T ? tf(ti) : 4;
+      if (blk > 0) bcur = ti < T ? Hb[ti] : 0;
+      const int kmax = nsteps - s0 < 32 ? nsteps - s0 : 32;
+      for (int k = 0; k < kmax; ++k) {
+        const int s = s0 + k;
+        const int i = s - lane;
+        const int tc = __shfl_sync(full, k >= lane ? tcur : tprev, (k - lane) & 31);
+        int up_hf = __shfl_up_sync(full, hf, 1);
+        int feed;
+        if (blk == 0) {
+          const int32_t h0 = -(q + e * (s + 1));
+          feed = (int)(((uint32_t)h0 & 0xffffu) | ((uint32_t)(h0 - q - e) << 16));
+        } else {
+          feed = __shfl_sync(full, bcur, k);
+        }
+        if (lane == 0) up_hf = feed;
+        const int32_t up_h = (int32_t)(int16_t)(up_hf & 0xffff);
+        const int32_t up_f = up_hf >> 16;
+        if (row_ok && i >= 0 && i < T) {
+          const int32_t sc = (tc > 3 || qc > 3) ? sc_amb : (tc == qc ? sc_match : sc_mis);
+          uint8_t d;
+          int32_t en, fn;
+          const int32_t h = ext_cell(diag + sc, e_cur, up_f, q, e, right, &d, &en, &fn);
+          dblk[s * rows + lane] = d;
+          diag = up_h;
+          e_cur = en;
+          hf = (int)(((uint32_t)h & 0xffffu) | ((uint32_t)fn << 16));
+          if (h > ezmax) ezmax = h;
+          if (j == m - 1 && h > mqe) mqe = h, mqe_t = i;
+          if (save_bnd && lane == 31) Hb[i] = hf;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  ezmax = __reduce_max_sync(full, ezmax);
+  mqe_t = __shfl_sync(full, mqe_t, (m - 1) & 31);
+  __syncwarp();
+  // ksw_backtrack, warp-cooperative: the path mostly runs down the diagonal, so the 32 lanes
+  // fetch the direction bytes of the next 32 diagonal cells in one go and the (warp-uniform)
+  // state machine walks them by shuffle; a gap step leaves the diagonal and refetches.  One
+  // memory round trip per <= 32 steps instead of one per step (the bytes of a long tail sit in L2).
+  // Runs of equal ops are counted in registers and pushed once (same result as ksw_push_cigar).
+  CigBuf cb{wcig, 0, D.wcig_cap};
+  {
+    auto dirf = [&](int i, int j) -> uint32_t {
+      const int b = j >> 5, l = j & 31;
+      const int rows = m - b * 32 < 32 ? m - b * 32 : 32;
+      return dir[(size_t)b * 32 * (T + 31) + (size_t)(i + l) * rows + l];
+    };
+    int i = mqe_t, j = m - 1, state = 0;
+    uint32_t run_op = 0;
+    int run_len = 0;
+    auto emit = [&](uint32_t op) {
+      if (run_len > 0 && op == run_op) {
+        ++run_len;
+      } else {
+        if (run_len > 0 && lane == 0) cb.push(run_op, run_len);
+        run_op = op, run_len = 1;
+      }
+    };
+    while (i >= 0 && j >= 0) {
+      const int wi = i - lane, wj = j - lane;
+      const uint32_t dv = (wi >= 0 && wj >= 0) ? dirf(wi, wj) : 0u;
+      for (int k = 0; k < 32; ++k) {
+        const uint32_t tmp = __shfl_sync(full, dv, k);
+        if (state == 0) state = tmp & 7;
+        else if (!(tmp >> (state + 2) & 1)) state = 0;
+        if (state == 0) state = tmp & 7;
+        if (state == 0) {
+          emit(0), --i, --j;
+          if (i < 0 || j < 0) break;
+        } else {
+          if (state == 1) emit(2), --i;
+          else emit(1), --j;
+          break;  // off this diagonal
+        }
+      }
+    }
+    if (lane == 0) {
+      if (run_len > 0) cb.push(run_op, run_len);
+      if (i >= 0) cb.push(2, i + 1);
+      if (j >= 0) cb.push(1, j + 1);
+      if (side != 0 && cb.n <= cb.cap) {  // right extension: ksw2 reverses the backtrack order
+        for (int a = 0; a < cb.n >> 1; ++a) {
+          const uint32_t t = cb.ops[a];
+          cb.ops[a] = cb.ops[cb.n - 1 - a];
+          cb.ops[cb.n - 1 - a] = t;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    ExtRec& E = reg->ext[side];
+    E.max = ezmax;
+    E.mqe_t = mqe_t;
+    E.n_cig = cb.n;
+    if (cb.n > D.wcig_cap) {
+      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+      E.n_cig = 0;
+    } else if (cb.n <= kInlineCig) {
+      E.cig_off = -1;
+      for (int c = 0; c < cb.n; ++c) E.inl[c] = wcig[c];
+    } else {
+      const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)cb.n);
+      if (o + cb.n > D.ext_arena_cap) {
+        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
+        E.n_cig = 0;
+      } else {
+        E.cig_off = (int32_t)o;
+        for (int c = 0; c < cb.n; ++c) D.ext_arena[o + c] = wcig[c];
+      }
+    }
+    *cells += (long long)m * T;
+    *cells_full += (long long)m * n;
+  }
+  __syncwarp();
+}
+
+#ifdef LGR_EXT_HIST
+__device__ unsigned long long g_ext_hist[256];  // [m] task count, [128 + m] warp cycles (debug builds only)
+#endif
+
+// Phase B1 kernel: the extensions no closed form covered, one warp per queued extension, through
+// the anti-diagonal wavefront.  Nothing but DP code lives here, so resident warps share one hot loop.
+constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
+
+__global__ void __launch_bounds__(128, LGR_EXT_MINB) k_ext_warp(const __grid_constant__ Dev D) {
+  __shared__ uint8_t s_dir[4 * kDirSmemPerWarp];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint8_t* dir = D.dir_scratch + (size_t)gwarp * D.dir_per_warp;
+  int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
+  int32_t* Fb = Hb + D.bnd_per_warp / 2;
+  uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
+  long long cells = 0, cells_full = 0;
+  long long n_task = D.ctr[C_NTASK];
+  if (n_task > D.tasks_cap) n_task = D.tasks_cap;
+  for (;;) {
+    long long t = 0;
+    if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
+    t = __shfl_sync(full, t, 0);
+    if (t >= n_task) break;
+    const TaskRec tk = D.tasks[t];
+    const uint8_t* hapc = D.hap_codes + D.hap_off[tk.hap];
+    const int64_t roff = D.read_off[tk.read];
+    ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
+    long long c1 = 0, c2 = 0;
+#ifdef LGR_EXT_HIST
+    const long long t_begin = clock64();
+#endif
+    ext_dp_warp(D, &D.regs[tk.reg], tk.side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig,
+                &c1, &c2);
+#ifdef LGR_EXT_HIST
+    if (lane == 0) {
+      int mb = D.regs[tk.reg].ext[tk.side].m;
+      mb = mb > 127 ? 127 : mb;
+      atomicAdd(&g_ext_hist[mb], 1ULL);
+      atomicAdd(&g_ext_hist[128 + mb], (unsigned long long)(clock64() - t_begin));
+    }
+#endif
+    cells += c1, cells_full += c2;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)cells);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)cells_full);
+  }
+}
+
+}  // namespace
+
+#endif  // LANCET2_B200_LGR_KERNELS_EXT_CUH_
