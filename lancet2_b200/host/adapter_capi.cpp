@@ -184,6 +184,52 @@ int lgr_adapter_genotype_dump(int device, const lgr_batch_in* in, const char* na
   }
 }
 
+// Host logic without a GPU (CPU test suite): pack the batch's groups through PackedJob/PackedBatch
+// and compare the resulting C-ABI SoA arrays with the arrays the batch came from (a round trip
+// through the C++ view), then run AddToTable (PackedBatch::BuildResult) on caller-provided
+// lgr_assign records (the oracle's, in the tests) and dump the evidence.  Returns the number of
+// mismatching array elements of the packing round trip in *pack_mismatches.
+int lgr_adapter_host_logic_dump(const lgr_batch_in* in, const char* names, const char* samples, const int* sample_id,
+                                const long long* start0, const long long* isize, const unsigned short* sam_flag,
+                                const unsigned char* mapq, const unsigned char* softclip, const lgr_assign* assign,
+                                long long* pack_mismatches, char* out, long long cap) {
+  try {
+    JobSet js;
+    BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
+    lancet_gpu::PackedBatch pb;
+    pb.Pack(js.jobs.data(), js.jobs.size(), 0);
+    const lgr_batch_in& p = pb.In();
+    long long bad = 0;
+    bad += p.n_groups != in->n_groups || p.n_haps != in->n_haps || p.n_reads != in->n_reads || p.n_vars != in->n_vars;
+    if (!bad) {
+      for (int g = 0; g <= in->n_groups; ++g)
+        bad += p.grp_hap_begin[g] != in->grp_hap_begin[g] || p.grp_read_begin[g] != in->grp_read_begin[g] ||
+               p.grp_var_begin[g] != in->grp_var_begin[g];
+      for (int h = 0; h <= in->n_haps; ++h) bad += p.hap_off[h] != in->hap_off[h];
+      for (int r = 0; r <= in->n_reads; ++r) bad += p.read_off[r] != in->read_off[r];
+      for (int v = 0; v <= in->n_vars; ++v) bad += p.var_hap_off[v] != in->var_hap_off[v];
+      bad += std::memcmp(p.hap_bases, in->hap_bases, (size_t)in->hap_off[in->n_haps]) != 0;
+      bad += std::memcmp(p.read_bases, in->read_bases, (size_t)in->read_off[in->n_reads]) != 0;
+      bad += std::memcmp(p.read_quals, in->read_quals, (size_t)in->read_off[in->n_reads]) != 0;
+      for (int r = 0; r < in->n_reads; ++r) bad += p.read_name_hash[r] != in->read_name_hash[r];
+      for (long long x = 0; x < in->var_hap_off[in->n_vars]; ++x)
+        bad += p.var_start[x] != in->var_start[x] || p.var_len[x] != in->var_len[x] || p.var_allele[x] != in->var_allele[x];
+      bad += p.grp_mid_occ != nullptr;  // latched value 0 → per-group derivation left to the device
+    }
+    if (pack_mismatches) *pack_mismatches = bad;
+    std::vector<lancet_gpu::Result> res(js.jobs.size());
+    long long off = 0;
+    for (std::size_t g = 0; g < js.jobs.size(); ++g) {
+      res[g] = lancet_gpu::PackedBatch::BuildResult(js.jobs[g], assign + off, X31OfView);
+      off += (long long)(js.jobs[g].n_reads * js.jobs[g].n_variants);
+    }
+    return WriteOut(DumpResults(in, js, res), out, cap);
+  } catch (const std::exception& e) {
+    std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
+    return -2;
+  }
+}
+
 // Same batch, but every group is a separate blocking GenotypeBatcher::Genotype() call issued
 // from `n_threads` worker threads (round-robin over the groups, `rounds` times), the way
 // Lancet2's workers would call it.  counters[9] = batches, jobs, pairs, max jobs in one batch,

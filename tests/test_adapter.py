@@ -51,30 +51,8 @@ def test_add_evidence_matches_reference_golden(lib):
         assert add_evidence_dump(lib, c["stream"]) == c["dump"]
 
 
-@pytest.mark.gpu
-def test_adapter_genotype_matches_oracle_evidence(lib):
-    rng = np.random.default_rng(5)
-    groups = synth.make_region_groups(9, ref_len=40_000)[:6] + synth.make_groups(3, 2, n_reads=64, n_haps=5, hap_len=700)
-    batch = abi.Batch(groups)
-    nr = batch.n_reads
-    names = [nm for g in groups for nm in g.names]
-    sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
-    start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
-    isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
-    flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
-    mapq = rng.integers(0, 61, nr).astype(np.uint8)
-    softclip = rng.integers(0, 2, nr).astype(np.uint8)
-    bi = batch.c_struct()
-    buf = C.create_string_buffer(64 << 20)
-    n = lib.lgr_adapter_genotype_dump(0, C.byref(bi), b"\0".join(x.encode() for x in names) + b"\0", b"normal\0tumor\0",
-                                      sample_id.ctypes.data, start0.ctypes.data, isize.ctypes.data, flag.ctypes.data,
-                                      mapq.ctypes.data, softclip.ctypes.data, buf, len(buf))
-    assert n >= 0, buf.value.decode()
-    got = buf.value.decode().splitlines()
-
-    # expected: oracle assignments → AddToTable (genotyper.cpp:423-456) → AddEvidence
-    prm = O.default_params()
-    want, _ = O.oracle_genotype(batch, prm)
+def expected_evidence(lib, batch, groups, names, sample_id, start0, isize, flag, mapq, softclip, want):
+    """oracle assignments → AddToTable (genotyper.cpp:423-456) → the reference-pinned AddEvidence dump"""
     expect = []
     snames = ["normal", "tumor"]
     for g_i, g in enumerate(groups):
@@ -108,6 +86,66 @@ def test_adapter_genotype_matches_oracle_evidence(lib):
                 for line in add_evidence_dump(lib, streams[s]).splitlines():
                     al, rest = line.split("|", 1)
                     expect.append(f"G{g_i} V{v} S{snames[s]} {al}|{rest}")
+    return expect
+
+
+def test_host_logic_packing_and_add_to_table_without_gpu(lib):
+    """CPU-only: PackedJob/PackedBatch must reproduce the batch's SoA arrays exactly, and
+    PackedBatch::BuildResult (AddToTable) fed with the ORACLE's assignments must give the evidence
+    the reference-pinned AddEvidence gives — the adapter's host half, no device involved."""
+    rng = np.random.default_rng(17)
+    groups = synth.make_region_groups(9, ref_len=40_000)[:5] + synth.make_groups(3, 2, n_reads=48, n_haps=4, hap_len=600)
+    batch = abi.Batch(groups)
+    nr = batch.n_reads
+    names = [nm for g in groups for nm in g.names]
+    sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
+    start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
+    isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
+    flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
+    mapq = rng.integers(0, 61, nr).astype(np.uint8)
+    softclip = rng.integers(0, 2, nr).astype(np.uint8)
+    want, _ = O.oracle_genotype(batch, O.default_params(), n_threads=4)
+    lib.lgr_adapter_host_logic_dump.argtypes = [C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + [C.c_void_p] * 7 + \
+        [C.POINTER(C.c_longlong), C.c_char_p, C.c_longlong]
+    lib.lgr_adapter_host_logic_dump.restype = C.c_int
+    bi = batch.c_struct()
+    buf = C.create_string_buffer(64 << 20)
+    bad = C.c_longlong(-1)
+    n = lib.lgr_adapter_host_logic_dump(C.byref(bi), b"\0".join(x.encode() for x in names) + b"\0", b"normal\0tumor\0",
+                                        sample_id.ctypes.data, start0.ctypes.data, isize.ctypes.data, flag.ctypes.data,
+                                        mapq.ctypes.data, softclip.ctypes.data, want.assign.ctypes.data, C.byref(bad), buf, len(buf))
+    assert n >= 0, buf.value.decode()
+    assert bad.value == 0
+    got = buf.value.decode().splitlines()
+    expect = expected_evidence(lib, batch, groups, names, sample_id, start0, isize, flag, mapq, softclip, want)
+    assert len(got) == len(expect) and len(got) > 10
+    assert got == expect
+
+
+@pytest.mark.gpu
+def test_adapter_genotype_matches_oracle_evidence(lib):
+    rng = np.random.default_rng(5)
+    groups = synth.make_region_groups(9, ref_len=40_000)[:6] + synth.make_groups(3, 2, n_reads=64, n_haps=5, hap_len=700)
+    batch = abi.Batch(groups)
+    nr = batch.n_reads
+    names = [nm for g in groups for nm in g.names]
+    sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
+    start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
+    isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
+    flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
+    mapq = rng.integers(0, 61, nr).astype(np.uint8)
+    softclip = rng.integers(0, 2, nr).astype(np.uint8)
+    bi = batch.c_struct()
+    buf = C.create_string_buffer(64 << 20)
+    n = lib.lgr_adapter_genotype_dump(0, C.byref(bi), b"\0".join(x.encode() for x in names) + b"\0", b"normal\0tumor\0",
+                                      sample_id.ctypes.data, start0.ctypes.data, isize.ctypes.data, flag.ctypes.data,
+                                      mapq.ctypes.data, softclip.ctypes.data, buf, len(buf))
+    assert n >= 0, buf.value.decode()
+    got = buf.value.decode().splitlines()
+
+    prm = O.default_params()
+    want, _ = O.oracle_genotype(batch, prm)
+    expect = expected_evidence(lib, batch, groups, names, sample_id, start0, isize, flag, mapq, softclip, want)
     assert len(got) == len(expect) and len(got) > 10
     assert got == expect
 
