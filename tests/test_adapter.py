@@ -51,10 +51,10 @@ def test_add_evidence_matches_reference_golden(lib):
         assert add_evidence_dump(lib, c["stream"]) == c["dump"]
 
 
-def expected_evidence(lib, batch, groups, names, sample_id, start0, isize, flag, mapq, softclip, want):
+def expected_evidence(lib, batch, groups, names, sample_id, start0, isize, flag, mapq, softclip, want,
+                      snames=("normal", "tumor")):
     """oracle assignments → AddToTable (genotyper.cpp:423-456) → the reference-pinned AddEvidence dump"""
     expect = []
-    snames = ["normal", "tumor"]
     for g_i, g in enumerate(groups):
         r0, r1 = batch.grp_read_begin[g_i], batch.grp_read_begin[g_i + 1]
         for v in range(len(g.variants)):
@@ -98,7 +98,9 @@ def test_host_logic_packing_and_add_to_table_without_gpu(lib):
     batch = abi.Batch(groups)
     nr = batch.n_reads
     names = [nm for g in groups for nm in g.names]
-    sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
+    # four samples (BASELINE configs[3]: multi-sample calling): sample identity only matters to AddToTable
+    snames = ("sampleA", "sampleB", "sampleC", "sampleD")
+    sample_id = rng.integers(0, 4, nr).astype(np.int32)
     start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
     isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
     flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
@@ -111,13 +113,14 @@ def test_host_logic_packing_and_add_to_table_without_gpu(lib):
     bi = batch.c_struct()
     buf = C.create_string_buffer(64 << 20)
     bad = C.c_longlong(-1)
-    n = lib.lgr_adapter_host_logic_dump(C.byref(bi), b"\0".join(x.encode() for x in names) + b"\0", b"normal\0tumor\0",
+    n = lib.lgr_adapter_host_logic_dump(C.byref(bi), b"\0".join(x.encode() for x in names) + b"\0",
+                                        b"\0".join(s.encode() for s in snames) + b"\0",
                                         sample_id.ctypes.data, start0.ctypes.data, isize.ctypes.data, flag.ctypes.data,
                                         mapq.ctypes.data, softclip.ctypes.data, want.assign.ctypes.data, C.byref(bad), buf, len(buf))
     assert n >= 0, buf.value.decode()
     assert bad.value == 0
     got = buf.value.decode().splitlines()
-    expect = expected_evidence(lib, batch, groups, names, sample_id, start0, isize, flag, mapq, softclip, want)
+    expect = expected_evidence(lib, batch, groups, names, sample_id, start0, isize, flag, mapq, softclip, want, snames)
     assert len(got) == len(expect) and len(got) > 10
     assert got == expect
 
