@@ -189,6 +189,10 @@ struct TrackBlock {  // surviving regs of one pair (mm_set_parent / mm_select_su
   uint64_t key[kTrack];
   int32_t qs[kTrack], qe[kTrack], rs[kTrack], re[kTrack], score[kTrack];
 };
+#ifndef LGR_FIN_CHUNK
+#define LGR_FIN_CHUNK 8
+#endif
+constexpr int kFinChunk = LGR_FIN_CHUNK;  // pairs a warp takes from the finish queue per atomic
 constexpr int kFinSmemCig = 64;  // cigar ops of a reg kept in shared memory; longer ones use the HBM scratch
 
 __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
@@ -277,11 +281,17 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_
   TrackBlock* trk = &s_trk[threadIdx.x >> 5];
   uint32_t* scig = s_cig[threadIdx.x >> 5];
   long long n_aligned = 0;
+  // pairs are taken kFinChunk at a time: the work per pair is uniform enough here, and one queue
+  // atomic per pair (hundreds of thousands on one address) is a measurable share of the kernel
+  long long chunk_next = 0, chunk_end = 0;
   for (;;) {
-    long long pair = 0;
-    if (lane == 0) pair = atomicAdd((unsigned long long*)&D.ctr[C_FINPOS], 1ULL);
-    pair = __shfl_sync(full, pair, 0);
-    if (pair >= D.n_pairs) break;
+    if (chunk_next >= chunk_end) {
+      if (lane == 0) chunk_next = atomicAdd((unsigned long long*)&D.ctr[C_FINPOS], (unsigned long long)kFinChunk);
+      chunk_next = __shfl_sync(full, chunk_next, 0);
+      if (chunk_next >= D.n_pairs) break;
+      chunk_end = chunk_next + kFinChunk < D.n_pairs ? chunk_next + kFinChunk : D.n_pairs;
+    }
+    const long long pair = chunk_next++;
     const PairReg d = D.pair_reg[pair];
     if (d.n <= 0) continue;
     const int read = d.read;
