@@ -131,6 +131,26 @@ def pin_result(res: abi.Result, torch):
     res._pinned = keep
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices)
+    also write to fd 1, so keep a private handle on the real stdout and point fd 1 at stderr for
+    everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle on all host cores, bounded sample per step."""
     if rank != 0:
@@ -165,7 +185,7 @@ def run_reference(args, rank, world):
             "config": {"workload": desc, "note": "CPU restatement of the reference path (oracle port, not Lancet2/minimap2 binaries)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def main():
@@ -178,6 +198,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-inflight", type=int, default=3)
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,8 +214,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the realignment path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / diagnostics go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from lancet2_b200.realign import GpuRealigner
@@ -367,7 +386,7 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": sb.n_pairs * passes / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {len(sel)} of {len(groups)} groups ({sb.n_pairs} pairs) x {passes} passes, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
