@@ -181,10 +181,11 @@ typedef struct lgr_batch_out {
 /* per-batch device timing + work counters (filled by lgr_genotype_batch) */
 typedef struct lgr_stats {
   float ms_h2d, ms_kernels, ms_d2h; /* CUDA-event times on the ctx stream */
-  float ms_k_index, ms_k_sketch;    /* haplotype tables; read sketches */
-  float ms_k_map;                   /* k_map fast pass alone (the dominant kernel) */
-  float ms_k_ext;                   /* overflow pass + k_ext_big + k_finish (incl. host round trips) */
-  float ms_k_assign;
+  float ms_k_index;                 /* encode + haplotype sketch/sort/mid_occ, with the read sketch beside it on the second stream */
+  float ms_k_sketch;                /* k_read_filter (mm_seed_mz_flt), after the two streams join */
+  float ms_k_map;                   /* k_chain_warp alone (the dominant kernel) */
+  float ms_k_ext;                   /* k_chain_overflow + k_ext_warp + k_finish_warp */
+  float ms_k_assign;                /* k_assign */
   int64_t n_pairs, n_aligned;
   int64_t dp_cells;        /* extension-DP cells actually computed       */
   int64_t dp_cells_full;   /* cells of the un-pruned rectangles the reference computes */
