@@ -344,6 +344,7 @@ def main():
                        "l2": "flushed between timed steps (512 MiB write, untimed)", "timing": "CUDA events on the library stream"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(e2e_st.h2d_bytes), "d2h_bytes_per_step": int(e2e_st.d2h_bytes),
                     "batches_in_flight": depth,
+                    "genotype_calls_per_s": e2e_v * batch.n_groups / max(1, batch.n_pairs),  # groups (= Genotype() payloads ~ windows) per second
                     "synchronous_value": total_pairs * args.steps / e2e_single_s,
                     "ms_h2d": e2e_st.ms_h2d, "ms_kernels": e2e_st.ms_kernels, "ms_d2h": e2e_st.ms_d2h,
                     "note": "every step is one lgr_submit+lgr_wait of the whole batch from pinned host buffers (H2D + kernels + D2H per step, one host thread); batches_in_flight steps are outstanding so copies overlap kernels; synchronous_value is the same through lgr_genotype_batch, one call at a time"},
