@@ -28,7 +28,12 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_work) break;
     if (item + lane < n_work) {
-      const int r = D.ovf_read[item + lane], h = D.ovf_hap[item + lane];
+      const int r = D.ovf_read[item + lane];
+      // bit 30: the warp kernel had already counted this pair's anchors and chain evaluations when
+      // it ran out of chain slots (kRegCap); do not count them twice
+      const bool counted = (D.ovf_hap[item + lane] >> 30) & 1;
+      const int h = D.ovf_hap[item + lane] & ~(1 << 30);
+      const ChainCounters ctr_before = ctr;
       const int g = D.read_grp[r];
       const int64_t pair = D.pair_off[r] + (h - D.grp_hap_begin[g]);
       const int64_t roff = D.read_off[r], hoff = D.hap_off[h];
@@ -38,6 +43,7 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
       PairIn pin{rv, D.hap_codes + hoff, hlen, D.idx + hoff, D.idx_n[h], D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], D.grp_mid[g]};
       int n_regs = 0;
       const int st = qlen > 0 ? map_chain_phase<32>(D.P, pin, ws, &rsx, &n_regs, &ctr) : kMapNoHit;
+      if (counted) ctr = ctr_before;
       PairReg pr{0, 0, r, h};
       if (st == kMapOverflow) {
         atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
@@ -655,7 +661,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
       if (lane == 0) {
         if (st == kMapOverflow) {
           const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
-          if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h;
+          if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h | (n_a > 0 ? 1 << 30 : 0);  // n_a > 0: overflowed after counting
           else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
         } else if (st == kMapNoHit) {
           write_invalid(&D.aln[pair]);
