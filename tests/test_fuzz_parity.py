@@ -105,7 +105,11 @@ def test_fuzz_gpu_vs_oracle(seed):
             continue  # option set outside what validate_params admits
         try:
             want, st = O.oracle_genotype(batch, prm, n_threads=8)
-            got, st2 = g.genotype_batch(batch)
+            try:
+                got, st2 = g.genotype_batch(batch)
+            except LgrError as e:
+                assert e.code == -4  # a pair beyond a device cap (e.g. > 16384 anchors in a long repeat): refused loudly
+                continue
             errs = compare_results(batch, want, got)
             assert not errs, "\n".join(errs[:20])
             for f in ("n_aligned", "chain_evals", "n_anchors", "dp_cells_full"):
