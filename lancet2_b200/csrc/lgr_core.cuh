@@ -1288,6 +1288,38 @@ struct ExtTarget {
   LGR_HD int operator()(int i) const { return (side == 0 ? hap[c_rs - 1 - i] : hap[c_re + i]) & 0xf; }
 };
 
+// Scalar statement of the data-dependent column bound the warp kernel computes with one lane
+// per gap length (lgr_kernels_ext.cuh, ext_dp_warp): LB = best score over "main diagonal for p
+// bases, one gap of delta in [-15, 16], shifted diagonal to the end"; columns at or beyond
+// m + floor((a*m - q - LB) / e) can hold neither the first last-row maximum, nor the global
+// maximum, nor a traceback cell.  Same gates and arithmetic as the kernel; the host emulation
+// runs it so that the bound is fuzzed against the un-pruned oracle on the CPU.
+constexpr int kDynPruneMinRowsCore = 12;
+template <typename QF, typename TF>
+LGR_HD int dyn_prune_cols(const DevParams& P, int m, int n, int t_static, const QF& qf, const TF& tf) {
+  if (!(n >= m && P.e > 0 && m >= kDynPruneMinRowsCore)) return t_static;
+  const int32_t sc_match = P.a, sc_mis = -P.b, sc_amb = -P.sc_ambi;
+  int32_t lb = kNegInf;
+  for (int delta = -15; delta <= 16; ++delta) {
+    if (!(delta >= 0 ? m + delta <= n : -delta < m)) continue;
+    const int k = delta < 0 ? -delta : 0;  // inserted query bases
+    int32_t p0 = 0, ps = 0, best = 0;
+    const int steps = m - k;
+    for (int p = 0; p < steps; ++p) {
+      const int tcp = tf(p), tcs = tf(p + (delta > 0 ? delta : 0)), qcp = qf(p), qcs = qf(p + k);
+      p0 += (tcp > 3 || qcp > 3) ? sc_amb : (tcp == qcp ? sc_match : sc_mis);
+      ps += (tcs > 3 || qcs > 3) ? sc_amb : (tcs == qcs ? sc_match : sc_mis);
+      const int32_t dlt = p0 - ps;
+      if (dlt > best) best = dlt;
+    }
+    const int32_t cand = best + ps - (delta != 0 ? P.q + P.e * (delta < 0 ? -delta : delta) : 0);
+    if (cand > lb) lb = cand;
+  }
+  const int X = P.a * m - P.q - lb;
+  const int Dd = X <= 0 ? 0 : X / P.e;
+  return m + Dd < t_static ? m + Dd : t_static;
+}
+
 // run one extension inline (scalar).  dir/hcol/ecol: scratch sized for m x T.
 // `arena`/`arena_used`/`arena_cap`: overflow storage for cigars longer than kInlineCig
 // (host emu and device differ only in how `alloc` bumps the counter).
@@ -1297,9 +1329,9 @@ LGR_HD bool run_ext_scalar(const DevParams& P, const ReadView& rv, const uint8_t
                            uint32_t* arena, Alloc alloc, ChainCounters* ctr) {
   ExtRec& E = reg->ext[side];
   const int m = E.m;
-  const int T = prune_cols(P, m, E.n);
   ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
   ExtTarget tf{hap, side, reg->c_rs, reg->c_re};
+  const int T = dyn_prune_cols(P, m, E.n, prune_cols(P, m, E.n), qf, tf);
   ext_dp_scalar(P, m, T, qf, tf, side == 0, dir, hcol, ecol, &E.max, &E.mqe_t);
   if (ctr) ctr->dp_cells += (int64_t)m * T, ctr->dp_cells_full += (int64_t)m * E.n;
   CigBuf cb{cig_tmp, 0, cig_tmp_cap};
