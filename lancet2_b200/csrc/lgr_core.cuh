@@ -47,6 +47,10 @@ constexpr int kSmallCig = 96;               // cigar runs of such a tail (<= 4*m
 constexpr int kInlineCig = 6;               // cigar ops kept inline in an ExtRec
 constexpr int kMaxWindow = 32;              // minimizer window cap (reference uses w = 5)
 constexpr int32_t kNegInf = -0x40000000;
+#ifdef LGR_CORE_SELFCHECK
+// host emulation only (tests/hostemu): closed forms of the warp kernels checked against the scalar paths
+static long long lgr_selfcheck_failures = 0, lgr_selfcheck_colinear_seen = 0, lgr_selfcheck_ext_seen = 0;
+#endif
 
 // strided view: element i of a per-lane array interleaved over S lanes
 template <typename T, int S>
@@ -1245,6 +1249,36 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
       }
     }
     if (ctr) ctr->chain_evals += n_iter;
+#ifdef LGR_CORE_SELFCHECK
+    // host emulation only: whenever the warp kernel's co-linear precondition holds, its closed
+    // form (p[i] = i-1, f = prefix sum of min(span, gap), sum of min(i, max_skip+2) iterations)
+    // must equal what the scalar loop above just computed
+    {
+      const uint32_t x0 = (uint32_t)sx[0], y0 = (uint32_t)sy[0];
+      const int diag0 = anchor_rpos(x0) - anchor_qpos(y0), span0 = anchor_span(y0);
+      bool ok = true;
+      for (int i = 0; i < n_a && ok; ++i) {
+        const uint32_t x = (uint32_t)sx[i], y = (uint32_t)sy[i];
+        ok = (x >> 31) == (x0 >> 31) && anchor_rpos(x) - anchor_qpos(y) == diag0 && anchor_span(y) == span0;
+        if (ok && i > 0) ok = anchor_rpos(x) > anchor_rpos((uint32_t)sx[i - 1]);
+      }
+      const int tot_span = anchor_rpos((uint32_t)sx[n_a - 1]) - anchor_rpos(x0);
+      if (ok && P.pen_skip == 0.0f && P.max_skip >= 0 && n_a <= P.max_iter && tot_span <= max_dist_x && tot_span <= max_dist_y &&
+          span0 > 0) {
+        ++lgr_selfcheck_colinear_seen;
+        int32_t acc = span0;
+        bool same = f[0] == span0 && p[0] == -1;
+        for (int i = 1; i < n_a && same; ++i) {
+          const int32_t dq = anchor_rpos((uint32_t)sx[i]) - anchor_rpos((uint32_t)sx[i - 1]);
+          acc += dq < span0 ? dq : span0;
+          same = f[i] == acc && p[i] == i - 1;
+        }
+        const long long cap_it = P.max_skip + 2, nm1 = n_a - 1;
+        const long long want_iter = nm1 <= cap_it ? nm1 * (nm1 + 1) / 2 : cap_it * (cap_it + 1) / 2 + (nm1 - cap_it) * cap_it;
+        if (!same || want_iter != (long long)n_iter) ++lgr_selfcheck_failures;
+      }
+    }
+#endif
   }
   return map_chain_tail<S>(P, qlen, in.hap_len, in.name_hash, ws, rsx, n_a, n_regs_out);
 }
@@ -1338,6 +1372,27 @@ LGR_HD bool run_ext_scalar(const DevParams& P, const ReadView& rv, const uint8_t
   ext_backtrack([&](int i, int j) { return dir[i * m + j]; }, m, E.mqe_t, side == 0, cb);
   E.n_cig = cb.n;
   if (cb.n > cig_tmp_cap) return false;
+#ifdef LGR_CORE_SELFCHECK
+  // host emulation only: whenever the warp kernel's exact-match / overhang precondition holds
+  // (warp_ext_exact), its closed form must equal what the DP and traceback just produced
+  if (P.a > 0 && !(E.n < m && (P.q <= 0 || P.e <= 0))) {
+    const int n = E.n, nn = n < m ? n : m;
+    bool same = true;
+    for (int j = 0; j < nn && same; ++j) same = qf(j) == tf(j) && qf(j) < 4;
+    if (same && n < m) same = qf(m - 1) != tf(n - 1);
+    if (same) {
+      ++lgr_selfcheck_ext_seen;
+      bool okc = E.max == nn * P.a && E.mqe_t == nn - 1;
+      if (n >= m) {
+        okc = okc && cb.n == 1 && cig_tmp[0] == ((uint32_t)m << 4);
+      } else {
+        const uint32_t mop = (uint32_t)n << 4, iop = (uint32_t)(m - n) << 4 | 1u;
+        okc = okc && cb.n == 2 && (side == 0 ? (cig_tmp[0] == iop && cig_tmp[1] == mop) : (cig_tmp[0] == mop && cig_tmp[1] == iop));
+      }
+      if (!okc) ++lgr_selfcheck_failures;
+    }
+  }
+#endif
   if (cb.n <= kInlineCig) {
     E.cig_off = -1;
     for (int i = 0; i < cb.n; ++i) E.inl[i] = cig_tmp[i];

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/lancet_gpu_realign.h"
+#define LGR_CORE_SELFCHECK 1  // closed forms of the warp kernels verified against the scalar paths as they run
 #include "../../lancet2_b200/csrc/lgr_core.cuh"
 
 static const double kPhredErr[256] = {
@@ -158,3 +159,9 @@ extern "C" int emu_genotype_batch(const lgr_params* prm, const lgr_batch_in* in,
 
 static_assert(sizeof(lgr::AlnOut) == sizeof(lgr_aln), "AlnOut must mirror lgr_aln");
 static_assert(sizeof(lgr::AssignOut) == sizeof(lgr_assign), "AssignOut must mirror lgr_assign");
+
+// closed-form self checks accumulated by the runs so far: out[0] = failures, out[1] = co-linear
+// chains checked, out[2] = closed-form extensions checked
+extern "C" void emu_selfcheck(long long* out) {
+  out[0] = lgr::lgr_selfcheck_failures, out[1] = lgr::lgr_selfcheck_colinear_seen, out[2] = lgr::lgr_selfcheck_ext_seen;
+}

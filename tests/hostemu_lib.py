@@ -36,3 +36,13 @@ def emu_genotype(batch, params, arena=1 << 20):
     st = abi.LgrStats()
     rc = lib.emu_genotype_batch(C.byref(params), C.byref(bi), C.byref(bo), C.byref(st), 0)
     return rc, res, st
+
+
+def selfcheck():
+    """(failures, co-linear chains checked, closed-form extensions checked) accumulated so far: the host
+    emulation verifies the warp kernels' closed forms against the scalar paths whenever their
+    preconditions hold (LGR_CORE_SELFCHECK in lgr_core.cuh)."""
+    lib = load()
+    out = (C.c_longlong * 3)()
+    lib.emu_selfcheck(out)
+    return int(out[0]), int(out[1]), int(out[2])

@@ -89,6 +89,10 @@ def test_fuzz_scalar_core_vs_oracle(seed):
         errs = compare_results(batch, want, got)
         assert not errs, "\n".join(errs[:20])
         assert (st.chain_evals, st.n_anchors, st.dp_cells_full) == (st2.chain_evals, st2.n_anchors, st2.dp_cells_full)
+    # the closed forms the warp kernels use (co-linear chain, exact-match / overhang extension) were
+    # checked against the scalar loops on every pair whose precondition held
+    failures, n_colinear, n_ext = H.selfcheck()
+    assert failures == 0 and n_colinear > 0 and n_ext > 0, (failures, n_colinear, n_ext)
 
 
 @pytest.mark.gpu

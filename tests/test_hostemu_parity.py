@@ -73,6 +73,7 @@ def test_scalar_core_matches_oracle(name):
     assert not errs, "\n".join(errs[:20])
     assert (st.chain_evals, st.n_anchors, st.dp_cells_full) == (st2.chain_evals, st2.n_anchors, st2.dp_cells_full)
     assert st2.dp_cells <= st2.dp_cells_full
+    assert H.selfcheck()[0] == 0  # closed forms of the warp kernels vs the scalar paths (LGR_CORE_SELFCHECK)
 
 
 def test_fixed_mid_occ_and_group_override():
