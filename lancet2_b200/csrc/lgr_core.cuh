@@ -49,7 +49,7 @@ constexpr int kMaxWindow = 32;              // minimizer window cap (reference u
 constexpr int32_t kNegInf = -0x40000000;
 #ifdef LGR_CORE_SELFCHECK
 // host emulation only (tests/hostemu): closed forms of the warp kernels checked against the scalar paths
-static long long lgr_selfcheck_failures = 0, lgr_selfcheck_colinear_seen = 0, lgr_selfcheck_ext_seen = 0;
+static long long lgr_selfcheck_failures = 0, lgr_selfcheck_colinear_seen = 0, lgr_selfcheck_ext_seen = 0, lgr_selfcheck_tail_seen = 0;
 #endif
 
 // strided view: element i of a per-lane array interleaved over S lanes
@@ -1122,6 +1122,10 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
   auto seedq = ws.arr(A_SEEDQ), seedn = ws.arr(A_SEEDN), seeds = ws.arr(A_SEEDS);
   const int qlen = in.read.qlen;
   *n_regs_out = 0;
+#ifdef LGR_CORE_SELFCHECK
+  bool sc_tail_expected = false;
+  int32_t sc_tail_score = 0;
+#endif
 
   // ---- seed.c: mm_seed_collect_all -------------------------------------------------
   // seedq: q_pos (pos<<1|strand) | span<<20 | tandem<<28 | flt<<29 ; seedn: occurrences ;
@@ -1276,11 +1280,47 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
         const long long cap_it = P.max_skip + 2, nm1 = n_a - 1;
         const long long want_iter = nm1 <= cap_it ? nm1 * (nm1 + 1) / 2 : cap_it * (cap_it + 1) / 2 + (nm1 - cap_it) * cap_it;
         if (!same || want_iter != (long long)n_iter) ++lgr_selfcheck_failures;
+        // ... and the closed-form tail (warp_chain_tail_colinear): one reg spanning all anchors
+        sc_tail_expected = true;
+        sc_tail_score = f[n_a - 1];
       }
     }
 #endif
   }
+#ifdef LGR_CORE_SELFCHECK
+  const uint32_t sc_x0 = (uint32_t)ws.arr(A_SX)[0], sc_y0 = (uint32_t)ws.arr(A_SY)[0];
+  const uint32_t sc_x1 = n_a > 0 ? (uint32_t)ws.arr(A_SX)[n_a - 1] : 0, sc_y1 = n_a > 0 ? (uint32_t)ws.arr(A_SY)[n_a - 1] : 0;
+  const int st_tail = map_chain_tail<S>(P, qlen, in.hap_len, in.name_hash, ws, rsx, n_a, n_regs_out);
+  if (sc_tail_expected) {
+    ++lgr_selfcheck_tail_seen;
+    bool okt;
+    if (!(sc_tail_score >= P.min_sc && n_a >= P.min_cnt)) {
+      okt = st_tail == kMapNoHit;
+    } else {
+      uint32_t hash = in.name_hash;
+      hash ^= wang_hash((uint32_t)qlen) + wang_hash((uint32_t)P.seed);
+      hash = wang_hash(hash);
+      const uint32_t h = (uint32_t)hash64_full((hash64_full(anchor_x64(sc_x0)) + hash64_full(anchor_y64(sc_y0))) ^ hash);
+      const int32_t span = anchor_span(sc_y0);
+      const int32_t rs = anchor_rpos(sc_x0) + 1 - span, qs = anchor_qpos(sc_y0) + 1 - span;
+      const int32_t re = anchor_rpos(sc_x1) + 1, qe = anchor_qpos(sc_y1) + 1;
+      int32_t l = qs;
+      l += l * P.a + P.end_bonus > P.q ? (l * P.a + P.end_bonus - P.q) / P.e : 0;
+      const int32_t rs0 = rs - l > 0 ? rs - l : 0;
+      l = qlen - qe;
+      l += l * P.a + P.end_bonus > P.q ? (l * P.a + P.end_bonus - P.q) / P.e : 0;
+      const int32_t re0 = re + l < in.hap_len ? re + l : in.hap_len;
+      okt = st_tail == kMapOk && *n_regs_out == 1 && ws.arr(R_SCORE)[0] == sc_tail_score && ws.arr(R_CNT)[0] == n_a &&
+            ws.arr(R_AS)[0] == 0 && (uint32_t)ws.arr(R_HASH)[0] == ((uint32_t)n_a ^ h) && ws.arr(R_REV)[0] == (int32_t)(sc_x0 >> 31) &&
+            ws.arr(R_QS)[0] == qs && ws.arr(R_QE)[0] == qe && ws.arr(R_RS)[0] == rs && ws.arr(R_RE)[0] == re &&
+            ws.arr(A_F)[0] == rs0 && ws.arr(A_P)[0] == re0;
+    }
+    if (!okt) ++lgr_selfcheck_failures;
+  }
+  return st_tail;
+#else
   return map_chain_tail<S>(P, qlen, in.hap_len, in.name_hash, ws, rsx, n_a, n_regs_out);
+#endif
 }
 
 // fill a RegRec (without the extension results) from the workspace after map_chain_phase
