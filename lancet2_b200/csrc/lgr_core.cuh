@@ -49,7 +49,7 @@ constexpr int kMaxWindow = 32;              // minimizer window cap (reference u
 constexpr int32_t kNegInf = -0x40000000;
 #ifdef LGR_CORE_SELFCHECK
 // host emulation only (tests/hostemu): closed forms of the warp kernels checked against the scalar paths
-static long long lgr_selfcheck_failures = 0, lgr_selfcheck_colinear_seen = 0, lgr_selfcheck_ext_seen = 0, lgr_selfcheck_tail_seen = 0;
+static long long lgr_selfcheck_failures = 0, lgr_selfcheck_colinear_seen = 0, lgr_selfcheck_ext_seen = 0, lgr_selfcheck_tail_seen = 0, lgr_selfcheck_sorted_seen = 0;
 #endif
 
 // strided view: element i of a per-lane array interleaved over S lanes
@@ -1184,6 +1184,15 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
     }
     if (sorted && (n_a <= 64 || strict)) {
       for (int i = 0; i < n_a; ++i) sx[i] = ax[i], sy[i] = ay[i];
+#ifdef LGR_CORE_SELFCHECK
+      if (n_a > 64) {  // the skipped in-place radix passes must be the identity on a strictly increasing sequence
+        ++lgr_selfcheck_sorted_seen;
+        for (int i = 0; i < n_a; ++i) perm[i] = i;
+        radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
+        for (int i = 0; i < n_a; ++i)
+          if (perm[i] != i) { ++lgr_selfcheck_failures; break; }
+      }
+#endif
     } else {
       // NB: for n_a > 64 an already sorted input is still permuted by the in-place radix
       // passes when keys tie, so only a strictly increasing sequence may skip the emulation.

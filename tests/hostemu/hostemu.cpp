@@ -161,8 +161,9 @@ static_assert(sizeof(lgr::AlnOut) == sizeof(lgr_aln), "AlnOut must mirror lgr_al
 static_assert(sizeof(lgr::AssignOut) == sizeof(lgr_assign), "AssignOut must mirror lgr_assign");
 
 // closed-form self checks accumulated by the runs so far: out[0] = failures, out[1] = co-linear
-// chains checked, out[2] = closed-form extensions checked, out[3] = closed-form chain tails checked
+// chains checked, out[2] = closed-form extensions checked, out[3] = closed-form chain tails checked,
+// out[4] = skipped radix passes (> 64 strictly sorted anchors) checked
 extern "C" void emu_selfcheck(long long* out) {
   out[0] = lgr::lgr_selfcheck_failures, out[1] = lgr::lgr_selfcheck_colinear_seen, out[2] = lgr::lgr_selfcheck_ext_seen;
-  out[3] = lgr::lgr_selfcheck_tail_seen;
+  out[3] = lgr::lgr_selfcheck_tail_seen, out[4] = lgr::lgr_selfcheck_sorted_seen;
 }

@@ -39,10 +39,11 @@ def emu_genotype(batch, params, arena=1 << 20):
 
 
 def selfcheck():
-    """(failures, co-linear chains checked, closed-form extensions checked, closed-form chain tails checked) so far: the host
+    """(failures, co-linear chains checked, closed-form extensions checked, closed-form chain tails checked,
+    skipped radix passes checked) so far: the host
     emulation verifies the warp kernels' closed forms against the scalar paths whenever their
     preconditions hold (LGR_CORE_SELFCHECK in lgr_core.cuh)."""
     lib = load()
-    out = (C.c_longlong * 4)()
+    out = (C.c_longlong * 5)()
     lib.emu_selfcheck(out)
-    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
+    return tuple(int(x) for x in out)

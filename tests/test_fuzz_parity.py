@@ -91,7 +91,7 @@ def test_fuzz_scalar_core_vs_oracle(seed):
         assert (st.chain_evals, st.n_anchors, st.dp_cells_full) == (st2.chain_evals, st2.n_anchors, st2.dp_cells_full)
     # the closed forms the warp kernels use (co-linear chain, exact-match / overhang extension) were
     # checked against the scalar loops on every pair whose precondition held
-    failures, n_colinear, n_ext, n_tail = H.selfcheck()
+    failures, n_colinear, n_ext, n_tail, _ = H.selfcheck()
     assert failures == 0 and n_colinear > 0 and n_ext > 0 and n_tail > 0, (failures, n_colinear, n_ext, n_tail)
 
 
