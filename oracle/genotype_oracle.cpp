@@ -11,7 +11,7 @@
 //   hts::ComputeEditDistance / CigarRefPosToQueryPos  (hts/cigar_utils.h:48-94, 104-139)
 // The minimap2 half is oracle/mm2_restate.cpp (PARITY UNPINNED, see its header);
 // the Lancet-owned half is pinned against the reference's own sources compiled
-// unmodified into oracle/_ref (oracle/Makefile, tests/test_oracle_ref.py) and
+// unmodified into oracle/_ref (oracle/Makefile; golden vectors tests/golden/, tests/test_oracle_scoring.py) and
 // against the 11 known-answer cases of tests/hts/cigar_utils_test.cpp:58-172.
 #include <algorithm>
 #include <atomic>
