@@ -248,6 +248,89 @@ void lgr_free_pinned(void* p);
 /* raw CUDA stream (cudaStream_t) the ctx launches on, for external event timing */
 void* lgr_stream(lgr_ctx* ctx);
 
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md §8f #2 — the direct consumer of the path: VariantSupport aggregation + FORMAT math.
+ *
+ * One *support* is one `caller::VariantSupport` object (one variant x one sample): a stream of
+ * `VariantSupport::ReadEvidence` records in AddToTable's append order
+ * (reference: src/lancet/caller/variant_support.h:64-84, genotyper.cpp:423-456).
+ * lgr_format_metrics replaces, per support:
+ *   VariantSupport::AddEvidence (first-seen read-name dedup)   variant_support.cpp:23-67
+ *   FwdCount/RevCount/TotalAlleleCov, RawPosteriorBaseQual     variant_support.cpp:140-171, posterior_base_qual.cpp:13-40
+ *   RmsMappingQual, StrandBiasLogOR, MeanAlnScore              variant_support.cpp:173-209
+ *   SoftClipAsymmetry, FragLengthDelta                         variant_support.cpp:211-232
+ *   MappingQualCohenD / ReadPosCohenD / BaseQualCohenD         variant_support.cpp:234-263, base/mann_whitney.h:13-65
+ *   AlleleMismatchDelta, ComputeFSSE, ComputeAHDD, ComputeHSE  variant_support.cpp:265-291, variant_support.h:362-412
+ *   ComputePLs / ComputeGQ                                     variant_support.cpp:294-310, genotype_likelihood.cpp:109-163
+ *   ComputeContinuousMixtureLods                               variant_support.cpp:312-335, genotype_likelihood.cpp:165-205
+ * Integer results (counts, PL, GQ) and the three Mann-Whitney effect sizes are exact; the other
+ * f64 metrics are warp-tree sums with CUDA's libm (log10/log2/log/lgamma/pow), i.e. equal to the
+ * reference within 1e-9 relative (the reference's own tests use 1e-6, and its entropy sums run
+ * in abseil's salted hash-map order, so it does not reproduce its own last bits either).
+ * Own context (device buffers + stream), independent of lgr_ctx; no CPU fallback.
+ */
+#define LGR_FMT_MAX_ALLELES 8
+#define LGR_FMT_MAX_GENOTYPES 36 /* K(K+1)/2 at K = 8 */
+/* lgr_evidence_in::flags bits */
+#define LGR_EV_REV 1u         /* ReadEvidence::mStrand == REV   */
+#define LGR_EV_SOFTCLIP 2u    /* ReadEvidence::mIsSoftClipped   */
+#define LGR_EV_PROPER_PAIR 4u /* ReadEvidence::mIsProperPair    */
+/* lgr_format::valid bits (std::optional has a value) */
+#define LGR_FMT_HAS_FLD 1u
+#define LGR_FMT_HAS_MQCD 2u
+#define LGR_FMT_HAS_RPCD 4u
+#define LGR_FMT_HAS_BQCD 8u
+#define LGR_FMT_HAS_ASMD 16u
+#define LGR_FMT_HAS_FSSE 32u
+#define LGR_FMT_HAS_AHDD 64u
+#define LGR_FMT_HAS_HSE 128u
+
+typedef struct lgr_evidence_in {
+  int32_t n_supports;
+  int32_t reserved;
+  int64_t n_evidence;
+  const int64_t* sup_begin;        /* [S+1] support s owns evidence [sup_begin[s], sup_begin[s+1]) */
+  const int32_t* sup_n_alleles;    /* [S] K: alleles of the variant (ComputePLs/ComputeContinuousMixtureLods argument) */
+  const int32_t* sup_variant_len;  /* [S] AlleleMismatchDelta(variant_length) */
+  const int32_t* sup_total_haps;   /* [S] ComputeHSE(total_haplotypes)        */
+  const int64_t* insert_size;      /* [N] mInsertSize     */
+  const int64_t* aln_start;        /* [N] mAlignmentStart */
+  const double* aln_score;         /* [N] mAlnScore       */
+  const double* folded_pos;        /* [N] mFoldedReadPos  */
+  const uint32_t* rname_hash;      /* [N] mRnameHash      */
+  const uint32_t* ref_nm;          /* [N] mRefNm          */
+  const uint32_t* own_hap_nm;      /* [N] mOwnHapNm       */
+  const uint32_t* hap_id;          /* [N] mAssignedHaplotypeId */
+  const uint8_t* allele;           /* [N] mAllele (< K)   */
+  const uint8_t* flags;            /* [N] LGR_EV_*        */
+  const uint8_t* base_qual;        /* [N] mBaseQual       */
+  const uint8_t* map_qual;         /* [N] mMapQual        */
+} lgr_evidence_in;
+
+typedef struct lgr_format {
+  double raw_pbq[LGR_FMT_MAX_ALLELES];  /* RawPosteriorBaseQual(a) */
+  double rms_mq[LGR_FMT_MAX_ALLELES];   /* RmsMappingQual(a)       */
+  double mean_aln[LGR_FMT_MAX_ALLELES]; /* MeanAlnScore(a)         */
+  double cmlod[LGR_FMT_MAX_ALLELES];    /* ComputeContinuousMixtureLods(K)[a] */
+  double sb, sca;                       /* StrandBiasLogOR, SoftClipAsymmetry */
+  double fld, mqcd, rpcd, bqcd, asmd, fsse, ahdd, hse; /* optionals: see `valid` */
+  uint32_t fwd[LGR_FMT_MAX_ALLELES], rev[LGR_FMT_MAX_ALLELES]; /* FwdCount/RevCount */
+  uint32_t soft_clip[LGR_FMT_MAX_ALLELES];                     /* PerAlleleData::mSoftClipCount */
+  uint32_t pl[LGR_FMT_MAX_GENOTYPES];   /* ComputePLs(K), VCF order j*(j+1)/2+i */
+  uint32_t gq;                          /* ComputeGQ(pl) */
+  uint32_t n_alleles;                   /* K */
+  uint32_t valid;                       /* LGR_FMT_HAS_* */
+  uint32_t n_kept;                      /* evidence records that survived the read-name dedup */
+} lgr_format;
+
+typedef struct lgr_fmt_ctx lgr_fmt_ctx;
+int lgr_format_create(int device_ordinal, lgr_fmt_ctx** out);
+void lgr_format_destroy(lgr_fmt_ctx* ctx);
+const char* lgr_format_last_error(const lgr_fmt_ctx* ctx);
+/* H2D of the evidence, k_fmt_dedup + k_fmt_metrics, D2H of out[S]; ms_kernels (may be NULL) =
+ * CUDA-event time of the two kernels. */
+int lgr_format_metrics(lgr_fmt_ctx* ctx, const lgr_evidence_in* in, lgr_format* out, float* ms_kernels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,11 +237,71 @@ class Result:
         return self.n_pairs * (ALN_DTYPE.itemsize + 4 * LGR_CIGAR_INLINE) + self.n_assign * ASSIGN_DTYPE.itemsize
 
 
+# ---- VariantSupport aggregation + FORMAT math (lgr_format_*) ----
+LGR_FMT_MAX_ALLELES = 8
+LGR_FMT_MAX_GENOTYPES = 36
+LGR_EV_REV, LGR_EV_SOFTCLIP, LGR_EV_PROPER_PAIR = 1, 2, 4
+LGR_FMT_HAS = {"fld": 1, "mqcd": 2, "rpcd": 4, "bqcd": 8, "asmd": 16, "fsse": 32, "ahdd": 64, "hse": 128}
+
+# SoA columns of VariantSupport::ReadEvidence (variant_support.h:64-84), in lgr_evidence_in's order
+EVIDENCE_FIELDS = [("insert_size", np.int64), ("aln_start", np.int64), ("aln_score", np.float64),
+                   ("folded_pos", np.float64), ("rname_hash", np.uint32), ("ref_nm", np.uint32),
+                   ("own_hap_nm", np.uint32), ("hap_id", np.uint32), ("allele", np.uint8), ("flags", np.uint8),
+                   ("base_qual", np.uint8), ("map_qual", np.uint8)]
+
+
+class LgrEvidenceIn(C.Structure):
+    _fields_ = [("n_supports", C.c_int32), ("reserved", C.c_int32), ("n_evidence", C.c_int64),
+                ("sup_begin", C.c_void_p), ("sup_n_alleles", C.c_void_p), ("sup_variant_len", C.c_void_p),
+                ("sup_total_haps", C.c_void_p)] + [(name, C.c_void_p) for name, _ in EVIDENCE_FIELDS]
+
+
+# numpy view of lgr_format (one record per support)
+FORMAT_DTYPE = np.dtype([
+    ("raw_pbq", np.float64, (LGR_FMT_MAX_ALLELES,)), ("rms_mq", np.float64, (LGR_FMT_MAX_ALLELES,)),
+    ("mean_aln", np.float64, (LGR_FMT_MAX_ALLELES,)), ("cmlod", np.float64, (LGR_FMT_MAX_ALLELES,)),
+    ("sb", np.float64), ("sca", np.float64), ("fld", np.float64), ("mqcd", np.float64), ("rpcd", np.float64),
+    ("bqcd", np.float64), ("asmd", np.float64), ("fsse", np.float64), ("ahdd", np.float64), ("hse", np.float64),
+    ("fwd", np.uint32, (LGR_FMT_MAX_ALLELES,)), ("rev", np.uint32, (LGR_FMT_MAX_ALLELES,)),
+    ("soft_clip", np.uint32, (LGR_FMT_MAX_ALLELES,)), ("pl", np.uint32, (LGR_FMT_MAX_GENOTYPES,)),
+    ("gq", np.uint32), ("n_alleles", np.uint32), ("valid", np.uint32), ("n_kept", np.uint32)], align=True)
+
+
+class EvidenceBatch:
+    """S supports (one VariantSupport each) packed into the C-ABI's SoA layout.  `supports` is a
+    list of dicts: the EVIDENCE_FIELDS columns (equal lengths) plus n_alleles, variant_len, total_haps."""
+
+    def __init__(self, supports: Sequence[dict]):
+        self.n_supports = len(supports)
+        lens = [len(s["allele"]) for s in supports]
+        self.sup_begin = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        self.n_evidence = int(self.sup_begin[-1])
+        self.sup_n_alleles = np.asarray([s["n_alleles"] for s in supports], dtype=np.int32)
+        self.sup_variant_len = np.asarray([s.get("variant_len", 0) for s in supports], dtype=np.int32)
+        self.sup_total_haps = np.asarray([s.get("total_haps", 2) for s in supports], dtype=np.int32)
+        self.cols = {}
+        for name, dt in EVIDENCE_FIELDS:
+            parts = [np.asarray(s[name], dtype=dt) for s in supports]
+            self.cols[name] = np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0, dt), dtype=dt)
+            if len(self.cols[name]) != self.n_evidence:
+                raise ValueError(f"evidence column {name} has the wrong length")
+
+    def c_struct(self) -> LgrEvidenceIn:
+        st = LgrEvidenceIn()
+        st.n_supports, st.n_evidence = self.n_supports, self.n_evidence
+        for name in ("sup_begin", "sup_n_alleles", "sup_variant_len", "sup_total_haps"):
+            setattr(st, name, getattr(self, name).ctypes.data)
+        for name, _ in EVIDENCE_FIELDS:
+            setattr(st, name, self.cols[name].ctypes.data)
+        return st
+
+
 _SYMBOLS = [
     "lgr_abi_version", "lgr_default_params", "lgr_strerror", "lgr_last_error", "lgr_x31_hash",
     "lgr_pair_offsets", "lgr_create", "lgr_destroy", "lgr_hap_mid_occ", "lgr_genotype_batch",
     "lgr_upload", "lgr_run_resident", "lgr_download", "lgr_stream", "lgr_submit", "lgr_wait",
     "lgr_alloc_pinned", "lgr_free_pinned",
+    "lgr_format_create", "lgr_format_destroy", "lgr_format_last_error", "lgr_format_metrics",
 ]
 
 
@@ -292,4 +352,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.lgr_free_pinned.restype = None
     lib.lgr_stream.argtypes = [C.c_void_p]
     lib.lgr_stream.restype = C.c_void_p
+    lib.lgr_format_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.lgr_format_create.restype = C.c_int
+    lib.lgr_format_destroy.argtypes = [C.c_void_p]
+    lib.lgr_format_destroy.restype = None
+    lib.lgr_format_last_error.argtypes = [C.c_void_p]
+    lib.lgr_format_last_error.restype = C.c_char_p
+    lib.lgr_format_metrics.argtypes = [C.c_void_p, C.POINTER(LgrEvidenceIn), C.c_void_p, C.POINTER(C.c_float)]
+    lib.lgr_format_metrics.restype = C.c_int
     return lib

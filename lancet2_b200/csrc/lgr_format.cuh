@@ -1,0 +1,405 @@
+// lgr_format.cuh — VariantSupport aggregation + FORMAT math for one support (one variant x one
+// sample), written ONCE for the device warp (lgr_format.cu) and for the g++ host emulation
+// (tests/hostemu/format_emu.cpp).  SURVEY.md §8f #2.
+//
+// Mapping: one warp per support.  Every reduction over the support's evidence records is a
+// lane-strided partial (lane l takes records l, l+32, ...) followed by an xor-butterfly, so all
+// 32 lanes end up with the same bits; the scalar math after a reduction is executed uniformly by
+// all lanes and only the leader stores.  The `W` policy supplies `reduce` (shuffles on the
+// device, a loop over 32 emulated lanes on the host), so host and device run the same
+// arithmetic in the same order and differ only in libm (log10/log2/log/lgamma/pow).
+//
+// Reference being restated (file:line in the reference tree, src/lancet/...):
+//   caller/variant_support.cpp:23-67   AddEvidence (first-seen dedup by read-name hash per allele)
+//   caller/variant_support.cpp:140-335 the accessors; caller/variant_support.h:362-412 the three
+//                                      templates (effect size, mean delta, pooled entropy)
+//   base/mann_whitney.h:13-65          MannWhitneyEffectSize
+//   caller/posterior_base_qual.cpp:13-40, caller/genotype_likelihood.cpp:29-205
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/lancet_gpu_realign.h"
+
+#if defined(__CUDACC__)
+#define FMT_HD __host__ __device__ __forceinline__
+#else
+#define FMT_HD inline
+#endif
+
+namespace lgr_fmt {
+
+constexpr int kLanes = 32;
+
+// SoA views of one batch of evidence (device pointers on the device, host pointers in the emulation)
+struct Ev {
+  const int64_t* insert_size;
+  const int64_t* aln_start;
+  const double* aln_score;
+  const double* folded_pos;
+  const uint32_t* rname_hash;
+  const uint32_t* ref_nm;
+  const uint32_t* own_hap_nm;
+  const uint32_t* hap_id;
+  const uint8_t* allele;
+  const uint8_t* flags;
+  const uint8_t* base_qual;
+  const uint8_t* map_qual;
+  const uint8_t* keep;  // result of dedup_keep for every record
+};
+
+template <int ND, int NI>
+struct Acc {
+  double d[ND > 0 ? ND : 1];
+  long long i[NI > 0 ? NI : 1];
+  FMT_HD Acc() {
+    for (int k = 0; k < (ND > 0 ? ND : 1); ++k) d[k] = 0.0;
+    for (int k = 0; k < (NI > 0 ? NI : 1); ++k) i[k] = 0;
+  }
+};
+
+// AddEvidence's try_emplace (variant_support.cpp:28-29): record i survives iff no earlier record
+// of the same support carries the same (allele, read-name hash).
+FMT_HD uint8_t dedup_keep(const uint8_t* allele, const uint32_t* hash, int64_t begin, int64_t i) {
+  const uint8_t a = allele[i];
+  const uint32_t h = hash[i];
+  for (int64_t j = begin; j < i; ++j)
+    if (hash[j] == h && allele[j] == a) return 0;
+  return 1;
+}
+
+// base/mann_whitney.h:47-64 from the exact integer rank statistics:
+// r2 = 2 x (sum of ALT mid-ranks), tie = sum over tie groups of t^3 - t.
+FMT_HD double mw_effect(long long r2, long long tie, long long n_ref_i, long long n_alt_i) {
+  const double n_ref = (double)n_ref_i, n_alt = (double)n_alt_i;
+  const double alt_rank_sum = (double)r2 / 2.0;
+  const double tie_correction = (double)tie;
+  const double u_stat = alt_rank_sum - ((n_alt * (n_alt + 1.0)) / 2.0);
+  const double mean_u = (n_ref * n_alt) / 2.0;
+  const double n_total = (double)(n_ref_i + n_alt_i);
+  const double var_u = (n_ref * n_alt / 12.0) * ((n_total + 1.0) - (tie_correction / (n_total * (n_total - 1.0))));
+  if (var_u <= 0.0) return 0.0;
+  const double z_score = (u_stat - mean_u) / sqrt(var_u);
+  return z_score / sqrt(n_total);
+}
+
+// Mann-Whitney over a byte-valued field: each lane owns 8 of the 256 values and counts, in one
+// pass over the records, how many REF / ALT records equal each of them and how many are smaller.
+template <class W, class Get>
+FMT_HD double mw_bytes(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_ref, long long n_alt, const Get& get) {
+  Acc<0, 2> r = w.template reduce<Acc<0, 2>>([&](int lane) {
+    int eq_ref[8], eq_alt[8], less[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) eq_ref[t] = eq_alt[t] = less[t] = 0;
+    const int v0 = lane * 8;
+    for (int64_t j = b; j < n_end; ++j) {
+      if (!e.keep[j]) continue;
+      const int v = get(j);
+      const int alt = e.allele[j] != 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int eq = v == v0 + t;
+        eq_ref[t] += eq & (alt ^ 1);
+        eq_alt[t] += eq & alt;
+        less[t] += v < v0 + t;
+      }
+    }
+    Acc<0, 2> a;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const long long ts = (long long)eq_ref[t] + eq_alt[t];
+      if (ts == 0) continue;
+      a.i[0] += (long long)eq_alt[t] * (2LL * less[t] + ts + 1);  // 2 x mid-rank = i + 1 + jdx
+      a.i[1] += ts * ts * ts - ts;
+    }
+    return a;
+  });
+  return mw_effect(r.i[0], r.i[1], n_ref, n_alt);
+}
+
+// Mann-Whitney over the f64 folded read positions: rank by counting (no sort, no scratch).
+template <class W>
+FMT_HD double mw_folded(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_ref, long long n_alt) {
+  Acc<0, 2> r = w.template reduce<Acc<0, 2>>([&](int lane) {
+    Acc<0, 2> a;
+    for (int64_t i = b + lane; i < n_end; i += kLanes) {
+      if (!e.keep[i]) continue;
+      const double x = e.folded_pos[i];
+      long long less = 0, eq = 0;
+      for (int64_t j = b; j < n_end; ++j) {
+        if (!e.keep[j]) continue;
+        const double y = e.folded_pos[j];
+        less += y < x;
+        eq += y == x;
+      }
+      if (e.allele[i] != 0) a.i[0] += 2 * less + eq + 1;
+      a.i[1] += eq * eq - 1;  // summed over the eq members of a tie group: t^3 - t
+    }
+    return a;
+  });
+  return mw_effect(r.i[0], r.i[1], n_ref, n_alt);
+}
+
+// variant_support.h:386-412 AltPooledEntropy: normalised Shannon entropy of the pooled ALT
+// records' bins (one term per distinct bin, taken at the bin's first record).
+template <class W, class Bin>
+FMT_HD double alt_entropy(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_alt, double max_bins, const Bin& bin) {
+  const double total = (double)n_alt;
+  Acc<1, 0> r = w.template reduce<Acc<1, 0>>([&](int lane) {
+    Acc<1, 0> a;
+    for (int64_t i = b + lane; i < n_end; i += kLanes) {
+      if (!e.keep[i] || e.allele[i] == 0) continue;
+      const long long key = bin(i);
+      long long count = 0;
+      bool first = true;
+      for (int64_t j = b; j < n_end; ++j) {
+        if (!e.keep[j] || e.allele[j] == 0 || bin(j) != key) continue;
+        if (j < i) first = false;
+        ++count;
+      }
+      if (!first) continue;
+      const double prob = (double)count / total;
+      a.d[0] -= prob * log2(prob);
+    }
+    return a;
+  });
+  const double max_entropy = log2(total < max_bins ? total : max_bins);
+  return max_entropy > 0.0 ? (r.d[0] / max_entropy) : 0.0;
+}
+
+// genotype_likelihood.cpp:29-46 LogDirichletMultinomial
+FMT_HD double log_dm(const int* counts, const double* alphas, int K) {
+  double log_prob = 0.0, alpha_sum = 0.0, count_alpha_sum = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double c = (double)counts[k], al = alphas[k];
+    log_prob += lgamma(c + al) - lgamma(al);
+    alpha_sum += al;
+    count_alpha_sum += c + al;
+  }
+  log_prob += lgamma(alpha_sum) - lgamma(count_alpha_sum);
+  return log_prob;
+}
+
+// genotype_likelihood.cpp:109-163 ComputeGenotypePLs + NormalizeToPLs + ComputeGenotypeQuality
+FMT_HD void genotype_pls(const int* counts, int K, uint32_t* pl, uint32_t* gq) {
+  const double kBackground = 0.005, kOverdispersion = 0.01, kAlphaFloor = 1e-6;
+  const double precision = (1.0 - kOverdispersion) / kOverdispersion;
+  double ll[LGR_FMT_MAX_GENOTYPES];
+  int g = 0;
+  for (int allele_b = 0; allele_b < K; ++allele_b) {
+    for (int allele_a = 0; allele_a <= allele_b; ++allele_a) {
+      double alphas[LGR_FMT_MAX_ALLELES];
+      const double main_mass = 1.0 - kBackground;
+      for (int k = 0; k < K; ++k) {
+        double mu = kBackground / K;
+        if (allele_a == allele_b) {
+          if (k == allele_a) mu += main_mass;
+        } else if (k == allele_a || k == allele_b) {
+          mu += main_mass / 2.0;
+        }
+        const double al = mu * precision;
+        alphas[k] = al > kAlphaFloor ? al : kAlphaFloor;
+      }
+      ll[g++] = log_dm(counts, alphas, K);
+    }
+  }
+  const int G = g;
+  double best = ll[0];
+  for (int i = 1; i < G; ++i) best = ll[i] > best ? ll[i] : best;
+  const double kPlCap = 4294967295.0 / 2.0, kLn10 = 2.302585092994045684;
+  uint32_t min1 = 0xffffffffu, min2 = 0xffffffffu;
+  for (int i = 0; i < G; ++i) {
+    const double raw = -10.0 * (ll[i] - best) / kLn10;
+    const uint32_t v = (uint32_t)round(raw < kPlCap ? raw : kPlCap);
+    pl[i] = v;
+    if (v < min1) {
+      min2 = min1;
+      min1 = v;
+    } else if (v < min2) {
+      min2 = v;
+    }
+  }
+  for (int i = G; i < LGR_FMT_MAX_GENOTYPES; ++i) pl[i] = 0;
+  const uint32_t d = min2 - min1;
+  *gq = G < 2 ? 0u : (d < 99u ? d : 99u);
+}
+
+// genotype_likelihood.cpp:75-84 PileupLogLikelihood under one allele-fraction vector
+template <class W>
+FMT_HD double pileup_loglk(W& w, const Ev& e, int64_t b, int64_t n_end, int K, const double* frac, const double* phred) {
+  double log_lk = 0.0;
+  const double denom = (double)(K - 1 > 1 ? K - 1 : 1);
+  for (int called_as = 0; called_as < K; ++called_as) {
+    const double f = frac[called_as];
+    Acc<2, 0> r = w.template reduce<Acc<2, 0>>([&](int lane) {
+      Acc<2, 0> a;
+      for (int64_t i = b + lane; i < n_end; i += kLanes) {
+        if (!e.keep[i] || e.allele[i] != called_as) continue;
+        const double error_prob = phred[e.base_qual[i]];
+        const double mismatch_prob = error_prob / denom;
+        const double match_bonus = (1.0 - error_prob) - mismatch_prob;
+        const double prob_read = mismatch_prob + (f * match_bonus);
+        const double term = log10(prob_read > 1e-15 ? prob_read : 1e-15);
+        if (e.flags[i] & LGR_EV_REV) a.d[1] += term;
+        else a.d[0] += term;
+      }
+      return a;
+    });
+    log_lk += r.d[0];
+    log_lk += r.d[1];
+  }
+  return log_lk;
+}
+
+// All FORMAT quantities of support [b, n_end).  `phred`: the 256-entry PhredToErrorProb table.
+template <class W>
+FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, int variant_len, int total_haps,
+                            const double* phred, lgr_format* out) {
+  int cov[LGR_FMT_MAX_ALLELES];
+  long long ref_fwd = 0, ref_rev = 0, alt_fwd = 0, alt_rev = 0, ref_sc = 0, alt_sc = 0;
+  long long isz_n[2] = {0, 0}, isz_sum[2] = {0, 0}, refnm_sum[2] = {0, 0}, ownnm_sum[2] = {0, 0};
+  const bool lead = w.leader();
+  if (lead) {
+    out->n_alleles = (uint32_t)K;
+    for (int a = K; a < LGR_FMT_MAX_ALLELES; ++a) {
+      out->raw_pbq[a] = out->rms_mq[a] = out->mean_aln[a] = out->cmlod[a] = 0.0;
+      out->fwd[a] = out->rev[a] = out->soft_clip[a] = 0;
+    }
+  }
+  // ---- per-allele statistics (PerAlleleData vectors, variant_support.cpp:140-209) ----
+  for (int a = 0; a < K; ++a) {
+    Acc<3, 8> r = w.template reduce<Acc<3, 8>>([&](int lane) {
+      Acc<3, 8> acc;
+      for (int64_t i = b + lane; i < n_end; i += kLanes) {
+        if (!e.keep[i] || e.allele[i] != a) continue;
+        const unsigned fl = e.flags[i];
+        if (fl & LGR_EV_REV) acc.i[1] += 1;
+        else acc.i[0] += 1;
+        acc.i[2] += (fl & LGR_EV_SOFTCLIP) ? 1 : 0;
+        const long long mq = e.map_qual[i];
+        acc.i[3] += mq * mq;
+        if ((fl & LGR_EV_PROPER_PAIR) && e.insert_size[i] != 0) acc.i[4] += 1, acc.i[5] += e.insert_size[i];
+        acc.i[6] += e.ref_nm[i];
+        acc.i[7] += e.own_hap_nm[i];
+        acc.d[0] += e.aln_score[i];
+        const double eps = phred[e.base_qual[i]];
+        const double ok = 1.0 - eps;
+        acc.d[1] += log10(eps > 1e-300 ? eps : 1e-300);
+        acc.d[2] += log10(ok > 1e-300 ? ok : 1e-300);
+      }
+      return acc;
+    });
+    const long long cnt = r.i[0] + r.i[1];
+    cov[a] = (int)cnt;
+    const int grp = a == 0 ? 0 : 1;
+    if (a == 0) ref_fwd = r.i[0], ref_rev = r.i[1], ref_sc = r.i[2];
+    else alt_fwd += r.i[0], alt_rev += r.i[1], alt_sc += r.i[2];
+    isz_n[grp] += r.i[4], isz_sum[grp] += r.i[5], refnm_sum[grp] += r.i[6], ownnm_sum[grp] += r.i[7];
+    double pbq = 0.0;
+    if (cnt > 0) {  // posterior_base_qual.cpp:13-40
+      const double log_err = r.d[1], log_ok = r.d[2];
+      const double max_log = log_err > log_ok ? log_err : log_ok;
+      const double min_log = log_err < log_ok ? log_err : log_ok;
+      const double log_sum = max_log + log10(1.0 + pow(10.0, min_log - max_log));
+      pbq = -10.0 * (log_err - log_sum);
+    }
+    if (lead) {
+      out->fwd[a] = (uint32_t)r.i[0], out->rev[a] = (uint32_t)r.i[1], out->soft_clip[a] = (uint32_t)r.i[2];
+      out->rms_mq[a] = cnt > 0 ? sqrt((double)r.i[3] / (double)cnt) : 0.0;
+      out->mean_aln[a] = cnt > 0 ? r.d[0] / (double)cnt : 0.0;
+      out->raw_pbq[a] = pbq;
+    }
+  }
+  const long long n_ref = ref_fwd + ref_rev, n_alt = alt_fwd + alt_rev;
+  uint32_t valid = 0;
+  // ---- StrandBiasLogOR / SoftClipAsymmetry (variant_support.cpp:182-225) ----
+  const double sb = log(((double)(ref_fwd + 1) * (double)(alt_rev + 1)) / ((double)(ref_rev + 1) * (double)(alt_fwd + 1)));
+  const double alt_frac = n_alt > 0 ? (double)alt_sc / (double)n_alt : 0.0;
+  const double ref_frac = n_ref > 0 ? (double)ref_sc / (double)n_ref : 0.0;
+  const double sca = alt_frac - ref_frac;
+  // ---- MeanAltMinusRef users: FLD, ASMD, AHDD (variant_support.h:362-384) ----
+  double fld = 0.0, asmd = 0.0, ahdd = 0.0;
+  if (isz_n[0] > 0 && isz_n[1] > 0) {
+    valid |= LGR_FMT_HAS_FLD;
+    fld = ((double)isz_sum[1] / (double)isz_n[1] - 0.0) - (double)isz_sum[0] / (double)isz_n[0];
+  }
+  if (n_ref > 0 && n_alt > 0) {
+    valid |= LGR_FMT_HAS_ASMD | LGR_FMT_HAS_AHDD | LGR_FMT_HAS_MQCD | LGR_FMT_HAS_RPCD | LGR_FMT_HAS_BQCD;
+    asmd = ((double)refnm_sum[1] / (double)n_alt - (double)variant_len) - (double)refnm_sum[0] / (double)n_ref;
+    ahdd = ((double)ownnm_sum[1] / (double)n_alt - 0.0) - (double)ownnm_sum[0] / (double)n_ref;
+  }
+  // ---- Mann-Whitney effect sizes: MQCD, BQCD, RPCD (variant_support.cpp:234-263) ----
+  double mqcd = 0.0, bqcd = 0.0, rpcd = 0.0;
+  if (n_ref > 0 && n_alt > 0) {
+    mqcd = mw_bytes(w, e, b, n_end, n_ref, n_alt, [&](int64_t j) { return (int)e.map_qual[j]; });
+    bqcd = mw_bytes(w, e, b, n_end, n_ref, n_alt, [&](int64_t j) { return (int)e.base_qual[j]; });
+    rpcd = mw_folded(w, e, b, n_end, n_ref, n_alt);
+  }
+  // ---- pooled-ALT entropies: FSSE (3 bp start bins, <= 20 bins) and HSE (variant_support.cpp:270-291) ----
+  double fsse = 0.0, hse = 0.0;
+  if (n_alt >= 3) {
+    valid |= LGR_FMT_HAS_FSSE;
+    fsse = alt_entropy(w, e, b, n_end, n_alt, 20.0, [&](int64_t j) { return (long long)(e.aln_start[j] / 3); });
+    if (total_haps >= 2) {
+      valid |= LGR_FMT_HAS_HSE;
+      hse = alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, [&](int64_t j) { return (long long)e.hap_id[j]; });
+    }
+  }
+  // ---- PL / GQ from the allele depths (variant_support.cpp:294-310) ----
+  uint32_t pl[LGR_FMT_MAX_GENOTYPES], gq = 0;
+  genotype_pls(cov, K, pl, &gq);
+  // ---- CMLOD (genotype_likelihood.cpp:165-205) ----
+  double lod[LGR_FMT_MAX_ALLELES];
+  for (int a = 0; a < LGR_FMT_MAX_ALLELES; ++a) lod[a] = 0.0;
+  long long total_depth = 0;
+  for (int a = 0; a < K; ++a) total_depth += cov[a];
+  if (K >= 2 && total_depth > 0) {
+    double frac_mle[LGR_FMT_MAX_ALLELES], frac_null[LGR_FMT_MAX_ALLELES];
+    for (int a = 0; a < K; ++a) frac_mle[a] = (double)cov[a] / (double)total_depth;
+    const double ll_mle = pileup_loglk(w, e, b, n_end, K, frac_mle, phred);
+    for (int t = 1; t < K; ++t) {
+      if (cov[t] == 0) continue;
+      for (int a = 0; a < K; ++a) frac_null[a] = frac_mle[a];
+      const double null_mass = frac_null[t];
+      frac_null[t] = 0.0;
+      const double remaining = 1.0 - null_mass;
+      if (remaining <= 0.0) {
+        frac_null[0] = 1.0;
+      } else {
+        for (int a = 0; a < K; ++a) frac_null[a] /= remaining;
+      }
+      const double ll_null = pileup_loglk(w, e, b, n_end, K, frac_null, phred);
+      const double dlt = ll_mle - ll_null;
+      lod[t] = dlt > 0.0 ? dlt : 0.0;
+    }
+  }
+  if (lead) {
+    out->sb = sb, out->sca = sca, out->fld = fld, out->asmd = asmd, out->ahdd = ahdd;
+    out->mqcd = mqcd, out->bqcd = bqcd, out->rpcd = rpcd, out->fsse = fsse, out->hse = hse;
+    for (int g = 0; g < LGR_FMT_MAX_GENOTYPES; ++g) out->pl[g] = pl[g];
+    for (int a = 0; a < K; ++a) out->cmlod[a] = lod[a];
+    out->gq = gq, out->valid = valid, out->n_kept = (uint32_t)(n_ref + n_alt);
+  }
+}
+
+// the xor-butterfly on 32 emulated lanes (host) — bit-identical to the shuffle version because
+// IEEE addition is commutative: at every level both partners add the same two numbers.
+struct WarpHost {
+  FMT_HD bool leader() const { return true; }
+  template <class A, class F>
+  inline A reduce(const F& f) {
+    A p[kLanes], q[kLanes];
+    for (int l = 0; l < kLanes; ++l) p[l] = f(l);
+    constexpr int nd = (int)(sizeof(p[0].d) / sizeof(double)), ni = (int)(sizeof(p[0].i) / sizeof(long long));
+    for (int off = kLanes / 2; off > 0; off >>= 1) {
+      for (int l = 0; l < kLanes; ++l) {
+        for (int k = 0; k < nd; ++k) q[l].d[k] = p[l].d[k] + p[l ^ off].d[k];
+        for (int k = 0; k < ni; ++k) q[l].i[k] = p[l].i[k] + p[l ^ off].i[k];
+      }
+      for (int l = 0; l < kLanes; ++l) p[l] = q[l];
+    }
+    return p[0];
+  }
+};
+
+}  // namespace lgr_fmt

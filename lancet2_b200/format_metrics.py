@@ -1,0 +1,48 @@
+"""Host-side handle of the device FORMAT path: the evidence streams of many
+`caller::VariantSupport` objects in, every FORMAT accessor's value out
+(reference: src/lancet/caller/variant_support.h:60-330).  Plumbing only — the arithmetic is
+k_fmt_dedup / k_fmt_metrics in csrc/lgr_format.cu; there is no CPU implementation here and the
+constructor raises when the CUDA library or a device is missing."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+
+
+class GpuFormatMetrics:
+    def __init__(self, device: int = 0):
+        self._lib = abi.load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.lgr_format_create(device, C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.lgr_format_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise RuntimeError(f"lgr_format_create failed ({self._lib.lgr_strerror(rc).decode()}): {msg}")
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.lgr_format_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, batch: "abi.EvidenceBatch | Sequence[dict]") -> Tuple[np.ndarray, float]:
+        """(records of abi.FORMAT_DTYPE, one per support; CUDA-event ms of the two kernels)."""
+        if not isinstance(batch, abi.EvidenceBatch):
+            batch = abi.EvidenceBatch(batch)
+        out = np.zeros(batch.n_supports, dtype=abi.FORMAT_DTYPE)
+        st = batch.c_struct()
+        ms = C.c_float(0.0)
+        rc = self._lib.lgr_format_metrics(self._ctx, C.byref(st), out.ctypes.data, C.byref(ms))
+        if rc != 0:
+            raise RuntimeError(f"lgr_format_metrics failed ({self._lib.lgr_strerror(rc).decode()}): "
+                               f"{self._lib.lgr_format_last_error(self._ctx).decode()}")
+        return out, float(ms.value)

@@ -150,3 +150,54 @@ extern "C" int ref_add_evidence_dump(int n, const long long* isize, const long l
   std::memcpy(out, s.c_str(), s.size() + 1);
   return (int)s.size();
 }
+
+// ---- every FORMAT accessor of the reference's VariantSupport on one evidence stream,
+// written into the C-ABI's lgr_format so that tests compare field by field.
+#include "../../include/lancet_gpu_realign.h"
+extern "C" int ref_support_metrics(int n, const long long* isize, const long long* start, const double* aln,
+                                   const double* fold, const unsigned* hash, const unsigned* ref_nm,
+                                   const unsigned* own_nm, const unsigned* hap_id, const unsigned char* allele,
+                                   const unsigned char* flags, const unsigned char* bq, const unsigned char* mapq,
+                                   int n_alleles, int variant_len, int total_haps, lgr_format* out) {
+  using namespace lancet::caller;
+  if (n_alleles < 1 || n_alleles > LGR_FMT_MAX_ALLELES) return -1;
+  VariantSupport vs;
+  for (int i = 0; i < n; ++i) {
+    VariantSupport::ReadEvidence ev{};
+    ev.mInsertSize = isize[i], ev.mAlignmentStart = start[i], ev.mAlnScore = aln[i], ev.mFoldedReadPos = fold[i];
+    ev.mRnameHash = hash[i], ev.mRefNm = ref_nm[i], ev.mOwnHapNm = own_nm[i], ev.mAssignedHaplotypeId = hap_id[i];
+    ev.mAllele = allele[i], ev.mStrand = (flags[i] & LGR_EV_REV) ? Strand::REV : Strand::FWD;
+    ev.mBaseQual = bq[i], ev.mMapQual = mapq[i];
+    ev.mIsSoftClipped = (flags[i] & LGR_EV_SOFTCLIP) != 0, ev.mIsProperPair = (flags[i] & LGR_EV_PROPER_PAIR) != 0;
+    vs.AddEvidence(ev);
+  }
+  std::memset(out, 0, sizeof(*out));
+  out->n_alleles = (uint32_t)n_alleles;
+  auto const ad = vs.AlleleData();
+  for (int a = 0; a < n_alleles; ++a) {
+    auto const idx = static_cast<AlleleIndex>(a);
+    out->raw_pbq[a] = vs.RawPosteriorBaseQual(idx), out->rms_mq[a] = vs.RmsMappingQual(idx);
+    out->mean_aln[a] = vs.MeanAlnScore(idx);
+    out->fwd[a] = (uint32_t)vs.FwdCount(idx), out->rev[a] = (uint32_t)vs.RevCount(idx);
+    out->soft_clip[a] = (std::size_t)a < ad.size() ? (uint32_t)ad[a].mSoftClipCount : 0u;
+  }
+  out->n_kept = (uint32_t)vs.TotalSampleCov();
+  out->sb = vs.StrandBiasLogOR(), out->sca = vs.SoftClipAsymmetry();
+  auto opt = [&](std::optional<double> v, uint32_t bit, double* dst) {
+    if (v.has_value()) out->valid |= bit, *dst = *v;
+  };
+  opt(vs.FragLengthDelta(), LGR_FMT_HAS_FLD, &out->fld);
+  opt(vs.MappingQualCohenD(), LGR_FMT_HAS_MQCD, &out->mqcd);
+  opt(vs.ReadPosCohenD(), LGR_FMT_HAS_RPCD, &out->rpcd);
+  opt(vs.BaseQualCohenD(), LGR_FMT_HAS_BQCD, &out->bqcd);
+  opt(vs.AlleleMismatchDelta((std::size_t)variant_len), LGR_FMT_HAS_ASMD, &out->asmd);
+  opt(vs.ComputeFSSE(), LGR_FMT_HAS_FSSE, &out->fsse);
+  opt(vs.ComputeAHDD(), LGR_FMT_HAS_AHDD, &out->ahdd);
+  opt(vs.ComputeHSE((std::size_t)total_haps), LGR_FMT_HAS_HSE, &out->hse);
+  auto const pls = vs.ComputePLs((std::size_t)n_alleles);
+  for (std::size_t g = 0; g < pls.size() && g < LGR_FMT_MAX_GENOTYPES; ++g) out->pl[g] = pls[g];
+  out->gq = VariantSupport::ComputeGQ(absl::MakeConstSpan(pls.data(), pls.size()));
+  auto const lods = vs.ComputeContinuousMixtureLods((std::size_t)n_alleles);
+  for (std::size_t a = 0; a < lods.size() && a < LGR_FMT_MAX_ALLELES; ++a) out->cmlod[a] = lods[a];
+  return 0;
+}

@@ -1,0 +1,86 @@
+"""CPU tests of the FORMAT-math row: the arithmetic the device runs
+(lancet2_b200/csrc/lgr_format.cuh, compiled by g++ with the warp emulated) against the
+reference's own VariantSupport — golden vectors generated from oracle/_ref, the reference's
+known-answer tests, its scipy-derived Mann-Whitney fixture, and oracle/_ref live when present."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import format_lib as F
+from lancet2_b200 import abi
+
+
+def test_struct_layouts_match_the_header():
+    # sizes printed by a C program over include/lancet_gpu_realign.h: 592 / 144
+    assert abi.FORMAT_DTYPE.itemsize == 592
+    assert C.sizeof(abi.LgrEvidenceIn) == 144
+    assert abi.FORMAT_DTYPE.fields["fwd"][1] == 32 * 8 + 10 * 8
+    assert abi.FORMAT_DTYPE.fields["gq"][1] == 32 * 8 + 10 * 8 + 3 * 32 + 36 * 4
+
+
+def test_golden_random_supports():
+    sups, want, _ = F.load_golden()
+    rc, got = F.emu_format(sups)
+    assert rc == 0
+    errs = F.compare_format(want, got)
+    assert not errs, "\n".join(errs[:20])
+
+
+def test_reference_known_answer_cases():
+    cases = F.reference_kat_cases()
+    rc, got = F.emu_format([c[1] for c in cases])
+    assert rc == 0
+    errs = F.check_kats(got)
+    assert not errs, "\n".join(errs)
+
+
+@pytest.mark.parametrize("as_bytes,field", [(True, "mqcd"), (False, "rpcd")])
+def test_scipy_mann_whitney_rows(as_bytes, field):
+    _, _, rows = F.load_golden()
+    rc, got = F.emu_format(F.scipy_supports(rows, as_bytes))
+    assert rc == 0
+    errs = F.check_scipy(rows, got, field)
+    assert not errs, "\n".join(errs)
+
+
+@pytest.mark.skipif(not F.have_ref(), reason="oracle/_ref not built (needs the reference tree)")
+def test_live_reference_random_supports():
+    rng = np.random.default_rng(99)
+    sups = [F.random_support(rng) for _ in range(600)]
+    sups += [F.random_support(rng, n=int(rng.integers(300, 900)), n_alleles=int(rng.integers(2, 4))) for _ in range(8)]
+    rc, got = F.emu_format(sups)
+    assert rc == 0
+    errs = F.compare_format(F.ref_format(sups), got)
+    assert not errs, "\n".join(errs[:20])
+
+
+def test_dedup_is_first_seen_per_allele():
+    # same read-name hash: twice on allele 1 (second dropped, even though its strand differs), once on allele 0 (kept)
+    sup = F.simple_support([(1, 1000, 0, 1, 7), (1, 1010, 0, 1, 7), (0, 1020, 0, 0, 7), (1, 1030, 0, 1, 8)])
+    sup["flags"] = np.array([0, abi.LGR_EV_REV, 0, abi.LGR_EV_REV])
+    rc, got = F.emu_format([sup])
+    assert rc == 0
+    r = got[0]
+    assert (r["n_kept"], r["fwd"][0], r["rev"][0], r["fwd"][1], r["rev"][1]) == (3, 1, 0, 1, 1)
+
+
+def test_results_do_not_depend_on_batch_composition():
+    rng = np.random.default_rng(5)
+    sups = [F.random_support(rng) for _ in range(40)]
+    _, together = F.emu_format(sups)
+    for i in (0, 7, 39):
+        _, alone = F.emu_format([sups[i]])
+        assert alone[0].tobytes() == together[i].tobytes()
+
+
+def test_empty_support_and_limits():
+    rng = np.random.default_rng(6)
+    rc, got = F.emu_format([F.random_support(rng, n=0, n_alleles=2)])
+    assert rc == 0 and got[0]["n_kept"] == 0 and got[0]["valid"] == 0 and list(got[0]["pl"][:3]) == [0, 0, 0]
+    bad = F.random_support(rng, n=5, n_alleles=2)
+    bad["allele"] = np.array([0, 1, 2, 0, 1])
+    assert F.emu_format([bad])[0] == -1      # LGR_E_ARG: allele index >= K
+    bad = F.random_support(rng, n=5, n_alleles=2)
+    bad["n_alleles"] = 9
+    assert F.emu_format([bad])[0] == -4      # LGR_E_LIMIT
