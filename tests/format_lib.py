@@ -204,3 +204,38 @@ def check_scipy(rows, records, field):
         elif not has or abs(rec[field] - row["expected"]) > 1e-9:  # the reference's EFFECT_SIZE_TOLERANCE
             errs.append(f"{field}: want {row['expected']} got {rec[field]} (valid={has})")
     return errs
+
+
+def supports_from_assignments(batch, assign, seed=0, n_samples=2):
+    """Genotyper::AddToTable (genotyper.cpp:423-456) on the path's own output: the lgr_assign records of a
+    batch become one evidence stream per (variant, sample), in read order.  Read metadata the
+    realignment does not carry (insert size, start, MAPQ, SAM flags, sample) is drawn from `seed`;
+    mates (reads 2i, 2i+1 of a group) share a name hash, so the dedup has work."""
+    rng = np.random.default_rng(seed)
+    sups = []
+    for g in range(batch.n_groups):
+        rb, re = int(batch.grp_read_begin[g]), int(batch.grp_read_begin[g + 1])
+        vb, ve = int(batch.grp_var_begin[g]), int(batch.grp_var_begin[g + 1])
+        P = int(batch.grp_hap_begin[g + 1] - batch.grp_hap_begin[g])
+        R = re - rb
+        meta = dict(isz=rng.integers(-600, 600, R) * (rng.random(R) < 0.9), start=rng.integers(1000, 3000, R),
+                    mapq=rng.choice([0, 20, 60, 60, 60], R), flags=rng.integers(0, 8, R),
+                    sample=np.sort(rng.integers(0, n_samples, R)))
+        for v in range(vb, ve):
+            lo, hi = int(batch.var_hap_off[v]), int(batch.var_hap_off[v + 1])
+            k = max(2, int(batch.var_allele[lo:hi].max()) + 1)
+            for s in range(n_samples):
+                rows = []
+                for i in range(R):
+                    a = assign[int(batch.asg_off[rb + i]) + (v - vb)]
+                    if meta["sample"][i] != s or not a["assigned"]:
+                        continue
+                    rows.append((meta["isz"][i], meta["start"][i],
+                                 float(a["global_score"]) + float(a["local_score"]) * float(a["local_identity"]),
+                                 a["folded_read_pos"], batch.read_name_hash[rb + i - (i % 2)], a["ref_nm"], a["own_hap_nm"],
+                                 a["hap_id"], a["allele"], meta["flags"][i], a["base_qual"], meta["mapq"][i]))
+                cols = list(zip(*rows)) if rows else [[] for _ in abi.EVIDENCE_FIELDS]
+                sup = {name: np.asarray(col, dtype=dt) for (name, dt), col in zip(abi.EVIDENCE_FIELDS, cols)}
+                sup.update(n_alleles=k, variant_len=int(batch.var_len[lo]), total_haps=P)
+                sups.append(sup)
+    return sups

@@ -84,3 +84,31 @@ def test_empty_support_and_limits():
     bad = F.random_support(rng, n=5, n_alleles=2)
     bad["n_alleles"] = 9
     assert F.emu_format([bad])[0] == -4      # LGR_E_LIMIT
+
+
+@pytest.mark.skipif(not F.have_ref(), reason="oracle/_ref not built (needs the reference tree)")
+def test_supports_built_from_the_paths_own_assignments():
+    # realignment oracle → AddToTable → FORMAT math: emulated device arithmetic vs the reference's VariantSupport
+    import oracle_lib as O
+    from lancet2_b200 import synth
+    batch = abi.Batch(synth.make_groups(42, 6, read_len=150, hap_len=800, n_haps=4, n_reads=120))
+    params = abi.LgrParams()
+    abi.load_library().lgr_default_params(C.byref(params))
+    res, _ = O.oracle_genotype(batch, params, n_threads=4)
+    sups = F.supports_from_assignments(batch, res.assign, seed=3)
+    assert sum(len(s["allele"]) for s in sups) > 300
+    rc, got = F.emu_format(sups)
+    assert rc == 0
+    want = F.ref_format(sups)
+    assert int(want["n_kept"].sum()) < sum(len(s["allele"]) for s in sups)  # the mate dedup removed something
+    errs = F.compare_format(want, got)
+    assert not errs, "\n".join(errs[:20])
+
+
+def test_device_path_refuses_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from lancet2_b200.format_metrics import GpuFormatMetrics
+    with pytest.raises(RuntimeError, match="no CUDA device|no usable CUDA device"):
+        GpuFormatMetrics(0)

@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""First measurement of the FORMAT-math row: lgr_format_metrics on the supports a cfg2
+step produces (253 variants x 2 samples, ≈ 230 evidence records each, mates deduplicated) and on a
+deep-coverage shape (≈ 2000 records per support).  Prints one JSON line per shape: CUDA-event time of
+k_fmt_dedup + k_fmt_metrics, the wall time of the whole call from host buffers, and — on the
+box's host cores, one thread — the same arithmetic compiled by g++ (tests/hostemu, checker only)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import format_lib as F  # noqa: E402
+from lancet2_b200 import abi  # noqa: E402
+from lancet2_b200.format_metrics import GpuFormatMetrics  # noqa: E402
+
+
+def main():
+    fmt = GpuFormatMetrics(0)
+    rng = np.random.default_rng(42)
+    for name, n_sup, n_rec in (("cfg2-step", 506, 230), ("deep", 506, 2000)):
+        sups = [F.random_support(rng, n=int(rng.integers(int(n_rec * 0.8), int(n_rec * 1.2))), n_alleles=2, dup_frac=0.4)
+                for _ in range(n_sup)]
+        batch = abi.EvidenceBatch(sups)
+        for _ in range(3):
+            got, _ = fmt.compute(batch)
+        ms_k, wall = [], []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            got, ms = fmt.compute(batch)
+            wall.append((time.perf_counter() - t0) * 1e3)
+            ms_k.append(ms)
+        t0 = time.perf_counter()
+        rc, want = F.emu_format(batch)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        errs = F.compare_format(want, got)
+        bytes_in = sum(v.nbytes for v in batch.cols.values())
+        print(json.dumps({"workload": name, "supports": n_sup, "evidence_records": batch.n_evidence,
+                          "ms_kernels_median": float(np.median(ms_k)), "ms_call_median": float(np.median(wall)),
+                          "supports_per_s_kernels": n_sup / (float(np.median(ms_k)) * 1e-3),
+                          "h2d_bytes": int(bytes_in), "d2h_bytes": int(got.nbytes),
+                          "cpu_same_arithmetic_ms_1thread": cpu_ms, "mismatches_vs_host_build": len(errs)}))
+
+
+if __name__ == "__main__":
+    main()
