@@ -64,15 +64,17 @@ struct WarpDev {
   }
 };
 
-// one warp per support; supports are taken in a grid-stride loop
+// one warp per (support, task): blockIdx.y is the task (lgr_fmt::kTask*), supports are taken in a
+// grid-stride loop along x, so a batch of a few hundred supports still puts >= 7 warps on every SM
 constexpr int kFmtWarpsPerCta = 4;
 __global__ void __launch_bounds__(kFmtWarpsPerCta * 32) k_fmt_metrics(const __grid_constant__ FmtDev D) {
   const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+  const unsigned task = 1u << blockIdx.y;
   WarpDev w{(int)(threadIdx.x & 31)};
   for (int s = warp; s < D.n_supports; s += n_warps) {
     lgr_fmt::support_metrics(w, D.e, D.sup_begin[s], D.sup_begin[s + 1], D.sup_n_alleles[s], D.sup_variant_len[s],
-                             D.sup_total_haps[s], g_phred, &D.out[s]);
+                             D.sup_total_haps[s], g_phred, &D.out[s], task);
   }
 }
 
@@ -243,10 +245,11 @@ int lgr_format_metrics(lgr_fmt_ctx* c, const lgr_evidence_in* in, lgr_format* ou
     FMT_CUDA(c, cudaGetLastError());
   }
   {
-    // one warp per support, at most a few waves of 4-warp CTAs per SM
+    // one warp per (support, task), at most a few waves of 4-warp CTAs per SM
     const int want = (S + kFmtWarpsPerCta - 1) / kFmtWarpsPerCta;
-    const int cap = c->sm_count * 16;
-    k_fmt_metrics<<<want < cap ? want : cap, kFmtWarpsPerCta * 32, 0, c->stream>>>(D);
+    const int cap = c->sm_count * 4;
+    const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)lgr_fmt::kNumTasks);
+    k_fmt_metrics<<<grid, kFmtWarpsPerCta * 32, 0, c->stream>>>(D);
     FMT_CUDA(c, cudaGetLastError());
   }
   FMT_CUDA(c, cudaEventRecord(c->ev1, c->stream));

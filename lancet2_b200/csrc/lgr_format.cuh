@@ -251,134 +251,179 @@ FMT_HD double pileup_loglk(W& w, const Ev& e, int64_t b, int64_t n_end, int K, c
   return log_lk;
 }
 
-// All FORMAT quantities of support [b, n_end).  `phred`: the 256-entry PhredToErrorProb table.
+// The FORMAT quantities of support [b, n_end) fall into independent tasks; the device runs one
+// warp per (support, task) so that a batch of a few hundred supports still fills the SMs, the
+// host emulation runs them all in one call.  Every task writes its own fields of `out`.
+enum : unsigned {
+  kTaskStats = 1u,   // per-allele statistics, SB, SCA, FLD, ASMD, AHDD, PL, GQ, valid bits
+  kTaskMqcd = 2u,
+  kTaskBqcd = 4u,
+  kTaskRpcd = 8u,
+  kTaskFsse = 16u,
+  kTaskHse = 32u,
+  kTaskCmlod = 64u,
+  kTaskAll = 127u,
+};
+constexpr int kNumTasks = 7;
+
+// `phred`: the 256-entry PhredToErrorProb table.
 template <class W>
 FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, int variant_len, int total_haps,
-                            const double* phred, lgr_format* out) {
-  int cov[LGR_FMT_MAX_ALLELES];
-  long long ref_fwd = 0, ref_rev = 0, alt_fwd = 0, alt_rev = 0, ref_sc = 0, alt_sc = 0;
-  long long isz_n[2] = {0, 0}, isz_sum[2] = {0, 0}, refnm_sum[2] = {0, 0}, ownnm_sum[2] = {0, 0};
+                            const double* phred, lgr_format* out, unsigned tasks = kTaskAll) {
   const bool lead = w.leader();
-  if (lead) {
-    out->n_alleles = (uint32_t)K;
-    for (int a = K; a < LGR_FMT_MAX_ALLELES; ++a) {
-      out->raw_pbq[a] = out->rms_mq[a] = out->mean_aln[a] = out->cmlod[a] = 0.0;
-      out->fwd[a] = out->rev[a] = out->soft_clip[a] = 0;
-    }
-  }
-  // ---- per-allele statistics (PerAlleleData vectors, variant_support.cpp:140-209) ----
-  for (int a = 0; a < K; ++a) {
-    Acc<3, 8> r = w.template reduce<Acc<3, 8>>([&](int lane) {
-      Acc<3, 8> acc;
+  // allele depths after the dedup (TotalAlleleCov) — every task needs them
+  int cov[LGR_FMT_MAX_ALLELES];
+  {
+    Acc<0, LGR_FMT_MAX_ALLELES> c = w.template reduce<Acc<0, LGR_FMT_MAX_ALLELES>>([&](int lane) {
+      Acc<0, LGR_FMT_MAX_ALLELES> acc;
       for (int64_t i = b + lane; i < n_end; i += kLanes) {
-        if (!e.keep[i] || e.allele[i] != a) continue;
-        const unsigned fl = e.flags[i];
-        if (fl & LGR_EV_REV) acc.i[1] += 1;
-        else acc.i[0] += 1;
-        acc.i[2] += (fl & LGR_EV_SOFTCLIP) ? 1 : 0;
-        const long long mq = e.map_qual[i];
-        acc.i[3] += mq * mq;
-        if ((fl & LGR_EV_PROPER_PAIR) && e.insert_size[i] != 0) acc.i[4] += 1, acc.i[5] += e.insert_size[i];
-        acc.i[6] += e.ref_nm[i];
-        acc.i[7] += e.own_hap_nm[i];
-        acc.d[0] += e.aln_score[i];
-        const double eps = phred[e.base_qual[i]];
-        const double ok = 1.0 - eps;
-        acc.d[1] += log10(eps > 1e-300 ? eps : 1e-300);
-        acc.d[2] += log10(ok > 1e-300 ? ok : 1e-300);
+        if (!e.keep[i]) continue;
+        const int al = e.allele[i];
+#pragma unroll
+        for (int a = 0; a < LGR_FMT_MAX_ALLELES; ++a) acc.i[a] += al == a;
       }
       return acc;
     });
-    const long long cnt = r.i[0] + r.i[1];
-    cov[a] = (int)cnt;
-    const int grp = a == 0 ? 0 : 1;
-    if (a == 0) ref_fwd = r.i[0], ref_rev = r.i[1], ref_sc = r.i[2];
-    else alt_fwd += r.i[0], alt_rev += r.i[1], alt_sc += r.i[2];
-    isz_n[grp] += r.i[4], isz_sum[grp] += r.i[5], refnm_sum[grp] += r.i[6], ownnm_sum[grp] += r.i[7];
-    double pbq = 0.0;
-    if (cnt > 0) {  // posterior_base_qual.cpp:13-40
-      const double log_err = r.d[1], log_ok = r.d[2];
-      const double max_log = log_err > log_ok ? log_err : log_ok;
-      const double min_log = log_err < log_ok ? log_err : log_ok;
-      const double log_sum = max_log + log10(1.0 + pow(10.0, min_log - max_log));
-      pbq = -10.0 * (log_err - log_sum);
-    }
+    for (int a = 0; a < LGR_FMT_MAX_ALLELES; ++a) cov[a] = (int)c.i[a];
+  }
+  const long long n_ref = cov[0];
+  long long n_alt = 0;
+  for (int a = 1; a < K; ++a) n_alt += cov[a];
+
+  if (tasks & kTaskStats) {
+    long long ref_fwd = 0, ref_rev = 0, alt_fwd = 0, alt_rev = 0, ref_sc = 0, alt_sc = 0;
+    long long isz_n[2] = {0, 0}, isz_sum[2] = {0, 0}, refnm_sum[2] = {0, 0}, ownnm_sum[2] = {0, 0};
     if (lead) {
-      out->fwd[a] = (uint32_t)r.i[0], out->rev[a] = (uint32_t)r.i[1], out->soft_clip[a] = (uint32_t)r.i[2];
-      out->rms_mq[a] = cnt > 0 ? sqrt((double)r.i[3] / (double)cnt) : 0.0;
-      out->mean_aln[a] = cnt > 0 ? r.d[0] / (double)cnt : 0.0;
-      out->raw_pbq[a] = pbq;
+      out->n_alleles = (uint32_t)K;
+      for (int a = K; a < LGR_FMT_MAX_ALLELES; ++a) {
+        out->raw_pbq[a] = out->rms_mq[a] = out->mean_aln[a] = out->cmlod[a] = 0.0;
+        out->fwd[a] = out->rev[a] = out->soft_clip[a] = 0;
+      }
     }
-  }
-  const long long n_ref = ref_fwd + ref_rev, n_alt = alt_fwd + alt_rev;
-  uint32_t valid = 0;
-  // ---- StrandBiasLogOR / SoftClipAsymmetry (variant_support.cpp:182-225) ----
-  const double sb = log(((double)(ref_fwd + 1) * (double)(alt_rev + 1)) / ((double)(ref_rev + 1) * (double)(alt_fwd + 1)));
-  const double alt_frac = n_alt > 0 ? (double)alt_sc / (double)n_alt : 0.0;
-  const double ref_frac = n_ref > 0 ? (double)ref_sc / (double)n_ref : 0.0;
-  const double sca = alt_frac - ref_frac;
-  // ---- MeanAltMinusRef users: FLD, ASMD, AHDD (variant_support.h:362-384) ----
-  double fld = 0.0, asmd = 0.0, ahdd = 0.0;
-  if (isz_n[0] > 0 && isz_n[1] > 0) {
-    valid |= LGR_FMT_HAS_FLD;
-    fld = ((double)isz_sum[1] / (double)isz_n[1] - 0.0) - (double)isz_sum[0] / (double)isz_n[0];
-  }
-  if (n_ref > 0 && n_alt > 0) {
-    valid |= LGR_FMT_HAS_ASMD | LGR_FMT_HAS_AHDD | LGR_FMT_HAS_MQCD | LGR_FMT_HAS_RPCD | LGR_FMT_HAS_BQCD;
-    asmd = ((double)refnm_sum[1] / (double)n_alt - (double)variant_len) - (double)refnm_sum[0] / (double)n_ref;
-    ahdd = ((double)ownnm_sum[1] / (double)n_alt - 0.0) - (double)ownnm_sum[0] / (double)n_ref;
+    // ---- per-allele statistics (PerAlleleData vectors, variant_support.cpp:140-209) ----
+    for (int a = 0; a < K; ++a) {
+      Acc<3, 8> r = w.template reduce<Acc<3, 8>>([&](int lane) {
+        Acc<3, 8> acc;
+        for (int64_t i = b + lane; i < n_end; i += kLanes) {
+          if (!e.keep[i] || e.allele[i] != a) continue;
+          const unsigned fl = e.flags[i];
+          if (fl & LGR_EV_REV) acc.i[1] += 1;
+          else acc.i[0] += 1;
+          acc.i[2] += (fl & LGR_EV_SOFTCLIP) ? 1 : 0;
+          const long long mq = e.map_qual[i];
+          acc.i[3] += mq * mq;
+          if ((fl & LGR_EV_PROPER_PAIR) && e.insert_size[i] != 0) acc.i[4] += 1, acc.i[5] += e.insert_size[i];
+          acc.i[6] += e.ref_nm[i];
+          acc.i[7] += e.own_hap_nm[i];
+          acc.d[0] += e.aln_score[i];
+          const double eps = phred[e.base_qual[i]];
+          const double ok = 1.0 - eps;
+          acc.d[1] += log10(eps > 1e-300 ? eps : 1e-300);
+          acc.d[2] += log10(ok > 1e-300 ? ok : 1e-300);
+        }
+        return acc;
+      });
+      const long long cnt = r.i[0] + r.i[1];
+      const int grp = a == 0 ? 0 : 1;
+      if (a == 0) ref_fwd = r.i[0], ref_rev = r.i[1], ref_sc = r.i[2];
+      else alt_fwd += r.i[0], alt_rev += r.i[1], alt_sc += r.i[2];
+      isz_n[grp] += r.i[4], isz_sum[grp] += r.i[5], refnm_sum[grp] += r.i[6], ownnm_sum[grp] += r.i[7];
+      double pbq = 0.0;
+      if (cnt > 0) {  // posterior_base_qual.cpp:13-40
+        const double log_err = r.d[1], log_ok = r.d[2];
+        const double max_log = log_err > log_ok ? log_err : log_ok;
+        const double min_log = log_err < log_ok ? log_err : log_ok;
+        const double log_sum = max_log + log10(1.0 + pow(10.0, min_log - max_log));
+        pbq = -10.0 * (log_err - log_sum);
+      }
+      if (lead) {
+        out->fwd[a] = (uint32_t)r.i[0], out->rev[a] = (uint32_t)r.i[1], out->soft_clip[a] = (uint32_t)r.i[2];
+        out->rms_mq[a] = cnt > 0 ? sqrt((double)r.i[3] / (double)cnt) : 0.0;
+        out->mean_aln[a] = cnt > 0 ? r.d[0] / (double)cnt : 0.0;
+        out->raw_pbq[a] = pbq;
+      }
+    }
+    uint32_t valid = 0;
+    // ---- StrandBiasLogOR / SoftClipAsymmetry (variant_support.cpp:182-225) ----
+    const double sb = log(((double)(ref_fwd + 1) * (double)(alt_rev + 1)) / ((double)(ref_rev + 1) * (double)(alt_fwd + 1)));
+    const double alt_frac = n_alt > 0 ? (double)alt_sc / (double)n_alt : 0.0;
+    const double ref_frac = n_ref > 0 ? (double)ref_sc / (double)n_ref : 0.0;
+    const double sca = alt_frac - ref_frac;
+    // ---- MeanAltMinusRef users: FLD, ASMD, AHDD (variant_support.h:362-384) ----
+    double fld = 0.0, asmd = 0.0, ahdd = 0.0;
+    if (isz_n[0] > 0 && isz_n[1] > 0) {
+      valid |= LGR_FMT_HAS_FLD;
+      fld = ((double)isz_sum[1] / (double)isz_n[1] - 0.0) - (double)isz_sum[0] / (double)isz_n[0];
+    }
+    if (n_ref > 0 && n_alt > 0) {
+      valid |= LGR_FMT_HAS_ASMD | LGR_FMT_HAS_AHDD | LGR_FMT_HAS_MQCD | LGR_FMT_HAS_RPCD | LGR_FMT_HAS_BQCD;
+      asmd = ((double)refnm_sum[1] / (double)n_alt - (double)variant_len) - (double)refnm_sum[0] / (double)n_ref;
+      ahdd = ((double)ownnm_sum[1] / (double)n_alt - 0.0) - (double)ownnm_sum[0] / (double)n_ref;
+    }
+    if (n_alt >= 3) valid |= LGR_FMT_HAS_FSSE | (total_haps >= 2 ? LGR_FMT_HAS_HSE : 0u);
+    // ---- PL / GQ from the allele depths (variant_support.cpp:294-310) ----
+    uint32_t pl[LGR_FMT_MAX_GENOTYPES], gq = 0;
+    genotype_pls(cov, K, pl, &gq);
+    if (lead) {
+      out->sb = sb, out->sca = sca, out->fld = fld, out->asmd = asmd, out->ahdd = ahdd;
+      for (int g = 0; g < LGR_FMT_MAX_GENOTYPES; ++g) out->pl[g] = pl[g];
+      out->gq = gq, out->valid = valid, out->n_kept = (uint32_t)(n_ref + n_alt);
+    }
   }
   // ---- Mann-Whitney effect sizes: MQCD, BQCD, RPCD (variant_support.cpp:234-263) ----
-  double mqcd = 0.0, bqcd = 0.0, rpcd = 0.0;
-  if (n_ref > 0 && n_alt > 0) {
-    mqcd = mw_bytes(w, e, b, n_end, n_ref, n_alt, [&](int64_t j) { return (int)e.map_qual[j]; });
-    bqcd = mw_bytes(w, e, b, n_end, n_ref, n_alt, [&](int64_t j) { return (int)e.base_qual[j]; });
-    rpcd = mw_folded(w, e, b, n_end, n_ref, n_alt);
+  const bool both = n_ref > 0 && n_alt > 0;
+  if (tasks & kTaskMqcd) {
+    const double v = both ? mw_bytes(w, e, b, n_end, n_ref, n_alt, [&](int64_t j) { return (int)e.map_qual[j]; }) : 0.0;
+    if (lead) out->mqcd = v;
+  }
+  if (tasks & kTaskBqcd) {
+    const double v = both ? mw_bytes(w, e, b, n_end, n_ref, n_alt, [&](int64_t j) { return (int)e.base_qual[j]; }) : 0.0;
+    if (lead) out->bqcd = v;
+  }
+  if (tasks & kTaskRpcd) {
+    const double v = both ? mw_folded(w, e, b, n_end, n_ref, n_alt) : 0.0;
+    if (lead) out->rpcd = v;
   }
   // ---- pooled-ALT entropies: FSSE (3 bp start bins, <= 20 bins) and HSE (variant_support.cpp:270-291) ----
-  double fsse = 0.0, hse = 0.0;
-  if (n_alt >= 3) {
-    valid |= LGR_FMT_HAS_FSSE;
-    fsse = alt_entropy(w, e, b, n_end, n_alt, 20.0, [&](int64_t j) { return (long long)(e.aln_start[j] / 3); });
-    if (total_haps >= 2) {
-      valid |= LGR_FMT_HAS_HSE;
-      hse = alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, [&](int64_t j) { return (long long)e.hap_id[j]; });
-    }
+  if (tasks & kTaskFsse) {
+    const double v = n_alt >= 3 ? alt_entropy(w, e, b, n_end, n_alt, 20.0, [&](int64_t j) { return (long long)(e.aln_start[j] / 3); })
+                                : 0.0;
+    if (lead) out->fsse = v;
   }
-  // ---- PL / GQ from the allele depths (variant_support.cpp:294-310) ----
-  uint32_t pl[LGR_FMT_MAX_GENOTYPES], gq = 0;
-  genotype_pls(cov, K, pl, &gq);
+  if (tasks & kTaskHse) {
+    const double v = n_alt >= 3 && total_haps >= 2
+                         ? alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, [&](int64_t j) { return (long long)e.hap_id[j]; })
+                         : 0.0;
+    if (lead) out->hse = v;
+  }
   // ---- CMLOD (genotype_likelihood.cpp:165-205) ----
-  double lod[LGR_FMT_MAX_ALLELES];
-  for (int a = 0; a < LGR_FMT_MAX_ALLELES; ++a) lod[a] = 0.0;
-  long long total_depth = 0;
-  for (int a = 0; a < K; ++a) total_depth += cov[a];
-  if (K >= 2 && total_depth > 0) {
-    double frac_mle[LGR_FMT_MAX_ALLELES], frac_null[LGR_FMT_MAX_ALLELES];
-    for (int a = 0; a < K; ++a) frac_mle[a] = (double)cov[a] / (double)total_depth;
-    const double ll_mle = pileup_loglk(w, e, b, n_end, K, frac_mle, phred);
-    for (int t = 1; t < K; ++t) {
-      if (cov[t] == 0) continue;
-      for (int a = 0; a < K; ++a) frac_null[a] = frac_mle[a];
-      const double null_mass = frac_null[t];
-      frac_null[t] = 0.0;
-      const double remaining = 1.0 - null_mass;
-      if (remaining <= 0.0) {
-        frac_null[0] = 1.0;
-      } else {
-        for (int a = 0; a < K; ++a) frac_null[a] /= remaining;
+  if (tasks & kTaskCmlod) {
+    double lod[LGR_FMT_MAX_ALLELES];
+    for (int a = 0; a < LGR_FMT_MAX_ALLELES; ++a) lod[a] = 0.0;
+    long long total_depth = 0;
+    for (int a = 0; a < K; ++a) total_depth += cov[a];
+    if (K >= 2 && total_depth > 0) {
+      double frac_mle[LGR_FMT_MAX_ALLELES], frac_null[LGR_FMT_MAX_ALLELES];
+      for (int a = 0; a < K; ++a) frac_mle[a] = (double)cov[a] / (double)total_depth;
+      const double ll_mle = pileup_loglk(w, e, b, n_end, K, frac_mle, phred);
+      for (int t = 1; t < K; ++t) {
+        if (cov[t] == 0) continue;
+        for (int a = 0; a < K; ++a) frac_null[a] = frac_mle[a];
+        const double null_mass = frac_null[t];
+        frac_null[t] = 0.0;
+        const double remaining = 1.0 - null_mass;
+        if (remaining <= 0.0) {
+          frac_null[0] = 1.0;
+        } else {
+          for (int a = 0; a < K; ++a) frac_null[a] /= remaining;
+        }
+        const double ll_null = pileup_loglk(w, e, b, n_end, K, frac_null, phred);
+        const double dlt = ll_mle - ll_null;
+        lod[t] = dlt > 0.0 ? dlt : 0.0;
       }
-      const double ll_null = pileup_loglk(w, e, b, n_end, K, frac_null, phred);
-      const double dlt = ll_mle - ll_null;
-      lod[t] = dlt > 0.0 ? dlt : 0.0;
     }
-  }
-  if (lead) {
-    out->sb = sb, out->sca = sca, out->fld = fld, out->asmd = asmd, out->ahdd = ahdd;
-    out->mqcd = mqcd, out->bqcd = bqcd, out->rpcd = rpcd, out->fsse = fsse, out->hse = hse;
-    for (int g = 0; g < LGR_FMT_MAX_GENOTYPES; ++g) out->pl[g] = pl[g];
-    for (int a = 0; a < K; ++a) out->cmlod[a] = lod[a];
-    out->gq = gq, out->valid = valid, out->n_kept = (uint32_t)(n_ref + n_alt);
+    if (lead)
+      for (int a = 0; a < K; ++a) out->cmlod[a] = lod[a];
   }
 }
 

@@ -31,14 +31,18 @@ def load_emu():
         _emu = C.CDLL(EMU_SO)
         _emu.emu_format_metrics.argtypes = [C.POINTER(abi.LgrEvidenceIn), C.c_void_p]
         _emu.emu_format_metrics.restype = C.c_int
+        _emu.emu_format_metrics_ex.argtypes = [C.POINTER(abi.LgrEvidenceIn), C.c_void_p, C.c_int]
+        _emu.emu_format_metrics_ex.restype = C.c_int
     return _emu
 
 
-def emu_format(supports):
+def emu_format(supports, split_tasks=True):
+    """split_tasks: one call of the core per (support, task) — what k_fmt_metrics launches; False: all
+    tasks of a support in one call."""
     batch = supports if isinstance(supports, abi.EvidenceBatch) else abi.EvidenceBatch(supports)
     out = np.zeros(batch.n_supports, dtype=abi.FORMAT_DTYPE)
     st = batch.c_struct()
-    rc = load_emu().emu_format_metrics(C.byref(st), out.ctypes.data)
+    rc = load_emu().emu_format_metrics_ex(C.byref(st), out.ctypes.data, 1 if split_tasks else 0)
     return rc, out
 
 

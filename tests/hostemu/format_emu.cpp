@@ -10,7 +10,8 @@ static const double kPhred[256] = {
 #include "../../lancet2_b200/csrc/phred_lut.inc"
 };
 
-extern "C" int emu_format_metrics(const lgr_evidence_in* in, lgr_format* out) {
+// split_tasks != 0: one call per (support, task), as k_fmt_metrics launches them; 0: all tasks in one call
+extern "C" int emu_format_metrics_ex(const lgr_evidence_in* in, lgr_format* out, int split_tasks) {
   using namespace lgr_fmt;
   const int S = in->n_supports;
   const int64_t N = in->n_evidence;
@@ -27,8 +28,11 @@ extern "C" int emu_format_metrics(const lgr_evidence_in* in, lgr_format* out) {
   Ev e{in->insert_size, in->aln_start, in->aln_score, in->folded_pos, in->rname_hash, in->ref_nm, in->own_hap_nm,
        in->hap_id,      in->allele,    in->flags,     in->base_qual,  in->map_qual,   keep.data()};
   WarpHost w;
-  for (int s = 0; s < S; ++s)
-    support_metrics(w, e, in->sup_begin[s], in->sup_begin[s + 1], in->sup_n_alleles[s], in->sup_variant_len[s],
-                    in->sup_total_haps[s], kPhred, &out[s]);
+  for (int t = 0; t < (split_tasks ? kNumTasks : 1); ++t)
+    for (int s = 0; s < S; ++s)
+      support_metrics(w, e, in->sup_begin[s], in->sup_begin[s + 1], in->sup_n_alleles[s], in->sup_variant_len[s],
+                      in->sup_total_haps[s], kPhred, &out[s], split_tasks ? 1u << t : (unsigned)kTaskAll);
   return LGR_OK;
 }
+
+extern "C" int emu_format_metrics(const lgr_evidence_in* in, lgr_format* out) { return emu_format_metrics_ex(in, out, 1); }

@@ -74,6 +74,14 @@ def test_results_do_not_depend_on_batch_composition():
         assert alone[0].tobytes() == together[i].tobytes()
 
 
+def test_task_split_equals_the_single_call():
+    rng = np.random.default_rng(8)
+    sups = [F.random_support(rng) for _ in range(200)]
+    _, split = F.emu_format(sups, split_tasks=True)
+    _, whole = F.emu_format(sups, split_tasks=False)
+    assert split.tobytes() == whole.tobytes()
+
+
 def test_empty_support_and_limits():
     rng = np.random.default_rng(6)
     rc, got = F.emu_format([F.random_support(rng, n=0, n_alleles=2)])
