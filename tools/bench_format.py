@@ -21,14 +21,16 @@ from lancet2_b200.format_metrics import GpuFormatMetrics  # noqa: E402
 def main():
     fmt = GpuFormatMetrics(0)
     rng = np.random.default_rng(42)
-    for name, n_sup, n_rec in (("cfg2-step", 506, 230), ("deep", 506, 2000)):
+    quick = os.environ.get("LGR_FMT_QUICK") == "1"  # profiler runs: the cfg2-step shape only, few repetitions
+    shapes = (("cfg2-step", 506, 230), ("deep", 506, 2000))
+    for name, n_sup, n_rec in shapes[:1] if quick else shapes:
         sups = [F.random_support(rng, n=int(rng.integers(int(n_rec * 0.8), int(n_rec * 1.2))), n_alleles=2, dup_frac=0.4)
                 for _ in range(n_sup)]
         batch = abi.EvidenceBatch(sups)
         for _ in range(3):
             got, _ = fmt.compute(batch)
         ms_k, wall = [], []
-        for _ in range(20):
+        for _ in range(2 if quick else 20):
             t0 = time.perf_counter()
             got, ms = fmt.compute(batch)
             wall.append((time.perf_counter() - t0) * 1e3)
