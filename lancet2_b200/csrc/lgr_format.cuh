@@ -141,30 +141,37 @@ FMT_HD double mw_folded(W& w, const Ev& e, int64_t b, int64_t n_end, long long n
 }
 
 // variant_support.h:386-412 AltPooledEntropy: normalised Shannon entropy of the pooled ALT
-// records' bins (one term per distinct bin, taken at the bin's first record).
-template <class W, class Bin>
-FMT_HD double alt_entropy(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_alt, double max_bins, const Bin& bin) {
+// records' bins, bin = val / width with C truncation (width 3: FSSE's start bins, 1: HSE's
+// haplotype ids).  The outer loop over ALT records is warp-uniform; the lanes share the scan
+// that counts a record's bin mates (low word) and the earlier ones among them (high word), and a
+// bin contributes its term at its first record, so the terms add up in first-occurrence order.
+// The bin test is a range test on the raw value — no division in the scan.
+template <class W, class Val>
+FMT_HD double alt_entropy(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_alt, double max_bins, long long width,
+                          const Val& val) {
   const double total = (double)n_alt;
-  Acc<1, 0> r = w.template reduce<Acc<1, 0>>([&](int lane) {
-    Acc<1, 0> a;
-    for (int64_t i = b + lane; i < n_end; i += kLanes) {
-      if (!e.keep[i] || e.allele[i] == 0) continue;
-      const long long key = bin(i);
-      long long count = 0;
-      bool first = true;
-      for (int64_t j = b; j < n_end; ++j) {
-        if (!e.keep[j] || e.allele[j] == 0 || bin(j) != key) continue;
-        if (j < i) first = false;
-        ++count;
+  double entropy = 0.0;
+  for (int64_t i = b; i < n_end; ++i) {
+    if (!e.keep[i] || e.allele[i] == 0) continue;
+    const long long key = val(i) / width;
+    const long long lo = key > 0 ? key * width : key * width - (width - 1);
+    const long long hi = key < 0 ? key * width : key * width + (width - 1);
+    Acc<0, 1> r = w.template reduce<Acc<0, 1>>([&](int lane) {
+      Acc<0, 1> a;
+      for (int64_t j = b + lane; j < n_end; j += kLanes) {
+        if (!e.keep[j] || e.allele[j] == 0) continue;
+        const long long v = val(j);
+        if (v < lo || v > hi) continue;
+        a.i[0] += j < i ? (1LL << 32) + 1 : 1;
       }
-      if (!first) continue;
-      const double prob = (double)count / total;
-      a.d[0] -= prob * log2(prob);
-    }
-    return a;
-  });
+      return a;
+    });
+    if (r.i[0] >> 32) continue;  // not the bin's first record
+    const double prob = (double)(r.i[0] & 0xffffffffLL) / total;
+    entropy -= prob * log2(prob);
+  }
   const double max_entropy = log2(total < max_bins ? total : max_bins);
-  return max_entropy > 0.0 ? (r.d[0] / max_entropy) : 0.0;
+  return max_entropy > 0.0 ? (entropy / max_entropy) : 0.0;
 }
 
 // genotype_likelihood.cpp:29-46 LogDirichletMultinomial
@@ -386,13 +393,13 @@ FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, 
   }
   // ---- pooled-ALT entropies: FSSE (3 bp start bins, <= 20 bins) and HSE (variant_support.cpp:270-291) ----
   if (tasks & kTaskFsse) {
-    const double v = n_alt >= 3 ? alt_entropy(w, e, b, n_end, n_alt, 20.0, [&](int64_t j) { return (long long)(e.aln_start[j] / 3); })
+    const double v = n_alt >= 3 ? alt_entropy(w, e, b, n_end, n_alt, 20.0, 3, [&](int64_t j) { return (long long)e.aln_start[j]; })
                                 : 0.0;
     if (lead) out->fsse = v;
   }
   if (tasks & kTaskHse) {
     const double v = n_alt >= 3 && total_haps >= 2
-                         ? alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, [&](int64_t j) { return (long long)e.hap_id[j]; })
+                         ? alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, 1, [&](int64_t j) { return (long long)e.hap_id[j]; })
                          : 0.0;
     if (lead) out->hse = v;
   }
