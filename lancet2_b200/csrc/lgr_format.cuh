@@ -142,36 +142,37 @@ FMT_HD double mw_folded(W& w, const Ev& e, int64_t b, int64_t n_end, long long n
 
 // variant_support.h:386-412 AltPooledEntropy: normalised Shannon entropy of the pooled ALT
 // records' bins, bin = val / width with C truncation (width 3: FSSE's start bins, 1: HSE's
-// haplotype ids).  The outer loop over ALT records is warp-uniform; the lanes share the scan
-// that counts a record's bin mates (low word) and the earlier ones among them (high word), and a
-// bin contributes its term at its first record, so the terms add up in first-occurrence order.
-// The bin test is a range test on the raw value — no division in the scan.
+// haplotype ids).  One lane per ALT record counts the record's bin mates; a bin contributes its
+// term at its first record.  The bin test inside the scan is a range test on the raw value (one
+// division per record, none per pair).  Measured and rejected (profiles/README.md): a
+// warp-uniform outer loop with the lanes sharing each scan — one dependent butterfly per record
+// costs more than the idle REF lanes do.
 template <class W, class Val>
 FMT_HD double alt_entropy(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_alt, double max_bins, long long width,
                           const Val& val) {
   const double total = (double)n_alt;
-  double entropy = 0.0;
-  for (int64_t i = b; i < n_end; ++i) {
-    if (!e.keep[i] || e.allele[i] == 0) continue;
-    const long long key = val(i) / width;
-    const long long lo = key > 0 ? key * width : key * width - (width - 1);
-    const long long hi = key < 0 ? key * width : key * width + (width - 1);
-    Acc<0, 1> r = w.template reduce<Acc<0, 1>>([&](int lane) {
-      Acc<0, 1> a;
-      for (int64_t j = b + lane; j < n_end; j += kLanes) {
-        if (!e.keep[j] || e.allele[j] == 0) continue;
+  Acc<1, 0> r = w.template reduce<Acc<1, 0>>([&](int lane) {
+    Acc<1, 0> a;
+    for (int64_t i = b + lane; i < n_end; i += kLanes) {
+      if (!e.keep[i] || e.allele[i] == 0) continue;
+      const long long key = val(i) / width;
+      const long long lo = key > 0 ? key * width : key * width - (width - 1);
+      const long long hi = key < 0 ? key * width : key * width + (width - 1);
+      int count = 0, earlier = 0;
+      for (int64_t j = b; j < n_end; ++j) {
         const long long v = val(j);
-        if (v < lo || v > hi) continue;
-        a.i[0] += j < i ? (1LL << 32) + 1 : 1;
+        const int hit = (e.keep[j] != 0) & (e.allele[j] != 0) & (v >= lo) & (v <= hi);
+        count += hit;
+        earlier += hit & (j < i);
       }
-      return a;
-    });
-    if (r.i[0] >> 32) continue;  // not the bin's first record
-    const double prob = (double)(r.i[0] & 0xffffffffLL) / total;
-    entropy -= prob * log2(prob);
-  }
+      if (earlier) continue;  // not the bin's first record
+      const double prob = (double)count / total;
+      a.d[0] -= prob * log2(prob);
+    }
+    return a;
+  });
   const double max_entropy = log2(total < max_bins ? total : max_bins);
-  return max_entropy > 0.0 ? (entropy / max_entropy) : 0.0;
+  return max_entropy > 0.0 ? (r.d[0] / max_entropy) : 0.0;
 }
 
 // genotype_likelihood.cpp:29-46 LogDirichletMultinomial
