@@ -46,13 +46,15 @@ __global__ void __launch_bounds__(256) k_fmt_dedup(const __grid_constant__ FmtDe
   D.keep[i] = lgr_fmt::dedup_keep(D.e.allele, D.e.rname_hash, D.sup_begin[lo], i);
 }
 
-struct WarpDev {
-  int lane;
-  __device__ __forceinline__ bool leader() const { return lane == 0; }
+struct CtaDev {
+  int tid;
+  __device__ __forceinline__ bool leader() const { return tid == 0; }
   template <class A, class F>
   __device__ __forceinline__ A reduce(const F& f) {
-    A a = f(lane);
-    constexpr int nd = (int)(sizeof(a.d) / sizeof(double)), ni = (int)(sizeof(a.i) / sizeof(long long));
+    constexpr int nd = (int)(sizeof(A::d) / sizeof(double)), ni = (int)(sizeof(A::i) / sizeof(long long));
+    __shared__ double s_d[lgr_fmt::kWarps][nd];
+    __shared__ long long s_i[lgr_fmt::kWarps][ni];
+    A a = f(tid);
 #pragma unroll
     for (int off = lgr_fmt::kLanes / 2; off > 0; off >>= 1) {
 #pragma unroll
@@ -60,19 +62,28 @@ struct WarpDev {
 #pragma unroll
       for (int k = 0; k < ni; ++k) a.i[k] = a.i[k] + __shfl_xor_sync(0xffffffffu, a.i[k], off);
     }
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < nd; ++k) s_d[tid >> 5][k] = a.d[k];
+#pragma unroll
+      for (int k = 0; k < ni; ++k) s_i[tid >> 5][k] = a.i[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < nd; ++k) a.d[k] = (s_d[0][k] + s_d[1][k]) + (s_d[2][k] + s_d[3][k]);
+#pragma unroll
+    for (int k = 0; k < ni; ++k) a.i[k] = (s_i[0][k] + s_i[1][k]) + (s_i[2][k] + s_i[3][k]);
+    __syncthreads();  // the partials may be overwritten by the next reduction of this instantiation
     return a;
   }
 };
 
-// one warp per (support, task): blockIdx.y is the task (lgr_fmt::kTask*), supports are taken in a
-// grid-stride loop along x, so a batch of a few hundred supports still puts >= 7 warps on every SM
-constexpr int kFmtWarpsPerCta = 4;
-__global__ void __launch_bounds__(kFmtWarpsPerCta * 32) k_fmt_metrics(const __grid_constant__ FmtDev D) {
-  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+// one 128-thread CTA per (support, task): blockIdx.y is the task (lgr_fmt::kTask*), supports are
+// taken in a grid-stride loop along x.  A batch of a few hundred supports is a few thousand CTAs.
+__global__ void __launch_bounds__(lgr_fmt::kThreads) k_fmt_metrics(const __grid_constant__ FmtDev D) {
   const unsigned task = 1u << blockIdx.y;
-  WarpDev w{(int)(threadIdx.x & 31)};
-  for (int s = warp; s < D.n_supports; s += n_warps) {
+  CtaDev w{(int)threadIdx.x};
+  for (int s = (int)blockIdx.x; s < D.n_supports; s += (int)gridDim.x) {
     lgr_fmt::support_metrics(w, D.e, D.sup_begin[s], D.sup_begin[s + 1], D.sup_n_alleles[s], D.sup_variant_len[s],
                              D.sup_total_haps[s], g_phred, &D.out[s], task);
   }
@@ -245,11 +256,10 @@ int lgr_format_metrics(lgr_fmt_ctx* c, const lgr_evidence_in* in, lgr_format* ou
     FMT_CUDA(c, cudaGetLastError());
   }
   {
-    // one warp per (support, task), at most a few waves of 4-warp CTAs per SM
-    const int want = (S + kFmtWarpsPerCta - 1) / kFmtWarpsPerCta;
-    const int cap = c->sm_count * 4;
-    const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)lgr_fmt::kNumTasks);
-    k_fmt_metrics<<<grid, kFmtWarpsPerCta * 32, 0, c->stream>>>(D);
+    // one CTA per (support, task); beyond 32 CTAs per SM and task the supports are grid-strided
+    const int cap = c->sm_count * 32;
+    const dim3 grid((unsigned)(S < cap ? S : cap), (unsigned)lgr_fmt::kNumTasks);
+    k_fmt_metrics<<<grid, lgr_fmt::kThreads, 0, c->stream>>>(D);
     FMT_CUDA(c, cudaGetLastError());
   }
   FMT_CUDA(c, cudaEventRecord(c->ev1, c->stream));

@@ -2,12 +2,13 @@
 // sample), written ONCE for the device warp (lgr_format.cu) and for the g++ host emulation
 // (tests/hostemu/format_emu.cpp).  SURVEY.md §8f #2.
 //
-// Mapping: one warp per support.  Every reduction over the support's evidence records is a
-// lane-strided partial (lane l takes records l, l+32, ...) followed by an xor-butterfly, so all
-// 32 lanes end up with the same bits; the scalar math after a reduction is executed uniformly by
-// all lanes and only the leader stores.  The `W` policy supplies `reduce` (shuffles on the
-// device, a loop over 32 emulated lanes on the host), so host and device run the same
-// arithmetic in the same order and differ only in libm (log10/log2/log/lgamma/pow).
+// Mapping: one 128-thread CTA per (support, task).  Every reduction over the support's evidence
+// records is a thread-strided partial (thread t takes records t, t+128, ...) followed by an
+// xor-butterfly inside each warp and a fixed-order sum of the four warp totals, so all threads
+// end up with the same bits; the scalar math after a reduction is executed uniformly by all
+// threads and only the leader stores.  The `W` policy supplies `reduce` (shuffles + shared
+// memory on the device, a loop over 128 emulated threads on the host), so host and device run
+// the same arithmetic in the same order and differ only in libm (log10/log2/log/lgamma/pow).
 //
 // Reference being restated (file:line in the reference tree, src/lancet/...):
 //   caller/variant_support.cpp:23-67   AddEvidence (first-seen dedup by read-name hash per allele)
@@ -30,6 +31,8 @@
 namespace lgr_fmt {
 
 constexpr int kLanes = 32;
+constexpr int kWarps = 4;
+constexpr int kThreads = kLanes * kWarps;  // threads cooperating on one (support, task)
 
 // SoA views of one batch of evidence (device pointers on the device, host pointers in the emulation)
 struct Ev {
@@ -83,21 +86,22 @@ FMT_HD double mw_effect(long long r2, long long tie, long long n_ref_i, long lon
   return z_score / sqrt(n_total);
 }
 
-// Mann-Whitney over a byte-valued field: each lane owns 8 of the 256 values and counts, in one
-// pass over the records, how many REF / ALT records equal each of them and how many are smaller.
+// Mann-Whitney over a byte-valued field: each thread owns kValsPerThread of the 256 values and counts,
+// in one pass over the records, how many REF / ALT records equal each of them and how many are smaller.
+constexpr int kValsPerThread = 256 / kThreads;
 template <class W, class Get>
 FMT_HD double mw_bytes(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_ref, long long n_alt, const Get& get) {
   Acc<0, 2> r = w.template reduce<Acc<0, 2>>([&](int lane) {
-    int eq_ref[8], eq_alt[8], less[8];
+    int eq_ref[kValsPerThread], eq_alt[kValsPerThread], less[kValsPerThread];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) eq_ref[t] = eq_alt[t] = less[t] = 0;
-    const int v0 = lane * 8;
+    for (int t = 0; t < kValsPerThread; ++t) eq_ref[t] = eq_alt[t] = less[t] = 0;
+    const int v0 = lane * kValsPerThread;
     for (int64_t j = b; j < n_end; ++j) {
       if (!e.keep[j]) continue;
       const int v = get(j);
       const int alt = e.allele[j] != 0;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < kValsPerThread; ++t) {
         const int eq = v == v0 + t;
         eq_ref[t] += eq & (alt ^ 1);
         eq_alt[t] += eq & alt;
@@ -106,7 +110,7 @@ FMT_HD double mw_bytes(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_
     }
     Acc<0, 2> a;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < kValsPerThread; ++t) {
       const long long ts = (long long)eq_ref[t] + eq_alt[t];
       if (ts == 0) continue;
       a.i[0] += (long long)eq_alt[t] * (2LL * less[t] + ts + 1);  // 2 x mid-rank = i + 1 + jdx
@@ -122,7 +126,7 @@ template <class W>
 FMT_HD double mw_folded(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_ref, long long n_alt) {
   Acc<0, 2> r = w.template reduce<Acc<0, 2>>([&](int lane) {
     Acc<0, 2> a;
-    for (int64_t i = b + lane; i < n_end; i += kLanes) {
+    for (int64_t i = b + lane; i < n_end; i += kThreads) {
       if (!e.keep[i]) continue;
       const double x = e.folded_pos[i];
       long long less = 0, eq = 0;
@@ -153,7 +157,7 @@ FMT_HD double alt_entropy(W& w, const Ev& e, int64_t b, int64_t n_end, long long
   const double total = (double)n_alt;
   Acc<1, 0> r = w.template reduce<Acc<1, 0>>([&](int lane) {
     Acc<1, 0> a;
-    for (int64_t i = b + lane; i < n_end; i += kLanes) {
+    for (int64_t i = b + lane; i < n_end; i += kThreads) {
       if (!e.keep[i] || e.allele[i] == 0) continue;
       const long long key = val(i) / width;
       const long long lo = key > 0 ? key * width : key * width - (width - 1);
@@ -241,7 +245,7 @@ FMT_HD double pileup_loglk(W& w, const Ev& e, int64_t b, int64_t n_end, int K, c
     const double f = frac[called_as];
     Acc<2, 0> r = w.template reduce<Acc<2, 0>>([&](int lane) {
       Acc<2, 0> a;
-      for (int64_t i = b + lane; i < n_end; i += kLanes) {
+      for (int64_t i = b + lane; i < n_end; i += kThreads) {
         if (!e.keep[i] || e.allele[i] != called_as) continue;
         const double error_prob = phred[e.base_qual[i]];
         const double mismatch_prob = error_prob / denom;
@@ -284,7 +288,7 @@ FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, 
   {
     Acc<0, LGR_FMT_MAX_ALLELES> c = w.template reduce<Acc<0, LGR_FMT_MAX_ALLELES>>([&](int lane) {
       Acc<0, LGR_FMT_MAX_ALLELES> acc;
-      for (int64_t i = b + lane; i < n_end; i += kLanes) {
+      for (int64_t i = b + lane; i < n_end; i += kThreads) {
         if (!e.keep[i]) continue;
         const int al = e.allele[i];
 #pragma unroll
@@ -312,7 +316,7 @@ FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, 
     for (int a = 0; a < K; ++a) {
       Acc<3, 8> r = w.template reduce<Acc<3, 8>>([&](int lane) {
         Acc<3, 8> acc;
-        for (int64_t i = b + lane; i < n_end; i += kLanes) {
+        for (int64_t i = b + lane; i < n_end; i += kThreads) {
           if (!e.keep[i] || e.allele[i] != a) continue;
           const unsigned fl = e.flags[i];
           if (fl & LGR_EV_REV) acc.i[1] += 1;
@@ -435,24 +439,29 @@ FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, 
   }
 }
 
-// the xor-butterfly on 32 emulated lanes (host) — bit-identical to the shuffle version because
-// IEEE addition is commutative: at every level both partners add the same two numbers.
+// the reduction on 128 emulated threads (host) — bit-identical to the device version: the
+// xor-butterfly inside each group of 32 (IEEE addition is commutative, so at every level both
+// partners add the same two numbers), then (w0 + w1) + (w2 + w3) over the four warp totals.
 struct WarpHost {
   FMT_HD bool leader() const { return true; }
   template <class A, class F>
   inline A reduce(const F& f) {
-    A p[kLanes], q[kLanes];
-    for (int l = 0; l < kLanes; ++l) p[l] = f(l);
+    A p[kThreads], q[kThreads];
+    for (int l = 0; l < kThreads; ++l) p[l] = f(l);
     constexpr int nd = (int)(sizeof(p[0].d) / sizeof(double)), ni = (int)(sizeof(p[0].i) / sizeof(long long));
     for (int off = kLanes / 2; off > 0; off >>= 1) {
-      for (int l = 0; l < kLanes; ++l) {
+      for (int l = 0; l < kThreads; ++l) {
         for (int k = 0; k < nd; ++k) q[l].d[k] = p[l].d[k] + p[l ^ off].d[k];
         for (int k = 0; k < ni; ++k) q[l].i[k] = p[l].i[k] + p[l ^ off].i[k];
       }
-      for (int l = 0; l < kLanes; ++l) p[l] = q[l];
+      for (int l = 0; l < kThreads; ++l) p[l] = q[l];
     }
-    return p[0];
+    A r;
+    for (int k = 0; k < nd; ++k) r.d[k] = (p[0].d[k] + p[kLanes].d[k]) + (p[2 * kLanes].d[k] + p[3 * kLanes].d[k]);
+    for (int k = 0; k < ni; ++k) r.i[k] = (p[0].i[k] + p[kLanes].i[k]) + (p[2 * kLanes].i[k] + p[3 * kLanes].i[k]);
+    return r;
   }
 };
+static_assert(kWarps == 4, "the fixed-order sum of the warp totals is written for four warps");
 
 }  // namespace lgr_fmt
