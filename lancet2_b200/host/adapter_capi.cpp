@@ -128,6 +128,7 @@ void BuildJobs(const lgr_batch_in* in, const char* names, const char* samples, c
         const int al = in->var_allele[o + h];
         if (al <= 0) continue;
         vi.alts[al - 1].seq_len = (size_t)in->var_len[o + h];
+        vi.alts[al - 1].length = (long long)in->var_len[o + h] - (long long)vi.ref_allele_len;
         vi.alts[al - 1].hap_start0.emplace_back((size_t)h, (size_t)in->var_start[o + h]);
       }
     }
@@ -301,6 +302,68 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
     return WriteOut(DumpResults(in, js, res), out, cap);
   } catch (const std::exception& e) {
     std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
+    return -2;
+  }
+}
+
+// SURVEY.md §8f #2 — EvidenceColumns::AppendJob over every group of the batch on caller-provided
+// lgr_assign records (no device involved).  Returns the columns as a lgr_evidence_in that stays
+// valid until the next call on this thread; key_out[3 s + 0..2] = group, variant (index within
+// the group) and sample id of support s (at most key_cap supports are described).
+const lgr_evidence_in* lgr_adapter_evidence_columns(const lgr_batch_in* in, const char* names, const char* samples,
+                                                    const int* sample_id, const long long* start0, const long long* isize,
+                                                    const unsigned short* sam_flag, const unsigned char* mapq,
+                                                    const unsigned char* softclip, const lgr_assign* assign, int* key_out,
+                                                    int key_cap) {
+  static thread_local lancet_gpu::EvidenceColumns cols;
+  static thread_local JobSet js;
+  try {
+    js = JobSet();
+    BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
+    cols.Clear();
+    long long off = 0;
+    std::vector<int> job_of_support;
+    for (std::size_t g = 0; g < js.jobs.size(); ++g) {
+      cols.AppendJob(js.jobs[g], assign + off, X31OfView);
+      off += (long long)(js.jobs[g].n_reads * js.jobs[g].n_variants);
+      job_of_support.resize(cols.NumSupports(), (int)g);
+    }
+    for (std::size_t s = 0; s < cols.NumSupports() && (int)s < key_cap; ++s) {
+      const auto& k = cols.Keys()[s];
+      const int v = (int)(static_cast<const lancet_gpu::VariantIn*>(k.variant) - js.vars.data());
+      int sid = -1;
+      for (std::size_t i = 0; i < js.sn.size(); ++i)
+        if (js.sn[i] == k.sample) sid = (int)i;
+      key_out[3 * s] = job_of_support[s], key_out[3 * s + 1] = v - in->grp_var_begin[job_of_support[s]], key_out[3 * s + 2] = sid;
+    }
+    return &cols.In();
+  } catch (const std::exception&) {
+    return nullptr;
+  }
+}
+
+// The same columns through lancet_gpu::GpuFormatMetrics::Compute on `device`: out must hold one
+// lgr_format per support (n_out of them); returns the number of supports, < 0 on error (message in err).
+int lgr_adapter_format_metrics(int device, const lgr_batch_in* in, const char* names, const char* samples, const int* sample_id,
+                               const long long* start0, const long long* isize, const unsigned short* sam_flag,
+                               const unsigned char* mapq, const unsigned char* softclip, const lgr_assign* assign,
+                               lgr_format* out, int n_out, char* err, int err_cap) {
+  try {
+    JobSet js;
+    BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
+    lancet_gpu::EvidenceColumns cols;
+    long long off = 0;
+    for (std::size_t g = 0; g < js.jobs.size(); ++g) {
+      cols.AppendJob(js.jobs[g], assign + off, X31OfView);
+      off += (long long)(js.jobs[g].n_reads * js.jobs[g].n_variants);
+    }
+    if ((int)cols.NumSupports() > n_out) throw std::runtime_error("output too small");
+    lancet_gpu::GpuFormatMetrics fm(device);
+    const std::vector<lgr_format> res = fm.Compute(cols);
+    std::memcpy(out, res.data(), res.size() * sizeof(lgr_format));
+    return (int)res.size();
+  } catch (const std::exception& e) {
+    std::snprintf(err, (size_t)err_cap, "%s", e.what());
     return -2;
   }
 }

@@ -236,6 +236,95 @@ Result PackedBatch::BuildResult(const GenotypeJob& j, const lgr_assign* assign, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// EvidenceColumns / GpuFormatMetrics
+// ---------------------------------------------------------------------------------------------
+void EvidenceColumns::Clear() {
+  mKeys.clear();
+  mSupBegin.assign(1, 0);
+  for (auto* v : {&mInsertSize, &mAlnStart}) v->clear();
+  for (auto* v : {&mNumAlleles, &mVariantLen, &mTotalHaps}) v->clear();
+  for (auto* v : {&mAlnScore, &mFoldedPos}) v->clear();
+  for (auto* v : {&mRnameHash, &mRefNm, &mOwnHapNm, &mHapId}) v->clear();
+  for (auto* v : {&mAllele, &mFlags, &mBaseQual, &mMapQual}) v->clear();
+}
+
+void EvidenceColumns::AppendJob(const GenotypeJob& j, const lgr_assign* assign, const NameHashFn& name_hash) {
+  // name hashes once per read that has any assignment (AddToTable hashes once per read, genotyper.cpp:426)
+  std::vector<std::uint32_t> hash(j.n_reads, 0);
+  for (std::size_t r = 0; r < j.n_reads; ++r)
+    for (std::size_t v = 0; v < j.n_variants; ++v)
+      if (assign[r * j.n_variants + v].assigned) {
+        hash[r] = name_hash(j.reads[r].qname);
+        break;
+      }
+  std::vector<std::string_view> samples;  // FindOrCreate's creation order for this variant
+  for (std::size_t v = 0; v < j.n_variants; ++v) {
+    const VariantIn& var = j.variants[v];
+    samples.clear();
+    for (std::size_t r = 0; r < j.n_reads; ++r) {
+      if (!assign[r * j.n_variants + v].assigned) continue;
+      const std::string_view s = j.reads[r].sample_name;
+      bool seen = false;
+      for (const auto& x : samples) seen = seen || x == s;
+      if (!seen) samples.push_back(s);
+    }
+    std::int64_t max_len = 0;  // variant_call.cpp:179-182: max |mLength| over the ALTs
+    for (const auto& alt : var.alts) max_len = std::max<std::int64_t>(max_len, alt.length < 0 ? -alt.length : alt.length);
+    for (const auto& sample : samples) {
+      for (std::size_t r = 0; r < j.n_reads; ++r) {
+        const lgr_assign& a = assign[r * j.n_variants + v];
+        const ReadIn& rd = j.reads[r];
+        if (!a.assigned || rd.sample_name != sample) continue;
+        mInsertSize.push_back(rd.insert_size);
+        mAlnStart.push_back(rd.start0);
+        mAlnScore.push_back(static_cast<double>(a.global_score) + (a.local_score * a.local_identity));  // CombinedScore()
+        mFoldedPos.push_back(a.folded_read_pos);
+        mRnameHash.push_back(hash[r]);
+        mRefNm.push_back(a.ref_nm), mOwnHapNm.push_back(a.own_hap_nm), mHapId.push_back(a.hap_id);
+        mAllele.push_back(static_cast<std::uint8_t>(a.allele));
+        mFlags.push_back(static_cast<std::uint8_t>(((rd.sam_flag & 0x10) ? LGR_EV_REV : 0u) | (rd.is_soft_clipped ? LGR_EV_SOFTCLIP : 0u) |
+                                                   ((rd.sam_flag & 0x2) ? LGR_EV_PROPER_PAIR : 0u)));
+        mBaseQual.push_back(a.base_qual), mMapQual.push_back(rd.map_qual);
+      }
+      mKeys.push_back(SupportKey{var.key, sample});
+      mSupBegin.push_back(static_cast<std::int64_t>(mAllele.size()));
+      mNumAlleles.push_back(static_cast<std::int32_t>(1 + var.alts.size()));
+      mVariantLen.push_back(static_cast<std::int32_t>(max_len));
+      mTotalHaps.push_back(static_cast<std::int32_t>(j.n_haps));
+    }
+  }
+}
+
+const lgr_evidence_in& EvidenceColumns::In() {
+  mIn = lgr_evidence_in{};
+  mIn.n_supports = static_cast<std::int32_t>(mKeys.size());
+  mIn.n_evidence = static_cast<std::int64_t>(mAllele.size());
+  mIn.sup_begin = mSupBegin.data(), mIn.sup_n_alleles = mNumAlleles.data();
+  mIn.sup_variant_len = mVariantLen.data(), mIn.sup_total_haps = mTotalHaps.data();
+  mIn.insert_size = mInsertSize.data(), mIn.aln_start = mAlnStart.data();
+  mIn.aln_score = mAlnScore.data(), mIn.folded_pos = mFoldedPos.data();
+  mIn.rname_hash = mRnameHash.data(), mIn.ref_nm = mRefNm.data(), mIn.own_hap_nm = mOwnHapNm.data(), mIn.hap_id = mHapId.data();
+  mIn.allele = mAllele.data(), mIn.flags = mFlags.data(), mIn.base_qual = mBaseQual.data(), mIn.map_qual = mMapQual.data();
+  return mIn;
+}
+
+GpuFormatMetrics::GpuFormatMetrics(int device_ordinal) {
+  const int rc = lgr_format_create(device_ordinal, &mCtx);
+  if (rc != LGR_OK)
+    throw std::runtime_error(std::string("lancet_gpu::GpuFormatMetrics: ") + lgr_strerror(rc) + ": " + lgr_format_last_error(nullptr));
+}
+
+GpuFormatMetrics::~GpuFormatMetrics() { lgr_format_destroy(mCtx); }
+
+std::vector<lgr_format> GpuFormatMetrics::Compute(EvidenceColumns& columns, float* ms_kernels) {
+  std::vector<lgr_format> out(columns.NumSupports());
+  const int rc = lgr_format_metrics(mCtx, &columns.In(), out.data(), ms_kernels);
+  if (rc != LGR_OK)
+    throw std::runtime_error(std::string("lancet_gpu::GpuFormatMetrics: ") + lgr_strerror(rc) + ": " + lgr_format_last_error(mCtx));
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
 // GpuGenotyper
 // ---------------------------------------------------------------------------------------------
 GpuGenotyper::GpuGenotyper(int device_ordinal, const lgr_params* params) {

@@ -58,6 +58,7 @@ struct ReadIn {
 struct AltAlleleIn {
   std::size_t seq_len;                                             // mSequence.size()
   std::vector<std::pair<std::size_t, std::size_t>> hap_start0;     // mLocalHapStart0Idxs (hap → start)
+  std::int64_t length = 0;                                         // mLength (alt_allele.h:50), for ASMD only
 };
 struct VariantIn {
   const void* key;                 // RawVariant const* (the Result key)
@@ -122,6 +123,52 @@ struct GenotypeJob {
   std::size_t n_reads;
   const VariantIn* variants;
   std::size_t n_variants;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the evidence as SoA columns for the device FORMAT math (lgr_format_metrics)
+// ---------------------------------------------------------------------------------------------
+// Identity of one support = one VariantSupport of the reference's Result (variant → sample).
+struct SupportKey {
+  const void* variant;      // RawVariant const*
+  std::string_view sample;  // aliases ReadIn::sample_name, like SupportArray's names (support_array.h:25-29)
+};
+
+// AddToTable (genotyper.cpp:423-456) with the evidence written as lgr_evidence_in columns instead
+// of per-allele vectors: supports in (job, variant, sample-first-seen) order, records of a support
+// in read order — the append order AddEvidence sees — so the device dedup (first seen per allele
+// and name hash) keeps exactly the records VariantSupport would keep.
+class EvidenceColumns {
+ public:
+  void Clear();
+  void AppendJob(const GenotypeJob& job, const lgr_assign* assign, const NameHashFn& name_hash);
+  [[nodiscard]] const lgr_evidence_in& In();
+  [[nodiscard]] const std::vector<SupportKey>& Keys() const noexcept { return mKeys; }
+  [[nodiscard]] std::size_t NumSupports() const noexcept { return mKeys.size(); }
+
+ private:
+  std::vector<SupportKey> mKeys;
+  std::vector<std::int64_t> mSupBegin{0}, mInsertSize, mAlnStart;
+  std::vector<std::int32_t> mNumAlleles, mVariantLen, mTotalHaps;
+  std::vector<double> mAlnScore, mFoldedPos;
+  std::vector<std::uint32_t> mRnameHash, mRefNm, mOwnHapNm, mHapId;
+  std::vector<std::uint8_t> mAllele, mFlags, mBaseQual, mMapQual;
+  lgr_evidence_in mIn{};
+};
+
+// Owner of one lgr_fmt_ctx: every FORMAT accessor of every support in one device call
+// (variant_support.cpp:140-335 → k_fmt_dedup / k_fmt_metrics).  Throws std::runtime_error on any
+// non-zero return code, like the rest of the adapter; no CPU fallback.
+class GpuFormatMetrics {
+ public:
+  explicit GpuFormatMetrics(int device_ordinal = 0);
+  ~GpuFormatMetrics();
+  GpuFormatMetrics(const GpuFormatMetrics&) = delete;
+  GpuFormatMetrics& operator=(const GpuFormatMetrics&) = delete;
+  std::vector<lgr_format> Compute(EvidenceColumns& columns, float* ms_kernels = nullptr);
+
+ private:
+  lgr_fmt_ctx* mCtx = nullptr;
 };
 
 // One Genotype() payload already in the C-ABI's SoA layout, offsets relative to the job.  Built by
