@@ -50,3 +50,29 @@ def merge_in_submission_order(shards: Sequence[Sequence[int]], per_rank_results:
         for i, r in zip(idx, res):
             out[i] = r
     return out
+
+
+def support_cost(n_records: int) -> int:
+    """work estimate of one VariantSupport in the FORMAT-math kernels: linear passes
+    plus the O(n^2) rank / bin scans"""
+    n = max(0, int(n_records))
+    return 64 + 16 * n + n * n // 8
+
+
+def partition_supports(n_records: Sequence[int], world: int) -> List[List[int]]:
+    """the same longest-processing-time partition for supports (one variant x one sample each):
+    supports are independent, so every rank runs `lgr_format_metrics` on its shard and the
+    records are merged back with `merge_in_submission_order`; no collective."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    order = sorted(range(len(n_records)), key=lambda i: (-support_cost(n_records[i]), i))
+    heap = [(0, r) for r in range(world)]
+    heapq.heapify(heap)
+    shards: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        load, r = heapq.heappop(heap)
+        shards[r].append(i)
+        heapq.heappush(heap, (load + support_cost(n_records[i]), r))
+    for s in shards:
+        s.sort()
+    return shards

@@ -87,3 +87,42 @@ def test_partition_balances_cost():
         assert max(loads) <= 1.25 * (sum(loads) / world) + max(group_cost(g) for g in groups)
     with pytest.raises(ValueError):
         partition_groups(groups, 0)
+
+
+def _format_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import format_lib as F
+    from lancet2_b200.dispatch import merge_in_submission_order, partition_supports
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(31)
+    sups = [F.random_support(rng) for _ in range(60)] + [F.random_support(rng, n=300, n_alleles=2)]
+    shards = partition_supports([len(s["allele"]) for s in sups], world)
+    _, mine = F.emu_format([sups[i] for i in shards[rank]])   # the host build of the device core stands in for the GPU
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [m.tobytes() for m in mine])
+    if rank == 0:
+        merged = merge_in_submission_order(shards, gathered)
+        _, single = F.emu_format(sups)
+        q.put((merged == [s.tobytes() for s in single], [len(s) for s in shards]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_of_supports():
+    """the FORMAT-math row shards by support: records computed on two ranks and merged
+    back equal the single-process records byte for byte"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_format_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, sizes = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and min(sizes) >= 1 and sum(sizes) == 61
