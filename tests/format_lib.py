@@ -243,3 +243,37 @@ def supports_from_assignments(batch, assign, seed=0, n_samples=2):
                 sup.update(n_alleles=k, variant_len=int(batch.var_len[lo]), total_haps=P)
                 sups.append(sup)
     return sups
+
+
+def edge_supports(seed=12):
+    """extreme qualities, 2^40 insert sizes / starts, bins around zero, big tie groups, zero variance,
+    one read name, single-allele and 8-allele supports, u32 / i32 maxima"""
+    rng = np.random.default_rng(seed)
+
+    def sup(n, k, **over):
+        s = random_support(rng, n=n, n_alleles=k)
+        s.update(over)
+        return s
+
+    n = 40
+    return [
+        sup(1, 2), sup(1, 1), sup(2, 2, allele=np.array([0, 1])), sup(3, 2, allele=np.array([1, 1, 1])),
+        sup(n, 2, base_qual=np.full(n, 255)), sup(n, 2, base_qual=np.zeros(n, int)), sup(n, 2, base_qual=np.full(n, 93)),
+        sup(n, 2, insert_size=rng.integers(-(1 << 40), 1 << 40, n)), sup(n, 2, aln_start=rng.integers(-(1 << 40), 1 << 40, n)),
+        sup(n, 2, aln_start=np.arange(n) - 20),                       # bins around zero: C truncation of start / 3
+        sup(n, 2, folded_pos=np.where(np.arange(n) % 2, 0.0, 0.5)),    # two big tie groups
+        sup(n, 2, folded_pos=np.full(n, 0.25), map_qual=np.full(n, 60), base_qual=np.full(n, 37)),  # var_u = 0 → 0.0
+        sup(n, 2, rname_hash=np.full(n, 7)),                           # one read name: one record per allele survives
+        sup(n, 2, allele=np.zeros(n, int)), sup(n, 2, allele=np.ones(n, int)), sup(n, 1, allele=np.zeros(n, int)),
+        sup(n, 8, allele=np.arange(n) % 8), sup(n, 3, allele=np.arange(n) % 3, total_haps=1),
+        sup(n, 2, aln_score=np.full(n, -1e300)), sup(n, 2, hap_id=np.full(n, 4294967295)),
+        sup(n, 2, ref_nm=np.full(n, 4294967295), own_hap_nm=np.full(n, 4294967295), variant_len=2147483647),
+    ]
+
+
+def load_golden_edge():
+    import json
+    g = json.load(open(os.path.join(HERE, "golden", "format_golden.json")))
+    sups = [c["support"] for c in g["edge"]]
+    want = np.frombuffer(bytes.fromhex("".join(c["record"] for c in g["edge"])), dtype=abi.FORMAT_DTYPE).copy()
+    return sups, want

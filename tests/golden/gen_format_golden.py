@@ -3,6 +3,7 @@
 (src/lancet/caller/variant_support.cpp, genotype_likelihood.cpp, posterior_base_qual.cpp and
 base/mann_whitney.h compiled unmodified into oracle/_ref by `make -C oracle ref`):
   * `random`: seeded evidence streams and every FORMAT accessor's value (lgr_format records, hex);
+  * `edge`: tests/format_lib.py:edge_supports (extreme qualities and magnitudes, ties, single alleles);
   * `scipy`: the rows of the reference's scipy-derived Mann-Whitney fixture
     (tests/data/base/mann_whitney_scipy_ref.tsv, consumed by tests/base/mann_whitney_test.cpp:231-330)
     — inputs and expected effect sizes, read from the reference tree at generation time.
@@ -32,6 +33,8 @@ def main():
     sups += [F.random_support(rng, n=int(rng.integers(150, 400)), n_alleles=2) for _ in range(6)]
     sups += [F.random_support(rng, n=60, n_alleles=8), F.random_support(rng, n=0, n_alleles=2)]
     ref = F.ref_format(sups)
+    edge = F.edge_supports()
+    ref_edge = F.ref_format(edge)
     scipy_rows = []
     with open(TSV) as fh:
         next(fh)
@@ -46,6 +49,7 @@ def main():
                          "tests/data/base/mann_whitney_scipy_ref.tsv",
                "dtype_itemsize": abi.FORMAT_DTYPE.itemsize,
                "random": [{"support": to_json(s), "record": ref[i:i + 1].tobytes().hex()} for i, s in enumerate(sups)],
+               "edge": [{"support": to_json(s), "record": ref_edge[i:i + 1].tobytes().hex()} for i, s in enumerate(edge)],
                "scipy": scipy_rows},
               open(os.path.join(HERE, "format_golden.json"), "w"), separators=(",", ":"))
     print("wrote", len(sups), "random supports and", len(scipy_rows), "scipy rows")

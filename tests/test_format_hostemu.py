@@ -120,3 +120,21 @@ def test_device_path_refuses_without_a_gpu():
     from lancet2_b200.format_metrics import GpuFormatMetrics
     with pytest.raises(RuntimeError, match="no CUDA device|no usable CUDA device"):
         GpuFormatMetrics(0)
+
+
+@pytest.mark.skipif(not F.have_ref(), reason="oracle/_ref not built (needs the reference tree)")
+def test_edge_supports_against_live_reference():
+    cases = F.edge_supports()
+    rc, got = F.emu_format(cases)
+    assert rc == 0
+    errs = F.compare_format(F.ref_format(cases), got)
+    assert not errs, "\n".join(errs[:20])
+
+
+def test_golden_edge_supports():
+    sups, want = F.load_golden_edge()
+    assert len(sups) >= 20
+    rc, got = F.emu_format(sups)
+    assert rc == 0
+    errs = F.compare_format(want, got)
+    assert not errs, "\n".join(errs[:20])

@@ -124,3 +124,16 @@ def test_gpu_format_metrics_class(lib):  # noqa: F811
     assert rc == 0
     errs = F.compare_format(emu, out)
     assert not errs, "\n".join(errs[:20])
+
+
+@pytest.mark.gpu
+def test_gpu_golden_edge_supports():
+    from lancet2_b200.format_metrics import GpuFormatMetrics
+    sups, want = F.load_golden_edge()
+    fmt = GpuFormatMetrics(0)
+    try:
+        got, _ = fmt.compute(sups)
+    finally:
+        fmt.close()
+    errs = F.compare_format(want, got)
+    assert not errs, "\n".join(errs[:20])
