@@ -267,7 +267,9 @@ void* lgr_stream(lgr_ctx* ctx);
  * f64 metrics are warp-tree sums with CUDA's libm (log10/log2/log/lgamma/pow), i.e. equal to the
  * reference within 1e-9 relative (the reference's own tests use 1e-6, and its entropy sums run
  * in abseil's salted hash-map order, so it does not reproduce its own last bits either).
- * Own context (device buffers + stream), independent of lgr_ctx; no CPU fallback.
+ * Own context (device buffers + stream), independent of lgr_ctx; a context is bound to one GPU
+ * and may be used by one thread at a time (one per worker, like lgr_ctx); the call returns when
+ * `out` is filled.  No CPU fallback: lgr_format_create returns LGR_E_NO_DEVICE without a GPU.
  */
 #define LGR_FMT_MAX_ALLELES 8
 #define LGR_FMT_MAX_GENOTYPES 36 /* K(K+1)/2 at K = 8 */

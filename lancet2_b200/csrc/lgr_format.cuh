@@ -442,7 +442,7 @@ FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, 
 // the reduction on 128 emulated threads (host) — bit-identical to the device version: the
 // xor-butterfly inside each group of 32 (IEEE addition is commutative, so at every level both
 // partners add the same two numbers), then (w0 + w1) + (w2 + w3) over the four warp totals.
-struct WarpHost {
+struct CtaHost {
   FMT_HD bool leader() const { return true; }
   template <class A, class F>
   inline A reduce(const F& f) {

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE: lancet2_b200/csrc/lgr_format.cuh — the code k_fmt_dedup / k_fmt_metrics run —
-// compiled by g++ with the 32 lanes of a warp emulated (lgr_fmt::WarpHost), behind the same
+// compiled by g++ with the 32 lanes of a warp emulated (lgr_fmt::CtaHost), behind the same
 // signature as the C-ABI's lgr_format_metrics, so CPU tests can diff the device arithmetic
 // against the reference (oracle/_ref) and the golden vectors without a GPU.
 #include <vector>
@@ -27,7 +27,7 @@ extern "C" int emu_format_metrics_ex(const lgr_evidence_in* in, lgr_format* out,
       keep[(size_t)i] = dedup_keep(in->allele, in->rname_hash, in->sup_begin[s], i);
   Ev e{in->insert_size, in->aln_start, in->aln_score, in->folded_pos, in->rname_hash, in->ref_nm, in->own_hap_nm,
        in->hap_id,      in->allele,    in->flags,     in->base_qual,  in->map_qual,   keep.data()};
-  WarpHost w;
+  CtaHost w;
   for (int t = 0; t < (split_tasks ? kNumTasks : 1); ++t)
     for (int s = 0; s < S; ++s)
       support_metrics(w, e, in->sup_begin[s], in->sup_begin[s + 1], in->sup_n_alleles[s], in->sup_variant_len[s],
