@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE: lancet2_b200/csrc/lgr_format.cuh — the code k_fmt_dedup / k_fmt_metrics run —
-// compiled by g++ with the 32 lanes of a warp emulated (lgr_fmt::CtaHost), behind the same
+// compiled by g++ with the 128 threads of a CTA emulated (lgr_fmt::CtaHost), behind the same
 // signature as the C-ABI's lgr_format_metrics, so CPU tests can diff the device arithmetic
 // against the reference (oracle/_ref) and the golden vectors without a GPU.
 #include <vector>
