@@ -49,6 +49,17 @@ __global__ void __launch_bounds__(256) k_fmt_dedup(const __grid_constant__ FmtDe
 struct CtaDev {
   int tid;
   __device__ __forceinline__ bool leader() const { return tid == 0; }
+#ifdef LGR_FMT_SORT  // not in the default build until it has run on a GPU
+  uint64_t* keys_;
+  uint8_t* tags_;
+  __device__ __forceinline__ uint64_t* sort_keys() const { return keys_; }
+  __device__ __forceinline__ uint8_t* sort_tags() const { return tags_; }
+  template <class F>
+  __device__ __forceinline__ void each(const F& f) {
+    f(tid);
+    __syncthreads();
+  }
+#endif
   template <class A, class F>
   __device__ __forceinline__ A reduce(const F& f) {
     constexpr int nd = (int)(sizeof(A::d) / sizeof(double)), ni = (int)(sizeof(A::i) / sizeof(long long));
@@ -82,7 +93,13 @@ struct CtaDev {
 // taken in a grid-stride loop along x.  A batch of a few hundred supports is a few thousand CTAs.
 __global__ void __launch_bounds__(lgr_fmt::kThreads) k_fmt_metrics(const __grid_constant__ FmtDev D) {
   const unsigned task = 1u << blockIdx.y;
+#ifdef LGR_FMT_SORT
+  __shared__ uint64_t s_keys[lgr_fmt::kSortCap];
+  __shared__ uint8_t s_tags[lgr_fmt::kSortCap];
+  CtaDev w{(int)threadIdx.x, s_keys, s_tags};
+#else
   CtaDev w{(int)threadIdx.x};
+#endif
   for (int s = (int)blockIdx.x; s < D.n_supports; s += (int)gridDim.x) {
     lgr_fmt::support_metrics(w, D.e, D.sup_begin[s], D.sup_begin[s + 1], D.sup_n_alleles[s], D.sup_variant_len[s],
                              D.sup_total_haps[s], g_phred, &D.out[s], task);

@@ -19,6 +19,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/lancet_gpu_realign.h"
 
@@ -178,6 +179,126 @@ FMT_HD double alt_entropy(W& w, const Ev& e, int64_t b, int64_t n_end, long long
   const double max_entropy = log2(total < max_bins ? total : max_bins);
   return max_entropy > 0.0 ? (r.d[0] / max_entropy) : 0.0;
 }
+
+#ifdef LGR_FMT_SORT
+// ---- sort instead of scan — compiled only with -DLGR_FMT_SORT: checked on the
+// CPU against the scan build and the reference, not yet run on a GPU, therefore not in the
+// default device build.  Supports of up to kSortCap records sort their keys in shared memory
+// with a bitonic network (one `each` phase per stage: the compare-exchanges of a stage are
+// disjoint, so the host emulation may run them thread by thread); larger supports keep the scan.
+constexpr int kSortCap = 2048;
+constexpr uint64_t kSortSentinel = ~0ull;  // dropped records sort behind every real key
+
+FMT_HD uint64_t ordered_f64(double x) {  // u64 image with the order of the doubles; -0.0 and +0.0 tie
+  if (x == 0.0) x = 0.0;
+  uint64_t u;
+  memcpy(&u, &x, sizeof u);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+FMT_HD uint64_t ordered_i64(long long v) { return (uint64_t)v ^ 0x8000000000000000ull; }
+
+template <class W, class Key>
+FMT_HD int fill_and_sort(W& w, int n, const Key& key) {  // key(idx) → sentinel for records that do not take part
+  uint64_t* keys = w.sort_keys();
+  uint8_t* tags = w.sort_tags();
+  int m = 2;
+  while (m < n) m <<= 1;
+  w.each([&](int t) {
+    for (int idx = t; idx < m; idx += kThreads) {
+      uint8_t tag = 0;
+      keys[idx] = idx < n ? key(idx, &tag) : kSortSentinel;
+      tags[idx] = tag;
+    }
+  });
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1)
+      w.each([&](int t) {
+        for (int idx = t; idx < m; idx += kThreads) {
+          const int partner = idx ^ j;
+          if (partner <= idx) continue;
+          const bool up = (idx & k) == 0;
+          const uint64_t a = keys[idx], c = keys[partner];
+          if ((a > c) == up && a != c) {
+            keys[idx] = c, keys[partner] = a;
+            const uint8_t ta = tags[idx];
+            tags[idx] = tags[partner], tags[partner] = ta;
+          }
+        }
+      });
+  return m;
+}
+
+FMT_HD int lower_bound_u64(const uint64_t* keys, int n, uint64_t x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] < x) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+FMT_HD int upper_bound_u64(const uint64_t* keys, int n, uint64_t x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] <= x) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <class W>
+FMT_HD double mw_folded_sorted(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_ref, long long n_alt) {
+  const int n = (int)(n_end - b), n_kept = (int)(n_ref + n_alt);
+  fill_and_sort(w, n, [&](int idx, uint8_t* tag) {
+    const int64_t i = b + idx;
+    if (!e.keep[i]) return kSortSentinel;
+    *tag = e.allele[i] != 0;
+    return ordered_f64(e.folded_pos[i]);
+  });
+  const uint64_t* keys = w.sort_keys();
+  const uint8_t* tags = w.sort_tags();
+  Acc<0, 2> r = w.template reduce<Acc<0, 2>>([&](int lane) {
+    Acc<0, 2> a;
+    for (int p = lane; p < n_kept; p += kThreads) {
+      const uint64_t x = keys[p];
+      const long long lo = lower_bound_u64(keys, n_kept, x), hi = upper_bound_u64(keys, n_kept, x);
+      if (tags[p]) a.i[0] += lo + hi + 1;  // 2 x mid-rank = i + 1 + jdx
+      if (p == lo) {
+        const long long ts = hi - lo;
+        a.i[1] += ts * ts * ts - ts;
+      }
+    }
+    return a;
+  });
+  return mw_effect(r.i[0], r.i[1], n_ref, n_alt);
+}
+
+template <class W, class Val>
+FMT_HD double alt_entropy_sorted(W& w, const Ev& e, int64_t b, int64_t n_end, long long n_alt, double max_bins, long long width,
+                                 const Val& val) {
+  const int n = (int)(n_end - b), na = (int)n_alt;
+  fill_and_sort(w, n, [&](int idx, uint8_t*) {
+    const int64_t i = b + idx;
+    if (!e.keep[i] || e.allele[i] == 0) return kSortSentinel;
+    return ordered_i64(val(i) / width);
+  });
+  const uint64_t* keys = w.sort_keys();
+  const double total = (double)n_alt;
+  Acc<1, 0> r = w.template reduce<Acc<1, 0>>([&](int lane) {
+    Acc<1, 0> a;
+    for (int p = lane; p < na; p += kThreads) {
+      const uint64_t x = keys[p];
+      if (p > 0 && keys[p - 1] == x) continue;  // not the bin's first key
+      const double prob = (double)(upper_bound_u64(keys, na, x) - p) / total;
+      a.d[0] -= prob * log2(prob);
+    }
+    return a;
+  });
+  const double max_entropy = log2(total < max_bins ? total : max_bins);
+  return max_entropy > 0.0 ? (r.d[0] / max_entropy) : 0.0;
+}
+#endif  // LGR_FMT_SORT
 
 // genotype_likelihood.cpp:29-46 LogDirichletMultinomial
 FMT_HD double log_dm(const int* counts, const double* alphas, int K) {
@@ -393,19 +514,34 @@ FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, 
     if (lead) out->bqcd = v;
   }
   if (tasks & kTaskRpcd) {
+#ifdef LGR_FMT_SORT
+    const double v = !both ? 0.0 : (n_end - b <= kSortCap ? mw_folded_sorted(w, e, b, n_end, n_ref, n_alt) : mw_folded(w, e, b, n_end, n_ref, n_alt));
+#else
     const double v = both ? mw_folded(w, e, b, n_end, n_ref, n_alt) : 0.0;
+#endif
     if (lead) out->rpcd = v;
   }
   // ---- pooled-ALT entropies: FSSE (3 bp start bins, <= 20 bins) and HSE (variant_support.cpp:270-291) ----
   if (tasks & kTaskFsse) {
-    const double v = n_alt >= 3 ? alt_entropy(w, e, b, n_end, n_alt, 20.0, 3, [&](int64_t j) { return (long long)e.aln_start[j]; })
-                                : 0.0;
+    auto start_of = [&](int64_t j) { return (long long)e.aln_start[j]; };
+#ifdef LGR_FMT_SORT
+    const double v = n_alt < 3 ? 0.0 : (n_end - b <= kSortCap ? alt_entropy_sorted(w, e, b, n_end, n_alt, 20.0, 3, start_of)
+                                                             : alt_entropy(w, e, b, n_end, n_alt, 20.0, 3, start_of));
+#else
+    const double v = n_alt >= 3 ? alt_entropy(w, e, b, n_end, n_alt, 20.0, 3, start_of) : 0.0;
+#endif
     if (lead) out->fsse = v;
   }
   if (tasks & kTaskHse) {
-    const double v = n_alt >= 3 && total_haps >= 2
-                         ? alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, 1, [&](int64_t j) { return (long long)e.hap_id[j]; })
-                         : 0.0;
+    auto hap_of = [&](int64_t j) { return (long long)e.hap_id[j]; };
+#ifdef LGR_FMT_SORT
+    const double v = !(n_alt >= 3 && total_haps >= 2)
+                         ? 0.0
+                         : (n_end - b <= kSortCap ? alt_entropy_sorted(w, e, b, n_end, n_alt, (double)total_haps, 1, hap_of)
+                                                  : alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, 1, hap_of));
+#else
+    const double v = n_alt >= 3 && total_haps >= 2 ? alt_entropy(w, e, b, n_end, n_alt, (double)total_haps, 1, hap_of) : 0.0;
+#endif
     if (lead) out->hse = v;
   }
   // ---- CMLOD (genotype_likelihood.cpp:165-205) ----
@@ -444,6 +580,16 @@ FMT_HD void support_metrics(W& w, const Ev& e, int64_t b, int64_t n_end, int K, 
 // partners add the same two numbers), then (w0 + w1) + (w2 + w3) over the four warp totals.
 struct CtaHost {
   FMT_HD bool leader() const { return true; }
+#ifdef LGR_FMT_SORT
+  uint64_t keys_[kSortCap];
+  uint8_t tags_[kSortCap];
+  uint64_t* sort_keys() { return keys_; }
+  uint8_t* sort_tags() { return tags_; }
+  template <class F>
+  inline void each(const F& f) {  // one phase: every thread once, then a barrier
+    for (int t = 0; t < kThreads; ++t) f(t);
+  }
+#endif
   template <class A, class F>
   inline A reduce(const F& f) {
     A p[kThreads], q[kThreads];

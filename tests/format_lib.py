@@ -36,6 +36,33 @@ def load_emu():
     return _emu
 
 
+_emu_sort = None
+EMU_SORT_SO = os.path.join(HERE, "hostemu", "libformat_emu_sort.so")
+
+
+def load_emu_sort():
+    """the same core compiled with -DLGR_FMT_SORT (shared-memory sort instead of the
+    O(n^2) scans; checked on the CPU only, not in the default device build)"""
+    global _emu_sort
+    if _emu_sort is None:
+        deps = [EMU_SRC, CORE, os.path.join(ROOT, "include", "lancet_gpu_realign.h")]
+        if not os.path.exists(EMU_SORT_SO) or os.path.getmtime(EMU_SORT_SO) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DLGR_FMT_SORT",
+                                   "-Wno-unknown-pragmas", "-o", EMU_SORT_SO, EMU_SRC])
+        _emu_sort = C.CDLL(EMU_SORT_SO)
+        _emu_sort.emu_format_metrics_ex.argtypes = [C.POINTER(abi.LgrEvidenceIn), C.c_void_p, C.c_int]
+        _emu_sort.emu_format_metrics_ex.restype = C.c_int
+    return _emu_sort
+
+
+def emu_format_sort(supports):
+    batch = supports if isinstance(supports, abi.EvidenceBatch) else abi.EvidenceBatch(supports)
+    out = np.zeros(batch.n_supports, dtype=abi.FORMAT_DTYPE)
+    st = batch.c_struct()
+    rc = load_emu_sort().emu_format_metrics_ex(C.byref(st), out.ctypes.data, 1)
+    return rc, out
+
+
 def emu_format(supports, split_tasks=True):
     """split_tasks: one call of the core per (support, task) — what k_fmt_metrics launches; False: all
     tasks of a support in one call."""

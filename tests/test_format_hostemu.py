@@ -138,3 +138,24 @@ def test_golden_edge_supports():
     assert rc == 0
     errs = F.compare_format(want, got)
     assert not errs, "\n".join(errs[:20])
+
+
+def test_sort_build_equals_scan_build():
+    """-DLGR_FMT_SORT (the next round's device build): ranks and bins from a
+    shared-memory bitonic sort instead of the O(n^2) scans.  The Mann-Whitney statistics are
+    integers, so RPCD must keep its bits; the entropies add their terms in sorted-bin order
+    (tolerance).  Supports beyond the 2048-record cap take the scan in both builds."""
+    rng = np.random.default_rng(77)
+    sups = [F.random_support(rng) for _ in range(300)] + F.edge_supports()
+    sups += [F.random_support(rng, n=n, n_alleles=2) for n in (127, 128, 129, 1000, 2047, 2048, 2049, 2500)]
+    sups += [dict(F.random_support(rng, n=50, n_alleles=2), folded_pos=np.where(np.arange(50) % 2, -0.0, 0.0))]
+    rc, scan = F.emu_format(sups)
+    rc2, sort = F.emu_format_sort(sups)
+    assert rc == 0 and rc2 == 0
+    for f in ("mqcd", "rpcd", "bqcd"):
+        assert scan[f].tobytes() == sort[f].tobytes(), f
+    errs = F.compare_format(scan, sort)
+    assert not errs, "\n".join(errs[:20])
+    sg, want, _ = F.load_golden()
+    errs = F.compare_format(want, F.emu_format_sort(sg)[1])
+    assert not errs, "\n".join(errs[:20])
