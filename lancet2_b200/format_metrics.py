@@ -6,6 +6,7 @@ constructor raises when the CUDA library or a device is missing."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Sequence, Tuple
 
 import numpy as np
@@ -15,13 +16,26 @@ from . import abi
 
 class GpuFormatMetrics:
     def __init__(self, device: int = 0):
-        self._lib = abi.load_library()
+        self._main = abi.load_library()
+        self._lib = self._main
+        # A/B builds of the same four entry points (e.g. csrc/liblgr_format_sort.so, the -DLGR_FMT_SORT kernels)
+        variant = os.environ.get("LGR_FORMAT_LIBRARY")
+        if variant:
+            self._lib = C.CDLL(variant)
+            self._lib.lgr_format_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+            self._lib.lgr_format_create.restype = C.c_int
+            self._lib.lgr_format_destroy.argtypes = [C.c_void_p]
+            self._lib.lgr_format_destroy.restype = None
+            self._lib.lgr_format_last_error.argtypes = [C.c_void_p]
+            self._lib.lgr_format_last_error.restype = C.c_char_p
+            self._lib.lgr_format_metrics.argtypes = [C.c_void_p, C.POINTER(abi.LgrEvidenceIn), C.c_void_p, C.POINTER(C.c_float)]
+            self._lib.lgr_format_metrics.restype = C.c_int
         self._ctx = C.c_void_p()
         rc = self._lib.lgr_format_create(device, C.byref(self._ctx))
         if rc != 0:
             msg = self._lib.lgr_format_last_error(None).decode()
             self._ctx = C.c_void_p()
-            raise RuntimeError(f"lgr_format_create failed ({self._lib.lgr_strerror(rc).decode()}): {msg}")
+            raise RuntimeError(f"lgr_format_create failed ({self._main.lgr_strerror(rc).decode()}): {msg}")
 
     def close(self) -> None:
         if getattr(self, "_ctx", None) and self._ctx.value:
@@ -43,6 +57,6 @@ class GpuFormatMetrics:
         ms = C.c_float(0.0)
         rc = self._lib.lgr_format_metrics(self._ctx, C.byref(st), out.ctypes.data, C.byref(ms))
         if rc != 0:
-            raise RuntimeError(f"lgr_format_metrics failed ({self._lib.lgr_strerror(rc).decode()}): "
+            raise RuntimeError(f"lgr_format_metrics failed ({self._main.lgr_strerror(rc).decode()}): "
                                f"{self._lib.lgr_format_last_error(self._ctx).decode()}")
         return out, float(ms.value)
