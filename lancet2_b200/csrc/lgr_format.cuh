@@ -182,8 +182,8 @@ FMT_HD double alt_entropy(W& w, const Ev& e, int64_t b, int64_t n_end, long long
 
 #ifdef LGR_FMT_SORT
 // ---- sort instead of scan — compiled only with -DLGR_FMT_SORT: checked on the
-// CPU against the scan build and the reference, not yet run on a GPU, therefore not in the
-// default device build.  Supports of up to kSortCap records sort their keys in shared memory
+// CPU against the scan build and the reference, run on a GPU for one shape only, therefore not
+// yet the default device build.  Supports of up to kSortCap records sort their keys in shared memory
 // with a bitonic network (one `each` phase per stage: the compare-exchanges of a stage are
 // disjoint, so the host emulation may run them thread by thread); larger supports keep the scan.
 constexpr int kSortCap = 2048;
