@@ -137,3 +137,20 @@ def test_gpu_golden_edge_supports():
         fmt.close()
     errs = F.compare_format(want, got)
     assert not errs, "\n".join(errs[:20])
+
+
+@pytest.mark.gpu
+def test_gpu_more_supports_than_resident_ctas():
+    # beyond 32 CTAs per SM and task (4736 supports on a B200) k_fmt_metrics walks the supports in a grid-stride loop
+    from lancet2_b200.format_metrics import GpuFormatMetrics
+    rng = np.random.default_rng(321)
+    sups = [F.random_support(rng, n=int(rng.integers(0, 24))) for _ in range(6000)]
+    rc, want = F.emu_format(sups)
+    assert rc == 0
+    fmt = GpuFormatMetrics(0)
+    try:
+        got, _ = fmt.compute(sups)
+    finally:
+        fmt.close()
+    errs = F.compare_format(want, got)
+    assert not errs, "\n".join(errs[:20])
