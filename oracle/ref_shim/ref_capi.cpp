@@ -201,3 +201,19 @@ extern "C" int ref_support_metrics(int n, const long long* isize, const long lon
   for (std::size_t a = 0; a < lods.size() && a < LGR_FMT_MAX_ALLELES; ++a) out->cmlod[a] = lods[a];
   return 0;
 }
+
+// the same over a whole lgr_evidence_in (S supports) in one call — the CPU baseline of
+// tools/bench_format.py times this loop (the reference's own code, one thread).
+extern "C" int ref_support_metrics_batch(const lgr_evidence_in* in, lgr_format* out) {
+  for (int s = 0; s < in->n_supports; ++s) {
+    const long long b = in->sup_begin[s];
+    const int n = (int)(in->sup_begin[s + 1] - b);
+    const int rc = ref_support_metrics(n, (const long long*)in->insert_size + b, (const long long*)in->aln_start + b,
+                                       in->aln_score + b, in->folded_pos + b, in->rname_hash + b, in->ref_nm + b,
+                                       in->own_hap_nm + b, in->hap_id + b, in->allele + b, in->flags + b, in->base_qual + b,
+                                       in->map_qual + b, in->sup_n_alleles[s], in->sup_variant_len[s], in->sup_total_haps[s],
+                                       &out[s]);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}

@@ -94,6 +94,18 @@ def ref_format(supports):
     return out
 
 
+def ref_format_batch(batch):
+    """one call of the reference's VariantSupport over a whole EvidenceBatch (timing baseline)"""
+    ref_format([])  # loads the library
+    _ref.ref_support_metrics_batch.argtypes = [C.POINTER(abi.LgrEvidenceIn), C.c_void_p]
+    _ref.ref_support_metrics_batch.restype = C.c_int
+    out = np.zeros(batch.n_supports, dtype=abi.FORMAT_DTYPE)
+    st = batch.c_struct()
+    rc = _ref.ref_support_metrics_batch(C.byref(st), out.ctypes.data)
+    assert rc == 0
+    return out
+
+
 def random_support(rng, n=None, n_alleles=None, dup_frac=0.3):
     n = int(rng.integers(0, 80)) if n is None else n
     k = int(rng.integers(1, 5)) if n_alleles is None else n_alleles

@@ -3,7 +3,8 @@
 step produces (253 variants x 2 samples, ≈ 230 evidence records each, mates deduplicated) and on a
 deep-coverage shape (≈ 2000 records per support).  Prints one JSON line per shape: CUDA-event time of
 k_fmt_dedup + k_fmt_metrics, the wall time of the whole call from host buffers, and — on the
-box's host cores, one thread — the same arithmetic compiled by g++ (tests/hostemu, checker only)."""
+box's host cores, one thread — the same arithmetic compiled by g++ (tests/hostemu, checker only) and the
+reference's own VariantSupport (oracle/_ref, when it was built)."""
 import json
 import os
 import sys
@@ -39,12 +40,19 @@ def main():
         rc, want = F.emu_format(batch)
         cpu_ms = (time.perf_counter() - t0) * 1e3
         errs = F.compare_format(want, got)
+        ref_ms = None
+        if F.have_ref():  # the reference's own VariantSupport (oracle/_ref), one host thread
+            t0 = time.perf_counter()
+            ref_rec = F.ref_format_batch(batch)
+            ref_ms = (time.perf_counter() - t0) * 1e3
+            errs += F.compare_format(ref_rec, got, label="vs reference: ")
         bytes_in = sum(v.nbytes for v in batch.cols.values())
         print(json.dumps({"workload": name, "supports": n_sup, "evidence_records": batch.n_evidence,
                           "ms_kernels_median": float(np.median(ms_k)), "ms_call_median": float(np.median(wall)),
                           "supports_per_s_kernels": n_sup / (float(np.median(ms_k)) * 1e-3),
                           "h2d_bytes": int(bytes_in), "d2h_bytes": int(got.nbytes),
-                          "cpu_same_arithmetic_ms_1thread": cpu_ms, "mismatches_vs_host_build": len(errs)}))
+                          "cpu_same_arithmetic_ms_1thread": cpu_ms, "cpu_reference_ms_1thread": ref_ms,
+                          "mismatches_vs_host_build": len(errs)}))
 
 
 if __name__ == "__main__":
