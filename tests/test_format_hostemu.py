@@ -159,3 +159,14 @@ def test_sort_build_equals_scan_build():
     sg, want, _ = F.load_golden()
     errs = F.compare_format(want, F.emu_format_sort(sg)[1])
     assert not errs, "\n".join(errs[:20])
+
+
+def test_sort_variant_library_exports_the_same_entry_points():
+    import os
+    path = os.path.join(os.path.dirname(abi.LIB_PATH), "liblgr_format_sort.so")
+    if not os.path.exists(path):
+        pytest.skip("variant library not built")
+    lib = C.CDLL(path)
+    for sym in ("lgr_format_create", "lgr_format_destroy", "lgr_format_last_error", "lgr_format_metrics"):
+        getattr(lib, sym)
+    assert not hasattr(lib, "lgr_genotype_batch")   # only the FORMAT entry points live there
