@@ -170,3 +170,38 @@ def test_sort_variant_library_exports_the_same_entry_points():
     for sym in ("lgr_format_create", "lgr_format_destroy", "lgr_format_last_error", "lgr_format_metrics"):
         getattr(lib, sym)
     assert not hasattr(lib, "lgr_genotype_batch")   # only the FORMAT entry points live there
+
+
+def test_checker_is_not_vacuous():
+    # compare_format must flag a one-unit PL change, a flipped valid bit, a last-bit change of a Cohen's d and a 1e-6 drift of an entropy
+    sups, want, _ = F.load_golden()
+    for field, mutate in (("pl", lambda r: r["pl"].__setitem__(1, r["pl"][1] + 1)),
+                          ("valid", lambda r: r.__setitem__("valid", r["valid"] ^ 32)),
+                          ("rpcd", lambda r: r.__setitem__("rpcd", np.nextafter(r["rpcd"], 1.0))),
+                          ("fsse", lambda r: r.__setitem__("fsse", r["fsse"] + 1e-6)),
+                          ("fwd", lambda r: r["fwd"].__setitem__(0, r["fwd"][0] + 1))):
+        got = want.copy()
+        idx = next(i for i in range(len(got)) if got[i]["valid"] & abi.LGR_FMT_HAS["fsse"] and got[i]["rpcd"] != 0.0)
+        mutate(got[idx])
+        errs = F.compare_format(want, got)
+        assert errs and any(field in e for e in errs), field
+
+
+def test_permutation_invariance_without_duplicates():
+    """oracle-free property at a size no reference run is needed for: with unique read names the order of
+    a support's records only changes the association of the f64 sums — integers and the Mann-Whitney
+    statistics keep their bits, the rest stays within the tolerance"""
+    rng = np.random.default_rng(4)
+    n = 5000                                  # beyond the sort variant's cap, far beyond any golden support
+    sup = F.random_support(rng, n=n, n_alleles=3, dup_frac=0.0)
+    sup["rname_hash"] = np.arange(n, dtype=np.uint32)
+    perm = rng.permutation(n)
+    shuffled = {k: (np.asarray(v)[perm] if not np.isscalar(v) and len(np.shape(v)) == 1 else v) for k, v in sup.items()}
+    _, a = F.emu_format([sup])
+    _, b = F.emu_format([shuffled])
+    assert a[0]["n_kept"] == n
+    errs = F.compare_format(a, b)
+    assert not errs, "\n".join(errs)
+    _, c = F.emu_format_sort([shuffled])
+    errs = F.compare_format(a, c)
+    assert not errs, "\n".join(errs)
