@@ -76,8 +76,9 @@ def python_model(groups, batch, names, meta, want):
     return sups, keys
 
 
-def test_evidence_columns_match_add_to_table_model(lib):  # noqa: F811
-    groups, batch, names, meta, want = make_case()
+@pytest.mark.parametrize("seed", [23, 24, 25])
+def test_evidence_columns_match_add_to_table_model(lib, seed):  # noqa: F811
+    groups, batch, names, meta, want = make_case(seed)
     lib.lgr_adapter_evidence_columns.argtypes = [C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + [C.c_void_p] * 7 + \
         [C.c_void_p, C.c_int]
     lib.lgr_adapter_evidence_columns.restype = C.POINTER(abi.LgrEvidenceIn)
