@@ -19,6 +19,17 @@ from lancet2_b200 import abi  # noqa: E402
 from lancet2_b200.format_metrics import GpuFormatMetrics  # noqa: E402
 
 
+def reference_all_cores(sups, cores):
+    """the reference's VariantSupport over the supports, split over `cores` threads (ctypes drops the GIL)"""
+    from concurrent.futures import ThreadPoolExecutor
+    chunks = [abi.EvidenceBatch(sups[i::cores]) for i in range(cores) if sups[i::cores]]
+    F.ref_format_batch(chunks[0])  # warm
+    with ThreadPoolExecutor(len(chunks)) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(F.ref_format_batch, chunks))
+        return (time.perf_counter() - t0) * 1e3
+
+
 def main():
     fmt = GpuFormatMetrics(0)
     rng = np.random.default_rng(42)
@@ -40,18 +51,21 @@ def main():
         rc, want = F.emu_format(batch)
         cpu_ms = (time.perf_counter() - t0) * 1e3
         errs = F.compare_format(want, got)
-        ref_ms = None
-        if F.have_ref():  # the reference's own VariantSupport (oracle/_ref), one host thread
+        ref_ms = ref_all_ms = None
+        cores = os.cpu_count() or 1
+        if F.have_ref():  # the reference's own VariantSupport (oracle/_ref): one host thread, then all of them
             t0 = time.perf_counter()
             ref_rec = F.ref_format_batch(batch)
             ref_ms = (time.perf_counter() - t0) * 1e3
             errs += F.compare_format(ref_rec, got, label="vs reference: ")
+            ref_all_ms = reference_all_cores(sups, cores)
         bytes_in = sum(v.nbytes for v in batch.cols.values())
         print(json.dumps({"workload": name, "supports": n_sup, "evidence_records": batch.n_evidence,
                           "ms_kernels_median": float(np.median(ms_k)), "ms_call_median": float(np.median(wall)),
                           "supports_per_s_kernels": n_sup / (float(np.median(ms_k)) * 1e-3),
                           "h2d_bytes": int(bytes_in), "d2h_bytes": int(got.nbytes),
                           "cpu_same_arithmetic_ms_1thread": cpu_ms, "cpu_reference_ms_1thread": ref_ms,
+                          "cpu_reference_ms_all_cores": ref_all_ms, "cores": cores,
                           "mismatches_vs_host_build": len(errs)}))
 
 
