@@ -60,13 +60,26 @@ def main():
             errs += F.compare_format(ref_rec, got, label="vs reference: ")
             ref_all_ms = reference_all_cores(sups, cores)
         bytes_in = sum(v.nbytes for v in batch.cols.values())
+        # same roofline object as bench.py: algorithmic bytes of the call over the kernels' time against the measured
+        # HBM peak — it documents that the row is NOT HBM bound; `issue` is the bound that matters (profiles/r1_format_ncu.txt)
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback 6650 GB/s"
+        k_ms = float(np.median(ms_k))
+        achieved = (bytes_in + got.nbytes) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_fmt_dedup + k_fmt_metrics", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": 5.16e6 + 0.38e6 if name == "cfg2-step" else None, "peak_source": peak_src,
+                    "note": "issue bound: k_fmt_metrics runs at 0.58 of the measured INT issue peak on the cfg2-step shape "
+                            "(ncu, profiles/r1_format_ncu.txt); traffic = dram bytes of that capture"}
         print(json.dumps({"workload": name, "supports": n_sup, "evidence_records": batch.n_evidence,
                           "ms_kernels_median": float(np.median(ms_k)), "ms_call_median": float(np.median(wall)),
                           "supports_per_s_kernels": n_sup / (float(np.median(ms_k)) * 1e-3),
                           "h2d_bytes": int(bytes_in), "d2h_bytes": int(got.nbytes),
                           "cpu_same_arithmetic_ms_1thread": cpu_ms, "cpu_reference_ms_1thread": ref_ms,
                           "cpu_reference_ms_all_cores": ref_all_ms, "cores": cores,
-                          "mismatches_vs_host_build": len(errs)}))
+                          "mismatches_vs_host_build": len(errs), "roofline": roofline}))
 
 
 if __name__ == "__main__":
