@@ -263,8 +263,9 @@ void* lgr_stream(lgr_ctx* ctx);
  *   AlleleMismatchDelta, ComputeFSSE, ComputeAHDD, ComputeHSE  variant_support.cpp:265-291, variant_support.h:362-412
  *   ComputePLs / ComputeGQ                                     variant_support.cpp:294-310, genotype_likelihood.cpp:109-163
  *   ComputeContinuousMixtureLods                               variant_support.cpp:312-335, genotype_likelihood.cpp:165-205
- * Integer results (counts, PL, GQ) and the three Mann-Whitney effect sizes are exact; the other
- * f64 metrics are warp-tree sums with CUDA's libm (log10/log2/log/lgamma/pow), i.e. equal to the
+ * Counts and the three Mann-Whitney effect sizes are exact by construction (integer rank
+ * statistics); PL/GQ are rounded lgamma differences and equal the reference's in every test; the
+ * other f64 metrics are tree sums with CUDA's libm (log10/log2/log/lgamma/pow), i.e. equal to the
  * reference within 1e-9 relative (the reference's own tests use 1e-6, and its entropy sums run
  * in abseil's salted hash-map order, so it does not reproduce its own last bits either).
  * Own context (device buffers + stream), independent of lgr_ctx; a context is bound to one GPU
