@@ -205,3 +205,20 @@ def test_permutation_invariance_without_duplicates():
     _, c = F.emu_format_sort([shuffled])
     errs = F.compare_format(a, c)
     assert not errs, "\n".join(errs)
+
+
+@pytest.mark.skipif(not F.have_ref(), reason="oracle/_ref not built (needs the reference tree)")
+def test_fuzz_up_to_eight_alleles_against_live_reference():
+    rng = np.random.default_rng(2025)
+    sups = []
+    for _ in range(3000):
+        k, n = int(rng.integers(1, 9)), int(rng.integers(0, 200))
+        s = F.random_support(rng, n=n, n_alleles=k, dup_frac=float(rng.random() * 0.8))
+        if k > 1 and n:
+            s["allele"] = rng.integers(0, k, n)
+        s["total_haps"], s["variant_len"] = int(rng.integers(0, 70)), int(rng.integers(0, 400))
+        sups.append(s)
+    want = F.ref_format(sups)
+    for got in (F.emu_format(sups)[1], F.emu_format_sort(sups)[1]):   # scan build and sort build
+        errs = F.compare_format(want, got)
+        assert not errs, "\n".join(errs[:20])
