@@ -156,12 +156,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle_lib as O
+    olib, oflags = O.load_native_oracle()
     groups, desc = build_workload(args.workload, 42)
     cores = os.cpu_count() or 1
     prm = O.default_params()
     probe = abi.Batch(groups[:8])
     t0 = time.perf_counter()
-    O.oracle_genotype(probe, prm, n_threads=cores)
+    O.oracle_genotype(probe, prm, n_threads=cores, lib=olib)
     rate = probe.n_pairs / max(time.perf_counter() - t0, 1e-6)
     want_pairs = rate * 8.0  # ~8 s per step
     sel, acc = [], 0
@@ -172,10 +173,10 @@ def run_reference(args, rank, world):
             break
     batch = abi.Batch(sel)
     for _ in range(max(args.warmup, 1) if args.warmup > 0 else 0):
-        O.oracle_genotype(abi.Batch(sel[:max(1, len(sel) // 8)]), prm, n_threads=cores)
+        O.oracle_genotype(abi.Batch(sel[:max(1, len(sel) // 8)]), prm, n_threads=cores, lib=olib)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.oracle_genotype(batch, prm, n_threads=cores)
+        O.oracle_genotype(batch, prm, n_threads=cores, lib=olib)
     dt = time.perf_counter() - t0
     v = batch.n_pairs * args.steps / dt
     sample = f"first {len(sel)} of {len(groups)} groups ({batch.n_pairs} pairs) per step"
@@ -183,9 +184,47 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": desc, "note": "CPU restatement of the reference path (oracle port, not Lancet2/minimap2 binaries)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "flags": oflags, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_line(line)
+
+
+def adapter_meta(groups, batch):
+    """per-read metadata AddToTable needs (names, sample, start, insert size, flag, mapq), synthetic like the reads"""
+    rng = np.random.default_rng(1)
+    nr = batch.n_reads
+    names = [nm for g in groups for nm in g.names]
+    meta = {
+        "blob": b"\0".join(x.encode() for x in names) + b"\0",
+        "sample_id": np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32),
+        "start0": rng.integers(10_000, 20_000, nr).astype(np.int64),
+        "isize": rng.integers(-500, 500, nr).astype(np.int64),
+        "flag": (rng.integers(0, 2, nr) * 0x10 + 0x2).astype(np.uint16),
+        "mapq": np.full(nr, 60, dtype=np.uint8),
+        "softclip": np.zeros(nr, dtype=np.uint8),
+    }
+    return meta
+
+
+def run_adapter(lib, device, batch, meta, threads, window, rounds):
+    """The reference-shaped call: every group is one Genotype() payload handed to the C++
+    lancet_gpu::GenotypeBatcher by `threads` worker threads (Enqueue/Collect with `window` payloads in
+    flight per worker, the split ProcessWindow of SURVEY.md §8f #1); packing into the pinned slab, the
+    one host->device copy per device batch, all kernels, the device->host copy of the assignments and
+    AddToTable on the workers are all inside the timed region.  Returns (seconds, counters)."""
+    fn = lib.lgr_adapter_batcher_bench
+    fn.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + [C.c_void_p] * 6 + \
+        [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
+    fn.restype = C.c_int
+    bi = batch.c_struct()
+    ctr = np.zeros(20, dtype=np.uint64)
+    err = C.create_string_buffer(4096)
+    rc = fn(device, C.byref(bi), meta["blob"], b"normal\0tumor\0", meta["sample_id"].ctypes.data, meta["start0"].ctypes.data,
+            meta["isize"].ctypes.data, meta["flag"].ctypes.data, meta["mapq"].ctypes.data, meta["softclip"].ctypes.data,
+            threads, rounds, window, 1, ctr.ctypes.data, err, len(err))
+    if rc != 0:
+        raise SystemExit(f"adapter bench failed: {err.value.decode()}")
+    return float(ctr[4]) * 1e-9, ctr
 
 
 def main():
@@ -197,6 +236,9 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-inflight", type=int, default=3)
+    ap.add_argument("--adapter-threads", type=int, default=0, help="worker threads of the adapter arm (0 = min(16, host cores / ranks))")
+    ap.add_argument("--adapter-window", type=int, default=16, help="Genotype() payloads a worker keeps enqueued")
+    ap.add_argument("--min-step-ms", type=float, default=50.0, help="repeat the batch inside a step until a step carries this much device time")
     args = ap.parse_args()
     claim_stdout()
 
@@ -219,55 +261,57 @@ def main():
     from lancet2_b200.realign import GpuRealigner
     groups, desc = build_workload(args.workload, 42 + rank)
     batch = abi.Batch(groups)
-    pin_batch(batch, torch)
     gpu = GpuRealigner(local_rank)
+    packed = abi.PackedBatch(groups, gpu.lib)  # the wire format the adapter ships: 2-bit planes, one slab
+    packed.pin(torch)
     res = abi.Result(batch, 1 << 20)
     pin_result(res, torch)
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    warm = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ----
-    gpu.upload(batch)
-    for _ in range(max(args.warmup, 3)):
-        gpu.run_resident()
+    # ---- device-resident arm: the slab is in HBM, a pass = unpack + every kernel of the path ----
+    gpu.upload_packed(packed)
+    probe = [gpu.run_resident().ms_kernels for _ in range(warm)]
+    reps = max(1, int(np.ceil(args.min_step_ms / max(min(probe), 1e-3))))
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    ms_steps, ms_map, launches = [], [], 0
+    ms_steps, ms_map, ms_ext, launches = [], [], [], 0
     last = None
     wall0 = time.perf_counter()
     for _ in range(args.steps):
-        flush_buf.fill_(1)
-        torch.cuda.synchronize()
-        st = gpu.run_resident()
-        ms_steps.append(st.ms_kernels)
-        ms_map.append(st.ms_k_map)
-        launches += st.kernel_launches
-        last = st
+        acc = 0.0
+        for _ in range(reps):  # one step = `reps` passes over the batch, L2 flushed (untimed) before each
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            st = gpu.run_resident()
+            acc += st.ms_kernels
+            ms_map.append(st.ms_k_map)
+            ms_ext.append(st.ms_k_ext)
+            launches += st.kernel_launches
+            last = st
+        ms_steps.append(acc)
     barrier()
     wall_resident = time.perf_counter() - wall0
     dev_ms = sum(ms_steps)
 
-    # ---- end-to-end arm (C-ABI call, pinned host buffers, H2D + D2H inside every step) ----
-    # single context: one synchronous lgr_genotype_batch per step
+    # ---- C-ABI arms on the pre-packed slab (pinned): H2D + unpack + kernels + D2H per call ----
     for _ in range(2):
-        gpu.genotype_batch(batch, result=res, want_aln=False)
+        gpu.genotype_packed(packed, batch, result=res, want_aln=False)
     barrier()
     t0 = time.perf_counter()
     e2e_st = None
     for _ in range(args.steps):
-        _, e2e_st = gpu.genotype_batch(batch, result=res, want_aln=False)
+        _, e2e_st = gpu.genotype_packed(packed, batch, result=res, want_aln=False)
     barrier()
     e2e_single_s = time.perf_counter() - t0
-    # pipelined: the same per-step call through lgr_submit/lgr_wait with a few batches in flight on
-    # ONE context and ONE host thread: every step still carries its own H2D and D2H, but the
-    # copies of one step overlap the kernels of the previous one
     depth = max(1, min(args.e2e_inflight, abi.LGR_MAX_INFLIGHT))
-    e2e_s = e2e_single_s
+    capi_s = e2e_single_s
     if depth > 1:
         ress = [res]
         for _ in range(depth - 1):
@@ -281,7 +325,7 @@ def main():
             for i in range(n_steps):
                 if len(open_t) == depth:
                     stl = gpu.wait(open_t.pop(0))
-                t, _ = gpu.submit(batch, result=ress[i % depth], want_aln=False)
+                t, _ = gpu.submit_packed(packed, batch, result=ress[i % depth], want_aln=False)
                 open_t.append(t)
             for t in open_t:
                 stl = gpu.wait(t)
@@ -292,14 +336,23 @@ def main():
         t0 = time.perf_counter()
         e2e_st = pipeline(args.steps)
         barrier()
-        e2e_s = time.perf_counter() - t0
+        capi_s = time.perf_counter() - t0
+
+    # ---- adapter arm: the reference-shaped call (C++ GenotypeBatcher, worker threads, AddToTable) ----
+    cores = os.cpu_count() or 1
+    threads = args.adapter_threads or max(1, min(16, cores // max(1, world)))
+    meta = adapter_meta(groups, batch)
+    run_adapter(gpu.lib, local_rank, batch, meta, threads, args.adapter_window, max(2, min(warm, 4)))  # grows pinned staging
+    barrier()
+    adapter_s, actr = run_adapter(gpu.lib, local_rank, batch, meta, threads, args.adapter_window, args.steps)
+    barrier()
     clocks = sampler.stop()
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, e2e_single_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, capi_s, e2e_single_s, adapter_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, e2e_single_s = float(t[0]), float(t[1]), float(t[2])
+        dev_ms, capi_s, e2e_single_s, adapter_s = (float(x) for x in t)
         cnt = torch.tensor([batch.n_pairs], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         total_pairs = float(cnt[0])
@@ -307,8 +360,9 @@ def main():
         total_pairs = float(batch.n_pairs)
 
     if rank == 0:
-        value = total_pairs * args.steps / (dev_ms * 1e-3)
-        e2e_v = total_pairs * args.steps / e2e_s
+        value = total_pairs * args.steps * reps / (dev_ms * 1e-3)
+        capi_v = total_pairs * args.steps / capi_s
+        adapter_v = total_pairs * args.steps / adapter_s
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -318,60 +372,75 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         abytes = algorithmic_bytes(batch)
         map_ms = statistics.mean(ms_map)
+        ext_ms = statistics.mean(ms_ext)
         achieved = abytes / (map_ms * 1e-3) / 1e9
-        # per-launch DRAM traffic and warp-instruction count of the dominant kernel: static for a
-        # given build and workload, taken from the committed ncu capture (never measured under ncu here)
+        # per-launch DRAM traffic / warp-instruction count of the dominant kernel come from a committed ncu
+        # capture of THIS build (profiles/r2_ncu_static.json, written by tools/ncu_summary.py); they are
+        # constants of the build and workload, never measured under ncu inside a timed run, and are
+        # reported as null when no capture of the current kernels has been committed
         static = {}
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_ncu_static.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r2_ncu_static.json")) as fh:
                 static = json.load(fh)
         except OSError:
             pass
-        wl = static.get(args.workload, {}) if world == 1 or args.workload in static else {}
+        wl = static.get(args.workload, {})
         traffic = wl.get("dram_bytes_per_launch")
         issue = None
         if wl.get("warp_inst_per_launch") and static.get("int_issue_peak_warp_inst_per_s"):
             ach = wl["warp_inst_per_launch"] / (map_ms * 1e-3)
             issue = {"kernel": "k_chain_warp", "achieved": ach, "peak": static["int_issue_peak_warp_inst_per_s"], "unit": "warp-instr/s",
                      "frac": ach / static["int_issue_peak_warp_inst_per_s"],
-                     "source": "instruction count: " + wl.get("source", "ncu") + "; peak: " + static.get("int_issue_peak_source", "")}
+                     "source": "static: instruction count from " + wl.get("source", "ncu") + "; peak: " + static.get("int_issue_peak_source", "")}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "pairs_per_step_per_gpu": batch.n_pairs, "groups": batch.n_groups,
-                       "reads": batch.n_reads, "haplotypes": batch.n_haps, "variants": batch.n_vars,
-                       "l2": "flushed between timed steps (512 MiB write, untimed)", "timing": "CUDA events on the library stream"},
-            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(e2e_st.h2d_bytes), "d2h_bytes_per_step": int(e2e_st.d2h_bytes),
-                    "batches_in_flight": depth,
-                    "genotype_calls_per_s": e2e_v * batch.n_groups / max(1, batch.n_pairs),  # groups (= Genotype() payloads ~ windows) per second
-                    "synchronous_value": total_pairs * args.steps / e2e_single_s,
-                    "ms_h2d": e2e_st.ms_h2d, "ms_kernels": e2e_st.ms_kernels, "ms_d2h": e2e_st.ms_d2h,
-                    "note": "every step is one lgr_submit+lgr_wait of the whole batch from pinned host buffers (H2D + kernels + D2H per step, one host thread); batches_in_flight steps are outstanding so copies overlap kernels; synchronous_value is the same through lgr_genotype_batch, one call at a time"},
+            "config": {"workload": desc, "pairs_per_step_per_gpu": batch.n_pairs * reps, "passes_per_step": reps,
+                       "pairs_per_pass": batch.n_pairs, "groups": batch.n_groups, "reads": batch.n_reads,
+                       "haplotypes": batch.n_haps, "variants": batch.n_vars, "input": "packed wire format (2-bit base planes, quality dictionary planes), one slab",
+                       "l2": "flushed before every timed pass (512 MiB write, untimed)", "timing": "CUDA events on the library stream, summed over the passes of a step"},
+            "e2e": {"value": adapter_v, "unit": UNIT, "h2d_bytes_per_step": int(actr[17]) // max(1, args.steps),
+                    "d2h_bytes_per_step": int(actr[18]) // max(1, args.steps),
+                    "path": "lancet_gpu::GenotypeBatcher (C++ adapter with the reference's Genotype() call shape): one payload per group, worker threads Enqueue/Collect; packing from the caller's strings into the pinned slab, ONE H2D per device batch, all kernels, D2H of the assignments and AddToTable on the workers inside the timed region",
+                    "worker_threads": threads, "payloads_in_flight_per_worker": args.adapter_window, "host_cores": cores,
+                    "genotype_calls_per_s": adapter_v * batch.n_groups / max(1, batch.n_pairs),
+                    "device_batches_per_step": float(actr[0]) / max(1, args.steps), "max_payloads_in_one_batch": int(actr[3]),
+                    "payloads_rerun_alone": int(actr[19]),
+                    "thread_ms_per_step": {"pack_all_workers": float(actr[5]) * 1e-6 / args.steps, "submit_batcher": float(actr[6]) * 1e-6 / args.steps,
+                                           "wait_batcher": float(actr[7]) * 1e-6 / args.steps, "add_to_table_all_workers": float(actr[8]) * 1e-6 / args.steps,
+                                           "wall": adapter_s * 1e3 / args.steps},
+                    "l2_flushed": False,
+                    "capi": {"value": capi_v, "batches_in_flight": depth, "synchronous_value": total_pairs * args.steps / e2e_single_s,
+                             "h2d_bytes_per_step": int(e2e_st.h2d_bytes), "d2h_bytes_per_step": int(e2e_st.d2h_bytes),
+                             "ms_h2d_and_unpack": e2e_st.ms_h2d, "ms_kernels": e2e_st.ms_kernels, "ms_d2h": e2e_st.ms_d2h,
+                             "note": "the same slab, already packed and pinned, through lgr_submit_packed/lgr_wait (one step = one call: H2D + unpack + kernels + D2H); with batches in flight neighbouring steps fill each other's low-parallelism phases and L2 is not flushed, so this figure can exceed `value`"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_chain_warp", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "traffic": traffic, "traffic_source": ("static: " + wl.get("source", "")) if traffic else None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": map_ms,
-                         "note": "path is integer-issue / latency bound, not HBM bound (DESIGN.md §roofline); `issue` is the same kernel against the measured INT issue peak"},
+                         "note": "path is integer-issue / latency bound, not HBM bound (DESIGN.md §5); `issue` is the same kernel against the measured INT issue peak"},
             "issue": issue,
             "work": {"aligned_frac": last.n_aligned / max(1, last.n_pairs), "chain_evals_per_pair": last.chain_evals / max(1, last.n_pairs),
                      "anchors_per_pair": last.n_anchors / max(1, last.n_pairs), "dp_cells_per_pair": last.dp_cells / max(1, last.n_pairs),
                      "dp_cells_full_per_pair": last.dp_cells_full / max(1, last.n_pairs),
                      "gcups_computed": last.dp_cells / (last.ms_kernels * 1e-3) / 1e9,
                      "gcups_reference_rectangles": last.dp_cells_full / (last.ms_kernels * 1e-3) / 1e9,
+                     "gcups_ext_stage": last.dp_cells / (ext_ms * 1e-3) / 1e9,
                      "chain_gevals_per_s": last.chain_evals / (last.ms_kernels * 1e-3) / 1e9,
                      "ms_index": last.ms_k_index, "ms_sketch": last.ms_k_sketch, "ms_map": last.ms_k_map, "ms_ext": last.ms_k_ext,
                      "ms_assign": last.ms_k_assign, "wall_resident_s": wall_resident},
         }
         if not args.no_cpu_baseline and world == 1:
             import oracle_lib as O
-            cores = os.cpu_count() or 1
+            olib, oflags = O.load_native_oracle()
             prm = O.default_params()
-            probe = abi.Batch(groups[:8])
+            probe_b = abi.Batch(groups[:8])
             t0 = time.perf_counter()
-            O.oracle_genotype(probe, prm, n_threads=cores)
-            rate = probe.n_pairs / max(time.perf_counter() - t0, 1e-6)
+            O.oracle_genotype(probe_b, prm, n_threads=cores, lib=olib)
+            rate = probe_b.n_pairs / max(time.perf_counter() - t0, 1e-6)
             sel, acc = [], 0
             for g in groups:
                 sel.append(g)
@@ -382,10 +451,10 @@ def main():
             t0 = time.perf_counter()
             passes = 0
             while passes < 1 or time.perf_counter() - t0 < 10.0:
-                O.oracle_genotype(sb, prm, n_threads=cores)
+                O.oracle_genotype(sb, prm, n_threads=cores, lib=olib)
                 passes += 1
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": sb.n_pairs * passes / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": sb.n_pairs * passes / dt, "unit": UNIT, "cores": cores, "kind": "port", "flags": oflags,
                                     "sample": f"first {len(sel)} of {len(groups)} groups ({sb.n_pairs} pairs) x {passes} passes, {dt:.1f} s"}
         emit_line(line)
     if world > 1:

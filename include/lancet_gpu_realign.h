@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 1
+#define LGR_ABI_VERSION 2
 
 /* error codes */
 #define LGR_OK 0
@@ -51,6 +51,7 @@ extern "C" {
 #define LGR_E_CIGAR_OVERFLOW (-5) /* cigar overflow arena exhausted         */
 #define LGR_E_NOMEM (-6)
 #define LGR_E_BUSY (-7)           /* all LGR_MAX_INFLIGHT submission slots in use */
+#define LGR_E_PARTIAL (-8)        /* some groups failed, the others are complete: see lgr_batch_out::grp_status */
 
 /* compile-time caps of the device path (checked, never silently truncated) */
 #define LGR_MAX_READ_LEN 1024
@@ -176,6 +177,13 @@ typedef struct lgr_batch_out {
   int64_t cigar_arena_cap;
   int64_t cigar_arena_used;/* out */
   lgr_assign* assign;      /* [n_assign]                                 */
+  int32_t* grp_status;     /* [n_groups] or NULL.  Per group: LGR_OK or the LGR_E_* code that hit one of ITS pairs (the
+                              group's records are then undefined; every other group is complete and the call returns
+                              LGR_E_PARTIAL).  NULL: any failing group fails the call with that code.  mm_map itself never
+                              refuses an input (genotyper.cpp:387-393), so a host that wants the reference's behaviour
+                              passes this array and re-submits or reports only the offending Genotype() payloads. */
+  int32_t* grp_mid_occ;    /* [n_groups] or NULL: out, the mid_occ each group ran with (a worker latches the value of its
+                              first group, mm_mapopt_update at genotyper.cpp:263-266)                                   */
 } lgr_batch_out;
 
 /* per-batch device timing + work counters (filled by lgr_genotype_batch) */
@@ -232,12 +240,95 @@ int lgr_genotype_batch(lgr_ctx* ctx, const lgr_batch_in* in, lgr_batch_out* out,
 typedef int32_t lgr_ticket;
 int lgr_submit(lgr_ctx* ctx, const lgr_batch_in* in, lgr_batch_out* out, lgr_ticket* ticket);
 int lgr_wait(lgr_ctx* ctx, lgr_ticket ticket, lgr_stats* stats);
+/* Completion without polling: after lgr_set_notify, every later lgr_submit / lgr_submit_packed on this ctx ends with a
+ * host callback (cudaLaunchHostFunc) that runs fn(user, ticket) on a CUDA-owned thread once the batch's last copy is
+ * done; lgr_wait(ticket) then returns without blocking.  fn must not call into this library or CUDA.  NULL disables. */
+typedef void (*lgr_notify_fn)(void* user, lgr_ticket ticket);
+int lgr_set_notify(lgr_ctx* ctx, lgr_notify_fn fn, void* user);
+/* LGR_OK when a Genotype() payload whose longest haplotype / read have these lengths is inside the device path's static
+ * caps for `params` (NULL = defaults), else LGR_E_LIMIT — the check lgr_submit applies to a whole batch, exposed so that
+ * a host batching many payloads can refuse the one offender instead (no CUDA call, any thread). */
+int lgr_check_limits(const lgr_params* params, int32_t max_hap_len, int32_t max_read_len);
 
 /* Device-resident variant for kernel-only timing: upload once, run many times,
  * download when wanted.  `lgr_upload` keeps a device copy of `in` inside ctx. */
 int lgr_upload(lgr_ctx* ctx, const lgr_batch_in* in);
 int lgr_run_resident(lgr_ctx* ctx, lgr_stats* stats);
 int lgr_download(lgr_ctx* ctx, lgr_batch_out* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Packed wire format (north_star: "2-bit-packed SoA buffers ... through a thin C-ABI layer").
+ *
+ * lgr_batch_in above is the plain form (ASCII strings, 13 arrays, one host->device copy each).  A host
+ * that feeds the GPU from many worker threads packs every Genotype() payload ONCE, on the thread that
+ * owns it, straight into one pinned slab, and the whole batch crosses PCIe in ONE copy:
+ *
+ *   slab  := group record, group record, ...  [directory]           (records 16-byte aligned)
+ *   group record := lgr_group_rec_hdr | hap_len i32[P] | read_len u16[R] | name_hash u32[R]
+ *                   | var_start i32[V*P] | var_len i32[V*P] | var_allele i8[V*P]
+ *                   | hap planes | read planes | qualities | exceptions
+ *   planes: bases as two bit planes per 32-base chunk {u32 lo, u32 hi} (A,C,G,T = 0..3, the nt4 code of
+ *           minimap2's seq_nt4_table; every sequence starts a new chunk);
+ *   exceptions: positions whose code byte is not plain A/C/G/T (N and other IUPAC letters, U: the
+ *           minimap2 and Lancet2 code tables differ there, scoring_constants.h:48-74) as
+ *           {u32 pos | 1<<31 for read space} + {u8 code} — lossless for any input byte;
+ *   qualities: when the group uses at most 4 (16) distinct Phred values, 2 (4) bit planes per 32-base
+ *           chunk indexing a 16-entry dictionary in the record header (binned instruments), else raw bytes.
+ * Offsets, group/pair/assignment prefix sums and the work-item list are derived on the device
+ * (k_unpack_scan / k_unpack_group); nothing but the slab is copied.
+ *
+ * lgr_packed_group_bytes / lgr_pack_group are pure host functions (no CUDA call, any thread).
+ */
+typedef struct lgr_group_desc {    /* one Genotype() payload as the caller holds it */
+  int32_t n_haps, n_reads, n_vars;
+  int32_t mid_occ;                  /* > 0: the worker's latched mid_occ; <= 0: derive from this group's REF haplotype */
+  const uint8_t* const* hap_seq;    /* [n_haps] ASCII, hap 0 = REF haplotype   */
+  const int32_t* hap_len;           /* [n_haps]                                */
+  const uint8_t* const* read_seq;   /* [n_reads] ASCII                         */
+  const uint8_t* const* read_qual;  /* [n_reads] raw Phred, read_len entries   */
+  const int32_t* read_len;          /* [n_reads]                               */
+  const uint32_t* read_name_hash;   /* [n_reads] lgr_x31_hash(qname)           */
+  const int32_t* var_start;         /* [n_vars * n_haps] dense ExtractHapBounds table, variant-major */
+  const int32_t* var_len;
+  const int8_t* var_allele;
+} lgr_group_desc;
+
+typedef struct lgr_group_dir {     /* directory entry of one packed group (40 bytes) */
+  uint64_t rec_off;                 /* byte offset of the group record in the slab (multiple of 16) */
+  int32_t n_haps, n_reads, n_vars;
+  int32_t hap_bases, read_bases;    /* total bases of the group                */
+  int32_t mid_occ;
+  int32_t max_hap_len, max_read_len;
+} lgr_group_dir;
+
+typedef struct lgr_group_rec_hdr { /* first 64 bytes of a group record */
+  uint32_t magic;                   /* LGR_PACK_MAGIC */
+  uint32_t qual_bits;               /* 2, 4 or 8 */
+  uint32_t n_exc;
+  uint32_t rec_bytes;               /* size of the record (multiple of 16) */
+  uint8_t qual_lut[16];
+  uint32_t off_hap_len, off_read_len, off_name_hash, off_var, off_hap_planes, off_read_planes, off_qual, off_exc;
+} lgr_group_rec_hdr;
+#define LGR_PACK_MAGIC 0x3252474cu /* "LGR2" */
+
+typedef struct lgr_packed_in {
+  int32_t n_groups;
+  int32_t reserved;
+  const void* slab;                 /* host memory (pinned for an asynchronous copy) */
+  size_t slab_bytes;                /* bytes to copy                                 */
+  const lgr_group_dir* dir;         /* [n_groups]; inside [slab, slab + slab_bytes) => ONE copy, else a second small one */
+} lgr_packed_in;
+
+/* bytes lgr_pack_group will write for this payload (upper bound, multiple of 16); 0 on a bad descriptor */
+size_t lgr_packed_group_bytes(const lgr_group_desc* g);
+/* pack one payload into dst[0..cap); fills *dir except rec_off (the caller places the record).  LGR_E_LIMIT when a
+ * sequence exceeds LGR_MAX_READ_LEN / LGR_MAX_HAP_LEN, LGR_E_ARG on a bad descriptor or too small a buffer. */
+int lgr_pack_group(const lgr_group_desc* g, void* dst, size_t cap, lgr_group_dir* dir);
+/* the packed forms of lgr_genotype_batch / lgr_submit (same outputs, same tickets, same lgr_wait) */
+int lgr_genotype_packed(lgr_ctx* ctx, const lgr_packed_in* in, lgr_batch_out* out, lgr_stats* stats);
+int lgr_submit_packed(lgr_ctx* ctx, const lgr_packed_in* in, lgr_batch_out* out, lgr_ticket* ticket);
+/* kernel-only timing on a packed batch: copy + unpack once, then lgr_run_resident / lgr_download */
+int lgr_upload_packed(lgr_ctx* ctx, const lgr_packed_in* in);
 
 /* Page-locked host memory for batch buffers (cudaMallocHost / cudaFreeHost): with pinned `in`/`out`
  * buffers the copies of lgr_submit are truly asynchronous.  NULL when it cannot be had (the

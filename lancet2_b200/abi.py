@@ -17,6 +17,7 @@ LGR_CIGAR_INLINE = 8
 LGR_MAX_READ_LEN = 1024
 LGR_MAX_HAP_LEN = 65535
 LGR_MAX_INFLIGHT = 4
+LGR_E_LIMIT, LGR_E_PARTIAL = -4, -8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblancet_gpu_realign.so")
@@ -57,8 +58,44 @@ class LgrBatchOut(C.Structure):
         ("n_pairs", C.c_int64), ("n_assign", C.c_int64),
         ("aln", C.c_void_p), ("cigar_inline", C.c_void_p), ("cigar_arena", C.c_void_p),
         ("cigar_arena_cap", C.c_int64), ("cigar_arena_used", C.c_int64),
-        ("assign", C.c_void_p),
+        ("assign", C.c_void_p), ("grp_status", C.c_void_p), ("grp_mid_occ", C.c_void_p),
     ]
+
+
+class LgrGroupDesc(C.Structure):
+    _fields_ = [
+        ("n_haps", C.c_int32), ("n_reads", C.c_int32), ("n_vars", C.c_int32), ("mid_occ", C.c_int32),
+        ("hap_seq", C.c_void_p), ("hap_len", C.c_void_p),
+        ("read_seq", C.c_void_p), ("read_qual", C.c_void_p), ("read_len", C.c_void_p),
+        ("read_name_hash", C.c_void_p),
+        ("var_start", C.c_void_p), ("var_len", C.c_void_p), ("var_allele", C.c_void_p),
+    ]
+
+
+class LgrGroupDir(C.Structure):
+    _fields_ = [
+        ("rec_off", C.c_uint64), ("n_haps", C.c_int32), ("n_reads", C.c_int32), ("n_vars", C.c_int32),
+        ("hap_bases", C.c_int32), ("read_bases", C.c_int32), ("mid_occ", C.c_int32),
+        ("max_hap_len", C.c_int32), ("max_read_len", C.c_int32),
+    ]
+
+
+class LgrGroupRecHdr(C.Structure):
+    _fields_ = [
+        ("magic", C.c_uint32), ("qual_bits", C.c_uint32), ("n_exc", C.c_uint32), ("rec_bytes", C.c_uint32),
+        ("qual_lut", C.c_uint8 * 16),
+        ("off_hap_len", C.c_uint32), ("off_read_len", C.c_uint32), ("off_name_hash", C.c_uint32), ("off_var", C.c_uint32),
+        ("off_hap_planes", C.c_uint32), ("off_read_planes", C.c_uint32), ("off_qual", C.c_uint32), ("off_exc", C.c_uint32),
+    ]
+
+
+class LgrPackedIn(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("reserved", C.c_int32), ("slab", C.c_void_p), ("slab_bytes", C.c_size_t),
+                ("dir", C.c_void_p)]
+
+
+LGR_PACK_MAGIC = 0x3252474C
+assert C.sizeof(LgrGroupDir) == 40 and C.sizeof(LgrGroupRecHdr) == 64
 
 
 class LgrStats(C.Structure):
@@ -206,6 +243,9 @@ class Result:
         self.cigar_inline = np.zeros(max(batch.n_pairs, 1) * LGR_CIGAR_INLINE, dtype=np.uint32)
         self.cigar_arena = np.zeros(max(cigar_arena_ops, 1), dtype=np.uint32)
         self.assign = np.zeros(max(batch.n_assign, 1), dtype=ASSIGN_DTYPE)
+        self.grp_status = np.zeros(max(batch.n_groups, 1), dtype=np.int32)
+        self.grp_mid_occ = np.zeros(max(batch.n_groups, 1), dtype=np.int32)
+        self.want_grp_status = False
         self.n_pairs = batch.n_pairs
         self.n_assign = batch.n_assign
         self._s = LgrBatchOut()
@@ -219,6 +259,8 @@ class Result:
         s.cigar_arena_cap = self.cigar_arena.size
         s.cigar_arena_used = 0
         s.assign = self.assign.ctypes.data
+        s.grp_status = self.grp_status.ctypes.data if self.want_grp_status else None
+        s.grp_mid_occ = self.grp_mid_occ.ctypes.data
         return s
 
     def cigar(self, pair: int) -> List[int]:
@@ -235,6 +277,71 @@ class Result:
 
     def bytes_d2h(self) -> int:
         return self.n_pairs * (ALN_DTYPE.itemsize + 4 * LGR_CIGAR_INLINE) + self.n_assign * ASSIGN_DTYPE.itemsize
+
+
+class PackedBatch:
+    """The same groups in the packed wire format (include/lancet_gpu_realign.h): one slab of group
+    records followed by the directory, built with the library's own lgr_pack_group.  `pin(torch)`
+    moves the slab into page-locked memory."""
+
+    def __init__(self, groups: Sequence[Group], lib: Optional[C.CDLL] = None):
+        lib = lib or load_library()
+        self.n_groups = len(groups)
+        descs, keep, sizes = [], [], []
+        for g in groups:
+            P, R, V = len(g.haps), len(g.reads), len(g.variants)
+            d = LgrGroupDesc()
+            d.n_haps, d.n_reads, d.n_vars, d.mid_occ = P, R, V, int(g.mid_occ)
+            hap_ptrs = (C.c_char_p * max(P, 1))(*g.haps)
+            hap_len = np.asarray([len(h) for h in g.haps], dtype=np.int32)
+            read_ptrs = (C.c_char_p * max(R, 1))(*g.reads)
+            qual_ptrs = (C.c_char_p * max(R, 1))(*g.quals)
+            read_len = np.asarray([len(r) for r in g.reads], dtype=np.int32)
+            hashes = np.asarray([x31_hash(nm) for nm in g.names], dtype=np.uint32)
+            vs = np.asarray([x[0] for var in g.variants for x in var], dtype=np.int32)
+            vl = np.asarray([x[1] for var in g.variants for x in var], dtype=np.int32)
+            va = np.asarray([x[2] for var in g.variants for x in var], dtype=np.int8)
+            d.hap_seq, d.hap_len = C.cast(hap_ptrs, C.c_void_p), hap_len.ctypes.data
+            d.read_seq, d.read_qual = C.cast(read_ptrs, C.c_void_p), C.cast(qual_ptrs, C.c_void_p)
+            d.read_len, d.read_name_hash = read_len.ctypes.data, hashes.ctypes.data
+            d.var_start, d.var_len, d.var_allele = vs.ctypes.data, vl.ctypes.data, va.ctypes.data
+            keep.append((hap_ptrs, hap_len, read_ptrs, qual_ptrs, read_len, hashes, vs, vl, va))
+            n = lib.lgr_packed_group_bytes(C.byref(d))
+            if n == 0:
+                raise ValueError("lgr_packed_group_bytes rejected a group")
+            descs.append(d)
+            sizes.append(n)
+        rec_bytes = sum(sizes)
+        self.dir = (LgrGroupDir * max(self.n_groups, 1))()
+        total = rec_bytes + C.sizeof(LgrGroupDir) * self.n_groups
+        self.slab = np.zeros(max(total, 16), dtype=np.uint8)
+        off = 0
+        for i, (d, n) in enumerate(zip(descs, sizes)):
+            rc = lib.lgr_pack_group(C.byref(d), self.slab.ctypes.data + off, n, C.byref(self.dir[i]))
+            if rc != 0:
+                raise ValueError(f"lgr_pack_group failed with {rc}")
+            self.dir[i].rec_off = off
+            off += n
+        self.rec_bytes = rec_bytes
+        self.slab_bytes = total
+        self._place_dir()
+
+    def _place_dir(self):
+        if self.n_groups:
+            C.memmove(self.slab.ctypes.data + self.rec_bytes, C.addressof(self.dir), C.sizeof(LgrGroupDir) * self.n_groups)
+
+    def pin(self, torch):
+        t = torch.from_numpy(self.slab).pin_memory()
+        self._pinned = t
+        self.slab = t.numpy()
+
+    def c_struct(self) -> LgrPackedIn:
+        s = LgrPackedIn()
+        s.n_groups = self.n_groups
+        s.slab = self.slab.ctypes.data
+        s.slab_bytes = self.slab_bytes
+        s.dir = self.slab.ctypes.data + self.rec_bytes  # the directory copy inside the slab: ONE host->device copy
+        return s
 
 
 # ---- SURVEY.md §8f #2: VariantSupport aggregation + FORMAT math (lgr_format_*) ----
@@ -301,6 +408,7 @@ _SYMBOLS = [
     "lgr_pair_offsets", "lgr_create", "lgr_destroy", "lgr_hap_mid_occ", "lgr_genotype_batch",
     "lgr_upload", "lgr_run_resident", "lgr_download", "lgr_stream", "lgr_submit", "lgr_wait",
     "lgr_alloc_pinned", "lgr_free_pinned",
+    "lgr_set_notify", "lgr_check_limits", "lgr_packed_group_bytes", "lgr_pack_group", "lgr_genotype_packed", "lgr_submit_packed", "lgr_upload_packed",
     "lgr_format_create", "lgr_format_destroy", "lgr_format_last_error", "lgr_format_metrics",
 ]
 
@@ -350,6 +458,20 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.lgr_alloc_pinned.restype = C.c_void_p
     lib.lgr_free_pinned.argtypes = [C.c_void_p]
     lib.lgr_free_pinned.restype = None
+    lib.lgr_set_notify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lgr_set_notify.restype = C.c_int
+    lib.lgr_check_limits.argtypes = [C.POINTER(LgrParams), C.c_int32, C.c_int32]
+    lib.lgr_check_limits.restype = C.c_int
+    lib.lgr_packed_group_bytes.argtypes = [C.POINTER(LgrGroupDesc)]
+    lib.lgr_packed_group_bytes.restype = C.c_size_t
+    lib.lgr_pack_group.argtypes = [C.POINTER(LgrGroupDesc), C.c_void_p, C.c_size_t, C.POINTER(LgrGroupDir)]
+    lib.lgr_pack_group.restype = C.c_int
+    lib.lgr_genotype_packed.argtypes = [C.c_void_p, C.POINTER(LgrPackedIn), C.POINTER(LgrBatchOut), C.POINTER(LgrStats)]
+    lib.lgr_genotype_packed.restype = C.c_int
+    lib.lgr_submit_packed.argtypes = [C.c_void_p, C.POINTER(LgrPackedIn), C.POINTER(LgrBatchOut), C.POINTER(C.c_int32)]
+    lib.lgr_submit_packed.restype = C.c_int
+    lib.lgr_upload_packed.argtypes = [C.c_void_p, C.POINTER(LgrPackedIn)]
+    lib.lgr_upload_packed.restype = C.c_int
     lib.lgr_stream.argtypes = [C.c_void_p]
     lib.lgr_stream.restype = C.c_void_p
     lib.lgr_format_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]

@@ -390,10 +390,12 @@ LGR_HD int32_t hap_mid_occ(const uint64_t* idx, int n, float f, int32_t min_mid_
 // their 64-bit sort key.  minimap2's results depend on this (unstable) permutation
 // whenever keys tie and n > 64, so it is reproduced move for move.
 // ------------------------------------------------------------------------------------
+// The pending-range stack holds ranges of more than 64 elements that are pairwise disjoint, so
+// n <= 65535 (the 16-bit positions) never needs more than 65535 / 65 = 1008 entries.
 struct RadixScratch {     // per-lane, lives in local memory; only touched when n > 64
   uint16_t bb[256], be[256];
-  uint16_t st_beg[256], st_end[256];
-  uint8_t st_s[256];
+  uint16_t st_beg[1024], st_end[1024];
+  uint8_t st_s[1024];
 };
 
 template <typename Perm, typename KeyFn>

@@ -14,7 +14,7 @@ __constant__ double c_phred_err[256] = {
 // counters (int64 slots in device memory)
 enum Ctr {
   C_ITEM = 0, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
-  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_COUNT
+  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_OVFNEED, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
@@ -51,7 +51,17 @@ struct Dev {      // everything the kernels need, passed by value
   int32_t *idx_n, *hap_mid;     // [NH]
   uint16_t* bkt;                // [NH][kBuckets+1] start of every hash bucket (top hash bits) in the sorted table
   int bkt_shift;                // hash >> bkt_shift = bucket
-  int32_t* grp_mid;             // [G] in: >0 fixed, <=0 latch from first hap; out: effective
+  const int32_t* grp_mid_req;   // [G] requested: >0 fixed (the worker's latched value), <=0 derive from the REF haplotype
+  int32_t* grp_mid;             // [G] effective mid_occ (k_group_mid)
+  int32_t* grp_err;             // [G] ErrBits that hit a pair of the group (0 = complete)
+  // packed wire format (lgr_submit_packed): the slab as copied + its directory, and the per-group
+  // prefix sums k_unpack_scan derives from the directory ([G+1] each)
+  const uint8_t* slab;
+  const lgr_group_dir* dir;
+  int64_t *grp_hapbase, *grp_readbase, *grp_vh, *grp_pair, *grp_asg;
+  int32_t* grp_item;
+  int item_reads;               // reads per phase-A work item
+  int mid_occ_param;            // lgr_params::mid_occ
   uint64_t* mz_x;               // [read_off-indexed]
   uint32_t* mz_y;
   int32_t* mz_n;                // [NR]
@@ -91,12 +101,19 @@ struct Dev {      // everything the kernels need, passed by value
 #ifndef LGR_FIN_MINB
 #define LGR_FIN_MINB 8
 #endif
+// a device-path limit hit one pair: remember it for the batch and for the pair's group (the other
+// groups of the batch stay valid, lgr_batch_out::grp_status)
+__device__ __forceinline__ void flag_err(const Dev& D, int g, int bit) {
+  atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)bit);
+  if (g >= 0 && g < D.n_groups) atomicOr(&D.grp_err[g], bit);
+}
+
 __device__ __forceinline__ void write_invalid(AlnOut* o) {
   o->valid = 0, o->score = 0, o->rs = 0, o->re = 0, o->qs = 0, o->qe = 0, o->rev = 0, o->dp_score = 0, o->dp_max = 0;
   o->mlen = 0, o->blen = 0, o->n_ambi = 0, o->nm = 0, o->n_cigar = 0, o->cigar_off = -1, o->n_regs = 0;
 }
 
-__device__ __forceinline__ void store_final(const Dev& D, int64_t pair, const AlnOut& a, const uint32_t* cig, int nc) {
+__device__ __forceinline__ void store_final(const Dev& D, int g, int64_t pair, const AlnOut& a, const uint32_t* cig, int nc) {
   AlnOut o = a;
   if (nc <= LGR_CIGAR_INLINE) {
     o.cigar_off = -1;
@@ -105,7 +122,7 @@ __device__ __forceinline__ void store_final(const Dev& D, int64_t pair, const Al
   } else {
     const long long off = atomicAdd((unsigned long long*)&D.ctr[C_CIGARENA], (unsigned long long)nc);
     if (off + nc > D.cigar_arena_cap) {
-      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_ARENA);
+      flag_err(D, g, E_CIG_ARENA);
       o.cigar_off = -2, o.n_cigar = 0;
     } else {
       o.cigar_off = (int32_t)off;

@@ -38,7 +38,10 @@
 #include "../../include/lancet_gpu_realign.h"
 #include "lgr_core.cuh"
 
+#include "lgr_pack.h"
+
 #include "lgr_dev.cuh"
+#include "lgr_kernels_unpack.cuh"
 #include "lgr_kernels_index.cuh"
 #include "lgr_kernels_ext.cuh"
 #include "lgr_kernels_finish.cuh"
@@ -70,9 +73,11 @@ struct lgr_ctx {
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
       b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
-      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks;
+      b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks, b_grp_mid_req, b_grp_err, b_slab, b_dir_tab, b_grp_hapbase,
+      b_grp_readbase, b_grp_vh, b_grp_pair, b_grp_asg, b_grp_item;
   Dev D;
-  bool resident = false;
+  bool resident = false, packed = false;
+  int occ_cap = 0, warp_blocks_full = 0, ext_blocks_full = 0, fin_blocks_full = 0, overflow_passes = 0;
   int max_read_len = 0, max_hap_len = 0;
   int64_t hap_bytes = 0, read_bytes = 0;
   int ext_blocks = 0, fin_blocks = 0, warp_blocks = 0, warp_cap = 64;
@@ -85,6 +90,9 @@ struct lgr_ctx {
   bool slot_busy[LGR_MAX_INFLIGHT] = {};
   lgr_batch_out* slot_out[LGR_MAX_INFLIGHT] = {};
   int64_t slot_h2d[LGR_MAX_INFLIGHT] = {}, slot_d2h[LGR_MAX_INFLIGHT] = {};
+  lgr_notify_fn notify_fn = nullptr;
+  void* notify_user = nullptr;
+  struct Note { lgr_ctx* ctx; int ticket; } slot_note[LGR_MAX_INFLIGHT] = {};
   // host staging of helper arrays
   std::vector<int32_t> h_read_grp, h_hap_grp, h_item_hap, h_item_r0, h_item_n, h_grp_mid;
   std::vector<int64_t> h_pair_off, h_asg_off;
@@ -146,6 +154,7 @@ const char* lgr_strerror(int code) {
     case LGR_E_LIMIT: return "a sequence or intermediate exceeds a device-path cap";
     case LGR_E_CIGAR_OVERFLOW: return "cigar overflow arena exhausted";
     case LGR_E_NOMEM: return "out of device memory";
+    case LGR_E_PARTIAL: return "some groups hit a device-path cap (see grp_status); the others are complete";
     default: return "unknown error";
   }
 }
@@ -215,7 +224,7 @@ int lgr_create(int device_ordinal, const lgr_params* params, lgr_ctx** out) {
   cudaGetDeviceProperties(&prop, device_ordinal);
   c->sm_count = prop.multiProcessorCount;
   for (auto& e : c->ev) cudaEventCreate(&e);
-  if (cudaMallocHost((void**)&c->h_ctr, sizeof(long long) * (C_COUNT + 1)) != cudaSuccess) {
+  if (cudaMallocHost((void**)&c->h_ctr, sizeof(long long) * (C_COUNT + 4)) != cudaSuccess) {
     g_create_err = "cudaMallocHost failed";
     delete c;
     return LGR_E_CUDA;
@@ -251,7 +260,9 @@ void lgr_destroy(lgr_ctx* c) {
                     &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
                     &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
                     &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
-                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt};
+                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt, &c->b_grp_mid_req, &c->b_grp_err,
+                    &c->b_slab, &c->b_dir_tab, &c->b_grp_hapbase, &c->b_grp_readbase, &c->b_grp_vh, &c->b_grp_pair, &c->b_grp_asg,
+                    &c->b_grp_item};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& e : c->ev) cudaEventDestroy(e);
@@ -275,7 +286,8 @@ int lgr_debug_ext_hist(unsigned long long* out256, int reset) {
 
 void* lgr_alloc_pinned(size_t bytes) {
   void* p = nullptr;
-  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+  // portable: usable from every device of the process (one batcher per GPU shares this allocator)
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
     (void)cudaGetLastError();
     return nullptr;
   }
@@ -288,135 +300,126 @@ void lgr_free_pinned(void* p) {
 
 void* lgr_stream(lgr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
-static constexpr int kCapBig = 16384;    // anchors per lane in the overflow pass
-static constexpr int kBigWarps = 4 * 19; // warps of the overflow pass (workspace = 28 arrays * cap * 4 B per lane, pre-allocated)
+static constexpr int kBigLanesMax = 4 * 19 * 32;  // lanes of the overflow pass (one pair each)
+static constexpr int kBigCapMax = 65535;          // anchors per pair the chain workspace can index (16-bit positions)
 
-static int validate_batch(lgr_ctx* c, const lgr_batch_in* in) {
+// everything the buffer plan needs to know about a batch (from lgr_batch_in or from the packed directory)
+struct BatchSizes {
+  int G = 0, NH = 0, NR = 0, NV = 0;
+  int64_t hap_bytes = 0, read_bytes = 0, nvh = 0, n_pairs = 0, n_assign = 0, n_items = 0;
+  int item_reads = 1, max_read_len = 0, max_hap_len = 0;
+};
+
+// reads per warp work item: several reads of one haplotype amortise the item's fixed cost when the
+// batch fills the machine many times over; a small batch (one Genotype() call) is latency bound
+// instead and wants every pair on its own warp
+static int choose_item_reads(const lgr_ctx* c, int64_t pairs_total) {
+  const int64_t warps_resident = (int64_t)c->sm_count * 36;
+  return pairs_total >= 8 * warps_resident ? kWarpItemReads : (pairs_total >= 3 * warps_resident ? 2 : 1);
+}
+
+// static caps of the device path for one payload shape; NULL when inside them
+static const char* limit_message(const lgr_params& prm, int max_hap_len, int max_read_len) {
+  if (max_hap_len > LGR_MAX_HAP_LEN) return "haplotype longer than LGR_MAX_HAP_LEN";
+  if (max_read_len > LGR_MAX_READ_LEN) return "read longer than LGR_MAX_READ_LEN";
+  {  // the warp wavefront exchanges H/F as packed int16: bound |H| for the longest read
+    const int Lm = max_read_len, mm = std::max(prm.b, prm.sc_ambi);
+    const int64_t Tm = Lm + ((int64_t)(prm.a + mm) * Lm) / prm.e + 2;
+    if (prm.q + (int64_t)prm.e * (Tm + Lm) + (int64_t)(mm + prm.a) * Lm > 32000)
+      return "scores could leave the int16 range of the extension kernel for this read length / scoring";
+  }
+  // ksw2 band (w = 1.5*bw + 1) must never bind
+  if ((int64_t)max_hap_len + max_read_len >= (int64_t)(prm.bw * 1.5))
+    return "haplotype+read length reaches the ksw2 band; unsupported by the device path";
+  return nullptr;
+}
+
+static int check_limits(lgr_ctx* c, const BatchSizes& z) {
+  if (const char* m = limit_message(c->prm, z.max_hap_len, z.max_read_len)) { c->err = m; return LGR_E_LIMIT; }
+  if (z.n_pairs > (int64_t)1 << 30) { c->err = "more than 2^30 (read, haplotype) pairs in one batch"; return LGR_E_LIMIT; }
+  return LGR_OK;
+}
+
+static int validate_batch(lgr_ctx* c, const lgr_batch_in* in, BatchSizes* z) {
   auto bad = [&](const std::string& m, int code = LGR_E_ARG) { c->err = m; return code; };
   if (!in || in->n_groups < 0 || in->n_haps < 0 || in->n_reads < 0 || in->n_vars < 0) return bad("null or negative counts");
   if (in->n_groups > 0 && (!in->grp_hap_begin || !in->grp_read_begin || !in->grp_var_begin)) return bad("null group arrays");
+  z->G = in->n_groups, z->NH = in->n_haps, z->NR = in->n_reads, z->NV = in->n_vars;
   if (in->n_groups == 0) return LGR_OK;
   if (in->grp_hap_begin[0] != 0 || in->grp_read_begin[0] != 0 || in->grp_var_begin[0] != 0) return bad("group prefix arrays must start at 0");
   if (in->grp_hap_begin[in->n_groups] != in->n_haps || in->grp_read_begin[in->n_groups] != in->n_reads ||
       in->grp_var_begin[in->n_groups] != in->n_vars)
     return bad("group prefix arrays do not end at the totals");
-  c->max_read_len = 0, c->max_hap_len = 0;
+  if ((in->n_haps > 0 && (!in->hap_off || in->hap_off[0] != 0)) || (in->n_reads > 0 && (!in->read_off || in->read_off[0] != 0)) ||
+      (in->n_vars > 0 && (!in->var_hap_off || in->var_hap_off[0] != 0)))
+    return bad("hap_off / read_off / var_hap_off must start at 0");
   for (int g = 0; g < in->n_groups; ++g) {
     if (in->grp_hap_begin[g + 1] < in->grp_hap_begin[g] || in->grp_read_begin[g + 1] < in->grp_read_begin[g] ||
         in->grp_var_begin[g + 1] < in->grp_var_begin[g])
       return bad("group prefix arrays must be non-decreasing");
-    if (in->grp_read_begin[g + 1] > in->grp_read_begin[g] && in->grp_hap_begin[g + 1] == in->grp_hap_begin[g])
-      return bad("a group with reads needs at least the REF haplotype");
+    const int P = in->grp_hap_begin[g + 1] - in->grp_hap_begin[g];
+    const int R = in->grp_read_begin[g + 1] - in->grp_read_begin[g];
+    if (R > 0 && P == 0) return bad("a group with reads needs at least the REF haplotype");
+    // k_assign reads var_*[var_hap_off[v] + h] for h < P: every variant owns exactly P entries
+    for (int v = in->grp_var_begin[g]; v < in->grp_var_begin[g + 1]; ++v)
+      if (in->var_hap_off[v + 1] - in->var_hap_off[v] != P) return bad("every variant needs one bounds entry per haplotype of its group");
+    z->n_pairs += (int64_t)R * P;
+    z->n_assign += (int64_t)R * (in->grp_var_begin[g + 1] - in->grp_var_begin[g]);
   }
   for (int h = 0; h < in->n_haps; ++h) {
     const int64_t l = in->hap_off[h + 1] - in->hap_off[h];
     if (l < 0) return bad("hap_off must be non-decreasing");
     if (l > LGR_MAX_HAP_LEN) return bad("haplotype longer than LGR_MAX_HAP_LEN", LGR_E_LIMIT);
-    c->max_hap_len = std::max<int>(c->max_hap_len, (int)l);
+    z->max_hap_len = std::max<int>(z->max_hap_len, (int)l);
   }
   for (int r = 0; r < in->n_reads; ++r) {
     const int64_t l = in->read_off[r + 1] - in->read_off[r];
     if (l < 0) return bad("read_off must be non-decreasing");
     if (l > LGR_MAX_READ_LEN) return bad("read longer than LGR_MAX_READ_LEN", LGR_E_LIMIT);
-    c->max_read_len = std::max<int>(c->max_read_len, (int)l);
+    z->max_read_len = std::max<int>(z->max_read_len, (int)l);
   }
-  {  // the warp wavefront exchanges H/F as packed int16: bound |H| for the longest read
-    const int Lm = c->max_read_len, mm = std::max(c->prm.b, c->prm.sc_ambi);
-    const int64_t Tm = Lm + ((int64_t)(c->prm.a + mm) * Lm) / c->prm.e + 2;
-    if (c->prm.q + (int64_t)c->prm.e * (Tm + Lm) + (int64_t)(mm + c->prm.a) * Lm > 32000)
-      return bad("scores could leave the int16 range of the extension kernel for this read length / scoring", LGR_E_LIMIT);
+  z->hap_bytes = in->n_haps ? in->hap_off[in->n_haps] : 0;
+  z->read_bytes = in->n_reads ? in->read_off[in->n_reads] : 0;
+  z->nvh = in->n_vars ? in->var_hap_off[in->n_vars] : 0;
+  for (int64_t x = 0; x < z->nvh; ++x)
+    if (in->var_allele[x] < -1) return bad("var_allele must be -1 (absent) or an allele index");
+  z->item_reads = choose_item_reads(c, z->n_pairs);
+  for (int g = 0; g < in->n_groups; ++g) {
+    const int64_t P = in->grp_hap_begin[g + 1] - in->grp_hap_begin[g], R = in->grp_read_begin[g + 1] - in->grp_read_begin[g];
+    z->n_items += P * ((R + z->item_reads - 1) / z->item_reads);
   }
-  // ksw2 band (w = 1.5*bw + 1) must never bind
-  if ((int64_t)c->max_hap_len + c->max_read_len >= (int64_t)(c->prm.bw * 1.5))
-    return bad("haplotype+read length reaches the ksw2 band; unsupported by the device path", LGR_E_LIMIT);
-  for (int v = 0; v < in->n_vars; ++v)
-    if (in->var_hap_off[v + 1] < in->var_hap_off[v]) return bad("var_hap_off must be non-decreasing");
-  return LGR_OK;
+  return check_limits(c, *z);
 }
 
-#define UP(buf, src, bytes)                                                                              \
-  do {                                                                                                   \
-    if ((rc = ensure(c, c->buf, (bytes))) != LGR_OK) return rc;                                          \
-    if ((bytes) > 0) LGR_CUDA(c, cudaMemcpyAsync(c->buf.p, (src), (bytes), cudaMemcpyHostToDevice, c->stream)); \
-    h2d += (bytes);                                                                                      \
-  } while (0)
-
-static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
-  int rc = validate_batch(c, in);
-  if (rc != LGR_OK) return rc;
+// device buffers + the Dev descriptor for a batch of these sizes (grow-only; no copies here)
+static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
+  int rc;
   LGR_CUDA(c, cudaSetDevice(c->device));
-  int64_t h2d = 0;
-  const int G = in->n_groups, NH = in->n_haps, NR = in->n_reads, NV = in->n_vars;
-  // host helper arrays
-  c->h_read_grp.resize(NR + 1), c->h_hap_grp.resize(NH + 1), c->h_pair_off.resize(NR + 1), c->h_asg_off.resize(NR + 1);
-  c->h_grp_mid.resize(G + 1);
-  c->h_item_hap.clear(), c->h_item_r0.clear(), c->h_item_n.clear();
-  int64_t po = 0, ao = 0;
-  // reads per warp work item: several reads of one haplotype amortise the item's fixed cost when
-  // the batch fills the machine many times over; a small batch (one Genotype() call) is latency
-  // bound instead and wants every pair on its own warp
-  int64_t pairs_total = 0;
-  for (int g = 0; g < G; ++g)
-    pairs_total += (int64_t)(in->grp_read_begin[g + 1] - in->grp_read_begin[g]) * (in->grp_hap_begin[g + 1] - in->grp_hap_begin[g]);
-  const int64_t warps_resident = (int64_t)c->sm_count * 36;
-  const int item_reads = pairs_total >= 8 * warps_resident ? kWarpItemReads : (pairs_total >= 3 * warps_resident ? 2 : 1);
-  for (int g = 0; g < G; ++g) {
-    const int h0 = in->grp_hap_begin[g], h1 = in->grp_hap_begin[g + 1];
-    const int r0 = in->grp_read_begin[g], r1 = in->grp_read_begin[g + 1];
-    const int V = in->grp_var_begin[g + 1] - in->grp_var_begin[g];
-    for (int h = h0; h < h1; ++h) c->h_hap_grp[h] = g;
-    for (int r = r0; r < r1; ++r) {
-      c->h_read_grp[r] = g, c->h_pair_off[r] = po, c->h_asg_off[r] = ao;
-      po += h1 - h0, ao += V;
-    }
-    for (int h = h0; h < h1; ++h)
-      for (int r = r0; r < r1; r += item_reads) {
-        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(item_reads, r1 - r));
-      }
-    int32_t mid = c->prm.mid_occ;
-    if (in->grp_mid_occ && in->grp_mid_occ[g] > 0) mid = in->grp_mid_occ[g];
-    c->h_grp_mid[g] = mid;
-  }
-  c->h_pair_off[NR] = po, c->h_asg_off[NR] = ao;
-  if (po > (int64_t)1 << 30) { c->err = "more than 2^30 (read, haplotype) pairs in one batch"; return LGR_E_LIMIT; }
-  const int64_t hap_bytes = NH ? in->hap_off[NH] : 0, read_bytes = NR ? in->read_off[NR] : 0;
-  const int64_t nvh = NV ? in->var_hap_off[NV] : 0;
+  const int G = z.G, NH = z.NH, NR = z.NR, NV = z.NV;
+  const int64_t hap_bytes = z.hap_bytes, read_bytes = z.read_bytes, nvh = z.nvh, n_pairs = z.n_pairs, n_assign = z.n_assign;
+  c->max_read_len = z.max_read_len, c->max_hap_len = z.max_hap_len;
   c->hap_bytes = hap_bytes, c->read_bytes = read_bytes;
-  UP(b_grp_hap, in->grp_hap_begin, sizeof(int32_t) * (G + 1));
-  UP(b_grp_read, in->grp_read_begin, sizeof(int32_t) * (G + 1));
-  UP(b_grp_var, in->grp_var_begin, sizeof(int32_t) * (G + 1));
-  UP(b_hap_off, in->hap_off, sizeof(int64_t) * (NH + 1));
-  UP(b_read_off, in->read_off, sizeof(int64_t) * (NR + 1));
-  UP(b_var_hap_off, in->var_hap_off, sizeof(int64_t) * (NV + 1));
-  UP(b_hap_bases, in->hap_bases, (size_t)hap_bytes);
-  UP(b_read_bases, in->read_bases, (size_t)read_bytes);
-  UP(b_read_quals, in->read_quals, (size_t)read_bytes);
-  UP(b_name_hash, in->read_name_hash, sizeof(uint32_t) * NR);
-  UP(b_var_start, in->var_start, sizeof(int32_t) * nvh);
-  UP(b_var_len, in->var_len, sizeof(int32_t) * nvh);
-  UP(b_var_allele, in->var_allele, (size_t)nvh);
-  UP(b_read_grp, c->h_read_grp.data(), sizeof(int32_t) * NR);
-  UP(b_hap_grp, c->h_hap_grp.data(), sizeof(int32_t) * NH);
-  UP(b_pair_off, c->h_pair_off.data(), sizeof(int64_t) * (NR + 1));
-  UP(b_asg_off, c->h_asg_off.data(), sizeof(int64_t) * (NR + 1));
-  UP(b_item_hap, c->h_item_hap.data(), sizeof(int32_t) * c->h_item_hap.size());
-  UP(b_item_r0, c->h_item_r0.data(), sizeof(int32_t) * c->h_item_r0.size());
-  UP(b_item_n, c->h_item_n.data(), sizeof(int32_t) * c->h_item_n.size());
-  UP(b_grp_mid, c->h_grp_mid.data(), sizeof(int32_t) * G);
-  // derived / scratch / outputs
-  const int64_t n_pairs = po, n_assign = ao;
-  if ((rc = ensure(c, c->b_hap_codes, hap_bytes)) || (rc = ensure(c, c->b_read_codes, read_bytes)) ||
-      (rc = ensure(c, c->b_idx, sizeof(uint64_t) * hap_bytes)) || (rc = ensure(c, c->b_idx_n, sizeof(int32_t) * NH)) ||
-      (rc = ensure(c, c->b_hap_mid, sizeof(int32_t) * NH)) || (rc = ensure(c, c->b_bkt, sizeof(uint16_t) * (size_t)NH * (kBuckets + 1))) || (rc = ensure(c, c->b_mz_x, sizeof(uint64_t) * read_bytes)) ||
-      (rc = ensure(c, c->b_mz_y, sizeof(uint32_t) * read_bytes)) || (rc = ensure(c, c->b_mz_n, sizeof(int32_t) * NR)) || (rc = ensure(c, c->b_mz_cnt, sizeof(uint64_t) * 2 * (size_t)NR)))
-    return rc;
+#define ENS(buf, bytes) if ((rc = ensure(c, c->buf, (size_t)(bytes))) != LGR_OK) return rc
+  ENS(b_grp_hap, sizeof(int32_t) * (G + 1)); ENS(b_grp_read, sizeof(int32_t) * (G + 1)); ENS(b_grp_var, sizeof(int32_t) * (G + 1));
+  ENS(b_hap_off, sizeof(int64_t) * (NH + 1)); ENS(b_read_off, sizeof(int64_t) * (NR + 1)); ENS(b_var_hap_off, sizeof(int64_t) * (NV + 1));
+  ENS(b_read_quals, read_bytes); ENS(b_name_hash, sizeof(uint32_t) * NR);
+  ENS(b_var_start, sizeof(int32_t) * nvh); ENS(b_var_len, sizeof(int32_t) * nvh); ENS(b_var_allele, nvh);
+  ENS(b_read_grp, sizeof(int32_t) * NR); ENS(b_hap_grp, sizeof(int32_t) * NH);
+  ENS(b_pair_off, sizeof(int64_t) * (NR + 1)); ENS(b_asg_off, sizeof(int64_t) * (NR + 1));
+  ENS(b_item_hap, sizeof(int32_t) * z.n_items); ENS(b_item_r0, sizeof(int32_t) * z.n_items); ENS(b_item_n, sizeof(int32_t) * z.n_items);
+  ENS(b_grp_mid_req, sizeof(int32_t) * G); ENS(b_grp_mid, sizeof(int32_t) * G); ENS(b_grp_err, sizeof(int32_t) * (G + 1));
+  ENS(b_hap_codes, hap_bytes); ENS(b_read_codes, read_bytes);
+  ENS(b_idx, sizeof(uint64_t) * hap_bytes); ENS(b_idx_n, sizeof(int32_t) * NH); ENS(b_hap_mid, sizeof(int32_t) * NH);
+  ENS(b_bkt, sizeof(uint16_t) * (size_t)NH * (kBuckets + 1));
+  ENS(b_mz_x, sizeof(uint64_t) * read_bytes); ENS(b_mz_y, sizeof(uint32_t) * read_bytes); ENS(b_mz_n, sizeof(int32_t) * NR);
+  ENS(b_mz_cnt, sizeof(uint64_t) * 2 * (size_t)NR);
   const int fin_cap = 2 * c->max_read_len + 16;
   const int Lm = std::max(c->max_read_len, 1);
   const int Tmax = Lm + ((c->prm.a + std::max(c->prm.b, c->prm.sc_ambi)) * Lm) / c->prm.e + 2;
   // warp-per-pair kernel: CAP anchors per pair in shared memory
   c->warp_cap = c->max_read_len <= 160 ? 64 : 128;
   c->warp_smem = (size_t)kWarpsPerCta * Ws<1>::elems(c->warp_cap, kRegCap) * sizeof(int32_t);
-  {
+  if (c->occ_cap != c->warp_cap) {  // occupancy of the three persistent kernels: once per context and shape
     int per_sm = 0;
     cudaError_t e1, e2;
     if (c->warp_cap == 64) {
@@ -432,15 +435,17 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
       c->err = "k_chain_warp does not fit on this device (shared memory / registers)";
       return LGR_E_CUDA;
     }
-    c->warp_blocks = c->sm_count * per_sm;
-  }
-  {
-    int per_sm = 0;
+    c->warp_blocks_full = c->sm_count * per_sm;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    c->ext_blocks = c->sm_count * per_sm;
+    c->ext_blocks_full = c->sm_count * per_sm;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    c->fin_blocks = c->sm_count * per_sm;
+    c->fin_blocks_full = c->sm_count * per_sm;
+    c->occ_cap = c->warp_cap;
   }
+  // a small batch (one Genotype() call) needs neither the full grids nor their per-warp scratch
+  c->warp_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->warp_blocks_full, (z.n_items + kWarpsPerCta - 1) / kWarpsPerCta));
+  c->ext_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->ext_blocks_full, (n_pairs + 3) / 4));
+  c->fin_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->fin_blocks_full, (n_pairs + 4 * kFinChunk - 1) / (4 * kFinChunk)));
   const int64_t ext_warps = std::max<int64_t>((int64_t)std::max(c->ext_blocks, c->fin_blocks) * 4, (int64_t)c->warp_blocks * kWarpsPerCta);
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
@@ -448,39 +453,36 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024;
   const int64_t ext_arena_cap = 4 * n_pairs + (1 << 20);
   const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
-  if ((rc = ensure(c, c->b_wreg, sizeof(RegRec) * (size_t)ext_warps * c->warp_cap)) ||
-      (rc = ensure(c, c->b_rsx, sizeof(RadixScratch) * (size_t)ext_warps)) ||
-      (rc = ensure(c, c->b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap)) ||
-      (rc = ensure(c, c->b_regs, sizeof(RegRec) * (size_t)regs_cap)) || (rc = ensure(c, c->b_pair_reg, sizeof(PairReg) * (size_t)n_pairs)) ||
-      (rc = ensure(c, c->b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2)) ||
-      (rc = ensure(c, c->b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap)) ||
-      (rc = ensure(c, c->b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
-      (rc = ensure(c, c->b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32))) ||
-      (rc = ensure(c, c->b_dir, (size_t)ext_warps * dir_per_warp)) ||
-      (rc = ensure(c, c->b_bnd, sizeof(int32_t) * (size_t)ext_warps * bnd_per_warp)) ||
-      (rc = ensure(c, c->b_wcig, sizeof(uint32_t) * (size_t)ext_warps * wcig_cap)) ||
-      (rc = ensure(c, c->b_aln, sizeof(AlnOut) * (size_t)n_pairs)) ||
-      (rc = ensure(c, c->b_cig_inline, sizeof(uint32_t) * (size_t)n_pairs * LGR_CIGAR_INLINE)) ||
-      (rc = ensure(c, c->b_cig_arena, sizeof(uint32_t) * (size_t)cig_arena_cap)) ||
-      (rc = ensure(c, c->b_assign, sizeof(AssignOut) * (size_t)n_assign)) || (rc = ensure(c, c->b_ctr, sizeof(long long) * C_COUNT)) ||
-      (rc = ensure(c, c->b_ws_big, sizeof(int32_t) * (size_t)(kBigWarps * 32) * A_COUNT * kCapBig)))
-    return rc;
+  ENS(b_wreg, sizeof(RegRec) * (size_t)ext_warps * c->warp_cap);
+  ENS(b_rsx, sizeof(RadixScratch) * (size_t)ext_warps);
+  ENS(b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap);
+  ENS(b_regs, sizeof(RegRec) * (size_t)regs_cap); ENS(b_pair_reg, sizeof(PairReg) * (size_t)n_pairs);
+  ENS(b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2);
+  ENS(b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap);
+  ENS(b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32)); ENS(b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32));
+  ENS(b_dir, (size_t)ext_warps * dir_per_warp);
+  ENS(b_bnd, sizeof(int32_t) * (size_t)ext_warps * bnd_per_warp);
+  ENS(b_wcig, sizeof(uint32_t) * (size_t)ext_warps * wcig_cap);
+  ENS(b_aln, sizeof(AlnOut) * (size_t)n_pairs);
+  ENS(b_cig_inline, sizeof(uint32_t) * (size_t)n_pairs * LGR_CIGAR_INLINE);
+  ENS(b_cig_arena, sizeof(uint32_t) * (size_t)cig_arena_cap);
+  ENS(b_assign, sizeof(AssignOut) * (size_t)n_assign); ENS(b_ctr, sizeof(long long) * C_COUNT);
   Dev& D = c->D;
   std::memset(&D, 0, sizeof(D));
   D.P = c->P;
   D.n_groups = G, D.n_haps = NH, D.n_reads = NR, D.n_vars = NV, D.n_pairs = n_pairs, D.n_assign = n_assign;
   D.grp_hap_begin = (int32_t*)c->b_grp_hap.p, D.grp_read_begin = (int32_t*)c->b_grp_read.p, D.grp_var_begin = (int32_t*)c->b_grp_var.p;
   D.hap_off = (int64_t*)c->b_hap_off.p, D.read_off = (int64_t*)c->b_read_off.p, D.var_hap_off = (int64_t*)c->b_var_hap_off.p;
-  D.hap_bases = (uint8_t*)c->b_hap_bases.p, D.read_bases = (uint8_t*)c->b_read_bases.p, D.read_quals = (uint8_t*)c->b_read_quals.p;
+  D.read_quals = (uint8_t*)c->b_read_quals.p;
   D.name_hash = (uint32_t*)c->b_name_hash.p;
   D.var_start = (int32_t*)c->b_var_start.p, D.var_len = (int32_t*)c->b_var_len.p, D.var_allele = (int8_t*)c->b_var_allele.p;
   D.read_grp = (int32_t*)c->b_read_grp.p, D.hap_grp = (int32_t*)c->b_hap_grp.p;
   D.pair_off = (int64_t*)c->b_pair_off.p, D.asg_off = (int64_t*)c->b_asg_off.p;
   D.item_hap = (int32_t*)c->b_item_hap.p, D.item_r0 = (int32_t*)c->b_item_r0.p, D.item_n = (int32_t*)c->b_item_n.p;
-  D.n_items = (int)c->h_item_hap.size();
+  D.n_items = (int)z.n_items, D.item_reads = z.item_reads, D.mid_occ_param = c->prm.mid_occ;
   D.hap_codes = (uint8_t*)c->b_hap_codes.p, D.read_codes = (uint8_t*)c->b_read_codes.p;
   D.idx = (uint64_t*)c->b_idx.p, D.idx_n = (int32_t*)c->b_idx_n.p, D.hap_mid = (int32_t*)c->b_hap_mid.p;
-  D.grp_mid = (int32_t*)c->b_grp_mid.p;
+  D.grp_mid_req = (int32_t*)c->b_grp_mid_req.p, D.grp_mid = (int32_t*)c->b_grp_mid.p, D.grp_err = (int32_t*)c->b_grp_err.p;
   D.bkt = (uint16_t*)c->b_bkt.p;
   D.bkt_shift = 2 * c->prm.k > kBucketBits ? 2 * c->prm.k - kBucketBits : 0;
   D.mz_x = (uint64_t*)c->b_mz_x.p, D.mz_y = (uint32_t*)c->b_mz_y.p, D.mz_n = (int32_t*)c->b_mz_n.p;
@@ -500,9 +502,129 @@ static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
   D.cigar_arena_cap = cig_arena_cap;
   D.assign = (AssignOut*)c->b_assign.p;
   D.ctr = (long long*)c->b_ctr.p;
+  return LGR_OK;
+#undef ENS
+}
+
+#define UP(buf, src, bytes)                                                                              \
+  do {                                                                                                   \
+    if ((rc = ensure(c, c->buf, (bytes))) != LGR_OK) return rc;                                          \
+    if ((bytes) > 0) LGR_CUDA(c, cudaMemcpyAsync(c->buf.p, (src), (bytes), cudaMemcpyHostToDevice, c->stream)); \
+    h2d += (bytes);                                                                                      \
+  } while (0)
+
+// plain form: 13 caller arrays + the host-derived helper arrays, one copy each
+static int upload_impl(lgr_ctx* c, const lgr_batch_in* in, int64_t* h2d_bytes) {
+  BatchSizes z;
+  int rc = validate_batch(c, in, &z);
+  if (rc != LGR_OK) return rc;
+  if ((rc = plan_batch(c, z)) != LGR_OK) return rc;
+  int64_t h2d = 0;
+  const int G = z.G, NH = z.NH, NR = z.NR, NV = z.NV;
+  c->h_read_grp.resize(NR + 1), c->h_hap_grp.resize(NH + 1), c->h_pair_off.resize(NR + 1), c->h_asg_off.resize(NR + 1);
+  c->h_grp_mid.resize(G + 1);
+  c->h_item_hap.clear(), c->h_item_r0.clear(), c->h_item_n.clear();
+  int64_t po = 0, ao = 0;
+  for (int g = 0; g < G; ++g) {
+    const int h0 = in->grp_hap_begin[g], h1 = in->grp_hap_begin[g + 1];
+    const int r0 = in->grp_read_begin[g], r1 = in->grp_read_begin[g + 1];
+    const int V = in->grp_var_begin[g + 1] - in->grp_var_begin[g];
+    for (int h = h0; h < h1; ++h) c->h_hap_grp[h] = g;
+    for (int r = r0; r < r1; ++r) {
+      c->h_read_grp[r] = g, c->h_pair_off[r] = po, c->h_asg_off[r] = ao;
+      po += h1 - h0, ao += V;
+    }
+    for (int h = h0; h < h1; ++h)
+      for (int r = r0; r < r1; r += z.item_reads) {
+        c->h_item_hap.push_back(h), c->h_item_r0.push_back(r), c->h_item_n.push_back(std::min(z.item_reads, r1 - r));
+      }
+    int32_t mid = c->prm.mid_occ;
+    if (in->grp_mid_occ && in->grp_mid_occ[g] > 0) mid = in->grp_mid_occ[g];
+    c->h_grp_mid[g] = mid;
+  }
+  c->h_pair_off[NR] = po, c->h_asg_off[NR] = ao;
+  UP(b_grp_hap, in->grp_hap_begin, sizeof(int32_t) * (G + 1));
+  UP(b_grp_read, in->grp_read_begin, sizeof(int32_t) * (G + 1));
+  UP(b_grp_var, in->grp_var_begin, sizeof(int32_t) * (G + 1));
+  UP(b_hap_off, in->hap_off, sizeof(int64_t) * (NH + 1));
+  UP(b_read_off, in->read_off, sizeof(int64_t) * (NR + 1));
+  UP(b_var_hap_off, in->var_hap_off, sizeof(int64_t) * (NV + 1));
+  UP(b_hap_bases, in->hap_bases, (size_t)z.hap_bytes);
+  UP(b_read_bases, in->read_bases, (size_t)z.read_bytes);
+  UP(b_read_quals, in->read_quals, (size_t)z.read_bytes);
+  UP(b_name_hash, in->read_name_hash, sizeof(uint32_t) * NR);
+  UP(b_var_start, in->var_start, sizeof(int32_t) * z.nvh);
+  UP(b_var_len, in->var_len, sizeof(int32_t) * z.nvh);
+  UP(b_var_allele, in->var_allele, (size_t)z.nvh);
+  UP(b_read_grp, c->h_read_grp.data(), sizeof(int32_t) * NR);
+  UP(b_hap_grp, c->h_hap_grp.data(), sizeof(int32_t) * NH);
+  UP(b_pair_off, c->h_pair_off.data(), sizeof(int64_t) * (NR + 1));
+  UP(b_asg_off, c->h_asg_off.data(), sizeof(int64_t) * (NR + 1));
+  UP(b_item_hap, c->h_item_hap.data(), sizeof(int32_t) * c->h_item_hap.size());
+  UP(b_item_r0, c->h_item_r0.data(), sizeof(int32_t) * c->h_item_r0.size());
+  UP(b_item_n, c->h_item_n.data(), sizeof(int32_t) * c->h_item_n.size());
+  UP(b_grp_mid_req, c->h_grp_mid.data(), sizeof(int32_t) * G);
+  c->D.hap_bases = (uint8_t*)c->b_hap_bases.p, c->D.read_bases = (uint8_t*)c->b_read_bases.p;
+  c->packed = false;
   c->resident = true;
   if (h2d_bytes) *h2d_bytes = h2d;
   return LGR_OK;
+}
+
+// packed form: the slab in one copy (plus the directory when it lives outside the slab); every
+// other array is derived on the device by k_unpack_scan / k_unpack_group (enqueued by run_launch)
+static int upload_packed_impl(lgr_ctx* c, const lgr_packed_in* in, int64_t* h2d_bytes) {
+  auto bad = [&](const std::string& m, int code = LGR_E_ARG) { c->err = m; return code; };
+  if (!in || in->n_groups < 0 || (in->n_groups > 0 && (!in->slab || !in->dir))) return bad("null packed batch");
+  BatchSizes z;
+  z.G = in->n_groups;
+  for (int g = 0; g < z.G; ++g) {
+    const lgr_group_dir& d = in->dir[g];
+    if (d.n_haps < 0 || d.n_reads < 0 || d.n_vars < 0 || d.hap_bases < 0 || d.read_bases < 0 || (d.n_reads > 0 && d.n_haps == 0))
+      return bad("bad group directory entry");
+    if ((d.rec_off & 15) || d.rec_off + sizeof(lgr_group_rec_hdr) > in->slab_bytes) return bad("group record outside the slab");
+    const lgr_group_rec_hdr* hdr = reinterpret_cast<const lgr_group_rec_hdr*>(static_cast<const uint8_t*>(in->slab) + d.rec_off);
+    if (hdr->magic != LGR_PACK_MAGIC || d.rec_off + hdr->rec_bytes > in->slab_bytes) return bad("group record corrupt or truncated");
+    if (hdr->qual_bits != 2 && hdr->qual_bits != 4 && hdr->qual_bits != 8) return bad("group record: bad qual_bits");
+    z.NH += d.n_haps, z.NR += d.n_reads, z.NV += d.n_vars;
+    z.hap_bytes += d.hap_bases, z.read_bytes += d.read_bases;
+    z.nvh += (int64_t)d.n_vars * d.n_haps, z.n_pairs += (int64_t)d.n_reads * d.n_haps, z.n_assign += (int64_t)d.n_reads * d.n_vars;
+    z.max_hap_len = std::max(z.max_hap_len, d.max_hap_len), z.max_read_len = std::max(z.max_read_len, d.max_read_len);
+    if (z.NH < 0 || z.NR < 0 || z.NV < 0) return bad("batch too large", LGR_E_LIMIT);
+  }
+  z.item_reads = choose_item_reads(c, z.n_pairs);
+  for (int g = 0; g < z.G; ++g)
+    z.n_items += (int64_t)in->dir[g].n_haps * ((in->dir[g].n_reads + z.item_reads - 1) / z.item_reads);
+  int rc = check_limits(c, z);
+  if (rc != LGR_OK) return rc;
+  if ((rc = plan_batch(c, z)) != LGR_OK) return rc;
+  int64_t h2d = 0;
+  const uint8_t* slab = static_cast<const uint8_t*>(in->slab);
+  const uint8_t* dirp = reinterpret_cast<const uint8_t*>(in->dir);
+  const size_t dir_bytes = sizeof(lgr_group_dir) * (size_t)z.G;
+  const bool dir_inside = z.G > 0 && dirp >= slab && dirp + dir_bytes <= slab + in->slab_bytes;
+  UP(b_slab, in->slab, in->slab_bytes);
+  if (!dir_inside) UP(b_dir_tab, in->dir, dir_bytes);
+#define ENS2(buf, bytes) if ((rc = ensure(c, c->buf, (size_t)(bytes))) != LGR_OK) return rc
+  ENS2(b_grp_hapbase, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_readbase, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_vh, sizeof(int64_t) * (z.G + 1));
+  ENS2(b_grp_pair, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_asg, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_item, sizeof(int32_t) * (z.G + 1));
+#undef ENS2
+  Dev& D = c->D;
+  D.slab = (const uint8_t*)c->b_slab.p;
+  D.dir = dir_inside ? reinterpret_cast<const lgr_group_dir*>(D.slab + (dirp - slab)) : (const lgr_group_dir*)c->b_dir_tab.p;
+  D.grp_hapbase = (int64_t*)c->b_grp_hapbase.p, D.grp_readbase = (int64_t*)c->b_grp_readbase.p, D.grp_vh = (int64_t*)c->b_grp_vh.p;
+  D.grp_pair = (int64_t*)c->b_grp_pair.p, D.grp_asg = (int64_t*)c->b_grp_asg.p, D.grp_item = (int32_t*)c->b_grp_item.p;
+  c->packed = true;
+  c->resident = true;
+  if (h2d_bytes) *h2d_bytes = h2d;
+  return LGR_OK;
+}
+
+// phase B (extensions, finish) + assignment, used by the main pass and the overflow pass
+static void launch_tail(lgr_ctx* c, const Dev& D, cudaStream_t s, int* launches) {
+  k_ext_warp<<<c->ext_blocks, 128, 0, s>>>(D);
+  k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D);
+  *launches += 2;
 }
 
 // enqueue one pass of the whole path on the context's streams; no host synchronisation
@@ -512,12 +634,15 @@ static int run_launch(lgr_ctx* c) {
   Dev& D = c->D;
   cudaStream_t s = c->stream;
   int launches = 0;
-  // the group mid_occ array is an in/out: restore the requested values before every run
-  if (D.n_groups > 0)
-    LGR_CUDA(c, cudaMemcpyAsync(D.grp_mid, c->h_grp_mid.data(), sizeof(int32_t) * D.n_groups, cudaMemcpyHostToDevice, s));
   LGR_CUDA(c, cudaMemsetAsync(D.ctr, 0, sizeof(long long) * C_COUNT, s));
+  LGR_CUDA(c, cudaMemsetAsync(D.grp_err, 0, sizeof(int32_t) * (D.n_groups + 1), s));
   cudaEventRecord(c->ev[0], s);
   const int64_t hb = c->hap_bytes, rb = c->read_bytes;
+  if (c->packed && D.n_groups > 0) {
+    k_unpack_scan<<<1, 1024, 0, s>>>(D);
+    k_unpack_group<<<std::min(D.n_groups, c->sm_count * 8), kUnpackThreads, 0, s>>>(D);
+    launches += 2;
+  }
   if (D.n_pairs > 0) {
     const int enc_blocks = c->sm_count * 8;
     // read side (encode + sketch) on the second stream, haplotype side (encode, sketch, sort,
@@ -525,17 +650,17 @@ static int run_launch(lgr_ctx* c) {
     cudaStream_t s2 = c->stream2;
     cudaEventRecord(c->ev_fork, s);
     cudaStreamWaitEvent(s2, c->ev_fork, 0);
-    k_encode<<<enc_blocks, 256, 0, s2>>>(D.read_bases, D.read_codes, rb);
+    if (!c->packed) k_encode<<<enc_blocks, 256, 0, s2>>>(D.read_bases, D.read_codes, rb), ++launches;
     k_read_sketch<<<(D.n_reads + 127) / 128, 128, 0, s2>>>(D);
     cudaEventRecord(c->ev_join, s2);
-    k_encode<<<enc_blocks, 256, 0, s>>>(D.hap_bases, D.hap_codes, hb);
+    if (!c->packed) k_encode<<<enc_blocks, 256, 0, s>>>(D.hap_bases, D.hap_codes, hb), ++launches;
     if (D.P.w == 5 && (D.P.k & 1) && 2 * D.P.k + 8 <= 32) k_hap_sketch_warp<uint32_t><<<(D.n_haps + 3) / 4, 128, 0, s>>>(D);
     else if (D.P.w == 5 && (D.P.k & 1)) k_hap_sketch_warp<uint64_t><<<(D.n_haps + 3) / 4, 128, 0, s>>>(D);
     else k_hap_sketch<<<(D.n_haps + 63) / 64, 64, 0, s>>>(D);
     k_hap_sort<<<D.n_haps, 128, 2048 * sizeof(uint64_t), s>>>(D, c->prm.mid_occ_frac, c->prm.min_mid_occ, c->prm.max_mid_occ);
     k_group_mid<<<(D.n_groups + 127) / 128, 128, 0, s>>>(D, c->prm.min_mid_occ);
     cudaStreamWaitEvent(s, c->ev_join, 0);
-    launches += 6;
+    launches += 4;
     cudaEventRecord(c->ev[1], s);
     k_read_filter<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
     launches += 1;
@@ -544,23 +669,14 @@ static int run_launch(lgr_ctx* c) {
     else k_chain_warp<128><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
     launches += 1;
     cudaEventRecord(c->ev[9], s);
-    {
-      // overflow pass (pairs whose seeds/anchors exceed the shared-memory cap): lane-per-pair over
-      // a large HBM workspace; exits immediately when the list is empty (no host round trip)
-      Dev D2 = D;
-      D2.ws = (int32_t*)c->b_ws_big.p, D2.ws_cap = kCapBig;
-      k_chain_overflow<<<kBigWarps / 4, 128, 0, s>>>(D2);
-      launches += 1;
-    }
-    k_ext_warp<<<c->ext_blocks, 128, 0, s>>>(D);
-    k_finish_warp<<<c->fin_blocks, 128, 0, s>>>(D);
-    launches += 2;
+    launch_tail(c, D, s, &launches);
     cudaEventRecord(c->ev[3], s);
     if (D.n_assign > 0) {
       k_assign<<<(unsigned)((D.n_assign + 127) / 128), 128, 0, s>>>(D);
       launches += 1;
     }
   } else {
+    if (D.n_groups > 0) k_group_mid<<<(D.n_groups + 127) / 128, 128, 0, s>>>(D, c->prm.min_mid_occ), ++launches;
     cudaEventRecord(c->ev[1], s), cudaEventRecord(c->ev[2], s), cudaEventRecord(c->ev[9], s), cudaEventRecord(c->ev[3], s);
   }
   cudaEventRecord(c->ev[4], s);
@@ -569,10 +685,58 @@ static int run_launch(lgr_ctx* c) {
   return LGR_OK;
 }
 
-// after the stream has drained: statistics and the device-side limit flags
+// Overflow pass, host driven, after the main pass has drained: the pairs whose seeds / anchors /
+// chains did not fit the shared-memory workspace of k_chain_warp (reads inside tandem repeats) were
+// listed, not refused.  Now their number and the largest anchor count among them are known, so the
+// HBM workspace is allocated to measure (nothing is reserved up front), k_chain_overflow maps them,
+// and extension / finish / assignment run again over what they added.  Rare: the price is one extra
+// host round trip for a batch that holds such a pair.
+static int overflow_pass(lgr_ctx* c) {
+  Dev& D = c->D;
+  cudaStream_t s = c->stream;
+  const long long n_ovf = std::min<long long>(c->h_ctr[C_NOVF], D.ovf_cap);
+  if (n_ovf <= 0) return LGR_OK;
+  long long need = std::max<long long>(c->h_ctr[C_OVFNEED], 256);
+  need = std::min<long long>((need + 255) / 256 * 256, kBigCapMax);
+  const int lanes = (int)std::min<long long>((n_ovf + 127) / 128 * 128, kBigLanesMax);
+  int rc = ensure(c, c->b_ws_big, sizeof(int32_t) * (size_t)lanes * A_COUNT * (size_t)need);
+  if (rc != LGR_OK) return rc;
+  Dev D2 = D;
+  D2.ws = (int32_t*)c->b_ws_big.p, D2.ws_cap = (int)need;
+  const long long n_task0 = std::min<long long>(c->h_ctr[C_NTASK], D.tasks_cap);
+  // restart the queues of phase B: extensions continue after the tasks already done, finish and
+  // assignment redo every pair (idempotent; the overflow cigar arena is refilled from 0)
+  long long* hc = c->h_ctr + C_COUNT + 2;  // pinned staging of the counter patch
+  hc[0] = n_task0;
+  LGR_CUDA(c, cudaMemcpyAsync(D.ctr + C_TASKPOS, hc, sizeof(long long), cudaMemcpyHostToDevice, s));
+  LGR_CUDA(c, cudaMemsetAsync(D.ctr + C_FINPOS, 0, sizeof(long long), s));
+  LGR_CUDA(c, cudaMemsetAsync(D.ctr + C_CIGARENA, 0, sizeof(long long), s));
+  LGR_CUDA(c, cudaMemsetAsync(D.ctr + C_ALIGNED, 0, sizeof(long long), s));
+  LGR_CUDA(c, cudaMemsetAsync(D.ctr + C_OVFPOS, 0, sizeof(long long), s));
+  int launches = 0;
+  k_chain_overflow<<<lanes / 128, 128, 0, s>>>(D2);
+  ++launches;
+  launch_tail(c, D, s, &launches);
+  if (D.n_assign > 0) {
+    k_assign<<<(unsigned)((D.n_assign + 127) / 128), 128, 0, s>>>(D);
+    ++launches;
+  }
+  LGR_CUDA(c, cudaMemcpyAsync(c->h_ctr, D.ctr, sizeof(long long) * C_COUNT, cudaMemcpyDeviceToHost, s));
+  LGR_CUDA(c, cudaStreamSynchronize(s));
+  c->launches += launches;
+  c->overflow_passes += 1;
+  return LGR_OK;
+}
+
+// after the stream has drained: overflow pass when needed, statistics, device-side limit flags
 static int run_finish(lgr_ctx* c, lgr_stats* st) {
   LGR_CUDA(c, cudaGetLastError());
   Dev& D = c->D;
+  if (c->h_ctr[C_NOVF] > 0) {
+    const int rc = overflow_pass(c);
+    if (rc != LGR_OK) return rc;
+    LGR_CUDA(c, cudaGetLastError());
+  }
   const long long* hctr = c->h_ctr;
   const int launches = c->launches;
   if (st) {
@@ -587,9 +751,10 @@ static int run_finish(lgr_ctx* c, lgr_stats* st) {
     st->dp_cells = hctr[C_CELLS], st->dp_cells_full = hctr[C_CELLSFULL];
     st->chain_evals = hctr[C_EVALS], st->n_anchors = hctr[C_ANCH];
     st->kernel_launches = launches;
+    st->reserved = (int32_t)std::min<long long>(hctr[C_NOVF], INT32_MAX);  // pairs that took the overflow pass
   }
   if (hctr[C_ERR]) {
-    char buf[160];
+    char buf[200];
     snprintf(buf, sizeof(buf), "device path limit hit (flags 0x%llx: 1 reg arena, 2 ext arena, 4 cigar arena, 8 anchor cap, 16 cigar scratch, 32 minimizer cap)",
              hctr[C_ERR]);
     c->err = buf;
@@ -606,7 +771,8 @@ static int run_impl(lgr_ctx* c, lgr_stats* st) {
 }
 
 // enqueue the device→host copies whose sizes are known up front (records, inline cigars,
-// assignments); the overflow cigar arena follows in download_finish once its fill is known
+// assignments, per-group status); the overflow cigar arena follows in download_finish once its
+// fill is known
 static int download_launch(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
   if (!c->resident || !out) { c->err = "nothing to download"; return LGR_E_ARG; }
   LGR_CUDA(c, cudaSetDevice(c->device));
@@ -627,13 +793,26 @@ static int download_launch(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
     LGR_CUDA(c, cudaMemcpyAsync(out->assign, D.assign, sizeof(AssignOut) * D.n_assign, cudaMemcpyDeviceToHost, c->stream));
     d2h += sizeof(AssignOut) * D.n_assign;
   }
+  if (out->grp_status && D.n_groups > 0) {
+    LGR_CUDA(c, cudaMemcpyAsync(out->grp_status, D.grp_err, sizeof(int32_t) * D.n_groups, cudaMemcpyDeviceToHost, c->stream));
+    d2h += sizeof(int32_t) * D.n_groups;
+  }
+  if (out->grp_mid_occ && D.n_groups > 0) {
+    LGR_CUDA(c, cudaMemcpyAsync(out->grp_mid_occ, D.grp_mid, sizeof(int32_t) * D.n_groups, cudaMemcpyDeviceToHost, c->stream));
+    d2h += sizeof(int32_t) * D.n_groups;
+  }
   if (d2h_bytes) *d2h_bytes = d2h;
   return LGR_OK;
 }
 
-// stream already drained by the caller
+// stream already drained by the caller.  ErrBits → LGR_E_* per group.
 static int download_finish(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
   Dev& D = c->D;
+  if (out->grp_status)
+    for (int g = 0; g < D.n_groups; ++g) {
+      const int bits = out->grp_status[g];
+      out->grp_status[g] = bits == 0 ? LGR_OK : (bits == E_CIG_ARENA ? LGR_E_CIGAR_OVERFLOW : LGR_E_LIMIT);
+    }
   if (out->aln) {
     const long long used = c->h_ctr[C_COUNT];
     out->cigar_arena_used = used;
@@ -654,9 +833,22 @@ static int download_impl(lgr_ctx* c, lgr_batch_out* out, int64_t* d2h_bytes) {
   return download_finish(c, out, d2h_bytes);
 }
 
+// a device-path limit hit some pairs: with a per-group status array the call is a partial success
+static int limit_code(int run_rc, const lgr_batch_out* out) {
+  if ((run_rc == LGR_E_LIMIT || run_rc == LGR_E_CIGAR_OVERFLOW) && out && out->grp_status) return LGR_E_PARTIAL;
+  return run_rc;
+}
+
 int lgr_upload(lgr_ctx* c, const lgr_batch_in* in) {
   if (!c) return LGR_E_ARG;
   int rc = upload_impl(c, in, nullptr);
+  if (rc == LGR_OK) LGR_CUDA(c, cudaStreamSynchronize(c->stream));
+  return rc;
+}
+
+int lgr_upload_packed(lgr_ctx* c, const lgr_packed_in* in) {
+  if (!c) return LGR_E_ARG;
+  int rc = upload_packed_impl(c, in, nullptr);
   if (rc == LGR_OK) LGR_CUDA(c, cudaStreamSynchronize(c->stream));
   return rc;
 }
@@ -672,18 +864,23 @@ int lgr_download(lgr_ctx* c, lgr_batch_out* out) {
   return download_impl(c, out, nullptr);
 }
 
-int lgr_genotype_batch(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_stats* stats) {
+// synchronous: upload (either form), all kernels, download
+typedef int (*upload_fn)(lgr_ctx*, const void*, int64_t*);
+static int up_plain(lgr_ctx* c, const void* in, int64_t* b) { return upload_impl(c, static_cast<const lgr_batch_in*>(in), b); }
+static int up_packed(lgr_ctx* c, const void* in, int64_t* b) { return upload_packed_impl(c, static_cast<const lgr_packed_in*>(in), b); }
+
+static int genotype_sync(lgr_ctx* c, const void* in, lgr_batch_out* out, lgr_stats* stats, upload_fn up) {
   if (!c || !in || !out) return LGR_E_ARG;
   lgr_stats st;
   std::memset(&st, 0, sizeof(st));
   int64_t h2d = 0, d2h = 0;
   cudaEventRecord(c->ev[5], c->stream);
-  int rc = upload_impl(c, in, &h2d);
+  int rc = up(c, in, &h2d);
   if (rc != LGR_OK) return rc;
   cudaEventRecord(c->ev[6], c->stream);
   rc = run_impl(c, &st);
   if (rc != LGR_OK && rc != LGR_E_LIMIT && rc != LGR_E_CIGAR_OVERFLOW) return rc;
-  const int run_rc = rc;
+  const int run_rc = limit_code(rc, out);
   cudaEventRecord(c->ev[7], c->stream);
   rc = download_impl(c, out, &d2h);
   cudaEventRecord(c->ev[8], c->stream);
@@ -696,7 +893,15 @@ int lgr_genotype_batch(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, l
   return run_rc != LGR_OK ? run_rc : rc;
 }
 
-int lgr_submit(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_ticket* ticket) {
+int lgr_genotype_batch(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_stats* stats) {
+  return genotype_sync(c, in, out, stats, up_plain);
+}
+
+int lgr_genotype_packed(lgr_ctx* c, const lgr_packed_in* in, lgr_batch_out* out, lgr_stats* stats) {
+  return genotype_sync(c, in, out, stats, up_packed);
+}
+
+static int submit_async(lgr_ctx* c, const void* in, lgr_batch_out* out, lgr_ticket* ticket, upload_fn up) {
   if (!c || !in || !out || !ticket) return LGR_E_ARG;
   int t = -1;
   for (int i = 0; i < LGR_MAX_INFLIGHT && t < 0; ++i)
@@ -709,7 +914,7 @@ int lgr_submit(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_ticke
   lgr_ctx* ch = c->slot[t];
   int64_t h2d = 0, d2h = 0;
   cudaEventRecord(ch->ev[5], ch->stream);
-  int rc = upload_impl(ch, in, &h2d);
+  int rc = up(ch, in, &h2d);
   if (rc == LGR_OK) {
     cudaEventRecord(ch->ev[6], ch->stream);
     rc = run_launch(ch);
@@ -726,7 +931,35 @@ int lgr_submit(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_ticke
   }
   c->slot_busy[t] = true, c->slot_out[t] = out, c->slot_h2d[t] = h2d, c->slot_d2h[t] = d2h;
   *ticket = t;
+  if (c->notify_fn) {
+    c->slot_note[t] = lgr_ctx::Note{c, t};
+    cudaLaunchHostFunc(ch->stream, [](void* p) {
+      const lgr_ctx::Note* n = static_cast<const lgr_ctx::Note*>(p);
+      if (n->ctx->notify_fn) n->ctx->notify_fn(n->ctx->notify_user, n->ticket);
+    }, &c->slot_note[t]);
+  }
   return LGR_OK;
+}
+
+int lgr_set_notify(lgr_ctx* c, lgr_notify_fn fn, void* user) {
+  if (!c) return LGR_E_ARG;
+  c->notify_fn = fn, c->notify_user = user;
+  return LGR_OK;
+}
+
+int lgr_check_limits(const lgr_params* params, int32_t max_hap_len, int32_t max_read_len) {
+  lgr_params p;
+  if (params) p = *params;
+  else lgr_default_params(&p);
+  return limit_message(p, max_hap_len, max_read_len) ? LGR_E_LIMIT : LGR_OK;
+}
+
+int lgr_submit(lgr_ctx* c, const lgr_batch_in* in, lgr_batch_out* out, lgr_ticket* ticket) {
+  return submit_async(c, in, out, ticket, up_plain);
+}
+
+int lgr_submit_packed(lgr_ctx* c, const lgr_packed_in* in, lgr_batch_out* out, lgr_ticket* ticket) {
+  return submit_async(c, in, out, ticket, up_packed);
 }
 
 int lgr_wait(lgr_ctx* c, lgr_ticket t, lgr_stats* stats) {
@@ -742,10 +975,17 @@ int lgr_wait(lgr_ctx* c, lgr_ticket t, lgr_stats* stats) {
   }
   lgr_stats st;
   std::memset(&st, 0, sizeof(st));
-  const int run_rc = run_finish(ch, &st);
+  const int passes0 = ch->overflow_passes;
+  int run_rc = run_finish(ch, &st);
   int rc = LGR_OK;
   int64_t d2h = c->slot_d2h[t];
-  if (run_rc == LGR_OK || run_rc == LGR_E_LIMIT || run_rc == LGR_E_CIGAR_OVERFLOW) rc = download_finish(ch, c->slot_out[t], &d2h);
+  if (run_rc == LGR_OK || run_rc == LGR_E_LIMIT || run_rc == LGR_E_CIGAR_OVERFLOW) {
+    // the overflow pass rewrote results after the copies of lgr_submit were taken: copy again
+    if (ch->overflow_passes != passes0) rc = download_launch(ch, c->slot_out[t], &d2h);
+    if (rc == LGR_OK && ch->overflow_passes != passes0 && cudaStreamSynchronize(ch->stream) != cudaSuccess) rc = LGR_E_CUDA;
+    if (rc == LGR_OK) rc = download_finish(ch, c->slot_out[t], &d2h);
+  }
+  run_rc = limit_code(run_rc, c->slot_out[t]);
   float ms;
   cudaEventElapsedTime(&ms, ch->ev[5], ch->ev[6]); st.ms_h2d = ms;
   cudaEventElapsedTime(&ms, ch->ev[7], ch->ev[8]); st.ms_d2h = ms;
@@ -753,6 +993,19 @@ int lgr_wait(lgr_ctx* c, lgr_ticket t, lgr_stats* stats) {
   if (stats) *stats = st;
   if (run_rc != LGR_OK || rc != LGR_OK) c->err = ch->err;
   return run_rc != LGR_OK ? run_rc : rc;
+}
+
+size_t lgr_packed_group_bytes(const lgr_group_desc* g) {
+  const lgr_pack::Plan p = lgr_pack::plan_group(g);
+  return p.rc == LGR_OK ? p.bytes : 0;
+}
+
+int lgr_pack_group(const lgr_group_desc* g, void* dst, size_t cap, lgr_group_dir* dir) {
+  if (!g || !dst || (reinterpret_cast<uintptr_t>(dst) & 7)) return LGR_E_ARG;
+  const lgr_pack::Plan p = lgr_pack::plan_group(g);
+  if (p.rc != LGR_OK) return p.rc;
+  if (p.bytes > cap) return LGR_E_ARG;
+  return lgr_pack::pack_group(g, p, dst, dir);
 }
 
 int lgr_hap_mid_occ(lgr_ctx* c, const uint8_t* hap, int32_t hap_len, int32_t* mid_occ) {

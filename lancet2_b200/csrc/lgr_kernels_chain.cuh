@@ -46,14 +46,14 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
       if (counted) ctr = ctr_before;
       PairReg pr{0, 0, r, h};
       if (st == kMapOverflow) {
-        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
+        flag_err(D, g, E_ANCHOR_CAP);
         write_invalid(&D.aln[pair]);
       } else if (st == kMapNoHit) {
         write_invalid(&D.aln[pair]);
       } else {
         const long long first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
         if (first + n_regs > D.regs_cap) {
-          atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+          flag_err(D, g, E_REG_ARENA);
           write_invalid(&D.aln[pair]);
         } else {
           pr = PairReg{(int32_t)first, n_regs, r, h};
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
               if (rg->ext[side].m <= 0) continue;
               const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
               if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
-              else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+              else flag_err(D, g, E_REG_ARENA);
             }
           }
         }
@@ -104,7 +104,7 @@ constexpr int kMapOkColinear = 2;  // warp_seed_chain: chain DP done by the co-l
 
 template <int CAP>
 __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const uint16_t* bkt, const Ws<1>& ws,
-                                               RadixScratch* rsx, ChainCounters* ctr, int* n_a_out) {
+                                               RadixScratch* rsx, ChainCounters* ctr, int* n_a_out, int* need_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
@@ -113,7 +113,7 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
   auto seedq = ws.arr(A_SEEDQ), seedn = ws.arr(A_SEEDN), seeds = ws.arr(A_SEEDS);
   const int qlen = in.read.qlen;
   // ---- seeds (mm_seed_collect_all) ----
-  int n_m = 0, n_high = 0;
+  int n_m = 0, n_high = 0, n_occ = 0;
   for (int base = 0; base < in.mz_n; base += 32) {
     const int i = base + lane;
     int occ = 0, s0 = 0;
@@ -149,7 +149,10 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     if (occ > 0 && pos < CAP) seedq[pos] = (int32_t)sq, seedn[pos] = occ, seeds[pos] = s0;
     n_high += __popc(__ballot_sync(full, occ > in.mid_occ));
     n_m += __popc(hit);
+    n_occ += __reduce_add_sync(full, occ);
   }
+  // what the overflow pass must hold for this pair: every seed and every occurrence (seed_select only removes)
+  *need_out = n_m > n_occ ? n_m : n_occ;
   if (n_m > CAP) return kMapOverflow;
   __syncwarp();
   if (n_high > 0) {
@@ -643,8 +646,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
       const int qlen = (int)(D.read_off[r + 1] - roff);
       ReadView rv{D.read_codes + roff, qlen};
       PairIn pin{rv, hapc, hlen, idx, idx_n, D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], mid_occ};
-      int n_a = 0, n_regs = 0;
-      int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, D.bkt + (size_t)h * (kBuckets + 1), ws, rsx, &ctr, &n_a) : kMapNoHit;
+      int n_a = 0, n_regs = 0, need = 0;
+      int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, D.bkt + (size_t)h * (kBuckets + 1), ws, rsx, &ctr, &n_a, &need) : kMapNoHit;
       if (st == kMapOkColinear) {
         st = warp_chain_tail_colinear(D.P, qlen, hlen, pin.name_hash, ws, n_a);
         n_regs = 1;
@@ -660,16 +663,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
       long long first = -1;
       if (lane == 0) {
         if (st == kMapOverflow) {
+          // not refused: listed for the host-driven overflow pass (lgr_gpu.cu overflow_pass), which
+          // sizes its HBM workspace from the largest need recorded here
           const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
           if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h | (n_a > 0 ? 1 << 30 : 0);  // n_a > 0: overflowed after counting
-          else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_ANCHOR_CAP);
+          else flag_err(D, g, E_ANCHOR_CAP);
+          atomicMax((unsigned long long*)&D.ctr[C_OVFNEED], (unsigned long long)need);
+          write_invalid(&D.aln[pair]);
+          D.pair_reg[pair] = PairReg{0, 0, r, h};
         } else if (st == kMapNoHit) {
           write_invalid(&D.aln[pair]);
           D.pair_reg[pair] = PairReg{0, 0, r, h};
         } else {
           first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
           if (first + n_regs > D.regs_cap) {
-            atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+            flag_err(D, g, E_REG_ARENA);
             write_invalid(&D.aln[pair]);
             D.pair_reg[pair] = PairReg{0, 0, r, h};
             first = -1;
@@ -691,7 +699,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
             if (lane == 0) {
               const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
               if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
-              else atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_REG_ARENA);
+              else flag_err(D, g, E_REG_ARENA);
             }
           }
         }

@@ -16,7 +16,7 @@ namespace {
 // ---------------------------------------------------------------------------------------
 constexpr int kDynPruneMinRows = 12;  // shorter tails: the static bound is already small, skip the extra pass
 
-__device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, const ReadView& rv, const uint8_t* hapc,
+__device__ __noinline__ void ext_dp_warp(const Dev& D, int grp, RegRec* reg, int side, const ReadView& rv, const uint8_t* hapc,
                                          uint8_t* dir_g, uint8_t* dir_s, int dir_s_cap, int32_t* Hb, int32_t* Fb, uint32_t* wcig,
                                          long long* cells, long long* cells_full) {
   const unsigned full = 0xffffffffu;
@@ -195,7 +195,7 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
     E.mqe_t = mqe_t;
     E.n_cig = cb.n;
     if (cb.n > D.wcig_cap) {
-      atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+      flag_err(D, grp, E_CIG_SCRATCH);
       E.n_cig = 0;
     } else if (cb.n <= kInlineCig) {
       E.cig_off = -1;
@@ -203,7 +203,7 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, RegRec* reg, int side, co
     } else {
       const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)cb.n);
       if (o + cb.n > D.ext_arena_cap) {
-        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_EXT_ARENA);
+        flag_err(D, grp, E_EXT_ARENA);
         E.n_cig = 0;
       } else {
         E.cig_off = (int32_t)o;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128, LGR_EXT_MINB) k_ext_warp(const __grid_con
 #ifdef LGR_EXT_HIST
     const long long t_begin = clock64();
 #endif
-    ext_dp_warp(D, &D.regs[tk.reg], tk.side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig,
+    ext_dp_warp(D, D.read_grp[tk.read], &D.regs[tk.reg], tk.side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig,
                 &c1, &c2);
 #ifdef LGR_EXT_HIST
     if (lane == 0) {

@@ -310,10 +310,10 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_
     }
     if (lane == 0) {
       if (nc < 0) {
-        atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_CIG_SCRATCH);
+        flag_err(D, D.read_grp[read], E_CIG_SCRATCH);
         write_invalid(&D.aln[pair]);
       } else {
-        store_final(D, pair, ao, fs.best, nc);
+        store_final(D, D.read_grp[read], pair, ao, fs.best, nc);
         n_aligned += ao.valid;
       }
     }

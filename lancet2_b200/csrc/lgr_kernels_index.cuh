@@ -56,7 +56,7 @@ __global__ void k_hap_sketch(const __grid_constant__ Dev D) {
       n = sketch(D.hap_codes + off, len, D.P.w, D.P.k, XW{tab}, YW{tab}, len);
     }
   }
-  if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
+  if (n > len) { n = len; flag_err(D, D.hap_grp[h], E_MZ_CAP); }
   D.idx_n[h] = n;
 }
 
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_hap_sketch_warp(const __grid_constant__
     if (lane < W) sx[lane] = sx[32 + lane], sy[lane] = sy[32 + lane];  // carry the last W records over
   }
   if (lane == 0) {
-    if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
+    if (n > len) { n = len; flag_err(D, D.hap_grp[h], E_MZ_CAP); }
     D.idx_n[h] = n;
   }
 }
@@ -243,9 +243,9 @@ __global__ void k_hap_sort(const __grid_constant__ Dev D, float mid_occ_frac, in
 __global__ void k_group_mid(const __grid_constant__ Dev D, int min_mid) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= D.n_groups) return;
-  if (D.grp_mid[g] > 0) return;
+  const int req = D.grp_mid_req[g];
   const int h0 = D.grp_hap_begin[g];
-  D.grp_mid[g] = D.grp_hap_begin[g + 1] > h0 ? D.hap_mid[h0] : min_mid;
+  D.grp_mid[g] = req > 0 ? req : (D.grp_hap_begin[g + 1] > h0 ? D.hap_mid[h0] : min_mid);
 }
 
 // one lane per read: sketch.  Independent of the haplotype index, so it runs on a second stream
@@ -270,7 +270,7 @@ __global__ void k_read_sketch(const __grid_constant__ Dev D) {
     };
     if (D.P.w == 5) sketch_sr<5>(D.read_codes + off, len, D.P.k, emit);
     else n = sketch(D.read_codes + off, len, D.P.w, D.P.k, mzx, mzy, len), cnt_lo = cnt_hi = ~0ULL;
-    if (n > len) { n = len; atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)E_MZ_CAP); }
+    if (n > len) { n = len; flag_err(D, D.read_grp[r], E_MZ_CAP); }
   }
   D.mz_n[r] = n;
   D.mz_cnt[2 * (size_t)r] = cnt_lo, D.mz_cnt[2 * (size_t)r + 1] = cnt_hi;

@@ -238,11 +238,11 @@ int lgr_adapter_host_logic_dump(const lgr_batch_in* in, const char* names, const
 // every worker keeps that many groups enqueued (Enqueue/Collect) instead of blocking per group.
 // n_devices > 1: a GenotypeDispatcher over devices device .. device+n_devices-1; counters[9 + d] =
 // payloads that went to device d (counters must hold 17 entries).
-int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
+static int BatcherRun(int device, const lgr_batch_in* in, const char* names, const char* samples,
                              const int* sample_id, const long long* start0, const long long* isize,
                              const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
-                             int n_threads, int rounds, int window, int n_devices, unsigned long long* counters, char* out,
-                             long long cap) {
+                             int n_threads, int rounds, int window, int n_devices, unsigned long long* counters, int n_counters,
+                             char* out, long long cap, bool dump) {
   try {
     JobSet js;
     BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
@@ -288,8 +288,10 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
         c.batches += cd.batches, c.jobs += cd.jobs, c.pairs += cd.pairs;
         c.max_jobs_in_batch = std::max(c.max_jobs_in_batch, cd.max_jobs_in_batch);
         c.ns_pack += cd.ns_pack, c.ns_submit += cd.ns_submit, c.ns_wait += cd.ns_wait, c.ns_deliver += cd.ns_deliver;
+        c.h2d_bytes += cd.h2d_bytes, c.d2h_bytes += cd.d2h_bytes, c.retried_alone += cd.retried_alone;
         if (counters && d < 8) counters[9 + d] = cd.jobs;
       }
+      if (counters && n_counters >= 20) counters[17] = c.h2d_bytes, counters[18] = c.d2h_bytes, counters[19] = c.retried_alone;
       if (counters) {
         counters[0] = c.batches, counters[1] = c.jobs, counters[2] = c.pairs, counters[3] = c.max_jobs_in_batch;
         counters[4] = (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
@@ -298,10 +300,76 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
     }
     for (const auto& e : errors)
       if (!e.empty()) throw std::runtime_error(e);
-    if (cap <= 0) return 0;
+    if (!dump || cap <= 0) return 0;
     return WriteOut(DumpResults(in, js, res), out, cap);
   } catch (const std::exception& e) {
-    std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
+    if (out && cap > 0) std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
+    return -2;
+  }
+}
+
+int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
+                             const int* sample_id, const long long* start0, const long long* isize,
+                             const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
+                             int n_threads, int rounds, int window, int n_devices, unsigned long long* counters, char* out,
+                             long long cap) {
+  return BatcherRun(device, in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, n_threads, rounds, window,
+                    n_devices, counters, 17, out, cap, true);
+}
+
+// the same without the dump, for bench.py's e2e arm: counters[20] adds [17] bytes copied host→device, [18] device→host,
+// [19] payloads re-run alone
+int lgr_adapter_batcher_bench(int device, const lgr_batch_in* in, const char* names, const char* samples,
+                              const int* sample_id, const long long* start0, const long long* isize,
+                              const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
+                              int n_threads, int rounds, int window, int n_devices, unsigned long long* counters, char* err,
+                              long long err_cap) {
+  const int rc = BatcherRun(device, in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, n_threads, rounds,
+                            window, n_devices, counters, 20, err, err_cap, false);
+  return rc;
+}
+
+// Failure isolation of the batcher: ONE worker enqueues every group before it collects the first (so they
+// share device batches), catching per payload.  job_status[g] = 0 ok, 1 Enqueue threw, 2 Collect threw; the dump
+// holds the evidence of the groups that succeeded.  mid_occ > 0 overrides lgr_params::mid_occ (to provoke a
+// device-side cap).  counters[0] = payloads re-run alone.
+int lgr_adapter_isolation_dump(int device, const lgr_batch_in* in, const char* names, const char* samples,
+                               const int* sample_id, const long long* start0, const long long* isize,
+                               const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
+                               int mid_occ, int* job_status, unsigned long long* counters, char* out, long long cap) {
+  try {
+    JobSet js;
+    BuildJobs(in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, js);
+    std::vector<lancet_gpu::Result> res(js.jobs.size());
+    lgr_params prm;
+    lgr_default_params(&prm);
+    if (mid_occ > 0) prm.mid_occ = mid_occ;
+    lancet_gpu::GenotypeBatcher::Options opt;
+    opt.device = device, opt.params = &prm, opt.linger_us = 2000;
+    {
+      lancet_gpu::GenotypeBatcher batcher(opt, X31OfView);
+      std::vector<lancet_gpu::GenotypeBatcher::Ticket> tickets(js.jobs.size());
+      for (std::size_t g = 0; g < js.jobs.size(); ++g) {
+        job_status[g] = 0;
+        try {
+          tickets[g] = batcher.Enqueue(js.jobs[g]);
+        } catch (const std::exception&) {
+          job_status[g] = 1;
+        }
+      }
+      for (std::size_t g = 0; g < js.jobs.size(); ++g) {
+        if (job_status[g]) continue;
+        try {
+          res[g] = batcher.Collect(tickets[g]);
+        } catch (const std::exception&) {
+          job_status[g] = 2;
+        }
+      }
+      if (counters) counters[0] = batcher.Stats().retried_alone, counters[1] = batcher.Stats().batches;
+    }
+    return WriteOut(DumpResults(in, js, res), out, cap);
+  } catch (const std::exception& e) {
+    if (out && cap > 0) std::snprintf(out, (size_t)cap, "EXCEPTION: %s", e.what());
     return -2;
   }
 }

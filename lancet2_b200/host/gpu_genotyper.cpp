@@ -2,6 +2,8 @@
 // and AddToTable/AddEvidence in the reference's read order.
 #include "gpu_genotyper.h"
 
+#include "../csrc/lgr_pack.h"
+
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -370,14 +372,137 @@ std::vector<Result> GpuGenotyper::GenotypeMany(const std::vector<GenotypeJob>& j
 // ---------------------------------------------------------------------------------------------
 // GenotypeBatcher
 // ---------------------------------------------------------------------------------------------
+static std::uint64_t NowNs() {
+  return static_cast<std::uint64_t>(
+      std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+
+// minimap2's __ac_X31_hash_string over the read name as mm_map sees it (a C string: stops at NUL)
+static std::uint32_t X31(std::string_view q) {
+  if (q.empty() || q[0] == '\0') return 0;
+  std::uint32_t h = static_cast<std::uint32_t>(static_cast<std::int32_t>(static_cast<signed char>(q[0])));
+  for (std::size_t i = 1; i < q.size() && q[i] != '\0'; ++i)
+    h = (h << 5) - h + static_cast<std::uint32_t>(static_cast<std::int32_t>(static_cast<signed char>(q[i])));
+  return h;
+}
+
+namespace {
+// per-thread scratch of Enqueue: the lgr_group_desc view of one payload (no allocation in steady state)
+struct PackScratch {
+  std::vector<const std::uint8_t*> hap_seq, read_seq, read_qual;
+  std::vector<std::int32_t> hap_len, read_len, var_start, var_len;
+  std::vector<std::uint32_t> x31;
+  std::vector<std::int8_t> var_allele;
+  lgr_pack::Plan last_plan;  // quality dictionary of this thread's previous payload
+  bool have_plan = false;
+};
+
+void DescribeJob(const GenotypeJob& j, PackScratch& sc, lgr_group_desc* d) {
+  sc.hap_seq.resize(j.n_haps), sc.hap_len.resize(j.n_haps);
+  for (std::size_t h = 0; h < j.n_haps; ++h) {
+    sc.hap_seq[h] = reinterpret_cast<const std::uint8_t*>(j.haps[h].data());
+    sc.hap_len[h] = static_cast<std::int32_t>(j.haps[h].size());
+  }
+  sc.read_seq.resize(j.n_reads), sc.read_qual.resize(j.n_reads), sc.read_len.resize(j.n_reads), sc.x31.resize(j.n_reads);
+  for (std::size_t r = 0; r < j.n_reads; ++r) {
+    const ReadIn& rd = j.reads[r];
+    sc.read_seq[r] = reinterpret_cast<const std::uint8_t*>(rd.seq.data());
+    sc.read_qual[r] = rd.qual;
+    sc.read_len[r] = static_cast<std::int32_t>(rd.seq.size());
+    sc.x31[r] = X31(rd.qname);
+  }
+  const std::size_t vh = j.n_variants * j.n_haps;
+  sc.var_start.assign(vh, -1), sc.var_len.assign(vh, 0), sc.var_allele.assign(vh, -1);
+  for (std::size_t v = 0; v < j.n_variants; ++v) {  // ExtractHapBounds (genotyper.cpp:329-352)
+    const VariantIn& var = j.variants[v];
+    const std::size_t row = v * j.n_haps;
+    if (j.n_haps > 0) {
+      sc.var_start[row] = static_cast<std::int32_t>(var.local_ref_start0);
+      sc.var_len[row] = static_cast<std::int32_t>(var.ref_allele_len);
+      sc.var_allele[row] = 0;
+    }
+    for (std::size_t a = 0; a < var.alts.size(); ++a)
+      for (const auto& kv : var.alts[a].hap_start0) {
+        const std::size_t h = kv.first;
+        if (h == 0 || h >= j.n_haps || sc.var_allele[row + h] >= 0) continue;  // first ALT that lists the haplotype wins
+        sc.var_start[row + h] = static_cast<std::int32_t>(kv.second);
+        sc.var_len[row + h] = static_cast<std::int32_t>(var.alts[a].seq_len);
+        sc.var_allele[row + h] = static_cast<std::int8_t>(a + 1);
+      }
+  }
+  d->n_haps = static_cast<std::int32_t>(j.n_haps), d->n_reads = static_cast<std::int32_t>(j.n_reads);
+  d->n_vars = static_cast<std::int32_t>(j.n_variants), d->mid_occ = 0;
+  d->hap_seq = sc.hap_seq.data(), d->hap_len = sc.hap_len.data();
+  d->read_seq = sc.read_seq.data(), d->read_qual = sc.read_qual.data(), d->read_len = sc.read_len.data();
+  d->read_name_hash = sc.x31.data();
+  d->var_start = sc.var_start.data(), d->var_len = sc.var_len.data(), d->var_allele = sc.var_allele.data();
+}
+
+std::atomic<std::uint64_t> g_latch_uid{1};
+// mm_mapopt_update latch of the calling thread, per batcher / dispatcher instance
+std::int32_t* ThreadLatch(std::uint64_t uid) {
+  thread_local std::unordered_map<std::uint64_t, std::int32_t> latches;
+  return &latches[uid];
+}
+}  // namespace
+
+// results of one device batch: lives until the last of its payloads has been collected, while the
+// staging slab it came from goes back to the pool as soon as the device is done with it (a worker may
+// enqueue many windows before it collects the first)
+struct GenotypeBatcher::ResultBlock {
+  lgr_assign* assign = nullptr;        // pinned
+  std::size_t assign_cap = 0;
+  std::int32_t* status = nullptr;      // pinned [max_jobs]: lgr_batch_out::grp_status
+  std::int32_t* mid = nullptr;         // pinned [max_jobs]: lgr_batch_out::grp_mid_occ
+  std::vector<std::int64_t> job_asg;   // [max_jobs] first lgr_assign record of every payload
+  std::vector<std::int32_t> job_mid;   // [max_jobs] mid_occ the payload was packed with (for a re-run alone)
+  std::uint32_t refs = 0;              // payloads not yet released
+  bool done = false;
+  int rc = LGR_OK;
+  std::string err;
+};
+
+struct GenotypeBatcher::Slab {
+  std::uint8_t* mem = nullptr;  // pinned: group records, then (at seal time) the directory
+  std::size_t cap = 0, used = 0;
+  std::vector<lgr_group_dir> dir;      // [max_jobs], entry written by the payload's worker
+  std::uint32_t n_jobs = 0;
+  std::int64_t pairs = 0, n_assign = 0;
+  std::atomic<int> packing{0};         // workers still writing their record
+  ResultBlock* res = nullptr;
+  lgr_packed_in in{};
+  lgr_batch_out out{};
+  lgr_ticket ticket = -1;
+  bool lingered = false;
+};
+
+static void* PinnedOrThrow(std::size_t bytes) {
+  void* p = lgr_alloc_pinned(bytes);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+
 GenotypeBatcher::GenotypeBatcher(const Options& opt, NameHashFn name_hash) : mOpt(opt), mNameHash(std::move(name_hash)) {
   if (mOpt.depth < 1) mOpt.depth = 1;
   if (mOpt.depth > LGR_MAX_INFLIGHT) mOpt.depth = LGR_MAX_INFLIGHT;
+  if (mOpt.max_jobs < 1) mOpt.max_jobs = 1;
+  if (mOpt.slab_bytes < (1u << 16)) mOpt.slab_bytes = 1u << 16;
   if (opt.params) mParams = *opt.params;
   else lgr_default_params(&mParams);
   mOpt.params = nullptr;
+  mUid = g_latch_uid.fetch_add(1);
   Check(nullptr, lgr_create(mOpt.device, &mParams, &mCtx));
-  for (int i = 0; i < mOpt.depth; ++i) mSlots.push_back(std::make_unique<Slot>());
+  Check(nullptr, lgr_create(mOpt.device, &mParams, &mAuxCtx));
+  Check(mCtx, lgr_set_notify(mCtx, &GenotypeBatcher::OnDeviceDone, this));
+  const int n_slabs = mOpt.depth + 2;  // in flight + one filling + one waiting for a device slot
+  for (int i = 0; i < n_slabs; ++i) {
+    auto s = std::make_unique<Slab>();
+    s->cap = mOpt.slab_bytes;
+    s->mem = static_cast<std::uint8_t*>(PinnedOrThrow(s->cap));
+    s->dir.resize(mOpt.max_jobs);
+    mFree.push_back(s.get());
+    mSlabs.push_back(std::move(s));
+  }
   mThread = std::thread([this] { Run(); });
 }
 
@@ -387,32 +512,300 @@ GenotypeBatcher::~GenotypeBatcher() {
     mStop = true;
   }
   mCv.notify_all();
+  mFreeCv.notify_all();
   if (mThread.joinable()) mThread.join();
-  mSlots.clear();
   lgr_destroy(mCtx);
+  lgr_destroy(mAuxCtx);
+  for (auto& s : mSlabs) lgr_free_pinned(s->mem);
+  for (auto& r : mResults) lgr_free_pinned(r->assign), lgr_free_pinned(r->status), lgr_free_pinned(r->mid);
+  mSlabs.clear();
+  mResults.clear();
+}
+
+void GenotypeBatcher::OnDeviceDone(void* self, lgr_ticket ticket) {  // CUDA-owned thread: no CUDA / library calls here
+  auto* b = static_cast<GenotypeBatcher*>(self);
+  {
+    std::lock_guard<std::mutex> lk(b->mMu);
+    b->mDeviceDone |= 1u << ticket;
+  }
+  b->mCv.notify_all();
+}
+
+// an EMPTY slab gets room for one payload of `need_bytes` (rare; pinned allocation is slow)
+void GenotypeBatcher::GrowSlab(Slab* s, std::size_t need_bytes) {
+  const std::size_t want = need_bytes + sizeof(lgr_group_dir) + 64;
+  if (s->cap >= want) return;
+  lgr_free_pinned(s->mem);
+  s->mem = nullptr, s->cap = 0;
+  s->mem = static_cast<std::uint8_t*>(PinnedOrThrow(want + want / 4));
+  s->cap = want + want / 4;
+}
+
+// an empty slab with room for `need_bytes` of records plus one directory entry
+GenotypeBatcher::Slab* GenotypeBatcher::TakeFreeSlabLocked(std::unique_lock<std::mutex>& lk, std::size_t need_bytes) {
+  mFreeCv.wait(lk, [&] { return mStop || !mFree.empty(); });
+  if (mStop) throw std::runtime_error("lancet_gpu::GenotypeBatcher: shut down");
+  Slab* s = mFree.back();
+  mFree.pop_back();
+  GrowSlab(s, need_bytes);
+  if (!s->res) {
+    if (mFreeResults.empty()) {
+      auto r = std::make_unique<ResultBlock>();
+      r->job_asg.resize(mOpt.max_jobs), r->job_mid.resize(mOpt.max_jobs);
+      r->status = static_cast<std::int32_t*>(PinnedOrThrow(sizeof(std::int32_t) * mOpt.max_jobs));
+      r->mid = static_cast<std::int32_t*>(PinnedOrThrow(sizeof(std::int32_t) * mOpt.max_jobs));
+      mFreeResults.push_back(r.get());
+      mResults.push_back(std::move(r));
+    }
+    s->res = mFreeResults.back();
+    mFreeResults.pop_back();
+  }
+  return s;
+}
+
+std::int32_t GenotypeBatcher::LatchFor(const GenotypeJob& job) {
+  if (mParams.mid_occ > 0) return 0;  // fixed by the option set: nothing to latch
+  std::int32_t* latch = job.mid_occ_latch ? job.mid_occ_latch : ThreadLatch(mUid);
+  if (*latch > 0 || job.n_haps == 0) return *latch;
+  std::lock_guard<std::mutex> lk(mAuxMu);
+  Check(mAuxCtx, lgr_hap_mid_occ(mAuxCtx, reinterpret_cast<const std::uint8_t*>(job.haps[0].data()),
+                                 static_cast<std::int32_t>(job.haps[0].size()), latch));
+  return *latch;
 }
 
 GenotypeBatcher::Ticket GenotypeBatcher::Enqueue(const GenotypeJob& job) {
-  Pending p;
-  p.job = job;
-  p.packed = std::make_unique<PackedJob>();
-  p.packed->Build(job);  // on the enqueuing worker: the batcher thread only concatenates
+  const std::uint64_t t0 = NowNs();
+  thread_local PackScratch sc;
+  lgr_group_desc desc;
+  DescribeJob(job, sc, &desc);
+  const lgr_pack::Plan plan = lgr_pack::plan_group(&desc, sc.have_plan ? &sc.last_plan : nullptr);
+  // a payload outside the static caps is refused here, alone: it never joins (and fails) a batch
+  if (plan.rc != LGR_OK) throw std::runtime_error(std::string("lancet_gpu::GenotypeBatcher: ") + lgr_strerror(plan.rc) + " (this payload only)");
+  if (lgr_check_limits(&mParams, plan.max_hap_len, plan.max_read_len) != LGR_OK)
+    throw std::runtime_error("lancet_gpu::GenotypeBatcher: payload beyond the device path's static caps (this payload only)");
+  sc.last_plan = plan, sc.have_plan = true;
+  desc.mid_occ = LatchFor(job);
+  const std::int64_t pairs = static_cast<std::int64_t>(job.n_reads) * static_cast<std::int64_t>(job.n_haps);
+  const std::int64_t n_asg = static_cast<std::int64_t>(job.n_reads) * static_cast<std::int64_t>(job.n_variants);
   Ticket t;
   t.job = job;
-  t.done = p.done.get_future();
+  std::size_t off = 0;
+  Slab* s = nullptr;
   {
-    std::lock_guard<std::mutex> lk(mMu);
+    std::unique_lock<std::mutex> lk(mMu);
     if (mStop) throw std::runtime_error("lancet_gpu::GenotypeBatcher: shut down");
-    mQueue.push_back(std::move(p));
+    for (;;) {
+      if (!mOpen) {
+        Slab* f = TakeFreeSlabLocked(lk, plan.bytes);  // may wait: another worker can open a slab meanwhile
+        if (mOpen) mFree.push_back(f), mFreeCv.notify_one();
+        else mOpen = f;
+      }
+      s = mOpen;
+      const std::size_t dir_room = sizeof(lgr_group_dir) * (s->n_jobs + 1) + 32;
+      if (s->n_jobs == 0 && s->used + plan.bytes + dir_room > s->cap) GrowSlab(s, plan.bytes);  // one payload larger than the block
+      const bool fits = s->n_jobs < mOpt.max_jobs && s->used + plan.bytes + dir_room <= s->cap &&
+                        (s->n_jobs == 0 || s->pairs + pairs <= mOpt.max_pairs);
+      if (fits) break;
+      mSealable.push_back(s);  // full: the batcher thread submits it as soon as a device slot is free
+      mOpen = nullptr;
+      mCv.notify_all();
+    }
+    s = mOpen;
+    t.res = s->res, t.slot = s->n_jobs++;
+    off = s->used, s->used += plan.bytes;
+    s->res->job_asg[t.slot] = s->n_assign, s->res->job_mid[t.slot] = desc.mid_occ;
+    s->n_assign += n_asg, s->pairs += pairs;
+    ++s->res->refs;
+    s->packing.fetch_add(1, std::memory_order_relaxed);
   }
   mCv.notify_all();
+  const int rc = lgr_pack::pack_group(&desc, plan, s->mem + off, &s->dir[t.slot]);
+  s->dir[t.slot].rec_off = off;
+  if (rc != LGR_OK) s->dir[t.slot].n_reads = -1;  // the batch will be rejected as a whole (cannot happen: plan checked)
+  if (s->packing.fetch_sub(1, std::memory_order_release) == 1) mCv.notify_all();
+  const std::uint64_t t1 = NowNs();
+  {
+    std::lock_guard<std::mutex> lk(mMu);
+    mCounters.ns_pack += t1 - t0;
+  }
   return t;
 }
 
+void GenotypeBatcher::SealAndSubmit(Slab* s) {
+  const std::uint64_t t0 = NowNs();
+  while (s->packing.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // workers finishing their record
+  try {
+    const std::size_t dir_off = (s->used + 15) & ~static_cast<std::size_t>(15);
+    std::memcpy(s->mem + dir_off, s->dir.data(), sizeof(lgr_group_dir) * s->n_jobs);
+    s->in = lgr_packed_in{};
+    s->in.n_groups = static_cast<std::int32_t>(s->n_jobs);
+    s->in.slab = s->mem;
+    s->in.slab_bytes = dir_off + sizeof(lgr_group_dir) * s->n_jobs;
+    s->in.dir = reinterpret_cast<const lgr_group_dir*>(s->mem + dir_off);
+    ResultBlock* r = s->res;
+    if (static_cast<std::size_t>(s->n_assign) + 1 > r->assign_cap) {
+      lgr_free_pinned(r->assign);
+      r->assign = nullptr, r->assign_cap = 0;
+      const std::size_t want = static_cast<std::size_t>(s->n_assign) + static_cast<std::size_t>(s->n_assign) / 2 + 1024;
+      r->assign = static_cast<lgr_assign*>(PinnedOrThrow(want * sizeof(lgr_assign)));
+      r->assign_cap = want;
+    }
+    s->out = lgr_batch_out{};
+    s->out.n_assign = s->n_assign;
+    s->out.assign = r->assign;  // aln stays NULL: the adapter only needs the assignments
+    s->out.grp_status = r->status, s->out.grp_mid_occ = r->mid;
+    Check(mCtx, lgr_submit_packed(mCtx, &s->in, &s->out, &s->ticket));
+  } catch (const std::exception& e) {
+    s->ticket = -1, s->res->rc = LGR_E_CUDA, s->res->err = e.what();
+  }
+  const std::uint64_t t1 = NowNs();
+  std::lock_guard<std::mutex> lk(mMu);
+  mCounters.ns_submit += t1 - t0;
+  mCounters.batches += 1, mCounters.jobs += s->n_jobs, mCounters.pairs += static_cast<std::uint64_t>(s->pairs);
+  mCounters.h2d_bytes += s->in.slab_bytes;
+  if (s->n_jobs > mCounters.max_jobs_in_batch) mCounters.max_jobs_in_batch = s->n_jobs;
+}
+
+void GenotypeBatcher::Complete(Slab* s) {
+  const std::uint64_t t0 = NowNs();
+  lgr_stats st{};
+  ResultBlock* r = s->res;
+  if (s->ticket >= 0) {
+    r->rc = lgr_wait(mCtx, s->ticket, &st);  // the stream has drained: returns at once (except for the rare overflow pass)
+    if (r->rc != LGR_OK) {
+      const char* detail = lgr_last_error(mCtx);
+      r->err = std::string(lgr_strerror(r->rc)) + (detail && *detail ? std::string(": ") + detail : std::string());
+    }
+  }
+  const std::uint64_t t1 = NowNs();
+  {
+    std::lock_guard<std::mutex> lk(mMu);
+    r->done = true;
+    mCounters.ns_wait += t1 - t0;
+    mCounters.d2h_bytes += static_cast<std::uint64_t>(st.d2h_bytes);
+    // the staging slab is free again; the result block stays with the tickets
+    s->used = 0, s->n_jobs = 0, s->pairs = 0, s->n_assign = 0, s->ticket = -1, s->lingered = false, s->res = nullptr;
+    mFree.push_back(s);
+  }
+  mDoneCv.notify_all();
+  mFreeCv.notify_all();
+}
+
+void GenotypeBatcher::Run() {
+  std::unique_lock<std::mutex> lk(mMu);
+  for (;;) {
+    // batches whose device work has finished (tickets may finish out of order: each has its own stream)
+    bool progressed = false;
+    for (auto it = mInFlight.begin(); it != mInFlight.end();) {
+      Slab* s = *it;
+      if (s->ticket < 0 || (mDeviceDone & (1u << s->ticket))) {
+        if (s->ticket >= 0) mDeviceDone &= ~(1u << s->ticket);
+        it = mInFlight.erase(it);
+        lk.unlock();
+        Complete(s);
+        lk.lock();
+        progressed = true;
+        break;  // the deque may have changed while unlocked
+      }
+      ++it;
+    }
+    if (progressed) continue;
+    if (mInFlight.size() < static_cast<std::size_t>(mOpt.depth)) {
+      Slab* s = nullptr;
+      if (!mSealable.empty()) {
+        s = mSealable.front();
+        mSealable.pop_front();
+      } else if (mOpen && mOpen->n_jobs > 0) {
+        // give the other workers a moment to join this launch, once per slab, unless it already fills the GPU
+        if (mOpt.linger_us > 0 && !mStop && !mOpen->lingered && mOpen->pairs < 65536) {
+          mOpen->lingered = true;
+          mCv.wait_for(lk, std::chrono::microseconds(mOpt.linger_us));
+          continue;
+        }
+        s = mOpen;
+        mOpen = nullptr;
+      }
+      if (s) {
+        lk.unlock();
+        SealAndSubmit(s);
+        lk.lock();
+        mInFlight.push_back(s);
+        continue;
+      }
+    }
+    if (mStop && mInFlight.empty() && mSealable.empty() && (!mOpen || mOpen->n_jobs == 0)) break;
+    mCv.wait(lk);
+  }
+}
+
+// one payload in a device batch of its own, synchronously (after a device-side cap hit it inside a shared batch)
+std::vector<lgr_assign> GenotypeBatcher::RunAlone(const GenotypeJob& job, std::int32_t mid_occ) {
+  PackScratch sc;
+  lgr_group_desc desc;
+  DescribeJob(job, sc, &desc);
+  desc.mid_occ = mid_occ;
+  const lgr_pack::Plan plan = lgr_pack::plan_group(&desc);
+  std::vector<std::uint64_t> buf((plan.bytes + sizeof(lgr_group_dir) + 64) / 8 + 1);
+  lgr_group_dir dir{};
+  if (lgr_pack::pack_group(&desc, plan, buf.data(), &dir) != LGR_OK) throw std::runtime_error("lancet_gpu::GenotypeBatcher: packing failed");
+  dir.rec_off = 0;
+  std::vector<lgr_assign> assign(job.n_reads * job.n_variants + 1);
+  lgr_packed_in in{};
+  in.n_groups = 1, in.slab = buf.data(), in.slab_bytes = plan.bytes, in.dir = &dir;
+  lgr_batch_out out{};
+  out.n_assign = static_cast<std::int64_t>(job.n_reads * job.n_variants), out.assign = assign.data();
+  std::lock_guard<std::mutex> lk(mAuxMu);
+  Check(mAuxCtx, lgr_genotype_packed(mAuxCtx, &in, &out, nullptr));
+  return assign;
+}
+
+const lgr_assign* GenotypeBatcher::WaitAssign(Ticket& t, std::vector<lgr_assign>* retry_storage) {
+  ResultBlock* r = t.res;
+  if (!r) throw std::runtime_error("lancet_gpu::GenotypeBatcher: empty ticket");
+  {
+    std::unique_lock<std::mutex> lk(mMu);
+    mDoneCv.wait(lk, [&] { return r->done; });
+  }
+  if (r->rc == LGR_OK || (r->rc == LGR_E_PARTIAL && r->status[t.slot] == LGR_OK)) return r->assign + r->job_asg[t.slot];
+  if (r->rc == LGR_E_PARTIAL) {  // a device-side cap hit THIS payload inside the shared batch: once more, alone
+    {
+      std::lock_guard<std::mutex> lk(mMu);
+      ++mCounters.retried_alone;
+    }
+    *retry_storage = RunAlone(t.job, r->job_mid[t.slot]);
+    return retry_storage->data();
+  }
+  throw std::runtime_error("lancet_gpu::GenotypeBatcher: " + r->err);
+}
+
+void GenotypeBatcher::Release(Ticket& t) {
+  ResultBlock* r = t.res;
+  if (!r) return;
+  t.res = nullptr;
+  std::lock_guard<std::mutex> lk(mMu);
+  if (--r->refs == 0) {
+    r->done = false, r->rc = LGR_OK, r->err.clear();
+    mFreeResults.push_back(r);
+  }
+}
+
 Result GenotypeBatcher::Collect(Ticket& ticket) {
-  const std::vector<lgr_assign> assign = ticket.done.get();  // rethrows a device error on this thread
-  // AddToTable on the collecting thread: the serial batcher thread only moves bytes
-  return PackedBatch::BuildResult(ticket.job, assign.data(), mNameHash);
+  struct Guard {
+    GenotypeBatcher* b;
+    Ticket* t;
+    ~Guard() { b->Release(*t); }
+  } guard{this, &ticket};
+  std::vector<lgr_assign> retry;
+  const lgr_assign* assign = WaitAssign(ticket, &retry);  // throws for this payload only
+  const std::uint64_t t0 = NowNs();
+  // AddToTable on the collecting thread, reading the records in place from the pinned result block
+  Result res = PackedBatch::BuildResult(ticket.job, assign, mNameHash);
+  const std::uint64_t t1 = NowNs();
+  {
+    std::lock_guard<std::mutex> lk(mMu);
+    mCounters.ns_deliver += t1 - t0;
+  }
+  return res;
 }
 
 Result GenotypeBatcher::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
@@ -426,103 +819,12 @@ GenotypeBatcher::Counters GenotypeBatcher::Stats() {
   return mCounters;
 }
 
-static std::uint64_t NowNs() {
-  return static_cast<std::uint64_t>(
-      std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count());
-}
-
-void GenotypeBatcher::Complete(Slot& s) {
-  std::exception_ptr err;
-  const std::uint64_t t0 = NowNs();
-  try {
-    Check(mCtx, lgr_wait(mCtx, s.ticket, nullptr));
-  } catch (...) {
-    err = std::current_exception();
-  }
-  const std::uint64_t t1 = NowNs();
-  s.ticket = -1;
-  for (std::size_t j = 0; j < s.jobs.size(); ++j) {
-    Pending& p = s.jobs[j];
-    if (err) {
-      p.done.set_exception(err);
-      continue;
-    }
-    const lgr_assign* a = s.pb.JobAssign(j);
-    p.done.set_value(std::vector<lgr_assign>(a, a + p.job.n_reads * p.job.n_variants));
-  }
-  s.jobs.clear();
-  const std::uint64_t t2 = NowNs();
-  std::lock_guard<std::mutex> lk(mMu);
-  mCounters.ns_wait += t1 - t0, mCounters.ns_deliver += t2 - t1;
-}
-
-void GenotypeBatcher::Run() {
-  std::size_t head = 0, tail = 0, inflight = 0;  // slots [tail, head) hold submitted batches
-  for (;;) {
-    std::vector<Pending> take;
-    {
-      std::unique_lock<std::mutex> lk(mMu);
-      if (inflight == 0) {
-        mCv.wait(lk, [&] { return mStop || !mQueue.empty(); });
-        if (mQueue.empty()) break;  // stop requested and nothing left
-        // the GPU is idle: give the other workers a moment to arrive so they share the launch
-        if (mOpt.linger_us > 0 && !mStop)
-          mCv.wait_for(lk, std::chrono::microseconds(mOpt.linger_us), [&] { return mStop || mQueue.size() >= mOpt.max_jobs; });
-      }
-      std::int64_t pairs = 0;
-      while (!mQueue.empty() && take.size() < mOpt.max_jobs) {
-        const GenotypeJob& j = mQueue.front().job;
-        const std::int64_t p = static_cast<std::int64_t>(j.n_reads) * static_cast<std::int64_t>(j.n_haps);
-        if (!take.empty() && pairs + p > mOpt.max_pairs) break;
-        pairs += p;
-        take.push_back(std::move(mQueue.front()));
-        mQueue.pop_front();
-      }
-      if (!take.empty()) {
-        mCounters.batches += 1, mCounters.jobs += take.size(), mCounters.pairs += static_cast<std::uint64_t>(pairs);
-        if (take.size() > mCounters.max_jobs_in_batch) mCounters.max_jobs_in_batch = take.size();
-      }
-    }
-    if (take.empty()) {  // nothing new to pack: hand the oldest batch back as soon as it is done
-      Complete(*mSlots[tail % mSlots.size()]);
-      ++tail, --inflight;
-      continue;
-    }
-    if (inflight == mSlots.size()) {
-      Complete(*mSlots[tail % mSlots.size()]);
-      ++tail, --inflight;
-    }
-    Slot& s = *mSlots[head % mSlots.size()];
-    s.jobs = std::move(take);
-    try {
-      std::vector<GenotypeJob> jobs;
-      jobs.reserve(s.jobs.size());
-      for (const Pending& p : s.jobs) jobs.push_back(p.job);
-      LatchMidOcc(mCtx, mParams, jobs.data(), jobs.size(), &mLatchedMidOcc);
-      const std::uint64_t t0 = NowNs();
-      std::vector<const PackedJob*> packed;
-      packed.reserve(s.jobs.size());
-      for (const Pending& p : s.jobs) packed.push_back(p.packed.get());
-      s.pb.PackPrepared(packed.data(), packed.size(), mLatchedMidOcc);
-      for (Pending& p : s.jobs) p.packed.reset();
-      const std::uint64_t t1 = NowNs();
-      Check(mCtx, lgr_submit(mCtx, &s.pb.In(), &s.pb.Out(), &s.ticket));
-      const std::uint64_t t2 = NowNs();
-      ++head, ++inflight;
-      std::lock_guard<std::mutex> lk(mMu);
-      mCounters.ns_pack += t1 - t0, mCounters.ns_submit += t2 - t1;
-    } catch (...) {
-      for (Pending& p : s.jobs) p.done.set_exception(std::current_exception());
-      s.jobs.clear();
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // GenotypeDispatcher
 // ---------------------------------------------------------------------------------------------
 GenotypeDispatcher::GenotypeDispatcher(const std::vector<int>& devices, NameHashFn name_hash, GenotypeBatcher::Options base) {
   if (devices.empty()) throw std::runtime_error("lancet_gpu::GenotypeDispatcher: no devices given (there is no CPU fallback)");
+  mUid = g_latch_uid.fetch_add(1);
   mOutstanding = std::make_unique<std::atomic<std::int64_t>[]>(devices.size());
   for (std::size_t i = 0; i < devices.size(); ++i) {
     base.device = devices[i];
@@ -537,7 +839,11 @@ std::int64_t GenotypeDispatcher::Cost(const GenotypeJob& job) {
   return static_cast<std::int64_t>(job.n_reads) * hap_total + 1;
 }
 
-GenotypeDispatcher::Ticket GenotypeDispatcher::Enqueue(const GenotypeJob& job) {
+GenotypeDispatcher::Ticket GenotypeDispatcher::Enqueue(const GenotypeJob& job_in) {
+  // the calling thread's mm_mapopt_update latch belongs to the dispatcher, not to the device a payload
+  // happens to be routed to: results do not depend on the routing
+  GenotypeJob job = job_in;
+  if (!job.mid_occ_latch) job.mid_occ_latch = ThreadLatch(mUid);
   std::size_t best = 0;
   std::int64_t best_load = mOutstanding[0].load(std::memory_order_relaxed);
   for (std::size_t i = 1; i < mBatchers.size(); ++i) {

@@ -123,6 +123,9 @@ struct GenotypeJob {
   std::size_t n_reads;
   const VariantIn* variants;
   std::size_t n_variants;
+  // mm_mapopt_update's latch (genotyper.cpp:263-266) of the logical worker this payload belongs to:
+  // 0 = not latched yet (set from this payload's REF haplotype), NULL = the calling thread's own latch
+  std::int32_t* mid_occ_latch = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -253,24 +256,46 @@ class GpuGenotyper {
 
 // Cross-thread batcher: the reference runs one Genotyper per worker thread
 // (core/variant_builder.h:94, core/pipeline_executor.cpp:174-197) and each Genotype() call
-// carries only ~10^3-10^4 pairs.  One GenotypeBatcher per GPU lets all workers share the device:
-// Genotype() has the reference's blocking call shape, but the payloads of every thread that is
-// waiting at that moment travel in ONE device batch (lgr_submit), up to `depth` batches in
-// flight so that packing/H2D of one overlaps the kernels of another; AddToTable runs on the
-// calling worker when its slice of the assignments is back.
+// carries only ~10^3-10^4 pairs.  One GenotypeBatcher per GPU lets all workers share the device.
+//
+// Data path (north_star: "batches (read, haplotype) pairs across many windows into ... 2-bit-packed
+// SoA buffers"): the ENQUEUING worker packs its payload once, straight into the pinned slab that is
+// currently being filled (lgr_pack.h: bit planes, quality dictionary, ExtractHapBounds' table, X31
+// name hashes) — a reservation under the lock, the packing itself outside it.  The batcher thread
+// only seals a slab (appends the directory) and hands it to lgr_submit_packed: ONE host→device copy
+// per device batch, every derived array built on the device.  Up to `depth` slabs are in flight;
+// completion arrives through lgr_set_notify (no polling).  The collecting worker reads its
+// lgr_assign records in place from the slab's pinned result block and runs AddToTable; the slab
+// returns to the pool when its last payload has been collected.
+//
+// Failure isolation (mm_map never refuses, genotyper.cpp:387-393; an exception terminates Lancet2,
+// core/async_worker.cpp:73-97): a payload beyond the device path's static caps throws in ITS
+// Enqueue and never joins a batch; a device-side cap that hits one payload's pairs is reported per
+// group (lgr_batch_out::grp_status), that payload alone is re-run in a batch of its own, and only if
+// that fails too does its Collect throw.  Every other payload of the batch is unaffected.
+//
+// mid_occ latch (mm_mapopt_update, genotyper.cpp:263-266): the reference latches per Genotyper, i.e.
+// per worker thread, from the first REF haplotype that worker sees.  Here the latch is per CALLING
+// THREAD (or per explicit GenotypeJob::mid_occ_latch), computed once from that thread's first
+// payload — independent of how payloads from different threads meet in a device batch and of the
+// GPU they are routed to, hence deterministic for a deterministic window-to-worker schedule.
 class GenotypeBatcher {
  public:
   struct Options {
     int device = 0;
-    int depth = 3;                       // batches in flight (<= LGR_MAX_INFLIGHT)
+    int depth = 3;                       // device batches in flight (<= LGR_MAX_INFLIGHT)
     std::int64_t max_pairs = 1 << 21;    // (read, haplotype) pairs per device batch
     std::size_t max_jobs = 8192;         // Genotype() payloads per device batch
     int linger_us = 100;                 // idle GPU: wait this long for more workers to arrive before launching
+    std::size_t slab_bytes = 32u << 20;  // pinned staging per slab (grown when one payload needs more)
     const lgr_params* params = nullptr;
   };
   struct Counters {
-    std::uint64_t batches = 0, jobs = 0, pairs = 0, max_jobs_in_batch = 0;
-    std::uint64_t ns_pack = 0, ns_submit = 0, ns_wait = 0, ns_deliver = 0;  // batcher-thread time per stage
+    std::uint64_t batches = 0, jobs = 0, pairs = 0, max_jobs_in_batch = 0, retried_alone = 0, h2d_bytes = 0, d2h_bytes = 0;
+    std::uint64_t ns_pack = 0;     // worker time: sizing + packing into the slab (summed over workers)
+    std::uint64_t ns_submit = 0;   // batcher thread: seal + lgr_submit_packed
+    std::uint64_t ns_wait = 0;     // batcher thread: lgr_wait (statistics, rare overflow pass)
+    std::uint64_t ns_deliver = 0;  // worker time: AddToTable (summed over workers)
   };
   GenotypeBatcher(const Options& opt, NameHashFn name_hash);
   ~GenotypeBatcher();  // drains what is queued, then joins
@@ -282,41 +307,54 @@ class GenotypeBatcher {
                                 const VariantIn* variants, std::size_t n_variants);
 
   // The two halves of Genotype() for a caller that has split ProcessWindow:
-  // Enqueue returns at once, the worker goes on to assemble its next window, and Collect (on any
-  // thread) waits for the device and runs AddToTable.  The job's buffers are borrowed until
+  // Enqueue packs and returns at once, the worker goes on to assemble its next window, and Collect
+  // (on any thread) waits for the device and runs AddToTable.  The job's buffers are borrowed until
   // Collect returns.  With many windows enqueued per worker the batches fill the GPU.
+  struct Slab;
+  struct ResultBlock;
   struct Ticket {
     GenotypeJob job{};
-    std::future<std::vector<lgr_assign>> done;
+    ResultBlock* res = nullptr;
+    std::uint32_t slot = 0;
   };
   [[nodiscard]] Ticket Enqueue(const GenotypeJob& job);
   [[nodiscard]] Result Collect(Ticket& ticket);
+  // the lgr_assign records of a ticket ([read][variant]) without AddToTable; valid until Release
+  [[nodiscard]] const lgr_assign* WaitAssign(Ticket& ticket, std::vector<lgr_assign>* retry_storage);
+  void Release(Ticket& ticket);
   [[nodiscard]] Counters Stats();
+  [[nodiscard]] const lgr_params& Params() const noexcept { return mParams; }
 
  private:
-  struct Pending {
-    GenotypeJob job;
-    std::unique_ptr<PackedJob> packed;  // built by the enqueuing thread
-    std::promise<std::vector<lgr_assign>> done;
-  };
-  struct Slot {
-    PackedBatch pb;
-    std::vector<Pending> jobs;
-    lgr_ticket ticket = -1;
-  };
   void Run();
-  void Complete(Slot& s);
+  void SealAndSubmit(Slab* s);
+  void Complete(Slab* s);
+  Slab* TakeFreeSlabLocked(std::unique_lock<std::mutex>& lk, std::size_t need_bytes);
+  static void GrowSlab(Slab* s, std::size_t need_bytes);
+  std::int32_t LatchFor(const GenotypeJob& job);
+  std::vector<lgr_assign> RunAlone(const GenotypeJob& job, std::int32_t mid_occ);
+  static void OnDeviceDone(void* self, lgr_ticket ticket);
   Options mOpt;
   NameHashFn mNameHash;
-  lgr_ctx* mCtx = nullptr;
+  lgr_ctx* mCtx = nullptr;       // batcher thread only
+  lgr_ctx* mAuxCtx = nullptr;    // latch computation and single-payload re-runs, under mAuxMu
+  std::mutex mAuxMu;
   lgr_params mParams;
-  std::int32_t mLatchedMidOcc = 0;
+  std::uint64_t mUid = 0;        // key of the per-thread latch
   std::mutex mMu;
-  std::condition_variable mCv;
-  std::deque<Pending> mQueue;
+  std::condition_variable mCv;       // batcher thread: work arrived / a batch finished on the device
+  std::condition_variable mFreeCv;   // workers waiting for a free slab
+  std::condition_variable mDoneCv;   // workers waiting for their slab's results
+  std::vector<std::unique_ptr<Slab>> mSlabs;
+  std::vector<Slab*> mFree;
+  std::vector<std::unique_ptr<ResultBlock>> mResults;
+  std::vector<ResultBlock*> mFreeResults;
+  Slab* mOpen = nullptr;             // the slab being filled
+  std::deque<Slab*> mSealable;       // full slabs waiting for a device slot, in order
+  std::deque<Slab*> mInFlight;       // submitted, oldest first
+  std::uint32_t mDeviceDone = 0;     // tickets whose device work has finished (bit per ticket)
   bool mStop = false;
   Counters mCounters;
-  std::vector<std::unique_ptr<Slot>> mSlots;
   std::thread mThread;
 };
 
@@ -345,6 +383,7 @@ class GenotypeDispatcher {
  private:
   std::vector<std::unique_ptr<GenotypeBatcher>> mBatchers;
   std::unique_ptr<std::atomic<std::int64_t>[]> mOutstanding;
+  std::uint64_t mUid = 0;  // key of the per-thread mid_occ latch
 };
 
 }  // namespace lancet_gpu

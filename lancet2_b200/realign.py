@@ -22,7 +22,7 @@ class LgrError(RuntimeError):
 class GpuRealigner:
     def __init__(self, device: int = 0, params: Optional[abi.LgrParams] = None, lib_path: Optional[str] = None):
         self.lib = abi.load_library(lib_path)
-        if self.lib.lgr_abi_version() != 1:
+        if self.lib.lgr_abi_version() != 2:
             raise RuntimeError("ABI version mismatch")
         if params is None:
             params = abi.LgrParams()
@@ -45,7 +45,9 @@ class GpuRealigner:
         except Exception:
             pass
 
-    def _check(self, rc: int):
+    def _check(self, rc: int, partial_ok: bool = False):
+        if rc == abi.LGR_E_PARTIAL and partial_ok:
+            return
         if rc != 0:
             raise LgrError(rc, (self.lib.lgr_last_error(self._ctx) or b"").decode() or self.lib.lgr_strerror(rc).decode())
 
@@ -55,15 +57,19 @@ class GpuRealigner:
         return out.value
 
     def genotype_batch(self, batch: abi.Batch, result: Optional[abi.Result] = None, want_aln: bool = True,
-                       arena: int = 1 << 20) -> Tuple[abi.Result, abi.LgrStats]:
-        """H2D + kernels + D2H through `lgr_genotype_batch` (the call a Genotyper adapter makes)."""
+                       arena: int = 1 << 20, group_status: bool = False) -> Tuple[abi.Result, abi.LgrStats]:
+        """H2D + kernels + D2H through `lgr_genotype_batch` (the call a Genotyper adapter makes).
+        group_status: ask for lgr_batch_out::grp_status; a batch in which some groups hit a device cap
+        then returns normally with `res.rc == LGR_E_PARTIAL` and the per-group codes in `res.grp_status`."""
         res = result or abi.Result(batch, arena)
+        res.want_grp_status = group_status
         bi, bo = batch.c_struct(), res.c_struct()
         if not want_aln:
             bo.aln = None
             bo.cigar_inline = None
         st = abi.LgrStats()
-        self._check(self.lib.lgr_genotype_batch(self._ctx, C.byref(bi), C.byref(bo), C.byref(st)))
+        res.rc = self.lib.lgr_genotype_batch(self._ctx, C.byref(bi), C.byref(bo), C.byref(st))
+        self._check(res.rc, partial_ok=group_status)
         return res, st
 
     def submit(self, batch: abi.Batch, result: Optional[abi.Result] = None, want_aln: bool = True,
@@ -79,6 +85,34 @@ class GpuRealigner:
         self._check(self.lib.lgr_submit(self._ctx, C.byref(bi), C.byref(bo), C.byref(t)))
         self._inflight[t.value] = (batch, res, bi, bo)  # keep every host buffer alive until wait()
         return t.value, res
+
+    def genotype_packed(self, packed: "abi.PackedBatch", batch: abi.Batch, result: Optional[abi.Result] = None,
+                        want_aln: bool = True, arena: int = 1 << 20) -> Tuple[abi.Result, abi.LgrStats]:
+        """the same call on the packed wire format (`batch` only sizes the result buffers)"""
+        res = result or abi.Result(batch, arena)
+        pi, bo = packed.c_struct(), res.c_struct()
+        if not want_aln:
+            bo.aln = None
+            bo.cigar_inline = None
+        st = abi.LgrStats()
+        self._check(self.lib.lgr_genotype_packed(self._ctx, C.byref(pi), C.byref(bo), C.byref(st)))
+        return res, st
+
+    def submit_packed(self, packed: "abi.PackedBatch", batch: abi.Batch, result: Optional[abi.Result] = None,
+                      want_aln: bool = True, arena: int = 1 << 20) -> Tuple[int, abi.Result]:
+        res = result or abi.Result(batch, arena)
+        pi, bo = packed.c_struct(), res.c_struct()
+        if not want_aln:
+            bo.aln = None
+            bo.cigar_inline = None
+        t = C.c_int32(-1)
+        self._check(self.lib.lgr_submit_packed(self._ctx, C.byref(pi), C.byref(bo), C.byref(t)))
+        self._inflight[t.value] = (packed, res, pi, bo)
+        return t.value, res
+
+    def upload_packed(self, packed: "abi.PackedBatch"):
+        pi = packed.c_struct()
+        self._check(self.lib.lgr_upload_packed(self._ctx, C.byref(pi)))
 
     def wait(self, ticket: int) -> abi.LgrStats:
         st = abi.LgrStats()

@@ -32,7 +32,7 @@ extern "C" int emu_genotype_batch(const lgr_params* prm, const lgr_batch_in* in,
                                   int small_only_inline) {
   using namespace lgr;
   const DevParams P = MakeDev(*prm);
-  const int cap = 1 << 15;
+  const int cap = 65535;  // the 16-bit positions of Ws / RadixScratch
   std::vector<int32_t> wsbuf((size_t)A_COUNT * cap);
   Ws<1> ws{wsbuf.data(), cap};
   RadixScratch rsx;

@@ -12,11 +12,42 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liblancet_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "liblancet_ref_scoring.so")
 
+NATIVE_SO = os.path.join(ORACLE_DIR, "_native", "liblancet_oracle_native.so")
+NATIVE_FLAGS = "-O3 -march=native -std=c++17 -fPIC -ffp-contract=off -pthread"
+PORTABLE_FLAGS = "-O2 -std=c++17 -fPIC -ffp-contract=off -pthread"
+
 _lib = None
+_native = None
 
 
 def build_oracle():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liblancet_oracle.so"])
+
+
+def load_native_oracle():
+    """The oracle compiled ON THIS HOST with -O3 -march=native (SURVEY.md §8d asks for that build as the
+    CPU baseline).  The portable -O2 library travels with the repo; a -march=native binary cannot
+    (the build container and the GPU box have different CPUs), so it is built where it runs, into
+    oracle/_native/ (git-ignored).  Returns (lib, flags); falls back to the portable build."""
+    global _native
+    if _native is not None:
+        return _native
+    try:
+        srcs = [os.path.join(ORACLE_DIR, f) for f in ("mm2_restate.cpp", "genotype_oracle.cpp")]
+        newest = max(os.path.getmtime(x) for x in srcs + [os.path.join(ORACLE_DIR, "mm2_restate.hpp")])
+        marker = NATIVE_SO + ".host"
+        host = open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0] if os.path.exists("/proc/cpuinfo") else ""
+        if (not os.path.exists(NATIVE_SO) or os.path.getmtime(NATIVE_SO) < newest or not os.path.exists(marker)
+                or open(marker).read() != host):
+            os.makedirs(os.path.dirname(NATIVE_SO), exist_ok=True)
+            subprocess.check_call(["g++"] + NATIVE_FLAGS.split() + ["-shared", "-o", NATIVE_SO] + srcs,
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            with open(marker, "w") as fh:
+                fh.write(host)
+        _native = (_bind(C.CDLL(NATIVE_SO)), NATIVE_FLAGS)
+    except Exception:  # noqa: BLE001 — no compiler on the box: the portable build is still a valid baseline
+        _native = (load_oracle(), PORTABLE_FLAGS)
+    return _native
 
 
 def load_oracle() -> C.CDLL:
@@ -25,7 +56,11 @@ def load_oracle() -> C.CDLL:
         return _lib
     if not os.path.exists(ORACLE_SO):
         build_oracle()
-    lib = C.CDLL(ORACLE_SO)
+    _lib = _bind(C.CDLL(ORACLE_SO))
+    return _lib
+
+
+def _bind(lib):
     lib.orc_genotype_batch.argtypes = [C.POINTER(abi.LgrParams), C.POINTER(abi.LgrBatchIn),
                                        C.POINTER(abi.LgrBatchOut), C.c_int, C.POINTER(abi.LgrStats)]
     lib.orc_genotype_batch.restype = C.c_int
@@ -58,7 +93,6 @@ def load_oracle() -> C.CDLL:
     lib.orc_lancet_encode.restype = C.c_uint8
     lib.orc_x31_hash.argtypes = [C.c_char_p]
     lib.orc_x31_hash.restype = C.c_uint32
-    _lib = lib
     return lib
 
 
@@ -68,8 +102,8 @@ def default_params() -> abi.LgrParams:
     return p
 
 
-def oracle_genotype(batch: abi.Batch, params: abi.LgrParams = None, n_threads: int = 1, arena: int = 1 << 20):
-    lib = load_oracle()
+def oracle_genotype(batch: abi.Batch, params: abi.LgrParams = None, n_threads: int = 1, arena: int = 1 << 20, lib=None):
+    lib = lib or load_oracle()
     params = params or default_params()
     res = abi.Result(batch, arena)
     bi, bo = batch.c_struct(), res.c_struct()

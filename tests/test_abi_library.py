@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(abi.declared_symbols())
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.lgr_abi_version() == 1
+    assert lib.lgr_abi_version() == 2
 
 
 def test_struct_layouts_match_header(lib):

@@ -203,3 +203,62 @@ def test_cross_thread_batcher_equals_synchronous_adapter(lib):
     assert buf4.value == buf1.value
     per_dev = [int(x) for x in counters[9:9 + n_dev]]
     assert sum(per_dev) == rounds * len(groups) and all(x > 0 for x in per_dev), per_dev
+
+
+def _meta(rng, groups, batch):
+    nr = batch.n_reads
+    names = [nm for g in groups for nm in g.names]
+    sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
+    start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
+    isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
+    flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
+    mapq = rng.integers(0, 61, nr).astype(np.uint8)
+    softclip = rng.integers(0, 2, nr).astype(np.uint8)
+    blob = b"\0".join(x.encode() for x in names) + b"\0"
+    return names, blob, (sample_id, start0, isize, flag, mapq, softclip)
+
+
+@pytest.mark.gpu
+def test_batcher_isolates_a_failing_payload(lib):
+    """One bad window must not take its batch-mates down (mm_map never refuses, genotyper.cpp:387-393;
+    an exception terminates Lancet2, core/async_worker.cpp:73-97): (i) a payload beyond the static caps
+    throws in its own Enqueue; (ii) a payload that hits a device-side cap inside a shared batch is
+    re-run alone and only its own Collect throws.  Every other payload's evidence equals the one-shot
+    adapter's on the healthy groups."""
+    from test_gpu_packed import homopolymer_group
+    lib.lgr_adapter_isolation_dump.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + [C.c_void_p] * 6 + \
+        [C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong]
+    lib.lgr_adapter_isolation_dump.restype = C.c_int
+    rng = np.random.default_rng(23)
+    ok = synth.make_groups(31, 5, n_reads=60, n_haps=3, hap_len=600)
+    long_read = abi.Group(haps=[b"ACGT" * 200], reads=[b"ACGT" * 500], quals=[b"\x1e" * 2000], names=["n_long"], variants=[])
+    hp = homopolymer_group(rng, 1200, 2, read_len=1000, flank=200)
+    cap_hit = abi.Group(haps=hp.haps, reads=[hp.haps[0][195:1195]], quals=[bytes([30] * 1000)], names=["n_bad"], variants=hp.variants)
+
+    def run(groups, mid_occ):
+        batch = abi.Batch(groups)
+        names, blob, cols = _meta(np.random.default_rng(1), groups, batch)
+        status = np.full(len(groups), -1, dtype=np.int32)
+        ctr = np.zeros(2, dtype=np.uint64)
+        buf = C.create_string_buffer(64 << 20)
+        bi = batch.c_struct()
+        n = lib.lgr_adapter_isolation_dump(0, C.byref(bi), blob, b"normal\0tumor\0", *[c.ctypes.data for c in cols], mid_occ,
+                                           status.ctypes.data, ctr.ctypes.data, buf, len(buf))
+        assert n >= 0, buf.value.decode()
+        per_group = {}
+        for line in buf.value.decode().splitlines():
+            g, rest = line.split(" ", 1)
+            per_group.setdefault(int(g[1:]), []).append(rest)
+        return status.tolist(), per_group, ctr
+
+    # (i) static cap: refused at Enqueue, alone
+    st, got, _ = run([ok[0], long_read, ok[1], ok[2]], 0)
+    assert st == [0, 1, 0, 0]
+    _, want, _ = run([ok[0], ok[1], ok[2]], 0)
+    assert got[0] == want[0] and got[2] == want[1] and got[3] == want[2] and 1 not in got
+    # (ii) device-side cap (> 65,535 anchors under a huge mid_occ): the batch is a partial success, the offender is
+    # re-run alone, fails again and throws from its own Collect; the rest is untouched
+    st, got, ctr = run([ok[3], cap_hit, ok[4]], 1000000)
+    assert st == [0, 2, 0] and int(ctr[0]) == 1 and int(ctr[1]) == 1
+    _, want, _ = run([ok[3], ok[4]], 1000000)
+    assert got[0] == want[0] and got[2] == want[1] and len(want[0]) > 0
