@@ -14,7 +14,7 @@ __constant__ double c_phred_err[256] = {
 // counters (int64 slots in device memory)
 enum Ctr {
   C_ITEM = 0, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
-  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_OVFNEED, C_COUNT
+  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_OVFNEED, C_NCOLD, C_COLDPOS, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
@@ -77,6 +77,7 @@ struct Dev {      // everything the kernels need, passed by value
   TaskRec* tasks; int64_t tasks_cap;
   uint32_t* ext_arena; int64_t ext_arena_cap;
   int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
+  int32_t* cold_read; int32_t* cold_hap;   // [n_pairs] pairs the hot chain kernel left to k_chain_cold
   // k_ext_big scratch
   uint8_t* dir_scratch; int64_t dir_per_warp;
   int32_t* bnd_scratch; int64_t bnd_per_warp;   // Hb/Fb boundary rows

@@ -52,9 +52,10 @@ namespace {
 // =========================================================================================
 // host side
 // =========================================================================================
-struct DevBuf {
+struct DevBuf {   // a device buffer: either its own cudaMalloc block (arena, overflow workspace) or a view into the arena
   void* p = nullptr;
   size_t cap = 0;
+  size_t off = 0;  // offset in the context's arena (views)
 };
 
 }  // namespace
@@ -67,21 +68,26 @@ struct lgr_ctx {
   DevParams P;
   std::string err;
   int sm_count = 0;
-  // grow-only device buffers
-  std::vector<DevBuf*> all;
+  // ONE grow-only device arena per context; every per-batch buffer below is a view into it, laid out
+  // afresh by plan_batch.  A batch larger than any before costs one cudaFree + one cudaMalloc (cudaFree
+  // synchronises the whole device; sixty separately growing buffers made that sixty stalls per regrow
+  // and dominated the batcher's submit time in the first round-2 measurement).
+  DevBuf arena;
+  size_t arena_off = 0;
+  std::vector<DevBuf*> views;
   DevBuf b_grp_hap, b_grp_read, b_grp_var, b_hap_off, b_read_off, b_var_hap_off, b_hap_bases, b_read_bases, b_read_quals,
       b_name_hash, b_var_start, b_var_len, b_var_allele, b_read_grp, b_hap_grp, b_pair_off, b_asg_off, b_item_hap, b_item_r0,
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
       b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
       b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks, b_grp_mid_req, b_grp_err, b_slab, b_dir_tab, b_grp_hapbase,
-      b_grp_readbase, b_grp_vh, b_grp_pair, b_grp_asg, b_grp_item;
+      b_grp_readbase, b_grp_vh, b_grp_pair, b_grp_asg, b_grp_item, b_cold_read, b_cold_hap;
   Dev D;
   bool resident = false, packed = false;
   int occ_cap = 0, warp_blocks_full = 0, ext_blocks_full = 0, fin_blocks_full = 0, overflow_passes = 0;
   int max_read_len = 0, max_hap_len = 0;
   int64_t hap_bytes = 0, read_bytes = 0;
-  int ext_blocks = 0, fin_blocks = 0, warp_blocks = 0, warp_cap = 64;
-  size_t warp_smem = 0;
+  int ext_blocks = 0, fin_blocks = 0, warp_blocks = 0, cold_blocks = 0, cold_blocks_full = 0, warp_cap = 64;
+  size_t warp_smem = 0, cold_smem = 0;
   cudaEvent_t ev[12];
   long long* h_ctr = nullptr;  // pinned copy of the device counters
   int launches = 0;
@@ -254,17 +260,8 @@ void lgr_destroy(lgr_ctx* c) {
   }
   cudaSetDevice(c->device);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
-  DevBuf* bufs[] = {&c->b_grp_hap, &c->b_grp_read, &c->b_grp_var, &c->b_hap_off, &c->b_read_off, &c->b_var_hap_off, &c->b_hap_bases,
-                    &c->b_read_bases, &c->b_read_quals, &c->b_name_hash, &c->b_var_start, &c->b_var_len, &c->b_var_allele,
-                    &c->b_read_grp, &c->b_hap_grp, &c->b_pair_off, &c->b_asg_off, &c->b_item_hap, &c->b_item_r0, &c->b_item_n,
-                    &c->b_hap_codes, &c->b_read_codes, &c->b_idx, &c->b_idx_n, &c->b_hap_mid, &c->b_grp_mid, &c->b_mz_x, &c->b_mz_y,
-                    &c->b_mz_n, &c->b_fin, &c->b_regs, &c->b_pair_reg, &c->b_tasks, &c->b_ext_arena, &c->b_ovf_read,
-                    &c->b_ovf_hap, &c->b_dir, &c->b_bnd, &c->b_wcig, &c->b_aln, &c->b_cig_inline, &c->b_cig_arena, &c->b_assign,
-                    &c->b_ctr, &c->b_ws_big, &c->b_wreg, &c->b_rsx, &c->b_bkt, &c->b_mz_cnt, &c->b_grp_mid_req, &c->b_grp_err,
-                    &c->b_slab, &c->b_dir_tab, &c->b_grp_hapbase, &c->b_grp_readbase, &c->b_grp_vh, &c->b_grp_pair, &c->b_grp_asg,
-                    &c->b_grp_item};
-  for (DevBuf* b : bufs)
-    if (b->p) cudaFree(b->p);
+  if (c->arena.p) cudaFree(c->arena.p);
+  if (c->b_ws_big.p) cudaFree(c->b_ws_big.p);
   for (auto& e : c->ev) cudaEventDestroy(e);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -305,6 +302,8 @@ static constexpr int kBigCapMax = 65535;          // anchors per pair the chain 
 
 // everything the buffer plan needs to know about a batch (from lgr_batch_in or from the packed directory)
 struct BatchSizes {
+  bool ascii = true;                       // plain form (ASCII strings) or packed slab
+  size_t slab_bytes = 0, dir_bytes = 0;    // packed form: bytes of the slab / of a directory outside the slab
   int G = 0, NH = 0, NR = 0, NV = 0;
   int64_t hap_bytes = 0, read_bytes = 0, nvh = 0, n_pairs = 0, n_assign = 0, n_items = 0;
   int item_reads = 1, max_read_len = 0, max_hap_len = 0;
@@ -314,8 +313,9 @@ struct BatchSizes {
 // batch fills the machine many times over; a small batch (one Genotype() call) is latency bound
 // instead and wants every pair on its own warp
 static int choose_item_reads(const lgr_ctx* c, int64_t pairs_total) {
+  // a work item is taken by a CTA (4 warps) that stages the haplotype's table once for all its reads
   const int64_t warps_resident = (int64_t)c->sm_count * 36;
-  return pairs_total >= 8 * warps_resident ? kWarpItemReads : (pairs_total >= 3 * warps_resident ? 2 : 1);
+  return pairs_total >= 8 * warps_resident ? kCtaItemReads : (pairs_total >= 3 * warps_resident ? 8 : kWarpsPerCta);
 }
 
 // static caps of the device path for one payload shape; NULL when inside them
@@ -399,7 +399,16 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
   const int64_t hap_bytes = z.hap_bytes, read_bytes = z.read_bytes, nvh = z.nvh, n_pairs = z.n_pairs, n_assign = z.n_assign;
   c->max_read_len = z.max_read_len, c->max_hap_len = z.max_hap_len;
   c->hap_bytes = hap_bytes, c->read_bytes = read_bytes;
-#define ENS(buf, bytes) if ((rc = ensure(c, c->buf, (size_t)(bytes))) != LGR_OK) return rc
+  c->arena_off = 0;
+  c->views.clear();
+  auto take = [&](DevBuf& b, size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    b.off = c->arena_off, b.cap = bytes, b.p = nullptr;
+    c->arena_off += (bytes + 255) & ~(size_t)255;
+    c->views.push_back(&b);
+  };
+#define ENS(buf, bytes) take(c->buf, (size_t)(bytes))
+  (void)rc;
   ENS(b_grp_hap, sizeof(int32_t) * (G + 1)); ENS(b_grp_read, sizeof(int32_t) * (G + 1)); ENS(b_grp_var, sizeof(int32_t) * (G + 1));
   ENS(b_hap_off, sizeof(int64_t) * (NH + 1)); ENS(b_read_off, sizeof(int64_t) * (NR + 1)); ENS(b_var_hap_off, sizeof(int64_t) * (NV + 1));
   ENS(b_read_quals, read_bytes); ENS(b_name_hash, sizeof(uint32_t) * NR);
@@ -418,24 +427,30 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
   const int Tmax = Lm + ((c->prm.a + std::max(c->prm.b, c->prm.sc_ambi)) * Lm) / c->prm.e + 2;
   // warp-per-pair kernel: CAP anchors per pair in shared memory
   c->warp_cap = c->max_read_len <= 160 ? 64 : 128;
-  c->warp_smem = (size_t)kWarpsPerCta * Ws<1>::elems(c->warp_cap, kRegCap) * sizeof(int32_t);
-  if (c->occ_cap != c->warp_cap) {  // occupancy of the three persistent kernels: once per context and shape
-    int per_sm = 0;
-    cudaError_t e1, e2;
+  c->warp_smem = chain_smem_bytes(c->warp_cap, true);
+  c->cold_smem = chain_smem_bytes(c->warp_cap, false);
+  if (c->occ_cap != c->warp_cap) {  // occupancy of the persistent kernels: once per context and shape
+    int per_sm = 0, per_sm_cold = 0;
+    cudaError_t e1, e2, e3, e4;
     if (c->warp_cap == 64) {
       e1 = cudaFuncSetAttribute(k_chain_warp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
       cudaFuncSetAttribute(k_chain_warp<64>, cudaFuncAttributePreferredSharedMemoryCarveout, LGR_CHAIN_CARVEOUT);
       e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_warp<64>, kWarpsPerCta * 32, c->warp_smem);
+      e3 = cudaFuncSetAttribute(k_chain_cold<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cold_smem);
+      e4 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cold, k_chain_cold<64>, kWarpsPerCta * 32, c->cold_smem);
     } else {
       e1 = cudaFuncSetAttribute(k_chain_warp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->warp_smem);
       cudaFuncSetAttribute(k_chain_warp<128>, cudaFuncAttributePreferredSharedMemoryCarveout, LGR_CHAIN_CARVEOUT);
       e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_warp<128>, kWarpsPerCta * 32, c->warp_smem);
+      e3 = cudaFuncSetAttribute(k_chain_cold<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cold_smem);
+      e4 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cold, k_chain_cold<128>, kWarpsPerCta * 32, c->cold_smem);
     }
-    if (e1 != cudaSuccess || e2 != cudaSuccess || per_sm < 1) {
-      c->err = "k_chain_warp does not fit on this device (shared memory / registers)";
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || per_sm < 1 || per_sm_cold < 1) {
+      c->err = "the chain kernels do not fit on this device (shared memory / registers)";
       return LGR_E_CUDA;
     }
     c->warp_blocks_full = c->sm_count * per_sm;
+    c->cold_blocks_full = c->sm_count * per_sm_cold;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ext_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     c->ext_blocks_full = c->sm_count * per_sm;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_finish_warp, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
@@ -443,23 +458,25 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
     c->occ_cap = c->warp_cap;
   }
   // a small batch (one Genotype() call) needs neither the full grids nor their per-warp scratch
-  c->warp_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->warp_blocks_full, (z.n_items + kWarpsPerCta - 1) / kWarpsPerCta));
-  c->ext_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->ext_blocks_full, (n_pairs + 3) / 4));
+  c->warp_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->warp_blocks_full, z.n_items));
+  c->cold_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->cold_blocks_full, (n_pairs + kWarpsPerCta - 1) / kWarpsPerCta));
+  c->ext_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->ext_blocks_full, (n_pairs + 15) / 16));  // ~0.3 queued extensions per pair
   c->fin_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->fin_blocks_full, (n_pairs + 4 * kFinChunk - 1) / (4 * kFinChunk)));
-  const int64_t ext_warps = std::max<int64_t>((int64_t)std::max(c->ext_blocks, c->fin_blocks) * 4, (int64_t)c->warp_blocks * kWarpsPerCta);
+  const int64_t ext_warps = std::max<int64_t>((int64_t)std::max(c->ext_blocks, c->fin_blocks) * 4,
+                                               (int64_t)std::max(c->warp_blocks, c->cold_blocks) * kWarpsPerCta);
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
   const int wcig_cap = 2 * Lm + 8;
   const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024;
   const int64_t ext_arena_cap = 4 * n_pairs + (1 << 20);
   const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
-  ENS(b_wreg, sizeof(RegRec) * (size_t)ext_warps * c->warp_cap);
   ENS(b_rsx, sizeof(RadixScratch) * (size_t)ext_warps);
   ENS(b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap);
   ENS(b_regs, sizeof(RegRec) * (size_t)regs_cap); ENS(b_pair_reg, sizeof(PairReg) * (size_t)n_pairs);
   ENS(b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2);
   ENS(b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap);
   ENS(b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32)); ENS(b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32));
+  ENS(b_cold_read, sizeof(int32_t) * (size_t)(n_pairs + 32)); ENS(b_cold_hap, sizeof(int32_t) * (size_t)(n_pairs + 32));
   ENS(b_dir, (size_t)ext_warps * dir_per_warp);
   ENS(b_bnd, sizeof(int32_t) * (size_t)ext_warps * bnd_per_warp);
   ENS(b_wcig, sizeof(uint32_t) * (size_t)ext_warps * wcig_cap);
@@ -467,6 +484,13 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
   ENS(b_cig_inline, sizeof(uint32_t) * (size_t)n_pairs * LGR_CIGAR_INLINE);
   ENS(b_cig_arena, sizeof(uint32_t) * (size_t)cig_arena_cap);
   ENS(b_assign, sizeof(AssignOut) * (size_t)n_assign); ENS(b_ctr, sizeof(long long) * C_COUNT);
+  // inputs as they arrive: ASCII strings (plain form) or the slab (+ directory, + directory scans) of the packed form
+  ENS(b_hap_bases, z.ascii ? hap_bytes : 0); ENS(b_read_bases, z.ascii ? read_bytes : 0);
+  ENS(b_slab, z.slab_bytes); ENS(b_dir_tab, z.dir_bytes);
+  ENS(b_grp_hapbase, sizeof(int64_t) * (G + 1)); ENS(b_grp_readbase, sizeof(int64_t) * (G + 1)); ENS(b_grp_vh, sizeof(int64_t) * (G + 1));
+  ENS(b_grp_pair, sizeof(int64_t) * (G + 1)); ENS(b_grp_asg, sizeof(int64_t) * (G + 1)); ENS(b_grp_item, sizeof(int32_t) * (G + 1));
+  if ((rc = ensure(c, c->arena, c->arena_off)) != LGR_OK) return rc;
+  for (DevBuf* b : c->views) b->p = static_cast<uint8_t*>(c->arena.p) + b->off;
   Dev& D = c->D;
   std::memset(&D, 0, sizeof(D));
   D.P = c->P;
@@ -488,13 +512,14 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
   D.mz_x = (uint64_t*)c->b_mz_x.p, D.mz_y = (uint32_t*)c->b_mz_y.p, D.mz_n = (int32_t*)c->b_mz_n.p;
   D.mz_cnt = (uint64_t*)c->b_mz_cnt.p;
   D.ws = nullptr, D.ws_cap = 0;
-  D.wreg_scratch = (RegRec*)c->b_wreg.p, D.rsx_scratch = (RadixScratch*)c->b_rsx.p;
+  D.wreg_scratch = nullptr, D.rsx_scratch = (RadixScratch*)c->b_rsx.p;
   D.fin_scratch = (uint32_t*)c->b_fin.p, D.fin_cap = fin_cap;
   D.regs = (RegRec*)c->b_regs.p, D.regs_cap = regs_cap;
   D.pair_reg = (PairReg*)c->b_pair_reg.p;
   D.tasks = (TaskRec*)c->b_tasks.p, D.tasks_cap = regs_cap * 2;
   D.ext_arena = (uint32_t*)c->b_ext_arena.p, D.ext_arena_cap = ext_arena_cap;
   D.ovf_read = (int32_t*)c->b_ovf_read.p, D.ovf_hap = (int32_t*)c->b_ovf_hap.p, D.ovf_cap = n_pairs;
+  D.cold_read = (int32_t*)c->b_cold_read.p, D.cold_hap = (int32_t*)c->b_cold_hap.p;
   D.dir_scratch = (uint8_t*)c->b_dir.p, D.dir_per_warp = dir_per_warp;
   D.bnd_scratch = (int32_t*)c->b_bnd.p, D.bnd_per_warp = bnd_per_warp;
   D.wcig_scratch = (uint32_t*)c->b_wcig.p, D.wcig_cap = wcig_cap;
@@ -508,7 +533,7 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
 
 #define UP(buf, src, bytes)                                                                              \
   do {                                                                                                   \
-    if ((rc = ensure(c, c->buf, (bytes))) != LGR_OK) return rc;                                          \
+    if (c->buf.cap < (size_t)(bytes)) { c->err = "internal: buffer plan too small"; return LGR_E_ARG; }   \
     if ((bytes) > 0) LGR_CUDA(c, cudaMemcpyAsync(c->buf.p, (src), (bytes), cudaMemcpyHostToDevice, c->stream)); \
     h2d += (bytes);                                                                                      \
   } while (0)
@@ -597,18 +622,15 @@ static int upload_packed_impl(lgr_ctx* c, const lgr_packed_in* in, int64_t* h2d_
     z.n_items += (int64_t)in->dir[g].n_haps * ((in->dir[g].n_reads + z.item_reads - 1) / z.item_reads);
   int rc = check_limits(c, z);
   if (rc != LGR_OK) return rc;
-  if ((rc = plan_batch(c, z)) != LGR_OK) return rc;
-  int64_t h2d = 0;
   const uint8_t* slab = static_cast<const uint8_t*>(in->slab);
   const uint8_t* dirp = reinterpret_cast<const uint8_t*>(in->dir);
   const size_t dir_bytes = sizeof(lgr_group_dir) * (size_t)z.G;
   const bool dir_inside = z.G > 0 && dirp >= slab && dirp + dir_bytes <= slab + in->slab_bytes;
+  z.ascii = false, z.slab_bytes = in->slab_bytes, z.dir_bytes = dir_inside ? 0 : dir_bytes;
+  if ((rc = plan_batch(c, z)) != LGR_OK) return rc;
+  int64_t h2d = 0;
   UP(b_slab, in->slab, in->slab_bytes);
   if (!dir_inside) UP(b_dir_tab, in->dir, dir_bytes);
-#define ENS2(buf, bytes) if ((rc = ensure(c, c->buf, (size_t)(bytes))) != LGR_OK) return rc
-  ENS2(b_grp_hapbase, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_readbase, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_vh, sizeof(int64_t) * (z.G + 1));
-  ENS2(b_grp_pair, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_asg, sizeof(int64_t) * (z.G + 1)); ENS2(b_grp_item, sizeof(int32_t) * (z.G + 1));
-#undef ENS2
   Dev& D = c->D;
   D.slab = (const uint8_t*)c->b_slab.p;
   D.dir = dir_inside ? reinterpret_cast<const lgr_group_dir*>(D.slab + (dirp - slab)) : (const lgr_group_dir*)c->b_dir_tab.p;
@@ -665,9 +687,14 @@ static int run_launch(lgr_ctx* c) {
     k_read_filter<<<(D.n_reads + 127) / 128, 128, 0, s>>>(D);
     launches += 1;
     cudaEventRecord(c->ev[2], s);
-    if (c->warp_cap == 64) k_chain_warp<64><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
-    else k_chain_warp<128><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
-    launches += 1;
+    if (c->warp_cap == 64) {
+      k_chain_warp<64><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
+      k_chain_cold<64><<<c->cold_blocks, kWarpsPerCta * 32, c->cold_smem, s>>>(D);
+    } else {
+      k_chain_warp<128><<<c->warp_blocks, kWarpsPerCta * 32, c->warp_smem, s>>>(D);
+      k_chain_cold<128><<<c->cold_blocks, kWarpsPerCta * 32, c->cold_smem, s>>>(D);
+    }
+    launches += 2;
     cudaEventRecord(c->ev[9], s);
     launch_tail(c, D, s, &launches);
     cudaEventRecord(c->ev[3], s);

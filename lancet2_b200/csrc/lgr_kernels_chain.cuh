@@ -101,10 +101,17 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
 // ---------------------------------------------------------------------------------------
 constexpr int kWarpsPerCta = 4;
 constexpr int kMapOkColinear = 2;  // warp_seed_chain: chain DP done by the co-linear closed form
+constexpr int kMapCold = -3;       // hot kernel only: a shape whose code lives in the cold kernel (queued, not computed)
 
-template <int CAP>
+// HOT: the instantiation inside k_chain_warp's hot kernel.  The rare shapes — a seed above mid_occ
+// (mm_seed_select), anchors that need upstream's radix pass emulated, a chain tail the fast form does
+// not cover — return kMapCold instead of running here, so their (large, lane-0) code is not part of
+// the hot kernel's instruction footprint; the cold kernel is the same source with HOT = false.
+// The pair's anchor / evaluation counts are returned to the caller, who commits them only for pairs
+// that finish here (a deferred pair is counted where it is computed).
+template <int CAP, bool HOT>
 __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const uint16_t* bkt, const Ws<1>& ws,
-                                               RadixScratch* rsx, ChainCounters* ctr, int* n_a_out, int* need_out) {
+                                               RadixScratch* rsx, long long* n_eval_out, int* n_a_out, int* need_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
@@ -156,6 +163,7 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
   if (n_m > CAP) return kMapOverflow;
   __syncwarp();
   if (n_high > 0) {
+    if (HOT) return kMapCold;
     if (lane == 0) seed_select(P, seedq, seedn, n_m, qlen, in.mid_occ);
     __syncwarp();
   }
@@ -197,7 +205,6 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     }
     n_a += total;
   }
-  if (lane == 0 && ctr) ctr->n_anchors += n_a;
   *n_a_out = n_a;
   if (n_a == 0) return kMapNoHit;
   __syncwarp();
@@ -216,6 +223,7 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     if (sorted && (n_a <= 64 || strictly)) {
       for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
     } else {
+      if (HOT) return kMapCold;
       if (lane == 0) {
         for (int i = 0; i < n_a; ++i) perm[i] = i;
         radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
@@ -270,7 +278,7 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
       }
       const long long cap_it = P.max_skip + 2, nm1 = n_a - 1;  // sum_{i=1}^{n_a-1} min(i, cap_it)
       n_iter = nm1 <= cap_it ? nm1 * (nm1 + 1) / 2 : cap_it * (cap_it + 1) / 2 + (nm1 - cap_it) * cap_it;
-      if (lane == 0 && ctr) ctr->chain_evals += n_iter;
+      *n_eval_out = n_iter;
       __syncwarp();
       return kMapOkColinear;
     }
@@ -393,7 +401,7 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     }
     __syncwarp();
   }
-  if (lane == 0 && ctr) ctr->chain_evals += n_iter;
+  *n_eval_out = n_iter;
   return kMapOk;
 }
 
@@ -609,16 +617,170 @@ __device__ __forceinline__ bool warp_ext_exact(const DevParams& P, const ReadVie
   return true;
 }
 
-constexpr int kWarpItemReads = 4;  // reads per warp work item (all against one haplotype) in machine-filling batches
+constexpr int kCtaItemReads = 32;  // reads per CTA work item (all against one haplotype) in machine-filling batches
 
 // Phase A kernel: seeds → anchors → chain DP → regs, one warp per pair.  Every pair with at least
 // one reg is parked: its RegRecs go to the arena and its PairReg slot tells k_finish_warp where.
 constexpr int kRegCap = 16;  // chains per pair held in shared memory (more → overflow pass)
 
+constexpr int kTabCap = 512;  // minimizer-table entries of one haplotype staged in shared memory (~1500 bp at w = 5)
+
+__device__ __forceinline__ void cold_push(const Dev& D, int r, int h) {
+  const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NCOLD], 1ULL);
+  D.cold_read[o] = r, D.cold_hap[o] = h;  // capacity n_pairs: every pair is pushed at most once
+}
+
+// One (read, haplotype) pair on one warp: seeds → anchors → chain DP → regs, closed-form extensions,
+// the other extensions queued, regs parked for k_finish_warp.  `tab` / `bkt` are the haplotype's
+// sorted minimizer table and bucket directory (shared memory in the hot kernel, HBM in the cold one).
+template <int CAP, bool HOT>
+__device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, int h_local, int mid_occ, const uint8_t* hapc, int hlen,
+                                           const uint64_t* tab, int idx_n, const uint16_t* bkt, const Ws<1>& ws, RadixScratch* rsx,
+                                           RegRec* s_reg, ChainCounters& ctr) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = D.pair_off[r] + h_local;
+  const int64_t roff = D.read_off[r];
+  const int qlen = (int)(D.read_off[r + 1] - roff);
+  ReadView rv{D.read_codes + roff, qlen};
+  PairIn pin{rv, hapc, hlen, tab, idx_n, D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], mid_occ};
+  int n_a = 0, n_regs = 0, need = 0;
+  long long n_eval = 0;
+  int st = qlen > 0 ? warp_seed_chain<CAP, HOT>(D, pin, bkt, ws, rsx, &n_eval, &n_a, &need) : kMapNoHit;
+  if (st == kMapOkColinear) {
+    st = warp_chain_tail_colinear(D.P, qlen, hlen, pin.name_hash, ws, n_a);
+    n_regs = 1;
+  } else if (st == kMapOk) {
+    st = warp_chain_tail_fast(D.P, qlen, hlen, pin.name_hash, ws, n_a);
+    n_regs = 1;
+    if (st == -2) {
+      if (HOT) {
+        st = kMapCold;
+      } else {
+        if (lane == 0) st = map_chain_tail<1>(D.P, qlen, hlen, pin.name_hash, ws, rsx, n_a, &n_regs);
+        st = __shfl_sync(full, st, 0);
+        n_regs = __shfl_sync(full, n_regs, 0);
+      }
+    }
+  }
+  if (st == kMapCold) {  // computed (and counted) by the cold kernel
+    if (lane == 0) cold_push(D, r, h);
+    __syncwarp();
+    return;
+  }
+  if (st != kMapOverflow || n_a > 0) ctr.n_anchors += n_a, ctr.chain_evals += n_eval;
+  if (st == kMapOverflow || st == kMapNoHit) {
+    if (lane == 0) {
+      if (st == kMapOverflow) {
+        // not refused: listed for the host-driven overflow pass (lgr_gpu.cu overflow_pass), which
+        // sizes its HBM workspace from the largest need recorded here
+        const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
+        if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h | (n_a > 0 ? 1 << 30 : 0);  // n_a > 0: overflowed after counting
+        else flag_err(D, g, E_ANCHOR_CAP);
+        atomicMax((unsigned long long*)&D.ctr[C_OVFNEED], (unsigned long long)need);
+      }
+      write_invalid(&D.aln[pair]);
+      D.pair_reg[pair] = PairReg{0, 0, r, h};
+    }
+    __syncwarp();
+    return;
+  }
+  if (n_regs == 1) {
+    // the common case: the reg stays in shared memory while the closed-form extensions are tried,
+    // then goes to the arena in one coalesced write (no HBM round trip between export and extension)
+    if (lane == 0) export_reg<1>(ws, 0, qlen, s_reg);
+    __syncwarp();
+    unsigned task_mask = 0;
+    for (int side = 0; side < 2; ++side) {
+      if (s_reg->ext[side].m <= 0) continue;
+      if (!warp_ext_exact(D.P, rv, hapc, s_reg, side, &ctr.dp_cells_full)) task_mask |= 1u << side;
+    }
+    long long first = -1, ti = 0;
+    if (lane == 0) {
+      first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], 1ULL);
+      if (first + 1 > D.regs_cap) {
+        flag_err(D, g, E_REG_ARENA);
+        write_invalid(&D.aln[pair]);
+        D.pair_reg[pair] = PairReg{0, 0, r, h};
+        first = -1;
+      } else {
+        D.pair_reg[pair] = PairReg{(int32_t)first, 1, r, h};
+        if (task_mask) {
+          const int nt = __popc(task_mask);
+          ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], (unsigned long long)nt);
+          if (ti + nt > D.tasks_cap) {
+            flag_err(D, g, E_REG_ARENA);
+          } else {
+            if (task_mask & 1u) D.tasks[ti++] = TaskRec{(int32_t)first, 0, r, h};
+            if (task_mask & 2u) D.tasks[ti] = TaskRec{(int32_t)first, 1, r, h};
+          }
+        }
+      }
+    }
+    first = __shfl_sync(full, first, 0);
+    if (first >= 0) {
+      constexpr int kWords = (int)(sizeof(RegRec) / 4);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(s_reg);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&D.regs[first]);
+      for (int w = lane; w < kWords; w += 32) dst[w] = src[w];
+    }
+    __syncwarp();
+    return;
+  }
+  long long first = -1;
+  if (lane == 0) {
+    first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
+    if (first + n_regs > D.regs_cap) {
+      flag_err(D, g, E_REG_ARENA);
+      write_invalid(&D.aln[pair]);
+      D.pair_reg[pair] = PairReg{0, 0, r, h};
+      first = -1;
+    } else {
+      D.pair_reg[pair] = PairReg{(int32_t)first, n_regs, r, h};
+      for (int i = 0; i < n_regs; ++i) export_reg<1>(ws, i, qlen, &D.regs[first + i]);
+    }
+  }
+  first = __shfl_sync(full, first, 0);
+  __syncwarp();
+  if (first >= 0) {
+    // extensions: closed forms here (warp-parallel compare), everything else → wavefront queue
+    for (int i = 0; i < n_regs; ++i) {
+      RegRec* rg = &D.regs[first + i];
+      for (int side = 0; side < 2; ++side) {
+        if (rg->ext[side].m <= 0) continue;
+        if (warp_ext_exact(D.P, rv, hapc, rg, side, &ctr.dp_cells_full)) continue;
+        if (lane == 0) {
+          const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
+          if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
+          else flag_err(D, g, E_REG_ARENA);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// shared memory of the chain kernels: per-warp workspace, per-warp RegRec slot, and (hot kernel) the
+// staged minimizer table + bucket directory of the CTA's haplotype
+__host__ __device__ inline size_t chain_smem_bytes(int cap, bool hot) {
+  return (size_t)kWarpsPerCta * (Ws<1>::elems(cap, kRegCap) * sizeof(int32_t) + sizeof(RegRec)) +
+         (hot ? (size_t)kTabCap * sizeof(uint64_t) + (size_t)(kBuckets + 2) * sizeof(uint16_t) : 0) + 16;
+}
+
+// Phase A, hot kernel.  A CTA takes a work item = (haplotype, up to item_reads consecutive reads of its
+// group), stages that haplotype's sorted minimizer table and 513-entry bucket directory in shared
+// memory (every seed lookup of every read of the item then stays on chip: the dependent
+// minimizer → bucket → table loads were the top stall of the round-1 kernel), and its warps take the
+// item's reads one at a time from a shared counter.  Rare shapes are queued for k_chain_cold.
 template <int CAP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_warp(const __grid_constant__ Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
+  uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem_raw);
+  int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw + (size_t)kTabCap * sizeof(uint64_t));
+  RegRec* s_regs = reinterpret_cast<RegRec*>(s_ws + (size_t)kWarpsPerCta * Ws<1>::elems(CAP, kRegCap));
+  uint16_t* s_bkt = reinterpret_cast<uint16_t*>(s_regs + kWarpsPerCta);
+  __shared__ long long s_item;
+  __shared__ int s_next;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kWarpsPerCta + warp;
@@ -626,86 +788,72 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
   RadixScratch* rsx = D.rsx_scratch + gwarp;
   ChainCounters ctr{0, 0, 0, 0};
   for (;;) {
-    long long item = 0;
-    if (lane == 0) item = atomicAdd((unsigned long long*)&D.ctr[C_ITEM], 1ULL);
-    item = __shfl_sync(full, item, 0);
+    __syncthreads();  // every warp is done with the previous item's table
+    if (threadIdx.x == 0) s_item = atomicAdd((unsigned long long*)&D.ctr[C_ITEM], 1ULL), s_next = 0;
+    __syncthreads();
+    const long long item = s_item;
     if (item >= D.n_items) break;
     const int h = D.item_hap[item], r0 = D.item_r0[item], nr = D.item_n[item];
     const int64_t hoff = D.hap_off[h];
     const int hlen = (int)(D.hap_off[h + 1] - hoff);
     const int idx_n = D.idx_n[h];
     const uint8_t* hapc = D.hap_codes + hoff;
-    const uint64_t* idx = D.idx + hoff;
     const int g = D.hap_grp[h];
     const int h_local = h - D.grp_hap_begin[g];
     const int mid_occ = D.grp_mid[g];
-    for (int rr = 0; rr < nr; ++rr) {
-      const int r = r0 + rr;
-      const int64_t pair = D.pair_off[r] + h_local;
-      const int64_t roff = D.read_off[r];
-      const int qlen = (int)(D.read_off[r + 1] - roff);
-      ReadView rv{D.read_codes + roff, qlen};
-      PairIn pin{rv, hapc, hlen, idx, idx_n, D.mz_x + roff, D.mz_y + roff, D.mz_n[r], D.name_hash[r], mid_occ};
-      int n_a = 0, n_regs = 0, need = 0;
-      int st = qlen > 0 ? warp_seed_chain<CAP>(D, pin, D.bkt + (size_t)h * (kBuckets + 1), ws, rsx, &ctr, &n_a, &need) : kMapNoHit;
-      if (st == kMapOkColinear) {
-        st = warp_chain_tail_colinear(D.P, qlen, hlen, pin.name_hash, ws, n_a);
-        n_regs = 1;
-      } else if (st == kMapOk) {
-        st = warp_chain_tail_fast(D.P, qlen, hlen, pin.name_hash, ws, n_a);
-        n_regs = 1;
-        if (st == -2) {
-          if (lane == 0) st = map_chain_tail<1>(D.P, qlen, hlen, pin.name_hash, ws, rsx, n_a, &n_regs);
-          st = __shfl_sync(full, st, 0);
-          n_regs = __shfl_sync(full, n_regs, 0);
-        }
-      }
-      long long first = -1;
-      if (lane == 0) {
-        if (st == kMapOverflow) {
-          // not refused: listed for the host-driven overflow pass (lgr_gpu.cu overflow_pass), which
-          // sizes its HBM workspace from the largest need recorded here
-          const long long o = atomicAdd((unsigned long long*)&D.ctr[C_NOVF], 1ULL);
-          if (o < D.ovf_cap) D.ovf_read[o] = r, D.ovf_hap[o] = h | (n_a > 0 ? 1 << 30 : 0);  // n_a > 0: overflowed after counting
-          else flag_err(D, g, E_ANCHOR_CAP);
-          atomicMax((unsigned long long*)&D.ctr[C_OVFNEED], (unsigned long long)need);
-          write_invalid(&D.aln[pair]);
-          D.pair_reg[pair] = PairReg{0, 0, r, h};
-        } else if (st == kMapNoHit) {
-          write_invalid(&D.aln[pair]);
-          D.pair_reg[pair] = PairReg{0, 0, r, h};
-        } else {
-          first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], (unsigned long long)n_regs);
-          if (first + n_regs > D.regs_cap) {
-            flag_err(D, g, E_REG_ARENA);
-            write_invalid(&D.aln[pair]);
-            D.pair_reg[pair] = PairReg{0, 0, r, h};
-            first = -1;
-          } else {
-            D.pair_reg[pair] = PairReg{(int32_t)first, n_regs, r, h};
-            for (int i = 0; i < n_regs; ++i) export_reg<1>(ws, i, qlen, &D.regs[first + i]);
-          }
-        }
-      }
-      first = __shfl_sync(full, first, 0);
-      __syncwarp();
-      if (first >= 0) {
-        // extensions: closed forms here (warp-parallel compare), everything else → wavefront queue
-        for (int i = 0; i < n_regs; ++i) {
-          RegRec* rg = &D.regs[first + i];
-          for (int side = 0; side < 2; ++side) {
-            if (rg->ext[side].m <= 0) continue;
-            if (warp_ext_exact(D.P, rv, hapc, rg, side, &ctr.dp_cells_full)) continue;
-            if (lane == 0) {
-              const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
-              if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
-              else flag_err(D, g, E_REG_ARENA);
-            }
-          }
-        }
-      }
-      __syncwarp();
+    if (idx_n > kTabCap) {
+      // a haplotype whose table does not fit the staging block (> ~1500 bp): its pairs go to the cold
+      // kernel, which reads the table from HBM
+      for (int rr = threadIdx.x; rr < nr; rr += blockDim.x) cold_push(D, r0 + rr, h);
+      continue;
     }
+    {
+      const uint64_t* idx = D.idx + hoff;
+      const uint16_t* bk = D.bkt + (size_t)h * (kBuckets + 1);
+      for (int i = threadIdx.x; i < idx_n; i += blockDim.x) s_tab[i] = idx[i];
+      for (int b = threadIdx.x; b <= kBuckets; b += blockDim.x) s_bkt[b] = bk[b];
+    }
+    __syncthreads();
+    for (;;) {
+      int rr = 0;
+      if (lane == 0) rr = atomicAdd(&s_next, 1);
+      rr = __shfl_sync(full, rr, 0);
+      if (rr >= nr) break;
+      chain_pair<CAP, true>(D, r0 + rr, h, g, h_local, mid_occ, hapc, hlen, s_tab, idx_n, s_bkt, ws, rsx, &s_regs[warp], ctr);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
+    atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
+    atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
+  }
+}
+
+// Phase A, cold kernel: the pairs the hot kernel queued, one warp per pair, the complete code
+// (mm_seed_select, the radix-pass emulation, the general chain tail), tables read from HBM.
+template <int CAP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_chain_cold(const __grid_constant__ Dev D) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
+  RegRec* s_regs = reinterpret_cast<RegRec*>(s_ws + (size_t)kWarpsPerCta * Ws<1>::elems(CAP, kRegCap));
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * kWarpsPerCta + warp;
+  const long long n_cold = D.ctr[C_NCOLD];
+  if (n_cold == 0) return;
+  Ws<1> ws{s_ws + (size_t)warp * Ws<1>::elems(CAP, kRegCap), Ws<1>::pack(CAP, kRegCap)};
+  RadixScratch* rsx = D.rsx_scratch + gwarp;
+  ChainCounters ctr{0, 0, 0, 0};
+  for (;;) {
+    long long i = 0;
+    if (lane == 0) i = atomicAdd((unsigned long long*)&D.ctr[C_COLDPOS], 1ULL);
+    i = __shfl_sync(full, i, 0);
+    if (i >= n_cold) break;
+    const int r = D.cold_read[i], h = D.cold_hap[i];
+    const int64_t hoff = D.hap_off[h];
+    const int g = D.hap_grp[h];
+    chain_pair<CAP, false>(D, r, h, g, h - D.grp_hap_begin[g], D.grp_mid[g], D.hap_codes + hoff, (int)(D.hap_off[h + 1] - hoff),
+                           D.idx + hoff, D.idx_n[h], D.bkt + (size_t)h * (kBuckets + 1), ws, rsx, &s_regs[warp], ctr);
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);

@@ -206,14 +206,16 @@ def test_cross_thread_batcher_equals_synchronous_adapter(lib):
 
 
 def _meta(rng, groups, batch):
-    nr = batch.n_reads
+    """per-read metadata as a function of the read NAME, so that a read keeps its metadata whichever
+    other groups share the batch"""
     names = [nm for g in groups for nm in g.names]
+    hs = np.asarray([abi.x31_hash(nm) for nm in names], dtype=np.uint64)
     sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
-    start0 = rng.integers(10_000, 20_000, nr).astype(np.int64)
-    isize = (rng.integers(-500, 500, nr) * (rng.random(nr) < 0.9)).astype(np.int64)
-    flag = (rng.integers(0, 2, nr) * 0x10 + rng.integers(0, 2, nr) * 0x2).astype(np.uint16)
-    mapq = rng.integers(0, 61, nr).astype(np.uint8)
-    softclip = rng.integers(0, 2, nr).astype(np.uint8)
+    start0 = (10_000 + hs % 10_000).astype(np.int64)
+    isize = ((hs // 7 % 1000).astype(np.int64) - 500) * (hs % 10 != 0)
+    flag = ((hs // 3 % 2) * 0x10 + (hs // 5 % 2) * 0x2).astype(np.uint16)
+    mapq = (hs // 11 % 61).astype(np.uint8)
+    softclip = (hs // 13 % 2).astype(np.uint8)
     blob = b"\0".join(x.encode() for x in names) + b"\0"
     return names, blob, (sample_id, start0, isize, flag, mapq, softclip)
 
