@@ -38,7 +38,30 @@ METRIC = "read-haplotype realignments/s (mm_map-equivalent pairs incl. allele as
 UNIT = "alignments/s"
 
 
-def build_workload(name: str, seed: int):
+def build_workload(name: str, seed: int, rank: int = 0, world: int = 1, tiles: int = 0, procs: int = 1):
+    """→ (groups of THIS rank, description, scaling, sample names).  cfg2/micro/tiny: every rank its own
+    copy of the shape (weak scaling, seed + rank).  cfg3/cfg4 (BASELINE configs[2]/[3]): ONE workload of
+    1 Mb tiles, sharded over the ranks with dispatch.partition_units (strong scaling)."""
+    if name in synth.TILED:
+        from lancet2_b200.dispatch import partition_units
+        spec = synth.TILED[name]
+        n_tiles = tiles or spec["tiles"]
+        costs = [synth.tile_cost(name, 42, t) for t in range(n_tiles)]
+        mine = partition_units(costs, world)[rank]
+        groups = synth.make_tiled_groups(name, 42, mine, procs=procs)
+        return groups, tiled_desc(name, n_tiles, world), "strong", spec["sample_names"]
+    groups, desc = _build_replica_workload(name, seed + rank)
+    return groups, desc, "weak", ["normal", "tumor"]
+
+
+def tiled_desc(name: str, n_tiles: int, world: int) -> str:
+    spec = synth.TILED[name]
+    cov = "/".join(f"{int(c)}x" for _, c, _ in spec["samples"])
+    return (f"{name}: synthetic {cov} ({len(spec['samples'])} samples) 2x150bp, {n_tiles} x 1 Mb reference tiles, spiked SNV/InDels, "
+            f"1000bp windows step 800; tiles sharded over {world} rank(s) by dispatch.partition_units")
+
+
+def _build_replica_workload(name: str, seed: int):
     if name == "cfg2":
         groups = synth.make_region_groups(seed, ref_len=1_000_000, cov_normal=30.0, cov_tumor=30.0)
         desc = "cfg2: synthetic 30x/30x tumor-normal 2x150bp, 1 Mb reference, spiked SNV/InDels, 1000bp windows step 800"
@@ -145,6 +168,15 @@ def claim_stdout():
         os.dup2(2, 1)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """progress on stderr (stdout carries only the JSON line)"""
+    sys.stderr.write(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}\n")
+    sys.stderr.flush()
+
+
 def emit_line(line):
     out = _REAL_STDOUT or sys.stdout
     out.write(json.dumps(line) + "\n")
@@ -157,8 +189,12 @@ def run_reference(args, rank, world):
         return
     import oracle_lib as O
     olib, oflags = O.load_native_oracle()
-    groups, desc = build_workload(args.workload, 42)
+    workload = args.workload if args.workload != "auto" else ("cfg2" if world == 1 else "cfg3")
     cores = os.cpu_count() or 1
+    # the reference arm times a bounded sample: for a tiled workload the first tile is representative
+    groups, desc, scaling, _ = build_workload(workload, 42, 0, 1, tiles=1 if workload in synth.TILED else 0)
+    if workload in synth.TILED:  # same configuration string as the GPU arm of this launch
+        desc = tiled_desc(workload, args.tiles or synth.TILED[workload]["tiles"], world)
     prm = O.default_params()
     probe = abi.Batch(groups[:8])
     t0 = time.perf_counter()
@@ -181,7 +217,7 @@ def run_reference(args, rank, world):
     v = batch.n_pairs * args.steps / dt
     sample = f"first {len(sel)} of {len(groups)} groups ({batch.n_pairs} pairs) per step"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": desc, "note": "CPU restatement of the reference path (oracle port, not Lancet2/minimap2 binaries)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "flags": oflags, "sample": sample},
@@ -189,14 +225,19 @@ def run_reference(args, rank, world):
     emit_line(line)
 
 
-def adapter_meta(groups, batch):
+def adapter_meta(groups, batch, sample_names):
     """per-read metadata AddToTable needs (names, sample, start, insert size, flag, mapq), synthetic like the reads"""
     rng = np.random.default_rng(1)
     nr = batch.n_reads
     names = [nm for g in groups for nm in g.names]
+    if all(g.sample is not None for g in groups):
+        sample_id = np.asarray([s for g in groups for s in g.sample], dtype=np.int32)
+    else:
+        sample_id = np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32)
     meta = {
         "blob": b"\0".join(x.encode() for x in names) + b"\0",
-        "sample_id": np.asarray([0 if nm.startswith("n") else 1 for nm in names], dtype=np.int32),
+        "samples": b"\0".join(x.encode() for x in sample_names) + b"\0",
+        "sample_id": sample_id,
         "start0": rng.integers(10_000, 20_000, nr).astype(np.int64),
         "isize": rng.integers(-500, 500, nr).astype(np.int64),
         "flag": (rng.integers(0, 2, nr) * 0x10 + 0x2).astype(np.uint16),
@@ -219,7 +260,7 @@ def run_adapter(lib, device, batch, meta, threads, window, rounds):
     bi = batch.c_struct()
     ctr = np.zeros(20, dtype=np.uint64)
     err = C.create_string_buffer(4096)
-    rc = fn(device, C.byref(bi), meta["blob"], b"normal\0tumor\0", meta["sample_id"].ctypes.data, meta["start0"].ctypes.data,
+    rc = fn(device, C.byref(bi), meta["blob"], meta["samples"], meta["sample_id"].ctypes.data, meta["start0"].ctypes.data,
             meta["isize"].ctypes.data, meta["flag"].ctypes.data, meta["mapq"].ctypes.data, meta["softclip"].ctypes.data,
             threads, rounds, window, 1, ctr.ctypes.data, err, len(err))
     if rc != 0:
@@ -233,7 +274,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="auto", help="auto = cfg2 on one GPU (BASELINE configs[1]), cfg3 sharded over the ranks otherwise (configs[2]); cfg2 | cfg3 | cfg4 | micro | tiny")
+    ap.add_argument("--tiles", type=int, default=0, help="cfg3/cfg4: number of 1 Mb tiles (0 = the configuration's own: 50 / 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-inflight", type=int, default=3)
     ap.add_argument("--adapter-threads", type=int, default=0, help="worker threads of the adapter arm (0 = min(16, host cores / ranks))")
@@ -259,7 +301,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from lancet2_b200.realign import GpuRealigner
-    groups, desc = build_workload(args.workload, 42 + rank)
+    cores = os.cpu_count() or 1
+    # every rank keeps to its own share of the host cores (generation, packing workers, batcher thread)
+    per_rank = max(1, cores // max(1, world))
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(avail) >= world:
+            share = len(avail) // world
+            os.sched_setaffinity(0, set(avail[local_rank * share:(local_rank + 1) * share]))
+    except (AttributeError, OSError):
+        pass
+    workload = args.workload if args.workload != "auto" else ("cfg2" if world == 1 else "cfg3")
+    groups, desc, scaling, sample_names = build_workload(workload, 42, rank, world, tiles=args.tiles, procs=per_rank)
+    if not groups:
+        raise SystemExit(f"rank {rank}: no work (fewer tiles than ranks)")
+    log(f"rank {rank}: workload {workload}: {len(groups)} groups generated")
     batch = abi.Batch(groups)
     gpu = GpuRealigner(local_rank)
     packed = abi.PackedBatch(groups, gpu.lib)  # the wire format the adapter ships: 2-bit planes, one slab
@@ -275,6 +331,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm: the slab is in HBM, a pass = unpack + every kernel of the path ----
+    log(f"packed {packed.slab_bytes} bytes; resident arm")
     gpu.upload_packed(packed)
     probe = [gpu.run_resident().ms_kernels for _ in range(warm)]
     reps = max(1, int(np.ceil(args.min_step_ms / max(min(probe), 1e-3))))
@@ -300,6 +357,7 @@ def main():
     wall_resident = time.perf_counter() - wall0
     dev_ms = sum(ms_steps)
 
+    log(f"resident arm done ({reps} passes per step); C-ABI arms")
     # ---- C-ABI arms on the pre-packed slab (pinned): H2D + unpack + kernels + D2H per call ----
     for _ in range(2):
         gpu.genotype_packed(packed, batch, result=res, want_aln=False)
@@ -339,13 +397,14 @@ def main():
         capi_s = time.perf_counter() - t0
 
     # ---- adapter arm: the reference-shaped call (C++ GenotypeBatcher, worker threads, AddToTable) ----
-    cores = os.cpu_count() or 1
-    threads = args.adapter_threads or max(1, min(16, cores // max(1, world)))
-    meta = adapter_meta(groups, batch)
+    threads = args.adapter_threads or max(1, min(16, per_rank))
+    log(f"C-ABI arms done; adapter arm with {threads} workers")
+    meta = adapter_meta(groups, batch, sample_names)
     run_adapter(gpu.lib, local_rank, batch, meta, threads, args.adapter_window, max(2, min(warm, 4)))  # grows pinned staging
     barrier()
     adapter_s, actr = run_adapter(gpu.lib, local_rank, batch, meta, threads, args.adapter_window, args.steps)
     barrier()
+    log("adapter arm done")
     clocks = sampler.stop()
 
     # max over ranks
@@ -384,7 +443,7 @@ def main():
                 static = json.load(fh)
         except OSError:
             pass
-        wl = static.get(args.workload, {})
+        wl = static.get(workload, {})
         traffic = wl.get("dram_bytes_per_launch")
         issue = None
         if wl.get("warp_inst_per_launch") and static.get("int_issue_peak_warp_inst_per_s"):
@@ -394,9 +453,9 @@ def main():
                      "source": "static: instruction count from " + wl.get("source", "ncu") + "; peak: " + static.get("int_issue_peak_source", "")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "pairs_per_step_per_gpu": batch.n_pairs * reps, "passes_per_step": reps,
+            "config": {"workload": desc, "pairs_per_step_rank0": batch.n_pairs * reps, "pairs_per_step_all_ranks": total_pairs * reps, "passes_per_step": reps,
                        "pairs_per_pass": batch.n_pairs, "groups": batch.n_groups, "reads": batch.n_reads,
                        "haplotypes": batch.n_haps, "variants": batch.n_vars, "input": "packed wire format (2-bit base planes, quality dictionary planes), one slab",
                        "l2": "flushed before every timed pass (512 MiB write, untimed)", "timing": "CUDA events on the library stream, summed over the passes of a step"},

@@ -150,6 +150,8 @@ class Group:
     # per variant: list over haplotypes of (start, len, allele) with allele = -1 when absent
     variants: List[List[tuple]] = field(default_factory=list)
     mid_occ: int = 0
+    # optional: index of each read's sample (ReadCollector order; AddToTable keys evidence by sample name)
+    sample: Optional[List[int]] = None
 
 
 class Batch:

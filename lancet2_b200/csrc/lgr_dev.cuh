@@ -13,8 +13,8 @@ __constant__ double c_phred_err[256] = {
 
 // counters (int64 slots in device memory)
 enum Ctr {
-  C_ITEM = 0, C_NTASK, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
-  C_ALIGNED, C_TASKPOS, C_FINPOS, C_OVFPOS, C_OVFNEED, C_NCOLD, C_COLDPOS, C_COUNT
+  C_ITEM = 0, C_NTASK, C_NTASK1, C_NTASK2, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ALIGNED, C_TASKPOS, C_TASKPOS1, C_TASKPOS2, C_FINPOS, C_OVFPOS, C_OVFNEED, C_NCOLD, C_COLDPOS, C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
@@ -24,6 +24,15 @@ constexpr int kBuckets = 1 << kBucketBits;
 struct TaskRec {  // one extension that needs the wavefront DP
   int32_t reg, side, read, hap;
 };
+
+// Extension tasks are queued by size class so that short tails share a warp (k_ext_warp):
+//   class 0: m <= 8 query rows, 4 tails per warp (8 lanes each)
+//   class 1: m <= 16, 2 tails per warp
+//   class 2: everything else, one tail per warp (row blocks of 32)
+// A class-0/1 tail must also keep its direction bytes in its share of the warp's shared-memory slice.
+constexpr int kExtClasses = 3;
+constexpr int kDirSmemPerWarp = 4096;  // direction bytes of the tails a warp works on, in shared memory
+constexpr int kSegHead = 96;           // bytes at the start of a sub-warp segment's slice: staged query + target codes
 
 struct PairReg {  // per pair: its parked RegRecs in the arena (n == 0: nothing to finish)
   int32_t first, n, read, hap;
@@ -74,7 +83,7 @@ struct Dev {      // everything the kernels need, passed by value
   // parked pairs / tails
   RegRec* regs;  int64_t regs_cap;
   PairReg* pair_reg;             // [n_pairs]
-  TaskRec* tasks; int64_t tasks_cap;
+  TaskRec* tasks; int64_t tasks_cap;   // [kExtClasses][tasks_cap]
   uint32_t* ext_arena; int64_t ext_arena_cap;
   int32_t* ovf_read; int32_t* ovf_hap; int64_t ovf_cap;
   int32_t* cold_read; int32_t* cold_hap;   // [n_pairs] pairs the hot chain kernel left to k_chain_cold
@@ -107,6 +116,24 @@ struct Dev {      // everything the kernels need, passed by value
 __device__ __forceinline__ void flag_err(const Dev& D, int g, int bit) {
   atomicOr((unsigned long long*)&D.ctr[C_ERR], (unsigned long long)bit);
   if (g >= 0 && g < D.n_groups) atomicOr(&D.grp_err[g], bit);
+}
+
+__device__ __forceinline__ int ext_class(const DevParams& P, int m, int n) {
+  if (m > 16) return 2;
+  const int T = prune_cols(P, m, n);
+  const int seg = m <= 8 ? 8 : 16;
+  const int need = kSegHead + m * (T + m - 1);          // staged codes + direction bytes [step][row]
+  if (T + 1 > kSegHead - seg || need > kDirSmemPerWarp / (32 / seg)) return 2;
+  return m <= 8 ? 0 : 1;
+}
+
+// queue one extension (lane 0 of the pair's warp); false when the queue is full
+__device__ __forceinline__ bool push_task(const Dev& D, int reg, int side, int r, int h, int m, int n) {
+  const int cls = ext_class(D.P, m, n);
+  const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK + cls], 1ULL);
+  if (ti >= D.tasks_cap) return false;
+  D.tasks[(size_t)cls * D.tasks_cap + ti] = TaskRec{reg, side, r, h};
+  return true;
 }
 
 __device__ __forceinline__ void write_invalid(AlnOut* o) {

@@ -230,7 +230,7 @@ int lgr_create(int device_ordinal, const lgr_params* params, lgr_ctx** out) {
   cudaGetDeviceProperties(&prop, device_ordinal);
   c->sm_count = prop.multiProcessorCount;
   for (auto& e : c->ev) cudaEventCreate(&e);
-  if (cudaMallocHost((void**)&c->h_ctr, sizeof(long long) * (C_COUNT + 4)) != cudaSuccess) {
+  if (cudaMallocHost((void**)&c->h_ctr, sizeof(long long) * (C_COUNT + 8)) != cudaSuccess) {
     g_create_err = "cudaMallocHost failed";
     delete c;
     return LGR_E_CUDA;
@@ -462,18 +462,19 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
   c->cold_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->cold_blocks_full, (n_pairs + kWarpsPerCta - 1) / kWarpsPerCta));
   c->ext_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->ext_blocks_full, (n_pairs + 15) / 16));  // ~0.3 queued extensions per pair
   c->fin_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->fin_blocks_full, (n_pairs + 4 * kFinChunk - 1) / (4 * kFinChunk)));
-  const int64_t ext_warps = std::max<int64_t>((int64_t)std::max(c->ext_blocks, c->fin_blocks) * 4,
-                                               (int64_t)std::max(c->warp_blocks, c->cold_blocks) * kWarpsPerCta);
+  // per-warp scratch follows the grid that indexes it: extension / finish kernels vs the chain kernels
+  const int64_t ext_warps = (int64_t)std::max(c->ext_blocks, c->fin_blocks) * 4;
+  const int64_t chain_warps = (int64_t)std::max(c->warp_blocks, c->cold_blocks) * kWarpsPerCta;
   const int64_t dir_per_warp = (int64_t)((Lm + 31) / 32) * (Tmax + 32) * 32;
   const int64_t bnd_per_warp = 2 * (int64_t)(Tmax + 32);
   const int wcig_cap = 2 * Lm + 8;
   const int64_t regs_cap = n_pairs + n_pairs / 4 + 1024;
   const int64_t ext_arena_cap = 4 * n_pairs + (1 << 20);
   const int64_t cig_arena_cap = std::max<int64_t>(c->prm.cigar_arena_ops, 1024);
-  ENS(b_rsx, sizeof(RadixScratch) * (size_t)ext_warps);
+  ENS(b_rsx, sizeof(RadixScratch) * (size_t)chain_warps);
   ENS(b_fin, sizeof(uint32_t) * (size_t)ext_warps * 2 * fin_cap);
   ENS(b_regs, sizeof(RegRec) * (size_t)regs_cap); ENS(b_pair_reg, sizeof(PairReg) * (size_t)n_pairs);
-  ENS(b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2);
+  ENS(b_tasks, sizeof(TaskRec) * (size_t)regs_cap * 2 * kExtClasses);
   ENS(b_ext_arena, sizeof(uint32_t) * (size_t)ext_arena_cap);
   ENS(b_ovf_read, sizeof(int32_t) * (size_t)(n_pairs + 32)); ENS(b_ovf_hap, sizeof(int32_t) * (size_t)(n_pairs + 32));
   ENS(b_cold_read, sizeof(int32_t) * (size_t)(n_pairs + 32)); ENS(b_cold_hap, sizeof(int32_t) * (size_t)(n_pairs + 32));
@@ -730,12 +731,11 @@ static int overflow_pass(lgr_ctx* c) {
   if (rc != LGR_OK) return rc;
   Dev D2 = D;
   D2.ws = (int32_t*)c->b_ws_big.p, D2.ws_cap = (int)need;
-  const long long n_task0 = std::min<long long>(c->h_ctr[C_NTASK], D.tasks_cap);
   // restart the queues of phase B: extensions continue after the tasks already done, finish and
   // assignment redo every pair (idempotent; the overflow cigar arena is refilled from 0)
   long long* hc = c->h_ctr + C_COUNT + 2;  // pinned staging of the counter patch
-  hc[0] = n_task0;
-  LGR_CUDA(c, cudaMemcpyAsync(D.ctr + C_TASKPOS, hc, sizeof(long long), cudaMemcpyHostToDevice, s));
+  for (int cls = 0; cls < kExtClasses; ++cls) hc[cls] = std::min<long long>(c->h_ctr[C_NTASK + cls], D.tasks_cap);
+  LGR_CUDA(c, cudaMemcpyAsync(D.ctr + C_TASKPOS, hc, sizeof(long long) * kExtClasses, cudaMemcpyHostToDevice, s));
   LGR_CUDA(c, cudaMemsetAsync(D.ctr + C_FINPOS, 0, sizeof(long long), s));
   LGR_CUDA(c, cudaMemsetAsync(D.ctr + C_CIGARENA, 0, sizeof(long long), s));
   LGR_CUDA(c, cudaMemsetAsync(D.ctr + C_ALIGNED, 0, sizeof(long long), s));

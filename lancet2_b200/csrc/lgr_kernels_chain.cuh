@@ -62,9 +62,7 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
             export_reg<32>(ws, i, qlen, rg);
             for (int side = 0; side < 2; ++side) {
               if (rg->ext[side].m <= 0) continue;
-              const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
-              if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
-              else flag_err(D, g, E_REG_ARENA);
+              if (!push_task(D, (int32_t)(first + i), side, r, h, rg->ext[side].m, rg->ext[side].n)) flag_err(D, g, E_REG_ARENA);
             }
           }
         }
@@ -695,7 +693,7 @@ __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, in
       if (s_reg->ext[side].m <= 0) continue;
       if (!warp_ext_exact(D.P, rv, hapc, s_reg, side, &ctr.dp_cells_full)) task_mask |= 1u << side;
     }
-    long long first = -1, ti = 0;
+    long long first = -1;
     if (lane == 0) {
       first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], 1ULL);
       if (first + 1 > D.regs_cap) {
@@ -705,16 +703,9 @@ __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, in
         first = -1;
       } else {
         D.pair_reg[pair] = PairReg{(int32_t)first, 1, r, h};
-        if (task_mask) {
-          const int nt = __popc(task_mask);
-          ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], (unsigned long long)nt);
-          if (ti + nt > D.tasks_cap) {
+        for (int side = 0; side < 2; ++side)
+          if ((task_mask >> side & 1u) && !push_task(D, (int32_t)first, side, r, h, s_reg->ext[side].m, s_reg->ext[side].n))
             flag_err(D, g, E_REG_ARENA);
-          } else {
-            if (task_mask & 1u) D.tasks[ti++] = TaskRec{(int32_t)first, 0, r, h};
-            if (task_mask & 2u) D.tasks[ti] = TaskRec{(int32_t)first, 1, r, h};
-          }
-        }
       }
     }
     first = __shfl_sync(full, first, 0);
@@ -749,11 +740,7 @@ __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, in
       for (int side = 0; side < 2; ++side) {
         if (rg->ext[side].m <= 0) continue;
         if (warp_ext_exact(D.P, rv, hapc, rg, side, &ctr.dp_cells_full)) continue;
-        if (lane == 0) {
-          const long long ti = atomicAdd((unsigned long long*)&D.ctr[C_NTASK], 1ULL);
-          if (ti < D.tasks_cap) D.tasks[ti] = TaskRec{(int32_t)(first + i), side, r, h};
-          else flag_err(D, g, E_REG_ARENA);
-        }
+        if (lane == 0 && !push_task(D, (int32_t)(first + i), side, r, h, rg->ext[side].m, rg->ext[side].n)) flag_err(D, g, E_REG_ARENA);
       }
     }
   }

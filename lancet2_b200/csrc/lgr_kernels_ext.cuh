@@ -216,51 +216,283 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, int grp, RegRec* reg, int
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------
+// ext_dp_multi<W>: 32 / W extension tails on one warp, W lanes each (W = 8: m <= 8, W = 16: m <= 16).
+// Most tails that reach the wavefront are a dozen rows (a mismatch or indel near a read end): one
+// tail per warp left half the lanes idle on every DP instruction (round-1 ncu: 14-15 of 32 active).
+// Same recurrence, tie rules, column bounds and backtrack as ext_dp_warp, with
+//   * one row block (m <= W), so no boundary row;
+//   * the tail's query and target codes staged in the segment's shared-memory slice (T is a few
+//     dozen columns at these sizes), so a step needs ONE shuffle (H|F from the row above, width W);
+//   * direction bytes [step][row] in the same slice (ext_class guarantees they fit);
+//   * the segment-wide backtrack: W diagonal cells per fetch.
+// Lane sl == 0 of a segment writes its tail's ExtRec.  Control flow is warp-uniform: loop bounds
+// are the maximum over the segments, the per-segment work is predicated.
+// ---------------------------------------------------------------------------------------
+template <int W>
+__device__ __noinline__ void ext_dp_multi(const Dev& D, const TaskRec* tasks, int n_here, uint8_t* dir_warp, uint32_t* cig_warp,
+                                          long long* cells, long long* cells_full) {
+  constexpr int NSEG = 32 / W;
+  constexpr int kSegBytes = kDirSmemPerWarp / NSEG;
+  constexpr int kSegCig = 2 * W + 8;  // ops of one tail's cigar (<= 2m + 2)
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, seg = lane / W, sl = lane % W;
+  const DevParams& P = D.P;
+  const int q = P.q, e = P.e;
+  const int32_t sc_match = P.a, sc_mis = -P.b, sc_amb = -P.sc_ambi;
+  const bool seg_ok = seg < n_here;
+  TaskRec tk = TaskRec{0, 0, 0, 0};
+  if (seg_ok) tk = tasks[seg];
+  RegRec* reg = &D.regs[tk.reg];
+  const int side = tk.side;
+  const bool right = side == 0;
+  const uint8_t* hapc = D.hap_codes + D.hap_off[tk.hap];
+  const int64_t roff = D.read_off[tk.read];
+  ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
+  const int m = seg_ok ? reg->ext[side].m : 0, n = seg_ok ? reg->ext[side].n : 0;
+  int T = seg_ok ? prune_cols(P, m, n) : 0;
+  ExtQuery qf{rv, seg_ok ? reg->rev : 0, side, seg_ok ? reg->c_qs : 0, seg_ok ? reg->c_qe : 0};
+  ExtTarget tf{hapc, side, seg_ok ? reg->c_rs : 0, seg_ok ? reg->c_re : 0};
+  uint8_t* sq = dir_warp + (size_t)seg * kSegBytes;  // [W] query codes
+  uint8_t* st = sq + W;                              // [kSegHead - W] target codes of the first T columns
+  uint8_t* dir = sq + kSegHead;                      // [T + m - 1][m] direction bytes
+  uint32_t* cig = cig_warp + (size_t)seg * kSegCig;
+  // stage the codes (T is the static bound here; the data-dependent bound below can only shrink it)
+  if (sl < m) sq[sl] = (uint8_t)qf(sl);
+  for (int x = sl; x < T; x += W) st[x] = (uint8_t)tf(x);
+  __syncwarp();
+  // ---- data-dependent column bound, as in ext_dp_warp: 32 gap families delta = -15 .. 16 ----
+  {
+    const bool want = seg_ok && n >= m && P.e > 0 && m >= kDynPruneMinRows;
+    int32_t lb = kNegInf;
+    if (W < 32 && __any_sync(full, want)) {
+      for (int round = 0; round < NSEG; ++round) {
+        const int delta = round * W + sl - 15;
+        if (want && (delta >= 0 ? m + delta <= n : -delta < m)) {
+          const int k = delta < 0 ? -delta : 0;
+          const int sh = delta > 0 ? delta : 0;
+          int32_t p0 = 0, ps = 0, best = 0;
+          const int steps = m - k;
+          bool in_stage = steps + sh <= T;  // the shifted diagonal must stay inside the staged columns
+          if (in_stage) {
+            for (int p = 0; p < steps; ++p) {
+              const int tcp = st[p], tcs = st[sh + p], qcp = sq[p], qcs = sq[k + p];
+              p0 += (tcp > 3 || qcp > 3) ? sc_amb : (tcp == qcp ? sc_match : sc_mis);
+              ps += (tcs > 3 || qcs > 3) ? sc_amb : (tcs == qcs ? sc_match : sc_mis);
+              const int32_t dlt = p0 - ps;
+              if (dlt > best) best = dlt;
+            }
+            const int32_t v = best + ps - (delta != 0 ? q + e * (delta < 0 ? -delta : delta) : 0);
+            if (v > lb) lb = v;
+          }
+        }
+      }
+      for (int o = W / 2; o > 0; o >>= 1) {
+        const int32_t v = __shfl_xor_sync(full, lb, o, W);
+        if (v > lb) lb = v;
+      }
+      if (want && lb > kNegInf) {
+        const int X = P.a * m - q - lb;
+        const int Dd = X <= 0 ? 0 : X / e;
+        if (m + Dd < T) T = m + Dd;
+      }
+    }
+  }
+  // ---- wavefront: lane sl owns query row sl, step s computes cell (i = s - sl, sl) ----
+  const int nsteps = seg_ok ? T + m - 1 : 0;
+  int nsteps_max = nsteps;
+  for (int o = 16; o >= W; o >>= 1) {
+    const int v = __shfl_xor_sync(full, nsteps_max, o);
+    if (v > nsteps_max) nsteps_max = v;
+  }
+  const bool row_ok = seg_ok && sl < m;
+  const int qc = row_ok ? sq[sl] : 4;
+  int32_t e_cur = -(q + e * (sl + 1)) - q - e;  // E(0, j)
+  int32_t diag = sl == 0 ? 0 : -(q + e * sl);   // H(-1, j-1)
+  int32_t hf = 0;                                // packed (H low16, F-out high16) of my last cell
+  int32_t ezmax = 0, mqe = kNegInf, mqe_t = -1;
+  for (int s = 0; s < nsteps_max; ++s) {
+    int up_hf = __shfl_up_sync(full, hf, 1, W);
+    if (sl == 0) {
+      const int32_t h0 = -(q + e * (s + 1));
+      up_hf = (int)(((uint32_t)h0 & 0xffffu) | ((uint32_t)(h0 - q - e) << 16));
+    }
+    const int i = s - sl;
+    if (row_ok && i >= 0 && i < T) {
+      const int tc = st[i];
+      const int32_t up_h = (int32_t)(int16_t)(up_hf & 0xffff);
+      const int32_t up_f = up_hf >> 16;
+      const int32_t sc = (tc > 3 || qc > 3) ? sc_amb : (tc == qc ? sc_match : sc_mis);
+      uint8_t d;
+      int32_t en, fn;
+      const int32_t h = ext_cell(diag + sc, e_cur, up_f, q, e, right, &d, &en, &fn);
+      dir[s * m + sl] = d;
+      diag = up_h;
+      e_cur = en;
+      hf = (int)(((uint32_t)h & 0xffffu) | ((uint32_t)fn << 16));
+      if (h > ezmax) ezmax = h;
+      if (sl == m - 1 && h > mqe) mqe = h, mqe_t = i;
+    }
+  }
+  for (int o = W / 2; o > 0; o >>= 1) {
+    const int32_t v = __shfl_xor_sync(full, ezmax, o, W);
+    if (v > ezmax) ezmax = v;
+  }
+  mqe_t = __shfl_sync(full, mqe_t, m > 0 ? m - 1 : 0, W);
+  __syncwarp();
+  // ---- ksw_backtrack, one segment each: W diagonal cells per fetch ----
+  CigBuf cb{cig, 0, kSegCig};
+  {
+    int i = mqe_t, j = m - 1, state = 0;
+    uint32_t run_op = 0;
+    int run_len = 0;
+    auto emit = [&](uint32_t op) {
+      if (run_len > 0 && op == run_op) {
+        ++run_len;
+      } else {
+        if (run_len > 0 && sl == 0) cb.push(run_op, run_len);
+        run_op = op, run_len = 1;
+      }
+    };
+    bool active = seg_ok && i >= 0 && j >= 0;
+    while (__any_sync(full, active)) {
+      const int wi = i - sl, wj = j - sl;
+      const uint32_t dv = (active && wi >= 0 && wj >= 0) ? dir[(wi + wj) * m + wj] : 0u;
+      bool off_diag = false;
+      for (int k = 0; k < W; ++k) {
+        const uint32_t tmp = __shfl_sync(full, dv, k, W);
+        if (active && !off_diag) {
+          if (state == 0) state = tmp & 7;
+          else if (!(tmp >> (state + 2) & 1)) state = 0;
+          if (state == 0) state = tmp & 7;
+          if (state == 0) {
+            emit(0), --i, --j;
+            if (i < 0 || j < 0) active = false;
+          } else {
+            if (state == 1) emit(2), --i;
+            else emit(1), --j;
+            off_diag = true;  // left this diagonal: refetch
+            if (i < 0 || j < 0) active = false;
+          }
+        }
+      }
+    }
+    if (seg_ok && sl == 0) {
+      if (run_len > 0) cb.push(run_op, run_len);
+      if (i >= 0) cb.push(2, i + 1);
+      if (j >= 0) cb.push(1, j + 1);
+      if (side != 0 && cb.n <= cb.cap) {  // right extension: ksw2 reverses the backtrack order
+        for (int a = 0; a < cb.n >> 1; ++a) {
+          const uint32_t t = cb.ops[a];
+          cb.ops[a] = cb.ops[cb.n - 1 - a];
+          cb.ops[cb.n - 1 - a] = t;
+        }
+      }
+    }
+  }
+  if (seg_ok && sl == 0) {
+    ExtRec& E = reg->ext[side];
+    E.max = ezmax;
+    E.mqe_t = mqe_t;
+    E.n_cig = cb.n;
+    if (cb.n > kSegCig) {
+      flag_err(D, D.read_grp[tk.read], E_CIG_SCRATCH);
+      E.n_cig = 0;
+    } else if (cb.n <= kInlineCig) {
+      E.cig_off = -1;
+      for (int c = 0; c < cb.n; ++c) E.inl[c] = cig[c];
+    } else {
+      const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)cb.n);
+      if (o + cb.n > D.ext_arena_cap) {
+        flag_err(D, D.read_grp[tk.read], E_EXT_ARENA);
+        E.n_cig = 0;
+      } else {
+        E.cig_off = (int32_t)o;
+        for (int c = 0; c < cb.n; ++c) D.ext_arena[o + c] = cig[c];
+      }
+    }
+    *cells += (long long)m * T;
+    *cells_full += (long long)m * n;
+  }
+  __syncwarp();
+}
+
 #ifdef LGR_EXT_HIST
 __device__ unsigned long long g_ext_hist[256];  // [m] task count, [128 + m] warp cycles (debug builds only)
 #endif
 
-// Phase B1 kernel: the extensions no closed form covered, one warp per queued extension, through
-// the anti-diagonal wavefront.  Nothing but DP code lives here, so resident warps share one hot loop.
-constexpr int kDirSmemPerWarp = 4096;  // direction bytes of one extension kept in shared memory when they fit
-
+// Phase B1 kernel: the extensions no closed form covered, through the anti-diagonal wavefront.
+// Persistent warps drain the three size classes, longest first: one tail per warp (class 2), then
+// two (class 1) and four (class 0) tails per warp.  Nothing but DP code lives here.
 __global__ void __launch_bounds__(128, LGR_EXT_MINB) k_ext_warp(const __grid_constant__ Dev D) {
-  __shared__ uint8_t s_dir[4 * kDirSmemPerWarp];
+  __shared__ __align__(16) uint8_t s_dir[4 * kDirSmemPerWarp];
+  __shared__ uint32_t s_cig[4][4 * 24];  // per-segment cigar staging of the sub-warp classes (4 x (2*8+8) = 2 x (2*16+8))
   const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint8_t* dir = D.dir_scratch + (size_t)gwarp * D.dir_per_warp;
   int32_t* Hb = D.bnd_scratch + (size_t)gwarp * D.bnd_per_warp;
   int32_t* Fb = Hb + D.bnd_per_warp / 2;
   uint32_t* wcig = D.wcig_scratch + (size_t)gwarp * D.wcig_cap;
   long long cells = 0, cells_full = 0;
-  long long n_task = D.ctr[C_NTASK];
-  if (n_task > D.tasks_cap) n_task = D.tasks_cap;
-  for (;;) {
-    long long t = 0;
-    if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 1ULL);
-    t = __shfl_sync(full, t, 0);
-    if (t >= n_task) break;
-    const TaskRec tk = D.tasks[t];
-    const uint8_t* hapc = D.hap_codes + D.hap_off[tk.hap];
-    const int64_t roff = D.read_off[tk.read];
-    ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
-    long long c1 = 0, c2 = 0;
+  {
+    long long n_task = D.ctr[C_NTASK + 2];
+    if (n_task > D.tasks_cap) n_task = D.tasks_cap;
+    const TaskRec* tasks = D.tasks + 2 * (size_t)D.tasks_cap;
+    for (;;) {
+      long long t = 0;
+      if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS + 2], 1ULL);
+      t = __shfl_sync(full, t, 0);
+      if (t >= n_task) break;
+      const TaskRec tk = tasks[t];
+      const uint8_t* hapc = D.hap_codes + D.hap_off[tk.hap];
+      const int64_t roff = D.read_off[tk.read];
+      ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
+      long long c1 = 0, c2 = 0;
 #ifdef LGR_EXT_HIST
-    const long long t_begin = clock64();
+      const long long t_begin = clock64();
 #endif
-    ext_dp_warp(D, D.read_grp[tk.read], &D.regs[tk.reg], tk.side, rv, hapc, dir, s_dir + (threadIdx.x >> 5) * kDirSmemPerWarp, kDirSmemPerWarp, Hb, Fb, wcig,
-                &c1, &c2);
+      ext_dp_warp(D, D.read_grp[tk.read], &D.regs[tk.reg], tk.side, rv, hapc, dir, s_dir + warp * kDirSmemPerWarp, kDirSmemPerWarp, Hb,
+                  Fb, wcig, &c1, &c2);
 #ifdef LGR_EXT_HIST
-    if (lane == 0) {
-      int mb = D.regs[tk.reg].ext[tk.side].m;
-      mb = mb > 127 ? 127 : mb;
-      atomicAdd(&g_ext_hist[mb], 1ULL);
-      atomicAdd(&g_ext_hist[128 + mb], (unsigned long long)(clock64() - t_begin));
+      if (lane == 0) {
+        int mb = D.regs[tk.reg].ext[tk.side].m;
+        mb = mb > 127 ? 127 : mb;
+        atomicAdd(&g_ext_hist[mb], 1ULL);
+        atomicAdd(&g_ext_hist[128 + mb], (unsigned long long)(clock64() - t_begin));
+      }
+#endif
+      cells += c1, cells_full += c2;
+      __syncwarp();
     }
-#endif
-    cells += c1, cells_full += c2;
-    __syncwarp();
+  }
+  {
+    long long n_task = D.ctr[C_NTASK + 1];
+    if (n_task > D.tasks_cap) n_task = D.tasks_cap;
+    const TaskRec* tasks = D.tasks + 1 * (size_t)D.tasks_cap;
+    for (;;) {
+      long long t = 0;
+      if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS + 1], 2ULL);
+      t = __shfl_sync(full, t, 0);
+      if (t >= n_task) break;
+      ext_dp_multi<16>(D, tasks + t, (int)(n_task - t < 2 ? n_task - t : 2), s_dir + warp * kDirSmemPerWarp, s_cig[warp], &cells, &cells_full);
+    }
+  }
+  {
+    long long n_task = D.ctr[C_NTASK];
+    if (n_task > D.tasks_cap) n_task = D.tasks_cap;
+    const TaskRec* tasks = D.tasks;
+    for (;;) {
+      long long t = 0;
+      if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS], 4ULL);
+      t = __shfl_sync(full, t, 0);
+      if (t >= n_task) break;
+      ext_dp_multi<8>(D, tasks + t, (int)(n_task - t < 4 ? n_task - t : 4), s_dir + warp * kDirSmemPerWarp, s_cig[warp], &cells, &cells_full);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {  // per-lane partial sums (lane 0 / the segment leaders) → total
+    cells += __shfl_xor_sync(full, cells, o);
+    cells_full += __shfl_xor_sync(full, cells_full, o);
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_CELLS], (unsigned long long)cells);

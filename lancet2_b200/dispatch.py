@@ -40,6 +40,24 @@ def partition_groups(groups: Sequence[Group], world: int) -> List[List[int]]:
     return shards
 
 
+def partition_units(costs: Sequence[int], world: int) -> List[List[int]]:
+    """the same longest-processing-time partition for any independent units with given costs (the 1 Mb
+    tiles of the sharded bench workloads, synth.TILED); deterministic, ascending per rank"""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
+    heap = [(0, r) for r in range(world)]
+    heapq.heapify(heap)
+    shards: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        load, r = heapq.heappop(heap)
+        shards[r].append(i)
+        heapq.heappush(heap, (load + int(costs[i]), r))
+    for s in shards:
+        s.sort()
+    return shards
+
+
 def merge_in_submission_order(shards: Sequence[Sequence[int]], per_rank_results: Sequence[Sequence[object]]) -> List[object]:
     """inverse of partition_groups: results[i] is the result of group i"""
     n = sum(len(s) for s in shards)

@@ -345,7 +345,7 @@ int lgr_adapter_isolation_dump(int device, const lgr_batch_in* in, const char* n
     lgr_default_params(&prm);
     if (mid_occ > 0) prm.mid_occ = mid_occ;
     lancet_gpu::GenotypeBatcher::Options opt;
-    opt.device = device, opt.params = &prm, opt.linger_us = 2000;
+    opt.device = device, opt.params = &prm, opt.linger_us = 50000;  // all payloads of the probe share one device batch
     {
       lancet_gpu::GenotypeBatcher batcher(opt, X31OfView);
       std::vector<lancet_gpu::GenotypeBatcher::Ticket> tickets(js.jobs.size());

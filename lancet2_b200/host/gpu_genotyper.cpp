@@ -450,10 +450,12 @@ std::int32_t* ThreadLatch(std::uint64_t uid) {
 // staging slab it came from goes back to the pool as soon as the device is done with it (a worker may
 // enqueue many windows before it collects the first)
 struct GenotypeBatcher::ResultBlock {
-  lgr_assign* assign = nullptr;        // pinned
+  // one pinned block: [lgr_assign x assign_cap][int32 status x max_jobs], (re)allocated at seal time by the
+  // batcher thread — never while mMu is held: CUDA's host allocator may wait for the device, and the
+  // device's completion callback (OnDeviceDone) needs mMu
+  lgr_assign* assign = nullptr;
   std::size_t assign_cap = 0;
-  std::int32_t* status = nullptr;      // pinned [max_jobs]: lgr_batch_out::grp_status
-  std::int32_t* mid = nullptr;         // pinned [max_jobs]: lgr_batch_out::grp_mid_occ
+  std::int32_t* status = nullptr;      // lgr_batch_out::grp_status
   std::vector<std::int64_t> job_asg;   // [max_jobs] first lgr_assign record of every payload
   std::vector<std::int32_t> job_mid;   // [max_jobs] mid_occ the payload was packed with (for a re-run alone)
   std::uint32_t refs = 0;              // payloads not yet released
@@ -473,7 +475,7 @@ struct GenotypeBatcher::Slab {
   lgr_packed_in in{};
   lgr_batch_out out{};
   lgr_ticket ticket = -1;
-  bool lingered = false;
+  std::uint64_t opened_ns = 0;         // when the batcher thread first saw jobs in this slab
 };
 
 static void* PinnedOrThrow(std::size_t bytes) {
@@ -517,7 +519,7 @@ GenotypeBatcher::~GenotypeBatcher() {
   lgr_destroy(mCtx);
   lgr_destroy(mAuxCtx);
   for (auto& s : mSlabs) lgr_free_pinned(s->mem);
-  for (auto& r : mResults) lgr_free_pinned(r->assign), lgr_free_pinned(r->status), lgr_free_pinned(r->mid);
+  for (auto& r : mResults) lgr_free_pinned(r->assign);
   mSlabs.clear();
   mResults.clear();
 }
@@ -531,29 +533,17 @@ void GenotypeBatcher::OnDeviceDone(void* self, lgr_ticket ticket) {  // CUDA-own
   b->mCv.notify_all();
 }
 
-// an EMPTY slab gets room for one payload of `need_bytes` (rare; pinned allocation is slow)
-void GenotypeBatcher::GrowSlab(Slab* s, std::size_t need_bytes) {
-  const std::size_t want = need_bytes + sizeof(lgr_group_dir) + 64;
-  if (s->cap >= want) return;
-  lgr_free_pinned(s->mem);
-  s->mem = nullptr, s->cap = 0;
-  s->mem = static_cast<std::uint8_t*>(PinnedOrThrow(want + want / 4));
-  s->cap = want + want / 4;
-}
-
 // an empty slab with room for `need_bytes` of records plus one directory entry
 GenotypeBatcher::Slab* GenotypeBatcher::TakeFreeSlabLocked(std::unique_lock<std::mutex>& lk, std::size_t need_bytes) {
   mFreeCv.wait(lk, [&] { return mStop || !mFree.empty(); });
   if (mStop) throw std::runtime_error("lancet_gpu::GenotypeBatcher: shut down");
   Slab* s = mFree.back();
   mFree.pop_back();
-  GrowSlab(s, need_bytes);
+  (void)need_bytes;
   if (!s->res) {
     if (mFreeResults.empty()) {
       auto r = std::make_unique<ResultBlock>();
-      r->job_asg.resize(mOpt.max_jobs), r->job_mid.resize(mOpt.max_jobs);
-      r->status = static_cast<std::int32_t*>(PinnedOrThrow(sizeof(std::int32_t) * mOpt.max_jobs));
-      r->mid = static_cast<std::int32_t*>(PinnedOrThrow(sizeof(std::int32_t) * mOpt.max_jobs));
+      r->job_asg.resize(mOpt.max_jobs), r->job_mid.resize(mOpt.max_jobs);  // no pinned memory here (mMu is held)
       mFreeResults.push_back(r.get());
       mResults.push_back(std::move(r));
     }
@@ -585,6 +575,13 @@ GenotypeBatcher::Ticket GenotypeBatcher::Enqueue(const GenotypeJob& job) {
     throw std::runtime_error("lancet_gpu::GenotypeBatcher: payload beyond the device path's static caps (this payload only)");
   sc.last_plan = plan, sc.have_plan = true;
   desc.mid_occ = LatchFor(job);
+  if (plan.bytes + sizeof(lgr_group_dir) + 64 > mOpt.slab_bytes) {
+    // a payload larger than a whole staging slab travels alone (no pinned reallocation on this path)
+    Ticket big;
+    big.job = job;
+    big.alone = std::make_shared<std::vector<lgr_assign>>(RunAlone(job, desc.mid_occ));
+    return big;
+  }
   const std::int64_t pairs = static_cast<std::int64_t>(job.n_reads) * static_cast<std::int64_t>(job.n_haps);
   const std::int64_t n_asg = static_cast<std::int64_t>(job.n_reads) * static_cast<std::int64_t>(job.n_variants);
   Ticket t;
@@ -602,7 +599,6 @@ GenotypeBatcher::Ticket GenotypeBatcher::Enqueue(const GenotypeJob& job) {
       }
       s = mOpen;
       const std::size_t dir_room = sizeof(lgr_group_dir) * (s->n_jobs + 1) + 32;
-      if (s->n_jobs == 0 && s->used + plan.bytes + dir_room > s->cap) GrowSlab(s, plan.bytes);  // one payload larger than the block
       const bool fits = s->n_jobs < mOpt.max_jobs && s->used + plan.bytes + dir_room <= s->cap &&
                         (s->n_jobs == 0 || s->pairs + pairs <= mOpt.max_pairs);
       if (fits) break;
@@ -643,17 +639,18 @@ void GenotypeBatcher::SealAndSubmit(Slab* s) {
     s->in.slab_bytes = dir_off + sizeof(lgr_group_dir) * s->n_jobs;
     s->in.dir = reinterpret_cast<const lgr_group_dir*>(s->mem + dir_off);
     ResultBlock* r = s->res;
-    if (static_cast<std::size_t>(s->n_assign) + 1 > r->assign_cap) {
+    if (!r->assign || static_cast<std::size_t>(s->n_assign) + 1 > r->assign_cap) {
       lgr_free_pinned(r->assign);
-      r->assign = nullptr, r->assign_cap = 0;
-      const std::size_t want = static_cast<std::size_t>(s->n_assign) + static_cast<std::size_t>(s->n_assign) / 2 + 1024;
-      r->assign = static_cast<lgr_assign*>(PinnedOrThrow(want * sizeof(lgr_assign)));
+      r->assign = nullptr, r->assign_cap = 0, r->status = nullptr;
+      const std::size_t want = static_cast<std::size_t>(s->n_assign) + static_cast<std::size_t>(s->n_assign) / 2 + 4096;
+      r->assign = static_cast<lgr_assign*>(PinnedOrThrow(want * sizeof(lgr_assign) + sizeof(std::int32_t) * mOpt.max_jobs));
       r->assign_cap = want;
+      r->status = reinterpret_cast<std::int32_t*>(r->assign + want);
     }
     s->out = lgr_batch_out{};
     s->out.n_assign = s->n_assign;
     s->out.assign = r->assign;  // aln stays NULL: the adapter only needs the assignments
-    s->out.grp_status = r->status, s->out.grp_mid_occ = r->mid;
+    s->out.grp_status = r->status;
     Check(mCtx, lgr_submit_packed(mCtx, &s->in, &s->out, &s->ticket));
   } catch (const std::exception& e) {
     s->ticket = -1, s->res->rc = LGR_E_CUDA, s->res->err = e.what();
@@ -684,7 +681,7 @@ void GenotypeBatcher::Complete(Slab* s) {
     mCounters.ns_wait += t1 - t0;
     mCounters.d2h_bytes += static_cast<std::uint64_t>(st.d2h_bytes);
     // the staging slab is free again; the result block stays with the tickets
-    s->used = 0, s->n_jobs = 0, s->pairs = 0, s->n_assign = 0, s->ticket = -1, s->lingered = false, s->res = nullptr;
+    s->used = 0, s->n_jobs = 0, s->pairs = 0, s->n_assign = 0, s->ticket = -1, s->opened_ns = 0, s->res = nullptr;
     mFree.push_back(s);
   }
   mDoneCv.notify_all();
@@ -716,10 +713,17 @@ void GenotypeBatcher::Run() {
         s = mSealable.front();
         mSealable.pop_front();
       } else if (mOpen && mOpen->n_jobs > 0) {
-        // give the other workers a moment to join this launch, once per slab, unless it already fills the GPU
-        if (mOpt.linger_us > 0 && !mStop && !mOpen->lingered && mOpen->pairs < 65536) {
-          mOpen->lingered = true;
-          mCv.wait_for(lk, std::chrono::microseconds(mOpt.linger_us));
+        // When to launch what has gathered so far.  Idle GPU: after one short linger (other workers get a
+        // moment to join).  Busy GPU: a small batch only adds per-launch overhead and leaves the device
+        // latency bound, so keep gathering until the slab carries enough pairs to fill the machine or has
+        // waited max_wait_us; the batches in flight hide the wait.
+        const std::uint64_t now = NowNs();
+        if (mOpen->opened_ns == 0) mOpen->opened_ns = now;
+        const std::uint64_t age_us = (now - mOpen->opened_ns) / 1000;
+        const bool big = mOpen->pairs >= mOpt.min_pairs_busy;
+        const std::uint64_t wait_us = mInFlight.empty() ? static_cast<std::uint64_t>(mOpt.linger_us) : static_cast<std::uint64_t>(mOpt.max_wait_us);
+        if (!mStop && !big && age_us < wait_us) {
+          mCv.wait_for(lk, std::chrono::microseconds(wait_us - age_us));
           continue;
         }
         s = mOpen;
@@ -761,6 +765,7 @@ std::vector<lgr_assign> GenotypeBatcher::RunAlone(const GenotypeJob& job, std::i
 
 const lgr_assign* GenotypeBatcher::WaitAssign(Ticket& t, std::vector<lgr_assign>* retry_storage) {
   ResultBlock* r = t.res;
+  if (!r && t.alone) return t.alone->data();
   if (!r) throw std::runtime_error("lancet_gpu::GenotypeBatcher: empty ticket");
   {
     std::unique_lock<std::mutex> lk(mMu);

@@ -287,6 +287,8 @@ class GenotypeBatcher {
     std::int64_t max_pairs = 1 << 21;    // (read, haplotype) pairs per device batch
     std::size_t max_jobs = 8192;         // Genotype() payloads per device batch
     int linger_us = 100;                 // idle GPU: wait this long for more workers to arrive before launching
+    int max_wait_us = 400;               // busy GPU: a slab waits at most this long for min_pairs_busy
+    std::int64_t min_pairs_busy = 49152; // busy GPU: pairs that make a batch worth its launch overhead
     std::size_t slab_bytes = 32u << 20;  // pinned staging per slab (grown when one payload needs more)
     const lgr_params* params = nullptr;
   };
@@ -316,6 +318,7 @@ class GenotypeBatcher {
     GenotypeJob job{};
     ResultBlock* res = nullptr;
     std::uint32_t slot = 0;
+    std::shared_ptr<std::vector<lgr_assign>> alone;  // results of a payload that travelled alone (larger than a slab)
   };
   [[nodiscard]] Ticket Enqueue(const GenotypeJob& job);
   [[nodiscard]] Result Collect(Ticket& ticket);
@@ -330,7 +333,6 @@ class GenotypeBatcher {
   void SealAndSubmit(Slab* s);
   void Complete(Slab* s);
   Slab* TakeFreeSlabLocked(std::unique_lock<std::mutex>& lk, std::size_t need_bytes);
-  static void GrowSlab(Slab* s, std::size_t need_bytes);
   std::int32_t LatchFor(const GenotypeJob& job);
   std::vector<lgr_assign> RunAlone(const GenotypeJob& job, std::int32_t mid_occ);
   static void OnDeviceDone(void* self, lgr_ticket ticket);

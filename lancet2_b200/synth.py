@@ -12,7 +12,7 @@ for indels), as VariantExtractor would hand them to ExtractHapBounds
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 
@@ -115,8 +115,15 @@ def make_groups(seed: int, n_groups: int, **kw) -> List[Group]:
 # --------------------------------------------------------------------------------------
 def make_region_groups(seed: int = 42, ref_len: int = 1_000_000, cov_normal: float = 30.0, cov_tumor: float = 30.0,
                        read_len: int = 150, window: int = 1000, step: int = 800, var_every: int = 2000,
-                       sub_err: float = 0.002, max_groups: int = 0) -> List[Group]:
+                       sub_err: float = 0.002, max_groups: int = 0, samples=None) -> List[Group]:
+    """samples: optional list of (read-name tag, coverage, is_tumor) in ReadCollector order (tag kind —
+    normal before tumor —, then sample name: core/read_collector.cpp:42-54).  Default: one normal
+    ("n") and one tumor ("t") at cov_normal / cov_tumor, i.e. BASELINE configs[1]/[2].  Every group
+    carries `sample`, the index into `samples` of each read."""
     rng = np.random.default_rng(seed)
+    if samples is None:
+        samples = [("n", cov_normal, False), ("t", cov_tumor, True)]
+    sample_spec = list(samples)
     ref = _rand_bases(rng, ref_len)
     # ---- spiked variants (sorted, spaced so that they never overlap) ----
     n_var = max(1, ref_len // var_every)
@@ -182,7 +189,7 @@ def make_region_groups(seed: int = 42, ref_len: int = 1_000_000, cov_normal: flo
         names = np.asarray([f"{tag}{f:07d}" for f in frag_id.tolist()])
         return starts, seqs, quals, names
 
-    samples = [sample_reads(cov_normal, False, "n"), sample_reads(cov_tumor, True, "t")]
+    samples = [sample_reads(cov, is_tumor, tag) for tag, cov, is_tumor in sample_spec]
     order = [np.argsort(s[0], kind="stable") for s in samples]
 
     groups: List[Group] = []
@@ -221,8 +228,8 @@ def make_region_groups(seed: int = 42, ref_len: int = 1_000_000, cov_normal: flo
                 if vi in soh:
                     row[hi_ + 1] = (soh[vi], len(aa), 1)
             rows.append(row)
-        reads, quals, names = [], [], []
-        for (starts, seqs, qv, nm), od in zip(samples, order):
+        reads, quals, names, sample_of = [], [], [], []
+        for si, ((starts, seqs, qv, nm), od) in enumerate(zip(samples, order)):
             ss = starts[od]
             a, b = np.searchsorted(ss, w0 - read_len + 1), np.searchsorted(ss, w0 + window)
             sel = od[a:b]
@@ -231,7 +238,52 @@ def make_region_groups(seed: int = 42, ref_len: int = 1_000_000, cov_normal: flo
                 reads.append(seqs[i].tobytes())
                 quals.append(qv[i].tobytes())
                 names.append(str(nm[i]))
-        groups.append(Group(haps=haps, reads=reads, quals=quals, names=names, variants=rows))
+                sample_of.append(si)
+        groups.append(Group(haps=haps, reads=reads, quals=quals, names=names, variants=rows, sample=sample_of))
         if max_groups and len(groups) >= max_groups:
             break
     return groups
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE.json configs[2] / configs[3], the multi-GPU workloads.  A ~50 Mb (cfg3) or 10 Mb (cfg4)
+# reference is laid out as independent 1 Mb tiles (contigs), tile t generated from seed
+# 1000 * seed + t, so that every rank of a sharded run generates exactly the tiles it owns and
+# the whole workload is the same whatever the number of ranks.
+#   cfg3: 60x tumor / 40x normal, 50 tiles
+#   cfg4: four samples at 30x each (one normal, three tumors: colored-graph multi-sample calling), 10 tiles
+# --------------------------------------------------------------------------------------
+TILED = {
+    "cfg3": dict(tiles=50, samples=[("n", 40.0, False), ("t", 60.0, True)],
+                 sample_names=["normal", "tumor"]),
+    "cfg4": dict(tiles=10, samples=[("a", 30.0, False), ("b", 30.0, True), ("c", 30.0, True), ("d", 30.0, True)],
+                 sample_names=["S1_normal", "S2_tumor", "S3_tumor", "S4_tumor"]),
+}
+
+
+def tile_cost(name: str, seed: int, tile: int) -> int:
+    """work estimate of one tile for the shard partition (lancet2_b200/dispatch.py): the tiles of one
+    workload are statistically identical (same length, coverage and variant density)"""
+    spec = TILED[name]
+    return int(sum(c for _, c, _ in spec["samples"]) * 1_000_000)
+
+
+def make_tile_groups(name: str, seed: int, tile: int, ref_len: int = 1_000_000) -> List[Group]:
+    spec = TILED[name]
+    return make_region_groups(1000 * seed + tile, ref_len=ref_len, samples=spec["samples"])
+
+
+def _tile_job(args):
+    return make_tile_groups(*args)
+
+
+def make_tiled_groups(name: str, seed: int, tiles: Sequence[int], ref_len: int = 1_000_000, procs: int = 1) -> List[Group]:
+    """the groups of the given tiles, in tile order; `procs` > 1 generates tiles in worker processes"""
+    jobs = [(name, seed, int(t), ref_len) for t in tiles]
+    if procs > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(procs, len(jobs))) as pool:
+            parts = pool.map(_tile_job, jobs, chunksize=1)
+    else:
+        parts = [_tile_job(j) for j in jobs]
+    return [g for part in parts for g in part]

@@ -261,6 +261,36 @@ def test_batcher_isolates_a_failing_payload(lib):
     # (ii) device-side cap (> 65,535 anchors under a huge mid_occ): the batch is a partial success, the offender is
     # re-run alone, fails again and throws from its own Collect; the rest is untouched
     st, got, ctr = run([ok[3], cap_hit, ok[4]], 1000000)
-    assert st == [0, 2, 0] and int(ctr[0]) == 1 and int(ctr[1]) == 1
+    assert st == [0, 2, 0] and int(ctr[0]) == 1 and int(ctr[1]) == 1, (st, ctr)  # one shared batch, one re-run
     _, want, _ = run([ok[3], ok[4]], 1000000)
     assert got[0] == want[0] and got[2] == want[1] and len(want[0]) > 0
+
+
+@pytest.mark.gpu
+def test_cfg4_four_samples_evidence_per_sample(lib):
+    """BASELINE configs[3] shape (four samples, colored-graph multi-sample calling): reads arrive in
+    ReadCollector order (tag kind, then sample name, then qname: core/read_collector.cpp:42-54) and
+    AddToTable keys the evidence by sample name in first-seen order (genotyper.cpp:423-456,
+    support_array.cpp:19-28).  Through the batcher (4 workers, 8 payloads in flight each) every
+    (variant, sample, allele) evidence block must equal what the oracle's assignments give."""
+    spec = synth.TILED["cfg4"]
+    groups = synth.make_tile_groups("cfg4", 42, 0, ref_len=80_000)
+    assert len(groups) >= 10 and all(set(g.sample) == {0, 1, 2, 3} for g in groups)
+    batch = abi.Batch(groups)
+    names, blob, cols = _meta(None, groups, batch)
+    sample_id = np.asarray([s for g in groups for s in g.sample], dtype=np.int32)
+    cols = (sample_id,) + cols[1:]
+    snames = tuple(spec["sample_names"])
+    sblob = b"\0".join(s.encode() for s in snames) + b"\0"
+    bi = batch.c_struct()
+    buf = C.create_string_buffer(128 << 20)
+    counters = np.zeros(17, dtype=np.uint64)
+    n = lib.lgr_adapter_batcher_dump(0, C.byref(bi), blob, sblob, *[c.ctypes.data for c in cols], 4, 1, 8, 1,
+                                     counters.ctypes.data, buf, len(buf))
+    assert n > 0, buf.value.decode()[:500]
+    got = buf.value.decode().splitlines()
+    want, _ = O.oracle_genotype(batch, O.default_params(), n_threads=8)
+    expect = expected_evidence(lib, batch, groups, names, *cols, want, snames)
+    assert len(got) == len(expect) and len(got) > 40
+    assert got == expect
+    assert {line.split(" ")[2] for line in got} == {"S" + s for s in snames}  # every sample has evidence
