@@ -258,7 +258,7 @@ def run_adapter(lib, device, batch, meta, threads, window, rounds):
         [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
     fn.restype = C.c_int
     bi = batch.c_struct()
-    ctr = np.zeros(20, dtype=np.uint64)
+    ctr = np.zeros(21, dtype=np.uint64)
     err = C.create_string_buffer(4096)
     rc = fn(device, C.byref(bi), meta["blob"], meta["samples"], meta["sample_id"].ctypes.data, meta["start0"].ctypes.data,
             meta["isize"].ctypes.data, meta["flag"].ctypes.data, meta["mapq"].ctypes.data, meta["softclip"].ctypes.data,
@@ -466,7 +466,7 @@ def main():
                     "genotype_calls_per_s": adapter_v * batch.n_groups / max(1, batch.n_pairs),
                     "device_batches_per_step": float(actr[0]) / max(1, args.steps), "max_payloads_in_one_batch": int(actr[3]),
                     "payloads_rerun_alone": int(actr[19]),
-                    "thread_ms_per_step": {"pack_all_workers": float(actr[5]) * 1e-6 / args.steps, "submit_batcher": float(actr[6]) * 1e-6 / args.steps,
+                    "thread_ms_per_step": {"pack_all_workers": float(actr[5]) * 1e-6 / args.steps, "submit_batcher": float(actr[6]) * 1e-6 / args.steps, "of_which_waiting_for_packers": float(actr[20]) * 1e-6 / args.steps,
                                            "wait_batcher": float(actr[7]) * 1e-6 / args.steps, "add_to_table_all_workers": float(actr[8]) * 1e-6 / args.steps,
                                            "wall": adapter_s * 1e3 / args.steps},
                     "l2_flushed": False,

@@ -110,8 +110,16 @@ inline std::int64_t count_exceptions(const std::uint8_t* s, int len) {
   std::int64_t n = 0;
   int i = 0;
 #if LGR_PACK_X86
-  if (have_avx2())
+  if (have_avx2()) {
     for (; i + 32 <= len; i += 32) n += 32 - __builtin_popcount(valid32_avx2(s + i));
+    if (i < len) {
+      alignas(32) std::uint8_t pad[32];
+      std::memset(pad, 'A', sizeof(pad));
+      std::memcpy(pad, s + i, (std::size_t)(len - i));
+      n += 32 - __builtin_popcount(valid32_avx2(pad));
+      i = len;
+    }
+  }
 #endif
   for (; i < len; ++i) n += !is_acgt(s[i]);
   return n;
@@ -125,9 +133,17 @@ inline void pack_bases(const std::uint8_t* s, int len, std::uint32_t* planes, st
     const int off = c << 5, n = len - off < 32 ? len - off : 32;
     std::uint32_t lo, hi, ok;
 #if LGR_PACK_X86
-    if (n == 32 && have_avx2()) {
-      planes32_avx2(s + off, &lo, &hi);
-      ok = valid32_avx2(s + off);
+    if (have_avx2()) {
+      // the last, partial chunk goes through a padded copy: never read past the caller's string
+      alignas(32) std::uint8_t pad[32];
+      const std::uint8_t* src = s + off;
+      if (n < 32) {
+        std::memset(pad, 0, sizeof(pad));
+        std::memcpy(pad, s + off, (std::size_t)n);
+        src = pad;
+      }
+      planes32_avx2(src, &lo, &hi);
+      ok = valid32_avx2(src);
     } else
 #endif
     {
@@ -177,6 +193,13 @@ inline bool quals_fit(const lgr_group_desc* g, const std::uint8_t* lut, int n_lu
       std::uint32_t lo, hi;
       for (; i + 32 <= n; i += 32)
         if (qual32_avx2(q + i, lut, n_lut, &lo, &hi) != 0xffffffffu) return false;
+      if (i < n) {
+        alignas(32) std::uint8_t pad[32];
+        std::memset(pad, lut[0], sizeof(pad));
+        std::memcpy(pad, q + i, (std::size_t)(n - i));
+        if (qual32_avx2(pad, lut, n_lut, &lo, &hi) != 0xffffffffu) return false;
+        i = n;
+      }
     }
 #endif
     for (; i < n; ++i) {
@@ -298,8 +321,16 @@ inline int pack_group(const lgr_group_desc* g, const Plan& p, void* dst, lgr_gro
         std::uint32_t* w = qplanes + (std::size_t)(chunk + c) * (std::size_t)p.qual_bits;
         if (p.qual_bits == 2) {
 #if LGR_PACK_X86
-          if (n == 32 && have_avx2()) {
-            (void)qual32_avx2(q + off, p.lut, 4, &w[0], &w[1]);
+          if (have_avx2()) {
+            alignas(32) std::uint8_t pad[32];
+            const std::uint8_t* src = q + off;
+            if (n < 32) {
+              std::memset(pad, p.lut[0], sizeof(pad));  // index 0 beyond the end
+              std::memcpy(pad, q + off, (std::size_t)n);
+              src = pad;
+            }
+            (void)qual32_avx2(src, p.lut, 4, &w[0], &w[1]);
+            if (n < 32) w[0] &= (1u << n) - 1u, w[1] &= (1u << n) - 1u;
             continue;
           }
 #endif

@@ -288,10 +288,11 @@ static int BatcherRun(int device, const lgr_batch_in* in, const char* names, con
         c.batches += cd.batches, c.jobs += cd.jobs, c.pairs += cd.pairs;
         c.max_jobs_in_batch = std::max(c.max_jobs_in_batch, cd.max_jobs_in_batch);
         c.ns_pack += cd.ns_pack, c.ns_submit += cd.ns_submit, c.ns_wait += cd.ns_wait, c.ns_deliver += cd.ns_deliver;
-        c.h2d_bytes += cd.h2d_bytes, c.d2h_bytes += cd.d2h_bytes, c.retried_alone += cd.retried_alone;
+        c.h2d_bytes += cd.h2d_bytes, c.d2h_bytes += cd.d2h_bytes, c.retried_alone += cd.retried_alone, c.ns_seal_wait += cd.ns_seal_wait;
         if (counters && d < 8) counters[9 + d] = cd.jobs;
       }
       if (counters && n_counters >= 20) counters[17] = c.h2d_bytes, counters[18] = c.d2h_bytes, counters[19] = c.retried_alone;
+      if (counters && n_counters >= 21) counters[20] = c.ns_seal_wait;
       if (counters) {
         counters[0] = c.batches, counters[1] = c.jobs, counters[2] = c.pairs, counters[3] = c.max_jobs_in_batch;
         counters[4] = (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
@@ -317,15 +318,15 @@ int lgr_adapter_batcher_dump(int device, const lgr_batch_in* in, const char* nam
                     n_devices, counters, 17, out, cap, true);
 }
 
-// the same without the dump, for bench.py's e2e arm: counters[20] adds [17] bytes copied host→device, [18] device→host,
-// [19] payloads re-run alone
+// the same without the dump, for bench.py's e2e arm: counters[21] adds [17] bytes copied host→device, [18] device→host,
+// [19] payloads re-run alone, [20] batcher-thread ns spent waiting for workers still packing when a slab was sealed
 int lgr_adapter_batcher_bench(int device, const lgr_batch_in* in, const char* names, const char* samples,
                               const int* sample_id, const long long* start0, const long long* isize,
                               const unsigned short* sam_flag, const unsigned char* mapq, const unsigned char* softclip,
                               int n_threads, int rounds, int window, int n_devices, unsigned long long* counters, char* err,
                               long long err_cap) {
   const int rc = BatcherRun(device, in, names, samples, sample_id, start0, isize, sam_flag, mapq, softclip, n_threads, rounds,
-                            window, n_devices, counters, 20, err, err_cap, false);
+                            window, n_devices, counters, 21, err, err_cap, false);
   return rc;
 }
 

@@ -630,6 +630,7 @@ GenotypeBatcher::Ticket GenotypeBatcher::Enqueue(const GenotypeJob& job) {
 void GenotypeBatcher::SealAndSubmit(Slab* s) {
   const std::uint64_t t0 = NowNs();
   while (s->packing.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // workers finishing their record
+  const std::uint64_t t_packed = NowNs();
   try {
     const std::size_t dir_off = (s->used + 15) & ~static_cast<std::size_t>(15);
     std::memcpy(s->mem + dir_off, s->dir.data(), sizeof(lgr_group_dir) * s->n_jobs);
@@ -657,7 +658,7 @@ void GenotypeBatcher::SealAndSubmit(Slab* s) {
   }
   const std::uint64_t t1 = NowNs();
   std::lock_guard<std::mutex> lk(mMu);
-  mCounters.ns_submit += t1 - t0;
+  mCounters.ns_submit += t1 - t0, mCounters.ns_seal_wait += t_packed - t0;
   mCounters.batches += 1, mCounters.jobs += s->n_jobs, mCounters.pairs += static_cast<std::uint64_t>(s->pairs);
   mCounters.h2d_bytes += s->in.slab_bytes;
   if (s->n_jobs > mCounters.max_jobs_in_batch) mCounters.max_jobs_in_batch = s->n_jobs;

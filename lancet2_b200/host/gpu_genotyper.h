@@ -296,6 +296,7 @@ class GenotypeBatcher {
     std::uint64_t batches = 0, jobs = 0, pairs = 0, max_jobs_in_batch = 0, retried_alone = 0, h2d_bytes = 0, d2h_bytes = 0;
     std::uint64_t ns_pack = 0;     // worker time: sizing + packing into the slab (summed over workers)
     std::uint64_t ns_submit = 0;   // batcher thread: seal + lgr_submit_packed
+    std::uint64_t ns_seal_wait = 0;  // ... of which waiting for workers that were still writing their record
     std::uint64_t ns_wait = 0;     // batcher thread: lgr_wait (statistics, rare overflow pass)
     std::uint64_t ns_deliver = 0;  // worker time: AddToTable (summed over workers)
   };

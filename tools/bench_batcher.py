@@ -22,9 +22,9 @@ def main():
     cfgs = [tuple(int(v) for v in (x.split(":") + ["1"])[:2]) for x in sys.argv[1:]] or [(1, 1), (16, 1), (4, 16), (16, 16)]
     lib = abi.load_library()
     n_dev = int(os.environ.get("LGR_BENCH_DEVICES", "1"))
-    lib.lgr_adapter_batcher_dump.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + \
+    lib.lgr_adapter_batcher_bench.argtypes = [C.c_int, C.POINTER(abi.LgrBatchIn), C.c_char_p, C.c_char_p] + \
         [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_longlong]
-    lib.lgr_adapter_batcher_dump.restype = C.c_int
+    lib.lgr_adapter_batcher_bench.restype = C.c_int
     groups = synth.make_region_groups(42, ref_len=1_000_000)
     batch = abi.Batch(groups)
     nr = batch.n_reads
@@ -42,13 +42,13 @@ def main():
     err = C.create_string_buffer(4096)
     for t, window in cfgs:
         rounds = 32
-        ctr = np.zeros(17, dtype=np.uint64)
-        for _ in range(2):  # first pass grows the pinned staging and device buffers to their steady-state size
-            rc = lib.lgr_adapter_batcher_dump(0, C.byref(bi), blob, b"normal\0tumor\0", *args, t, rounds, window, n_dev, ctr.ctypes.data, err, 0)
+        ctr = np.zeros(21, dtype=np.uint64)
+        for _ in range(2):  # first pass warms the allocators of the process
+            rc = lib.lgr_adapter_batcher_bench(0, C.byref(bi), blob, b"normal\0tumor\0", *args, t, rounds, window, n_dev, ctr.ctypes.data, err, len(err))
             assert rc == 0, err.value.decode()
         sec = float(ctr[4]) * 1e-9
         print(json.dumps({"devices": n_dev, "calls_per_device": [int(x) for x in ctr[9:9 + n_dev]], "worker_threads": t, "groups_in_flight_per_worker": window, "genotype_calls_per_s": float(ctr[1]) / sec, "pairs_per_s": float(ctr[2]) / sec,
-                          "device_batches": int(ctr[0]), "batcher_ms": {"pack": float(ctr[5]) * 1e-6, "submit": float(ctr[6]) * 1e-6, "wait": float(ctr[7]) * 1e-6, "deliver": float(ctr[8]) * 1e-6, "wall": sec * 1e3}, "calls": int(ctr[1]), "max_calls_in_one_batch": int(ctr[3]),
+                          "device_batches": int(ctr[0]), "thread_ms": {"pack_all_workers": float(ctr[5]) * 1e-6, "submit_batcher": float(ctr[6]) * 1e-6, "of_which_waiting_for_packers": float(ctr[20]) * 1e-6, "wait_batcher": float(ctr[7]) * 1e-6, "add_to_table_all_workers": float(ctr[8]) * 1e-6, "wall": sec * 1e3}, "h2d_bytes": int(ctr[17]), "d2h_bytes": int(ctr[18]), "calls": int(ctr[1]), "max_calls_in_one_batch": int(ctr[3]),
                           "workload": "cfg2 groups, one Genotype() payload per group (blocking call when 1 in flight, Enqueue/Collect otherwise), AddToTable on the workers"}), flush=True)
 
 

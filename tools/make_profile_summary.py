@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Turn an ncu report of bench.py (cfg2) into the tracked summaries under profiles/:
-  profiles/r1_ncu_cfg2_final.txt  raw metrics per kernel + per-source-line attribution
-  profiles/r1_ncu_static.json     per-launch DRAM bytes / warp-instructions of k_chain_warp (bench.py reads it)
-usage: tools/make_profile_summary.py gpurun_out/r1_final_cfg2.ncu-rep [int_peak.json]"""
+  profiles/<tag>_ncu_cfg2.txt     raw metrics per kernel + per-source-line attribution
+  profiles/<tag>_ncu_static.json  per-launch DRAM bytes / warp-instructions of k_chain_warp (bench.py reads r2's)
+usage: tools/make_profile_summary.py gpurun_out/<report>.ncu-rep [tag] [int_peak.json]"""
 import csv
 import json
 import os
@@ -24,7 +24,8 @@ KEYS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_
 
 def main():
     rep = sys.argv[1]
-    peak_file = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "r1_int_peak.json")
+    tag = sys.argv[2] if len(sys.argv) > 2 else "r2"
+    peak_file = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles", "r1_int_peak.json")
     raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
     h, units = raw[0], raw[1]
     out, txt = {}, ["ncu --set full --import-source on --clock-control none, bench.py cfg2 (233,282 pairs per step)", ""]
@@ -36,21 +37,22 @@ def main():
         txt += [f"  {k} = {d[k]} {units[h.index(k)] if h.index(k) < len(units) else ''}" for k in KEYS if k in d]
         txt.append("")
     lib = os.path.join(ROOT, "lancet2_b200", "csrc", "liblancet_gpu_realign.so")
-    for mangled, human in (("k_chain_warpILi64", "k_chain_warp"), ("k_ext_warp", "k_ext_warp"), ("k_finish_warp", "k_finish_warp")):
+    for mangled, human in (("k_chain_warpILi64", "k_chain_warp"), ("k_chain_coldILi64", "k_chain_cold"), ("k_ext_warp", "k_ext_warp"),
+                           ("k_finish_warp", "k_finish_warp"), ("k_read_sketch", "k_read_sketch"), ("k_assign", "k_assign")):
         txt.append(f"==== per-source-line attribution: {human} ====")
         txt.append(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, lib, mangled, "25", human],
                                   capture_output=True, text=True).stdout)
-    with open(os.path.join(ROOT, "profiles", "r1_ncu_cfg2_final.txt"), "w") as fh:
+    with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_cfg2.txt"), "w") as fh:
         fh.write("\n".join(txt) + "\n")
     ch = [v for k, v in out.items() if k.startswith("k_chain_warp")][0]
     peak = json.load(open(peak_file))
     static = {"cfg2": {"kernel": "k_chain_warp",
                        "dram_bytes_per_launch": (ch["dram__bytes_read.sum"] + ch["dram__bytes_write.sum"]) * 1e6,
                        "warp_inst_per_launch": ch["smsp__inst_executed.sum"],
-                       "source": "profiles/r1_ncu_cfg2_final.txt (ncu --set full, one launch)"},
+                       "source": f"profiles/{tag}_ncu_cfg2.txt (ncu --set full, one launch)"},
               "int_issue_peak_warp_inst_per_s": peak["iadd3"] * 1e12 / 32,
               "int_issue_peak_source": "profiles/r1_int_peak.json (tools/int_peak.cu, IADD3 thread-ops/s / 32)"}
-    with open(os.path.join(ROOT, "profiles", "r1_ncu_static.json"), "w") as fh:
+    with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_static.json"), "w") as fh:
         json.dump(static, fh, indent=1)
     for k, v in out.items():
         print(k, v["gpu__time_duration.sum"], "ms", int(v["smsp__inst_executed.sum"]), "inst", v["smsp__issue_active.avg.pct_of_peak_sustained_active"], "% issue")
