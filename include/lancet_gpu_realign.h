@@ -378,6 +378,11 @@ void* lgr_stream(lgr_ctx* ctx);
 #define LGR_FMT_HAS_FSSE 32u
 #define LGR_FMT_HAS_AHDD 64u
 #define LGR_FMT_HAS_HSE 128u
+/* The support's variant has more than LGR_FMT_MAX_ALLELES alleles (the reference's ComputePLs /
+ * ComputeContinuousMixtureLods take any K; a record here has fixed arrays).  Such a support is NOT computed: its record
+ * is zero except n_alleles and this bit, lgr_format_metrics returns LGR_E_PARTIAL, and every other support of the call is
+ * complete.  The integrating host keeps such sites (STR loci with many ALTs) on its own VariantSupport code. */
+#define LGR_FMT_WIDE 256u
 
 typedef struct lgr_evidence_in {
   int32_t n_supports;

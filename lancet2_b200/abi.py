@@ -350,6 +350,7 @@ class PackedBatch:
 LGR_FMT_MAX_ALLELES = 8
 LGR_FMT_MAX_GENOTYPES = 36
 LGR_EV_REV, LGR_EV_SOFTCLIP, LGR_EV_PROPER_PAIR = 1, 2, 4
+LGR_FMT_WIDE = 256
 LGR_FMT_HAS = {"fld": 1, "mqcd": 2, "rpcd": 4, "bqcd": 8, "asmd": 16, "fsse": 32, "ahdd": 64, "hse": 128}
 
 # SoA columns of VariantSupport::ReadEvidence (variant_support.h:64-84), in lgr_evidence_in's order

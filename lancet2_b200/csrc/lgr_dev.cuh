@@ -13,8 +13,11 @@ __constant__ double c_phred_err[256] = {
 
 // counters (int64 slots in device memory)
 enum Ctr {
-  C_ITEM = 0, C_NTASK, C_NTASK1, C_NTASK2, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
-  C_ALIGNED, C_TASKPOS, C_TASKPOS1, C_TASKPOS2, C_FINPOS, C_OVFPOS, C_OVFNEED, C_NCOLD, C_COLDPOS, C_COUNT
+  C_ITEM = 0, C_NTASK, C_NTASK1, C_NTASK2, C_NTASK3, C_NTASK4, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
+  C_ALIGNED, C_TASKPOS, C_TASKPOS1, C_TASKPOS2, C_TASKPOS3, C_TASKPOS4, C_FINPOS, C_OVFPOS, C_OVFNEED, C_NCOLD, C_COLDPOS,
+  C_COLD_HIGH, C_COLD_SORT, C_COLD_TAIL, C_COLD_LONG,  // why pairs went to the cold kernel (diagnostics)
+  C_ALIGNED_FUSED,                                     // valid alignments finished inside the chain kernels
+  C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
 
@@ -29,9 +32,13 @@ struct TaskRec {  // one extension that needs the wavefront DP
 //   class 0: m <= 8 query rows, 4 tails per warp (8 lanes each)
 //   class 1: m <= 16, 2 tails per warp
 //   class 2: everything else, one tail per warp (row blocks of 32)
-// A class-0/1 tail must also keep its direction bytes in its share of the warp's shared-memory slice.
-constexpr int kExtClasses = 3;
-constexpr int kDirSmemPerWarp = 4096;  // direction bytes of the tails a warp works on, in shared memory
+//   class 3: n <= 8 target columns and fewer columns than rows (a read overhanging a haplotype end:
+//            ~100 rows x ~5 columns), TRANSPOSED — lanes own columns — 4 tails per warp
+//   class 4: the same with n <= 16, 2 tails per warp
+// A sub-warp tail must also keep its staged codes and direction bytes in its share of the warp's
+// shared-memory slice.
+constexpr int kExtClasses = 5;
+constexpr int kDirSmemPerWarp = 6144;  // staged codes + direction bytes of the tails a warp works on, in shared memory
 constexpr int kSegHead = 96;           // bytes at the start of a sub-warp segment's slice: staged query + target codes
 
 struct PairReg {  // per pair: its parked RegRecs in the arena (n == 0: nothing to finish)
@@ -69,6 +76,7 @@ struct Dev {      // everything the kernels need, passed by value
   const lgr_group_dir* dir;
   int64_t *grp_hapbase, *grp_readbase, *grp_vh, *grp_pair, *grp_asg;
   int32_t* grp_item;
+  int32_t *hap_chk, *read_chk;  // [NH] / [NR] first plane chunk of every sequence within its group record
   int item_reads;               // reads per phase-A work item
   int mid_occ_param;            // lgr_params::mid_occ
   uint64_t* mz_x;               // [read_off-indexed]
@@ -119,6 +127,10 @@ __device__ __forceinline__ void flag_err(const Dev& D, int g, int bit) {
 }
 
 __device__ __forceinline__ int ext_class(const DevParams& P, int m, int n) {
+  if (n < m && n <= 16) {  // transposed: head = m query + n target codes, direction bytes [m + n - 1][n]
+    const int seg = n <= 8 ? 8 : 16;
+    if (m + n + n * (m + n - 1) <= kDirSmemPerWarp / (32 / seg)) return n <= 8 ? 3 : 4;
+  }
   if (m > 16) return 2;
   const int T = prune_cols(P, m, n);
   const int seg = m <= 8 ? 8 : 16;

@@ -5,6 +5,8 @@
 // with -ffp-contract=off).  No CPU fallback: a missing device is LGR_E_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include <string>
 #include <vector>
 
@@ -101,8 +103,13 @@ __global__ void __launch_bounds__(lgr_fmt::kThreads) k_fmt_metrics(const __grid_
   CtaDev w{(int)threadIdx.x};
 #endif
   for (int s = (int)blockIdx.x; s < D.n_supports; s += (int)gridDim.x) {
-    lgr_fmt::support_metrics(w, D.e, D.sup_begin[s], D.sup_begin[s + 1], D.sup_n_alleles[s], D.sup_variant_len[s],
-                             D.sup_total_haps[s], g_phred, &D.out[s], task);
+    // a support with more alleles than the record's fixed arrays hold is not computed here (the host marks its
+    // record LGR_FMT_WIDE): it runs as an empty one-allele support so that nothing indexes past the arrays
+    const int K = D.sup_n_alleles[s];
+    const bool wide = K > LGR_FMT_MAX_ALLELES;
+    const int64_t b = D.sup_begin[s];
+    lgr_fmt::support_metrics(w, D.e, b, wide ? b : D.sup_begin[s + 1], wide ? 1 : K, D.sup_variant_len[s], D.sup_total_haps[s], g_phred,
+                             &D.out[s], task);
   }
 }
 
@@ -199,13 +206,14 @@ int lgr_format_metrics(lgr_fmt_ctx* c, const lgr_evidence_in* in, lgr_format* ou
   const int64_t N = in->n_evidence;
   if (S < 0 || N < 0) return c->err = "negative sizes", LGR_E_ARG;
   if (S == 0) return LGR_OK;
+  int n_wide = 0;
   if (!in->sup_begin || !in->sup_n_alleles || !in->sup_variant_len || !in->sup_total_haps)
     return c->err = "missing support arrays", LGR_E_ARG;
   if (in->sup_begin[0] != 0 || in->sup_begin[S] != N) return c->err = "sup_begin must span [0, n_evidence]", LGR_E_ARG;
   for (int s = 0; s < S; ++s) {
     if (in->sup_begin[s + 1] < in->sup_begin[s]) return c->err = "sup_begin not monotone", LGR_E_ARG;
     if (in->sup_n_alleles[s] < 1) return c->err = "support with fewer than one allele", LGR_E_ARG;
-    if (in->sup_n_alleles[s] > LGR_FMT_MAX_ALLELES) return c->err = "more than LGR_FMT_MAX_ALLELES alleles", LGR_E_LIMIT;
+    n_wide += in->sup_n_alleles[s] > LGR_FMT_MAX_ALLELES;  // not an error of the batch: see LGR_FMT_WIDE
   }
   if (N > 0 && !(in->insert_size && in->aln_start && in->aln_score && in->folded_pos && in->rname_hash && in->ref_nm &&
                  in->own_hap_nm && in->hap_id && in->allele && in->flags && in->base_qual && in->map_qual))
@@ -283,6 +291,15 @@ int lgr_format_metrics(lgr_fmt_ctx* c, const lgr_evidence_in* in, lgr_format* ou
   FMT_CUDA(c, cudaMemcpyAsync(out, c->b_out.p, (size_t)S * sizeof(lgr_format), cudaMemcpyDeviceToHost, c->stream));
   FMT_CUDA(c, cudaStreamSynchronize(c->stream));
   if (ms_kernels) FMT_CUDA(c, cudaEventElapsedTime(ms_kernels, c->ev0, c->ev1));
+  if (n_wide > 0) {
+    for (int s = 0; s < S; ++s)
+      if (in->sup_n_alleles[s] > LGR_FMT_MAX_ALLELES) {
+        std::memset(&out[s], 0, sizeof(lgr_format));
+        out[s].n_alleles = (uint32_t)in->sup_n_alleles[s], out[s].valid = LGR_FMT_WIDE;
+      }
+    c->err = "some supports have more than LGR_FMT_MAX_ALLELES alleles (records flagged LGR_FMT_WIDE)";
+    return LGR_E_PARTIAL;
+  }
   return LGR_OK;
 }
 

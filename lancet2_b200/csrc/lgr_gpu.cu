@@ -80,7 +80,7 @@ struct lgr_ctx {
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
       b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
       b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks, b_grp_mid_req, b_grp_err, b_slab, b_dir_tab, b_grp_hapbase,
-      b_grp_readbase, b_grp_vh, b_grp_pair, b_grp_asg, b_grp_item, b_cold_read, b_cold_hap;
+      b_grp_readbase, b_grp_vh, b_grp_pair, b_grp_asg, b_grp_item, b_cold_read, b_cold_hap, b_hap_chk, b_read_chk;
   Dev D;
   bool resident = false, packed = false;
   int occ_cap = 0, warp_blocks_full = 0, ext_blocks_full = 0, fin_blocks_full = 0, overflow_passes = 0;
@@ -490,6 +490,7 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
   ENS(b_slab, z.slab_bytes); ENS(b_dir_tab, z.dir_bytes);
   ENS(b_grp_hapbase, sizeof(int64_t) * (G + 1)); ENS(b_grp_readbase, sizeof(int64_t) * (G + 1)); ENS(b_grp_vh, sizeof(int64_t) * (G + 1));
   ENS(b_grp_pair, sizeof(int64_t) * (G + 1)); ENS(b_grp_asg, sizeof(int64_t) * (G + 1)); ENS(b_grp_item, sizeof(int32_t) * (G + 1));
+  ENS(b_hap_chk, z.ascii ? 0 : sizeof(int32_t) * NH); ENS(b_read_chk, z.ascii ? 0 : sizeof(int32_t) * NR);
   if ((rc = ensure(c, c->arena, c->arena_off)) != LGR_OK) return rc;
   for (DevBuf* b : c->views) b->p = static_cast<uint8_t*>(c->arena.p) + b->off;
   Dev& D = c->D;
@@ -637,6 +638,7 @@ static int upload_packed_impl(lgr_ctx* c, const lgr_packed_in* in, int64_t* h2d_
   D.dir = dir_inside ? reinterpret_cast<const lgr_group_dir*>(D.slab + (dirp - slab)) : (const lgr_group_dir*)c->b_dir_tab.p;
   D.grp_hapbase = (int64_t*)c->b_grp_hapbase.p, D.grp_readbase = (int64_t*)c->b_grp_readbase.p, D.grp_vh = (int64_t*)c->b_grp_vh.p;
   D.grp_pair = (int64_t*)c->b_grp_pair.p, D.grp_asg = (int64_t*)c->b_grp_asg.p, D.grp_item = (int32_t*)c->b_grp_item.p;
+  D.hap_chk = (int32_t*)c->b_hap_chk.p, D.read_chk = (int32_t*)c->b_read_chk.p;
   c->packed = true;
   c->resident = true;
   if (h2d_bytes) *h2d_bytes = h2d;
@@ -664,6 +666,11 @@ static int run_launch(lgr_ctx* c) {
   if (c->packed && D.n_groups > 0) {
     k_unpack_scan<<<1, 1024, 0, s>>>(D);
     k_unpack_group<<<std::min(D.n_groups, c->sm_count * 8), kUnpackThreads, 0, s>>>(D);
+    const long long n_seq = (long long)D.n_haps + D.n_reads;
+    if (n_seq > 0) {
+      k_unpack_decode<<<(unsigned)std::min<long long>((n_seq + 7) / 8, (long long)c->sm_count * 16), kUnpackThreads, 0, s>>>(D);
+      ++launches;
+    }
     launches += 2;
   }
   if (D.n_pairs > 0) {
@@ -774,7 +781,7 @@ static int run_finish(lgr_ctx* c, lgr_stats* st) {
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[9]); st->ms_k_map = ms;
     cudaEventElapsedTime(&ms, c->ev[9], c->ev[3]); st->ms_k_ext = ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); st->ms_k_assign = ms;
-    st->n_pairs = D.n_pairs, st->n_aligned = hctr[C_ALIGNED];
+    st->n_pairs = D.n_pairs, st->n_aligned = hctr[C_ALIGNED] + hctr[C_ALIGNED_FUSED];
     st->dp_cells = hctr[C_CELLS], st->dp_cells_full = hctr[C_CELLSFULL];
     st->chain_evals = hctr[C_EVALS], st->n_anchors = hctr[C_ANCH];
     st->kernel_launches = launches;
@@ -966,6 +973,14 @@ static int submit_async(lgr_ctx* c, const void* in, lgr_batch_out* out, lgr_tick
     }, &c->slot_note[t]);
   }
   return LGR_OK;
+}
+
+// Diagnostics: the device counters of the last finished batch of this context (enum Ctr in lgr_dev.cuh: work
+// queues, cold-path reasons, extension tasks per size class).  Not part of the stable ABI.
+int lgr_debug_counters(lgr_ctx* c, long long* out, int n) {
+  if (!c || !out) return LGR_E_ARG;
+  for (int i = 0; i < n; ++i) out[i] = i < C_COUNT ? c->h_ctr[i] : 0;
+  return C_COUNT;
 }
 
 int lgr_set_notify(lgr_ctx* c, lgr_notify_fn fn, void* user) {

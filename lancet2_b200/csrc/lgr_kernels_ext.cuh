@@ -417,6 +417,164 @@ __device__ __noinline__ void ext_dp_multi(const Dev& D, const TaskRec* tasks, in
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------
+// ext_dp_multi_t<W>: the TRANSPOSED sub-warp wavefront for tails with few target columns (n <= W,
+// n < m): lane sl owns target column i = sl and sweeps the query rows, step s computes cell
+// (i = sl, j = s - sl).  A read that overhangs a haplotype end leaves ~100 query bases against the
+// handful of haplotype bases outside the first anchor; with lanes on rows that is four 32-row blocks
+// of a few columns each (every block pays 31 steps of pipeline fill for ~5 useful ones).  Here the
+// whole tail is one pass of m + n - 1 steps with n lanes busy, and 32 / W tails share the warp.
+// Roles swap with respect to ext_dp_multi: F (the gap that runs along the query) stays in the lane,
+// H and E travel to the lane on the right.  Same cell function, tie rules, maxima and backtrack.
+// ---------------------------------------------------------------------------------------
+template <int W>
+__device__ __noinline__ void ext_dp_multi_t(const Dev& D, const TaskRec* tasks, int n_here, uint8_t* dir_warp, uint32_t* cig_warp,
+                                            long long* cells, long long* cells_full) {
+  constexpr int NSEG = 32 / W;
+  constexpr int kSegBytes = kDirSmemPerWarp / NSEG;
+  constexpr int kSegCig = 2 * W + 8;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, seg = lane / W, sl = lane % W;
+  const DevParams& P = D.P;
+  const int q = P.q, e = P.e;
+  const int32_t sc_match = P.a, sc_mis = -P.b, sc_amb = -P.sc_ambi;
+  const bool seg_ok = seg < n_here;
+  TaskRec tk = TaskRec{0, 0, 0, 0};
+  if (seg_ok) tk = tasks[seg];
+  RegRec* reg = &D.regs[tk.reg];
+  const int side = tk.side;
+  const bool right = side == 0;
+  const uint8_t* hapc = D.hap_codes + D.hap_off[tk.hap];
+  const int64_t roff = D.read_off[tk.read];
+  ReadView rv{D.read_codes + roff, (int)(D.read_off[tk.read + 1] - roff)};
+  const int m = seg_ok ? reg->ext[side].m : 0, n = seg_ok ? reg->ext[side].n : 0;  // n < m, n <= W: every column is computed
+  ExtQuery qf{rv, seg_ok ? reg->rev : 0, side, seg_ok ? reg->c_qs : 0, seg_ok ? reg->c_qe : 0};
+  ExtTarget tf{hapc, side, seg_ok ? reg->c_rs : 0, seg_ok ? reg->c_re : 0};
+  uint8_t* sq = dir_warp + (size_t)seg * kSegBytes;  // [m] query codes
+  uint8_t* dir = sq + m + n;                         // [m + n - 1][n] direction bytes (the target codes stay in registers)
+  uint32_t* cig = cig_warp + (size_t)seg * kSegCig;
+  for (int x = sl; x < m; x += W) sq[x] = (uint8_t)qf(x);
+  const bool col_ok = seg_ok && sl < n;
+  const int tc = col_ok ? tf(sl) : 4;
+  __syncwarp();
+  const int nsteps = seg_ok ? m + n - 1 : 0;
+  int nsteps_max = nsteps;
+  for (int o = 16; o >= W; o >>= 1) {
+    const int v = __shfl_xor_sync(full, nsteps_max, o);
+    if (v > nsteps_max) nsteps_max = v;
+  }
+  int32_t f_cur = -(q + e * (sl + 1)) - q - e;  // F(i, 0)
+  int32_t diag = sl == 0 ? 0 : -(q + e * sl);   // H(i-1, -1)
+  int32_t he = 0;                                // packed (H low16, E-out high16) of my last cell
+  int32_t ezmax = 0, mqe = kNegInf;
+  for (int s = 0; s < nsteps_max; ++s) {
+    int left = __shfl_up_sync(full, he, 1, W);
+    if (sl == 0) {
+      const int32_t h0 = -(q + e * (s + 1));    // H(-1, j), j = s
+      left = (int)(((uint32_t)h0 & 0xffffu) | ((uint32_t)(h0 - q - e) << 16));
+    }
+    const int j = s - sl;
+    if (col_ok && j >= 0 && j < m) {
+      const int qc = sq[j];
+      const int32_t left_h = (int32_t)(int16_t)(left & 0xffff);
+      const int32_t left_e = left >> 16;
+      const int32_t sc = (tc > 3 || qc > 3) ? sc_amb : (tc == qc ? sc_match : sc_mis);
+      uint8_t d;
+      int32_t en, fn;
+      const int32_t h = ext_cell(diag + sc, left_e, f_cur, q, e, right, &d, &en, &fn);
+      dir[s * n + sl] = d;
+      diag = left_h;
+      f_cur = fn;
+      he = (int)(((uint32_t)h & 0xffffu) | ((uint32_t)en << 16));
+      if (h > ezmax) ezmax = h;
+      if (j == m - 1) mqe = h;  // this column's cell of the last query row
+    }
+  }
+  // first maximum of the last row in column order: (max score, then smallest column)
+  int32_t mqe_t = col_ok ? sl : -1;
+  for (int o = W / 2; o > 0; o >>= 1) {
+    const int32_t v = __shfl_xor_sync(full, ezmax, o, W);
+    if (v > ezmax) ezmax = v;
+    const int32_t oq = __shfl_xor_sync(full, mqe, o, W), ot = __shfl_xor_sync(full, mqe_t, o, W);
+    if (oq > mqe || (oq == mqe && ot >= 0 && (mqe_t < 0 || ot < mqe_t))) mqe = oq, mqe_t = ot;
+  }
+  __syncwarp();
+  CigBuf cb{cig, 0, kSegCig};
+  {
+    int i = mqe_t, j = m - 1, state = 0;
+    uint32_t run_op = 0;
+    int run_len = 0;
+    auto emit = [&](uint32_t op) {
+      if (run_len > 0 && op == run_op) {
+        ++run_len;
+      } else {
+        if (run_len > 0 && sl == 0) cb.push(run_op, run_len);
+        run_op = op, run_len = 1;
+      }
+    };
+    bool active = seg_ok && i >= 0 && j >= 0;
+    while (__any_sync(full, active)) {
+      const int wi = i - sl, wj = j - sl;
+      const uint32_t dv = (active && wi >= 0 && wj >= 0) ? dir[(wi + wj) * n + wi] : 0u;
+      bool off_diag = false;
+      for (int k = 0; k < W; ++k) {
+        const uint32_t tmp = __shfl_sync(full, dv, k, W);
+        if (active && !off_diag) {
+          if (state == 0) state = tmp & 7;
+          else if (!(tmp >> (state + 2) & 1)) state = 0;
+          if (state == 0) state = tmp & 7;
+          if (state == 0) {
+            emit(0), --i, --j;
+            if (i < 0 || j < 0) active = false;
+          } else {
+            if (state == 1) emit(2), --i;
+            else emit(1), --j;
+            off_diag = true;
+            if (i < 0 || j < 0) active = false;
+          }
+        }
+      }
+    }
+    if (seg_ok && sl == 0) {
+      if (run_len > 0) cb.push(run_op, run_len);
+      if (i >= 0) cb.push(2, i + 1);
+      if (j >= 0) cb.push(1, j + 1);
+      if (side != 0 && cb.n <= cb.cap) {
+        for (int a = 0; a < cb.n >> 1; ++a) {
+          const uint32_t t = cb.ops[a];
+          cb.ops[a] = cb.ops[cb.n - 1 - a];
+          cb.ops[cb.n - 1 - a] = t;
+        }
+      }
+    }
+  }
+  if (seg_ok && sl == 0) {
+    ExtRec& E = reg->ext[side];
+    E.max = ezmax;
+    E.mqe_t = mqe_t;
+    E.n_cig = cb.n;
+    if (cb.n > kSegCig) {
+      flag_err(D, D.read_grp[tk.read], E_CIG_SCRATCH);
+      E.n_cig = 0;
+    } else if (cb.n <= kInlineCig) {
+      E.cig_off = -1;
+      for (int c = 0; c < cb.n; ++c) E.inl[c] = cig[c];
+    } else {
+      const long long o = atomicAdd((unsigned long long*)&D.ctr[C_EXTARENA], (unsigned long long)cb.n);
+      if (o + cb.n > D.ext_arena_cap) {
+        flag_err(D, D.read_grp[tk.read], E_EXT_ARENA);
+        E.n_cig = 0;
+      } else {
+        E.cig_off = (int32_t)o;
+        for (int c = 0; c < cb.n; ++c) D.ext_arena[o + c] = cig[c];
+      }
+    }
+    *cells += (long long)m * n;
+    *cells_full += (long long)m * n;
+  }
+  __syncwarp();
+}
+
 #ifdef LGR_EXT_HIST
 __device__ unsigned long long g_ext_hist[256];  // [m] task count, [128 + m] warp cycles (debug builds only)
 #endif
@@ -476,6 +634,30 @@ __global__ void __launch_bounds__(128, LGR_EXT_MINB) k_ext_warp(const __grid_con
       t = __shfl_sync(full, t, 0);
       if (t >= n_task) break;
       ext_dp_multi<16>(D, tasks + t, (int)(n_task - t < 2 ? n_task - t : 2), s_dir + warp * kDirSmemPerWarp, s_cig[warp], &cells, &cells_full);
+    }
+  }
+  {
+    long long n_task = D.ctr[C_NTASK + 4];
+    if (n_task > D.tasks_cap) n_task = D.tasks_cap;
+    const TaskRec* tasks = D.tasks + 4 * (size_t)D.tasks_cap;
+    for (;;) {
+      long long t = 0;
+      if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS + 4], 2ULL);
+      t = __shfl_sync(full, t, 0);
+      if (t >= n_task) break;
+      ext_dp_multi_t<16>(D, tasks + t, (int)(n_task - t < 2 ? n_task - t : 2), s_dir + warp * kDirSmemPerWarp, s_cig[warp], &cells, &cells_full);
+    }
+  }
+  {
+    long long n_task = D.ctr[C_NTASK + 3];
+    if (n_task > D.tasks_cap) n_task = D.tasks_cap;
+    const TaskRec* tasks = D.tasks + 3 * (size_t)D.tasks_cap;
+    for (;;) {
+      long long t = 0;
+      if (lane == 0) t = atomicAdd((unsigned long long*)&D.ctr[C_TASKPOS + 3], 4ULL);
+      t = __shfl_sync(full, t, 0);
+      if (t >= n_task) break;
+      ext_dp_multi_t<8>(D, tasks + t, (int)(n_task - t < 4 ? n_task - t : 4), s_dir + warp * kDirSmemPerWarp, s_cig[warp], &cells, &cells_full);
     }
   }
   {

@@ -3,10 +3,10 @@
 // the realignment kernels read.  Part of the single translation unit lgr_gpu.cu.
 //   k_unpack_scan   one CTA: exclusive prefix sums over the group directory (haplotypes, reads,
 //                   variants, bases, bounds-table entries, pairs, assignments, work items)
-//   k_unpack_group  one CTA per group: per-sequence offsets (block scans of the lengths), bit planes →
-//                   code bytes / Phred bytes (a warp per sequence, 32 coalesced bytes per step),
-//                   exception patch, name hashes, bounds table, read→group / pair / assignment
-//                   offsets, the phase-A work items
+//   k_unpack_group  one CTA per group: per-sequence offsets (block scans of the lengths), name hashes,
+//                   bounds table, read→group / pair / assignment offsets, the phase-A work items
+//   k_unpack_decode one warp per sequence of the batch: bit planes → code bytes / Phred bytes (32
+//                   coalesced bytes per step) and the sequence's share of the exception list
 #ifndef LANCET2_B200_LGR_KERNELS_UNPACK_CUH_
 #define LANCET2_B200_LGR_KERNELS_UNPACK_CUH_
 
@@ -90,27 +90,15 @@ __global__ void __launch_bounds__(1024) k_unpack_scan(const __grid_constant__ De
 
 constexpr int kUnpackThreads = 256;
 
-// sequences of one kind (haplotypes or reads) of one group: offsets, then planes → bytes
+// offsets of the sequences of one kind (haplotypes or reads) of one group: block scans of the lengths
 template <bool READS>
-__device__ __forceinline__ void unpack_seqs(const Dev& D, const uint8_t* rec, const lgr_group_rec_hdr& hdr, int n_seq, int first,
-                                            long long gbase, int g, long long pair0, long long asg0, int P, int V,
-                                            long long* s_w, int* s_off, int* s_len, int* s_chk) {
-  const unsigned full = 0xffffffffu;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void unpack_offsets(const Dev& D, const uint8_t* rec, const lgr_group_rec_hdr& hdr, int n_seq, int first,
+                                               long long gbase, int g, long long pair0, long long asg0, int P, int V, long long* s_w) {
+  const int tid = threadIdx.x;
   const int32_t* hap_len = reinterpret_cast<const int32_t*>(rec + hdr.off_hap_len);
   const uint16_t* read_len = reinterpret_cast<const uint16_t*>(rec + hdr.off_read_len);
-  const uint32_t* planes = reinterpret_cast<const uint32_t*>(rec + (READS ? hdr.off_read_planes : hdr.off_hap_planes));
-  const uint32_t* qplanes = reinterpret_cast<const uint32_t*>(rec + hdr.off_qual);
-  const uint8_t* qraw = rec + hdr.off_qual;
-  const int qbits = (int)hdr.qual_bits;
   int64_t* out_off = const_cast<int64_t*>(READS ? D.read_off : D.hap_off) + first;
-  uint8_t* codes = (READS ? D.read_codes : D.hap_codes) + gbase;
-  uint8_t* quals = const_cast<uint8_t*>(D.read_quals) + gbase;
-  uint32_t lutw[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    lutw[k] = (uint32_t)hdr.qual_lut[4 * k] | (uint32_t)hdr.qual_lut[4 * k + 1] << 8 | (uint32_t)hdr.qual_lut[4 * k + 2] << 16 |
-              (uint32_t)hdr.qual_lut[4 * k + 3] << 24;
+  int32_t* out_chk = (READS ? D.read_chk : D.hap_chk) + first;
   long long carry_off = 0, carry_chk = 0;
   for (int base = 0; base < n_seq; base += kUnpackThreads) {
     const int i = base + tid;
@@ -118,10 +106,9 @@ __device__ __forceinline__ void unpack_seqs(const Dev& D, const uint8_t* rec, co
     long long t_len, t_chk;
     const long long ex_len = block_excl_scan<kUnpackThreads / 32>(len, s_w, &t_len);
     const long long ex_chk = block_excl_scan<kUnpackThreads / 32>((len + 31) >> 5, s_w, &t_chk);
-    const int off = (int)(carry_off + ex_len), chk = (int)(carry_chk + ex_chk);
-    s_off[tid] = off, s_len[tid] = len, s_chk[tid] = chk;
     if (i < n_seq) {
-      out_off[i] = gbase + off;
+      out_off[i] = gbase + carry_off + ex_len;
+      out_chk[i] = (int32_t)(carry_chk + ex_chk);
       if (READS) {
         const int r = first + i;
         const_cast<int32_t*>(D.read_grp)[r] = g;
@@ -132,37 +119,13 @@ __device__ __forceinline__ void unpack_seqs(const Dev& D, const uint8_t* rec, co
         const_cast<int32_t*>(D.hap_grp)[first + i] = g;
       }
     }
-    __syncthreads();
-    const int n_here = n_seq - base < kUnpackThreads ? n_seq - base : kUnpackThreads;
-    for (int j = warp; j < n_here; j += kUnpackThreads / 32) {
-      const int o = s_off[j], l = s_len[j], c0 = s_chk[j];
-      for (int c = 0; (c << 5) < l; ++c) {
-        const uint32_t lo = planes[2 * (size_t)(c0 + c)], hi = planes[2 * (size_t)(c0 + c) + 1];
-        const int b = (c << 5) + lane;
-        if (b < l) {
-          const uint32_t nt = (lo >> lane & 1u) | (hi >> lane & 1u) << 1;
-          codes[o + b] = (uint8_t)(nt * 0x11u);
-        }
-        if (READS) {
-          if (qbits == 8) {
-            if (b < l) quals[o + b] = qraw[o + b];
-          } else {
-            uint32_t k = 0;
-            for (int p = 0; p < qbits; ++p) k |= (qplanes[(size_t)(c0 + c) * qbits + p] >> lane & 1u) << p;
-            if (b < l) quals[o + b] = (uint8_t)(lutw[k >> 2] >> (8 * (k & 3)));
-          }
-        }
-      }
-    }
     carry_off += t_len, carry_chk += t_chk;
-    __syncthreads();
   }
-  (void)full;
 }
 
+// one CTA per group: everything but the sequence bytes
 __global__ void __launch_bounds__(kUnpackThreads) k_unpack_group(const __grid_constant__ Dev D) {
   __shared__ long long s_w[kUnpackThreads / 32 + 1];
-  __shared__ int s_off[kUnpackThreads], s_len[kUnpackThreads], s_chk[kUnpackThreads];
   const int tid = threadIdx.x;
   for (int g = blockIdx.x; g < D.n_groups; g += gridDim.x) {
     const lgr_group_dir d = D.dir[g];
@@ -172,8 +135,8 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack_group(const __grid_co
     const int hb = D.grp_hap_begin[g], rb = D.grp_read_begin[g], vb = D.grp_var_begin[g];
     const long long hbase = D.grp_hapbase[g], rbase = D.grp_readbase[g], vh0 = D.grp_vh[g];
     const long long pair0 = D.grp_pair[g], asg0 = D.grp_asg[g];
-    unpack_seqs<false>(D, rec, hdr, P, hb, hbase, g, 0, 0, P, V, s_w, s_off, s_len, s_chk);
-    unpack_seqs<true>(D, rec, hdr, R, rb, rbase, g, pair0, asg0, P, V, s_w, s_off, s_len, s_chk);
+    unpack_offsets<false>(D, rec, hdr, P, hb, hbase, g, 0, 0, P, V, s_w);
+    unpack_offsets<true>(D, rec, hdr, R, rb, rbase, g, pair0, asg0, P, V, s_w);
     // ExtractHapBounds' dense table
     {
       const long long vh = (long long)V * P;
@@ -199,17 +162,67 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack_group(const __grid_co
         const_cast<int32_t*>(D.item_n)[it0 + x] = R - r0 < D.item_reads ? R - r0 : D.item_reads;
       }
     }
-    __syncthreads();  // every code byte of the group is written: patch the exceptions
-    {
-      const uint32_t* epos = reinterpret_cast<const uint32_t*>(rec + hdr.off_exc);
-      const uint8_t* ecode = reinterpret_cast<const uint8_t*>(epos + hdr.n_exc);
-      for (uint32_t e = tid; e < hdr.n_exc; e += kUnpackThreads) {
-        const uint32_t p = epos[e];
-        if (p >> 31) D.read_codes[rbase + (p & 0x7fffffffu)] = ecode[e];
-        else D.hap_codes[hbase + p] = ecode[e];
+    __syncthreads();
+  }
+}
+
+// one WARP per sequence of the whole batch (haplotypes first, then reads): bit planes → code bytes
+// (and Phred bytes for reads), 32 coalesced bytes per step, then the sequence's share of its group's
+// exception list.  Flat over the batch, so the copy runs at memory speed whatever the group sizes.
+__global__ void __launch_bounds__(kUnpackThreads) k_unpack_decode(const __grid_constant__ Dev D) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long n_seq = (long long)D.n_haps + D.n_reads;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_seq; q += warps) {
+    const bool is_read = q >= D.n_haps;
+    const int idx = is_read ? (int)(q - D.n_haps) : (int)q;
+    const int g = is_read ? D.read_grp[idx] : D.hap_grp[idx];
+    const uint8_t* rec = D.slab + D.dir[g].rec_off;
+    const lgr_group_rec_hdr* hdr = reinterpret_cast<const lgr_group_rec_hdr*>(rec);
+    const int64_t* offs = is_read ? D.read_off : D.hap_off;
+    const long long o = offs[idx];
+    const int l = (int)(offs[idx + 1] - o);
+    const int c0 = is_read ? D.read_chk[idx] : D.hap_chk[idx];
+    const uint32_t* planes = reinterpret_cast<const uint32_t*>(rec + (is_read ? hdr->off_read_planes : hdr->off_hap_planes));
+    uint8_t* codes = (is_read ? D.read_codes : D.hap_codes) + o;
+    for (int c = 0; (c << 5) < l; ++c) {
+      const uint32_t lo = planes[2 * (size_t)(c0 + c)], hi = planes[2 * (size_t)(c0 + c) + 1];
+      const int b = (c << 5) + lane;
+      if (b < l) codes[b] = (uint8_t)(((lo >> lane & 1u) | (hi >> lane & 1u) << 1) * 0x11u);
+    }
+    if (is_read) {
+      const int qbits = (int)hdr->qual_bits;
+      uint8_t* quals = const_cast<uint8_t*>(D.read_quals) + o;
+      const long long in_group = o - D.grp_readbase[g];  // the read's first base within its group
+      if (qbits == 8) {
+        const uint8_t* qraw = rec + hdr->off_qual + in_group;
+        for (int b = lane; b < l; b += 32) quals[b] = qraw[b];
+      } else {
+        const uint32_t* qplanes = reinterpret_cast<const uint32_t*>(rec + hdr->off_qual);
+        const uint32_t lut_lo = lane < 16 ? hdr->qual_lut[lane] : 0;  // dictionary entry `lane` lives in lane `lane`
+        for (int c = 0; (c << 5) < l; ++c) {
+          uint32_t k = 0;
+          for (int p = 0; p < qbits; ++p) k |= (qplanes[(size_t)(c0 + c) * qbits + p] >> lane & 1u) << p;
+          const uint32_t v = __shfl_sync(full, lut_lo, (int)k);
+          const int b = (c << 5) + lane;
+          if (b < l) quals[b] = (uint8_t)v;
+        }
       }
     }
-    __syncthreads();
+    // exceptions (N, IUPAC, U): the entries of the group that fall inside this sequence
+    const uint32_t n_exc = hdr->n_exc;
+    if (n_exc) {
+      __syncwarp();
+      const uint32_t* epos = reinterpret_cast<const uint32_t*>(rec + hdr->off_exc);
+      const uint8_t* ecode = reinterpret_cast<const uint8_t*>(epos + n_exc);
+      const long long start = o - (is_read ? D.grp_readbase[g] : D.grp_hapbase[g]);
+      for (uint32_t e = lane; e < n_exc; e += 32) {
+        const uint32_t p = epos[e];
+        const long long pos = p & 0x7fffffffu;
+        if ((p >> 31) == (is_read ? 1u : 0u) && pos >= start && pos < start + l) codes[pos - start] = ecode[e];
+      }
+    }
   }
 }
 

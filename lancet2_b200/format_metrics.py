@@ -56,6 +56,9 @@ class GpuFormatMetrics:
         st = batch.c_struct()
         ms = C.c_float(0.0)
         rc = self._lib.lgr_format_metrics(self._ctx, C.byref(st), out.ctypes.data, C.byref(ms))
+        self.last_rc = rc
+        if rc == abi.LGR_E_PARTIAL:  # supports with more than LGR_FMT_MAX_ALLELES alleles are flagged, not fatal
+            return out, float(ms.value)
         if rc != 0:
             raise RuntimeError(f"lgr_format_metrics failed ({self._main.lgr_strerror(rc).decode()}): "
                                f"{self._lib.lgr_format_last_error(self._ctx).decode()}")

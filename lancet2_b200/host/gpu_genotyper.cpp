@@ -4,6 +4,7 @@
 
 #include "../csrc/lgr_pack.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -321,7 +322,9 @@ GpuFormatMetrics::~GpuFormatMetrics() { lgr_format_destroy(mCtx); }
 std::vector<lgr_format> GpuFormatMetrics::Compute(EvidenceColumns& columns, float* ms_kernels) {
   std::vector<lgr_format> out(columns.NumSupports());
   const int rc = lgr_format_metrics(mCtx, &columns.In(), out.data(), ms_kernels);
-  if (rc != LGR_OK)
+  // LGR_E_PARTIAL: supports of sites with more than LGR_FMT_MAX_ALLELES alleles come back flagged LGR_FMT_WIDE
+  // (variant_support.cpp:294-335 takes any K); they do not fail the batch
+  if (rc != LGR_OK && rc != LGR_E_PARTIAL)
     throw std::runtime_error(std::string("lancet_gpu::GpuFormatMetrics: ") + lgr_strerror(rc) + ": " + lgr_format_last_error(mCtx));
   return out;
 }
@@ -505,6 +508,18 @@ GenotypeBatcher::GenotypeBatcher(const Options& opt, NameHashFn name_hash) : mOp
     mFree.push_back(s.get());
     mSlabs.push_back(std::move(s));
   }
+  // result blocks are sized once, generously: growing one means cudaFreeHost + cudaHostAlloc (hundreds of
+  // microseconds on the batcher thread, and a device-wide synchronisation) — measured as the bulk of the
+  // per-batch submit time when the blocks were sized to each batch
+  for (int i = 0; i < n_slabs + 2; ++i) {
+    auto r = std::make_unique<ResultBlock>();
+    r->job_asg.resize(mOpt.max_jobs), r->job_mid.resize(mOpt.max_jobs);
+    r->assign_cap = mOpt.result_records;
+    r->assign = static_cast<lgr_assign*>(PinnedOrThrow(r->assign_cap * sizeof(lgr_assign) + sizeof(std::int32_t) * mOpt.max_jobs));
+    r->status = reinterpret_cast<std::int32_t*>(r->assign + r->assign_cap);
+    mFreeResults.push_back(r.get());
+    mResults.push_back(std::move(r));
+  }
   mThread = std::thread([this] { Run(); });
 }
 
@@ -643,7 +658,7 @@ void GenotypeBatcher::SealAndSubmit(Slab* s) {
     if (!r->assign || static_cast<std::size_t>(s->n_assign) + 1 > r->assign_cap) {
       lgr_free_pinned(r->assign);
       r->assign = nullptr, r->assign_cap = 0, r->status = nullptr;
-      const std::size_t want = static_cast<std::size_t>(s->n_assign) + static_cast<std::size_t>(s->n_assign) / 2 + 4096;
+      const std::size_t want = std::max<std::size_t>(mOpt.result_records, static_cast<std::size_t>(s->n_assign) + static_cast<std::size_t>(s->n_assign) / 2 + 4096);
       r->assign = static_cast<lgr_assign*>(PinnedOrThrow(want * sizeof(lgr_assign) + sizeof(std::int32_t) * mOpt.max_jobs));
       r->assign_cap = want;
       r->status = reinterpret_cast<std::int32_t*>(r->assign + want);

@@ -289,7 +289,8 @@ class GenotypeBatcher {
     int linger_us = 100;                 // idle GPU: wait this long for more workers to arrive before launching
     int max_wait_us = 400;               // busy GPU: a slab waits at most this long for min_pairs_busy
     std::int64_t min_pairs_busy = 49152; // busy GPU: pairs that make a batch worth its launch overhead
-    std::size_t slab_bytes = 32u << 20;  // pinned staging per slab (grown when one payload needs more)
+    std::size_t slab_bytes = 32u << 20;  // pinned staging per slab (a payload larger than this travels alone)
+    std::size_t result_records = 1u << 18;  // lgr_assign records per pinned result block (grown if a batch needs more)
     const lgr_params* params = nullptr;
   };
   struct Counters {

@@ -316,3 +316,49 @@ def load_golden_edge():
     sups = [c["support"] for c in g["edge"]]
     want = np.frombuffer(bytes.fromhex("".join(c["record"] for c in g["edge"])), dtype=abi.FORMAT_DTYPE).copy()
     return sups, want
+
+
+# ---------------------------------------------------------------------------------------------
+# The text a VCF reader sees.  north_star: "and therefore the final VCF records" must be equal.
+# VariantCall narrows VariantSupport's f64 metrics to f32 and SampleFormatData prints them with fixed
+# precision (reference: src/lancet/caller/variant_call.cpp:160-209 (narrowing, NPBQ = raw PBQ / depth,
+# :366-379), sample_format_data.cpp:45-92 (formats: RMQ/NPBQ "%.1F" on f32, SB "{:.3f}", SCA "{:.4f}",
+# FLD "{:.1f}", RPCD/BQCD/MQCD/FSSE/HSE "{:.4f}", ASMD/AHDD "{:.3f}", CMLOD "%.4F" on f64 from index 1,
+# PL joined by ',', missing optional = ".")).  Those two files need fmt and abseil, which are not in
+# this container, so the formatting is restated here: printf-style fixed formatting of the exact binary
+# value, which is what both fmt and absl::StrFormat produce.  Fields that VariantCall derives from
+# other inputs (GT, DP, SDFC, PRAD, PANG, PDCV) are not part of lgr_format and are left out.
+# ---------------------------------------------------------------------------------------------
+def render_vcf_fields(rec) -> str:
+    k = int(rec["n_alleles"])
+    f32 = np.float32
+
+    def fx(v, nd):  # fixed formatting of an f32 value
+        return f"%.{nd}f" % float(f32(v))
+
+    def opt(name, nd):
+        return fx(rec[name], nd) if int(rec["valid"]) & abi.LGR_FMT_HAS[name] else "."
+
+    ad = [int(rec["fwd"][a]) + int(rec["rev"][a]) for a in range(k)]
+    npbq = [float(rec["raw_pbq"][a]) / ad[a] if ad[a] > 0 else 0.0 for a in range(k)]
+    parts = [
+        ",".join(str(x) for x in ad), ",".join(str(int(rec["fwd"][a])) for a in range(k)),
+        ",".join(str(int(rec["rev"][a])) for a in range(k)),
+        ",".join(fx(rec["rms_mq"][a], 1) for a in range(k)), ",".join(fx(v, 1) for v in npbq),
+        fx(rec["sb"], 3), fx(rec["sca"], 4), opt("fld", 1), opt("rpcd", 4), opt("bqcd", 4), opt("mqcd", 4), opt("asmd", 3),
+        ",".join("%.4f" % float(rec["cmlod"][a]) for a in range(1, k)) if k >= 2 else ".",
+        opt("fsse", 4), opt("ahdd", 3), opt("hse", 4),
+        ",".join(str(int(x)) for x in rec["pl"][:k * (k + 1) // 2]), str(int(rec["gq"])),
+    ]
+    return ":".join(parts)
+
+
+def vcf_string_mismatches(want, got, limit=10):
+    bad = []
+    for i, (w, g) in enumerate(zip(want, got)):
+        a, b = render_vcf_fields(w), render_vcf_fields(g)
+        if a != b:
+            bad.append(f"support {i}: reference {a}\n{' ' * (len(str(i)) + 10)}     ours {b}")
+            if len(bad) >= limit:
+                break
+    return bad

@@ -222,3 +222,29 @@ def test_fuzz_up_to_eight_alleles_against_live_reference():
     for got in (F.emu_format(sups)[1], F.emu_format_sort(sups)[1]):   # scan build and sort build
         errs = F.compare_format(want, got)
         assert not errs, "\n".join(errs[:20])
+
+
+def test_vcf_text_of_golden_supports_equals_the_references():
+    """the FORMAT text a VCF reader sees (f32 narrowing + fixed precision, format_lib.render_vcf_fields):
+    the golden records made by the reference's own VariantSupport against the host build of the core"""
+    sups, want, _ = F.load_golden()
+    rc, got = F.emu_format(sups)
+    assert rc == 0
+    assert not F.vcf_string_mismatches(want, got)
+    esups, ewant = F.load_golden_edge()
+    rc, egot = F.emu_format(esups)
+    assert rc == 0 and not F.vcf_string_mismatches(ewant, egot)
+
+
+@pytest.mark.skipif(not F.have_ref(), reason="oracle/_ref not built (needs the reference tree)")
+def test_vcf_text_of_ten_thousand_random_supports_equals_the_live_reference():
+    """1e-9 relative agreement does not by itself exclude a flipped rounding boundary in the printed
+    text: 10^4 random supports rendered from the live reference and from the core must be identical
+    strings"""
+    rng = np.random.default_rng(2026)
+    sups = [F.random_support(rng) for _ in range(10_000)]
+    want = F.ref_format(sups)
+    rc, got = F.emu_format(sups)
+    assert rc == 0
+    bad = F.vcf_string_mismatches(want, got)
+    assert not bad, "\n".join(bad)

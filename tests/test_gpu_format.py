@@ -91,7 +91,26 @@ def test_gpu_format_argument_errors(fmt):
     bad["allele"] = np.array([0, 1, 2, 0, 1])
     with pytest.raises(RuntimeError, match="allele index"):
         fmt.compute([bad])
-    bad = F.random_support(rng, n=5, n_alleles=2)
-    bad["n_alleles"] = 9
-    with pytest.raises(RuntimeError, match="LGR_FMT_MAX_ALLELES"):
-        fmt.compute([bad])
+    # a site with more alleles than a record holds (STR loci): flagged per support, the batch is not failed
+    wide = F.random_support(rng, n=40, n_alleles=11)
+    ok = [F.random_support(rng, n=30, n_alleles=3), F.random_support(rng, n=25, n_alleles=8)]
+    got, _ = fmt.compute([ok[0], wide, ok[1]])
+    assert fmt.last_rc == abi.LGR_E_PARTIAL
+    assert got[1]["valid"] == abi.LGR_FMT_WIDE and got[1]["n_alleles"] == 11 and got[1]["n_kept"] == 0
+    alone, _ = fmt.compute(ok)
+    assert fmt.last_rc == 0 and got[0].tobytes() == alone[0].tobytes() and got[2].tobytes() == alone[1].tobytes()
+
+
+def test_gpu_vcf_text_equals_the_references(fmt):
+    """the device records rendered the way VariantCall / SampleFormatData print them must be the same
+    text as the reference's: golden supports always, 10^4 random ones when oracle/_ref travelled"""
+    sups, want, _ = F.load_golden()
+    got, _ = fmt.compute(sups)
+    bad = F.vcf_string_mismatches(want, got)
+    assert not bad, "\n".join(bad)
+    if F.have_ref():
+        rng = np.random.default_rng(2026)
+        rs = [F.random_support(rng) for _ in range(10_000)]
+        got, _ = fmt.compute(rs)
+        bad = F.vcf_string_mismatches(F.ref_format(rs), got)
+        assert not bad, "\n".join(bad)

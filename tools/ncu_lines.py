@@ -16,13 +16,14 @@ def main():
     top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-    # find the function section
-    start = None
-    for i, l in enumerate(dis):
-        if l.startswith(".text.") and kern in l and l.rstrip().endswith(":"):
-            start = i
+    start, dis = None, []
+    for cubin in sorted(os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")):  # one per translation unit
+        dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+        for i, l in enumerate(dis):
+            if l.startswith(".text.") and kern in l and l.rstrip().endswith(":"):
+                start = i
+                break
+        if start is not None:
             break
     assert start is not None, "kernel not found"
     line_of = []  # per instruction index → (file, line)
