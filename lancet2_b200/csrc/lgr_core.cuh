@@ -786,7 +786,6 @@ struct PairIn {          // everything phase A needs about one (read, haplotype)
 
 struct ChainCounters {
   int64_t chain_evals, n_anchors, dp_cells, dp_cells_full;
-  int64_t n_aligned = 0;  // pairs finished (valid) inside the chain kernel
 };
 
 // lower bound in the sorted minimizer table

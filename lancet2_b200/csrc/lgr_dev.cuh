@@ -16,7 +16,6 @@ enum Ctr {
   C_ITEM = 0, C_NTASK, C_NTASK1, C_NTASK2, C_NTASK3, C_NTASK4, C_REGS, C_EXTARENA, C_CIGARENA, C_NOVF, C_ERR, C_EVALS, C_ANCH, C_CELLS, C_CELLSFULL,
   C_ALIGNED, C_TASKPOS, C_TASKPOS1, C_TASKPOS2, C_TASKPOS3, C_TASKPOS4, C_FINPOS, C_OVFPOS, C_OVFNEED, C_NCOLD, C_COLDPOS,
   C_COLD_HIGH, C_COLD_SORT, C_COLD_TAIL, C_COLD_LONG,  // why pairs went to the cold kernel (diagnostics)
-  C_ALIGNED_FUSED,                                     // valid alignments finished inside the chain kernels
   C_COUNT
 };
 enum ErrBits { E_REG_ARENA = 1, E_EXT_ARENA = 2, E_CIG_ARENA = 4, E_ANCHOR_CAP = 8, E_CIG_SCRATCH = 16, E_MZ_CAP = 32 };
@@ -158,7 +157,9 @@ __device__ __forceinline__ void store_final(const Dev& D, int g, int64_t pair, c
   if (nc <= LGR_CIGAR_INLINE) {
     o.cigar_off = -1;
     uint32_t* dst = D.cigar_inline + pair * LGR_CIGAR_INLINE;
-    for (int i = 0; i < nc; ++i) dst[i] = cig[i];
+    if (nc == 1) dst[0] = cig[0];  // the common case: one M run
+    else
+      for (int i = 0; i < nc; ++i) dst[i] = cig[i];
   } else {
     const long long off = atomicAdd((unsigned long long*)&D.ctr[C_CIGARENA], (unsigned long long)nc);
     if (off + nc > D.cigar_arena_cap) {
@@ -169,7 +170,10 @@ __device__ __forceinline__ void store_final(const Dev& D, int g, int64_t pair, c
       for (int i = 0; i < nc; ++i) D.cigar_arena[off + i] = cig[i];
     }
   }
-  D.aln[pair] = o;
+  // 64-byte record, 64-byte aligned: four 16-byte stores
+  const uint4* src = reinterpret_cast<const uint4*>(&o);
+  uint4* dst = reinterpret_cast<uint4*>(&D.aln[pair]);
+  dst[0] = src[0], dst[1] = src[1], dst[2] = src[2], dst[3] = src[3];
 }
 
 }  // namespace

@@ -781,7 +781,7 @@ static int run_finish(lgr_ctx* c, lgr_stats* st) {
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[9]); st->ms_k_map = ms;
     cudaEventElapsedTime(&ms, c->ev[9], c->ev[3]); st->ms_k_ext = ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); st->ms_k_assign = ms;
-    st->n_pairs = D.n_pairs, st->n_aligned = hctr[C_ALIGNED] + hctr[C_ALIGNED_FUSED];
+    st->n_pairs = D.n_pairs, st->n_aligned = hctr[C_ALIGNED];
     st->dp_cells = hctr[C_CELLS], st->dp_cells_full = hctr[C_CELLSFULL];
     st->chain_evals = hctr[C_EVALS], st->n_anchors = hctr[C_ANCH];
     st->kernel_launches = launches;

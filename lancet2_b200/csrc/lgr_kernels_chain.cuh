@@ -223,19 +223,24 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     const bool strictly = __all_sync(full, strict);
     if (sorted && (n_a <= 64 || strictly)) {
       for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
-    } else if (n_a <= 64) {
+    } else if (!HOT && n_a <= 64) {
       // upstream's radix_sort_128x is an insertion sort up to 64 elements, i.e. STABLE: the result is
-      // the unique stable order, which the warp gets by ranking (two elements per lane, n_a broadcast
-      // reads each) — typically two reverse-strand anchors of a short palindrome sit mid-list
-      for (int i = lane; i < n_a; i += 32) {
-        const uint32_t xi = (uint32_t)ax[i];
+      // the unique stable order, which the warp gets by ranking instead of sorting on one lane
+      // (typically two reverse-strand anchors of a short palindrome sit mid-list).  Warp-uniform trip
+      // counts on purpose: a lane-dependent loop here cost the whole kernel its convergence (measured:
+      // +0.8 ms on cfg2 when this ran in the hot kernel), so these pairs stay with the cold kernel.
+      for (int base = 0; base < n_a; base += 32) {
+        const int i = base + lane;
+        const uint32_t xi = i < n_a ? (uint32_t)ax[i] : 0u;
         int rank = 0;
         for (int j = 0; j < n_a; ++j) {
           const uint32_t xj = (uint32_t)ax[j];
           rank += (xj < xi) || (xj == xi && j < i);
         }
-        sx[rank] = (int32_t)xi, sy[rank] = ay[i];
+        __syncwarp();
+        if (i < n_a) sx[rank] = (int32_t)xi, sy[rank] = ay[i];
       }
+      __syncwarp();
     } else {
       if (HOT) {
         if (lane == 0) atomicAdd((unsigned long long*)&D.ctr[C_COLD_SORT], 1ULL);
@@ -713,49 +718,6 @@ __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, in
       if (s_reg->ext[side].m <= 0) continue;
       if (!warp_ext_exact(D.P, rv, hapc, s_reg, side, &ctr.dp_cells_full)) task_mask |= 1u << side;
     }
-    if (task_mask == 0 && s_reg->rev == 0) {
-      // Nine pairs in ten end here: one forward-strand reg whose tails were both closed forms of pure
-      // matches (or absent).  Its cigar is ONE M run, so mm_append_cigar x3 / mm_fix_cigar reduce to
-      // arithmetic (assemble_fix_reg with n == 1) and the rest of the finish stage is the single pass
-      // warp_finish_pure_m over the aligned columns: the record is written here and the reg never
-      // travels through HBM to k_finish_warp.  Same statements as finish_pair_warp for this shape.
-      const ExtRec& L = s_reg->ext[0];
-      const ExtRec& R = s_reg->ext[1];
-      const bool lok = L.m <= 0 || (L.n_cig == 1 && (L.inl[0] & 0xf) == 0);
-      const bool rok = R.m <= 0 || (R.n_cig == 1 && (R.inl[0] & 0xf) == 0);
-      if (lok && rok) {
-        int32_t dp_ext = 0, rs1 = s_reg->c_rs, qs1 = s_reg->c_qs, re1 = s_reg->c_re, qe1 = s_reg->c_qe;
-        int32_t len = s_reg->c_qe - s_reg->c_qs;
-        if (L.m > 0) len += (int32_t)(L.inl[0] >> 4), dp_ext += L.max, rs1 = s_reg->c_rs - (L.mqe_t + 1), qs1 = 0;
-        if (R.m > 0) len += (int32_t)(R.inl[0] >> 4), dp_ext += R.max, re1 = s_reg->c_re + (R.mqe_t + 1), qe1 = qlen;
-        RegFinal rf;
-        int32_t core = 0, nm = 0;
-        warp_finish_pure_m(D.P, rv.codes, hapc, qs1, rs1, len, s_reg->c_qs, s_reg->c_qe, &rf, &core, &nm);
-        bool flt = false;
-        if (s_reg->cnt < D.P.min_cnt) flt = true;
-        if (rf.mlen < D.P.min_sc) flt = true;
-        else if (rf.dp_max < D.P.min_dp_max) flt = true;
-        else if ((float)qs1 > (float)qlen * D.P.max_clip_ratio && (float)(qlen - qe1) > (float)qlen * D.P.max_clip_ratio) flt = true;
-        if (lane == 0) {
-          AlnOut o;
-          if (flt) {
-            write_invalid(&o);
-          } else {
-            o.valid = 1, o.score = s_reg->score, o.rs = rs1, o.re = re1, o.qs = qs1, o.qe = qe1, o.rev = 0;
-            o.dp_score = dp_ext + core, o.dp_max = rf.dp_max, o.mlen = rf.mlen, o.blen = rf.blen, o.n_ambi = rf.n_ambi;
-            o.nm = nm, o.n_cigar = 1, o.cigar_off = -1, o.n_regs = 1;
-            D.cigar_inline[pair * LGR_CIGAR_INLINE] = (uint32_t)len << 4;
-          }
-          const uint4* src = reinterpret_cast<const uint4*>(&o);
-          uint4* dst = reinterpret_cast<uint4*>(&D.aln[pair]);
-          dst[0] = src[0], dst[1] = src[1], dst[2] = src[2], dst[3] = src[3];
-          D.pair_reg[pair] = PairReg{0, 0, r, h};
-        }
-        ctr.n_aligned += flt ? 0 : 1;
-        __syncwarp();
-        return;
-      }
-    }
     long long first = -1;
     if (lane == 0) {
       first = atomicAdd((unsigned long long*)&D.ctr[C_REGS], 1ULL);
@@ -877,7 +839,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
     atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
     atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
-    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED_FUSED], (unsigned long long)ctr.n_aligned);
   }
 }
 
@@ -911,7 +872,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_chain_cold(const __grid_c
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);
     atomicAdd((unsigned long long*)&D.ctr[C_ANCH], (unsigned long long)ctr.n_anchors);
     atomicAdd((unsigned long long*)&D.ctr[C_CELLSFULL], (unsigned long long)ctr.dp_cells_full);
-    atomicAdd((unsigned long long*)&D.ctr[C_ALIGNED_FUSED], (unsigned long long)ctr.n_aligned);
   }
 }
 

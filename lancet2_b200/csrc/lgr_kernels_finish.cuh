@@ -196,7 +196,7 @@ constexpr int kFinChunk = LGR_FIN_CHUNK;  // pairs a warp takes from the finish 
 constexpr int kFinSmemCig = 64;  // cigar ops of a reg kept in shared memory; longer ones use the HBM scratch
 
 __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
-                                             FinishScratch& fs, TrackBlock* trk, AlnOut* out) {
+                                             FinishScratch& fs, TrackBlock* trk, RegRec* s_reg, AlnOut* out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
@@ -209,18 +209,44 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
   int32_t *s_qs = trk->qs, *s_qe = trk->qe, *s_rs = trk->rs, *s_re = trk->re, *s_score = trk->score;
   uint64_t* s_key = trk->key;
   for (int r = 0; r < n_regs; ++r) {
-    RegAsm ra;
-    int okf = 1;
-    if (lane == 0) okf = assemble_fix_reg(rv, hap, regs[r], D.ext_arena, fs.cig, fs.cap, &ra) ? 1 : 0;
-    okf = __shfl_sync(full, okf, 0);
-    if (!okf) return -1;
-    ra.n = __shfl_sync(full, ra.n, 0), ra.rs = __shfl_sync(full, ra.rs, 0), ra.re = __shfl_sync(full, ra.re, 0);
-    ra.qs = __shfl_sync(full, ra.qs, 0), ra.qe = __shfl_sync(full, ra.qe, 0), ra.qb = __shfl_sync(full, ra.qb, 0);
-    ra.tb = __shfl_sync(full, ra.tb, 0), ra.dp_ext = __shfl_sync(full, ra.dp_ext, 0);
+    // the reg comes out of HBM once, in one coalesced read, and is read from shared memory from here on
     __syncwarp();
-    const int rev = regs[r].rev, c_qs = regs[r].c_qs, c_qe = regs[r].c_qe, c_rs = regs[r].c_rs;
-    const int32_t score = regs[r].score, cnt = regs[r].cnt;
-    const uint32_t hash = regs[r].hash;
+    {
+      constexpr int kWords = (int)(sizeof(RegRec) / 4);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&regs[r]);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(s_reg);
+      for (int w = lane; w < kWords; w += 32) dst[w] = src[w];
+    }
+    __syncwarp();
+    const RegRec& rg = *s_reg;
+    RegAsm ra;
+    const ExtRec& L = rg.ext[0];
+    const ExtRec& R = rg.ext[1];
+    const bool pure = rg.rev == 0 && (L.m <= 0 || (L.n_cig == 1 && (L.inl[0] & 0xf) == 0)) &&
+                      (R.m <= 0 || (R.n_cig == 1 && (R.inl[0] & 0xf) == 0));
+    if (pure) {
+      // both tails are pure match runs (or absent) on the forward strand: mm_append_cigar x3 merges them
+      // with the core into ONE M op and mm_fix_cigar has nothing to do (assemble_fix_reg with n == 1) —
+      // plain arithmetic on every lane instead of the scalar assembly on lane 0 and eight broadcasts
+      int32_t len = rg.c_qe - rg.c_qs;
+      ra.dp_ext = 0, ra.rs = rg.c_rs, ra.qs = rg.c_qs, ra.re = rg.c_re, ra.qe = rg.c_qe;
+      if (L.m > 0) len += (int32_t)(L.inl[0] >> 4), ra.dp_ext += L.max, ra.rs = rg.c_rs - (L.mqe_t + 1), ra.qs = 0;
+      if (R.m > 0) len += (int32_t)(R.inl[0] >> 4), ra.dp_ext += R.max, ra.re = rg.c_re + (R.mqe_t + 1), ra.qe = qlen;
+      ra.n = 1, ra.qb = ra.qs, ra.tb = ra.rs;
+      if (lane == 0) fs.cig[0] = (uint32_t)len << 4;
+    } else {
+      int okf = 1;
+      if (lane == 0) okf = assemble_fix_reg(rv, hap, rg, D.ext_arena, fs.cig, fs.cap, &ra) ? 1 : 0;
+      okf = __shfl_sync(full, okf, 0);
+      if (!okf) return -1;
+      ra.n = __shfl_sync(full, ra.n, 0), ra.rs = __shfl_sync(full, ra.rs, 0), ra.re = __shfl_sync(full, ra.re, 0);
+      ra.qs = __shfl_sync(full, ra.qs, 0), ra.qe = __shfl_sync(full, ra.qe, 0), ra.qb = __shfl_sync(full, ra.qb, 0);
+      ra.tb = __shfl_sync(full, ra.tb, 0), ra.dp_ext = __shfl_sync(full, ra.dp_ext, 0);
+    }
+    __syncwarp();
+    const int rev = rg.rev, c_qs = rg.c_qs, c_qe = rg.c_qe, c_rs = rg.c_rs;
+    const int32_t score = rg.score, cnt = rg.cnt;
+    const uint32_t hash = rg.hash;
     RegFinal rf;
     int32_t nm_reg = -1;
     if (ra.n == 1 && rev == 0 && (fs.cig[0] & 0xf) == 0) {
@@ -277,6 +303,7 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   __shared__ TrackBlock s_trk[4];
   __shared__ uint32_t s_cig[4][2 * kFinSmemCig];
+  __shared__ RegRec s_regs[4];
   uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
   TrackBlock* trk = &s_trk[threadIdx.x >> 5];
   uint32_t* scig = s_cig[threadIdx.x >> 5];
@@ -302,11 +329,11 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_
     // cigars live in shared memory; the rare reg with more ops than fit reruns on the HBM scratch
     FinishScratch fs{scig, scig + kFinSmemCig, kFinSmemCig};
     AlnOut ao;
-    int nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &ao);
+    int nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &s_regs[threadIdx.x >> 5], &ao);
     if (nc < 0) {
       __syncwarp();
       fs = FinishScratch{fin0, fin0 + D.fin_cap, D.fin_cap};
-      nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &ao);
+      nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &s_regs[threadIdx.x >> 5], &ao);
     }
     if (lane == 0) {
       if (nc < 0) {
