@@ -4,7 +4,7 @@ length 300-1500 bp x 2-64 haplotypes per window (SURVEY.md §8d cfg 5: hap 0 ran
 = hap 0 + one spiked variant, R = 512 reads sampled from the P haps, 5 % overhanging).
 One JSON line per point: resident-batch pairs/s (CUDA events, L2 flushed), DP cells/s, chain
 evaluations/s, and a bit-exact check of the first groups against the oracle.
-usage: python tools/bench_sweep.py [--pairs 262144] [--steps 5] > profiles/r1_sweep.jsonl"""
+usage: python tools/bench_sweep.py [--pairs 262144] [--steps 5] > profiles/r2_sweep.jsonl"""
 import argparse
 import json
 import os
@@ -38,7 +38,7 @@ def main():
                 want, _ = O.oracle_genotype(chk, gpu.params, n_threads=os.cpu_count() or 1)
                 got, _ = gpu.genotype_batch(chk)
                 ok = not compare_results(chk, want, got)
-                gpu.upload(batch)
+                gpu.upload_packed(abi.PackedBatch(groups, gpu.lib))  # the product path: packed wire format, unpack inside the step
                 for _ in range(3):
                     gpu.run_resident()
                 ms, st = 0.0, None
