@@ -75,7 +75,9 @@ struct Dev {      // everything the kernels need, passed by value
   const lgr_group_dir* dir;
   int64_t *grp_hapbase, *grp_readbase, *grp_vh, *grp_pair, *grp_asg;
   int32_t* grp_item;
-  int32_t *hap_chk, *read_chk;  // [NH] / [NR] first plane chunk of every sequence within its group record
+  uint64_t *hap_plane, *read_plane;  // [NH] / [NR] slab offset of every sequence's first plane word (| kSeqHasExc)
+  uint64_t* read_qoff;               // [NR] slab offset of the read's quality data | quality plane count << 56
+  uint32_t* grp_lut;                 // [G][4] the groups' quality dictionaries
   int item_reads;               // reads per phase-A work item
   int mid_occ_param;            // lgr_params::mid_occ
   uint64_t* mz_x;               // [read_off-indexed]

@@ -80,7 +80,7 @@ struct lgr_ctx {
       b_item_n, b_hap_codes, b_read_codes, b_idx, b_idx_n, b_hap_mid, b_grp_mid, b_mz_x, b_mz_y, b_mz_n, b_fin, b_regs,
       b_pair_reg, b_ext_arena, b_ovf_read, b_ovf_hap, b_dir, b_bnd, b_wcig, b_aln, b_cig_inline, b_cig_arena, b_assign,
       b_ctr, b_ws_big, b_wreg, b_rsx, b_bkt, b_mz_cnt, b_tasks, b_grp_mid_req, b_grp_err, b_slab, b_dir_tab, b_grp_hapbase,
-      b_grp_readbase, b_grp_vh, b_grp_pair, b_grp_asg, b_grp_item, b_cold_read, b_cold_hap, b_hap_chk, b_read_chk;
+      b_grp_readbase, b_grp_vh, b_grp_pair, b_grp_asg, b_grp_item, b_cold_read, b_cold_hap, b_hap_chk, b_read_chk, b_read_qoff, b_grp_lut;
   Dev D;
   bool resident = false, packed = false;
   int occ_cap = 0, warp_blocks_full = 0, ext_blocks_full = 0, fin_blocks_full = 0, overflow_passes = 0;
@@ -490,7 +490,8 @@ static int plan_batch(lgr_ctx* c, const BatchSizes& z) {
   ENS(b_slab, z.slab_bytes); ENS(b_dir_tab, z.dir_bytes);
   ENS(b_grp_hapbase, sizeof(int64_t) * (G + 1)); ENS(b_grp_readbase, sizeof(int64_t) * (G + 1)); ENS(b_grp_vh, sizeof(int64_t) * (G + 1));
   ENS(b_grp_pair, sizeof(int64_t) * (G + 1)); ENS(b_grp_asg, sizeof(int64_t) * (G + 1)); ENS(b_grp_item, sizeof(int32_t) * (G + 1));
-  ENS(b_hap_chk, z.ascii ? 0 : sizeof(int32_t) * NH); ENS(b_read_chk, z.ascii ? 0 : sizeof(int32_t) * NR);
+  ENS(b_hap_chk, z.ascii ? 0 : sizeof(uint64_t) * NH); ENS(b_read_chk, z.ascii ? 0 : sizeof(uint64_t) * NR);
+  ENS(b_read_qoff, z.ascii ? 0 : sizeof(uint64_t) * NR); ENS(b_grp_lut, z.ascii ? 0 : 16 * (size_t)G);
   if ((rc = ensure(c, c->arena, c->arena_off)) != LGR_OK) return rc;
   for (DevBuf* b : c->views) b->p = static_cast<uint8_t*>(c->arena.p) + b->off;
   Dev& D = c->D;
@@ -638,7 +639,8 @@ static int upload_packed_impl(lgr_ctx* c, const lgr_packed_in* in, int64_t* h2d_
   D.dir = dir_inside ? reinterpret_cast<const lgr_group_dir*>(D.slab + (dirp - slab)) : (const lgr_group_dir*)c->b_dir_tab.p;
   D.grp_hapbase = (int64_t*)c->b_grp_hapbase.p, D.grp_readbase = (int64_t*)c->b_grp_readbase.p, D.grp_vh = (int64_t*)c->b_grp_vh.p;
   D.grp_pair = (int64_t*)c->b_grp_pair.p, D.grp_asg = (int64_t*)c->b_grp_asg.p, D.grp_item = (int32_t*)c->b_grp_item.p;
-  D.hap_chk = (int32_t*)c->b_hap_chk.p, D.read_chk = (int32_t*)c->b_read_chk.p;
+  D.hap_plane = (uint64_t*)c->b_hap_chk.p, D.read_plane = (uint64_t*)c->b_read_chk.p;
+  D.read_qoff = (uint64_t*)c->b_read_qoff.p, D.grp_lut = (uint32_t*)c->b_grp_lut.p;
   c->packed = true;
   c->resident = true;
   if (h2d_bytes) *h2d_bytes = h2d;

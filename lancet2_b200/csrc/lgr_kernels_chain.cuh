@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
 //   finish    scalar core on lane 0 (cigar assembly, mm_fix_cigar, mm_update_extra, NM)
 // Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_chain_overflow).
 // ---------------------------------------------------------------------------------------
+#ifndef LGR_HOT_WARP_SORT
+#define LGR_HOT_WARP_SORT 0  // 1: the hot kernel ranks unsorted anchor lists itself instead of queueing the pair for the cold kernel
+#endif
 constexpr int kWarpsPerCta = 4;
 constexpr int kMapOkColinear = 2;  // warp_seed_chain: chain DP done by the co-linear closed form
 constexpr int kMapCold = -3;       // hot kernel only: a shape whose code lives in the cold kernel (queued, not computed)
@@ -223,7 +226,7 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     const bool strictly = __all_sync(full, strict);
     if (sorted && (n_a <= 64 || strictly)) {
       for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
-    } else if (!HOT && n_a <= 64) {
+    } else if ((!HOT || LGR_HOT_WARP_SORT) && n_a <= 64) {
       // upstream's radix_sort_128x is an insertion sort up to 64 elements, i.e. STABLE: the result is
       // the unique stable order, which the warp gets by ranking instead of sorting on one lane
       // (typically two reverse-strand anchors of a short palindrome sit mid-list).  Warp-uniform trip

@@ -91,14 +91,25 @@ __global__ void __launch_bounds__(1024) k_unpack_scan(const __grid_constant__ De
 constexpr int kUnpackThreads = 256;
 
 // offsets of the sequences of one kind (haplotypes or reads) of one group: block scans of the lengths
+constexpr uint64_t kSeqHasExc = 1ull << 55;  // descriptor flag: the sequence's group carries an exception list
+
+// offsets of the sequences of one kind (haplotypes or reads) of one group: block scans of the lengths.
+// Besides the offset arrays every sequence gets a descriptor for k_unpack_decode: the absolute slab
+// offset of its first plane word (and, for reads, of its quality data, with the plane count in the top
+// byte), so that the decode kernel reaches the payload bytes without walking directory → record header.
 template <bool READS>
-__device__ __forceinline__ void unpack_offsets(const Dev& D, const uint8_t* rec, const lgr_group_rec_hdr& hdr, int n_seq, int first,
-                                               long long gbase, int g, long long pair0, long long asg0, int P, int V, long long* s_w) {
+__device__ __forceinline__ void unpack_offsets(const Dev& D, const uint8_t* rec, const lgr_group_rec_hdr& hdr, uint64_t rec_off, int n_seq,
+                                               int first, long long gbase, int g, long long pair0, long long asg0, int P, int V,
+                                               long long* s_w) {
   const int tid = threadIdx.x;
   const int32_t* hap_len = reinterpret_cast<const int32_t*>(rec + hdr.off_hap_len);
   const uint16_t* read_len = reinterpret_cast<const uint16_t*>(rec + hdr.off_read_len);
   int64_t* out_off = const_cast<int64_t*>(READS ? D.read_off : D.hap_off) + first;
-  int32_t* out_chk = (READS ? D.read_chk : D.hap_chk) + first;
+  uint64_t* out_plane = (READS ? D.read_plane : D.hap_plane) + first;
+  const uint64_t exc = hdr.n_exc ? kSeqHasExc : 0;
+  const uint64_t plane0 = rec_off + (READS ? hdr.off_read_planes : hdr.off_hap_planes);
+  const uint64_t qual0 = rec_off + hdr.off_qual;
+  const uint64_t qbits = hdr.qual_bits;
   long long carry_off = 0, carry_chk = 0;
   for (int base = 0; base < n_seq; base += kUnpackThreads) {
     const int i = base + tid;
@@ -107,10 +118,12 @@ __device__ __forceinline__ void unpack_offsets(const Dev& D, const uint8_t* rec,
     const long long ex_len = block_excl_scan<kUnpackThreads / 32>(len, s_w, &t_len);
     const long long ex_chk = block_excl_scan<kUnpackThreads / 32>((len + 31) >> 5, s_w, &t_chk);
     if (i < n_seq) {
-      out_off[i] = gbase + carry_off + ex_len;
-      out_chk[i] = (int32_t)(carry_chk + ex_chk);
+      const long long off = carry_off + ex_len, chk = carry_chk + ex_chk;
+      out_off[i] = gbase + off;
+      out_plane[i] = (plane0 + 8ull * (uint64_t)chk) | exc;
       if (READS) {
         const int r = first + i;
+        D.read_qoff[r] = (qbits == 8 ? qual0 + (uint64_t)off : qual0 + 4ull * qbits * (uint64_t)chk) | qbits << 56;
         const_cast<int32_t*>(D.read_grp)[r] = g;
         const_cast<int64_t*>(D.pair_off)[r] = pair0 + (long long)i * P;
         const_cast<int64_t*>(D.asg_off)[r] = asg0 + (long long)i * V;
@@ -135,8 +148,9 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack_group(const __grid_co
     const int hb = D.grp_hap_begin[g], rb = D.grp_read_begin[g], vb = D.grp_var_begin[g];
     const long long hbase = D.grp_hapbase[g], rbase = D.grp_readbase[g], vh0 = D.grp_vh[g];
     const long long pair0 = D.grp_pair[g], asg0 = D.grp_asg[g];
-    unpack_offsets<false>(D, rec, hdr, P, hb, hbase, g, 0, 0, P, V, s_w);
-    unpack_offsets<true>(D, rec, hdr, R, rb, rbase, g, pair0, asg0, P, V, s_w);
+    unpack_offsets<false>(D, rec, hdr, d.rec_off, P, hb, hbase, g, 0, 0, P, V, s_w);
+    unpack_offsets<true>(D, rec, hdr, d.rec_off, R, rb, rbase, g, pair0, asg0, P, V, s_w);
+    if (tid < 4) D.grp_lut[4 * (size_t)g + tid] = reinterpret_cast<const uint32_t*>(hdr.qual_lut)[tid];
     // ExtractHapBounds' dense table
     {
       const long long vh = (long long)V * P;
@@ -167,8 +181,9 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack_group(const __grid_co
 }
 
 // one WARP per sequence of the whole batch (haplotypes first, then reads): bit planes → code bytes
-// (and Phred bytes for reads), 32 coalesced bytes per step, then the sequence's share of its group's
-// exception list.  Flat over the batch, so the copy runs at memory speed whatever the group sizes.
+// (and Phred bytes for reads), 32 coalesced bytes per step, then the sequence's share of the exception
+// list.  Flat over the batch and fed by per-sequence descriptors (two independent loads, then the
+// payload), so the copy does not depend on group sizes or on a chain of header lookups.
 __global__ void __launch_bounds__(kUnpackThreads) k_unpack_decode(const __grid_constant__ Dev D) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -177,43 +192,44 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack_decode(const __grid_c
   for (long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_seq; q += warps) {
     const bool is_read = q >= D.n_haps;
     const int idx = is_read ? (int)(q - D.n_haps) : (int)q;
-    const int g = is_read ? D.read_grp[idx] : D.hap_grp[idx];
-    const uint8_t* rec = D.slab + D.dir[g].rec_off;
-    const lgr_group_rec_hdr* hdr = reinterpret_cast<const lgr_group_rec_hdr*>(rec);
     const int64_t* offs = is_read ? D.read_off : D.hap_off;
     const long long o = offs[idx];
     const int l = (int)(offs[idx + 1] - o);
-    const int c0 = is_read ? D.read_chk[idx] : D.hap_chk[idx];
-    const uint32_t* planes = reinterpret_cast<const uint32_t*>(rec + (is_read ? hdr->off_read_planes : hdr->off_hap_planes));
+    const uint64_t pd = is_read ? D.read_plane[idx] : D.hap_plane[idx];
+    const uint64_t qd = is_read ? D.read_qoff[idx] : 0;
+    const uint32_t* planes = reinterpret_cast<const uint32_t*>(D.slab + (pd & ~kSeqHasExc));
     uint8_t* codes = (is_read ? D.read_codes : D.hap_codes) + o;
     for (int c = 0; (c << 5) < l; ++c) {
-      const uint32_t lo = planes[2 * (size_t)(c0 + c)], hi = planes[2 * (size_t)(c0 + c) + 1];
+      const uint32_t lo = planes[2 * c], hi = planes[2 * c + 1];
       const int b = (c << 5) + lane;
       if (b < l) codes[b] = (uint8_t)(((lo >> lane & 1u) | (hi >> lane & 1u) << 1) * 0x11u);
     }
     if (is_read) {
-      const int qbits = (int)hdr->qual_bits;
+      const int qbits = (int)(qd >> 56);
+      const uint8_t* qsrc = D.slab + (qd & ((1ull << 55) - 1));
       uint8_t* quals = const_cast<uint8_t*>(D.read_quals) + o;
-      const long long in_group = o - D.grp_readbase[g];  // the read's first base within its group
       if (qbits == 8) {
-        const uint8_t* qraw = rec + hdr->off_qual + in_group;
-        for (int b = lane; b < l; b += 32) quals[b] = qraw[b];
+        for (int b = lane; b < l; b += 32) quals[b] = qsrc[b];
       } else {
-        const uint32_t* qplanes = reinterpret_cast<const uint32_t*>(rec + hdr->off_qual);
-        const uint32_t lut_lo = lane < 16 ? hdr->qual_lut[lane] : 0;  // dictionary entry `lane` lives in lane `lane`
+        const int g = D.read_grp[idx];
+        const uint32_t lutw = D.grp_lut[4 * (size_t)g + (lane >> 2 & 3)];
+        const uint32_t lut_lo = lutw >> (8 * (lane & 3)) & 0xffu;  // dictionary entry `lane` (< 16) lives in lane `lane`
+        const uint32_t* qplanes = reinterpret_cast<const uint32_t*>(qsrc);
         for (int c = 0; (c << 5) < l; ++c) {
           uint32_t k = 0;
-          for (int p = 0; p < qbits; ++p) k |= (qplanes[(size_t)(c0 + c) * qbits + p] >> lane & 1u) << p;
+          for (int p = 0; p < qbits; ++p) k |= (qplanes[c * qbits + p] >> lane & 1u) << p;
           const uint32_t v = __shfl_sync(full, lut_lo, (int)k);
           const int b = (c << 5) + lane;
           if (b < l) quals[b] = (uint8_t)v;
         }
       }
     }
-    // exceptions (N, IUPAC, U): the entries of the group that fall inside this sequence
-    const uint32_t n_exc = hdr->n_exc;
-    if (n_exc) {
+    if (pd & kSeqHasExc) {  // exceptions (N, IUPAC, U): the entries of the group that fall inside this sequence
       __syncwarp();
+      const int g = is_read ? D.read_grp[idx] : D.hap_grp[idx];
+      const uint8_t* rec = D.slab + D.dir[g].rec_off;
+      const lgr_group_rec_hdr* hdr = reinterpret_cast<const lgr_group_rec_hdr*>(rec);
+      const uint32_t n_exc = hdr->n_exc;
       const uint32_t* epos = reinterpret_cast<const uint32_t*>(rec + hdr->off_exc);
       const uint8_t* ecode = reinterpret_cast<const uint8_t*>(epos + n_exc);
       const long long start = o - (is_read ? D.grp_readbase[g] : D.grp_hapbase[g]);

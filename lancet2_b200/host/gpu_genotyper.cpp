@@ -488,6 +488,15 @@ static void* PinnedOrThrow(std::size_t bytes) {
 }
 
 GenotypeBatcher::GenotypeBatcher(const Options& opt, NameHashFn name_hash) : mOpt(opt), mNameHash(std::move(name_hash)) {
+  // tuning knobs without a rebuild (tools/bench_batcher.py sweeps them); unset = the Options given
+  auto env_int = [](const char* name, long long cur) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoll(v) : cur;
+  };
+  mOpt.depth = static_cast<int>(env_int("LGR_BATCHER_DEPTH", mOpt.depth));
+  mOpt.min_pairs_busy = env_int("LGR_BATCHER_MIN_PAIRS", mOpt.min_pairs_busy);
+  mOpt.max_wait_us = static_cast<int>(env_int("LGR_BATCHER_MAX_WAIT_US", mOpt.max_wait_us));
+  mOpt.linger_us = static_cast<int>(env_int("LGR_BATCHER_LINGER_US", mOpt.linger_us));
   if (mOpt.depth < 1) mOpt.depth = 1;
   if (mOpt.depth > LGR_MAX_INFLIGHT) mOpt.depth = LGR_MAX_INFLIGHT;
   if (mOpt.max_jobs < 1) mOpt.max_jobs = 1;

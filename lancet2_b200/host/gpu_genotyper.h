@@ -283,7 +283,7 @@ class GenotypeBatcher {
  public:
   struct Options {
     int device = 0;
-    int depth = 3;                       // device batches in flight (<= LGR_MAX_INFLIGHT)
+    int depth = 4;                       // device batches in flight (<= LGR_MAX_INFLIGHT); 4 measured best on one B200
     std::int64_t max_pairs = 1 << 21;    // (read, haplotype) pairs per device batch
     std::size_t max_jobs = 8192;         // Genotype() payloads per device batch
     int linger_us = 100;                 // idle GPU: wait this long for more workers to arrive before launching

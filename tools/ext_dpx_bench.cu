@@ -169,8 +169,12 @@ __global__ void __launch_bounds__(kWarps * 32) k_dpx(int reps, unsigned long lon
     }
     if (DIR) {
       __syncwarp();
-      for (int x = lane; x < nsteps * 32; x += 32)
-        if ((x & 31) < 16) dsum += (dir[x] & 0xff) + (dir[x] >> 8);  // rows 0..31 only: comparable with k_scalar
+      for (int x = lane; x < nsteps * 32; x += 32) {
+        const int s = x >> 5, l = x & 31, i0 = s - 2 * l, i1 = i0 - 1;
+        if (l >= 16) continue;  // rows 0..31 only: comparable with k_scalar
+        if (i0 >= 0 && i0 < kT) dsum += dir[x] & 0xff;  // slots of steps outside a row's columns are never written
+        if (i1 >= 0 && i1 < kT) dsum += dir[x] >> 8;
+      }
       __syncwarp();
     }
   }
