@@ -448,7 +448,7 @@ def main():
         issue = None
         if wl.get("warp_inst_per_launch") and static.get("int_issue_peak_warp_inst_per_s"):
             ach = wl["warp_inst_per_launch"] / (map_ms * 1e-3)
-            issue = {"kernel": "k_chain_warp", "achieved": ach, "peak": static["int_issue_peak_warp_inst_per_s"], "unit": "warp-instr/s",
+            issue = {"kernel": wl.get("kernel", "k_chain_warp"), "achieved": ach, "peak": static["int_issue_peak_warp_inst_per_s"], "unit": "warp-instr/s",
                      "frac": ach / static["int_issue_peak_warp_inst_per_s"],
                      "source": "static: instruction count from " + wl.get("source", "ncu") + "; peak: " + static.get("int_issue_peak_source", "")}
         line = {
@@ -476,7 +476,7 @@ def main():
                              "note": "the same slab, already packed and pinned, through lgr_submit_packed/lgr_wait (one step = one call: H2D + unpack + kernels + D2H); with batches in flight neighbouring steps fill each other's low-parallelism phases and L2 is not flushed, so this figure can exceed `value`"}},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_chain_warp", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "k_chain_warp + k_chain_cold (phase A: seeds, anchors, chaining)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": ("static: " + wl.get("source", "")) if traffic else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": map_ms,

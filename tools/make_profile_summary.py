@@ -44,11 +44,12 @@ def main():
                                   capture_output=True, text=True).stdout)
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_cfg2.txt"), "w") as fh:
         fh.write("\n".join(txt) + "\n")
-    ch = [v for k, v in out.items() if k.startswith("k_chain_warp")][0]
+    # bench.py's ms_k_map spans the hot and the cold chain kernel: both go into the per-launch constants
+    chains = [v for k, v in out.items() if k.startswith("k_chain_warp") or k.startswith("k_chain_cold")]
     peak = json.load(open(peak_file))
-    static = {"cfg2": {"kernel": "k_chain_warp",
-                       "dram_bytes_per_launch": (ch["dram__bytes_read.sum"] + ch["dram__bytes_write.sum"]) * 1e6,
-                       "warp_inst_per_launch": ch["smsp__inst_executed.sum"],
+    static = {"cfg2": {"kernel": "k_chain_warp + k_chain_cold",
+                       "dram_bytes_per_launch": sum(ch["dram__bytes_read.sum"] + ch["dram__bytes_write.sum"] for ch in chains) * 1e6,
+                       "warp_inst_per_launch": sum(ch["smsp__inst_executed.sum"] for ch in chains),
                        "source": f"profiles/{tag}_ncu_cfg2.txt (ncu --set full, one launch)"},
               "int_issue_peak_warp_inst_per_s": peak["iadd3"] * 1e12 / 32,
               "int_issue_peak_source": "profiles/r1_int_peak.json (tools/int_peak.cu, IADD3 thread-ops/s / 32)"}
