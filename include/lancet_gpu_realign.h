@@ -430,6 +430,38 @@ const char* lgr_format_last_error(const lgr_fmt_ctx* ctx);
  * CUDA-event time of the two kernels. */
 int lgr_format_metrics(lgr_fmt_ctx* ctx, const lgr_evidence_in* in, lgr_format* out, float* ms_kernels);
 
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md §8f #3 (first half) — repeat detection over the sliding k-mers of reference windows.
+ *
+ * One *job* = one (sequence, k, max_mismatches) question: do two k-mers of the sequence, taken at different
+ * offsets, differ in at most max_mismatches byte positions?  lgr_repeat_scan replaces, per job:
+ *   cbdg::Graph::HasExactOrApproxRepeat   src/lancet/cbdg/graph.h:127-131   (max_mismatches = 2, once per k of the k-loop)
+ *   VariantBuilder::ShouldSkipWindow      src/lancet/core/variant_builder.cpp:116-117 (HasExactRepeat at max_k)
+ *   base::HasRepeat / HasExactRepeat      src/lancet/base/repeat.cpp:348-375 over base::SlidingView (sliding.h:17-34)
+ * Bytes are compared raw, as the reference does; fewer than two k-mers give 0.  A sequence longer than
+ * LGR_REPEAT_MAX_LEN is not computed: its answer is LGR_REPEAT_TOO_LONG and the call returns LGR_E_PARTIAL
+ * (Lancet2's windows are <= 2.5 kb).  Own context, bound to one GPU, one thread at a time; the call returns when
+ * has_repeat[0..n_jobs) is filled.  No CPU fallback: lgr_repeat_create returns LGR_E_NO_DEVICE without a GPU.
+ * The k-mer insertion of Graph::AddNodes (the second half of §8f #3) is not part of this library.
+ */
+#define LGR_REPEAT_MAX_LEN 8192
+#define LGR_REPEAT_TOO_LONG 255
+typedef struct lgr_repeat_job {
+  int64_t seq_off;          /* byte offset of the sequence in `seqs`            */
+  int32_t seq_len;          /* bases                                            */
+  int32_t k;                /* k-mer length (> 0)                               */
+  int32_t max_mismatches;   /* 0 = exact repeat; Graph uses 2                   */
+  int32_t reserved;
+} lgr_repeat_job;
+typedef struct lgr_rep_ctx lgr_rep_ctx;
+int lgr_repeat_create(int device_ordinal, lgr_rep_ctx** out);
+void lgr_repeat_destroy(lgr_rep_ctx* ctx);
+const char* lgr_repeat_last_error(const lgr_rep_ctx* ctx);
+/* H2D of the sequences and jobs, k_repeat_scan, D2H of one byte per job (0 / 1 / LGR_REPEAT_TOO_LONG);
+ * ms_kernels (may be NULL) = CUDA-event time of the kernel. */
+int lgr_repeat_scan(lgr_rep_ctx* ctx, const uint8_t* seqs, int64_t seq_bytes, const lgr_repeat_job* jobs, int32_t n_jobs,
+                    uint8_t* has_repeat, float* ms_kernels);
+
 #ifdef __cplusplus
 }
 #endif

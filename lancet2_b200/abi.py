@@ -406,6 +406,14 @@ class EvidenceBatch:
         return st
 
 
+class LgrRepeatJob(C.Structure):
+    _fields_ = [("seq_off", C.c_int64), ("seq_len", C.c_int32), ("k", C.c_int32), ("max_mismatches", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+LGR_REPEAT_MAX_LEN = 8192
+LGR_REPEAT_TOO_LONG = 255
+
 _SYMBOLS = [
     "lgr_abi_version", "lgr_default_params", "lgr_strerror", "lgr_last_error", "lgr_x31_hash",
     "lgr_pair_offsets", "lgr_create", "lgr_destroy", "lgr_hap_mid_occ", "lgr_genotype_batch",
@@ -413,6 +421,7 @@ _SYMBOLS = [
     "lgr_alloc_pinned", "lgr_free_pinned",
     "lgr_set_notify", "lgr_check_limits", "lgr_packed_group_bytes", "lgr_pack_group", "lgr_genotype_packed", "lgr_submit_packed", "lgr_upload_packed",
     "lgr_format_create", "lgr_format_destroy", "lgr_format_last_error", "lgr_format_metrics",
+    "lgr_repeat_create", "lgr_repeat_destroy", "lgr_repeat_last_error", "lgr_repeat_scan",
 ]
 
 
@@ -485,4 +494,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.lgr_format_last_error.restype = C.c_char_p
     lib.lgr_format_metrics.argtypes = [C.c_void_p, C.POINTER(LgrEvidenceIn), C.c_void_p, C.POINTER(C.c_float)]
     lib.lgr_format_metrics.restype = C.c_int
+    lib.lgr_repeat_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.lgr_repeat_create.restype = C.c_int
+    lib.lgr_repeat_destroy.argtypes = [C.c_void_p]
+    lib.lgr_repeat_destroy.restype = None
+    lib.lgr_repeat_last_error.argtypes = [C.c_void_p]
+    lib.lgr_repeat_last_error.restype = C.c_char_p
+    lib.lgr_repeat_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
+    lib.lgr_repeat_scan.restype = C.c_int
     return lib

@@ -18,7 +18,7 @@ class GpuFormatMetrics:
     def __init__(self, device: int = 0):
         self._main = abi.load_library()
         self._lib = self._main
-        # A/B builds of the same four entry points (e.g. csrc/liblgr_format_sort.so, the -DLGR_FMT_SORT kernels)
+        # A/B builds of the same four entry points (e.g. csrc/liblgr_format_scan.so, the O(n^2)-scan kernels; the shipped build is -DLGR_FMT_SORT)
         variant = os.environ.get("LGR_FORMAT_LIBRARY")
         if variant:
             self._lib = C.CDLL(variant)

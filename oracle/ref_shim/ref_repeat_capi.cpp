@@ -29,4 +29,11 @@ int ref_has_repeat(const char* seq, int64_t len, int64_t k, int64_t max_mismatch
   return lancet::base::HasRepeat(absl::MakeConstSpan(kmers), (size_t)max_mismatches) ? 1 : 0;
 }
 
+// the same over an explicit list of n_kmers k-mers stored back to back (the reference's KAT form)
+int ref_has_repeat_kmers(const char* kmers, int64_t n_kmers, int64_t k, int64_t max_mismatches) {
+  std::vector<std::string_view> views;
+  for (int64_t i = 0; i < n_kmers; ++i) views.emplace_back(kmers + i * k, (size_t)k);
+  return lancet::base::HasRepeat(absl::MakeConstSpan(views), (size_t)max_mismatches) ? 1 : 0;
+}
+
 }  // extern "C"

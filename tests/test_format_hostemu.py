@@ -141,7 +141,7 @@ def test_golden_edge_supports():
 
 
 def test_sort_build_equals_scan_build():
-    """-DLGR_FMT_SORT (the next round's device build): ranks and bins from a
+    """-DLGR_FMT_SORT (the shipped device build since round 2): ranks and bins from a
     shared-memory bitonic sort instead of the O(n^2) scans.  The Mann-Whitney statistics are
     integers, so RPCD must keep its bits; the entropies add their terms in sorted-bin order
     (tolerance).  Supports beyond the 2048-record cap take the scan in both builds."""
@@ -161,9 +161,9 @@ def test_sort_build_equals_scan_build():
     assert not errs, "\n".join(errs[:20])
 
 
-def test_sort_variant_library_exports_the_same_entry_points():
+def test_scan_variant_library_exports_the_same_entry_points():
     import os
-    path = os.path.join(os.path.dirname(abi.LIB_PATH), "liblgr_format_sort.so")
+    path = os.path.join(os.path.dirname(abi.LIB_PATH), "liblgr_format_scan.so")
     if not os.path.exists(path):
         pytest.skip("variant library not built")
     lib = C.CDLL(path)
