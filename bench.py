@@ -54,6 +54,41 @@ def build_workload(name: str, seed: int, rank: int = 0, world: int = 1, tiles: i
     return groups, desc, "weak", ["normal", "tumor"]
 
 
+def _cpulist(text: str):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def _numa_share(avail, local_rank: int, world: int):
+    """Cores of the NUMA node each GPU hangs off (/sys/bus/pci/devices/<bdf>/numa_node), split between the
+    ranks whose GPUs share that node.  None when the box does not say (single node, virtualised PCI)."""
+    try:
+        import torch
+        nodes = []
+        for r in range(world):
+            p = torch.cuda.get_device_properties(r)
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            nodes.append(int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read()))
+        node = nodes[local_rank]
+        if node < 0:
+            return None
+        ok = set(avail)
+        cpus = [c for c in _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()) if c in ok]
+        peers = [r for r in range(world) if nodes[r] == node]
+        share = len(cpus) // len(peers)
+        if share < 1:
+            return None
+        at = peers.index(local_rank)
+        return cpus[at * share:(at + 1) * share]
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def tiled_desc(name: str, n_tiles: int, world: int) -> str:
     spec = synth.TILED[name]
     cov = "/".join(f"{int(c)}x" for _, c, _ in spec["samples"])
@@ -68,6 +103,9 @@ def _build_replica_workload(name: str, seed: int):
     elif name == "micro":
         groups = synth.make_groups(seed, 1024, read_len=150, hap_len=1000, n_haps=8, n_reads=256)
         desc = "cfg5 point: L=150, H=1000, P=8, R=256, 1024 groups"
+    elif name == "l250":
+        groups = synth.make_groups(1000 * 250 + 1000 + 8, 64, read_len=250, hap_len=1000, n_haps=8, n_reads=512)
+        desc = "cfg5 point: L=250, H=1000, P=8, R=512, 64 groups"
     elif name == "tiny":
         groups = synth.make_region_groups(seed, ref_len=60_000)
         desc = "tiny: 60 kb region (debug)"
@@ -304,11 +342,19 @@ def main():
     cores = os.cpu_count() or 1
     # every rank keeps to its own share of the host cores (generation, packing workers, batcher thread)
     per_rank = max(1, cores // max(1, world))
+    affinity = "inherited"
     try:
         avail = sorted(os.sched_getaffinity(0))
         if world > 1 and len(avail) >= world:
-            share = len(avail) // world
-            os.sched_setaffinity(0, set(avail[local_rank * share:(local_rank + 1) * share]))
+            mine = _numa_share(avail, local_rank, world)
+            if mine:
+                affinity = f"numa-local share of {len(mine)} cores"
+            else:
+                share = len(avail) // world
+                mine = avail[local_rank * share:(local_rank + 1) * share]
+                affinity = f"equal share of {len(mine)} cores (no NUMA information)"
+            os.sched_setaffinity(0, set(mine))
+            per_rank = len(mine)
     except (AttributeError, OSError):
         pass
     workload = args.workload if args.workload != "auto" else ("cfg2" if world == 1 else "cfg3")
@@ -462,7 +508,7 @@ def main():
             "e2e": {"value": adapter_v, "unit": UNIT, "h2d_bytes_per_step": int(actr[17]) // max(1, args.steps),
                     "d2h_bytes_per_step": int(actr[18]) // max(1, args.steps),
                     "path": "lancet_gpu::GenotypeBatcher (C++ adapter with the reference's Genotype() call shape): one payload per group, worker threads Enqueue/Collect; packing from the caller's strings into the pinned slab, ONE H2D per device batch, all kernels, D2H of the assignments and AddToTable on the workers inside the timed region",
-                    "worker_threads": threads, "payloads_in_flight_per_worker": args.adapter_window, "host_cores": cores,
+                    "worker_threads": threads, "payloads_in_flight_per_worker": args.adapter_window, "host_cores": cores, "cpu_affinity": affinity,
                     "genotype_calls_per_s": adapter_v * batch.n_groups / max(1, batch.n_pairs),
                     "device_batches_per_step": float(actr[0]) / max(1, args.steps), "max_payloads_in_one_batch": int(actr[3]),
                     "payloads_rerun_alone": int(actr[19]),

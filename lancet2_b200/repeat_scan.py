@@ -12,6 +12,10 @@ import numpy as np
 from . import abi
 
 
+_JOB_DTYPE = np.dtype([("seq_off", "<i8"), ("seq_len", "<i4"), ("k", "<i4"), ("max_mismatches", "<i4"), ("reserved", "<i4")])
+assert _JOB_DTYPE.itemsize == C.sizeof(abi.LgrRepeatJob)
+
+
 class GpuRepeatScan:
     def __init__(self, device: int = 0):
         self._lib = abi.load_library()
@@ -38,18 +42,25 @@ class GpuRepeatScan:
         """jobs: (sequence, k, max_mismatches).  → (uint8 answers: 0 / 1 / LGR_REPEAT_TOO_LONG, kernel ms).
         Equal sequences are uploaded once (a window is asked once per k of the graph's k-loop)."""
         offs, blobs, pos = {}, [], 0
-        arr = (abi.LgrRepeatJob * max(len(jobs), 1))()
-        for i, (seq, k, mm) in enumerate(jobs):
+        arr = np.zeros(max(len(jobs), 1), dtype=_JOB_DTYPE)
+        seq_off = np.empty(len(jobs), dtype=np.int64)
+        for i, (seq, _, _) in enumerate(jobs):
             key = id(seq) if len(seq) > 64 else seq
-            if key not in offs:
-                offs[key] = pos
+            at = offs.get(key)
+            if at is None:
+                at = offs[key] = pos
                 blobs.append(seq)
                 pos += len(seq)
-            arr[i].seq_off, arr[i].seq_len, arr[i].k, arr[i].max_mismatches = offs[key], len(seq), k, mm
+            seq_off[i] = at
+        if jobs:
+            arr["seq_off"][:len(jobs)] = seq_off
+            arr["seq_len"][:len(jobs)] = [len(j[0]) for j in jobs]
+            arr["k"][:len(jobs)] = [j[1] for j in jobs]
+            arr["max_mismatches"][:len(jobs)] = [j[2] for j in jobs]
         buf = np.frombuffer(b"".join(blobs) + b"\0", dtype=np.uint8)
         out = np.zeros(max(len(jobs), 1), dtype=np.uint8)
         ms = C.c_float(0.0)
-        rc = self._lib.lgr_repeat_scan(self._ctx, buf.ctypes.data, pos, C.byref(arr), len(jobs), out.ctypes.data, C.byref(ms))
+        rc = self._lib.lgr_repeat_scan(self._ctx, buf.ctypes.data, pos, arr.ctypes.data, len(jobs), out.ctypes.data, C.byref(ms))
         self.last_rc = rc
         if rc not in (0, abi.LGR_E_PARTIAL):
             raise RuntimeError(f"lgr_repeat_scan failed ({self._lib.lgr_strerror(rc).decode()}): "

@@ -41,7 +41,7 @@ def plant_repeat(rng, seq, k, mismatches, gap=None):
     if n < k + 1:
         return bytes(s)
     src = int(rng.integers(0, max(1, n - 2 * k))) if gap is None else 0
-    dst = int(rng.integers(src + 1, n - k + 1)) if gap is None else gap
+    dst = int(rng.integers(min(src + k, n - k), n - k + 1)) if gap is None else gap  # clear of the source when it fits
     kmer = bytearray(s[src:src + k])
     for p in rng.choice(k, size=mismatches, replace=False):
         kmer[p] = ord("ACGT"[("ACGT".index(chr(kmer[p])) + 1 + int(rng.integers(0, 3))) % 4])
