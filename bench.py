@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-inflight", type=int, default=3)
     ap.add_argument("--adapter-threads", type=int, default=0, help="worker threads of the adapter arm (0 = min(16, host cores / ranks))")
-    ap.add_argument("--adapter-window", type=int, default=16, help="Genotype() payloads a worker keeps enqueued")
+    ap.add_argument("--adapter-window", type=int, default=32, help="Genotype() payloads a worker keeps enqueued")
     ap.add_argument("--min-step-ms", type=float, default=50.0, help="repeat the batch inside a step until a step carries this much device time")
     args = ap.parse_args()
     claim_stdout()

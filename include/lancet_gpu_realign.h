@@ -245,6 +245,12 @@ int lgr_wait(lgr_ctx* ctx, lgr_ticket ticket, lgr_stats* stats);
  * done; lgr_wait(ticket) then returns without blocking.  fn must not call into this library or CUDA.  NULL disables. */
 typedef void (*lgr_notify_fn)(void* user, lgr_ticket ticket);
 int lgr_set_notify(lgr_ctx* ctx, lgr_notify_fn fn, void* user);
+/* Device memory is one grow-only arena per in-flight slot, and growing it (cudaFree + cudaMalloc) synchronises the whole
+ * device.  lgr_reserve creates the first n_slots (<= LGR_MAX_INFLIGHT) submission slots now and gives each an arena of
+ * at least arena_bytes, so that a pipelined caller pays neither inside its steady state; a batch that needs more still
+ * grows its slot.  lgr_arena_bytes = device bytes this ctx currently holds in arenas (its own and its slots'). */
+int lgr_reserve(lgr_ctx* ctx, int64_t arena_bytes, int n_slots);
+int64_t lgr_arena_bytes(const lgr_ctx* ctx);
 /* LGR_OK when a Genotype() payload whose longest haplotype / read have these lengths is inside the device path's static
  * caps for `params` (NULL = defaults), else LGR_E_LIMIT — the check lgr_submit applies to a whole batch, exposed so that
  * a host batching many payloads can refuse the one offender instead (no CUDA call, any thread). */

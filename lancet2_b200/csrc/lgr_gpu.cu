@@ -977,6 +977,29 @@ static int submit_async(lgr_ctx* c, const void* in, lgr_batch_out* out, lgr_tick
   return LGR_OK;
 }
 
+int lgr_reserve(lgr_ctx* c, int64_t arena_bytes, int n_slots) {
+  if (!c || arena_bytes < 0 || n_slots < 0 || n_slots > LGR_MAX_INFLIGHT) return LGR_E_ARG;
+  LGR_CUDA(c, cudaSetDevice(c->device));
+  for (int t = 0; t < n_slots; ++t) {
+    if (c->slot_busy[t]) continue;  // in flight: its arena is in use, leave it alone
+    if (!c->slot[t]) {
+      int rc = lgr_create(c->device, &c->prm, &c->slot[t]);
+      if (rc != LGR_OK) { c->err = g_create_err; return rc; }
+    }
+    int rc = ensure(c->slot[t], c->slot[t]->arena, (size_t)arena_bytes);
+    if (rc != LGR_OK) { c->err = c->slot[t]->err; return rc; }
+  }
+  return LGR_OK;
+}
+
+int64_t lgr_arena_bytes(const lgr_ctx* c) {
+  if (!c) return 0;
+  int64_t b = (int64_t)c->arena.cap;
+  for (int t = 0; t < LGR_MAX_INFLIGHT; ++t)
+    if (c->slot[t]) b += (int64_t)c->slot[t]->arena.cap;
+  return b;
+}
+
 // Diagnostics: the device counters of the last finished batch of this context (enum Ctr in lgr_dev.cuh: work
 // queues, cold-path reasons, extension tasks per size class).  Not part of the stable ABI.
 int lgr_debug_counters(lgr_ctx* c, long long* out, int n) {

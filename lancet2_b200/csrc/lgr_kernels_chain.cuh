@@ -226,12 +226,19 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     const bool strictly = __all_sync(full, strict);
     if (sorted && (n_a <= 64 || strictly)) {
       for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
-    } else if ((!HOT || LGR_HOT_WARP_SORT) && n_a <= 64) {
+    } else if (HOT && !(LGR_HOT_WARP_SORT && n_a <= 64)) {
+      if (lane == 0) atomicAdd((unsigned long long*)&D.ctr[C_COLD_SORT], 1ULL);
+      return kMapCold;
+    } else {
       // upstream's radix_sort_128x is an insertion sort up to 64 elements, i.e. STABLE: the result is
       // the unique stable order, which the warp gets by ranking instead of sorting on one lane
-      // (typically two reverse-strand anchors of a short palindrome sit mid-list).  Warp-uniform trip
-      // counts on purpose: a lane-dependent loop here cost the whole kernel its convergence (measured:
-      // +0.8 ms on cfg2 when this ran in the hot kernel), so these pairs stay with the cold kernel.
+      // (typically two reverse-strand anchors of a short palindrome sit mid-list).  Beyond 64 elements
+      // upstream runs its unstable in-place radix passes: if all keys are distinct there is still only
+      // one sorted order and ranking gives it; only a list with tied keys needs the move-for-move
+      // emulation on lane 0.  Warp-uniform trip counts on purpose: a lane-dependent loop here cost the
+      // whole kernel its convergence (measured: +0.8 ms on cfg2 when this ran in the hot kernel), so
+      // these pairs stay with the cold kernel.
+      bool tie = false;
       for (int base = 0; base < n_a; base += 32) {
         const int i = base + lane;
         const uint32_t xi = i < n_a ? (uint32_t)ax[i] : 0u;
@@ -239,20 +246,18 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
         for (int j = 0; j < n_a; ++j) {
           const uint32_t xj = (uint32_t)ax[j];
           rank += (xj < xi) || (xj == xi && j < i);
+          tie |= xj == xi && j != i && i < n_a;
         }
         __syncwarp();
         if (i < n_a) sx[rank] = (int32_t)xi, sy[rank] = ay[i];
       }
       __syncwarp();
-    } else {
-      if (HOT) {
-        if (lane == 0) atomicAdd((unsigned long long*)&D.ctr[C_COLD_SORT], 1ULL);
-        return kMapCold;
-      }
-      if (lane == 0) {
-        for (int i = 0; i < n_a; ++i) perm[i] = i;
-        radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
-        for (int i = 0; i < n_a; ++i) sx[i] = ax[perm[i]], sy[i] = ay[perm[i]];
+      if (n_a > 64 && __any_sync(full, tie)) {
+        if (lane == 0) {
+          for (int i = 0; i < n_a; ++i) perm[i] = i;
+          radix_sort_perm(perm, n_a, [&](int32_t id) { return anchor_x64((uint32_t)ax[id]); }, rsx);
+          for (int i = 0; i < n_a; ++i) sx[i] = ax[perm[i]], sy[i] = ay[perm[i]];
+        }
       }
     }
   }

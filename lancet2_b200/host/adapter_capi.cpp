@@ -257,14 +257,17 @@ static int BatcherRun(int device, const lgr_batch_in* in, const char* names, con
       for (int t = 0; t < n_threads; ++t) {
         workers.emplace_back([&, t] {
           try {
+            // split ProcessWindow: up to `window` groups enqueued per worker before the oldest is collected.  The
+            // window rolls across rounds (a worker of the caller has thousands of windows queued, it never drains
+            // its pipeline between two of them); everything is collected before the clock stops.
+            std::deque<std::pair<std::size_t, lancet_gpu::GenotypeDispatcher::Ticket>> open_t;
             for (int round = 0; round < rounds; ++round) {
               if (window <= 1) {  // the reference's call shape: one blocking call per group
                 for (std::size_t g = (size_t)t; g < js.jobs.size(); g += (size_t)n_threads) {
                   const lancet_gpu::GenotypeJob& j = js.jobs[g];
                   res[g] = batcher.Genotype(j.haps, j.n_haps, j.reads, j.n_reads, j.variants, j.n_variants);
                 }
-              } else {  // split ProcessWindow: up to `window` groups enqueued per worker before collecting
-                std::deque<std::pair<std::size_t, lancet_gpu::GenotypeDispatcher::Ticket>> open_t;
+              } else {
                 for (std::size_t g = (size_t)t; g < js.jobs.size(); g += (size_t)n_threads) {
                   if ((int)open_t.size() == window) {
                     res[open_t.front().first] = batcher.Collect(open_t.front().second);
@@ -272,9 +275,9 @@ static int BatcherRun(int device, const lgr_batch_in* in, const char* names, con
                   }
                   open_t.emplace_back(g, batcher.Enqueue(js.jobs[g]));
                 }
-                for (auto& ot : open_t) res[ot.first] = batcher.Collect(ot.second);
               }
             }
+            for (auto& ot : open_t) res[ot.first] = batcher.Collect(ot.second);
           } catch (const std::exception& e) {
             errors[(size_t)t] = e.what();
           }

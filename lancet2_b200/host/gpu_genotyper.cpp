@@ -508,6 +508,8 @@ GenotypeBatcher::GenotypeBatcher(const Options& opt, NameHashFn name_hash) : mOp
   Check(nullptr, lgr_create(mOpt.device, &mParams, &mCtx));
   Check(nullptr, lgr_create(mOpt.device, &mParams, &mAuxCtx));
   Check(mCtx, lgr_set_notify(mCtx, &GenotypeBatcher::OnDeviceDone, this));
+  mOpt.arena_reserve_bytes = env_int("LGR_BATCHER_ARENA_MB", mOpt.arena_reserve_bytes >> 20) << 20;
+  if (mOpt.arena_reserve_bytes > 0) Check(mCtx, lgr_reserve(mCtx, mOpt.arena_reserve_bytes, mOpt.depth));
   const int n_slabs = mOpt.depth + 2;  // in flight + one filling + one waiting for a device slot
   for (int i = 0; i < n_slabs; ++i) {
     auto s = std::make_unique<Slab>();
@@ -624,7 +626,8 @@ GenotypeBatcher::Ticket GenotypeBatcher::Enqueue(const GenotypeJob& job) {
       s = mOpen;
       const std::size_t dir_room = sizeof(lgr_group_dir) * (s->n_jobs + 1) + 32;
       const bool fits = s->n_jobs < mOpt.max_jobs && s->used + plan.bytes + dir_room <= s->cap &&
-                        (s->n_jobs == 0 || s->pairs + pairs <= mOpt.max_pairs);
+                        (s->n_jobs == 0 || (s->pairs + pairs <= mOpt.max_pairs &&
+                                            static_cast<std::size_t>(s->n_assign + n_asg) < mOpt.result_records));
       if (fits) break;
       mSealable.push_back(s);  // full: the batcher thread submits it as soon as a device slot is free
       mOpen = nullptr;
@@ -746,7 +749,10 @@ void GenotypeBatcher::Run() {
         if (mOpen->opened_ns == 0) mOpen->opened_ns = now;
         const std::uint64_t age_us = (now - mOpen->opened_ns) / 1000;
         const bool big = mOpen->pairs >= mOpt.min_pairs_busy;
-        const std::uint64_t wait_us = mInFlight.empty() ? static_cast<std::uint64_t>(mOpt.linger_us) : static_cast<std::uint64_t>(mOpt.max_wait_us);
+        // the idle-GPU linger only pays while it actually gathers company: after eight batches in a row that left
+        // with a single payload (one blocking caller) it is skipped until a batch carries more than one again
+        const std::uint64_t linger_us = mLingerCredit > 0 ? static_cast<std::uint64_t>(mOpt.linger_us) : 0;
+        const std::uint64_t wait_us = mInFlight.empty() ? linger_us : static_cast<std::uint64_t>(mOpt.max_wait_us);
         if (!mStop && !big && age_us < wait_us) {
           mCv.wait_for(lk, std::chrono::microseconds(wait_us - age_us));
           continue;
@@ -755,6 +761,8 @@ void GenotypeBatcher::Run() {
         mOpen = nullptr;
       }
       if (s) {
+        if (s->n_jobs > 1) mLingerCredit = 8;
+        else if (mLingerCredit > 0) --mLingerCredit;
         lk.unlock();
         SealAndSubmit(s);
         lk.lock();

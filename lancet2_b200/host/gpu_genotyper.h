@@ -284,13 +284,18 @@ class GenotypeBatcher {
   struct Options {
     int device = 0;
     int depth = 4;                       // device batches in flight (<= LGR_MAX_INFLIGHT); 4 measured best on one B200
-    std::int64_t max_pairs = 1 << 21;    // (read, haplotype) pairs per device batch
+    std::int64_t max_pairs = 1 << 18;    // (read, haplotype) pairs per device batch (the kernels are saturated well below;
+                                         // the reserved arena covers a batch of this size)
     std::size_t max_jobs = 8192;         // Genotype() payloads per device batch
     int linger_us = 100;                 // idle GPU: wait this long for more workers to arrive before launching
     int max_wait_us = 400;               // busy GPU: a slab waits at most this long for min_pairs_busy
     std::int64_t min_pairs_busy = 49152; // busy GPU: pairs that make a batch worth its launch overhead
     std::size_t slab_bytes = 32u << 20;  // pinned staging per slab (a payload larger than this travels alone)
-    std::size_t result_records = 1u << 18;  // lgr_assign records per pinned result block (grown if a batch needs more)
+    std::size_t result_records = 1u << 18;  // lgr_assign records per pinned result block: a slab is sealed before it would
+                                            // hold more (only a single payload beyond this grows a block)
+    std::int64_t arena_reserve_bytes = 1ll << 30;    // device arena reserved per in-flight slot at construction (lgr_reserve;
+                                                     // a cfg2-sized batch of 233 K pairs needs 0.75 GiB, mostly per-warp scratch):
+                                                     // a regrow inside the steady state synchronises the whole device
     const lgr_params* params = nullptr;
   };
   struct Counters {
@@ -356,6 +361,7 @@ class GenotypeBatcher {
   Slab* mOpen = nullptr;             // the slab being filled
   std::deque<Slab*> mSealable;       // full slabs waiting for a device slot, in order
   std::deque<Slab*> mInFlight;       // submitted, oldest first
+  int mLingerCredit = 8;              // batches still allowed the idle-GPU linger (see Run)
   std::uint32_t mDeviceDone = 0;     // tickets whose device work has finished (bit per ticket)
   bool mStop = false;
   Counters mCounters;
