@@ -436,6 +436,40 @@ const char* lgr_format_last_error(const lgr_fmt_ctx* ctx);
  * CUDA-event time of the two kernels. */
 int lgr_format_metrics(lgr_fmt_ctx* ctx, const lgr_evidence_in* in, lgr_format* out, float* ms_kernels);
 
+/* AddToTable on the device (second step): the evidence of every (variant, sample) support is built
+ * from the realignment's lgr_assign records — read straight from the device when dev_assign comes from
+ * lgr_resident_assign() of a context on the same GPU, so the records never visit the host — plus the per-read fields
+ * AddToTable takes from cbdg::Read (genotyper.cpp:423-456), in the order lancet_gpu::EvidenceColumns::AppendJob defines:
+ * supports by (group, variant, first read of each sample), records in read order.  Then the FORMAT math runs as in
+ * lgr_format_metrics.  read_name_hash replaces absl::HashOf(qname): the dedup only compares names of one support.
+ * Returns the number of supports in *n_supports, their records in out[0..S) and sup_key[3 s + 0..2] = group, variant
+ * (index in the batch) and sample id of support s; S <= n_vars * n_samples (out_cap must cover the actual S). */
+typedef struct lgr_assign_batch {
+  const lgr_assign* dev_assign;      /* DEVICE pointer (lgr_resident_assign), or NULL to upload host_assign     */
+  const lgr_assign* host_assign;     /* [n_assign] host records, used when dev_assign is NULL                   */
+  int64_t n_assign;                  /* sum over groups of reads x variants, group-major, read-major inside     */
+  int32_t n_groups, n_reads, n_vars, n_samples; /* n_samples <= 32 */
+  const int32_t* grp_read_begin;     /* [G+1] as in lgr_batch_in                                                */
+  const int32_t* grp_var_begin;      /* [G+1]                                                                   */
+  const int32_t* grp_n_haps;         /* [G]  ComputeHSE(total_haplotypes)                                       */
+  const int32_t* var_n_alleles;      /* [NV] 1 + ALT alleles                                                    */
+  const int32_t* var_len;            /* [NV] max |ALT length| (AlleleMismatchDelta)                             */
+  const int64_t* read_insert_size;   /* [NR] */
+  const int64_t* read_aln_start;     /* [NR] */
+  const uint32_t* read_name_hash;    /* [NR] */
+  const int32_t* read_sample;        /* [NR] dense sample id in [0, n_samples)                                  */
+  const uint16_t* read_sam_flag;     /* [NR] 0x10 reverse strand, 0x2 proper pair                               */
+  const uint8_t* read_map_qual;      /* [NR] */
+  const uint8_t* read_soft_clipped;  /* [NR] */
+} lgr_assign_batch;
+int lgr_format_from_assign(lgr_fmt_ctx* ctx, const lgr_assign_batch* in, lgr_format* out, int32_t out_cap, int32_t* sup_key,
+                           int32_t* n_supports, float* ms_kernels);
+/* the device-resident lgr_assign records of the batch ctx last ran (lgr_genotype_*, lgr_run_resident); valid until the
+ * next batch on ctx.  For lgr_assign_batch::dev_assign. */
+int lgr_resident_assign(lgr_ctx* ctx, const lgr_assign** dev_assign, int64_t* n_assign);
+/* test hook: the evidence columns lgr_format_from_assign built last, copied into dst's (caller-allocated) arrays */
+int lgr_format_debug_evidence(lgr_fmt_ctx* ctx, lgr_evidence_in* dst);
+
 /* ------------------------------------------------------------------------------------------
  * SURVEY.md §8f #3 (first half) — repeat detection over the sliding k-mers of reference windows.
  *

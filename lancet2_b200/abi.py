@@ -366,6 +366,15 @@ class LgrEvidenceIn(C.Structure):
                 ("sup_total_haps", C.c_void_p)] + [(name, C.c_void_p) for name, _ in EVIDENCE_FIELDS]
 
 
+class LgrAssignBatch(C.Structure):
+    _fields_ = [("dev_assign", C.c_void_p), ("host_assign", C.c_void_p), ("n_assign", C.c_int64),
+                ("n_groups", C.c_int32), ("n_reads", C.c_int32), ("n_vars", C.c_int32), ("n_samples", C.c_int32),
+                ("grp_read_begin", C.c_void_p), ("grp_var_begin", C.c_void_p), ("grp_n_haps", C.c_void_p),
+                ("var_n_alleles", C.c_void_p), ("var_len", C.c_void_p), ("read_insert_size", C.c_void_p),
+                ("read_aln_start", C.c_void_p), ("read_name_hash", C.c_void_p), ("read_sample", C.c_void_p),
+                ("read_sam_flag", C.c_void_p), ("read_map_qual", C.c_void_p), ("read_soft_clipped", C.c_void_p)]
+
+
 # numpy view of lgr_format (one record per support)
 FORMAT_DTYPE = np.dtype([
     ("raw_pbq", np.float64, (LGR_FMT_MAX_ALLELES,)), ("rms_mq", np.float64, (LGR_FMT_MAX_ALLELES,)),
@@ -421,6 +430,7 @@ _SYMBOLS = [
     "lgr_alloc_pinned", "lgr_free_pinned",
     "lgr_set_notify", "lgr_reserve", "lgr_arena_bytes", "lgr_check_limits", "lgr_packed_group_bytes", "lgr_pack_group", "lgr_genotype_packed", "lgr_submit_packed", "lgr_upload_packed",
     "lgr_format_create", "lgr_format_destroy", "lgr_format_last_error", "lgr_format_metrics",
+    "lgr_format_from_assign", "lgr_resident_assign", "lgr_format_debug_evidence",
     "lgr_repeat_create", "lgr_repeat_destroy", "lgr_repeat_last_error", "lgr_repeat_scan",
 ]
 
@@ -498,6 +508,13 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.lgr_format_last_error.restype = C.c_char_p
     lib.lgr_format_metrics.argtypes = [C.c_void_p, C.POINTER(LgrEvidenceIn), C.c_void_p, C.POINTER(C.c_float)]
     lib.lgr_format_metrics.restype = C.c_int
+    lib.lgr_format_from_assign.argtypes = [C.c_void_p, C.POINTER(LgrAssignBatch), C.c_void_p, C.c_int32, C.c_void_p,
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    lib.lgr_format_from_assign.restype = C.c_int
+    lib.lgr_resident_assign.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.lgr_resident_assign.restype = C.c_int
+    lib.lgr_format_debug_evidence.argtypes = [C.c_void_p, C.POINTER(LgrEvidenceIn)]
+    lib.lgr_format_debug_evidence.restype = C.c_int
     lib.lgr_repeat_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.lgr_repeat_create.restype = C.c_int
     lib.lgr_repeat_destroy.argtypes = [C.c_void_p]

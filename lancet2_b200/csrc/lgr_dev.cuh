@@ -115,7 +115,7 @@ struct Dev {      // everything the kernels need, passed by value
 #define LGR_CHAIN_MINB 9
 #endif
 #ifndef LGR_EXT_MINB
-#define LGR_EXT_MINB 8
+#define LGR_EXT_MINB 6
 #endif
 #ifndef LGR_FIN_MINB
 #define LGR_FIN_MINB 8

@@ -992,6 +992,14 @@ int lgr_reserve(lgr_ctx* c, int64_t arena_bytes, int n_slots) {
   return LGR_OK;
 }
 
+int lgr_resident_assign(lgr_ctx* c, const lgr_assign** dev_assign, int64_t* n_assign) {
+  if (!c || !dev_assign || !n_assign) return LGR_E_ARG;
+  static_assert(sizeof(AssignOut) == sizeof(lgr_assign), "device and ABI records must coincide");
+  *dev_assign = reinterpret_cast<const lgr_assign*>(c->D.assign);
+  *n_assign = c->D.n_assign;
+  return c->D.assign ? LGR_OK : LGR_E_ARG;
+}
+
 int64_t lgr_arena_bytes(const lgr_ctx* c) {
   if (!c) return 0;
   int64_t b = (int64_t)c->arena.cap;

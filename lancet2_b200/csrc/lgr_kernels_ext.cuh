@@ -15,6 +15,8 @@ namespace {
 // All 32 lanes must call it; results are written by lane 0 into reg->ext[side].
 // ---------------------------------------------------------------------------------------
 constexpr int kDynPruneMinRows = 12;  // shorter tails: the static bound is already small, skip the extra pass
+constexpr int32_t kBandLow = -30000;   // stand-in for H/E/F of cells outside the band: below every true value (checked per task)
+constexpr int kBandLowPacked = (int)(((uint32_t)kBandLow & 0xffffu) | ((uint32_t)kBandLow << 16));
 
 __device__ __noinline__ void ext_dp_warp(const Dev& D, int grp, RegRec* reg, int side, const ReadView& rv, const uint8_t* hapc,
                                          uint8_t* dir_g, uint8_t* dir_s, int dir_s_cap, int32_t* Hb, int32_t* Fb, uint32_t* wcig,
@@ -26,6 +28,7 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, int grp, RegRec* reg, int
   const int32_t sc_match = P.a, sc_mis = -P.b, sc_amb = -P.sc_ambi;  // in registers: the loop's generic stores could alias P
   const int m = reg->ext[side].m, n = reg->ext[side].n;
   int T = prune_cols(P, m, n);
+  int band_ins = 1 << 20, band_del = 1 << 20;  // |i - j| kept on the insertion / deletion side (no band by default)
   const bool right = side == 0;
   ExtQuery qf{rv, reg->rev, side, reg->c_qs, reg->c_qe};
   ExtTarget tf{hapc, side, reg->c_rs, reg->c_re};
@@ -69,6 +72,19 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, int grp, RegRec* reg, int
     const int X = P.a * m - q - lb;
     const int Dd = X <= 0 ? 0 : X / e;
     if (m + Dd < T) T = m + Dd;
+    // The same LB bounds the band.  A path through a cell with i - j = d > 0 has deleted >= d target bases
+    // (score <= a*m - q - e*d), one through a cell with j - i = d > 0 has inserted >= d query bases and can
+    // match at most m - d of them (score <= a*(m-d) - q - e*d), whether it ends in the last row or right
+    // there.  Cells whose bound is < LB can hold neither the last-row maximum, nor the global maximum, nor a
+    // traceback cell, and any cell they feed either loses to an in-band input or is itself unreachable by the
+    // traceback (a tie would be a path through the cell scoring >= LB).  So they may be skipped, or computed
+    // from inputs that are merely <= the true values (kBandLow), without changing any result.
+    // kBandLow must undercut every true H/E/F and survive ~100 steps of drift inside int16.
+    const int64_t lowest = -(3 * (int64_t)q + (int64_t)e * (T + m + 4) + (int64_t)(P.b > P.sc_ambi ? P.b : P.sc_ambi) * m);
+    if (lowest >= kBandLow + 64 && e <= 16) {
+      band_del = Dd;
+      band_ins = X <= 0 ? 0 : X / (P.a + e);
+    }
     __syncwarp();  // the staging bytes are dead from here on; the slice becomes direction storage
   }
   const int nblk = (m + 31) >> 5;
@@ -89,18 +105,34 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, int grp, RegRec* reg, int
     uint8_t* dblk = dir + (size_t)blk * 32 * (T + 31);
     const int nsteps = T + rows - 1;
     const bool save_bnd = blk + 1 < nblk;
+    // Band (see above): the block only runs the anti-diagonals [s_lo, s_hi) that hold in-band cells of its
+    // rows.  Everything on anti-diagonal s_lo - 1 and before is out of band (i - j <= -band_ins - 2 there), so
+    // a lane that starts mid-row takes kBandLow for the three inputs it never saw; a lane that starts at
+    // column 0 keeps the true boundary values.  Past the band's right edge the boundary row of the previous
+    // block holds kBandLow (filled below).
+    const int s_lo = blk * 32 - band_ins - 1 > 0 ? blk * 32 - band_ins - 1 : 0;
+    const int s_hi = band_del < nsteps && blk * 32 + 63 + band_del < nsteps ? blk * 32 + 63 + band_del : nsteps;
+    if (s_lo > 0) {
+      hf = kBandLowPacked;
+      if (s_lo - lane > 0) e_cur = kBandLow, diag = kBandLow;
+    }
     // Per 32 steps every lane fetches one target base (and one packed boundary cell for row
     // blocks > 0): coalesced, off the per-step dependency chain, and the step body stays
     // branch-free — lane l takes its base t[s-l] with one indexed shuffle out of the current or
     // previous 32-base register window, lane 0 takes its boundary input with a broadcast.
+    const int s_first = s_lo & ~31;
     int tprev = 4, tcur = 4, bcur = 0;
-    for (int s0 = 0; s0 < nsteps; s0 += 32) {
+    {
+      const int ti = s_first - 32 + lane;  // the window before the first one (lanes look back up to 31 columns)
+      tcur = ti >= 0 && ti < T ? tf(ti) : 4;
+    }
+    for (int s0 = s_first; s0 < s_hi; s0 += 32) {
       const int ti = s0 + lane;
       tprev = tcur;
       tcur = ti < T ? tf(ti) : 4;
       if (blk > 0) bcur = ti < T ? Hb[ti] : 0;
-      const int kmax = nsteps - s0 < 32 ? nsteps - s0 : 32;
-      for (int k = 0; k < kmax; ++k) {
+      const int kmax = s_hi - s0 < 32 ? s_hi - s0 : 32;
+      for (int k = s0 < s_lo ? s_lo - s0 : 0; k < kmax; ++k) {
         const int s = s0 + k;
         const int i = s - lane;
         const int tc = __shfl_sync(full, k >= lane ? tcur : tprev, (k - lane) & 31);
@@ -129,6 +161,13 @@ __device__ __noinline__ void ext_dp_warp(const Dev& D, int grp, RegRec* reg, int
           if (save_bnd && lane == 31) Hb[i] = hf;
         }
       }
+    }
+    if (save_bnd && s_hi < nsteps) {
+      // columns of the boundary row this block did not reach but the next one will ask for: all beyond the
+      // band's right edge of row 32*blk + 31
+      const int from = s_hi - 31 > 0 ? s_hi - 31 : 0;
+      const int to = s_hi + 32 < T ? s_hi + 32 : T;
+      for (int x = from + lane; x < to; x += 32) Hb[x] = kBandLowPacked;
     }
     __syncwarp();
   }

@@ -63,3 +63,55 @@ class GpuFormatMetrics:
             raise RuntimeError(f"lgr_format_metrics failed ({self._main.lgr_strerror(rc).decode()}): "
                                f"{self._lib.lgr_format_last_error(self._ctx).decode()}")
         return out, float(ms.value)
+
+    def from_assign(self, batch: "abi.Batch", *, n_samples: int, sample_id, start0, isize, sam_flag, mapq, softclip,
+                    var_n_alleles, var_len, host_assign=None, dev_assign: int = 0):
+        """AddToTable + FORMAT math on the device (lgr_format_from_assign): evidence columns are built by
+        k_evidence_* from the realignment's lgr_assign records — `dev_assign` (a device address from
+        GpuRealigner.resident_assign()) or `host_assign` (numpy records, uploaded) — and the per-read fields.
+        → (records, keys[S,3] = group / variant / sample id, CUDA-event ms of all kernels)."""
+        if self._lib is not self._main:
+            raise RuntimeError("from_assign is not part of the A/B FORMAT libraries")
+        keep = [np.ascontiguousarray(a, dtype=dt) for a, dt in (
+            (batch.grp_read_begin, np.int32), (batch.grp_var_begin, np.int32),
+            (np.diff(batch.grp_hap_begin), np.int32), (var_n_alleles, np.int32), (var_len, np.int32), (isize, np.int64),
+            (start0, np.int64), (batch.read_name_hash, np.uint32), (sample_id, np.int32), (sam_flag, np.uint16),
+            (mapq, np.uint8), (softclip, np.uint8))]
+        st = abi.LgrAssignBatch()
+        st.dev_assign = dev_assign or None
+        if host_assign is not None:
+            host_assign = np.ascontiguousarray(host_assign)
+            st.host_assign = host_assign.ctypes.data
+        st.n_assign = int(batch.n_assign)
+        st.n_groups, st.n_reads, st.n_vars, st.n_samples = batch.n_groups, batch.n_reads, batch.n_vars, n_samples
+        for name, arr in zip(("grp_read_begin", "grp_var_begin", "grp_n_haps", "var_n_alleles", "var_len", "read_insert_size",
+                              "read_aln_start", "read_name_hash", "read_sample", "read_sam_flag", "read_map_qual",
+                              "read_soft_clipped"), keep):
+            setattr(st, name, arr.ctypes.data)
+        cap = max(1, batch.n_vars * n_samples)
+        out = np.zeros(cap, dtype=abi.FORMAT_DTYPE)
+        keys = np.zeros((cap, 3), dtype=np.int32)
+        n_sup, ms = C.c_int32(0), C.c_float(0.0)
+        rc = self._lib.lgr_format_from_assign(self._ctx, C.byref(st), out.ctypes.data, cap, keys.ctypes.data, C.byref(n_sup), C.byref(ms))
+        self.last_rc = rc
+        if rc not in (0, abi.LGR_E_PARTIAL):
+            raise RuntimeError(f"lgr_format_from_assign failed ({self._main.lgr_strerror(rc).decode()}): "
+                               f"{self._lib.lgr_format_last_error(self._ctx).decode()}")
+        return out[:n_sup.value], keys[:n_sup.value], float(ms.value)
+
+    def debug_evidence(self) -> dict:
+        """The evidence columns the last from_assign built on the device (test hook)."""
+        probe = abi.LgrEvidenceIn()
+        if self._lib.lgr_format_debug_evidence(self._ctx, C.byref(probe)) != 0:
+            raise RuntimeError("lgr_format_debug_evidence failed")
+        n, s = int(probe.n_evidence), int(probe.n_supports)
+        cols = {"sup_begin": np.zeros(s + 1, np.int64), "sup_n_alleles": np.zeros(s, np.int32),
+                "sup_variant_len": np.zeros(s, np.int32), "sup_total_haps": np.zeros(s, np.int32)}
+        for name, dt in abi.EVIDENCE_FIELDS:
+            cols[name] = np.zeros(n, dtype=dt)
+        st = abi.LgrEvidenceIn()
+        for name, arr in cols.items():
+            setattr(st, name, arr.ctypes.data if arr.size else None)
+        if self._lib.lgr_format_debug_evidence(self._ctx, C.byref(st)) != 0:
+            raise RuntimeError("lgr_format_debug_evidence failed")
+        return cols

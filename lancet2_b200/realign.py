@@ -137,6 +137,13 @@ class GpuRealigner:
         self._check(self.lib.lgr_download(self._ctx, C.byref(bo)))
         return res
 
+    def resident_assign(self):
+        """(device address, count) of the lgr_assign records of the batch this context ran last: the input of
+        GpuFormatMetrics.from_assign(dev_assign=...), so the assignments never visit the host."""
+        p, n = C.c_void_p(), C.c_int64(0)
+        self._check(self.lib.lgr_resident_assign(self._ctx, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
     @property
     def stream(self) -> int:
         return int(self.lib.lgr_stream(self._ctx) or 0)
