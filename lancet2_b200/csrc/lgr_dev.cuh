@@ -118,7 +118,7 @@ struct Dev {      // everything the kernels need, passed by value
 #define LGR_EXT_MINB 6
 #endif
 #ifndef LGR_FIN_MINB
-#define LGR_FIN_MINB 8
+#define LGR_FIN_MINB 6
 #endif
 // a device-path limit hit one pair: remember it for the batch and for the pair's group (the other
 // groups of the batch stay valid, lgr_batch_out::grp_status)
@@ -172,10 +172,13 @@ __device__ __forceinline__ void store_final(const Dev& D, int g, int64_t pair, c
       for (int i = 0; i < nc; ++i) D.cigar_arena[off + i] = cig[i];
     }
   }
-  // 64-byte record, 64-byte aligned: four 16-byte stores
-  const uint4* src = reinterpret_cast<const uint4*>(&o);
+  // 64-byte record, 64-byte aligned: four 16-byte stores straight from registers (taking the record's
+  // address would park it in local memory)
   uint4* dst = reinterpret_cast<uint4*>(&D.aln[pair]);
-  dst[0] = src[0], dst[1] = src[1], dst[2] = src[2], dst[3] = src[3];
+  dst[0] = make_uint4((uint32_t)o.valid, (uint32_t)o.score, (uint32_t)o.rs, (uint32_t)o.re);
+  dst[1] = make_uint4((uint32_t)o.qs, (uint32_t)o.qe, (uint32_t)o.rev, (uint32_t)o.dp_score);
+  dst[2] = make_uint4((uint32_t)o.dp_max, (uint32_t)o.mlen, (uint32_t)o.blen, (uint32_t)o.n_ambi);
+  dst[3] = make_uint4((uint32_t)o.nm, (uint32_t)o.n_cigar, (uint32_t)o.cigar_off, (uint32_t)o.n_regs);
 }
 
 }  // namespace

@@ -97,10 +97,16 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
 //   finish    scalar core on lane 0 (cigar assembly, mm_fix_cigar, mm_update_extra, NM)
 // Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_chain_overflow).
 // ---------------------------------------------------------------------------------------
+#ifndef LGR_CHAIN_LOCKSTEP
+#define LGR_CHAIN_LOCKSTEP 0
+#endif
 #ifndef LGR_HOT_WARP_SORT
 #define LGR_HOT_WARP_SORT 0  // 1: the hot kernel ranks unsorted anchor lists itself instead of queueing the pair for the cold kernel
 #endif
-constexpr int kWarpsPerCta = 4;
+#ifndef LGR_WARPS_PER_CTA
+#define LGR_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = LGR_WARPS_PER_CTA;
 constexpr int kMapOkColinear = 2;  // warp_seed_chain: chain DP done by the co-linear closed form
 constexpr int kMapCold = -3;       // hot kernel only: a shape whose code lives in the cold kernel (queued, not computed)
 
@@ -835,6 +841,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
       for (int b = threadIdx.x; b <= kBuckets; b += blockDim.x) s_bkt[b] = bk[b];
     }
     __syncthreads();
+#if LGR_CHAIN_LOCKSTEP
+    // the CTA's warps start every pair together: they then run the same stretch of this (large) kernel at about
+    // the same time and share its instruction-cache lines, at the price of waiting for the slowest pair of a round
+    for (int base = 0; base < nr; base += kWarpsPerCta) {
+      __syncthreads();
+      const int rr = base + warp;
+      if (rr < nr) chain_pair<CAP, true>(D, r0 + rr, h, g, h_local, mid_occ, hapc, hlen, s_tab, idx_n, s_bkt, ws, rsx, &s_regs[warp], ctr);
+    }
+#else
     for (;;) {
       int rr = 0;
       if (lane == 0) rr = atomicAdd(&s_next, 1);
@@ -842,6 +857,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
       if (rr >= nr) break;
       chain_pair<CAP, true>(D, r0 + rr, h, g, h_local, mid_occ, hapc, hlen, s_tab, idx_n, s_bkt, ws, rsx, &s_regs[warp], ctr);
     }
+#endif
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&D.ctr[C_EVALS], (unsigned long long)ctr.chain_evals);

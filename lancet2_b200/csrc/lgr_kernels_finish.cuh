@@ -127,7 +127,7 @@ __device__ __forceinline__ int32_t warp_edit_distance(const uint8_t* read_codes,
 // One pass over a gap-free forward-strand alignment (cigar = one M op, the normal case):
 // mm_update_extra's mlen / blen / n_ambi / dp_max, the ungapped core score and NM together,
 // from the same two code bytes per column.
-__device__ __noinline__ void warp_finish_pure_m(const DevParams& P, const uint8_t* read_codes, const uint8_t* hap, int qb, int tb,
+__device__ __forceinline__ void warp_finish_pure_m(const DevParams& P, const uint8_t* read_codes, const uint8_t* hap, int qb, int tb,
                                                 int len, int c_qs, int c_qe, RegFinal* out, int32_t* core_out, int32_t* nm_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -195,8 +195,8 @@ struct TrackBlock {  // surviving regs of one pair (mm_set_parent / mm_select_su
 constexpr int kFinChunk = LGR_FIN_CHUNK;  // pairs a warp takes from the finish queue per atomic
 constexpr int kFinSmemCig = 64;  // cigar ops of a reg kept in shared memory; longer ones use the HBM scratch
 
-__device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
-                                             FinishScratch& fs, TrackBlock* trk, RegRec* s_reg, AlnOut* out) {
+__device__ __forceinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, const uint8_t* hap, const RegRec* regs, int n_regs,
+                                             FinishScratch& fs, TrackBlock* trk, RegRec* s_reg, RegFinal* s_bf, AlnOut* out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const DevParams& P = D.P;
@@ -204,8 +204,8 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
   int best = -1, n_surv = 0;
   int32_t best_nm = -1;
   uint64_t best_key = 0;
-  RegFinal bf;
-  bf.n_cig = 0;
+  // the best reg so far and the final record live in the warp's shared-memory slots (s_bf, out): as locals they
+  // were spilled to local memory, whose write-through traffic to L2 bounded this kernel
   int32_t *s_qs = trk->qs, *s_qe = trk->qe, *s_rs = trk->rs, *s_re = trk->re, *s_score = trk->score;
   uint64_t* s_key = trk->key;
   for (int r = 0; r < n_regs; ++r) {
@@ -254,7 +254,9 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
       warp_finish_pure_m(P, rv.codes, hap, ra.qb, ra.tb, (int)(fs.cig[0] >> 4), c_qs, c_qe, &rf, &core, &nm_reg);
       rf.dp_score = ra.dp_ext + core;
     } else {
-      warp_update_extra(P, rv, rev, hap, ra.qb, ra.tb, fs.cig, ra.n, &rf);
+      RegFinal far;  // the out-of-line call's result lives in local memory; `rf` itself stays in registers
+      warp_update_extra(P, rv, rev, hap, ra.qb, ra.tb, fs.cig, ra.n, &far);
+      rf.dp_max = far.dp_max, rf.mlen = far.mlen, rf.blen = far.blen, rf.n_ambi = far.n_ambi;
       rf.dp_score = ra.dp_ext + warp_core_score(P, rv, rev, hap, c_qs, c_rs, c_qe - c_qs);
     }
     rf.rs = ra.rs, rf.re = ra.re, rf.qs = ra.qs, rf.qe = ra.qe, rf.n_cig = ra.n;
@@ -271,27 +273,26 @@ __device__ __noinline__ int finish_pair_warp(const Dev& D, const ReadView& rv, c
     }
     ++n_surv;
     if (best < 0 || key >= best_key) {
-      best = r, best_key = key, bf = rf, best_nm = nm_reg;
+      best = r, best_key = key, best_nm = nm_reg;
+      if (lane == 0) *s_bf = rf;
       uint32_t* tmp = fs.best;
       fs.best = fs.cig;
       fs.cig = tmp;
     }
   }
-  out->valid = 0, out->score = 0, out->rs = out->re = out->qs = out->qe = 0, out->rev = 0, out->dp_score = 0;
-  out->dp_max = 0, out->mlen = out->blen = out->n_ambi = 0, out->nm = 0, out->n_cigar = 0, out->cigar_off = -1;
-  out->n_regs = 0;
-  if (best < 0) return 0;
+  if (best < 0) {
+    if (lane == 0) *out = AlnOut{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1, 0};
+    __syncwarp();
+    return 0;
+  }
   __syncwarp();
   const int n_ret = n_surv > 1 ? select_returned(P, n_surv, s_qs, s_qe, s_rs, s_re, s_score, s_key) : n_surv;
-  out->valid = 1;
-  out->score = regs[best].score;
-  out->rs = bf.rs, out->re = bf.re, out->qs = bf.qs, out->qe = bf.qe;
-  out->rev = regs[best].rev;
-  out->dp_score = bf.dp_score, out->dp_max = bf.dp_max, out->mlen = bf.mlen, out->blen = bf.blen;
-  out->n_ambi = bf.n_ambi;
-  out->n_cigar = bf.n_cig;
-  out->n_regs = n_ret;
-  out->nm = best_nm >= 0 ? best_nm : warp_edit_distance(rv.codes, qlen, hap, bf.rs, bf.re, bf.qs, fs.best, bf.n_cig);
+  const RegFinal bf = *s_bf;
+  const int32_t nm = best_nm >= 0 ? best_nm : warp_edit_distance(rv.codes, qlen, hap, bf.rs, bf.re, bf.qs, fs.best, bf.n_cig);
+  if (lane == 0)
+    *out = AlnOut{1, regs[best].score, bf.rs, bf.re, bf.qs, bf.qe, regs[best].rev, bf.dp_score, bf.dp_max, bf.mlen, bf.blen,
+                  bf.n_ambi, nm, bf.n_cig, -1, n_ret};
+  __syncwarp();
   return bf.n_cig;
 }
 
@@ -304,6 +305,8 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_
   __shared__ TrackBlock s_trk[4];
   __shared__ uint32_t s_cig[4][2 * kFinSmemCig];
   __shared__ RegRec s_regs[4];
+  __shared__ RegFinal s_bf[4];
+  __shared__ __align__(16) AlnOut s_out[4];
   uint32_t* fin0 = D.fin_scratch + (size_t)gwarp * 2 * D.fin_cap;
   TrackBlock* trk = &s_trk[threadIdx.x >> 5];
   uint32_t* scig = s_cig[threadIdx.x >> 5];
@@ -327,21 +330,26 @@ __global__ void __launch_bounds__(128, LGR_FIN_MINB) k_finish_warp(const __grid_
     ReadView rv{D.read_codes + roff, (int)(D.read_off[read + 1] - roff)};
     RegRec* regs = D.regs + d.first;
     // cigars live in shared memory; the rare reg with more ops than fit reruns on the HBM scratch
+    // (one inlined body, run a second time on the HBM scratch in the rare overflow case: the record and the
+    // per-reg structs then live in registers — as an out-of-line call they went through local memory, and the
+    // spills around the call were 2.7 GB of L1→L2 write traffic per cfg2 step)
     FinishScratch fs{scig, scig + kFinSmemCig, kFinSmemCig};
-    AlnOut ao;
-    int nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &s_regs[threadIdx.x >> 5], &ao);
-    if (nc < 0) {
-      __syncwarp();
-      fs = FinishScratch{fin0, fin0 + D.fin_cap, D.fin_cap};
-      nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &s_regs[threadIdx.x >> 5], &ao);
+    AlnOut* ao = &s_out[threadIdx.x >> 5];
+    int nc = -1;
+    for (int attempt = 0; attempt < 2 && nc < 0; ++attempt) {
+      if (attempt == 1) {
+        __syncwarp();
+        fs = FinishScratch{fin0, fin0 + D.fin_cap, D.fin_cap};
+      }
+      nc = finish_pair_warp(D, rv, hapc, regs, d.n, fs, trk, &s_regs[threadIdx.x >> 5], &s_bf[threadIdx.x >> 5], ao);
     }
     if (lane == 0) {
       if (nc < 0) {
         flag_err(D, D.read_grp[read], E_CIG_SCRATCH);
         write_invalid(&D.aln[pair]);
       } else {
-        store_final(D, D.read_grp[read], pair, ao, fs.best, nc);
-        n_aligned += ao.valid;
+        store_final(D, D.read_grp[read], pair, *ao, fs.best, nc);
+        n_aligned += ao->valid;
       }
     }
     __syncwarp();

@@ -28,7 +28,7 @@ def main():
     peak_file = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles", "r1_int_peak.json")
     raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
     h, units = raw[0], raw[1]
-    out, txt = {}, ["ncu --set full --import-source on --clock-control none, bench.py cfg2 (233,282 pairs per step)", ""]
+    out, txt = {}, ["ncu --set full --import-source on --clock-control none -c 13, one resident pass over the cfg2 workload (233,282 pairs; tools/debug_counters.py cfg2, no L2 flush before the pass)", ""]
     for r in raw[2:]:
         short = r[h.index("Kernel Name")].split("(")[0].split("::")[-1]
         d = {k: r[h.index(k)] for k in KEYS if k in h}

@@ -47,6 +47,8 @@ def main():
     h2 = sass[1]
     ci = {h: i for i, h in enumerate(h2)}
     agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
+    local = collections.defaultdict(lambda: [0.0, 0.0])  # executed STL / LDL per source line (LGR_NCU_LOCAL=1)
+    src_col = ci.get("Source")
     n = 0
     tot_s = tot_i = 0.0
     for r in sass[2:]:
@@ -57,9 +59,19 @@ def main():
         key = line_of[n] if n < len(line_of) else ("?", -1)
         a = agg[key]
         a[0] += samp; a[1] += inst; a[2] += thr
+        if src_col is not None and src_col < len(r):
+            if " STL" in " " + r[src_col]:
+                local[key][0] += inst
+            elif " LDL" in " " + r[src_col]:
+                local[key][1] += inst
         tot_s += samp; tot_i += inst
         n += 1
     print(f"instructions in profile {n}, in disassembly {len(line_of)}")
+    if os.environ.get("LGR_NCU_LOCAL") == "1":
+        print(f"local memory: {sum(v[0] for v in local.values()):.0f} STL, {sum(v[1] for v in local.values()):.0f} LDL executed")
+        for (f, ln), (st, ld) in sorted(local.items(), key=lambda kv: -(kv[1][0] + kv[1][1]))[:top_n]:
+            print(f"  STL {st:10.0f}  LDL {ld:10.0f}  {f}:{ln}")
+        return
     src_cache = {}
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top_n]
     print(" %inst  %samp  lanes  file:line  source")
