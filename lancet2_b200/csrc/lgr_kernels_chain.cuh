@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
 //   finish    scalar core on lane 0 (cigar assembly, mm_fix_cigar, mm_update_extra, NM)
 // Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_chain_overflow).
 // ---------------------------------------------------------------------------------------
+#ifndef LGR_COLD_MINB
+#define LGR_COLD_MINB 1
+#endif
 #ifndef LGR_CHAIN_LOCKSTEP
 #define LGR_CHAIN_LOCKSTEP 0
 #endif
@@ -869,7 +872,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
 // Phase A, cold kernel: the pairs the hot kernel queued, one warp per pair, the complete code
 // (mm_seed_select, the radix-pass emulation, the general chain tail), tables read from HBM.
 template <int CAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_chain_cold(const __grid_constant__ Dev D) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_COLD_MINB) k_chain_cold(const __grid_constant__ Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
   RegRec* s_regs = reinterpret_cast<RegRec*>(s_ws + (size_t)kWarpsPerCta * Ws<1>::elems(CAP, kRegCap));
