@@ -415,6 +415,11 @@ def main():
     barrier()
     e2e_single_s = time.perf_counter() - t0
     depth = max(1, min(args.e2e_inflight, abi.LGR_MAX_INFLIGHT))
+    # every batch in flight owns a device arena the size of this context's: a whole cfg3 shard in one batch is tens of GB
+    arena = int(gpu.lib.lgr_arena_bytes(gpu._ctx))
+    free_b, _ = torch.cuda.mem_get_info()
+    if arena > 0:
+        depth = max(1, min(depth, int(free_b * 0.8) // int(arena * 1.6)))
     capi_s = e2e_single_s
     if depth > 1:
         ress = [res]
