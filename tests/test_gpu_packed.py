@@ -180,3 +180,37 @@ def test_many_contexts_share_one_gpu():
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_reserve_presizes_slots_and_results_do_not_change():
+    """lgr_reserve (what the batcher calls at construction): the submission slots and their arenas exist
+    before the first batch, no arena grows while batches that fit are in flight, results are the same."""
+    from lancet2_b200.realign import GpuRealigner
+    groups = synth.make_region_groups(13, ref_len=40_000)
+    batch = abi.Batch(groups)
+    plain = GpuRealigner(0)
+    g = GpuRealigner(0)
+    try:
+        ref, _ = plain.genotype_batch(batch)
+        assert g.lib.lgr_arena_bytes(g._ctx) == 0
+        assert g.lib.lgr_reserve(g._ctx, 256 << 20, 3) == 0
+        reserved = g.lib.lgr_arena_bytes(g._ctx)
+        assert reserved >= 3 * (256 << 20)
+        packed = abi.PackedBatch(groups, g.lib)
+        import torch
+        packed.pin(torch)
+        tickets = []
+        outs = []
+        for _ in range(3):
+            t, res = g.submit_packed(packed, batch, want_aln=False)
+            tickets.append(t), outs.append(res)
+        for t in tickets:
+            g.wait(t)
+        assert g.lib.lgr_arena_bytes(g._ctx) == reserved          # nothing grew
+        for res in outs:
+            assert res.assign[:batch.n_assign].tobytes() == ref.assign[:batch.n_assign].tobytes()
+        assert g.lib.lgr_reserve(g._ctx, 1 << 20, abi.LGR_MAX_INFLIGHT + 1) == -1
+        assert g.lib.lgr_reserve(g._ctx, -1, 1) == -1
+    finally:
+        g.close()
+        plain.close()
