@@ -521,6 +521,7 @@ def main():
                                            "wait_batcher": float(actr[7]) * 1e-6 / args.steps, "add_to_table_all_workers": float(actr[8]) * 1e-6 / args.steps,
                                            "wall": adapter_s * 1e3 / args.steps},
                     "l2_flushed": False,
+                    "l2_note": "no flush kernel between steps: every device batch runs in one of four submission slots whose arenas (0.75 GiB of working set each on cfg2-sized batches) rotate, and its inputs arrive by a fresh H2D copy, so a batch finds none of its data in the 126 MB L2",
                     "capi": {"value": capi_v, "batches_in_flight": depth, "synchronous_value": total_pairs * args.steps / e2e_single_s,
                              "h2d_bytes_per_step": int(e2e_st.h2d_bytes), "d2h_bytes_per_step": int(e2e_st.d2h_bytes),
                              "ms_h2d_and_unpack": e2e_st.ms_h2d, "ms_kernels": e2e_st.ms_kernels, "ms_d2h": e2e_st.ms_d2h,

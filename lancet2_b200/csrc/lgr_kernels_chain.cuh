@@ -697,6 +697,7 @@ __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, in
         st = kMapCold;
         if (lane == 0) atomicAdd((unsigned long long*)&D.ctr[C_COLD_TAIL], 1ULL);
       } else {
+        __syncwarp();  // the lanes' reads of the workspace in the fast form are done before lane 0 rewrites it
         if (lane == 0) st = map_chain_tail<1>(D.P, qlen, hlen, pin.name_hash, ws, rsx, n_a, &n_regs);
         st = __shfl_sync(full, st, 0);
         n_regs = __shfl_sync(full, n_regs, 0);

@@ -61,7 +61,11 @@ __global__ void __launch_bounds__(kRepThreads) k_repeat_scan(const RepDev D) {
     uint32_t* mask = s_mask[warp];
     uint16_t* pre = s_pre[warp];
     for (int d = 1 + warp; d < n_kmers; d += kRepWarps) {
-      if (s_found) break;
+      // another warp found a repeat: one lane reads the flag (atomics on both sides, no data race) and the
+      // whole warp follows its answer, so the lanes can never disagree about leaving the loop
+      int stop = 0;
+      if (lane == 0) stop = atomicOr(&s_found, 0);
+      if (__shfl_sync(full, stop, 0)) break;
       const int span = len - d;            // positions p with a partner p + d
       const int starts = n_kmers - d;      // k-mer pairs (i, i + d) on this diagonal
       const int words = (span + 31) >> 5;
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(kRepThreads) k_repeat_scan(const RepDev D) {
         }
       }
       if (__any_sync(full, hit)) {
-        if (lane == 0) s_found = 1;
+        if (lane == 0) atomicExch(&s_found, 1);
         break;
       }
       __syncwarp();

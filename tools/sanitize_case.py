@@ -36,7 +36,37 @@ def main():
     t2, r2 = gpu.submit(batch)
     gpu.wait(t2), gpu.wait(t1)
     errs += compare_results(batch, want, r1) + compare_results(batch, want, r2)
+    # the packed wire format (unpack kernels) and the long-read point (banded extension, > 64 anchors per pair)
+    pk, _ = gpu.genotype_packed(abi.PackedBatch(groups, gpu.lib), batch)
+    errs += compare_results(batch, want, pk)
+    long_groups = synth.make_groups(1000 * 250 + 1000 + 8, 1, read_len=250, hap_len=1000, n_haps=4, n_reads=24 if small else 96)
+    lb = abi.Batch(long_groups)
+    lw, _ = O.oracle_genotype(lb, gpu.params, n_threads=8)
+    lg, _ = gpu.genotype_packed(abi.PackedBatch(long_groups, gpu.lib), lb)
+    errs += compare_results(lb, lw, lg)
     gpu.close()
+    # the two other entry-point families: repeat scan, AddToTable + FORMAT math on the device
+    import repeat_lib
+    from lancet2_b200.format_metrics import GpuFormatMetrics
+    from lancet2_b200.repeat_scan import GpuRepeatScan
+    jobs = repeat_lib.window_jobs(3, 4 if small else 12, k_values=(13, 31, 64), lengths=(300, 700))
+    rs = GpuRepeatScan(0)
+    rep, _ = rs.scan(jobs)
+    orc = repeat_lib.oracle()
+    errs += [f"repeat job {i}" for i, (sq, k, mm) in enumerate(jobs) if int(rep[i]) != orc.orc_has_repeat(sq, len(sq), k, mm)]
+    rs.close()
+    rng = np.random.default_rng(2)
+    nr = batch.n_reads
+    fmt = GpuFormatMetrics(0)
+    from test_gpu_evidence_build import variant_tables
+    kk, vlen = variant_tables(groups, batch)
+    recs, keys, _ = fmt.from_assign(batch, n_samples=3, sample_id=rng.integers(0, 3, nr).astype(np.int32),
+                                    start0=rng.integers(0, 10_000, nr).astype(np.int64), isize=rng.integers(-500, 500, nr).astype(np.int64),
+                                    sam_flag=rng.integers(0, 64, nr).astype(np.uint16), mapq=rng.integers(0, 61, nr).astype(np.uint8),
+                                    softclip=rng.integers(0, 2, nr).astype(np.uint8), var_n_alleles=kk, var_len=vlen,
+                                    host_assign=got.assign[:batch.n_assign])
+    fmt.close()
+    print(f"sanitize_case: repeat jobs {len(jobs)}, supports {len(recs)}")
     print(f"sanitize_case: {batch.n_pairs} pairs, {st.kernel_launches} launches, mismatches: {len(errs)}")
     sys.exit(1 if errs else 0)
 
