@@ -559,7 +559,10 @@ enum WsArray {
   A_COUNT
 };
 
-template <int S>
+// COMPACT: the layout of the hot chain kernel at 128 anchors (reads beyond 160 bp), which never sorts (the sorted arrays ARE the anchor arrays), never
+// needs the seed arrays once the anchors exist (they share the slots of the chaining arrays, which are written
+// later) and never touches A_Z / A_PERM: 8 anchor-sized arrays instead of 15, so that more CTAs fit an SM.
+template <int S, bool COMPACT = false>
 struct Ws {
   int32_t* base;  // already offset to this lane
   // capacities, packed (keeps the struct at two words: a third member made nvcc lose track of
@@ -568,14 +571,29 @@ struct Ws {
   // chain/reg-sized arrays (R_*; 0 = same as the anchor arrays).  A pair with more chains
   // than that overflows.
   int caps;
+  static constexpr int kSlots = COMPACT ? 8 : (int)R_SCORE;
+  static LGR_HD constexpr int slot(int k) {
+    if (!COMPACT) return k;
+    switch (k) {
+      case A_AX: case A_SX: return 0;
+      case A_AY: case A_SY: return 1;
+      case A_F: case A_SEEDQ: return 2;
+      case A_P: case A_SEEDN: return 3;
+      case A_T: case A_SEEDS: return 4;
+      case A_V: return 5;
+      case A_CX: return 6;
+      case A_CY: return 7;
+      default: return 5;  // A_Z, A_PERM: not used with this layout
+    }
+  }
   LGR_HD int cap() const { return caps & 0xffff; }
   LGR_HD int rcap() const { return caps >> 16 ? caps >> 16 : caps; }
   static LGR_HD int pack(int cap_, int rcap_) { return cap_ | rcap_ << 16; }
   LGR_HD Strided<int32_t, S> arr(int k) const {
-    const int off = k < R_SCORE ? k * cap() : R_SCORE * cap() + (k - R_SCORE) * rcap();
+    const int off = k < R_SCORE ? slot(k) * cap() : kSlots * cap() + (k - R_SCORE) * rcap();
     return Strided<int32_t, S>{base + (size_t)off * S};
   }
-  static LGR_HD size_t elems(int cap_, int rcap_) { return (size_t)R_SCORE * cap_ + (size_t)(A_COUNT - R_SCORE) * rcap_; }
+  static LGR_HD size_t elems(int cap_, int rcap_) { return (size_t)kSlots * cap_ + (size_t)(A_COUNT - R_SCORE) * rcap_; }
 };
 
 // ------------------------------------------------------------------------------------
@@ -1335,8 +1353,8 @@ LGR_HDN int map_chain_phase(const DevParams& P, const PairIn& in, const Ws<S>& w
 }
 
 // fill a RegRec (without the extension results) from the workspace after map_chain_phase
-template <int S>
-LGR_HD void export_reg(const Ws<S>& ws, int r, int qlen, RegRec* out) {
+template <int S, bool C>
+LGR_HD void export_reg(const Ws<S, C>& ws, int r, int qlen, RegRec* out) {
   out->score = ws.arr(R_SCORE)[r];
   out->cnt = ws.arr(R_CNT)[r];
   out->hash = (uint32_t)ws.arr(R_HASH)[r];

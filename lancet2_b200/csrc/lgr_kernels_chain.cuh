@@ -97,8 +97,10 @@ __global__ void __launch_bounds__(128) k_chain_overflow(const __grid_constant__ 
 //   finish    scalar core on lane 0 (cigar assembly, mm_fix_cigar, mm_update_extra, NM)
 // Pairs whose seeds/anchors exceed CAP are appended to the overflow list (k_chain_overflow).
 // ---------------------------------------------------------------------------------------
-#ifndef LGR_COLD_MINB
-#define LGR_COLD_MINB 1
+#ifdef LGR_COLD_MINB  // A/B builds only; measured: no gain from more CTAs per SM (the kernel waits for its slowest pairs)
+#define LGR_COLD_BOUNDS __launch_bounds__(LGR_WARPS_PER_CTA * 32, LGR_COLD_MINB)
+#else
+#define LGR_COLD_BOUNDS __launch_bounds__(LGR_WARPS_PER_CTA * 32)
 #endif
 #ifndef LGR_CHAIN_LOCKSTEP
 #define LGR_CHAIN_LOCKSTEP 0
@@ -120,7 +122,7 @@ constexpr int kMapCold = -3;       // hot kernel only: a shape whose code lives 
 // The pair's anchor / evaluation counts are returned to the caller, who commits them only for pairs
 // that finish here (a deferred pair is counted where it is computed).
 template <int CAP, bool HOT>
-__device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const uint16_t* bkt, const Ws<1>& ws,
+__device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, const uint16_t* bkt, const Ws<1, (HOT && CAP > 64)>& ws,
                                                RadixScratch* rsx, long long* n_eval_out, int* n_a_out, int* need_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -234,7 +236,8 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
     const bool sorted = __all_sync(full, ok);
     const bool strictly = __all_sync(full, strict);
     if (sorted && (n_a <= 64 || strictly)) {
-      for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
+      if constexpr (!(HOT && CAP > 64))  // the compact hot layout has no separate sorted arrays: sx/sy are ax/ay
+        for (int i = lane; i < n_a; i += 32) sx[i] = ax[i], sy[i] = ay[i];
     } else if (HOT && !(LGR_HOT_WARP_SORT && n_a <= 64)) {
       if (lane == 0) atomicAdd((unsigned long long*)&D.ctr[C_COLD_SORT], 1ULL);
       return kMapCold;
@@ -451,7 +454,8 @@ __device__ __forceinline__ int warp_seed_chain(const Dev& D, const PairIn& in, c
 // kMapNoHit, or -2 when the shape is different (then lane 0 runs the exact scalar map_chain_tail
 // from scratch).
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ int warp_chain_tail_fast(const DevParams& P, int qlen, int hap_len, uint32_t name_hash, const Ws<1>& ws, int n_a) {
+template <bool C>
+__device__ __noinline__ int warp_chain_tail_fast(const DevParams& P, int qlen, int hap_len, uint32_t name_hash, const Ws<1, C>& ws, int n_a) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   auto sx = ws.arr(A_SX), sy = ws.arr(A_SY), f = ws.arr(A_F), p = ws.arr(A_P), t = ws.arr(A_T), v = ws.arr(A_V);
@@ -580,8 +584,9 @@ __device__ __noinline__ int warp_chain_tail_fast(const DevParams& P, int qlen, i
 // f > 0), the chain is ALL anchors with score f[n_a-1]; if it fails min_sc / min_cnt every other
 // candidate is already marked used, so there is no hit.  All anchors share the diagonal, hence
 // mm_max_stretch returns the whole chain.  Fills the same R_* slots as map_chain_tail.
+template <bool C>
 __device__ __forceinline__ int warp_chain_tail_colinear(const DevParams& P, int qlen, int hap_len, uint32_t name_hash,
-                                                        const Ws<1>& ws, int n_a) {
+                                                        const Ws<1, C>& ws, int n_a) {
   const int lane = threadIdx.x & 31;
   auto sx = ws.arr(A_SX), sy = ws.arr(A_SY), f = ws.arr(A_F), p = ws.arr(A_P);
   const int32_t sc = f[n_a - 1];
@@ -674,7 +679,7 @@ __device__ __forceinline__ void cold_push(const Dev& D, int r, int h) {
 // sorted minimizer table and bucket directory (shared memory in the hot kernel, HBM in the cold one).
 template <int CAP, bool HOT>
 __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, int h_local, int mid_occ, const uint8_t* hapc, int hlen,
-                                           const uint64_t* tab, int idx_n, const uint16_t* bkt, const Ws<1>& ws, RadixScratch* rsx,
+                                           const uint64_t* tab, int idx_n, const uint16_t* bkt, const Ws<1, (HOT && CAP > 64)>& ws, RadixScratch* rsx,
                                            RegRec* s_reg, ChainCounters& ctr) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -693,7 +698,7 @@ __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, in
     st = warp_chain_tail_fast(D.P, qlen, hlen, pin.name_hash, ws, n_a);
     n_regs = 1;
     if (st == -2) {
-      if (HOT) {
+      if constexpr (HOT) {
         st = kMapCold;
         if (lane == 0) atomicAdd((unsigned long long*)&D.ctr[C_COLD_TAIL], 1ULL);
       } else {
@@ -793,7 +798,9 @@ __device__ __forceinline__ void chain_pair(const Dev& D, int r, int h, int g, in
 // shared memory of the chain kernels: per-warp workspace, per-warp RegRec slot, and (hot kernel) the
 // staged minimizer table + bucket directory of the CTA's haplotype
 __host__ __device__ inline size_t chain_smem_bytes(int cap, bool hot) {
-  return (size_t)kWarpsPerCta * (Ws<1>::elems(cap, kRegCap) * sizeof(int32_t) + sizeof(RegRec)) +
+  // the hot kernel takes the compact layout for 128 anchors (reads beyond 160 bp), where shared memory bounds its
+  // occupancy: +15 % there; at 64 anchors the full layout measured 1-3 % faster
+  return (size_t)kWarpsPerCta * ((hot && cap > 64 ? Ws<1, true>::elems(cap, kRegCap) : Ws<1>::elems(cap, kRegCap)) * sizeof(int32_t) + sizeof(RegRec)) +
          (hot ? (size_t)kTabCap * sizeof(uint64_t) + (size_t)(kBuckets + 2) * sizeof(uint16_t) : 0) + 16;
 }
 
@@ -807,14 +814,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* s_tab = reinterpret_cast<uint64_t*>(smem_raw);
   int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw + (size_t)kTabCap * sizeof(uint64_t));
-  RegRec* s_regs = reinterpret_cast<RegRec*>(s_ws + (size_t)kWarpsPerCta * Ws<1>::elems(CAP, kRegCap));
+  using HotWs = Ws<1, (CAP > 64)>;
+  RegRec* s_regs = reinterpret_cast<RegRec*>(s_ws + (size_t)kWarpsPerCta * HotWs::elems(CAP, kRegCap));
   uint16_t* s_bkt = reinterpret_cast<uint16_t*>(s_regs + kWarpsPerCta);
   __shared__ long long s_item;
   __shared__ int s_next;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kWarpsPerCta + warp;
-  Ws<1> ws{s_ws + (size_t)warp * Ws<1>::elems(CAP, kRegCap), Ws<1>::pack(CAP, kRegCap)};
+  HotWs ws{s_ws + (size_t)warp * HotWs::elems(CAP, kRegCap), HotWs::pack(CAP, kRegCap)};
   RadixScratch* rsx = D.rsx_scratch + gwarp;
   ChainCounters ctr{0, 0, 0, 0};
   for (;;) {
@@ -873,7 +881,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_CHAIN_MINB) k_chain_war
 // Phase A, cold kernel: the pairs the hot kernel queued, one warp per pair, the complete code
 // (mm_seed_select, the radix-pass emulation, the general chain tail), tables read from HBM.
 template <int CAP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, LGR_COLD_MINB) k_chain_cold(const __grid_constant__ Dev D) {
+__global__ void LGR_COLD_BOUNDS k_chain_cold(const __grid_constant__ Dev D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_ws = reinterpret_cast<int32_t*>(smem_raw);
   RegRec* s_regs = reinterpret_cast<RegRec*>(s_ws + (size_t)kWarpsPerCta * Ws<1>::elems(CAP, kRegCap));
