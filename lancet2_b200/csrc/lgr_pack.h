@@ -106,61 +106,74 @@ inline void planes32_scalar(const std::uint8_t* s, int n, std::uint32_t* lo, std
 }
 
 // count the bases of s[0..len) that need an exception entry
-inline std::int64_t count_exceptions(const std::uint8_t* s, int len) {
+#if LGR_PACK_X86
+// (whole-sequence routines carry the target attribute themselves, so that the 32-byte helpers inline into their
+// loops: as separate calls per chunk the helpers were a third of the packing time)
+__attribute__((target("avx2"))) inline std::int64_t count_exceptions_avx2(const std::uint8_t* s, int len) {
   std::int64_t n = 0;
   int i = 0;
-#if LGR_PACK_X86
-  if (have_avx2()) {
-    for (; i + 32 <= len; i += 32) n += 32 - __builtin_popcount(valid32_avx2(s + i));
-    if (i < len) {
-      alignas(32) std::uint8_t pad[32];
-      std::memset(pad, 'A', sizeof(pad));
-      std::memcpy(pad, s + i, (std::size_t)(len - i));
-      n += 32 - __builtin_popcount(valid32_avx2(pad));
-      i = len;
-    }
+  for (; i + 32 <= len; i += 32) n += 32 - __builtin_popcount(valid32_avx2(s + i));
+  if (i < len) {
+    // the partial last chunk: the LAST 32 bytes of the string, of which the top len - i bits are new
+    // (no padded copy, and nothing is read beyond the caller's string); len >= 32 is the caller's check
+    const std::uint32_t ok = valid32_avx2(s + len - 32) >> (32 - (len - i));
+    n += (len - i) - __builtin_popcount(ok);
   }
+  return n;
+}
 #endif
-  for (; i < len; ++i) n += !is_acgt(s[i]);
+inline std::int64_t count_exceptions(const std::uint8_t* s, int len) {
+#if LGR_PACK_X86
+  if (len >= 32 && have_avx2()) return count_exceptions_avx2(s, len);
+#endif
+  std::int64_t n = 0;
+  for (int i = 0; i < len; ++i) n += !is_acgt(s[i]);
   return n;
 }
 
 // bases of one sequence → planes (2 words per chunk) + exception entries (pos = base + index)
-inline void pack_bases(const std::uint8_t* s, int len, std::uint32_t* planes, std::uint32_t pos_base, std::uint32_t* exc_pos,
-                       std::uint8_t* exc_code, std::int64_t* n_exc) {
+inline void emit_chunk(const std::uint8_t* s, int off, int n, std::uint32_t lo, std::uint32_t hi, std::uint32_t ok, std::uint32_t* planes,
+                       int c, std::uint32_t pos_base, std::uint32_t* exc_pos, std::uint8_t* exc_code, std::int64_t* n_exc) {
+  const std::uint32_t full = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+  std::uint32_t bad = ~ok & full;
+  lo &= ok, hi &= ok;  // exception positions carry 0 bits: the record is a pure function of the payload
+  planes[2 * c] = lo, planes[2 * c + 1] = hi;
+  while (bad) {
+    const int b = __builtin_ctz(bad);
+    bad &= bad - 1;
+    exc_pos[*n_exc] = pos_base + (std::uint32_t)(off + b);
+    exc_code[*n_exc] = code_of(s[off + b]);
+    ++*n_exc;
+  }
+}
+#if LGR_PACK_X86
+__attribute__((target("avx2"))) inline void pack_bases_avx2(const std::uint8_t* s, int len, std::uint32_t* planes, std::uint32_t pos_base,
+                                                            std::uint32_t* exc_pos, std::uint8_t* exc_code, std::int64_t* n_exc) {
   const int nc = chunks_of(len);
   for (int c = 0; c < nc; ++c) {
     const int off = c << 5, n = len - off < 32 ? len - off : 32;
-    std::uint32_t lo, hi, ok;
-#if LGR_PACK_X86
-    if (have_avx2()) {
-      // the last, partial chunk goes through a padded copy: never read past the caller's string
-      alignas(32) std::uint8_t pad[32];
-      const std::uint8_t* src = s + off;
-      if (n < 32) {
-        std::memset(pad, 0, sizeof(pad));
-        std::memcpy(pad, s + off, (std::size_t)n);
-        src = pad;
-      }
-      planes32_avx2(src, &lo, &hi);
-      ok = valid32_avx2(src);
-    } else
+    // the last, partial chunk is read as the LAST 32 bytes of the string and shifted down: never a read past
+    // the caller's string, and no padded copy (len >= 32 is the caller's check)
+    const std::uint8_t* src = n == 32 ? s + off : s + len - 32;
+    std::uint32_t lo, hi;
+    planes32_avx2(src, &lo, &hi);
+    std::uint32_t ok = valid32_avx2(src);
+    if (n < 32) lo >>= 32 - n, hi >>= 32 - n, ok >>= 32 - n;
+    emit_chunk(s, off, n, lo, hi, ok, planes, c, pos_base, exc_pos, exc_code, n_exc);
+  }
+}
 #endif
-    {
-      planes32_scalar(s + off, n, &lo, &hi);
-      ok = valid32_scalar(s + off, n);
-    }
-    const std::uint32_t full = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
-    std::uint32_t bad = ~ok & full;
-    lo &= ok, hi &= ok;  // exception positions carry 0 bits: the record is a pure function of the payload
-    planes[2 * c] = lo, planes[2 * c + 1] = hi;
-    while (bad) {
-      const int b = __builtin_ctz(bad);
-      bad &= bad - 1;
-      exc_pos[*n_exc] = pos_base + (std::uint32_t)(off + b);
-      exc_code[*n_exc] = code_of(s[off + b]);
-      ++*n_exc;
-    }
+inline void pack_bases(const std::uint8_t* s, int len, std::uint32_t* planes, std::uint32_t pos_base, std::uint32_t* exc_pos,
+                       std::uint8_t* exc_code, std::int64_t* n_exc) {
+#if LGR_PACK_X86
+  if (len >= 32 && have_avx2()) return pack_bases_avx2(s, len, planes, pos_base, exc_pos, exc_code, n_exc);
+#endif
+  const int nc = chunks_of(len);
+  for (int c = 0; c < nc; ++c) {
+    const int off = c << 5, n = len - off < 32 ? len - off : 32;
+    std::uint32_t lo, hi;
+    planes32_scalar(s + off, n, &lo, &hi);
+    emit_chunk(s, off, n, lo, hi, valid32_scalar(s + off, n), planes, c, pos_base, exc_pos, exc_code, n_exc);
   }
 }
 
@@ -183,26 +196,36 @@ inline int build_qual_lut(const lgr_group_desc* g, std::uint8_t* lut) {
 }
 
 // does every quality byte of the group lie in lut[0..n_lut)? (n_lut <= 4)
+#if LGR_PACK_X86
+__attribute__((target("avx2"))) inline bool quals_fit_avx2(const std::uint8_t* q, int n, const std::uint8_t* lut, int n_lut) {
+  std::uint32_t lo, hi;
+  int i = 0;
+  for (; i + 32 <= n; i += 32)
+    if (qual32_avx2(q + i, lut, n_lut, &lo, &hi) != 0xffffffffu) return false;
+  // the last 32 bytes cover the partial chunk (bytes seen twice do not matter here); n >= 32 is the caller's check
+  return i == n || qual32_avx2(q + n - 32, lut, n_lut, &lo, &hi) == 0xffffffffu;
+}
+// 2-bit quality planes of one read (n >= 32): two words per chunk, index 0 beyond the end
+__attribute__((target("avx2"))) inline void pack_quals2_avx2(const std::uint8_t* q, int n, const std::uint8_t* lut, std::uint32_t* w) {
+  const int nc = chunks_of(n);
+  for (int c = 0; c < nc; ++c) {
+    const int off = c << 5, m = n - off < 32 ? n - off : 32;
+    (void)qual32_avx2(m == 32 ? q + off : q + n - 32, lut, 4, &w[2 * c], &w[2 * c + 1]);
+    if (m < 32) w[2 * c] >>= 32 - m, w[2 * c + 1] >>= 32 - m;
+  }
+}
+#endif
 inline bool quals_fit(const lgr_group_desc* g, const std::uint8_t* lut, int n_lut) {
   for (int r = 0; r < g->n_reads; ++r) {
     const std::uint8_t* q = g->read_qual[r];
     const int n = g->read_len[r];
-    int i = 0;
 #if LGR_PACK_X86
-    if (have_avx2()) {
-      std::uint32_t lo, hi;
-      for (; i + 32 <= n; i += 32)
-        if (qual32_avx2(q + i, lut, n_lut, &lo, &hi) != 0xffffffffu) return false;
-      if (i < n) {
-        alignas(32) std::uint8_t pad[32];
-        std::memset(pad, lut[0], sizeof(pad));
-        std::memcpy(pad, q + i, (std::size_t)(n - i));
-        if (qual32_avx2(pad, lut, n_lut, &lo, &hi) != 0xffffffffu) return false;
-        i = n;
-      }
+    if (n >= 32 && have_avx2()) {
+      if (!quals_fit_avx2(q, n, lut, n_lut)) return false;
+      continue;
     }
 #endif
-    for (; i < n; ++i) {
+    for (int i = 0; i < n; ++i) {
       bool ok = false;
       for (int k = 0; k < n_lut; ++k) ok |= q[i] == lut[k];
       if (!ok) return false;
@@ -316,24 +339,17 @@ inline int pack_group(const lgr_group_desc* g, const Plan& p, void* dst, lgr_gro
       if (l) std::memcpy(qraw + pos, q, (std::size_t)l);
     } else {
       const int nc = chunks_of(l);
+#if LGR_PACK_X86
+      if (p.qual_bits == 2 && l >= 32 && have_avx2()) {
+        pack_quals2_avx2(q, l, p.lut, qplanes + (std::size_t)chunk * 2);
+        pos += (std::uint32_t)l, chunk += nc;
+        continue;
+      }
+#endif
       for (int c = 0; c < nc; ++c) {
         const int off = c << 5, n = l - off < 32 ? l - off : 32;
         std::uint32_t* w = qplanes + (std::size_t)(chunk + c) * (std::size_t)p.qual_bits;
         if (p.qual_bits == 2) {
-#if LGR_PACK_X86
-          if (have_avx2()) {
-            alignas(32) std::uint8_t pad[32];
-            const std::uint8_t* src = q + off;
-            if (n < 32) {
-              std::memset(pad, p.lut[0], sizeof(pad));  // index 0 beyond the end
-              std::memcpy(pad, q + off, (std::size_t)n);
-              src = pad;
-            }
-            (void)qual32_avx2(src, p.lut, 4, &w[0], &w[1]);
-            if (n < 32) w[0] &= (1u << n) - 1u, w[1] &= (1u << n) - 1u;
-            continue;
-          }
-#endif
           std::uint32_t lo = 0, hi = 0;
           for (int i = 0; i < n; ++i) {
             const std::uint8_t v = q[off + i];

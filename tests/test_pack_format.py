@@ -174,3 +174,20 @@ def test_empty_batch_and_empty_group(lib):
     assert pb.n_groups == 0
     g = abi.Group(haps=[b"ACGTACGT"], reads=[], quals=[], names=[], variants=[])
     check_round_trip([g], lib)
+
+
+def test_every_tail_length_with_short_dictionary(lib):
+    """Partial last chunks are read as the last 32 bytes of the string and shifted down (no padded copy): every
+    length 1..100, three Phred values (2-bit planes), a non-ACGT base in the very last position of every other read."""
+    rng = np.random.default_rng(11)
+    vals = np.asarray([2, 23, 37], dtype=np.uint8)
+    reads, quals = [], []
+    for ln in range(1, 101):
+        r = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=ln)
+        if ln % 2:
+            r[-1] = ord("N")
+        reads.append(r.tobytes())
+        quals.append(vals[rng.integers(0, 3, size=ln)].tobytes())
+    g = abi.Group(haps=[b"ACGTTGCA" * 9 + b"n"], reads=reads, quals=quals, names=[f"t{i}" for i in range(100)], variants=[])
+    _, dec = check_round_trip([g, g], lib)
+    assert dec[0]["qual_bits"] == 2 and dec[0]["n_exc"] == 51
