@@ -449,6 +449,21 @@ std::int32_t* ThreadLatch(std::uint64_t uid) {
 }
 }  // namespace
 
+// per calling thread: device context + pinned staging of the blocking Genotype() path (GenotypeDirect below)
+struct GenotypeBatcher::DirectSlot {
+  lgr_ctx* ctx = nullptr;
+  std::uint8_t* slab = nullptr;
+  std::size_t slab_cap = 0;
+  lgr_assign* assign = nullptr;  // pinned [assign_cap + 1] followed by one int32 status
+  std::size_t assign_cap = 0;
+  PackScratch sc;
+  ~DirectSlot() {
+    if (ctx) lgr_destroy(ctx);
+    if (slab) lgr_free_pinned(slab);
+    if (assign) lgr_free_pinned(assign);
+  }
+};
+
 // results of one device batch: lives until the last of its payloads has been collected, while the
 // staging slab it came from goes back to the pool as soon as the device is done with it (a worker may
 // enqueue many windows before it collects the first)
@@ -497,6 +512,7 @@ GenotypeBatcher::GenotypeBatcher(const Options& opt, NameHashFn name_hash) : mOp
   mOpt.min_pairs_busy = env_int("LGR_BATCHER_MIN_PAIRS", mOpt.min_pairs_busy);
   mOpt.max_wait_us = static_cast<int>(env_int("LGR_BATCHER_MAX_WAIT_US", mOpt.max_wait_us));
   mOpt.linger_us = static_cast<int>(env_int("LGR_BATCHER_LINGER_US", mOpt.linger_us));
+  mOpt.direct_blocking_callers = static_cast<int>(env_int("LGR_BATCHER_DIRECT", mOpt.direct_blocking_callers));
   if (mOpt.depth < 1) mOpt.depth = 1;
   if (mOpt.depth > LGR_MAX_INFLIGHT) mOpt.depth = LGR_MAX_INFLIGHT;
   if (mOpt.max_jobs < 1) mOpt.max_jobs = 1;
@@ -846,9 +862,88 @@ Result GenotypeBatcher::Collect(Ticket& ticket) {
   return res;
 }
 
+// The blocking call shape on a context of its own.  A caller that blocks keeps one window in flight, so there is
+// nothing for the batcher to coalesce with unless other threads happen to arrive inside the linger; what the detour
+// through the batcher thread did cost was four thread hand-offs per call (worker -> batcher -> CUDA callback ->
+// batcher -> worker).  Here the calling thread packs into its own pinned slab and runs lgr_genotype_packed on its
+// own lgr_ctx (the reference's model: one Genotyper per worker thread); concurrent callers overlap on the GPU
+// through their streams.  An idle context holds < 64 MiB of device memory (tests/test_gpu_packed.py).
+
+GenotypeBatcher::DirectSlot* GenotypeBatcher::DirectFor() {
+  thread_local std::unordered_map<std::uint64_t, DirectSlot*> mine;  // per batcher instance
+  DirectSlot*& slot = mine[mUid];
+  if (!slot) {
+    auto s = std::make_unique<DirectSlot>();
+    Check(nullptr, lgr_create(mOpt.device, &mParams, &s->ctx));
+    std::lock_guard<std::mutex> lk(mDirectMu);
+    slot = s.get();
+    mDirect.push_back(std::move(s));
+  }
+  return slot;
+}
+
+Result GenotypeBatcher::GenotypeDirect(const GenotypeJob& job) {
+  const std::uint64_t t0 = NowNs();
+  DirectSlot* ds = DirectFor();
+  lgr_group_desc desc;
+  DescribeJob(job, ds->sc, &desc);
+  const lgr_pack::Plan plan = lgr_pack::plan_group(&desc, ds->sc.have_plan ? &ds->sc.last_plan : nullptr);
+  if (plan.rc != LGR_OK) throw std::runtime_error(std::string("lancet_gpu::GenotypeBatcher: ") + lgr_strerror(plan.rc) + " (this payload only)");
+  if (lgr_check_limits(&mParams, plan.max_hap_len, plan.max_read_len) != LGR_OK)
+    throw std::runtime_error("lancet_gpu::GenotypeBatcher: payload beyond the device path's static caps (this payload only)");
+  ds->sc.last_plan = plan, ds->sc.have_plan = true;
+  desc.mid_occ = LatchFor(job);
+  const std::size_t need = plan.bytes + sizeof(lgr_group_dir) + 64;
+  if (need > ds->slab_cap) {
+    if (ds->slab) lgr_free_pinned(ds->slab);
+    ds->slab = nullptr, ds->slab_cap = 0;
+    ds->slab = static_cast<std::uint8_t*>(PinnedOrThrow(need + need / 2));
+    ds->slab_cap = need + need / 2;
+  }
+  const std::size_t n_asg = job.n_reads * job.n_variants;
+  if (!ds->assign || n_asg + 1 > ds->assign_cap) {
+    if (ds->assign) lgr_free_pinned(ds->assign);
+    ds->assign = nullptr, ds->assign_cap = 0;
+    const std::size_t want = n_asg + n_asg / 2 + 4096;
+    ds->assign = static_cast<lgr_assign*>(PinnedOrThrow(want * sizeof(lgr_assign) + sizeof(std::int32_t)));
+    ds->assign_cap = want;
+  }
+  lgr_group_dir* dir = reinterpret_cast<lgr_group_dir*>(ds->slab + ((plan.bytes + 15) & ~static_cast<std::size_t>(15)));
+  if (lgr_pack::pack_group(&desc, plan, ds->slab, dir) != LGR_OK) throw std::runtime_error("lancet_gpu::GenotypeBatcher: packing failed");
+  dir->rec_off = 0;
+  lgr_packed_in in{};
+  in.n_groups = 1, in.slab = ds->slab, in.dir = dir;
+  in.slab_bytes = static_cast<std::size_t>(reinterpret_cast<std::uint8_t*>(dir + 1) - ds->slab);
+  lgr_batch_out out{};
+  out.n_assign = static_cast<std::int64_t>(n_asg), out.assign = ds->assign;
+  out.grp_status = reinterpret_cast<std::int32_t*>(ds->assign + ds->assign_cap);
+  const std::uint64_t t1 = NowNs();
+  Check(ds->ctx, lgr_genotype_packed(ds->ctx, &in, &out, nullptr));  // throws for this payload only
+  const std::uint64_t t2 = NowNs();
+  Result res = PackedBatch::BuildResult(job, ds->assign, mNameHash);
+  const std::uint64_t t3 = NowNs();
+  std::lock_guard<std::mutex> lk(mMu);
+  mCounters.ns_pack += t1 - t0, mCounters.ns_submit += t2 - t1, mCounters.ns_deliver += t3 - t2;
+  mCounters.batches += 1, mCounters.jobs += 1, mCounters.pairs += static_cast<std::uint64_t>(job.n_reads * job.n_haps);
+  mCounters.h2d_bytes += in.slab_bytes, mCounters.d2h_bytes += n_asg * sizeof(lgr_assign);
+  if (mCounters.max_jobs_in_batch < 1) mCounters.max_jobs_in_batch = 1;
+  return res;
+}
+
 Result GenotypeBatcher::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
                                  const VariantIn* variants, std::size_t n_variants) {
-  Ticket t = Enqueue(GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants});
+  return Genotype(GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants});
+}
+
+Result GenotypeBatcher::Genotype(const GenotypeJob& job) {
+  struct Inside {
+    std::atomic<int>& n;
+    int mine;
+    explicit Inside(std::atomic<int>& c) : n(c), mine(c.fetch_add(1, std::memory_order_relaxed) + 1) {}
+    ~Inside() { n.fetch_sub(1, std::memory_order_relaxed); }
+  } inside{mBlockingCallers};
+  if (inside.mine <= mOpt.direct_blocking_callers) return GenotypeDirect(job);
+  Ticket t = Enqueue(job);
   return Collect(t);
 }
 
@@ -912,8 +1007,21 @@ Result GenotypeDispatcher::Collect(Ticket& ticket) {
 
 Result GenotypeDispatcher::Genotype(const std::string* haps, std::size_t n_haps, const ReadIn* reads, std::size_t n_reads,
                                     const VariantIn* variants, std::size_t n_variants) {
-  Ticket t = Enqueue(GenotypeJob{haps, n_haps, reads, n_reads, variants, n_variants});
-  return Collect(t);
+  GenotypeJob job{haps, n_haps, reads, n_reads, variants, n_variants};
+  job.mid_occ_latch = ThreadLatch(mUid);
+  std::size_t best = 0;
+  std::int64_t best_load = mOutstanding[0].load(std::memory_order_relaxed);
+  for (std::size_t i = 1; i < mBatchers.size(); ++i) {
+    const std::int64_t load = mOutstanding[i].load(std::memory_order_relaxed);
+    if (load < best_load) best = i, best_load = load;
+  }
+  struct Load {
+    std::atomic<std::int64_t>& load;
+    std::int64_t cost;
+    Load(std::atomic<std::int64_t>& l, std::int64_t c) : load(l), cost(c) { load.fetch_add(cost, std::memory_order_relaxed); }
+    ~Load() { load.fetch_sub(cost, std::memory_order_relaxed); }
+  } held{mOutstanding[best], Cost(job)};
+  return mBatchers[best]->Genotype(job);  // blocking: the batcher runs it on the calling thread's own context
 }
 
 }  // namespace lancet_gpu
