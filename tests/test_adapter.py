@@ -178,13 +178,26 @@ def test_cross_thread_batcher_equals_synchronous_adapter(lib):
     buf2 = C.create_string_buffer(64 << 20)
     counters = np.zeros(17, dtype=np.uint64)
     rounds = 3
-    n2 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 8, rounds, 1, 1, counters.ctypes.data,
-                                      buf2, len(buf2))
+    # (i) every blocking caller through the batcher thread (LGR_BATCHER_DIRECT=0): the calls must be coalesced
+    os.environ["LGR_BATCHER_DIRECT"] = "0"
+    try:
+        n2 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 8, rounds, 1, 1, counters.ctypes.data,
+                                          buf2, len(buf2))
+    finally:
+        del os.environ["LGR_BATCHER_DIRECT"]
     assert n2 > 0, buf2.value.decode()
     assert buf2.value == buf1.value
     batches, jobs, pairs, max_jobs = (int(x) for x in counters[:4])
     assert jobs == rounds * len(groups) and pairs == rounds * batch.n_pairs
     assert batches < jobs and max_jobs > 1, (batches, jobs, max_jobs)  # calls were coalesced
+    # (ii) the default: up to eight blocking callers run on a device context of their own, the rest are coalesced —
+    # with 12 threads both paths are in use, and the evidence is the same
+    buf2b = C.create_string_buffer(64 << 20)
+    n2b = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 12, rounds, 1, 1, counters.ctypes.data,
+                                       buf2b, len(buf2b))
+    assert n2b > 0, buf2b.value.decode()
+    assert buf2b.value == buf1.value
+    assert int(counters[1]) == rounds * len(groups) and int(counters[2]) == rounds * batch.n_pairs
     # Enqueue/Collect: two workers with 16 groups in flight each — same evidence, fewer device batches
     buf3 = C.create_string_buffer(64 << 20)
     n3 = lib.lgr_adapter_batcher_dump(0, C.byref(bi), nm_blob, b"normal\0tumor\0", *args, 2, rounds, 16, 1, counters.ctypes.data,
