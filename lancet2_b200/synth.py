@@ -277,8 +277,9 @@ def _tile_job(args):
     return make_tile_groups(*args)
 
 
-def make_tiled_groups(name: str, seed: int, tiles: Sequence[int], ref_len: int = 1_000_000, procs: int = 1) -> List[Group]:
-    """the groups of the given tiles, in tile order; `procs` > 1 generates tiles in worker processes"""
+def make_tiled_groups(name: str, seed: int, tiles: Sequence[int], ref_len: int = 1_000_000, procs: int = 1, per_tile: bool = False):
+    """the groups of the given tiles, in tile order (per_tile: one list per tile); `procs` > 1 generates tiles in
+    worker processes"""
     jobs = [(name, seed, int(t), ref_len) for t in tiles]
     if procs > 1 and len(jobs) > 1:
         import multiprocessing as mp
@@ -286,4 +287,4 @@ def make_tiled_groups(name: str, seed: int, tiles: Sequence[int], ref_len: int =
             parts = pool.map(_tile_job, jobs, chunksize=1)
     else:
         parts = [_tile_job(j) for j in jobs]
-    return [g for part in parts for g in part]
+    return parts if per_tile else [g for part in parts for g in part]

@@ -126,3 +126,31 @@ def test_two_rank_sharding_of_supports():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok and min(sizes) >= 1 and sum(sizes) == 61
+
+
+def test_split_partition_is_exact_and_covers_every_group():
+    """dispatch.partition_units_split (bench.py's strong-scaling shards at N > 1): every rank carries total / world of
+    the cost, every unit's fractions tile [0, 1) without gap or overlap — also after rounding to a unit's groups —
+    and a rank touches at most two partial units."""
+    from lancet2_b200.dispatch import partition_units_split
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 4, 7, 8):
+        for costs in ([10] * 50, rng.integers(1, 1000, 50).tolist(), [5], [3, 0, 9, 1]):
+            shards = partition_units_split(costs, world)
+            total = sum(costs)
+            for s in shards:
+                load = sum(costs[t] * (hi - lo) for t, lo, hi in s)
+                assert abs(load - total / world) <= 1e-6 * total
+                assert sum(1 for _, lo, hi in s if lo > 0 or hi < 1) <= 2
+                assert [t for t, _, _ in s] == sorted(t for t, _, _ in s)
+            for t, c in enumerate(costs):
+                parts = sorted((lo, hi) for s in shards for tt, lo, hi in s if tt == t)
+                if c == 0:
+                    assert not parts
+                    continue
+                assert parts[0][0] == 0 and abs(parts[-1][1] - 1) < 1e-12
+                n_groups = 237  # what bench.py does with a tile's groups
+                taken = []
+                for lo, hi in parts:
+                    taken += list(range(int(round(lo * n_groups)), int(round(hi * n_groups))))
+                assert taken == list(range(n_groups))
