@@ -497,7 +497,9 @@ typedef struct lgr_rep_ctx lgr_rep_ctx;
 int lgr_repeat_create(int device_ordinal, lgr_rep_ctx** out);
 void lgr_repeat_destroy(lgr_rep_ctx* ctx);
 const char* lgr_repeat_last_error(const lgr_rep_ctx* ctx);
-/* H2D of the sequences and jobs, k_repeat_scan, D2H of one byte per job (0 / 1 / LGR_REPEAT_TOO_LONG);
+/* H2D of the sequences and jobs, k_repeat_scan, D2H of one byte per job (0 / 1 / LGR_REPEAT_TOO_LONG).  Consecutive
+ * jobs with the same seq_off, seq_len and max_mismatches (a window's k-loop) are answered together from shared mismatch
+ * masks — keep them adjacent in `jobs`;
  * ms_kernels (may be NULL) = CUDA-event time of the kernel. */
 int lgr_repeat_scan(lgr_rep_ctx* ctx, const uint8_t* seqs, int64_t seq_bytes, const lgr_repeat_job* jobs, int32_t n_jobs,
                     uint8_t* has_repeat, float* ms_kernels);
