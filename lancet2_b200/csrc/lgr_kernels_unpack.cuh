@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack_decode(const __grid_c
     const uint32_t* planes = reinterpret_cast<const uint32_t*>(D.slab + (pd & ~kSeqHasExc));
     uint8_t* codes = (is_read ? D.read_codes : D.hap_codes) + o;
     for (int c = 0; (c << 5) < l; ++c) {
-      const uint32_t lo = planes[2 * c], hi = planes[2 * c + 1];
+      const uint2 w = *reinterpret_cast<const uint2*>(planes + 2 * c);  // (low-bit plane, high-bit plane), 8-byte aligned
       const int b = (c << 5) + lane;
-      if (b < l) codes[b] = (uint8_t)(((lo >> lane & 1u) | (hi >> lane & 1u) << 1) * 0x11u);
+      if (b < l) codes[b] = (uint8_t)(((w.x >> lane & 1u) | (w.y >> lane & 1u) << 1) * 0x11u);
     }
     if (is_read) {
       const int qbits = (int)(qd >> 56);
@@ -215,12 +215,25 @@ __global__ void __launch_bounds__(kUnpackThreads) k_unpack_decode(const __grid_c
         const uint32_t lutw = D.grp_lut[4 * (size_t)g + (lane >> 2 & 3)];
         const uint32_t lut_lo = lutw >> (8 * (lane & 3)) & 0xffu;  // dictionary entry `lane` (< 16) lives in lane `lane`
         const uint32_t* qplanes = reinterpret_cast<const uint32_t*>(qsrc);
-        for (int c = 0; (c << 5) < l; ++c) {
-          uint32_t k = 0;
-          for (int p = 0; p < qbits; ++p) k |= (qplanes[c * qbits + p] >> lane & 1u) << p;
-          const uint32_t v = __shfl_sync(full, lut_lo, (int)k);
-          const int b = (c << 5) + lane;
-          if (b < l) quals[b] = (uint8_t)v;
+        // (the two plane counts spelled out: as one loop over a run-time plane count this line was half of the
+        // kernel's instructions)
+        if (qbits == 2) {
+          for (int c = 0; (c << 5) < l; ++c) {
+            const uint2 w = *reinterpret_cast<const uint2*>(qplanes + 2 * c);  // plane words are 8-byte aligned in the record
+            const uint32_t k = (w.x >> lane & 1u) | (w.y >> lane & 1u) << 1;
+            const uint32_t v = __shfl_sync(full, lut_lo, (int)k);
+            const int b = (c << 5) + lane;
+            if (b < l) quals[b] = (uint8_t)v;
+          }
+        } else {
+          for (int c = 0; (c << 5) < l; ++c) {
+            const uint2 w0 = *reinterpret_cast<const uint2*>(qplanes + 4 * c);  // 8-byte, not 16-byte, alignment is guaranteed
+            const uint2 w1 = *reinterpret_cast<const uint2*>(qplanes + 4 * c + 2);
+            const uint32_t k = (w0.x >> lane & 1u) | (w0.y >> lane & 1u) << 1 | (w1.x >> lane & 1u) << 2 | (w1.y >> lane & 1u) << 3;
+            const uint32_t v = __shfl_sync(full, lut_lo, (int)k);
+            const int b = (c << 5) + lane;
+            if (b < l) quals[b] = (uint8_t)v;
+          }
         }
       }
     }
